@@ -1,0 +1,166 @@
+/*
+ * msg_b200.h — C-ABI of the B200-native Multi-StyleGAN training-step hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream; none allocates,
+ * none synchronises, none touches a torch type.  All functions return MSG_OK (0) or a
+ * negative-free error code below; msg_last_error() gives the thread-local reason string.
+ * All tensors are dense row-major ("contiguous") unless stated otherwise.
+ *
+ * Each declaration cites the reference interface (file:line under
+ * ChristophReich1996/Multi-StyleGAN) whose arithmetic it replaces.
+ */
+#ifndef MSG_B200_H_
+#define MSG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSG_B200_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------- */
+enum {
+  MSG_OK = 0,
+  MSG_ERR_BAD_ARG = 1,      /* null pointer, negative size, inconsistent shapes            */
+  MSG_ERR_UNSUPPORTED = 2,  /* configuration outside what the kernels implement            */
+  MSG_ERR_CUDA = 3,         /* a CUDA runtime / driver call or a kernel launch failed      */
+  MSG_ERR_WORKSPACE = 4     /* caller-provided workspace too small                         */
+};
+
+/* ---- element types accepted by the bandwidth-bound ops ------------------------------------ */
+enum { MSG_F32 = 0, MSG_F64 = 1 };
+
+/* opaque cudaStream_t */
+typedef void* msg_stream_t;
+
+int msg_abi_version(void);
+/* thread-local, valid until the next failing call on the same thread */
+const char* msg_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t msg_launch_count(void);
+/* 1 when the tcgen05/TMA implicit-GEMM path is usable on the current device (sm_100) */
+int msg_tensor_core_path_available(void);
+
+/* -------------------------------------------------------------------------------------------
+ * fused_bias_act  — replaces fused_act_cuda.fused_bias_act
+ *   multi_stylegan/op_static/fused_bias_act.cpp:11-20, fused_bias_act_kernel.cu:18-99
+ *   out[i] = act(x[i] + bias[(i / step_b) % size_b], ref[i]) * scale
+ *     act*10+grad: 10,11 -> y=x; 12 -> 0; 30 -> x>0?x:alpha*x; 31 -> ref>0?x:alpha*x; 32 -> 0
+ *   bias == NULL / ref == NULL mean "absent" (reference: numel()==0, kernel.cu:62-63).
+ *   64-bit indexing (the reference's int32 index overflows at 2^31 elements, kernel.cu:21).
+ * ------------------------------------------------------------------------------------------- */
+int msg_fused_bias_act(void* out, const void* x, const void* bias, const void* ref,
+                       int act, int grad, double alpha, double scale,
+                       int64_t size_x, int64_t step_b, int64_t size_b,
+                       int dtype, msg_stream_t stream);
+
+/* Backward of the above fused with the bias-gradient reduction that the reference performs as
+ * a separate ATen sum (op_static/fused_act.py:31-40):
+ *   dx[i] = (ref[i] > 0 ? g[i] : alpha*g[i]) * scale ;  dbias[c] = sum_{i in channel c} dx[i]
+ * x is viewed as [outer, size_b, step_b].  workspace: msg_fused_bias_act_bwd_workspace() bytes.
+ * Deterministic (two-stage reduction, no atomics). */
+size_t msg_fused_bias_act_bwd_workspace(int64_t size_x, int64_t step_b, int64_t size_b, int dtype);
+int msg_fused_bias_act_bwd(void* dx, void* dbias, const void* g, const void* ref,
+                           double alpha, double scale,
+                           int64_t size_x, int64_t step_b, int64_t size_b,
+                           void* workspace, size_t workspace_bytes,
+                           int dtype, msg_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * upfirdn2d — replaces upfirdn2d_cuda.upfirdn2d
+ *   multi_stylegan/op_static/upfirdn2d.cpp:12-22, upfirdn2d_kernel.cu:52-272
+ *   in  [major, in_h, in_w, minor], kernel [kernel_h, kernel_w] (applied flipped: true convolution,
+ *   kernel.cu:77), out [major, out_h, out_w, minor] with
+ *   out_h = (in_h*up_y + pad_y0 + pad_y1 - kernel_h + down_y) / down_y   (kernel.cu:167-168)
+ *   Negative pads crop.  Every (up, down, pad, kernel<=32x32) combination is implemented; the
+ *   reference launches nothing (returns uninitialised memory) outside its six modes.
+ * ------------------------------------------------------------------------------------------- */
+int msg_upfirdn2d_out_size(int in_size, int up, int down, int pad0, int pad1, int ksize);
+int msg_upfirdn2d(void* out, const void* in, const void* kernel,
+                  int64_t major, int in_h, int in_w, int minor,
+                  int kernel_h, int kernel_w,
+                  int up_x, int up_y, int down_x, int down_y,
+                  int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                  int dtype, msg_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Dense / per-sample ("grouped by batch") 2-D convolution primitives, fp32 storage, TF32 tensor
+ * cores (tcgen05) with fp32 accumulation for the shapes the implicit-GEMM kernels tile, an fp32
+ * CUDA-core kernel for the rest.  Replaces the ATen/cuDNN calls at
+ *   multi_stylegan/multi_stylegan_generator.py:398 (conv_transpose2d, groups=B),
+ *   multi_stylegan/multi_stylegan_generator.py:409 (conv2d, groups=B),
+ *   multi_stylegan/equalized_layer.py:70-73        (conv2d)
+ * and their autograd-generated dgrad / wgrad.
+ *
+ *   x  [B, C, H, W]            w  [O, C, kh, kw]        (w_batch_stride == 0, shared weights)
+ *   y  [B, O, OH, OW]          w  [B, O, C, kh, kw]     (w_batch_stride == O*C*kh*kw)
+ *   OH = (H + 2*pad_h - kh) / stride_h + 1
+ *
+ * forward : y  = conv(x, w)
+ * dgrad   : dx = conv^T(dy, w)     (also the forward of conv_transpose2d)
+ * wgrad   : dw = sum_{b,p} dy (x) x   (per sample when dw_batch_stride != 0)
+ * `alpha` scales the result (used to fold the equalised-lr constant); `flags` selects the engine.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int B, C, H, W;          /* input activation                                   */
+  int O, kh, kw;           /* filter                                             */
+  int stride_h, stride_w;
+  int pad_h, pad_w;
+  int OH, OW;              /* output activation extent (must match the formula)  */
+  int64_t w_batch_stride;  /* 0 = shared weights, else elements between samples  */
+} msg_conv_desc;
+
+enum {
+  MSG_CONV_AUTO = 0,        /* tensor cores when the shape tiles, else CUDA cores */
+  MSG_CONV_FORCE_SIMT = 1,  /* fp32 CUDA-core kernel (exact fp32)                 */
+  MSG_CONV_FORCE_TC = 2     /* fail with MSG_ERR_UNSUPPORTED if the shape does not tile */
+};
+
+size_t msg_conv2d_workspace(const msg_conv_desc* d, int which /*0 fwd,1 dgrad,2 wgrad*/, int flags);
+int msg_conv2d_forward(float* y, const float* x, const float* w, const msg_conv_desc* d,
+                       float alpha, void* workspace, size_t workspace_bytes, int flags,
+                       msg_stream_t stream);
+int msg_conv2d_dgrad(float* dx, const float* dy, const float* w, const msg_conv_desc* d,
+                     float alpha, void* workspace, size_t workspace_bytes, int flags,
+                     msg_stream_t stream);
+int msg_conv2d_wgrad(float* dw, const float* dy, const float* x, const msg_conv_desc* d,
+                     float alpha, void* workspace, size_t workspace_bytes, int flags,
+                     msg_stream_t stream);
+/* which engine the last conv call on this thread used: 0 none, 1 simt, 2 tcgen05 */
+int msg_conv2d_last_engine(void);
+
+/* -------------------------------------------------------------------------------------------
+ * Weight modulation / demodulation — multi_stylegan/multi_stylegan_generator.py:384-388
+ *   w_mod[b,o,c,t] = scale * W[o,c,t] * s[b,c] * (demod ? rsqrt(sum_{c,t}(scale*W*s)^2 + 1e-8) : 1)
+ *   demod_out[b,o] (optional) receives the demodulation factor.
+ * ------------------------------------------------------------------------------------------- */
+int msg_modulate_weights(float* w_mod, float* demod_out, const float* W, const float* s,
+                         int B, int O, int C, int taps, float scale, int demodulate,
+                         msg_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Fused StyledConv2d epilogue — multi_stylegan_generator.py:292 (noise) + op_static/fused_act.py:58
+ *   out[b,c,p] = lrelu(x[b,c,p] + noise_w * noise[b or 0, p] + bias[c], alpha) * scale
+ * noise may be NULL (noise_w ignored); noise_batch_stride is 0 when one map is shared by the batch.
+ * ------------------------------------------------------------------------------------------- */
+int msg_noise_bias_act(float* out, const float* x, const float* noise, const float* noise_w,
+                       const float* bias, int B, int C, int64_t HW, int64_t noise_batch_stride,
+                       float alpha, float scale, msg_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * ADA geometric warp — multi_stylegan/adaptive_discriminator_augmentation.py:116-199
+ *   out[b,c,y,x] = bilinear sample of in[b,c] at (x,y,1) * theta[b]^T  in pixel coordinates,
+ *   reflection padding, align_corners=True (grid_sample semantics); theta [B,2,3] is the
+ *   composed inverse map of every stage applied to sample b (identity rows leave the sample
+ *   untouched bit-exactly).  mode 0 = reflection padding, 1 = zeros (kornia rotate).
+ * ------------------------------------------------------------------------------------------- */
+int msg_affine_warp(float* out, const float* in, const float* theta, int B, int C, int H, int W,
+                    int mode, msg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSG_B200_H_ */

@@ -1,0 +1,338 @@
+"""Raw (non-autograd) device ops: torch tensors in, torch tensors out, arithmetic in libmsg_b200.so.
+
+This is the torch-facing side of the C-ABI: it checks devices/dtypes the way the reference's pybind
+shims do (``CHECK_CUDA``, multi_stylegan/op_static/fused_bias_act.cpp:13-14), forces contiguity like
+the reference launchers (fused_bias_act_kernel.cu:58-60), allocates outputs and workspaces through
+torch's caching allocator and launches on torch's current stream.  Nothing here falls back to
+PyTorch arithmetic.
+"""
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ConvDesc
+
+import ctypes
+
+_DTYPES = {torch.float32: _lib.MSG_F32, torch.float64: _lib.MSG_F64}
+
+# engine selection for the conv primitives (tests flip this to cross-check the two engines)
+conv_flags = _lib.CONV_AUTO
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor (multi_stylegan_b200 has no CPU path)" % name)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    if t is None or t.numel() == 0:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _aligned(t: torch.Tensor) -> torch.Tensor:
+    """Contiguous and 16-byte aligned (TMA / 128-bit accesses)."""
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.contiguous_format)
+    return t
+
+
+def _dtype_code(t: torch.Tensor, what: str) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError("%s: dtype %s not supported (float32 / float64 only)" % (what, t.dtype))
+
+
+def _workspace(nbytes: int, device) -> Tuple[Optional[torch.Tensor], Optional[ctypes.c_void_p]]:
+    if nbytes <= 0:
+        return None, None
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    return ws, ctypes.c_void_p(ws.data_ptr())
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused_bias_act — same signature as the reference's fused_act_cuda.fused_bias_act
+# (multi_stylegan/op_static/fused_bias_act.cpp:11-20)
+# ---------------------------------------------------------------------------------------------------
+def fused_bias_act(input: torch.Tensor, bias: torch.Tensor, refer: torch.Tensor, act: int, grad: int,
+                   alpha: float, scale: float) -> torch.Tensor:
+    _require_cuda(input, "input")
+    _require_cuda(bias, "bias")
+    x = _aligned(input)
+    b = bias.contiguous()
+    ref = _aligned(refer) if refer.numel() else refer
+    dt = _dtype_code(x, "fused_bias_act")
+    if b.numel() and b.dtype != x.dtype:
+        raise RuntimeError("fused_bias_act: bias dtype %s != input dtype %s" % (b.dtype, x.dtype))
+    if ref.numel() and (ref.dtype != x.dtype or ref.numel() != x.numel()):
+        raise RuntimeError("fused_bias_act: refer must match input in dtype and size")
+    step_b = 1
+    for i in range(2, x.dim()):
+        step_b *= x.size(i)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().msg_fused_bias_act(_ptr(out), _ptr(x), _ptr(b), _ptr(ref), int(act), int(grad),
+                                           float(alpha), float(scale), x.numel(), step_b, b.numel(), dt,
+                                           _stream(x))
+    _lib.check(rc, "fused_bias_act")
+    return out
+
+
+def fused_bias_act_bwd(grad_output: torch.Tensor, out: torch.Tensor, alpha: float, scale: float,
+                       channels: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(grad_input, grad_bias) of lrelu(x + b) * scale in one pass over the data
+    (reference: op_static/fused_act.py:31-40 = kernel + separate ATen sum)."""
+    _require_cuda(grad_output, "grad_output")
+    _require_cuda(out, "out")
+    g = _aligned(grad_output)
+    ref = _aligned(out)
+    dt = _dtype_code(g, "fused_bias_act_bwd")
+    if ref.dtype != g.dtype or ref.shape != g.shape:
+        raise RuntimeError("fused_bias_act_bwd: out must match grad_output")
+    if g.dim() < 2 or g.size(1) != channels:
+        raise RuntimeError("fused_bias_act_bwd: dim 1 of grad_output must be the bias dimension")
+    step_b = 1
+    for i in range(2, g.dim()):
+        step_b *= g.size(i)
+    dx = torch.empty_like(g)
+    db = torch.empty(channels, dtype=g.dtype, device=g.device)
+    L = _lib.lib()
+    with torch.cuda.device(g.device):
+        nbytes = L.msg_fused_bias_act_bwd_workspace(g.numel(), step_b, channels, dt)
+        ws, wsp = _workspace(nbytes, g.device)
+        rc = L.msg_fused_bias_act_bwd(_ptr(dx), ctypes.c_void_p(db.data_ptr()), _ptr(g), _ptr(ref), float(alpha),
+                                      float(scale), g.numel(), max(step_b, 1), channels, wsp, nbytes, dt,
+                                      _stream(g))
+    _lib.check(rc, "fused_bias_act_bwd")
+    return dx, db
+
+
+# ---------------------------------------------------------------------------------------------------
+# upfirdn2d — same signature as the reference's upfirdn2d_cuda.upfirdn2d
+# (multi_stylegan/op_static/upfirdn2d.cpp:12-22); input is [major, in_h, in_w, minor]
+# ---------------------------------------------------------------------------------------------------
+def upfirdn2d(input: torch.Tensor, kernel: torch.Tensor, up_x: int, up_y: int, down_x: int, down_y: int,
+              pad_x0: int, pad_x1: int, pad_y0: int, pad_y1: int) -> torch.Tensor:
+    _require_cuda(input, "input")
+    _require_cuda(kernel, "kernel")
+    if input.dim() != 4 or kernel.dim() != 2:
+        raise RuntimeError("upfirdn2d: input must be [major, h, w, minor] and kernel [kh, kw]")
+    x = _aligned(input)
+    k = kernel.contiguous()
+    dt = _dtype_code(x, "upfirdn2d")
+    if k.dtype != x.dtype:
+        k = k.to(x.dtype)
+    major, in_h, in_w, minor = x.shape
+    kh, kw = k.shape
+    L = _lib.lib()
+    out_h = L.msg_upfirdn2d_out_size(in_h, up_y, down_y, pad_y0, pad_y1, kh)
+    out_w = L.msg_upfirdn2d_out_size(in_w, up_x, down_x, pad_x0, pad_x1, kw)
+    if out_h < 0 or out_w < 0:
+        raise RuntimeError("upfirdn2d: negative output size (%d, %d)" % (out_h, out_w))
+    out = torch.empty((major, out_h, out_w, minor), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = L.msg_upfirdn2d(_ptr(out), _ptr(x), _ptr(k), major, in_h, in_w, minor, kh, kw, up_x, up_y, down_x,
+                             down_y, pad_x0, pad_x1, pad_y0, pad_y1, dt, _stream(x))
+    _lib.check(rc, "upfirdn2d")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# conv primitives (fp32).  w is [O, C, kh, kw] (shared) or [B, O, C, kh, kw] (one filter bank per sample,
+# the reference's groups=B trick, multi_stylegan_generator.py:390-411).
+# ---------------------------------------------------------------------------------------------------
+def _pair(v) -> Tuple[int, int]:
+    if isinstance(v, (tuple, list)):
+        return int(v[0]), int(v[1])
+    return int(v), int(v)
+
+
+def _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample) -> ConvDesc:
+    sh, sw = _pair(stride)
+    ph, pw = _pair(padding)
+    if H + 2 * ph < kh or W + 2 * pw < kw:
+        raise RuntimeError("conv2d: kernel (%d,%d) larger than padded input (%d,%d)" % (kh, kw, H + 2 * ph, W + 2 * pw))
+    d = ConvDesc()
+    d.B, d.C, d.H, d.W, d.O, d.kh, d.kw = B, C, H, W, O, kh, kw
+    d.stride_h, d.stride_w, d.pad_h, d.pad_w = sh, sw, ph, pw
+    d.OH = (H + 2 * ph - kh) // sh + 1
+    d.OW = (W + 2 * pw - kw) // sw + 1
+    d.w_batch_stride = O * C * kh * kw if per_sample else 0
+    return d
+
+
+def _check_f32(t: torch.Tensor, name: str) -> None:
+    _require_cuda(t, name)
+    if t.dtype != torch.float32:
+        raise RuntimeError("conv2d: %s must be float32, got %s" % (name, t.dtype))
+
+
+def _w_dims(w: torch.Tensor, B: int):
+    if w.dim() == 5:
+        if w.size(0) != B:
+            raise RuntimeError("conv2d: per-sample weight batch %d != input batch %d" % (w.size(0), B))
+        return True, w.size(1), w.size(2), w.size(3), w.size(4)
+    if w.dim() == 4:
+        return False, w.size(0), w.size(1), w.size(2), w.size(3)
+    raise RuntimeError("conv2d: weight must be [O,C,kh,kw] or [B,O,C,kh,kw]")
+
+
+def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha: float = 1.0) -> torch.Tensor:
+    _check_f32(x, "x")
+    _check_f32(w, "w")
+    x = _aligned(x)
+    w = _aligned(w)
+    B, C, H, W = x.shape
+    per_sample, O, Cw, kh, kw = _w_dims(w, B)
+    if Cw != C:
+        raise RuntimeError("conv2d: weight has %d input channels, input has %d" % (Cw, C))
+    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample)
+    y = torch.empty((B, O, d.OH, d.OW), dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 0, conv_flags)
+        ws, wsp = _workspace(nbytes, x.device)
+        rc = L.msg_conv2d_forward(_ptr(y), _ptr(x), _ptr(w), ctypes.byref(d), float(alpha), wsp, nbytes,
+                                  conv_flags, _stream(x))
+    _lib.check(rc, "conv2d_forward")
+    return y
+
+
+def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Sequence[int], stride=1, padding=0,
+                 alpha: float = 1.0) -> torch.Tensor:
+    """dx of conv2d(x, w) given dy; also conv_transpose2d(dy, w) with output size in_hw."""
+    _check_f32(dy, "dy")
+    _check_f32(w, "w")
+    dy = _aligned(dy)
+    w = _aligned(w)
+    B, O, OH, OW = dy.shape
+    per_sample, Ow, C, kh, kw = _w_dims(w, B)
+    if Ow != O:
+        raise RuntimeError("conv2d_dgrad: weight has %d output channels, dy has %d" % (Ow, O))
+    H, W = int(in_hw[0]), int(in_hw[1])
+    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample)
+    if (d.OH, d.OW) != (OH, OW):
+        raise RuntimeError("conv2d_dgrad: dy spatial size (%d,%d) inconsistent with input size (%d,%d)" % (OH, OW, H, W))
+    dx = torch.empty((B, C, H, W), dtype=torch.float32, device=dy.device)
+    L = _lib.lib()
+    with torch.cuda.device(dy.device):
+        nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 1, conv_flags)
+        ws, wsp = _workspace(nbytes, dy.device)
+        rc = L.msg_conv2d_dgrad(_ptr(dx), _ptr(dy), _ptr(w), ctypes.byref(d), float(alpha), wsp, nbytes,
+                                conv_flags, _stream(dy))
+    _lib.check(rc, "conv2d_dgrad")
+    return dx
+
+
+def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, khw: Sequence[int], stride=1, padding=0,
+                 per_sample: bool = False, alpha: float = 1.0) -> torch.Tensor:
+    _check_f32(dy, "dy")
+    _check_f32(x, "x")
+    dy = _aligned(dy)
+    x = _aligned(x)
+    B, C, H, W = x.shape
+    if dy.size(0) != B:
+        raise RuntimeError("conv2d_wgrad: batch mismatch")
+    O = dy.size(1)
+    kh, kw = int(khw[0]), int(khw[1])
+    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample)
+    if (d.OH, d.OW) != (dy.size(2), dy.size(3)):
+        raise RuntimeError("conv2d_wgrad: dy spatial size inconsistent with x")
+    shape = (B, O, C, kh, kw) if per_sample else (O, C, kh, kw)
+    dw = torch.empty(shape, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 2, conv_flags)
+        ws, wsp = _workspace(nbytes, x.device)
+        rc = L.msg_conv2d_wgrad(_ptr(dw), _ptr(dy), _ptr(x), ctypes.byref(d), float(alpha), wsp, nbytes,
+                                conv_flags, _stream(x))
+    _lib.check(rc, "conv2d_wgrad")
+    return dw
+
+
+def conv2d_last_engine() -> str:
+    return {0: "none", 1: "simt", 2: "tcgen05"}[_lib.lib().msg_conv2d_last_engine()]
+
+
+def tensor_core_path_available() -> bool:
+    return bool(_lib.lib().msg_tensor_core_path_available())
+
+
+def launch_count() -> int:
+    return int(_lib.lib().msg_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------------
+# small fused kernels
+# ---------------------------------------------------------------------------------------------------
+def modulate_weights(W: torch.Tensor, s: torch.Tensor, scale: float, demodulate: bool):
+    """W [O,C,kh,kw], s [B,C] -> (w_mod [B,O,C,kh,kw], demod [B,O] or None)
+    (multi_stylegan/multi_stylegan_generator.py:384-388)."""
+    _check_f32(W, "W")
+    _check_f32(s, "s")
+    W = _aligned(W)
+    s = _aligned(s)
+    O, C, kh, kw = W.shape
+    B = s.size(0)
+    if s.shape != (B, C):
+        raise RuntimeError("modulate_weights: style must be [B, C]")
+    out = torch.empty((B, O, C, kh, kw), dtype=torch.float32, device=W.device)
+    dm = torch.empty((B, O), dtype=torch.float32, device=W.device) if demodulate else None
+    with torch.cuda.device(W.device):
+        rc = _lib.lib().msg_modulate_weights(_ptr(out), _ptr(dm), _ptr(W), _ptr(s), B, O, C, kh * kw, float(scale),
+                                             1 if demodulate else 0, _stream(W))
+    _lib.check(rc, "modulate_weights")
+    return out, dm
+
+
+def noise_bias_act(x: torch.Tensor, noise: Optional[torch.Tensor], noise_w: Optional[torch.Tensor],
+                   bias: Optional[torch.Tensor], alpha: float, scale: float) -> torch.Tensor:
+    """lrelu(x + noise_w * noise + bias[c]) * scale — multi_stylegan_generator.py:292 fused with
+    op_static/fused_act.py:58."""
+    _check_f32(x, "x")
+    x = _aligned(x)
+    B, C = x.size(0), x.size(1)
+    HW = x.numel() // max(B * C, 1)
+    nbs = 0
+    if noise is not None:
+        _check_f32(noise, "noise")
+        noise = _aligned(noise)
+        if noise.numel() == HW:
+            nbs = 0
+        elif noise.numel() == B * HW:
+            nbs = HW
+        else:
+            raise RuntimeError("noise_bias_act: noise must be [B or 1, 1, H, W]")
+        noise_w = _aligned(noise_w)
+    if bias is not None:
+        bias = _aligned(bias)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().msg_noise_bias_act(_ptr(out), _ptr(x), _ptr(noise), _ptr(noise_w) if noise is not None else None,
+                                           _ptr(bias), B, C, HW, nbs, float(alpha), float(scale), _stream(x))
+    _lib.check(rc, "noise_bias_act")
+    return out
+
+
+def affine_warp(x: torch.Tensor, theta: torch.Tensor, mode: int = 0) -> torch.Tensor:
+    """Bilinear warp in pixel coordinates; theta [B,2,3] maps output (x,y,1) to input (x,y)."""
+    _check_f32(x, "x")
+    _check_f32(theta, "theta")
+    x = _aligned(x)
+    theta = _aligned(theta)
+    B, C, H, W = x.shape
+    if theta.shape != (B, 2, 3):
+        raise RuntimeError("affine_warp: theta must be [B, 2, 3]")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().msg_affine_warp(_ptr(out), _ptr(x), _ptr(theta), B, C, H, W, int(mode), _stream(x))
+    _lib.check(rc, "affine_warp")
+    return out

@@ -1,0 +1,91 @@
+"""Differentiable conv primitives on top of the C-ABI conv kernels (csrc/conv_*.cu).
+
+A convolution is bilinear in (input, weight), so the three kernels {forward, dgrad, wgrad} are closed
+under differentiation: each autograd Function's backward is written with the other two, which gives
+gradients of any order — R1 (loss.py:311-316) differentiates the discriminator's input gradient and
+path-length regularisation (multi_stylegan_generator.py:193-200) the generator's latent gradient.
+
+Replaces F.conv2d / F.conv_transpose2d at multi_stylegan_generator.py:398,409 and equalized_layer.py:70-73.
+Weights are [O, C, kh, kw] (shared) or [B, O, C, kh, kw] (one filter bank per sample = the reference's
+``groups=batch`` reshaping)."""
+from typing import Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import _C
+
+
+def _pair(v) -> Tuple[int, int]:
+    return (int(v[0]), int(v[1])) if isinstance(v, (tuple, list)) else (int(v), int(v))
+
+
+class _ConvForward(Function):
+    @staticmethod
+    def forward(ctx, x, w, stride, padding):
+        ctx.save_for_backward(x, w)
+        ctx.stride, ctx.padding = stride, padding
+        return _C.conv2d_forward(x, w, stride, padding)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = _ConvDgrad.apply(dy, w, tuple(x.shape[2:]), ctx.stride, ctx.padding)
+        if ctx.needs_input_grad[1]:
+            dw = _ConvWgrad.apply(dy, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5)
+        return dx, dw, None, None
+
+
+class _ConvDgrad(Function):
+    """dx = conv^T(dy, w); as a function of (dy, w) it is the transposed convolution."""
+
+    @staticmethod
+    def forward(ctx, dy, w, in_hw, stride, padding):
+        ctx.save_for_backward(dy, w)
+        ctx.in_hw, ctx.stride, ctx.padding = in_hw, stride, padding
+        return _C.conv2d_dgrad(dy, w, in_hw, stride, padding)
+
+    @staticmethod
+    def backward(ctx, ddx):
+        dy, w = ctx.saved_tensors
+        g_dy = g_w = None
+        if ctx.needs_input_grad[0]:
+            g_dy = _ConvForward.apply(ddx, w, ctx.stride, ctx.padding)
+        if ctx.needs_input_grad[1]:
+            g_w = _ConvWgrad.apply(dy, ddx, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5)
+        return g_dy, g_w, None, None, None
+
+
+class _ConvWgrad(Function):
+    @staticmethod
+    def forward(ctx, dy, x, khw, stride, padding, per_sample):
+        ctx.save_for_backward(dy, x)
+        ctx.stride, ctx.padding = stride, padding
+        return _C.conv2d_wgrad(dy, x, khw, stride, padding, per_sample)
+
+    @staticmethod
+    def backward(ctx, ddw):
+        dy, x = ctx.saved_tensors
+        g_dy = g_x = None
+        if ctx.needs_input_grad[0]:
+            g_dy = _ConvForward.apply(x, ddw, ctx.stride, ctx.padding)
+        if ctx.needs_input_grad[1]:
+            g_x = _ConvDgrad.apply(dy, ddw, tuple(x.shape[2:]), ctx.stride, ctx.padding)
+        return g_dy, g_x, None, None, None, None
+
+
+def conv2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0) -> torch.Tensor:
+    """x [B,C,H,W]; w [O,C,kh,kw] or [B,O,C,kh,kw]."""
+    return _ConvForward.apply(x, w, _pair(stride), _pair(padding))
+
+
+def conv_transpose2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0) -> torch.Tensor:
+    """x [B,Cin,H,W]; w [Cin,Cout,kh,kw] or [B,Cin,Cout,kh,kw] (torch's conv_transpose2d weight layout,
+    which is the layout of the conv whose input-gradient this is).  output_padding = 0."""
+    sh, sw = _pair(stride)
+    ph, pw = _pair(padding)
+    kh, kw = w.shape[-2:]
+    out_hw = ((x.shape[2] - 1) * sh - 2 * ph + kh, (x.shape[3] - 1) * sw - 2 * pw + kw)
+    return _ConvDgrad.apply(x, w, out_hw, (sh, sw), (ph, pw))

@@ -1,0 +1,657 @@
+// tcgen05 / TMEM / TMA engine (sm_100a) for the two gather GEMMs of conv_common.cuh.
+//
+// PixGemm (forward / dgrad / transposed conv):  D[128 pixels, BN channels] += A * B per (tap, 32-channel
+//   chunk).  A is read by TMA straight out of the NCHW activation: box (AW px, 32 ch, 128/AW rows) of
+//   the 4-D view (W, C, H, B) lands in shared memory as an MN-major (pixel-contiguous) UMMA operand
+//   with the hardware 128B (AW=32) or 64B (AW=16) swizzle; a filter tap is just a shifted TMA
+//   coordinate and the conv zero padding is TMA out-of-bounds fill.  B is the pre-transformed,
+//   TF32-rounded weight tile [tap][n][c] (K-major, 128B swizzle).  Accumulator: 128 lanes x BN
+//   columns of TMEM, read back with tcgen05.ld; lanes are pixels, so each column is one coalesced
+//   NCHW row segment.
+// RedGemm (wgrad):  D[128 out-ch, BN in-ch] += dy[n, 32 px] * x[c, 32 px (shifted)]; both operands are
+//   K-major (pixel-contiguous) NCHW tiles, split-K over pixels into a workspace + deterministic reduce.
+//
+// Warp roles (192 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one
+// elected lane), warps 2..5 = epilogue (TMEM lane quarter = warp & 3).  smem full/empty mbarrier ring.
+#include <cuda.h>
+#include <stdlib.h>
+#include <mutex>
+
+#include "conv_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace msg {
+
+using namespace ptx;
+
+// ------------------------------------------------------------------------------------------------
+// TMA descriptor encoding through the driver entry point (no link-time libcuda dependency).
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+    (void)cudaGetLastError();
+  });
+  return fn;
+}
+
+bool tc_available() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0;
+    bool ok = cudaGetDevice(&dev) == cudaSuccess &&
+              cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess && major == 10 &&
+              get_encode() != nullptr;
+    (void)cudaGetLastError();
+    const char* off = getenv("MSG_B200_DISABLE_TC");
+    if (off && off[0] == '1') ok = false;
+    cached = ok ? 1 : 0;
+  }
+  return cached == 1;
+}
+
+static uint32_t tc_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MSG_B200_TC_VARIANT");
+    v = e ? atoi(e) : 0;
+  }
+  return (uint32_t)v;
+}
+
+// 4-D fp32 tensor map; dims[0] is the contiguous dimension, strides_bytes for dims 1..3.
+static int make_tmap(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                     const uint32_t box[4], CUtensorMapSwizzle swz) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(MSG_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gs[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MSG_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): dims %llu,%llu,%llu,%llu strides %llu,%llu,%llu box %u,%u,%u,%u",
+                (int)r, (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)gd[2],
+                (unsigned long long)gd[3], (unsigned long long)gs[0], (unsigned long long)gs[1],
+                (unsigned long long)gs[2], bx[0], bx[1], bx[2], bx[3]);
+  return MSG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight transform for PixGemm: wt[bw][t][n][c] = tf32_rna(w(b, n, c, tap_wi[t])), zero padded.
+// ------------------------------------------------------------------------------------------------
+struct WtParams {
+  const float* w;
+  int64_t w_sb, w_sn, w_sc, w_st;
+  int N, Cr, Npad, Cpad, ntaps, BW;
+  int tap_wi[kMaxTaps];
+};
+
+__device__ __forceinline__ float to_tf32_rna(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256)
+tc_weight_transform_kernel(float* __restrict__ wt, const WtParams p) {
+  const int64_t total = (int64_t)p.BW * p.ntaps * p.Npad * p.Cpad;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int64_t r = i;
+    const int c = (int)(r % p.Cpad); r /= p.Cpad;
+    const int n = (int)(r % p.Npad); r /= p.Npad;
+    const int t = (int)(r % p.ntaps); r /= p.ntaps;
+    const int b = (int)r;
+    float v = 0.f;
+    if (c < p.Cr && n < p.N)
+      v = to_tf32_rna(__ldg(p.w + b * p.w_sb + n * p.w_sn + c * p.w_sc + p.tap_wi[t] * p.w_st));
+    wt[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// PixGemm kernel
+// ------------------------------------------------------------------------------------------------
+struct TcPixParams {
+  int ntaps, cchunks;
+  int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
+  int PH, PW, N, tiles_x;
+  float* out;
+  int64_t out_sb, out_sn;
+  int out_pitch, out_sy, out_sx, out_oy, out_ox;
+  float alpha;
+  int w_per_sample;
+  uint32_t variant;
+};
+
+template <int AW, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                  const TcPixParams p) {
+  constexpr int AH = 128 / AW;
+  constexpr uint32_t A_BYTES = 128 * 32 * 4;
+  constexpr uint32_t B_BYTES = BN * 32 * 4;
+  constexpr uint32_t A_SWZ = (AW == 32) ? SWZ_128B : SWZ_64B;
+  constexpr uint32_t A_ROW = AW * 4;          // one channel row of the atom (= swizzle span)
+  constexpr uint32_t A_KATOM = 8 * A_ROW;     // 8 channels = one UMMA K step
+  constexpr uint32_t A_MATOM = 32 * A_ROW;    // next image row (M atom) inside the box [h][c][w]
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t IDESC = make_idesc_tf32(128, BN, /*A MN-major*/ 1, /*B K-major*/ 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + STAGES * A_BYTES;
+  const uint32_t bars = sB + STAGES * B_BYTES;
+  const uint32_t acc_full = bars + 16 * STAGES;
+  const uint32_t tmem_slot = acc_full + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+  const int y0 = ty * AH, x0 = tx * AW;
+  const int n0 = blockIdx.y * BN;
+  const int b = blockIdx.z;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);             // full
+      mbar_init(bars + 8 * (STAGES + s), 1);  // empty
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int kiters = p.ntaps * p.cchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int bw = p.w_per_sample ? b : 0;
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u);
+        const int t = it / p.cchunks;
+        const int c0 = (it - t * p.cchunks) * 32;
+        const uint32_t full = bars + 8 * s;
+        mbar_expect_tx(full, A_BYTES + B_BYTES);
+        tma_load_4d(sA + s * A_BYTES, &tmA, full, x0 + p.tap_dx[t], c0, y0 + p.tap_dy[t], b);
+        tma_load_4d(sB + s * B_BYTES, &tmB, full, c0, n0, t, bw);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const bool swapA = p.variant & 1u;
+      const uint32_t a_lbo = swapA ? A_KATOM : A_MATOM;
+      const uint32_t a_sbo = swapA ? A_MATOM : A_KATOM;
+      const uint32_t b_lbo = (p.variant & 2u) ? 16u : 0u;
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(bars + 8 * s, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = make_smem_desc(sA + s * A_BYTES + k * A_KATOM, a_lbo, a_sbo, A_SWZ);
+          const uint64_t bd = make_smem_desc(sB + s * B_BYTES + k * 32, b_lbo, 1024, SWZ_128B);
+          mma_tf32(tmem_base, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(bars + 8 * (STAGES + s));  // smem stage reusable once these MMAs retire
+      }
+      mma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int row = m / AW, col = m - row * AW;
+    const int y = y0 + row, x = x0 + col;
+    const bool valid = (y < p.PH) && (x < p.PW);
+    float* optr = p.out + (int64_t)b * p.out_sb + (int64_t)(y * p.out_sy + p.out_oy) * p.out_pitch +
+                  (x * p.out_sx + p.out_ox);
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (BN >= 32) {
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        float r[32];
+        tmem_ld_32x32(tlane + cc, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int n = n0 + cc + j;
+          if (valid && n < p.N) optr[(int64_t)n * p.out_sn] = p.alpha * r[j];
+        }
+      }
+    } else {
+      float r[16];
+      tmem_ld_32x16(tlane, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = n0 + j;
+        if (valid && n < p.N) optr[(int64_t)n * p.out_sn] = p.alpha * r[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RedGemm kernel (wgrad): both operands K-major, split-K into `part`.
+// ------------------------------------------------------------------------------------------------
+struct TcRedParams {
+  int ntaps;
+  int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
+  int B, per_sample;
+  int chunks_x, chunks_y;
+  int ctiles;               // number of BN-wide tiles along C
+  int Npad, Cpad, splits;
+  float* part;              // [splits][BS][ntaps][Npad][Cpad]
+};
+
+template <int AW, int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmI,
+                  const TcRedParams p) {
+  constexpr int KH = 32 / AW;
+  constexpr uint32_t A_BYTES = 128 * 32 * 4;
+  constexpr uint32_t B_BYTES = BN * 32 * 4;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t IDESC = make_idesc_tf32(128, BN, 0, 0);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + STAGES * A_BYTES;
+  const uint32_t bars = sB + STAGES * B_BYTES;
+  const uint32_t acc_full = bars + 16 * STAGES;
+  const uint32_t tmem_slot = acc_full + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntile = blockIdx.x / p.ctiles, ctile = blockIdx.x - ntile * p.ctiles;
+  const int n0 = ntile * 128, c0 = ctile * BN;
+  const int t = blockIdx.y % p.ntaps;
+  const int bs = blockIdx.y / p.ntaps;      // sample index when per_sample, else 0
+  const int split = blockIdx.z;
+
+  const int per = p.chunks_x * p.chunks_y;
+  const int64_t total = (int64_t)per * (p.per_sample ? 1 : p.B);
+  const int k_begin = (int)(total * split / p.splits);
+  const int k_end = (int)(total * (split + 1) / p.splits);
+  const int kiters = k_end - k_begin;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);
+      mbar_init(bars + 8 * (STAGES + s), 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmG);
+    tma_prefetch_desc(&tmI);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int dy = p.tap_dy[t], dx = p.tap_dx[t];
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u);
+        const int kk = k_begin + it;
+        const int bl = kk / per;
+        const int r = kk - bl * per;
+        const int yc = r / p.chunks_x, xc = r - yc * p.chunks_x;
+        const int b = p.per_sample ? bs : bl;
+        const uint32_t full = bars + 8 * s;
+        mbar_expect_tx(full, A_BYTES + B_BYTES);
+        tma_load_4d(sA + s * A_BYTES, &tmG, full, xc * AW, yc * KH, n0, b);
+        tma_load_4d(sB + s * B_BYTES, &tmI, full, xc * AW + dx, yc * KH + dy, c0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int it = 0; it < kiters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(bars + 8 * s, ph);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t ad = make_smem_desc(sA + s * A_BYTES + k * 32, 0, 1024, SWZ_128B);
+          const uint64_t bd = make_smem_desc(sB + s * B_BYTES + k * 32, 0, 1024, SWZ_128B);
+          mma_tf32(tmem_base, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        mma_commit(bars + 8 * (STAGES + s));
+      }
+      mma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int n = q * 32 + lane;
+    float* prow = p.part + ((((int64_t)split * gridDim.y + blockIdx.y) * p.Npad) + n0 + n) * p.Cpad + c0;
+    if (kiters > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (BN >= 32) {
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        float r[32];
+        if (kiters > 0) {
+          tmem_ld_32x32(tlane + cc, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(prow + cc + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+    } else {
+      float r[16];
+      if (kiters > 0) {
+        tmem_ld_32x16(tlane, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(prow + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+struct RedReduceParams {
+  const float* part;
+  float* dw;
+  int64_t dw_sb, dw_sn, dw_sc, dw_st;
+  int splits, BS, ntaps, N, C, Npad, Cpad;
+  int tap_wi[kMaxTaps];
+  float alpha;
+};
+
+__global__ void __launch_bounds__(256)
+tc_red_reduce_kernel(const RedReduceParams p) {
+  const int64_t total = (int64_t)p.BS * p.ntaps * p.N * p.C;
+  const int64_t slab = (int64_t)p.BS * p.ntaps * p.Npad * p.Cpad;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int64_t r = i;
+    const int c = (int)(r % p.C); r /= p.C;
+    const int n = (int)(r % p.N); r /= p.N;
+    const int t = (int)(r % p.ntaps); r /= p.ntaps;
+    const int bs = (int)r;
+    const int64_t off = (((int64_t)bs * p.ntaps + t) * p.Npad + n) * p.Cpad + c;
+    float acc = 0.f;
+    for (int s = 0; s < p.splits; ++s) acc += p.part[s * slab + off];
+    p.dw[bs * p.dw_sb + n * p.dw_sn + c * p.dw_sc + p.tap_wi[t] * p.dw_st] = p.alpha * acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static int pick_bn(int n) {
+  if (n > 128) return 256;
+  if (n > 64) return 128;
+  if (n > 32) return 64;
+  if (n > 16) return 32;
+  return 16;
+}
+static int stages_for(int bn) {
+  const int per = 16384 + bn * 128;
+  int s = (200 * 1024) / per;
+  return s > 6 ? 6 : s;
+}
+
+bool tc_pixgemm_supported(const PixGemm& g) {
+  if (!tc_available()) return false;
+  if (g.ntaps <= 0 || g.ntaps > kMaxTaps || g.Cr <= 0 || g.N <= 0 || g.B <= 0) return false;
+  if (g.in_sy != 1 || g.in_sx != 1) return false;
+  if (g.PW < 16 || g.PH < 1 || g.IW < 16) return false;
+  if (!al16(g.in) || (g.in_pitch & 3) || (g.in_sc & 3) || (g.in_sb & 3)) return false;
+  if (g.B > 65535) return false;
+  return true;
+}
+
+size_t tc_pixgemm_workspace(const PixGemm& g) {
+  const int BN = pick_bn(g.N);
+  const int64_t Npad = round_up(g.N, BN), Cpad = round_up(g.Cr, 32);
+  const int64_t BW = g.w_sb != 0 ? g.B : 1;
+  return (size_t)(BW * g.ntaps * Npad * Cpad) * sizeof(float) + 256;
+}
+
+template <int AW, int BN>
+static int launch_pix(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPixParams& p, dim3 grid,
+                      cudaStream_t st) {
+  constexpr int STAGES = (BN == 256) ? 4 : 6;
+  constexpr size_t smem = (size_t)STAGES * (16384 + BN * 128) + 16 * STAGES + 64 + 1024;
+  auto kfn = tc_pixgemm_kernel<AW, BN, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  kfn<<<grid, 192, smem, st>>>(tmA, tmB, p);
+  MSG_CHECK_LAUNCH("conv pixgemm(tcgen05)");
+  return MSG_OK;
+}
+
+int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!tc_pixgemm_supported(g)) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): shape not supported");
+  const size_t need = tc_pixgemm_workspace(g);
+  if (!ws || ws_bytes < need) return fail(MSG_ERR_WORKSPACE, "conv pixgemm(tcgen05): workspace %zu < %zu", ws_bytes, need);
+  float* wt = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  const int BN = pick_bn(g.N);
+  const int Npad = round_up(g.N, BN), Cpad = round_up(g.Cr, 32);
+  const int BW = g.w_sb != 0 ? g.B : 1;
+
+  WtParams wp{};
+  wp.w = g.w; wp.w_sb = g.w_sb; wp.w_sn = g.w_sn; wp.w_sc = g.w_sc; wp.w_st = g.w_st;
+  wp.N = g.N; wp.Cr = g.Cr; wp.Npad = Npad; wp.Cpad = Cpad; wp.ntaps = g.ntaps; wp.BW = BW;
+  for (int t = 0; t < g.ntaps; ++t) wp.tap_wi[t] = g.tap_wi[t];
+  {
+    const int64_t total = (int64_t)BW * g.ntaps * Npad * Cpad;
+    const int64_t want = ceil_div(total, 256);
+    const int64_t cap = (int64_t)num_sms() * 16;
+    tc_weight_transform_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(wt, wp);
+    MSG_CHECK_LAUNCH("conv weight transform");
+  }
+
+  const int AW = g.PW >= 32 ? 32 : 16;
+  const int AH = 128 / AW;
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {(uint64_t)g.IW, (uint64_t)g.Cr, (uint64_t)g.IH, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)g.in_sc * 4, (uint64_t)g.in_pitch * 4, (uint64_t)g.in_sb * 4};
+    const uint32_t box[4] = {(uint32_t)AW, 32, (uint32_t)AH, 1};
+    int rc = make_tmap(&tmA, g.in, dims, strides, box, AW == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)Cpad, (uint64_t)Npad, (uint64_t)g.ntaps, (uint64_t)BW};
+    const uint64_t strides[3] = {(uint64_t)Cpad * 4, (uint64_t)Cpad * Npad * 4, (uint64_t)Cpad * Npad * g.ntaps * 4};
+    const uint32_t box[4] = {32, (uint32_t)BN, 1, 1};
+    int rc = make_tmap(&tmB, wt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  TcPixParams p{};
+  p.ntaps = g.ntaps; p.cchunks = Cpad / 32;
+  for (int t = 0; t < g.ntaps; ++t) { p.tap_dy[t] = g.tap_dy[t]; p.tap_dx[t] = g.tap_dx[t]; }
+  p.PH = g.PH; p.PW = g.PW; p.N = g.N;
+  p.tiles_x = (int)ceil_div(g.PW, AW);
+  const int tiles_y = (int)ceil_div(g.PH, AH);
+  p.out = g.out; p.out_sb = g.out_sb; p.out_sn = g.out_sn; p.out_pitch = g.out_pitch;
+  p.out_sy = g.out_sy; p.out_sx = g.out_sx; p.out_oy = g.out_oy; p.out_ox = g.out_ox;
+  p.alpha = g.alpha; p.w_per_sample = g.w_sb != 0; p.variant = tc_variant();
+  dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)(Npad / BN), (unsigned)g.B);
+  if (grid.y > 65535) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): too many N tiles");
+
+#define PIX_CASE(AW_, BN_) if (AW == AW_ && BN == BN_) return launch_pix<AW_, BN_>(tmA, tmB, p, grid, st)
+  PIX_CASE(32, 256); PIX_CASE(32, 128); PIX_CASE(32, 64); PIX_CASE(32, 32); PIX_CASE(32, 16);
+  PIX_CASE(16, 256); PIX_CASE(16, 128); PIX_CASE(16, 64); PIX_CASE(16, 32); PIX_CASE(16, 16);
+#undef PIX_CASE
+  return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): no kernel for AW=%d BN=%d", AW, BN);
+}
+
+// ---- RedGemm host -------------------------------------------------------------------------------
+bool tc_redgemm_supported(const RedGemm& g) {
+  if (!tc_available()) return false;
+  if (g.ntaps <= 0 || g.ntaps > kMaxTaps || g.C <= 0 || g.N <= 0 || g.B <= 0) return false;
+  if (g.in_sy != 1 || g.in_sx != 1) return false;
+  if (g.PW < 16 || g.IW < 16 || g.PH < 2 || g.IH < 2) return false;
+  if (!al16(g.in) || (g.in_pitch & 3) || (g.in_sc & 3) || (g.in_sb & 3)) return false;
+  if (!al16(g.g) || (g.g_pitch & 3) || (g.g_sn & 3) || (g.g_sb & 3)) return false;
+  const int BS = g.dw_sb != 0 ? g.B : 1;
+  if ((int64_t)g.ntaps * BS > 65535) return false;
+  return true;
+}
+
+struct RedPlan {
+  int AW, BN, Npad, Cpad, BS, splits, chunks_x, chunks_y;
+  size_t part_bytes;
+};
+
+static RedPlan red_plan(const RedGemm& g) {
+  RedPlan pl{};
+  pl.AW = g.PW >= 32 ? 32 : 16;
+  pl.BN = pick_bn(g.C);
+  pl.Npad = round_up(g.N, 128);
+  pl.Cpad = round_up(g.C, pl.BN);
+  pl.BS = g.dw_sb != 0 ? g.B : 1;
+  const int KH = 32 / pl.AW;
+  pl.chunks_x = (int)ceil_div(g.PW, pl.AW);
+  pl.chunks_y = (int)ceil_div(g.PH, KH);
+  const int64_t kiters = (int64_t)pl.chunks_x * pl.chunks_y * (g.dw_sb != 0 ? 1 : g.B);
+  const int64_t tiles = (int64_t)(pl.Npad / 128) * (pl.Cpad / pl.BN) * g.ntaps * pl.BS;
+  int64_t splits = ceil_div(2 * (int64_t)num_sms(), tiles);
+  const int64_t max_by_k = kiters / 8 > 0 ? kiters / 8 : 1;   // keep >= 8 k-iterations per CTA
+  if (splits > max_by_k) splits = max_by_k;
+  if (splits > 64) splits = 64;
+  if (splits < 1) splits = 1;
+  pl.splits = (int)splits;
+  pl.part_bytes = (size_t)pl.splits * pl.BS * g.ntaps * pl.Npad * pl.Cpad * sizeof(float);
+  return pl;
+}
+
+size_t tc_redgemm_workspace(const RedGemm& g) { return red_plan(g).part_bytes + 256; }
+
+template <int AW, int BN>
+static int launch_red(const CUtensorMap& tmG, const CUtensorMap& tmI, const TcRedParams& p, dim3 grid,
+                      cudaStream_t st) {
+  constexpr int STAGES = (BN == 256) ? 4 : 6;
+  constexpr size_t smem = (size_t)STAGES * (16384 + BN * 128) + 16 * STAGES + 64 + 1024;
+  auto kfn = tc_redgemm_kernel<AW, BN, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  kfn<<<grid, 192, smem, st>>>(tmG, tmI, p);
+  MSG_CHECK_LAUNCH("conv redgemm(tcgen05)");
+  return MSG_OK;
+}
+
+int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (!tc_redgemm_supported(g)) return fail(MSG_ERR_UNSUPPORTED, "conv wgrad(tcgen05): shape not supported");
+  const RedPlan pl = red_plan(g);
+  if (!ws || ws_bytes < pl.part_bytes + 256)
+    return fail(MSG_ERR_WORKSPACE, "conv wgrad(tcgen05): workspace %zu < %zu", ws_bytes, pl.part_bytes + 256);
+  float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  const int KH = 32 / pl.AW;
+  CUtensorMap tmG, tmI;
+  {
+    const uint64_t dims[4] = {(uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.N, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)g.g_pitch * 4, (uint64_t)g.g_sn * 4, (uint64_t)g.g_sb * 4};
+    const uint32_t box[4] = {(uint32_t)pl.AW, (uint32_t)KH, 128, 1};
+    int rc = make_tmap(&tmG, g.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.C, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)g.in_pitch * 4, (uint64_t)g.in_sc * 4, (uint64_t)g.in_sb * 4};
+    const uint32_t box[4] = {(uint32_t)pl.AW, (uint32_t)KH, (uint32_t)pl.BN, 1};
+    int rc = make_tmap(&tmI, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  TcRedParams p{};
+  p.ntaps = g.ntaps;
+  for (int t = 0; t < g.ntaps; ++t) { p.tap_dy[t] = g.tap_dy[t]; p.tap_dx[t] = g.tap_dx[t]; }
+  p.B = g.B; p.per_sample = g.dw_sb != 0;
+  p.chunks_x = pl.chunks_x; p.chunks_y = pl.chunks_y;
+  p.ctiles = pl.Cpad / pl.BN;
+  p.Npad = pl.Npad; p.Cpad = pl.Cpad; p.splits = pl.splits; p.part = part;
+  dim3 grid((unsigned)((pl.Npad / 128) * p.ctiles), (unsigned)(g.ntaps * pl.BS), (unsigned)pl.splits);
+  int rc = MSG_ERR_UNSUPPORTED;
+  const int AW = pl.AW, BN = pl.BN;
+#define RED_CASE(AW_, BN_) if (AW == AW_ && BN == BN_) rc = launch_red<AW_, BN_>(tmG, tmI, p, grid, st)
+  RED_CASE(32, 256); RED_CASE(32, 128); RED_CASE(32, 64); RED_CASE(32, 32); RED_CASE(32, 16);
+  RED_CASE(16, 256); RED_CASE(16, 128); RED_CASE(16, 64); RED_CASE(16, 32); RED_CASE(16, 16);
+#undef RED_CASE
+  if (rc) return rc;
+
+  RedReduceParams rp{};
+  rp.part = part; rp.dw = g.dw; rp.dw_sb = g.dw_sb; rp.dw_sn = g.dw_sn; rp.dw_sc = g.dw_sc; rp.dw_st = g.dw_st;
+  rp.splits = pl.splits; rp.BS = pl.BS; rp.ntaps = g.ntaps; rp.N = g.N; rp.C = g.C; rp.Npad = pl.Npad; rp.Cpad = pl.Cpad;
+  for (int t = 0; t < g.ntaps; ++t) rp.tap_wi[t] = g.tap_wi[t];
+  rp.alpha = g.alpha;
+  const int64_t total = (int64_t)pl.BS * g.ntaps * g.N * g.C;
+  const int64_t want = ceil_div(total, 256);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  tc_red_reduce_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(rp);
+  MSG_CHECK_LAUNCH("conv wgrad reduce");
+  return MSG_OK;
+}
+
+}  // namespace msg

@@ -1,0 +1,169 @@
+// Library bookkeeping + the small bandwidth-bound kernels around the modulated convolution and ADA.
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace msg {
+thread_local char g_last_error[512] = "";
+std::atomic<uint64_t> g_launch_count{0};
+
+// ---- weight modulation + demodulation (multi_stylegan_generator.py:384-388) ------------------------
+// one block per (b, o): w_mod[b,o,:,:] = scale*W[o,:,:]*s[b,:] * rsqrt(sum(.)^2 + 1e-8)
+__global__ void __launch_bounds__(256)
+modulate_weights_kernel(float* __restrict__ w_mod, float* __restrict__ demod_out, const float* __restrict__ W,
+                        const float* __restrict__ s, int O, int C, int taps, float scale, int demodulate) {
+  const int o = blockIdx.x, b = blockIdx.y;
+  const int n = C * taps;
+  const float* Wo = W + (int64_t)o * n;
+  const float* sb = s + (int64_t)b * C;
+  float* out = w_mod + ((int64_t)b * O + o) * n;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = scale * __ldg(Wo + i) * __ldg(sb + i / taps);
+    out[i] = v;
+    ss = fmaf(v, v, ss);
+  }
+  if (!demodulate) return;
+  __shared__ float scratch[32];
+  __shared__ float dsh;
+  ss = block_sum(ss, scratch);
+  if (threadIdx.x == 0) {
+    dsh = rsqrtf(ss + 1e-8f);
+    if (demod_out) demod_out[(int64_t)b * O + o] = dsh;
+  }
+  __syncthreads();
+  const float dm = dsh;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] *= dm;
+}
+
+// ---- noise + bias + leaky ReLU ------------------------------------------------------------------------
+// grid: (chunks of HW/4, B*C)
+__global__ void __launch_bounds__(256)
+noise_bias_act_kernel(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ noise,
+                      const float* __restrict__ noise_w, const float* __restrict__ bias, int C, int64_t HW,
+                      int64_t noise_bs, float alpha, float scale) {
+  const int64_t plane = blockIdx.y;
+  const int b = (int)(plane / C), c = (int)(plane - (int64_t)b * C);
+  const float bv = bias ? __ldg(bias + c) : 0.f;
+  const float nw = noise ? __ldg(noise_w) : 0.f;
+  const float* xp = x + plane * HW;
+  const float* np = noise ? noise + (int64_t)b * noise_bs : nullptr;
+  float* op = out + plane * HW;
+  const bool vec = (HW & 3) == 0 && (noise_bs & 3) == 0 &&
+                   ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) |
+                     reinterpret_cast<uintptr_t>(noise)) & 15u) == 0;
+  if (vec) {
+    const int64_t n4 = HW >> 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(xp) + i);
+      float4 nz = np ? __ldg(reinterpret_cast<const float4*>(np) + i) : make_float4(0, 0, 0, 0);
+      float4 o;
+      float t;
+      t = v.x + nw * nz.x + bv; o.x = (t > 0.f ? t : t * alpha) * scale;
+      t = v.y + nw * nz.y + bv; o.y = (t > 0.f ? t : t * alpha) * scale;
+      t = v.z + nw * nz.z + bv; o.z = (t > 0.f ? t : t * alpha) * scale;
+      t = v.w + nw * nz.w + bv; o.w = (t > 0.f ? t : t * alpha) * scale;
+      reinterpret_cast<float4*>(op)[i] = o;
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += (int64_t)gridDim.x * blockDim.x) {
+      const float t = xp[i] + (np ? nw * np[i] : 0.f) + bv;
+      op[i] = (t > 0.f ? t : t * alpha) * scale;
+    }
+  }
+}
+
+// ---- affine warp (grid_sample bilinear, align_corners=True) ---------------------------------------------
+__device__ __forceinline__ float reflect_coord(float x, int size) {
+  // torch grid_sample reflection with align_corners=True: reflect over [0, size-1]
+  if (size <= 1) return 0.f;
+  const float span = (float)(size - 1);
+  x = fabsf(x);
+  const float flips = floorf(x / span);
+  const float extra = x - flips * span;
+  const float r = (fmodf(flips, 2.f) == 0.f) ? extra : span - extra;
+  return fminf(fmaxf(r, 0.f), span);
+}
+
+__global__ void __launch_bounds__(256)
+affine_warp_kernel(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ theta, int C,
+                   int H, int W, int mode) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= W) return;
+  const float* th = theta + b * 6;
+  float sx = th[0] * x + th[1] * y + th[2];
+  float sy = th[3] * x + th[4] * y + th[5];
+  if (mode == 0) { sx = reflect_coord(sx, W); sy = reflect_coord(sy, H); }
+  const float fx = floorf(sx), fy = floorf(sy);
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = sx - fx, wy1 = sy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+  const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+  const int64_t plane = (int64_t)H * W;
+  const float* ip = in + (int64_t)b * C * plane;
+  float* op = out + (int64_t)b * C * plane + (int64_t)y * W + x;
+  for (int c = 0; c < C; ++c) {
+    const float* p = ip + c * plane;
+    float v = 0.f;
+    if (vy0 && vx0) v += p[(int64_t)y0 * W + x0] * (wy0 * wx0);
+    if (vy0 && vx1) v += p[(int64_t)y0 * W + x1] * (wy0 * wx1);
+    if (vy1 && vx0) v += p[(int64_t)y1 * W + x0] * (wy1 * wx0);
+    if (vy1 && vx1) v += p[(int64_t)y1 * W + x1] * (wy1 * wx1);
+    op[c * plane] = v;
+  }
+}
+
+}  // namespace msg
+
+using namespace msg;
+
+extern "C" int msg_abi_version(void) { return MSG_B200_ABI_VERSION; }
+extern "C" const char* msg_last_error(void) { return g_last_error; }
+extern "C" uint64_t msg_launch_count(void) { return g_launch_count.load(); }
+extern "C" int msg_tensor_core_path_available(void) { return tc_available() ? 1 : 0; }
+
+extern "C" int msg_modulate_weights(float* w_mod, float* demod_out, const float* W, const float* s, int B, int O,
+                                    int C, int taps, float scale, int demodulate, msg_stream_t stream) {
+  if (B < 0 || O <= 0 || C <= 0 || taps <= 0) return fail(MSG_ERR_BAD_ARG, "modulate_weights: bad sizes");
+  if (B == 0) return MSG_OK;
+  if (!w_mod || !W || !s) return fail(MSG_ERR_BAD_ARG, "modulate_weights: null pointer");
+  if (B > 65535) return fail(MSG_ERR_UNSUPPORTED, "modulate_weights: batch > 65535");
+  dim3 grid((unsigned)O, (unsigned)B);
+  modulate_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_mod, demod_out, W, s, O, C, taps, scale, demodulate);
+  MSG_CHECK_LAUNCH("modulate_weights");
+  return MSG_OK;
+}
+
+extern "C" int msg_noise_bias_act(float* out, const float* x, const float* noise, const float* noise_w,
+                                  const float* bias, int B, int C, int64_t HW, int64_t noise_batch_stride,
+                                  float alpha, float scale, msg_stream_t stream) {
+  if (B < 0 || C <= 0 || HW < 0) return fail(MSG_ERR_BAD_ARG, "noise_bias_act: bad sizes");
+  if (B == 0 || HW == 0) return MSG_OK;
+  if (!out || !x) return fail(MSG_ERR_BAD_ARG, "noise_bias_act: null pointer");
+  if (noise && !noise_w) return fail(MSG_ERR_BAD_ARG, "noise_bias_act: noise without noise_w");
+  const int64_t planes = (int64_t)B * C;
+  if (planes > 65535) {
+    return fail(MSG_ERR_UNSUPPORTED, "noise_bias_act: B*C > 65535");
+  }
+  int64_t chunks = ceil_div(HW, 256 * 4 * 4);
+  if (chunks < 1) chunks = 1;
+  dim3 grid((unsigned)chunks, (unsigned)planes);
+  noise_bias_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(out, x, noise, noise_w, bias, C, HW,
+                                                               noise_batch_stride, alpha, scale);
+  MSG_CHECK_LAUNCH("noise_bias_act");
+  return MSG_OK;
+}
+
+extern "C" int msg_affine_warp(float* out, const float* in, const float* theta, int B, int C, int H, int W, int mode,
+                               msg_stream_t stream) {
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0) return fail(MSG_ERR_BAD_ARG, "affine_warp: bad sizes");
+  if (mode != 0 && mode != 1) return fail(MSG_ERR_BAD_ARG, "affine_warp: mode must be 0 (reflection) or 1 (zeros)");
+  if (B == 0) return MSG_OK;
+  if (!out || !in || !theta) return fail(MSG_ERR_BAD_ARG, "affine_warp: null pointer");
+  if (out == in) return fail(MSG_ERR_BAD_ARG, "affine_warp: in-place not supported");
+  if (B > 65535 || H > 65535) return fail(MSG_ERR_UNSUPPORTED, "affine_warp: B or H > 65535");
+  dim3 grid((unsigned)ceil_div(W, 128), (unsigned)H, (unsigned)B);
+  affine_warp_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(out, in, theta, C, H, W, mode);
+  MSG_CHECK_LAUNCH("affine_warp");
+  return MSG_OK;
+}

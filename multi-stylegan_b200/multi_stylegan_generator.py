@@ -1,0 +1,311 @@
+"""Twin-branch ("dual-style") StyleGAN2 generator with the reference's module tree, constructor
+arguments, forward signature and state_dict names (multi_stylegan/multi_stylegan_generator.py:15-641),
+so reference checkpoints load unchanged — with every convolution, FIR and activation on the sm_100a
+kernels of this package.
+
+Behaviours reproduced on purpose: FusedLeakyReLU gain 1.0; `Upsample` without the
+x4 gain; 2x2/stride-2 transposed up-convs followed by a 4x4 blur with pad (2,1); constant inputs of
+ones; the second branch's main convolutions never reach the image (`output_blocks_2` is fed branch-1
+features, reference :189).  Because that branch is unobservable, `compute_dead_branch=False` skips it
+(identical outputs and gradients; with noise=None it also skips the dead layers' randn draws).
+"""
+import math
+from typing import Any, Dict, Iterable, List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch import autograd
+
+from . import conv, equalized_layer
+from .op_static import FusedLeakyReLU, upfirdn2d
+
+
+def _fir_kernel(taps: List[int]) -> torch.Tensor:
+    k = torch.tensor(taps, dtype=torch.float32)
+    if k.ndim == 1:
+        k = k[None, :] * k[:, None]
+    return k / k.sum()
+
+
+class Upsample(nn.Module):
+    """x2 zero-insertion + FIR, taps normalised to sum 1 (no factor^2 gain) — reference :529-575."""
+
+    def __init__(self, blur_kernel: List[int] = [1, 3, 3, 1], factor: int = 2) -> None:
+        super().__init__()
+        self.factor = factor
+        kernel = _fir_kernel(blur_kernel)
+        self.register_buffer("kernel", kernel)
+        p = kernel.shape[0] - factor
+        self.padding = ((p + 1) // 2 + factor - 1, p // 2)
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        return upfirdn2d(input, self.kernel, up=self.factor, pad=self.padding)
+
+
+class Blur(nn.Module):
+    """FIR low-pass; taps x sampling_factor^2 when sampling_factor > 1 — reference :578-641."""
+
+    def __init__(self, kernel: List[int], sampling_factor: int = 1, sampling_factor_padding: int = 2,
+                 kernel_size: int = 3) -> None:
+        super().__init__()
+        p = (len(kernel) - sampling_factor_padding) + (kernel_size - 1)
+        self.padding = ((p + 1) // 2, p // 2)
+        k = _fir_kernel(kernel)
+        if sampling_factor > 1:
+            k = k * (sampling_factor ** 2)
+        self.register_buffer("kernel", k)
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        return upfirdn2d(input, self.kernel, pad=self.padding)
+
+
+class StyleMapping(nn.Module):
+    def __init__(self, latent_dimensions: int = 512, depth: int = 8) -> None:
+        super().__init__()
+        layers: List[nn.Module] = [equalized_layer.PixelwiseNormalization()]
+        for _ in range(depth):
+            layers += [equalized_layer.EqualizedLinear(latent_dimensions, latent_dimensions, bias=False),
+                       FusedLeakyReLU(latent_dimensions)]
+        self.layers = nn.Sequential(*layers)
+
+    def forward(self, noise: torch.Tensor) -> torch.Tensor:
+        return self.layers(noise)
+
+
+class ConstantInput(nn.Module):
+    def __init__(self, channel: int, size: Tuple[int, int] = (4, 4)) -> None:
+        super().__init__()
+        self.input = nn.Parameter(torch.ones(1, channel, size[0], size[1]))
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        return self.input.repeat_interleave(dim=0, repeats=input.shape[0])
+
+
+class NoiseInjection(nn.Module):
+    def __init__(self) -> None:
+        super().__init__()
+        self.weight = nn.Parameter(torch.zeros(1, dtype=torch.float32))
+
+    def forward(self, input: torch.Tensor, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if noise is None:
+            noise = torch.randn(input.shape[0], 1, input.shape[2], input.shape[3], device=input.device,
+                                dtype=torch.float32)
+        return input + self.weight * noise
+
+
+class ModulatedConv2d(nn.Module):
+    """Weight-modulated / demodulated per-sample convolution — reference :295-414.
+
+    The per-sample filter banks scale*W*s (*demod) are built with the reference's own arithmetic and
+    handed to the per-sample conv kernels as the GEMM B operand; upsampling layers are the 2x2/stride-2
+    transposed convolution (= the conv's dgrad kernel) followed by the x4 blur."""
+
+    def __init__(self, in_channels: int, out_channels: int, style_dimension: int,
+                 kernel_size: Union[int, Tuple[int, int]] = (3, 3), demodulate: bool = True, upsampling: bool = True,
+                 blur_kernel: List[int] = [1, 3, 3, 1], modulation_mapping: bool = True) -> None:
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.demodulate, self.upsampling = demodulate, upsampling
+        self.kernel_size = kernel_size if isinstance(kernel_size, tuple) else (kernel_size, kernel_size)
+        self.blur = Blur(kernel=blur_kernel, sampling_factor=2, sampling_factor_padding=2,
+                         kernel_size=self.kernel_size[0]) if upsampling else None
+        if upsampling:
+            self.padding, self.stride = (0, 0), (2, 2)
+        else:
+            self.padding, self.stride = (self.kernel_size[0] // 2, self.kernel_size[1] // 2), (1, 1)
+        self.scale = math.sqrt(2) / math.sqrt(in_channels * self.kernel_size[0] * self.kernel_size[1])
+        self.weight = nn.Parameter(torch.randn(1, out_channels, in_channels, *self.kernel_size))
+        self.modulation_mapping = equalized_layer.EqualizedLinear(style_dimension, in_channels, bias=True) \
+            if modulation_mapping else None
+        if modulation_mapping:
+            self.modulation_mapping.bias.data.fill_(1.0)
+
+    def extra_repr(self) -> str:
+        return "{}, {}, kernel_size={}, stride={}, padding={}, upsampling={}".format(
+            self.in_channels, self.out_channels, self.kernel_size, self.stride, self.padding, self.upsampling)
+
+    def forward(self, input: torch.Tensor, style: torch.Tensor):
+        batch_size, features, height, width = input.shape
+        assert features == self.in_channels, \
+            "Expect input feature shape of {} but get {}.".format(self.in_channels, features)
+        if self.modulation_mapping is not None:
+            modulated_style = self.modulation_mapping(style).view(batch_size, 1, self.in_channels, 1, 1)
+        else:
+            modulated_style = style
+        weight = self.scale * self.weight * modulated_style                      # [B, O, C, kh, kw]
+        if self.demodulate:
+            demodulation = torch.rsqrt(torch.sum(weight ** 2, dim=[2, 3, 4]) + 1e-08)
+            weight = weight * demodulation.view(batch_size, self.out_channels, 1, 1, 1)
+        if self.upsampling:
+            output = conv.conv_transpose2d(input, weight.transpose(1, 2), stride=self.stride, padding=self.padding)
+            output = self.blur(output)
+        else:
+            output = conv.conv2d(input, weight, stride=self.stride, padding=self.padding)
+        if self.modulation_mapping is not None:
+            return output, modulated_style
+        return output
+
+
+class StyledConv2d(nn.Module):
+    """Modulated conv -> noise injection -> bias + leaky ReLU; returns (out, style) when it owns the
+    style linear, so the paired block of the second branch can reuse the style — reference :417-469."""
+
+    def __init__(self, in_channels: int, out_channels: int, kernel_size: Union[int, Tuple[int, int]],
+                 style_dimension: int, demodulate: bool = True, upsampling: bool = False,
+                 blur_kernel: List[int] = [1, 3, 3, 1], modulation_mapping: bool = True) -> None:
+        super().__init__()
+        self.modulation_mapping = modulation_mapping
+        self.modulated_convolution = ModulatedConv2d(in_channels=in_channels, out_channels=out_channels,
+                                                     kernel_size=kernel_size, style_dimension=style_dimension,
+                                                     demodulate=demodulate, upsampling=upsampling,
+                                                     blur_kernel=blur_kernel, modulation_mapping=modulation_mapping)
+        self.noise_injection = NoiseInjection()
+        self.activation = FusedLeakyReLU(out_channels)
+
+    def forward(self, input: torch.Tensor, style: torch.Tensor, noise: torch.Tensor = None):
+        if self.modulation_mapping:
+            output, style = self.modulated_convolution(input, style)
+        else:
+            output = self.modulated_convolution(input, style)
+        output = self.activation(self.noise_injection(output, noise=noise))
+        if self.modulation_mapping:
+            return output, style
+        return output
+
+
+class OutputBlock(nn.Module):
+    """tRGB: 1x1 modulated conv without demodulation + scalar bias + upsampled skip — reference :472-526."""
+
+    def __init__(self, in_channels: int, style_dimension: int, out_channels: int = 1, upsampling: bool = False,
+                 blur_kernel: List[int] = [1, 3, 3, 1], modulation_mapping: bool = True) -> None:
+        super().__init__()
+        self.modulation_mapping = modulation_mapping
+        self.upsampling = Upsample(blur_kernel=blur_kernel, factor=2) if upsampling else nn.Identity()
+        self.modulated_convolution = ModulatedConv2d(in_channels=in_channels, out_channels=out_channels,
+                                                     style_dimension=style_dimension, kernel_size=(1, 1),
+                                                     upsampling=False, demodulate=False,
+                                                     modulation_mapping=modulation_mapping)
+        self.bias = nn.Parameter(torch.zeros(1, 1, 1, 1, dtype=torch.float32))
+
+    def forward(self, input: torch.Tensor, style: torch.Tensor, skip: torch.Tensor = None):
+        if self.modulation_mapping:
+            output, style = self.modulated_convolution(input, style)
+        else:
+            output = self.modulated_convolution(input, style)
+        output = output + self.bias
+        if skip is not None:
+            output = output + self.upsampling(skip)
+        if self.modulation_mapping:
+            return output, style
+        return output
+
+
+class Generator(nn.Module):
+    def __init__(self, config: Dict[str, Any], compute_dead_branch: bool = True) -> None:
+        super().__init__()
+        channels: Tuple[int, ...] = config["channels"]
+        f = config["channel_factor"]
+        ch = [int(c // f) for c in channels]
+        self.out_channels = 3
+        self.latent_dimensions: int = config["latent_dimensions"]
+        self.starting_resolution: Tuple[int, int] = config["starting_resolution"]
+        self.compute_dead_branch = compute_dead_branch
+        L = self.latent_dimensions
+        self.style_mapping = StyleMapping(latent_dimensions=L, depth=config["depth_style_mapping"])
+        self.constant_input_1 = ConstantInput(channel=ch[0], size=self.starting_resolution)
+        self.constant_input_2 = ConstantInput(channel=ch[0], size=self.starting_resolution)
+        self.starting_convolution_1 = StyledConv2d(ch[0], ch[0], (3, 3), L, upsampling=False, demodulate=True)
+        self.starting_convolution_2 = StyledConv2d(ch[0], ch[0], (3, 3), L, upsampling=False, demodulate=True,
+                                                   modulation_mapping=False)
+        self.starting_output_block_1 = OutputBlock(ch[0], L, self.out_channels, upsampling=False)
+        self.starting_output_block_2 = OutputBlock(ch[0], L, self.out_channels, upsampling=False,
+                                                   modulation_mapping=False)
+        self.main_convolutions_1 = nn.ModuleList()
+        self.output_blocks_1 = nn.ModuleList()
+        self.main_convolutions_2 = nn.ModuleList()
+        self.output_blocks_2 = nn.ModuleList()
+        for i in range(len(ch) - 1):
+            self.main_convolutions_1.append(StyledConv2d(ch[i], ch[i + 1], (2, 2), L, upsampling=True))
+            self.main_convolutions_1.append(StyledConv2d(ch[i + 1], ch[i + 1], (3, 3), L, upsampling=False))
+            self.output_blocks_1.append(OutputBlock(ch[i + 1], L, self.out_channels, upsampling=True))
+            self.main_convolutions_2.append(StyledConv2d(ch[i], ch[i + 1], (2, 2), L, upsampling=True,
+                                                         modulation_mapping=False))
+            self.main_convolutions_2.append(StyledConv2d(ch[i + 1], ch[i + 1], (3, 3), L, upsampling=False,
+                                                         modulation_mapping=False))
+            self.output_blocks_2.append(OutputBlock(ch[i + 1], L, self.out_channels, upsampling=True,
+                                                    modulation_mapping=False))
+        self.noises = nn.Module()
+        r0 = self.starting_resolution
+        self.noises.register_buffer("noise_start", torch.randn(1, 1, r0[0], r0[1]))
+        for i in range(len(ch) - 1):
+            self.noises.register_buffer("noise_{}".format(2 * i), torch.randn(1, 1, 2 ** (i + 3), 2 ** (i + 3)))
+            self.noises.register_buffer("noise_{}".format(2 * i + 1), torch.randn(1, 1, 2 ** (i + 3), 2 ** (i + 3)))
+
+    def get_parameters(self, lr_main: float = 1e-03, lr_style: float = 1e-05) -> Iterable:
+        """Parameter groups of the reference (:97-112): everything at lr_main, the mapping network at lr_style."""
+        main = [self.constant_input_1, self.starting_convolution_1, self.starting_output_block_1,
+                self.main_convolutions_1, self.output_blocks_1, self.constant_input_2,
+                self.starting_convolution_2, self.starting_output_block_2, self.main_convolutions_2,
+                self.output_blocks_2]
+        groups = [{"params": m.parameters(), "lr": lr_main} for m in main]
+        groups.append({"params": self.style_mapping.parameters(), "lr": lr_style})
+        return groups
+
+    def _latent(self, input, input_is_latent: bool, inject_index: Optional[int]) -> torch.Tensor:
+        n_latent = len(self.main_convolutions_1) + 2
+        if not input_is_latent:
+            if isinstance(input, list):
+                styles = [self.style_mapping(z) for z in input]
+                if inject_index is None:
+                    inject_index = np.random.randint(1, n_latent - 1)
+                return torch.cat((styles[0].unsqueeze(1).repeat(1, inject_index, 1),
+                                  styles[1].unsqueeze(1).repeat(1, n_latent - inject_index, 1)), dim=1)
+            return self.style_mapping(input).unsqueeze(1).repeat(1, n_latent, 1)
+        if input.ndim < 3:
+            return input.unsqueeze(1).repeat(1, n_latent, 1)
+        if input.shape[1] != n_latent:
+            assert input.shape[1] == 0
+            return input.repeat(1, n_latent, 1)
+        return input
+
+    def forward(self, input: Union[List[torch.Tensor], torch.Tensor], return_main_style_vectors: bool = False,
+                noise: Optional[List[torch.Tensor]] = None, randomize_noise: bool = True,
+                inject_index: Optional[int] = None, input_is_latent: bool = False,
+                return_path_length_grads: bool = False):
+        n_main = len(self.main_convolutions_1)
+        if noise is None:
+            if randomize_noise:
+                noise_start, noise = None, [None] * n_main
+            else:
+                noise_start = self.noises.noise_start
+                noise = [getattr(self.noises, "noise_{}".format(i)) for i in range(n_main)]
+        else:
+            noise_start, noise = noise[0], noise[1:]
+        latent = self._latent(input, input_is_latent, inject_index)
+        dead = self.compute_dead_branch
+
+        out_1 = self.constant_input_1(latent)
+        out_2 = self.constant_input_2(latent)
+        out_1, style = self.starting_convolution_1(out_1, latent[:, 0], noise=noise_start)
+        out_2 = self.starting_convolution_2(out_2, style, noise=noise_start)
+        skip_1, style = self.starting_output_block_1(out_1, latent[:, 1])
+        skip_2 = self.starting_output_block_2(out_2, style)
+        for i in range(n_main // 2):
+            out_1, style = self.main_convolutions_1[2 * i](out_1, latent[:, 2 * i + 1], noise=noise[2 * i])
+            if dead:
+                out_2 = self.main_convolutions_2[2 * i](out_2, style, noise=noise[2 * i])
+            out_1, style = self.main_convolutions_1[2 * i + 1](out_1, latent[:, 2 * i + 2], noise=noise[2 * i + 1])
+            if dead:
+                out_2 = self.main_convolutions_2[2 * i + 1](out_2, style, noise=noise[2 * i + 1])
+            skip_1, style = self.output_blocks_1[i](out_1, latent[:, 2 * i + 3], skip=skip_1)
+            skip_2 = self.output_blocks_2[i](out_1, style, skip=skip_2)     # branch-1 features (reference :189)
+        image = torch.stack([skip_1, skip_2], dim=1)
+        if return_path_length_grads:
+            pl_noise = torch.randn(image.shape, device=image.device, dtype=torch.float32, requires_grad=True) \
+                / math.sqrt(image.shape[2] * image.shape[3] * image.shape[4])
+            return autograd.grad(outputs=(image * pl_noise).sum(), inputs=latent, create_graph=True,
+                                 retain_graph=True, only_inputs=True)[0]
+        if return_main_style_vectors:
+            return image, latent
+        return image

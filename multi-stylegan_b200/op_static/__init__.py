@@ -1,0 +1,5 @@
+"""Drop-in for multi_stylegan/op_static/__init__.py:1-2 (same exported names)."""
+from .fused_act import FusedLeakyReLU, fused_leaky_relu
+from .upfirdn2d import upfirdn2d
+
+__all__ = ["FusedLeakyReLU", "fused_leaky_relu", "upfirdn2d"]

@@ -1,0 +1,154 @@
+"""U-Net discriminator (encoder/decoder of residual + non-local blocks, scalar and per-pixel heads) with
+the reference's module tree and state_dict names (multi_stylegan/u_net_2d_discriminator.py:14-381).
+Convolutions, blurs, upsampling and activations run on this package's sm_100a kernels; the 4096x1024
+attention of the non-local block keeps torch.bmm / softmax / max_pool2d as in the reference (:370-380).
+The FFT input option relied on torch.rfft, which no longer exists; `fft: True` raises."""
+import math
+from typing import Any, Dict, List, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import equalized_layer
+from .multi_stylegan_generator import _fir_kernel
+from .op_static import FusedLeakyReLU, upfirdn2d
+
+
+class Upsample(nn.Module):
+    def __init__(self, blur_kernel: List[int] = [1, 3, 3, 1], factor: int = 2) -> None:
+        super().__init__()
+        self.factor = factor
+        kernel = _fir_kernel(blur_kernel)
+        self.register_buffer("kernel", kernel)
+        p = kernel.shape[0] - factor
+        self.padding = ((p + 1) // 2 + factor - 1, p // 2)
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        return upfirdn2d(input, self.kernel, up=self.factor, pad=self.padding)
+
+
+class Blur(nn.Module):
+    def __init__(self, kernel: List[int] = [1, 3, 3, 1], sampling_factor: int = 1, sampling_factor_padding: int = 2,
+                 kernel_size: int = 3) -> None:
+        super().__init__()
+        p = (len(kernel) - sampling_factor_padding) + (kernel_size - 1)
+        self.padding = ((p + 1) // 2, p // 2)
+        k = _fir_kernel(kernel)
+        if sampling_factor > 1:
+            k = k * (sampling_factor ** 2)
+        self.register_buffer("kernel", k)
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        return upfirdn2d(input, self.kernel, pad=self.padding)
+
+
+class MinibatchStdDev(nn.Module):
+    """One extra channel holding the mean over (c,h,w) of the per-position batch std — reference :189-217."""
+
+    def __init__(self, alpha: float = 1e-8) -> None:
+        super().__init__()
+        self.alpha = alpha
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        centred = input - input.mean(dim=0, keepdim=True)
+        std = torch.sqrt((centred ** 2).mean(dim=0).clamp(min=self.alpha)).mean().view(1, 1, 1)
+        return torch.cat((input, std.repeat(input.shape[0], 1, input.shape[2], input.shape[3])), 1)
+
+
+class ResNetBlock(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int, mini_batch_std_dev: bool = False) -> None:
+        super().__init__()
+        self.mini_batch_std_dev = MinibatchStdDev() if mini_batch_std_dev else nn.Identity()
+        self.main_mapping = nn.Sequential(
+            equalized_layer.EqualizedConv2d(in_channels + 1 if mini_batch_std_dev else in_channels, out_channels,
+                                            kernel_size=(3, 3), stride=(1, 1), padding=(1, 1), bias=False),
+            FusedLeakyReLU(out_channels),
+            equalized_layer.EqualizedConv2d(out_channels, out_channels, kernel_size=(3, 3), stride=(1, 1),
+                                            padding=(1, 1), bias=False),
+            FusedLeakyReLU(out_channels))
+        self.residual_mapping = equalized_layer.EqualizedConv2d(
+            in_channels, out_channels, kernel_size=1, stride=1, padding=0, bias=False) \
+            if in_channels != out_channels else nn.Identity()
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        output = self.main_mapping(self.mini_batch_std_dev(input))
+        return (output + self.residual_mapping(input)) / math.sqrt(2)
+
+
+class NonLocalBlock(nn.Module):
+    def __init__(self, in_channels: int, out_channels: int) -> None:
+        super().__init__()
+        def c1(i, o):
+            return equalized_layer.EqualizedConv2d(i, o, kernel_size=(1, 1), padding=(0, 0), bias=False)
+        self.theta = c1(in_channels, out_channels // 8)
+        self.phi = c1(in_channels, out_channels // 8)
+        self.g = c1(in_channels, out_channels // 2)
+        self.o = c1(out_channels // 2, out_channels)
+        self.residual_mapping = c1(in_channels, out_channels) if in_channels != out_channels else nn.Identity()
+        self.register_parameter(name="gamma", param=nn.Parameter(torch.tensor(0.)))
+
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        batch_size, _, height, width = input.shape
+        theta = self.theta(input).flatten(start_dim=2)                                   # [B, C/8, HW]
+        phi = F.max_pool2d(self.phi(input), kernel_size=(2, 2), stride=(2, 2)).flatten(start_dim=2)
+        g = F.max_pool2d(self.g(input), kernel_size=(2, 2), stride=(2, 2)).flatten(start_dim=2)
+        beta = F.softmax(torch.bmm(theta.transpose(1, 2), phi), -1)                       # [B, HW, HW/4]
+        output = self.o(torch.bmm(g, beta.transpose(1, 2)).view(batch_size, -1, height, width))
+        return (self.gamma * output + self.residual_mapping(input)) / math.sqrt(2)
+
+
+class Discriminator(nn.Module):
+    def __init__(self, config: Dict[str, Any], no_rfp: bool = False, no_gfp: bool = False) -> None:
+        super().__init__()
+        enc: Tuple[Tuple[int, int], ...] = config["encoder_channels"]
+        dec: Tuple[Tuple[int, int], ...] = config["decoder_channels"]
+        self.fft: bool = config["fft"]
+        if self.fft:
+            raise NotImplementedError("fft input relied on torch.rfft (removed from PyTorch); config 'fft' must be False")
+        self.encoder_blocks = nn.ModuleList()
+        for index, (c_in, c_out) in enumerate(enc):
+            if index == 0:
+                self.encoder_blocks.append(ResNetBlock(3 if no_gfp else (6 if no_rfp else 9), c_out))
+            elif index == 2:
+                self.encoder_blocks.append(NonLocalBlock(c_in, c_out))
+            else:
+                self.encoder_blocks.append(ResNetBlock(c_in, c_out, mini_batch_std_dev=index >= (len(enc) - 2)))
+        self.downscale_convolutions = nn.ModuleList(
+            [nn.Sequential(equalized_layer.EqualizedConv2d(c[1], c[1], kernel_size=(3, 3), stride=(2, 2),
+                                                           padding=(0, 0)), Blur()) for c in enc[:-1]])
+        self.classification_head = nn.Sequential(
+            nn.AdaptiveAvgPool2d(output_size=(1, 1)),
+            nn.Flatten(start_dim=1),
+            equalized_layer.EqualizedLinear(enc[-1][-1], 128, bias=False),
+            FusedLeakyReLU(channel=128),
+            equalized_layer.EqualizedLinear(128, 1, bias=False))
+        self.decoder_blocks = nn.ModuleList()
+        for index, (c_in, c_out) in enumerate(dec):
+            self.decoder_blocks.append(NonLocalBlock(c_in, c_out) if index == 1 else ResNetBlock(c_in, c_out))
+        self.transposed_convolutions = nn.ModuleList()
+        for current, past, d in zip(reversed(enc[1:]), reversed(enc[:-1]), dec):
+            self.transposed_convolutions.append(nn.Sequential(
+                Upsample(),
+                equalized_layer.EqualizedConv2d(current[-1], d[0] - past[-1], kernel_size=(1, 1), stride=(1, 1),
+                                                padding=(0, 0), bias=False)))
+        self.final_mapping = nn.Sequential(
+            FusedLeakyReLU(channel=dec[-1][-1]),
+            equalized_layer.EqualizedConv2d(dec[-1][-1], 1, kernel_size=(1, 1), stride=(1, 1), padding=(0, 0),
+                                            bias=False))
+
+    def forward(self, input: torch.Tensor, **kwargs) -> Tuple[torch.Tensor, torch.Tensor]:
+        """input [B, channels, frames, H, W] -> (scalar [B,1], pixel-wise [B,1,1,H,W]); extra kwargs
+        (is_real / is_cut_mix from the train step) are accepted and ignored like the reference (:99)."""
+        x = input.flatten(start_dim=1, end_dim=2)
+        features = []
+        last = len(self.encoder_blocks) - 1
+        for index, block in enumerate(self.encoder_blocks):
+            x = block(x)
+            if index != last:
+                features.append(x)
+                x = self.downscale_convolutions[index](x)
+        classification = self.classification_head(x)
+        for block, up, skip in zip(self.decoder_blocks, self.transposed_convolutions, reversed(features)):
+            x = block(torch.cat([up(x), skip], dim=1))
+        return classification, self.final_mapping(x).unsqueeze(dim=2)

@@ -1,0 +1,46 @@
+"""CPU stand-ins for multi_stylegan_b200._C built from oracle.ops — used ONLY by the `oracle_backend`
+fixture to test host-side logic without a GPU.  The product never imports this."""
+import torch
+
+from oracle import ops
+
+__all__ = ["fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_forward", "conv2d_dgrad", "conv2d_wgrad",
+           "modulate_weights", "noise_bias_act", "affine_warp"]
+
+
+def fused_bias_act(input, bias, refer, act, grad, alpha, scale):
+    return ops.fused_bias_act(input, bias, refer, act, grad, alpha, scale)
+
+
+def fused_bias_act_bwd(grad_output, out, alpha, scale, channels):
+    dx = ops.fused_bias_act(grad_output, grad_output.new_empty(0), out, 3, 1, alpha, scale)
+    dims = [0] + list(range(2, dx.dim()))
+    return dx, dx.sum(dims)
+
+
+def upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1):
+    return ops.upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+
+
+def conv2d_forward(x, w, stride=1, padding=0, alpha=1.0):
+    return ops.conv2d(x, w, stride, padding) * alpha
+
+
+def conv2d_dgrad(dy, w, in_hw, stride=1, padding=0, alpha=1.0):
+    return ops.conv2d_dgrad(dy, w, in_hw, stride, padding) * alpha
+
+
+def conv2d_wgrad(dy, x, khw, stride=1, padding=0, per_sample=False, alpha=1.0):
+    return ops.conv2d_wgrad(dy, x, khw, stride, padding, per_sample) * alpha
+
+
+def modulate_weights(W, s, scale, demodulate):
+    return ops.modulate_weights(W, s, scale, demodulate)
+
+
+def noise_bias_act(x, noise, noise_w, bias, alpha, scale):
+    return ops.noise_bias_act(x, noise, noise_w, bias, alpha, scale)
+
+
+def affine_warp(x, theta, mode=0):
+    return ops.affine_warp(x, theta, mode)

