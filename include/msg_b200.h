@@ -43,6 +43,9 @@ const char* msg_last_error(void);
 uint64_t msg_launch_count(void);
 /* 1 when the tcgen05/TMA implicit-GEMM path is usable on the current device (sm_100) */
 int msg_tensor_core_path_available(void);
+/* Diagnostics (NULL unless the process runs with MSG_B200_TC_DEBUG=1): host-mapped words that CTA 0 of
+ * every tcgen05 kernel fills with progress markers and its first shared-memory operand tiles. */
+const uint32_t* msg_debug_buffer(size_t* words);
 
 /* -------------------------------------------------------------------------------------------
  * fused_bias_act  — replaces fused_act_cuda.fused_bias_act

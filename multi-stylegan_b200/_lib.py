@@ -58,6 +58,7 @@ _SIGNATURES = {
     "msg_last_error": (_c.c_char_p, []),
     "msg_launch_count": (_c.c_uint64, []),
     "msg_tensor_core_path_available": (_c.c_int, []),
+    "msg_debug_buffer": (_c.POINTER(_c.c_uint32), [_c.POINTER(_c.c_size_t)]),
     "msg_fused_bias_act": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                       _c.c_double, _c.c_double, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int,
                                       _c.c_void_p]),

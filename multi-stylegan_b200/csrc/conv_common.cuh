@@ -55,6 +55,7 @@ int simt_pixgemm(const PixGemm& g, cudaStream_t st);
 int simt_redgemm(const RedGemm& g, cudaStream_t st);
 
 bool tc_available();
+uint32_t* tc_debug_host(size_t* words);
 bool tc_pixgemm_supported(const PixGemm& g);
 size_t tc_pixgemm_workspace(const PixGemm& g);
 int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -15,6 +15,7 @@
 // elected lane), warps 2..5 = epilogue (TMEM lane quarter = warp & 3).  smem full/empty mbarrier ring.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 #include <mutex>
 
 #include "conv_common.cuh"
@@ -58,6 +59,35 @@ bool tc_available() {
     cached = ok ? 1 : 0;
   }
   return cached == 1;
+}
+
+// Diagnostics: with MSG_B200_TC_DEBUG=1 CTA 0 of every tcgen05 kernel records progress markers and dumps
+// its first A/B shared-memory tiles into host-mapped memory (readable even after a device fault), and
+// barrier waits time out softly instead of trapping.
+constexpr size_t kDbgWords = 1 << 18;
+static uint32_t* g_dbg_host = nullptr;
+static uint32_t* g_dbg_dev = nullptr;
+static uint32_t* tc_debug_buffer() {
+  static int init = 0;
+  if (!init) {
+    init = 1;
+    const char* e = getenv("MSG_B200_TC_DEBUG");
+    if (e && e[0] == '1') {
+      void* h = nullptr;
+      if (cudaHostAlloc(&h, kDbgWords * 4, cudaHostAllocMapped) == cudaSuccess) {
+        memset(h, 0, kDbgWords * 4);
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) { g_dbg_host = (uint32_t*)h; g_dbg_dev = (uint32_t*)d; }
+      }
+      (void)cudaGetLastError();
+    }
+  }
+  return g_dbg_dev;
+}
+uint32_t* tc_debug_host(size_t* words) { tc_debug_buffer(); if (words) *words = kDbgWords; return g_dbg_host; }
+
+__device__ __forceinline__ void dbg_set(uint32_t* dbg, int idx, uint32_t v) {
+  if (dbg) { *reinterpret_cast<volatile uint32_t*>(dbg + idx) = v; __threadfence_system(); }
 }
 
 static uint32_t tc_variant() {
@@ -137,6 +167,7 @@ struct TcPixParams {
   float alpha;
   int w_per_sample;
   uint32_t variant;
+  uint32_t* dbg;
 };
 
 template <int AW, int BN, int STAGES>
@@ -146,8 +177,13 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr int AH = 128 / AW;
   constexpr uint32_t A_BYTES = 128 * 32 * 4;
   constexpr uint32_t B_BYTES = BN * 32 * 4;
-  constexpr uint32_t A_SWZ = (AW == 32) ? SWZ_128B : SWZ_64B;
-  constexpr uint32_t A_ROW = AW * 4;          // one channel row of the atom (= swizzle span)
+  // MN-major TF32 operands have exactly one legal shared-memory layout: 128-byte rows (32 pixels)
+  // swizzled in 32-byte chunks (UMMA SWIZZLE_128B_BASE32B == TMA SWIZZLE_128B_ATOM_32B); its K atom
+  // is 4 rows, so one K=8 MMA spans two K atoms (stride SBO) and M atoms (image rows) are LBO apart.
+  static_assert(AW == 32, "MN-major TF32 needs 32-pixel (128-byte) rows");
+  constexpr uint32_t A_SWZ = SWZ_128B_BASE32B;
+  constexpr uint32_t A_ROW = AW * 4;          // one channel row (= swizzle span)
+  constexpr uint32_t A_KATOM4 = 4 * A_ROW;    // 4 channels = one swizzle K atom
   constexpr uint32_t A_KATOM = 8 * A_ROW;     // 8 channels = one UMMA K step
   constexpr uint32_t A_MATOM = 32 * A_ROW;    // next image row (M atom) inside the box [h][c][w]
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
@@ -189,6 +225,9 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int kiters = p.ntaps * p.cchunks;
+  uint32_t* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg : nullptr;
+  const bool soft = p.dbg != nullptr;
+  if (threadIdx.x == 0) { dbg_set(dbg, 0, 0xC0FFEE01u); dbg_set(dbg, 5, tmem_base); dbg_set(dbg, 6, (uint32_t)kiters); }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -196,35 +235,47 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u);
+        if (!mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u, soft)) { dbg_set(dbg, 4, 0x100u | (it << 12)); break; }
         const int t = it / p.cchunks;
         const int c0 = (it - t * p.cchunks) * 32;
         const uint32_t full = bars + 8 * s;
         mbar_expect_tx(full, A_BYTES + B_BYTES);
         tma_load_4d(sA + s * A_BYTES, &tmA, full, x0 + p.tap_dx[t], c0, y0 + p.tap_dy[t], b);
+        dbg_set(dbg, 1, 2 * it + 1);
         tma_load_4d(sB + s * B_BYTES, &tmB, full, c0, n0, t, bw);
+        dbg_set(dbg, 1, 2 * it + 2);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const bool swapA = p.variant & 1u;
-      const uint32_t a_lbo = swapA ? A_KATOM : A_MATOM;
-      const uint32_t a_sbo = swapA ? A_MATOM : A_KATOM;
+      const uint32_t a_lbo = swapA ? A_KATOM4 : A_MATOM;
+      const uint32_t a_sbo = swapA ? A_MATOM : A_KATOM4;
       const uint32_t b_lbo = (p.variant & 2u) ? 16u : 0u;
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(bars + 8 * s, ph);
+        if (!mbar_wait(bars + 8 * s, ph, soft)) { dbg_set(dbg, 4, 0x200u | (it << 12)); break; }
         tc_fence_after();
+        if (dbg && it == 0) {   // dump the first A and B tiles exactly as TMA laid them out
+          const float* a0 = reinterpret_cast<const float*>(smem_raw + (sA - raw));
+          const float* b0 = reinterpret_cast<const float*>(smem_raw + (sB - raw));
+          for (int i = 0; i < 4096; ++i) dbg[256 + i] = __float_as_uint(a0[i]);
+          for (int i = 0; i < BN * 32; ++i) dbg[256 + 4096 + i] = __float_as_uint(b0[i]);
+          __threadfence_system();
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t ad = make_smem_desc(sA + s * A_BYTES + k * A_KATOM, a_lbo, a_sbo, A_SWZ);
           const uint64_t bd = make_smem_desc(sB + s * B_BYTES + k * 32, b_lbo, 1024, SWZ_128B);
           mma_tf32(tmem_base, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
         }
+        dbg_set(dbg, 2, 2 * it + 1);
         mma_commit(bars + 8 * (STAGES + s));  // smem stage reusable once these MMAs retire
+        dbg_set(dbg, 2, 2 * it + 2);
       }
       mma_commit(acc_full);
+      dbg_set(dbg, 2, 0x80000000u | (uint32_t)kiters);
     }
   } else {
     const int q = warp & 3;
@@ -234,10 +285,14 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool valid = (y < p.PH) && (x < p.PW);
     float* optr = p.out + (int64_t)b * p.out_sb + (int64_t)(y * p.out_sy + p.out_oy) * p.out_pitch +
                   (x * p.out_sx + p.out_ox);
-    mbar_wait(acc_full, 0);
+    const bool acc_ok = mbar_wait(acc_full, 0, soft);
+    if (!acc_ok && threadIdx.x == 64) dbg_set(dbg, 4, 0x300u);
     tc_fence_after();
+    if (threadIdx.x == 64) dbg_set(dbg, 3, 1);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (BN >= 32) {
+    if (!acc_ok) {
+      // drained in debug mode: leave the output untouched
+    } else if (BN >= 32) {
 #pragma unroll 1
       for (int cc = 0; cc < BN; cc += 32) {
         float r[32];
@@ -249,6 +304,7 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (valid && n < p.N) optr[(int64_t)n * p.out_sn] = p.alpha * r[j];
         }
       }
+      if (threadIdx.x == 64) dbg_set(dbg, 3, 2);
     } else {
       float r[16];
       tmem_ld_32x16(tlane, r);
@@ -276,6 +332,7 @@ struct TcRedParams {
   int ctiles;               // number of BN-wide tiles along C
   int Npad, Cpad, splits;
   float* part;              // [splits][BS][ntaps][Npad][Cpad]
+  uint32_t* dbg;
 };
 
 template <int AW, int BN, int STAGES>
@@ -329,6 +386,9 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  uint32_t* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg : nullptr;
+  const bool soft = p.dbg != nullptr;
+  if (threadIdx.x == 0) { dbg_set(dbg, 0, 0xC0FFEE02u); dbg_set(dbg, 5, tmem_base); dbg_set(dbg, 6, (uint32_t)kiters); }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -336,7 +396,7 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u);
+        if (!mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u, soft)) { dbg_set(dbg, 4, 0x100u | (it << 12)); break; }
         const int kk = k_begin + it;
         const int bl = kk / per;
         const int r = kk - bl * per;
@@ -346,6 +406,7 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         mbar_expect_tx(full, A_BYTES + B_BYTES);
         tma_load_4d(sA + s * A_BYTES, &tmG, full, xc * AW, yc * KH, n0, b);
         tma_load_4d(sB + s * B_BYTES, &tmI, full, xc * AW + dx, yc * KH + dy, c0, b);
+        dbg_set(dbg, 1, 2 * it + 2);
       }
     }
   } else if (warp == 1) {
@@ -353,25 +414,36 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(bars + 8 * s, ph);
+        if (!mbar_wait(bars + 8 * s, ph, soft)) { dbg_set(dbg, 4, 0x200u | (it << 12)); break; }
         tc_fence_after();
+        if (dbg && it == 0) {
+          const float* a0 = reinterpret_cast<const float*>(smem_raw + (sA - raw));
+          const float* b0 = reinterpret_cast<const float*>(smem_raw + (sB - raw));
+          for (int i = 0; i < 4096; ++i) dbg[256 + i] = __float_as_uint(a0[i]);
+          for (int i = 0; i < BN * 32; ++i) dbg[256 + 4096 + i] = __float_as_uint(b0[i]);
+          __threadfence_system();
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t ad = make_smem_desc(sA + s * A_BYTES + k * 32, 0, 1024, SWZ_128B);
           const uint64_t bd = make_smem_desc(sB + s * B_BYTES + k * 32, 0, 1024, SWZ_128B);
           mma_tf32(tmem_base, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
         }
+        dbg_set(dbg, 2, 2 * it + 1);
         mma_commit(bars + 8 * (STAGES + s));
+        dbg_set(dbg, 2, 2 * it + 2);
       }
       mma_commit(acc_full);
+      dbg_set(dbg, 2, 0x80000000u | (uint32_t)kiters);
     }
   } else {
     const int q = warp & 3;
     const int n = q * 32 + lane;
     float* prow = p.part + ((((int64_t)split * gridDim.y + blockIdx.y) * p.Npad) + n0 + n) * p.Cpad + c0;
     if (kiters > 0) {
-      mbar_wait(acc_full, 0);
+      if (!mbar_wait(acc_full, 0, soft) && threadIdx.x == 64) dbg_set(dbg, 4, 0x300u);
       tc_fence_after();
+      if (threadIdx.x == 64) dbg_set(dbg, 3, 1);
     }
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     if (BN >= 32) {
@@ -459,7 +531,7 @@ bool tc_pixgemm_supported(const PixGemm& g) {
   if (!tc_available()) return false;
   if (g.ntaps <= 0 || g.ntaps > kMaxTaps || g.Cr <= 0 || g.N <= 0 || g.B <= 0) return false;
   if (g.in_sy != 1 || g.in_sx != 1) return false;
-  if (g.PW < 16 || g.PH < 1 || g.IW < 16) return false;
+  if (g.PW < 32 || g.PH < 1 || g.IW < 32) return false;   // 32-pixel M atoms (see kernel)
   if (!al16(g.in) || (g.in_pitch & 3) || (g.in_sc & 3) || (g.in_sb & 3)) return false;
   if (g.B > 65535) return false;
   return true;
@@ -509,14 +581,14 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     MSG_CHECK_LAUNCH("conv weight transform");
   }
 
-  const int AW = g.PW >= 32 ? 32 : 16;
+  const int AW = 32;
   const int AH = 128 / AW;
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[4] = {(uint64_t)g.IW, (uint64_t)g.Cr, (uint64_t)g.IH, (uint64_t)g.B};
     const uint64_t strides[3] = {(uint64_t)g.in_sc * 4, (uint64_t)g.in_pitch * 4, (uint64_t)g.in_sb * 4};
     const uint32_t box[4] = {(uint32_t)AW, 32, (uint32_t)AH, 1};
-    int rc = make_tmap(&tmA, g.in, dims, strides, box, AW == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    int rc = make_tmap(&tmA, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   {
@@ -534,13 +606,12 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int tiles_y = (int)ceil_div(g.PH, AH);
   p.out = g.out; p.out_sb = g.out_sb; p.out_sn = g.out_sn; p.out_pitch = g.out_pitch;
   p.out_sy = g.out_sy; p.out_sx = g.out_sx; p.out_oy = g.out_oy; p.out_ox = g.out_ox;
-  p.alpha = g.alpha; p.w_per_sample = g.w_sb != 0; p.variant = tc_variant();
+  p.alpha = g.alpha; p.w_per_sample = g.w_sb != 0; p.variant = tc_variant(); p.dbg = tc_debug_buffer();
   dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)(Npad / BN), (unsigned)g.B);
   if (grid.y > 65535) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): too many N tiles");
 
 #define PIX_CASE(AW_, BN_) if (AW == AW_ && BN == BN_) return launch_pix<AW_, BN_>(tmA, tmB, p, grid, st)
   PIX_CASE(32, 256); PIX_CASE(32, 128); PIX_CASE(32, 64); PIX_CASE(32, 32); PIX_CASE(32, 16);
-  PIX_CASE(16, 256); PIX_CASE(16, 128); PIX_CASE(16, 64); PIX_CASE(16, 32); PIX_CASE(16, 16);
 #undef PIX_CASE
   return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): no kernel for AW=%d BN=%d", AW, BN);
 }
@@ -631,7 +702,7 @@ int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.B = g.B; p.per_sample = g.dw_sb != 0;
   p.chunks_x = pl.chunks_x; p.chunks_y = pl.chunks_y;
   p.ctiles = pl.Cpad / pl.BN;
-  p.Npad = pl.Npad; p.Cpad = pl.Cpad; p.splits = pl.splits; p.part = part;
+  p.Npad = pl.Npad; p.Cpad = pl.Cpad; p.splits = pl.splits; p.part = part; p.dbg = tc_debug_buffer();
   dim3 grid((unsigned)((pl.Npad / 128) * p.ctiles), (unsigned)(g.ntaps * pl.BS), (unsigned)pl.splits);
   int rc = MSG_ERR_UNSUPPORTED;
   const int AW = pl.AW, BN = pl.BN;

@@ -121,6 +121,7 @@ extern "C" int msg_abi_version(void) { return MSG_B200_ABI_VERSION; }
 extern "C" const char* msg_last_error(void) { return g_last_error; }
 extern "C" uint64_t msg_launch_count(void) { return g_launch_count.load(); }
 extern "C" int msg_tensor_core_path_available(void) { return tc_available() ? 1 : 0; }
+extern "C" const uint32_t* msg_debug_buffer(size_t* words) { return tc_debug_host(words); }
 
 extern "C" int msg_modulate_weights(float* w_mod, float* demod_out, const float* W, const float* s, int B, int O,
                                     int C, int taps, float scale, int demodulate, msg_stream_t stream) {

@@ -37,15 +37,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a broken pipeline traps (sticky CUDA error on the host) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Bounded wait: a broken pipeline never hangs the GPU.  Returns false on timeout when `soft` (debug
+// mode: the caller records where it stalled and drains), otherwise traps (sticky CUDA error, loud).
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, bool soft = false) {
+  if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
+  const long long limit = soft ? 400000000LL : 4000000000LL;   // ~0.2 s / ~2 s at 2 GHz
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+    if (clock64() - t0 > limit) {
+      if (soft) return false;
       asm volatile("trap;");
     }
   }
+  return true;
 }
 
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -128,7 +132,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
 }
 
 // ---- descriptors ----------------------------------------------------------------------------------
-enum : uint32_t { SWZ_NONE = 0, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6 };
+enum : uint32_t { SWZ_NONE = 0, SWZ_128B_BASE32B = 1, SWZ_128B = 2, SWZ_64B = 4, SWZ_32B = 6 };
 
 // Shared-memory matrix descriptor (64 bit):
 //   [0,14)  start address >> 4        [16,30) leading-dim byte offset >> 4

@@ -1,0 +1,53 @@
+"""GPU: module- and step-level parity of the product (real kernels) with the reference fixtures."""
+import pytest
+import torch
+
+from tests.conftest import load_golden, rel_err
+from tests import test_host_logic as H
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = 1e-2     # TF32 tensor-core convs (north star); the fp32 CUDA-core engine is checked at 1e-4
+
+
+@pytest.fixture(params=["auto", "simt"])
+def engine(request, built_library):
+    from multi_stylegan_b200 import _C, _lib
+    old = _C.conv_flags
+    _C.conv_flags = _lib.CONV_AUTO if request.param == "auto" else _lib.CONV_FORCE_SIMT
+    yield request.param
+    _C.conv_flags = old
+
+
+def tol_for(engine):
+    return TOL if engine == "auto" else 1e-4
+
+
+def test_dual_style_block(engine):
+    for c in load_golden("dual_style_block.pt"):
+        H.check_block(c, DEV, tol_for(engine))
+
+
+def test_generator_forward_backward_path_length(engine):
+    g = load_golden("generator.pt")
+    net = H.check_generator(g, DEV, tol_for(engine), dead=False)
+    assert H.check_path_length(g, net, DEV, tol_for(engine)) < 10 * tol_for(engine)
+
+
+def test_generator_dead_branch_is_unobservable(built_library):
+    import multi_stylegan_b200.multi_stylegan_generator as G_mod
+    g = load_golden("generator.pt")
+    a = G_mod.Generator(g["config"], compute_dead_branch=True).to(DEV)
+    b = G_mod.Generator(g["config"], compute_dead_branch=False).to(DEV)
+    a.load_state_dict(g["state_dict"]), b.load_state_dict(g["state_dict"])
+    z = [t.to(DEV) for t in g["z"]]
+    noise = [t.to(DEV) for t in g["noise"]]
+    with torch.no_grad():
+        assert torch.equal(a(z, noise=noise, inject_index=3), b(z, noise=noise, inject_index=3))
+
+
+def test_discriminator_forward_backward_r1(engine):
+    g = load_golden("discriminator.pt")
+    net = H.check_discriminator(g, DEV, tol_for(engine))
+    err, worst = H.check_r1(g, net, DEV)
+    assert err < tol_for(engine) and worst < 20 * tol_for(engine)

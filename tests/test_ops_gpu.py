@@ -1,0 +1,171 @@
+"""GPU: fused_bias_act and upfirdn2d kernels, through the C-ABI, against the CPU oracle, the reference
+fixtures, and size-independent properties at BASELINE sizes.  Tolerance 1e-4 relative (north star)."""
+import pytest
+import torch
+
+from oracle import ops
+from tests.conftest import load_golden, rel_err
+from tests.test_host_logic import check_fir_autograd_case, check_lrelu_case
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_library_loaded_and_counts_launches(built_library):
+    from multi_stylegan_b200 import _C
+    n0 = _C.launch_count()
+    x = torch.randn(4, 8, 16, 16, device=dev())
+    _C.fused_bias_act(x, torch.zeros(8, device=dev()), x.new_empty(0), 3, 0, 0.2, 1.0)
+    assert _C.launch_count() == n0 + 1
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 6, 7), (3, 4), (2, 3, 40, 40), (2, 16, 64, 64), (1, 3, 33, 31), (0, 4, 8, 8)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_fused_bias_act_all_modes(built_library, shape, dtype):
+    from multi_stylegan_b200 import _C
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(shape, generator=g, dtype=dtype)
+    b = torch.randn(shape[1], generator=g, dtype=dtype)
+    ref = torch.randn(shape, generator=g, dtype=dtype)
+    e = torch.empty(0, dtype=dtype)
+    for act, grad in [(3, 0), (3, 1), (3, 2), (1, 0), (1, 1), (1, 2)]:
+        for bias in (b, e):
+            r = ref if grad == 1 else e
+            want = ops.fused_bias_act(x, bias, r, act, grad, 0.2, 1.5)
+            got = _C.fused_bias_act(x.to(dev()), bias.to(dev()), r.to(dev()), act, grad, 0.2, 1.5)
+            assert got.shape == want.shape and got.dtype == dtype
+            if x.numel():
+                assert rel_err(got, want) < 1e-6, (act, grad, bias.numel())
+
+
+def test_fused_bias_act_non_contiguous_input(built_library):
+    from multi_stylegan_b200 import _C
+    x = torch.randn(2, 6, 8, 4).permute(0, 3, 1, 2)       # [2,4,6,8] non-contiguous
+    b = torch.randn(4)
+    want = ops.fused_bias_act(x.contiguous(), b, torch.empty(0), 3, 0, 0.2, 1.0)
+    got = _C.fused_bias_act(x.to(dev()), b.to(dev()), torch.empty(0, device=dev()), 3, 0, 0.2, 1.0)
+    assert got.is_contiguous() and rel_err(got, want) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 6, 7), (3, 4), (2, 3, 40, 40), (4, 32, 64, 64)])
+def test_fused_bias_act_bwd_fused_reduction(built_library, shape):
+    from multi_stylegan_b200 import _C
+    g = torch.Generator().manual_seed(1)
+    go = torch.randn(shape, generator=g)
+    out = torch.randn(shape, generator=g)
+    dx = ops.fused_bias_act(go, torch.empty(0), out, 3, 1, 0.2, 1.0)
+    db = dx.sum([0] + list(range(2, dx.dim())))
+    gdx, gdb = _C.fused_bias_act_bwd(go.to(dev()), out.to(dev()), 0.2, 1.0, shape[1])
+    assert rel_err(gdx, dx) < 1e-6 and rel_err(gdb, db) < 1e-5
+    # deterministic: bit-identical on a second run
+    gdx2, gdb2 = _C.fused_bias_act_bwd(go.to(dev()), out.to(dev()), 0.2, 1.0, shape[1])
+    assert torch.equal(gdb, gdb2)
+
+
+def test_lrelu_reference_fixtures(built_library):
+    for c in load_golden("ops.pt")["lrelu"]:
+        check_lrelu_case(c, dev(), TOL)
+
+
+def test_upfirdn2d_reference_fixtures(built_library):
+    from multi_stylegan_b200 import _C
+    for c in load_golden("ops.pt")["fir"]:
+        y = _C.upfirdn2d(c["x"].to(dev()), c["k"].to(dev()), *c["cfg"])
+        assert y.shape == c["y"].shape, c["cfg"]
+        assert rel_err(y, c["y"]) < TOL, c["cfg"]
+    for c in load_golden("ops.pt")["fir_autograd"]:
+        check_fir_autograd_case(c, dev(), TOL)
+
+
+CFGS = [  # (up, down, px0, px1, py0, py1, kh, kw)
+    (1, 1, 2, 1, 2, 1, 4, 4), (1, 1, 1, 2, 1, 2, 4, 4), (1, 1, 2, 2, 2, 2, 4, 4), (1, 1, 1, 1, 1, 1, 4, 4),
+    (2, 1, 2, 1, 2, 1, 4, 4), (1, 2, 1, 1, 1, 1, 4, 4), (1, 1, 1, 1, 1, 1, 3, 3), (2, 1, 1, 0, 1, 0, 2, 2),
+    (1, 2, 0, 0, 0, 0, 2, 2), (1, 1, -1, 2, 0, -1, 4, 4), (3, 2, 3, 2, 1, 4, 5, 5), (2, 2, 0, 1, 2, 0, 4, 3),
+]
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+@pytest.mark.parametrize("hw", [(4, 4), (8, 8), (17, 23), (64, 64), (127, 127), (130, 260)])
+def test_upfirdn2d_vs_oracle(built_library, cfg, hw):
+    from multi_stylegan_b200 import _C
+    up, down, px0, px1, py0, py1, kh, kw = cfg
+    h, w = hw
+    if h * up + py0 + py1 < kh or w * up + px0 + px1 < kw:
+        pytest.skip("kernel larger than padded input")
+    g = torch.Generator().manual_seed(h * 1000 + w)
+    x = torch.randn(3, h, w, 1, generator=g)
+    k = torch.randn(kh, kw, generator=g)
+    want = ops.upfirdn2d(x, k, up, up, down, down, px0, px1, py0, py1)
+    got = _C.upfirdn2d(x.to(dev()), k.to(dev()), up, up, down, down, px0, px1, py0, py1)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < TOL
+
+
+def test_upfirdn2d_minor_dim_and_fp64(built_library):
+    from multi_stylegan_b200 import _C
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 9, 7, 3, generator=g, dtype=torch.float64)
+    k = torch.randn(4, 4, generator=g, dtype=torch.float64)
+    want = ops.upfirdn2d(x, k, 2, 2, 1, 1, 2, 1, 2, 1)
+    got = _C.upfirdn2d(x.to(dev()), k.to(dev()), 2, 2, 1, 1, 2, 1, 2, 1)
+    assert rel_err(got, want) < 1e-12
+    assert _C.upfirdn2d(torch.zeros(0, 4, 4, 1, device=dev()), torch.ones(4, 4, device=dev()), 1, 1, 1, 1, 2, 1, 2, 1).shape == (0, 4, 4, 1)
+
+
+def test_upfirdn2d_full_size_properties(built_library):
+    """BASELINE config 2 sizes ([8,512,R,R]); the oracle is too slow there, so check properties:
+    linearity, and <Fx, y> == <x, F^T y> with the adjoint configuration the autograd wrapper uses."""
+    from multi_stylegan_b200.op_static import upfirdn2d
+    torch.manual_seed(0)
+    k = torch.tensor([1., 3., 3., 1.], device=dev())
+    k = (k[None] * k[:, None]) / 64 * 4
+    for (up, down, pad, R) in [(1, 1, (2, 1), 128), (2, 1, (2, 1), 64), (1, 1, (2, 2), 127)]:
+        x = torch.randn(8, 512, R, R, device=dev(), requires_grad=True)
+        y = upfirdn2d(x, k, up=up, down=down, pad=pad)
+        gy = torch.randn_like(y)
+        gx, = torch.autograd.grad(y, x, gy)
+        lhs = (y.double() * gy.double()).sum()
+        rhs = (x.double() * gx.double()).sum()
+        assert abs((lhs - rhs) / lhs).item() < 1e-5
+        x2 = torch.randn_like(x)
+        y2 = upfirdn2d(x2, k, up=up, down=down, pad=pad)
+        y12 = upfirdn2d(x.detach() + 2 * x2, k, up=up, down=down, pad=pad)
+        assert rel_err(y12, y.detach() + 2 * y2) < 1e-5
+        # DC gain: constant input -> interior equals sum(taps) (/up^2 for zero insertion)
+        c = upfirdn2d(torch.ones(1, 1, R, R, device=dev()), k, up=up, down=down, pad=pad)
+        assert abs(c[0, 0, 8, 8].item() - k.sum().item() / (up * up)) < 1e-5
+
+
+def test_small_ops_vs_oracle(built_library):
+    from multi_stylegan_b200 import _C
+    g = torch.Generator().manual_seed(5)
+    W = torch.randn(12, 8, 3, 3, generator=g)
+    s = torch.randn(3, 8, generator=g)
+    for demod in (True, False):
+        want, wd = ops.modulate_weights(W, s, 0.1, demod)
+        got, gd = _C.modulate_weights(W.to(dev()), s.to(dev()), 0.1, demod)
+        assert rel_err(got, want) < 1e-5
+        if demod:
+            assert rel_err(gd, wd) < 1e-5
+    x = torch.randn(3, 5, 16, 16, generator=g)
+    for noise in (torch.randn(3, 1, 16, 16, generator=g), torch.randn(1, 1, 16, 16, generator=g), None):
+        nw = torch.tensor([0.3])
+        b = torch.randn(5, generator=g)
+        want = ops.noise_bias_act(x, noise, nw, b, 0.2, 1.0)
+        got = _C.noise_bias_act(x.to(dev()), None if noise is None else noise.to(dev()), nw.to(dev()), b.to(dev()), 0.2, 1.0)
+        assert rel_err(got, want) < 1e-6
+    import math
+    th = []
+    for a, sc in [(0.0, 1.0), (30.0, 1.2), (-100.0, 0.8)]:
+        c, sn = math.cos(math.radians(a)) / sc, math.sin(math.radians(a)) / sc
+        cx = cy = 7.5
+        th.append([[c, -sn, cx - c * cx + sn * cy], [sn, c, cy - sn * cx - c * cy]])
+    theta = torch.tensor(th)
+    for mode in (0, 1):
+        want = ops.affine_warp(x, theta, mode)
+        got = _C.affine_warp(x.to(dev()), theta.to(dev()), mode)
+        assert rel_err(got, want) < 1e-4
