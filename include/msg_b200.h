@@ -100,6 +100,7 @@ int msg_upfirdn2d(void* out, const void* in, const void* kernel,
  *
  *   x  [B, C, H, W]            w  [O, C, kh, kw]        (w_batch_stride == 0, shared weights)
  *   y  [B, O, OH, OW]          w  [B, O, C, kh, kw]     (w_batch_stride == O*C*kh*kw)
+ *   (logical shapes; activations are stored NCHW or channels-last NHWC, see msg_conv_desc.layout)
  *   OH = (H + 2*pad_h - kh) / stride_h + 1
  *
  * forward : y  = conv(x, w)
@@ -107,13 +108,19 @@ int msg_upfirdn2d(void* out, const void* in, const void* kernel,
  * wgrad   : dw = sum_{b,p} dy (x) x   (per sample when dw_batch_stride != 0)
  * `alpha` scales the result (used to fold the equalised-lr constant); `flags` selects the engine.
  * ------------------------------------------------------------------------------------------- */
+enum {
+  MSG_LAYOUT_NCHW = 0,      /* dense [B,C,H,W]: CUDA-core engine                                   */
+  MSG_LAYOUT_NHWC = 1       /* dense channels-last [B,H,W,C] (torch.channels_last): tcgen05 engine */
+};
+
 typedef struct {
-  int B, C, H, W;          /* input activation                                   */
-  int O, kh, kw;           /* filter                                             */
+  int B, C, H, W;          /* input activation (logical NCHW shape)              */
+  int O, kh, kw;           /* filter, always stored [O, C, kh, kw]               */
   int stride_h, stride_w;
   int pad_h, pad_w;
   int OH, OW;              /* output activation extent (must match the formula)  */
   int64_t w_batch_stride;  /* 0 = shared weights, else elements between samples  */
+  int layout;              /* memory layout of x, y, dx, dy: MSG_LAYOUT_*        */
 } msg_conv_desc;
 
 enum {

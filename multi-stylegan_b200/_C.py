@@ -19,6 +19,9 @@ _DTYPES = {torch.float32: _lib.MSG_F32, torch.float64: _lib.MSG_F64}
 
 # engine selection for the conv primitives (tests flip this to cross-check the two engines)
 conv_flags = _lib.CONV_AUTO
+# The tcgen05 engine works on channels-last activations; with this on (default) the conv primitives
+# convert NCHW inputs to torch.channels_last and return channels-last outputs (same logical shape).
+conv_channels_last = True
 
 
 def _require_cuda(t: torch.Tensor, name: str) -> None:
@@ -42,6 +45,25 @@ def _aligned(t: torch.Tensor) -> torch.Tensor:
     if t.data_ptr() % 16:
         t = t.clone(memory_format=torch.contiguous_format)
     return t
+
+
+def _is_cl(t: torch.Tensor) -> bool:
+    return t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)
+
+
+def _act(t: torch.Tensor):
+    """Activation operand of a conv primitive -> (dense tensor, layout code)."""
+    if conv_channels_last or (_is_cl(t) and not t.is_contiguous()):
+        t = t.contiguous(memory_format=torch.channels_last)
+        if t.data_ptr() % 16:
+            t = t.clone(memory_format=torch.channels_last)
+        return t, _lib.LAYOUT_NHWC
+    return _aligned(t), _lib.LAYOUT_NCHW
+
+
+def _empty_act(shape, layout, device) -> torch.Tensor:
+    fmt = torch.channels_last if layout == _lib.LAYOUT_NHWC else torch.contiguous_format
+    return torch.empty(shape, dtype=torch.float32, device=device, memory_format=fmt)
 
 
 def _dtype_code(t: torch.Tensor, what: str) -> int:
@@ -155,7 +177,7 @@ def _pair(v) -> Tuple[int, int]:
     return int(v), int(v)
 
 
-def _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample) -> ConvDesc:
+def _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout) -> ConvDesc:
     sh, sw = _pair(stride)
     ph, pw = _pair(padding)
     if H + 2 * ph < kh or W + 2 * pw < kw:
@@ -166,6 +188,7 @@ def _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample) -> ConvDesc:
     d.OH = (H + 2 * ph - kh) // sh + 1
     d.OW = (W + 2 * pw - kw) // sw + 1
     d.w_batch_stride = O * C * kh * kw if per_sample else 0
+    d.layout = layout
     return d
 
 
@@ -188,14 +211,14 @@ def _w_dims(w: torch.Tensor, B: int):
 def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha: float = 1.0) -> torch.Tensor:
     _check_f32(x, "x")
     _check_f32(w, "w")
-    x = _aligned(x)
+    x, layout = _act(x)
     w = _aligned(w)
     B, C, H, W = x.shape
     per_sample, O, Cw, kh, kw = _w_dims(w, B)
     if Cw != C:
         raise RuntimeError("conv2d: weight has %d input channels, input has %d" % (Cw, C))
-    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample)
-    y = torch.empty((B, O, d.OH, d.OW), dtype=torch.float32, device=x.device)
+    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout)
+    y = _empty_act((B, O, d.OH, d.OW), layout, x.device)
     L = _lib.lib()
     with torch.cuda.device(x.device):
         nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 0, conv_flags)
@@ -211,17 +234,17 @@ def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Sequence[int], stride
     """dx of conv2d(x, w) given dy; also conv_transpose2d(dy, w) with output size in_hw."""
     _check_f32(dy, "dy")
     _check_f32(w, "w")
-    dy = _aligned(dy)
+    dy, layout = _act(dy)
     w = _aligned(w)
     B, O, OH, OW = dy.shape
     per_sample, Ow, C, kh, kw = _w_dims(w, B)
     if Ow != O:
         raise RuntimeError("conv2d_dgrad: weight has %d output channels, dy has %d" % (Ow, O))
     H, W = int(in_hw[0]), int(in_hw[1])
-    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample)
+    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout)
     if (d.OH, d.OW) != (OH, OW):
         raise RuntimeError("conv2d_dgrad: dy spatial size (%d,%d) inconsistent with input size (%d,%d)" % (OH, OW, H, W))
-    dx = torch.empty((B, C, H, W), dtype=torch.float32, device=dy.device)
+    dx = _empty_act((B, C, H, W), layout, dy.device)
     L = _lib.lib()
     with torch.cuda.device(dy.device):
         nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 1, conv_flags)
@@ -236,14 +259,16 @@ def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, khw: Sequence[int], stride=1
                  per_sample: bool = False, alpha: float = 1.0) -> torch.Tensor:
     _check_f32(dy, "dy")
     _check_f32(x, "x")
-    dy = _aligned(dy)
-    x = _aligned(x)
+    x, layout = _act(x)
+    dy, layout_dy = _act(dy)
+    if layout_dy != layout:
+        dy = dy.contiguous(memory_format=torch.channels_last if layout == _lib.LAYOUT_NHWC else torch.contiguous_format)
     B, C, H, W = x.shape
     if dy.size(0) != B:
         raise RuntimeError("conv2d_wgrad: batch mismatch")
     O = dy.size(1)
     kh, kw = int(khw[0]), int(khw[1])
-    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample)
+    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout)
     if (d.OH, d.OW) != (dy.size(2), dy.size(3)):
         raise RuntimeError("conv2d_wgrad: dy spatial size inconsistent with x")
     shape = (B, O, C, kh, kw) if per_sample else (O, C, kh, kw)

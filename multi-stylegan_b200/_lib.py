@@ -14,6 +14,7 @@ INCLUDE_DIR = os.path.join(REPO_ROOT, "include")
 MSG_OK, MSG_ERR_BAD_ARG, MSG_ERR_UNSUPPORTED, MSG_ERR_CUDA, MSG_ERR_WORKSPACE = 0, 1, 2, 3, 4
 MSG_F32, MSG_F64 = 0, 1
 CONV_AUTO, CONV_FORCE_SIMT, CONV_FORCE_TC = 0, 1, 2
+LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -26,7 +27,7 @@ class ConvDesc(ctypes.Structure):
                 ("stride_h", ctypes.c_int), ("stride_w", ctypes.c_int),
                 ("pad_h", ctypes.c_int), ("pad_w", ctypes.c_int),
                 ("OH", ctypes.c_int), ("OW", ctypes.c_int),
-                ("w_batch_stride", ctypes.c_int64)]
+                ("w_batch_stride", ctypes.c_int64), ("layout", ctypes.c_int)]
 
 
 def sources():

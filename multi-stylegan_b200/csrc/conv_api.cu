@@ -7,8 +7,11 @@
 //                          (this is also the forward of conv_transpose2d, multi_stylegan_generator.py:398)
 //   wgrad   (stride 1)  -> RedGemm on (dy, x)
 //   wgrad   (stride 2)  -> tcgen05: space-to-depth(x), one RedGemm per input phase; CUDA cores: strided
-// Rows whose pitch is not a multiple of 16 bytes (the 127x127 maps after the discriminator's stride-2
-// convs, u_net_2d_discriminator.py:59-63) are re-pitched into the workspace so TMA can address them.
+//
+// The tcgen05 engine runs on channels-last (MSG_LAYOUT_NHWC) activations; channel counts that are not a
+// multiple of 4 (6-channel images, the +1 minibatch-stddev channel, 3-channel tRGB gradients) are
+// zero-padded into the workspace so every TMA stride is a multiple of 16 bytes.  NCHW activations are
+// served by the CUDA-core engine.
 #include "conv_common.cuh"
 
 namespace msg {
@@ -23,64 +26,65 @@ static inline int fdiv(int a, int b) {  // floor division, b > 0
 static inline int r4(int v) { return (v + 3) & ~3; }
 static inline size_t r256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// ---- helper kernels --------------------------------------------------------------------------------
-// xs[b, (py*2+px)*C + c, y2, x2 (pitch W2p)] = x[b, c, 2*y2+py, 2*x2+px]  (zero outside)
+// ---- helper kernels (channels-last) ------------------------------------------------------------------
+// xs[b, y2, x2, ph*C4 + c] = x[b, 2*y2+py, 2*x2+px, c]  (zero outside the image / for c >= C)
 __global__ void __launch_bounds__(256)
-s2d_kernel(float* __restrict__ xs, const float* __restrict__ x, int B, int C, int H, int W, int H2, int W2p) {
-  const int64_t total = (int64_t)B * 4 * C * H2 * W2p;
+s2d_nhwc_kernel(float* __restrict__ xs, const float* __restrict__ x, int B, int C, int C4, int H, int W, int H2,
+                int W2) {
+  const int64_t total = (int64_t)B * H2 * W2 * 4 * C4;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
     int64_t r = i;
-    const int x2 = (int)(r % W2p); r /= W2p;
-    const int y2 = (int)(r % H2); r /= H2;
-    const int c = (int)(r % C); r /= C;
+    const int c = (int)(r % C4); r /= C4;
     const int ph = (int)(r % 4); r /= 4;
+    const int x2 = (int)(r % W2); r /= W2;
+    const int y2 = (int)(r % H2); r /= H2;
     const int b = (int)r;
     const int iy = 2 * y2 + (ph >> 1), ix = 2 * x2 + (ph & 1);
     float v = 0.f;
-    if (iy < H && ix < W) v = __ldg(x + (((int64_t)b * C + c) * H + iy) * W + ix);
+    if (c < C && iy < H && ix < W) v = __ldg(x + (((int64_t)b * H + iy) * W + ix) * C + c);
     xs[i] = v;
   }
 }
 
-// dst[plane, y, x (pitch Wp)] = src[plane, y, x (pitch W)], zero padded columns
+// dst[pixel, Cp] = src[pixel, C], zero padded channels
 __global__ void __launch_bounds__(256)
-repitch_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t planes, int H, int W, int Wp) {
-  const int64_t total = planes * H * Wp;
+chanpad_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t pixels, int C, int Cp) {
+  const int64_t total = pixels * Cp;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
-    const int x = (int)(i % Wp);
-    const int64_t row = i / Wp;
-    dst[i] = x < W ? __ldg(src + row * W + x) : 0.f;
+    const int c = (int)(i % Cp);
+    const int64_t px = i / Cp;
+    dst[i] = c < C ? __ldg(src + px * C + c) : 0.f;
   }
 }
 
-// w2[bw, n, (ph*C + c), a] = w[bw, n, c, ky, kx] with ky = 2*ay + py + pad_h (zero if outside the filter)
+// w2[bw, n, (ph*C4 + c), a] = w[bw, n, c, ky, kx] with ky = 2*ay + py + pad_h (zero outside the filter)
 struct W2Params {
   const float* w;
   int64_t w_sb;     // 0 or O*C*kh*kw
-  int BW, N, C, kh, kw, pad_h, pad_w;
+  int BW, N, C, C4, kh, kw, pad_h, pad_w;
   int ay0, ax0, nay, nax;
 };
 __global__ void __launch_bounds__(256)
 s2d_weight_kernel(float* __restrict__ w2, const W2Params p) {
   const int nt = p.nay * p.nax;
-  const int64_t total = (int64_t)p.BW * p.N * 4 * p.C * nt;
+  const int64_t total = (int64_t)p.BW * p.N * 4 * p.C4 * nt;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (; i < total; i += stride) {
     int64_t r = i;
     const int a = (int)(r % nt); r /= nt;
-    const int c = (int)(r % p.C); r /= p.C;
+    const int c = (int)(r % p.C4); r /= p.C4;
     const int ph = (int)(r % 4); r /= 4;
     const int n = (int)(r % p.N); r /= p.N;
     const int bw = (int)r;
     const int ay = p.ay0 + a / p.nax, ax = p.ax0 + a % p.nax;
     const int ky = 2 * ay + (ph >> 1) + p.pad_h, kx = 2 * ax + (ph & 1) + p.pad_w;
     float v = 0.f;
-    if (ky >= 0 && ky < p.kh && kx >= 0 && kx < p.kw)
+    if (c < p.C && ky >= 0 && ky < p.kh && kx >= 0 && kx < p.kw)
       v = __ldg(p.w + bw * p.w_sb + (((int64_t)n * p.C + c) * p.kh + ky) * p.kw + kx);
     w2[i] = v;
   }
@@ -101,6 +105,8 @@ static int check_desc(const msg_conv_desc* d, const char* who) {
     return fail(MSG_ERR_UNSUPPORTED, "%s: stride (%d,%d) (only 1 or 2, equal)", who, d->stride_h, d->stride_w);
   if (d->pad_h < 0 || d->pad_w < 0) return fail(MSG_ERR_BAD_ARG, "%s: negative padding", who);
   if (d->kh * d->kw > kMaxTaps) return fail(MSG_ERR_UNSUPPORTED, "%s: filter larger than %d taps", who, kMaxTaps);
+  if (d->layout != MSG_LAYOUT_NCHW && d->layout != MSG_LAYOUT_NHWC)
+    return fail(MSG_ERR_BAD_ARG, "%s: unknown layout %d", who, d->layout);
   const int oh = (d->H + 2 * d->pad_h - d->kh) / d->stride_h + 1;
   const int ow = (d->W + 2 * d->pad_w - d->kw) / d->stride_w + 1;
   if (d->H + 2 * d->pad_h < d->kh || d->W + 2 * d->pad_w < d->kw || oh != d->OH || ow != d->OW)
@@ -111,31 +117,28 @@ static int check_desc(const msg_conv_desc* d, const char* who) {
   return MSG_OK;
 }
 
-static inline bool want_tc(int flags) { return flags != MSG_CONV_FORCE_SIMT && tc_available(); }
-static inline bool tma_ok_rows(const void* p, int W) { return (W % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15u) == 0); }
+static inline bool want_tc(const msg_conv_desc* d, int flags) {
+  return flags != MSG_CONV_FORCE_SIMT && d->layout == MSG_LAYOUT_NHWC && tc_available();
+}
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static View4 dense_view(int layout, int C, int H, int W) {
+  View4 v;
+  if (layout == MSG_LAYOUT_NHWC) { v.sb = (int64_t)H * W * C; v.sc = 1; v.sy = (int64_t)W * C; v.sx = C; }
+  else { v.sb = (int64_t)C * H * W; v.sc = (int64_t)H * W; v.sy = W; v.sx = 1; }
+  return v;
+}
+static const float* const kAligned = reinterpret_cast<const float*>(256);   // placeholder for support queries
 
 // ---- plans -----------------------------------------------------------------------------------------
 // A plan is computed identically by the workspace query and by the call.
 struct FwdPlan {
-  bool tc;
-  bool s2d;         // stride-2 lowering
-  bool repitch;     // stride-1 input rows need re-pitching
-  int H2, W2p;      // s2d buffer geometry
+  bool tc, s2d, pad_in;
+  int C4, H2, W2;
   int ay0, ax0, nay, nax;
   size_t off_x, off_w2, off_eng, total;
   PixGemm g;
 };
-
-static void fill_taps_fwd(PixGemm& g, const msg_conv_desc* d) {
-  g.ntaps = d->kh * d->kw;
-  for (int ky = 0; ky < d->kh; ++ky)
-    for (int kx = 0; kx < d->kw; ++kx) {
-      const int t = ky * d->kw + kx;
-      g.tap_dy[t] = ky - d->pad_h;
-      g.tap_dx[t] = kx - d->pad_w;
-      g.tap_wi[t] = t;
-    }
-}
 
 static FwdPlan plan_forward(const msg_conv_desc* d, const float* x, const float* w, float* y, float alpha, int flags) {
   FwdPlan pl{};
@@ -143,63 +146,55 @@ static FwdPlan plan_forward(const msg_conv_desc* d, const float* x, const float*
   const int s = d->stride_h;
   const int64_t taps = (int64_t)d->kh * d->kw;
   g.B = d->B; g.N = d->O; g.PH = d->OH; g.PW = d->OW;
-  g.out = y; g.out_sb = (int64_t)d->O * d->OH * d->OW; g.out_sn = (int64_t)d->OH * d->OW; g.out_pitch = d->OW;
-  g.out_sy = 1; g.out_sx = 1; g.out_oy = 0; g.out_ox = 0; g.alpha = alpha;
-  // direct (CUDA-core capable) formulation
-  g.in = x; g.Cr = d->C; g.IH = d->H; g.IW = d->W;
-  g.in_sb = (int64_t)d->C * d->H * d->W; g.in_sc = (int64_t)d->H * d->W; g.in_pitch = d->W;
-  g.in_sy = s; g.in_sx = s;
+  g.out = y; g.os = dense_view(d->layout, d->O, d->OH, d->OW);
+  g.out_my = 1; g.out_mx = 1; g.out_oy = 0; g.out_ox = 0; g.alpha = alpha;
+  g.in = x; g.Cr = d->C; g.IH = d->H; g.IW = d->W; g.is = dense_view(d->layout, d->C, d->H, d->W);
+  g.my = s; g.mx = s;
   g.w = w; g.w_sb = d->w_batch_stride; g.w_sn = d->C * taps; g.w_sc = taps; g.w_st = 1;
-  fill_taps_fwd(g, d);
+  g.ntaps = (int)taps;
+  for (int ky = 0; ky < d->kh; ++ky)
+    for (int kx = 0; kx < d->kw; ++kx) {
+      const int t = ky * d->kw + kx;
+      g.tap_dy[t] = ky - d->pad_h; g.tap_dx[t] = kx - d->pad_w; g.tap_wi[t] = t;
+    }
   size_t off = 0;
-  if (want_tc(flags)) {
+  pl.C4 = r4(d->C);
+  if (want_tc(d, flags)) {
     if (s == 1) {
       PixGemm t = g;
-      if (!tma_ok_rows(x, d->W)) {
-        pl.repitch = true;
-        const int Wp = r4(d->W);
-        t.in = reinterpret_cast<const float*>(16);  // aligned placeholder for the support query
-        t.in_pitch = Wp; t.in_sc = (int64_t)d->H * Wp; t.in_sb = (int64_t)d->C * d->H * Wp;
-      }
+      pl.pad_in = (d->C % 4 != 0) || !al16(x);
+      if (pl.pad_in) { t.in = kAligned; t.is = dense_view(MSG_LAYOUT_NHWC, pl.C4, d->H, d->W); }
       if (tc_pixgemm_supported(t)) {
         pl.tc = true;
-        if (pl.repitch) {
-          pl.off_x = off;
-          off += r256((size_t)d->B * d->C * d->H * r4(d->W) * sizeof(float));
-        }
+        if (pl.pad_in) { pl.off_x = off; off += r256((size_t)d->B * d->H * d->W * pl.C4 * sizeof(float)); }
         g = t;
       } else {
-        pl.repitch = false;
+        pl.pad_in = false;
       }
     } else {
       // stride 2: u = k - pad = 2a + ph
       pl.ay0 = fdiv(0 - d->pad_h, 2); pl.ax0 = fdiv(0 - d->pad_w, 2);
       pl.nay = fdiv(d->kh - 1 - d->pad_h, 2) - pl.ay0 + 1;
       pl.nax = fdiv(d->kw - 1 - d->pad_w, 2) - pl.ax0 + 1;
-      pl.H2 = (d->H + 1) / 2;
-      const int W2 = (d->W + 1) / 2;
-      pl.W2p = r4(W2);
-      PixGemm t = g;
-      t.in = reinterpret_cast<const float*>(16);
-      t.Cr = 4 * d->C; t.IH = pl.H2; t.IW = W2;
-      t.in_pitch = pl.W2p; t.in_sc = (int64_t)pl.H2 * pl.W2p; t.in_sb = (int64_t)4 * d->C * pl.H2 * pl.W2p;
-      t.in_sy = 1; t.in_sx = 1;
+      pl.H2 = (d->H + 1) / 2; pl.W2 = (d->W + 1) / 2;
       const int nt = pl.nay * pl.nax;
+      PixGemm t = g;
+      t.in = kAligned; t.Cr = 4 * pl.C4; t.IH = pl.H2; t.IW = pl.W2;
+      t.is = dense_view(MSG_LAYOUT_NHWC, 4 * pl.C4, pl.H2, pl.W2);
+      t.my = 1; t.mx = 1;
       t.ntaps = nt;
-      for (int a = 0; a < nt; ++a) {
-        t.tap_dy[a] = pl.ay0 + a / pl.nax;
-        t.tap_dx[a] = pl.ax0 + a % pl.nax;
-        t.tap_wi[a] = a;
+      for (int a = 0; a < nt && a < kMaxTaps; ++a) {
+        t.tap_dy[a] = pl.ay0 + a / pl.nax; t.tap_dx[a] = pl.ax0 + a % pl.nax; t.tap_wi[a] = a;
       }
-      t.w_sn = (int64_t)4 * d->C * nt; t.w_sc = nt; t.w_st = 1;
-      t.w_sb = d->w_batch_stride ? (int64_t)d->O * 4 * d->C * nt : 0;
+      t.w_sn = (int64_t)4 * pl.C4 * nt; t.w_sc = nt; t.w_st = 1;
+      t.w_sb = d->w_batch_stride ? (int64_t)d->O * 4 * pl.C4 * nt : 0;
       if (nt <= kMaxTaps && tc_pixgemm_supported(t)) {
         pl.tc = true; pl.s2d = true;
         pl.off_x = off;
-        off += r256((size_t)d->B * 4 * d->C * pl.H2 * pl.W2p * sizeof(float));
+        off += r256((size_t)d->B * pl.H2 * pl.W2 * 4 * pl.C4 * sizeof(float));
         pl.off_w2 = off;
         const int64_t BW = d->w_batch_stride ? d->B : 1;
-        off += r256((size_t)BW * d->O * 4 * d->C * nt * sizeof(float));
+        off += r256((size_t)BW * d->O * 4 * pl.C4 * nt * sizeof(float));
         g = t;
       }
     }
@@ -211,11 +206,12 @@ static FwdPlan plan_forward(const msg_conv_desc* d, const float* x, const float*
 }
 
 struct DgradPlan {
-  bool tc, repitch;
+  bool tc, pad_in;
+  int O4;
   int nph;                       // s*s phase problems
   PixGemm g[4];
   bool use_tc[4];
-  size_t off_x, off_eng, total;
+  size_t off_x, off_eng, eng_each, total;
 };
 
 static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float* w, float* dx, float alpha, int flags) {
@@ -223,21 +219,21 @@ static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float
   const int s = d->stride_h;
   const int64_t taps = (int64_t)d->kh * d->kw;
   pl.nph = s * s;
+  pl.O4 = r4(d->O);
   bool any_tc = false;
-  const bool tcw = want_tc(flags);
-  const bool need_repitch = tcw && !tma_ok_rows(dy, d->OW);
+  const bool tcw = want_tc(d, flags);
+  const bool need_pad = tcw && ((d->O % 4 != 0) || !al16(dy));
   size_t eng = 0;
   for (int ph = 0; ph < pl.nph; ++ph) {
     PixGemm& g = pl.g[ph];
     const int py = ph / s, px = ph % s;
     g.B = d->B; g.N = d->C; g.Cr = d->O;
-    g.in = dy; g.IH = d->OH; g.IW = d->OW;
-    g.in_sb = (int64_t)d->O * d->OH * d->OW; g.in_sc = (int64_t)d->OH * d->OW; g.in_pitch = d->OW;
-    g.in_sy = 1; g.in_sx = 1;
+    g.in = dy; g.IH = d->OH; g.IW = d->OW; g.is = dense_view(d->layout, d->O, d->OH, d->OW);
+    g.my = 1; g.mx = 1;
     g.w = w; g.w_sb = d->w_batch_stride; g.w_sn = taps; g.w_sc = d->C * taps; g.w_st = 1;
     g.PH = (d->H - py + s - 1) / s; g.PW = (d->W - px + s - 1) / s;
-    g.out = dx; g.out_sb = (int64_t)d->C * d->H * d->W; g.out_sn = (int64_t)d->H * d->W; g.out_pitch = d->W;
-    g.out_sy = s; g.out_sx = s; g.out_oy = py; g.out_ox = px; g.alpha = alpha;
+    g.out = dx; g.os = dense_view(d->layout, d->C, d->H, d->W);
+    g.out_my = s; g.out_mx = s; g.out_oy = py; g.out_ox = px; g.alpha = alpha;
     g.ntaps = 0;
     for (int ky = 0; ky < d->kh; ++ky) {
       if ((py + d->pad_h - ky) % s != 0) continue;
@@ -252,11 +248,7 @@ static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float
     pl.use_tc[ph] = false;
     if (tcw && g.ntaps > 0 && g.PH > 0 && g.PW > 0) {
       PixGemm t = g;
-      if (need_repitch) {
-        const int Wp = r4(d->OW);
-        t.in = reinterpret_cast<const float*>(16);
-        t.in_pitch = Wp; t.in_sc = (int64_t)d->OH * Wp; t.in_sb = (int64_t)d->O * d->OH * Wp;
-      }
+      if (need_pad) { t.in = kAligned; t.is = dense_view(MSG_LAYOUT_NHWC, pl.O4, d->OH, d->OW); }
       if (tc_pixgemm_supported(t)) {
         pl.use_tc[ph] = true; any_tc = true; g = t;
         const size_t e = tc_pixgemm_workspace(g);
@@ -265,22 +257,21 @@ static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float
     }
   }
   pl.tc = any_tc;
-  pl.repitch = any_tc && need_repitch;
+  pl.pad_in = any_tc && need_pad;
   size_t off = 0;
-  if (pl.repitch) { pl.off_x = off; off += r256((size_t)d->B * d->O * d->OH * r4(d->OW) * sizeof(float)); }
+  if (pl.pad_in) { pl.off_x = off; off += r256((size_t)d->B * d->OH * d->OW * pl.O4 * sizeof(float)); }
   pl.off_eng = off;
-  // the phases run back to back on one stream but each needs its own transformed weights alive until
-  // its kernel has run; give every phase a private slice.
-  off += (size_t)pl.nph * r256(eng);
+  pl.eng_each = r256(eng);
+  // each phase keeps its own transformed weights alive until its kernel has run
+  off += (size_t)pl.nph * pl.eng_each;
   pl.total = off + 256;
   return pl;
 }
 
 struct WgradPlan {
-  bool tc, s2d, repitch_g, repitch_x;
-  int nprob;
+  bool tc, s2d, pad_g, pad_x;
+  int nprob, O4, C4, H2, W2;
   RedGemm g[4];
-  int H2, W2p;
   size_t off_g, off_x, off_eng, eng_each, total;
 };
 
@@ -288,12 +279,12 @@ static WgradPlan plan_wgrad(const msg_conv_desc* d, const float* dy, const float
   WgradPlan pl{};
   const int s = d->stride_h;
   const int64_t taps = (int64_t)d->kh * d->kw;
+  pl.O4 = r4(d->O); pl.C4 = r4(d->C);
   RedGemm base{};
   base.g = dy; base.B = d->B; base.N = d->O; base.PH = d->OH; base.PW = d->OW;
-  base.g_sb = (int64_t)d->O * d->OH * d->OW; base.g_sn = (int64_t)d->OH * d->OW; base.g_pitch = d->OW;
-  base.in = x; base.C = d->C; base.IH = d->H; base.IW = d->W;
-  base.in_sb = (int64_t)d->C * d->H * d->W; base.in_sc = (int64_t)d->H * d->W; base.in_pitch = d->W;
-  base.in_sy = s; base.in_sx = s;
+  base.gs = dense_view(d->layout, d->O, d->OH, d->OW);
+  base.in = x; base.C = d->C; base.IH = d->H; base.IW = d->W; base.is = dense_view(d->layout, d->C, d->H, d->W);
+  base.my = s; base.mx = s;
   base.dw = dw; base.dw_sb = d->w_batch_stride; base.dw_sn = d->C * taps; base.dw_sc = taps; base.dw_st = 1;
   base.alpha = alpha;
   base.ntaps = (int)taps;
@@ -305,38 +296,27 @@ static WgradPlan plan_wgrad(const msg_conv_desc* d, const float* dy, const float
   pl.nprob = 1;
   pl.g[0] = base;
   size_t off = 0;
-  if (want_tc(flags)) {
+  if (want_tc(d, flags)) {
     RedGemm t = base;
-    const bool rg = !tma_ok_rows(dy, d->OW);
-    if (rg) {
-      const int Wp = r4(d->OW);
-      t.g = reinterpret_cast<const float*>(16);
-      t.g_pitch = Wp; t.g_sn = (int64_t)d->OH * Wp; t.g_sb = (int64_t)d->O * d->OH * Wp;
-    }
+    const bool pg = (d->O % 4 != 0) || !al16(dy);
+    if (pg) { t.g = kAligned; t.gs = dense_view(MSG_LAYOUT_NHWC, pl.O4, d->OH, d->OW); }
     if (s == 1) {
-      const bool rx = !tma_ok_rows(x, d->W);
-      if (rx) {
-        const int Wp = r4(d->W);
-        t.in = reinterpret_cast<const float*>(16);
-        t.in_pitch = Wp; t.in_sc = (int64_t)d->H * Wp; t.in_sb = (int64_t)d->C * d->H * Wp;
-      }
+      const bool px_ = (d->C % 4 != 0) || !al16(x);
+      if (px_) { t.in = kAligned; t.is = dense_view(MSG_LAYOUT_NHWC, pl.C4, d->H, d->W); }
       if (tc_redgemm_supported(t)) {
-        pl.tc = true; pl.repitch_g = rg; pl.repitch_x = rx;
+        pl.tc = true; pl.pad_g = pg; pl.pad_x = px_;
         pl.g[0] = t;
       }
     } else {
-      pl.H2 = (d->H + 1) / 2;
-      const int W2 = (d->W + 1) / 2;
-      pl.W2p = r4(W2);
+      pl.H2 = (d->H + 1) / 2; pl.W2 = (d->W + 1) / 2;
       bool ok = true;
       RedGemm ph_g[4];
       for (int ph = 0; ph < 4 && ok; ++ph) {
         RedGemm q = t;
         const int py = ph >> 1, px = ph & 1;
-        q.in = reinterpret_cast<const float*>(16);
-        q.IH = pl.H2; q.IW = W2; q.in_pitch = pl.W2p; q.in_sc = (int64_t)pl.H2 * pl.W2p;
-        q.in_sb = (int64_t)4 * d->C * pl.H2 * pl.W2p;
-        q.in_sy = 1; q.in_sx = 1;
+        q.in = kAligned;
+        q.IH = pl.H2; q.IW = pl.W2; q.is = dense_view(MSG_LAYOUT_NHWC, 4 * pl.C4, pl.H2, pl.W2);
+        q.my = 1; q.mx = 1;
         q.ntaps = 0;
         for (int ky = 0; ky < d->kh; ++ky) {
           const int u = ky - d->pad_h;
@@ -352,16 +332,16 @@ static WgradPlan plan_wgrad(const msg_conv_desc* d, const float* dy, const float
         if (q.ntaps > 0 && !tc_redgemm_supported(q)) ok = false;
       }
       if (ok) {
-        pl.tc = true; pl.s2d = true; pl.repitch_g = rg;
+        pl.tc = true; pl.s2d = true; pl.pad_g = pg;
         pl.nprob = 4;
         for (int ph = 0; ph < 4; ++ph) pl.g[ph] = ph_g[ph];
       }
     }
   }
   if (pl.tc) {
-    if (pl.repitch_g) { pl.off_g = off; off += r256((size_t)d->B * d->O * d->OH * r4(d->OW) * sizeof(float)); }
-    if (pl.s2d) { pl.off_x = off; off += r256((size_t)d->B * 4 * d->C * pl.H2 * pl.W2p * sizeof(float)); }
-    else if (pl.repitch_x) { pl.off_x = off; off += r256((size_t)d->B * d->C * d->H * r4(d->W) * sizeof(float)); }
+    if (pl.pad_g) { pl.off_g = off; off += r256((size_t)d->B * d->OH * d->OW * pl.O4 * sizeof(float)); }
+    if (pl.s2d) { pl.off_x = off; off += r256((size_t)d->B * pl.H2 * pl.W2 * 4 * pl.C4 * sizeof(float)); }
+    else if (pl.pad_x) { pl.off_x = off; off += r256((size_t)d->B * d->H * d->W * pl.C4 * sizeof(float)); }
     size_t eng = 0;
     for (int i = 0; i < pl.nprob; ++i)
       if (pl.g[i].ntaps > 0) { const size_t e = tc_redgemm_workspace(pl.g[i]); if (e > eng) eng = e; }
@@ -385,12 +365,11 @@ extern "C" int msg_conv2d_last_engine(void) { return g_last_engine; }
 
 extern "C" size_t msg_conv2d_workspace(const msg_conv_desc* d, int which, int flags) {
   if (check_desc(d, "conv2d_workspace")) return 0;
-  // pointers only matter for their 16-byte alignment; assume torch's (always >= 256-byte aligned)
-  // allocations, and re-check at call time.
-  const float* al = reinterpret_cast<const float*>(256);
-  if (which == 0) return plan_forward(d, al, al, const_cast<float*>(al), 1.f, flags).total;
-  if (which == 1) return plan_dgrad(d, al, al, const_cast<float*>(al), 1.f, flags).total;
-  if (which == 2) return plan_wgrad(d, al, al, const_cast<float*>(al), 1.f, flags).total;
+  // pointers only matter for their 16-byte alignment; assume aligned allocations (re-checked at call time)
+  float* al = const_cast<float*>(kAligned);
+  if (which == 0) return plan_forward(d, al, al, al, 1.f, flags).total;
+  if (which == 1) return plan_dgrad(d, al, al, al, 1.f, flags).total;
+  if (which == 2) return plan_wgrad(d, al, al, al, 1.f, flags).total;
   return 0;
 }
 
@@ -403,7 +382,7 @@ extern "C" int msg_conv2d_forward(float* y, const float* x, const float* w, cons
   cudaStream_t st = (cudaStream_t)stream;
   FwdPlan pl = plan_forward(d, x, w, y, alpha, flags);
   if (!pl.tc) {
-    if (flags == MSG_CONV_FORCE_TC) return fail(MSG_ERR_UNSUPPORTED, "conv2d_forward: shape does not tile on tcgen05");
+    if (flags == MSG_CONV_FORCE_TC) return fail(MSG_ERR_UNSUPPORTED, "conv2d_forward: not eligible for tcgen05 (needs NHWC)");
     g_last_engine = 1;
     return simt_pixgemm(pl.g, st);
   }
@@ -413,23 +392,23 @@ extern "C" int msg_conv2d_forward(float* y, const float* x, const float* w, cons
   if (pl.s2d) {
     float* xs = reinterpret_cast<float*>(ws + pl.off_x);
     float* w2 = reinterpret_cast<float*>(ws + pl.off_w2);
-    const int64_t tot = (int64_t)d->B * 4 * d->C * pl.H2 * pl.W2p;
-    s2d_kernel<<<grid_for(tot), 256, 0, st>>>(xs, x, d->B, d->C, d->H, d->W, pl.H2, pl.W2p);
+    const int64_t tot = (int64_t)d->B * pl.H2 * pl.W2 * 4 * pl.C4;
+    s2d_nhwc_kernel<<<grid_for(tot), 256, 0, st>>>(xs, x, d->B, d->C, pl.C4, d->H, d->W, pl.H2, pl.W2);
     MSG_CHECK_LAUNCH("conv s2d");
     W2Params wp{};
     wp.w = w; wp.w_sb = d->w_batch_stride; wp.BW = d->w_batch_stride ? d->B : 1; wp.N = d->O; wp.C = d->C;
-    wp.kh = d->kh; wp.kw = d->kw; wp.pad_h = d->pad_h; wp.pad_w = d->pad_w;
+    wp.C4 = pl.C4; wp.kh = d->kh; wp.kw = d->kw; wp.pad_h = d->pad_h; wp.pad_w = d->pad_w;
     wp.ay0 = pl.ay0; wp.ax0 = pl.ax0; wp.nay = pl.nay; wp.nax = pl.nax;
-    const int64_t wtot = (int64_t)wp.BW * d->O * 4 * d->C * pl.nay * pl.nax;
+    const int64_t wtot = (int64_t)wp.BW * d->O * 4 * pl.C4 * pl.nay * pl.nax;
     s2d_weight_kernel<<<grid_for(wtot), 256, 0, st>>>(w2, wp);
     MSG_CHECK_LAUNCH("conv s2d weights");
     pl.g.in = xs;
     pl.g.w = w2;
-  } else if (pl.repitch) {
+  } else if (pl.pad_in) {
     float* xp = reinterpret_cast<float*>(ws + pl.off_x);
-    const int64_t planes = (int64_t)d->B * d->C;
-    repitch_kernel<<<grid_for(planes * d->H * r4(d->W)), 256, 0, st>>>(xp, x, planes, d->H, d->W, r4(d->W));
-    MSG_CHECK_LAUNCH("conv repitch");
+    const int64_t pixels = (int64_t)d->B * d->H * d->W;
+    chanpad_kernel<<<grid_for(pixels * pl.C4), 256, 0, st>>>(xp, x, pixels, d->C, pl.C4);
+    MSG_CHECK_LAUNCH("conv channel pad");
     pl.g.in = xp;
   }
   g_last_engine = 2;
@@ -445,7 +424,7 @@ extern "C" int msg_conv2d_dgrad(float* dx, const float* dy, const float* w, cons
   cudaStream_t st = (cudaStream_t)stream;
   DgradPlan pl = plan_dgrad(d, dy, w, dx, alpha, flags);
   if (!pl.tc && flags == MSG_CONV_FORCE_TC)
-    return fail(MSG_ERR_UNSUPPORTED, "conv2d_dgrad: shape does not tile on tcgen05");
+    return fail(MSG_ERR_UNSUPPORTED, "conv2d_dgrad: not eligible for tcgen05 (needs NHWC)");
   uint8_t* ws = nullptr;
   if (pl.tc) {
     if (!workspace || workspace_bytes < pl.total)
@@ -453,21 +432,20 @@ extern "C" int msg_conv2d_dgrad(float* dx, const float* dy, const float* w, cons
     ws = ws_base(workspace);
   }
   const float* dyp = dy;
-  if (pl.repitch) {
+  if (pl.pad_in) {
     float* p = reinterpret_cast<float*>(ws + pl.off_x);
-    const int64_t planes = (int64_t)d->B * d->O;
-    repitch_kernel<<<grid_for(planes * d->OH * r4(d->OW)), 256, 0, st>>>(p, dy, planes, d->OH, d->OW, r4(d->OW));
-    MSG_CHECK_LAUNCH("conv repitch");
+    const int64_t pixels = (int64_t)d->B * d->OH * d->OW;
+    chanpad_kernel<<<grid_for(pixels * pl.O4), 256, 0, st>>>(p, dy, pixels, d->O, pl.O4);
+    MSG_CHECK_LAUNCH("conv channel pad");
     dyp = p;
   }
-  const size_t eng_each = pl.tc ? (pl.total - 256 - pl.off_eng) / pl.nph : 0;
   g_last_engine = pl.tc ? 2 : 1;
   for (int ph = 0; ph < pl.nph; ++ph) {
     PixGemm& g = pl.g[ph];
     if (g.PH <= 0 || g.PW <= 0) continue;
     if (pl.use_tc[ph]) {
       g.in = dyp;
-      rc = tc_pixgemm(g, ws + pl.off_eng + ph * eng_each, eng_each, st);
+      rc = tc_pixgemm(g, ws + pl.off_eng + ph * pl.eng_each, pl.eng_each, st);
     } else {
       rc = simt_pixgemm(g, st);   // also zero-fills phases that no filter tap reaches
     }
@@ -490,7 +468,7 @@ extern "C" int msg_conv2d_wgrad(float* dw, const float* dy, const float* x, cons
   if (!dy || !x) return fail(MSG_ERR_BAD_ARG, "conv2d_wgrad: null pointer");
   WgradPlan pl = plan_wgrad(d, dy, x, dw, alpha, flags);
   if (!pl.tc) {
-    if (flags == MSG_CONV_FORCE_TC) return fail(MSG_ERR_UNSUPPORTED, "conv2d_wgrad: shape does not tile on tcgen05");
+    if (flags == MSG_CONV_FORCE_TC) return fail(MSG_ERR_UNSUPPORTED, "conv2d_wgrad: not eligible for tcgen05 (needs NHWC)");
     g_last_engine = 1;
     return simt_redgemm(pl.g[0], st);
   }
@@ -499,24 +477,24 @@ extern "C" int msg_conv2d_wgrad(float* dw, const float* dy, const float* x, cons
   uint8_t* ws = ws_base(workspace);
   const float* gp = dy;
   const float* xp = x;
-  if (pl.repitch_g) {
+  if (pl.pad_g) {
     float* p = reinterpret_cast<float*>(ws + pl.off_g);
-    const int64_t planes = (int64_t)d->B * d->O;
-    repitch_kernel<<<grid_for(planes * d->OH * r4(d->OW)), 256, 0, st>>>(p, dy, planes, d->OH, d->OW, r4(d->OW));
-    MSG_CHECK_LAUNCH("conv repitch");
+    const int64_t pixels = (int64_t)d->B * d->OH * d->OW;
+    chanpad_kernel<<<grid_for(pixels * pl.O4), 256, 0, st>>>(p, dy, pixels, d->O, pl.O4);
+    MSG_CHECK_LAUNCH("conv channel pad");
     gp = p;
   }
   if (pl.s2d) {
     float* xs = reinterpret_cast<float*>(ws + pl.off_x);
-    const int64_t tot = (int64_t)d->B * 4 * d->C * pl.H2 * pl.W2p;
-    s2d_kernel<<<grid_for(tot), 256, 0, st>>>(xs, x, d->B, d->C, d->H, d->W, pl.H2, pl.W2p);
+    const int64_t tot = (int64_t)d->B * pl.H2 * pl.W2 * 4 * pl.C4;
+    s2d_nhwc_kernel<<<grid_for(tot), 256, 0, st>>>(xs, x, d->B, d->C, pl.C4, d->H, d->W, pl.H2, pl.W2);
     MSG_CHECK_LAUNCH("conv s2d");
     xp = xs;
-  } else if (pl.repitch_x) {
+  } else if (pl.pad_x) {
     float* p = reinterpret_cast<float*>(ws + pl.off_x);
-    const int64_t planes = (int64_t)d->B * d->C;
-    repitch_kernel<<<grid_for(planes * d->H * r4(d->W)), 256, 0, st>>>(p, x, planes, d->H, d->W, r4(d->W));
-    MSG_CHECK_LAUNCH("conv repitch");
+    const int64_t pixels = (int64_t)d->B * d->H * d->W;
+    chanpad_kernel<<<grid_for(pixels * pl.C4), 256, 0, st>>>(p, x, pixels, d->C, pl.C4);
+    MSG_CHECK_LAUNCH("conv channel pad");
     xp = p;
   }
   g_last_engine = 2;
@@ -524,8 +502,7 @@ extern "C" int msg_conv2d_wgrad(float* dw, const float* dy, const float* x, cons
     RedGemm& g = pl.g[i];
     if (g.ntaps == 0) continue;
     g.g = gp;
-    if (pl.s2d) g.in = xp + (int64_t)i * d->C * pl.H2 * pl.W2p;  // phase plane block
-    else g.in = xp;
+    g.in = pl.s2d ? xp + (int64_t)i * pl.C4 : xp;     // phase i = channel block i of the s2d tensor
     rc = tc_redgemm(g, ws + pl.off_eng + i * pl.eng_each, pl.eng_each, st);
     if (rc) return rc;
   }

@@ -27,7 +27,7 @@ pixgemm_simt_kernel(const PixGemm g) {
   // B loader
   const int ln = tid & 63, lkb = tid >> 6;
 
-  const float* inb = g.in + (int64_t)b * g.in_sb;
+  const float* inb = g.in + (int64_t)b * g.is.sb;
   const float* wb = g.w + (int64_t)b * g.w_sb;
 
   float acc[4][4];
@@ -37,16 +37,16 @@ pixgemm_simt_kernel(const PixGemm g) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   for (int t = 0; t < g.ntaps; ++t) {
-    const int iy = py * g.in_sy + g.tap_dy[t], ix = px * g.in_sx + g.tap_dx[t];
+    const int iy = py * g.my + g.tap_dy[t], ix = px * g.mx + g.tap_dx[t];
     const bool inb_ok = pvalid && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
-    const int64_t poff = (int64_t)iy * g.in_pitch + ix;
+    const int64_t poff = (int64_t)iy * g.is.sy + (int64_t)ix * g.is.sx;
     const int64_t woff = (int64_t)g.tap_wi[t] * g.w_st;
     for (int c0 = 0; c0 < g.Cr; c0 += SK_) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int k = lk + 4 * i, c = c0 + k;
         float v = 0.f;
-        if (inb_ok && c < g.Cr) v = __ldg(inb + (int64_t)c * g.in_sc + poff);
+        if (inb_ok && c < g.Cr) v = __ldg(inb + (int64_t)c * g.is.sc + poff);
         As[k][lm] = v;
       }
 #pragma unroll
@@ -73,17 +73,17 @@ pixgemm_simt_kernel(const PixGemm g) {
     }
   }
 
-  float* outb = g.out + (int64_t)b * g.out_sb;
+  float* outb = g.out + (int64_t)b * g.os.sb;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int m = m0 + tm + 16 * j;
     if (m >= g.PH * g.PW) continue;
     const int y = m / g.PW, x = m - y * g.PW;
-    const int64_t o = (int64_t)(y * g.out_sy + g.out_oy) * g.out_pitch + (x * g.out_sx + g.out_ox);
+    const int64_t o = (int64_t)(y * g.out_my + g.out_oy) * g.os.sy + (int64_t)(x * g.out_mx + g.out_ox) * g.os.sx;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int n = n0 + tn * 4 + i;
-      if (n < g.N) outb[(int64_t)n * g.out_sn + o] = g.alpha * acc[i][j];
+      if (n < g.N) outb[(int64_t)n * g.os.sc + o] = g.alpha * acc[i][j];
     }
   }
 }
@@ -112,22 +112,22 @@ redgemm_simt_kernel(const RedGemm g) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   for (int b = b_begin; b < b_end; ++b) {
-    const float* gb = g.g + (int64_t)b * g.g_sb;
-    const float* ib = g.in + (int64_t)b * g.in_sb;
+    const float* gb = g.g + (int64_t)b * g.gs.sb;
+    const float* ib = g.in + (int64_t)b * g.is.sb;
     for (int p0 = 0; p0 < npix; p0 += SK_) {
       const int p = p0 + lk;
       const bool pv = p < npix;
       const int y = pv ? p / g.PW : 0, x = pv ? p - y * g.PW : 0;
-      const int iy = y * g.in_sy + dy, ix = x * g.in_sx + dx;
+      const int iy = y * g.my + dy, ix = x * g.mx + dx;
       const bool iv = pv && iy >= 0 && iy < g.IH && ix >= 0 && ix < g.IW;
-      const int64_t goff = (int64_t)y * g.g_pitch + x;
-      const int64_t ioff = (int64_t)iy * g.in_pitch + ix;
+      const int64_t goff = (int64_t)y * g.gs.sy + (int64_t)x * g.gs.sx;
+      const int64_t ioff = (int64_t)iy * g.is.sy + (int64_t)ix * g.is.sx;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int r = lr + 16 * i;
         const int n = n0 + r, c = c0 + r;
-        As[lk][r] = (pv && n < g.N) ? __ldg(gb + (int64_t)n * g.g_sn + goff) : 0.f;
-        Bs[lk][r] = (iv && c < g.C) ? __ldg(ib + (int64_t)c * g.in_sc + ioff) : 0.f;
+        As[lk][r] = (pv && n < g.N) ? __ldg(gb + (int64_t)n * g.gs.sc + goff) : 0.f;
+        Bs[lk][r] = (iv && c < g.C) ? __ldg(ib + (int64_t)c * g.is.sc + ioff) : 0.f;
       }
       __syncthreads();
 #pragma unroll

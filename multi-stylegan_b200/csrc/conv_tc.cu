@@ -1,15 +1,17 @@
-// tcgen05 / TMEM / TMA engine (sm_100a) for the two gather GEMMs of conv_common.cuh.
+// tcgen05 / TMEM / TMA engine (sm_100a) for the two gather GEMMs of conv_common.cuh, on channels-last
+// (NHWC) activations.
 //
 // PixGemm (forward / dgrad / transposed conv):  D[128 pixels, BN channels] += A * B per (tap, 32-channel
-//   chunk).  A is read by TMA straight out of the NCHW activation: box (AW px, 32 ch, 128/AW rows) of
-//   the 4-D view (W, C, H, B) lands in shared memory as an MN-major (pixel-contiguous) UMMA operand
-//   with the hardware 128B (AW=32) or 64B (AW=16) swizzle; a filter tap is just a shifted TMA
-//   coordinate and the conv zero padding is TMA out-of-bounds fill.  B is the pre-transformed,
-//   TF32-rounded weight tile [tap][n][c] (K-major, 128B swizzle).  Accumulator: 128 lanes x BN
-//   columns of TMEM, read back with tcgen05.ld; lanes are pixels, so each column is one coalesced
-//   NCHW row segment.
-// RedGemm (wgrad):  D[128 out-ch, BN in-ch] += dy[n, 32 px] * x[c, 32 px (shifted)]; both operands are
-//   K-major (pixel-contiguous) NCHW tiles, split-K over pixels into a workspace + deterministic reduce.
+//   chunk).  A is read by TMA straight out of the activation: box (32 ch, Wt px, 128/Wt rows) of the
+//   4-D view (C, W, H, B) lands in shared memory as 128 pixel rows of 128 bytes = a K-major UMMA
+//   operand with the hardware 128B swizzle; a filter tap is a shifted TMA coordinate in W/H and the
+//   conv zero padding is TMA out-of-bounds fill.  B is the pre-transformed, TF32-rounded weight tile
+//   [tap][n][c] (K-major, 128B swizzle).  Accumulator: 128 lanes x BN columns of TMEM, read back with
+//   tcgen05.ld; a lane is a pixel, whose BN output channels are contiguous in NHWC (128-bit stores).
+// RedGemm (wgrad):  D[128 out-ch, BN in-ch] += dy[32 px, n]^T * x[32 px (shifted), c]; pixels are K, so
+//   both operands are MN-major: the only legal TF32 layout for that is 128-byte rows swizzled in
+//   32-byte chunks (UMMA SWIZZLE_128B_BASE32B == TMA SWIZZLE_128B_ATOM_32B), one TMA box per group of
+//   32 channels.  Split-K over pixels into a workspace + deterministic reduce.
 //
 // Warp roles (192 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (one
 // elected lane), warps 2..5 = epilogue (TMEM lane quarter = warp & 3).  smem full/empty mbarrier ring.
@@ -155,39 +157,30 @@ tc_weight_transform_kernel(float* __restrict__ wt, const WtParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// PixGemm kernel
+// PixGemm kernel (K-major A from NHWC, K-major B)
 // ------------------------------------------------------------------------------------------------
 struct TcPixParams {
   int ntaps, cchunks;
   int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
-  int PH, PW, N, tiles_x;
+  int PH, PW, N;
+  int wt_log2, tiles_x;        // tile = (1 << wt_log2) x (128 >> wt_log2) pixels
   float* out;
-  int64_t out_sb, out_sn;
-  int out_pitch, out_sy, out_sx, out_oy, out_ox;
+  View4 os;
+  int out_my, out_mx, out_oy, out_ox;
   float alpha;
   int w_per_sample;
-  uint32_t variant;
+  int vec_store;               // NHWC output, 16-byte aligned channel runs
   uint32_t* dbg;
 };
 
-template <int AW, int BN, int STAGES>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const TcPixParams p) {
-  constexpr int AH = 128 / AW;
   constexpr uint32_t A_BYTES = 128 * 32 * 4;
   constexpr uint32_t B_BYTES = BN * 32 * 4;
-  // MN-major TF32 operands have exactly one legal shared-memory layout: 128-byte rows (32 pixels)
-  // swizzled in 32-byte chunks (UMMA SWIZZLE_128B_BASE32B == TMA SWIZZLE_128B_ATOM_32B); its K atom
-  // is 4 rows, so one K=8 MMA spans two K atoms (stride SBO) and M atoms (image rows) are LBO apart.
-  static_assert(AW == 32, "MN-major TF32 needs 32-pixel (128-byte) rows");
-  constexpr uint32_t A_SWZ = SWZ_128B_BASE32B;
-  constexpr uint32_t A_ROW = AW * 4;          // one channel row (= swizzle span)
-  constexpr uint32_t A_KATOM4 = 4 * A_ROW;    // 4 channels = one swizzle K atom
-  constexpr uint32_t A_KATOM = 8 * A_ROW;     // 8 channels = one UMMA K step
-  constexpr uint32_t A_MATOM = 32 * A_ROW;    // next image row (M atom) inside the box [h][c][w]
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  constexpr uint32_t IDESC = make_idesc_tf32(128, BN, /*A MN-major*/ 1, /*B K-major*/ 0);
+  constexpr uint32_t IDESC = make_idesc_tf32(128, BN, 0, 0);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -200,8 +193,9 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Wt = 1 << p.wt_log2, Ht = 128 >> p.wt_log2;
   const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
-  const int y0 = ty * AH, x0 = tx * AW;
+  const int y0 = ty * Ht, x0 = tx * Wt;
   const int n0 = blockIdx.y * BN;
   const int b = blockIdx.z;
 
@@ -240,37 +234,24 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int c0 = (it - t * p.cchunks) * 32;
         const uint32_t full = bars + 8 * s;
         mbar_expect_tx(full, A_BYTES + B_BYTES);
-        tma_load_4d(sA + s * A_BYTES, &tmA, full, x0 + p.tap_dx[t], c0, y0 + p.tap_dy[t], b);
-        dbg_set(dbg, 1, 2 * it + 1);
+        tma_load_4d(sA + s * A_BYTES, &tmA, full, c0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b);
         tma_load_4d(sB + s * B_BYTES, &tmB, full, c0, n0, t, bw);
         dbg_set(dbg, 1, 2 * it + 2);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const bool swapA = p.variant & 1u;
-      const uint32_t a_lbo = swapA ? A_KATOM4 : A_MATOM;
-      const uint32_t a_sbo = swapA ? A_MATOM : A_KATOM4;
-      const uint32_t b_lbo = (p.variant & 2u) ? 16u : 0u;
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         if (!mbar_wait(bars + 8 * s, ph, soft)) { dbg_set(dbg, 4, 0x200u | (it << 12)); break; }
         tc_fence_after();
-        if (dbg && it == 0) {   // dump the first A and B tiles exactly as TMA laid them out
-          const float* a0 = reinterpret_cast<const float*>(smem_raw + (sA - raw));
-          const float* b0 = reinterpret_cast<const float*>(smem_raw + (sB - raw));
-          for (int i = 0; i < 4096; ++i) dbg[256 + i] = __float_as_uint(a0[i]);
-          for (int i = 0; i < BN * 32; ++i) dbg[256 + 4096 + i] = __float_as_uint(b0[i]);
-          __threadfence_system();
-        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = make_smem_desc(sA + s * A_BYTES + k * A_KATOM, a_lbo, a_sbo, A_SWZ);
-          const uint64_t bd = make_smem_desc(sB + s * B_BYTES + k * 32, b_lbo, 1024, SWZ_128B);
+          const uint64_t ad = make_smem_desc(sA + s * A_BYTES + k * 32, 0, 1024, SWZ_128B);
+          const uint64_t bd = make_smem_desc(sB + s * B_BYTES + k * 32, 0, 1024, SWZ_128B);
           mma_tf32(tmem_base, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
         }
-        dbg_set(dbg, 2, 2 * it + 1);
         mma_commit(bars + 8 * (STAGES + s));  // smem stage reusable once these MMAs retire
         dbg_set(dbg, 2, 2 * it + 2);
       }
@@ -280,15 +261,14 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int row = m / AW, col = m - row * AW;
+    const int row = m >> p.wt_log2, col = m & (Wt - 1);
     const int y = y0 + row, x = x0 + col;
     const bool valid = (y < p.PH) && (x < p.PW);
-    float* optr = p.out + (int64_t)b * p.out_sb + (int64_t)(y * p.out_sy + p.out_oy) * p.out_pitch +
-                  (x * p.out_sx + p.out_ox);
+    float* optr = p.out + (int64_t)b * p.os.sb + (int64_t)(y * p.out_my + p.out_oy) * p.os.sy +
+                  (int64_t)(x * p.out_mx + p.out_ox) * p.os.sx;
     const bool acc_ok = mbar_wait(acc_full, 0, soft);
     if (!acc_ok && threadIdx.x == 64) dbg_set(dbg, 4, 0x300u);
     tc_fence_after();
-    if (threadIdx.x == 64) dbg_set(dbg, 3, 1);
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     if (!acc_ok) {
       // drained in debug mode: leave the output untouched
@@ -298,13 +278,23 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float r[32];
         tmem_ld_32x32(tlane + cc, r);
         tmem_ld_wait();
+        const int nb = n0 + cc;
+        if (p.vec_store && nb + 32 <= p.N) {
+          if (valid) {
+            float4* o4 = reinterpret_cast<float4*>(optr + nb);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = n0 + cc + j;
-          if (valid && n < p.N) optr[(int64_t)n * p.out_sn] = p.alpha * r[j];
+            for (int j = 0; j < 8; ++j)
+              o4[j] = make_float4(p.alpha * r[4 * j], p.alpha * r[4 * j + 1], p.alpha * r[4 * j + 2],
+                                  p.alpha * r[4 * j + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            if (valid && n < p.N) optr[(int64_t)n * p.os.sc] = p.alpha * r[j];
+          }
         }
       }
-      if (threadIdx.x == 64) dbg_set(dbg, 3, 2);
     } else {
       float r[16];
       tmem_ld_32x16(tlane, r);
@@ -312,9 +302,10 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int n = n0 + j;
-        if (valid && n < p.N) optr[(int64_t)n * p.out_sn] = p.alpha * r[j];
+        if (valid && n < p.N) optr[(int64_t)n * p.os.sc] = p.alpha * r[j];
       }
     }
+    if (threadIdx.x == 64) dbg_set(dbg, 3, 2);
   }
   tc_fence_before();
   __syncthreads();
@@ -322,28 +313,31 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
-// RedGemm kernel (wgrad): both operands K-major, split-K into `part`.
+// RedGemm kernel (wgrad): both operands MN-major (BASE32B), split-K into `part`.
 // ------------------------------------------------------------------------------------------------
 struct TcRedParams {
   int ntaps;
   int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
   int B, per_sample;
+  int wk_log2;              // K chunk = (1 << wk_log2) x (32 >> wk_log2) pixels
   int chunks_x, chunks_y;
   int ctiles;               // number of BN-wide tiles along C
   int Npad, Cpad, splits;
   float* part;              // [splits][BS][ntaps][Npad][Cpad]
+  uint32_t variant;
   uint32_t* dbg;
 };
 
-template <int AW, int BN, int STAGES>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmI,
                   const TcRedParams p) {
-  constexpr int KH = 32 / AW;
-  constexpr uint32_t A_BYTES = 128 * 32 * 4;
-  constexpr uint32_t B_BYTES = BN * 32 * 4;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  constexpr uint32_t IDESC = make_idesc_tf32(128, BN, 0, 0);
+  static_assert(BN % 32 == 0, "N-major TF32 operand comes in 32-channel atoms");
+  constexpr uint32_t ATOM_BYTES = 32 * 32 * 4;        // 32 pixels x 32 channels
+  constexpr uint32_t A_BYTES = 4 * ATOM_BYTES;        // 128 output channels
+  constexpr uint32_t B_BYTES = (BN / 32) * ATOM_BYTES;
+  constexpr uint32_t TMEM_COLS = BN;
+  constexpr uint32_t IDESC = make_idesc_tf32(128, BN, 1, 1);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -361,6 +355,7 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const int t = blockIdx.y % p.ntaps;
   const int bs = blockIdx.y / p.ntaps;      // sample index when per_sample, else 0
   const int split = blockIdx.z;
+  const int Wk = 1 << p.wk_log2, Hk = 32 >> p.wk_log2;
 
   const int per = p.chunks_x * p.chunks_y;
   const int64_t total = (int64_t)per * (p.per_sample ? 1 : p.B);
@@ -404,32 +399,33 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         const int b = p.per_sample ? bs : bl;
         const uint32_t full = bars + 8 * s;
         mbar_expect_tx(full, A_BYTES + B_BYTES);
-        tma_load_4d(sA + s * A_BYTES, &tmG, full, xc * AW, yc * KH, n0, b);
-        tma_load_4d(sB + s * B_BYTES, &tmI, full, xc * AW + dx, yc * KH + dy, c0, b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          tma_load_4d(sA + s * A_BYTES + j * ATOM_BYTES, &tmG, full, n0 + 32 * j, xc * Wk, yc * Hk, b);
+#pragma unroll
+        for (int j = 0; j < BN / 32; ++j)
+          tma_load_4d(sB + s * B_BYTES + j * ATOM_BYTES, &tmI, full, c0 + 32 * j, xc * Wk + dx, yc * Hk + dy, b);
         dbg_set(dbg, 1, 2 * it + 2);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
+      // MN-major BASE32B: M/N atoms (32 channels) are ATOM_BYTES apart (LBO), K atoms (4 pixel rows of
+      // 128 bytes) 512 bytes apart (SBO); one K=8 MMA covers 2 K atoms = 1024 bytes.
+      const bool swap = p.variant & 1u;
+      const uint32_t lbo = swap ? 512u : ATOM_BYTES;
+      const uint32_t sbo = swap ? ATOM_BYTES : 512u;
       for (int it = 0; it < kiters; ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         if (!mbar_wait(bars + 8 * s, ph, soft)) { dbg_set(dbg, 4, 0x200u | (it << 12)); break; }
         tc_fence_after();
-        if (dbg && it == 0) {
-          const float* a0 = reinterpret_cast<const float*>(smem_raw + (sA - raw));
-          const float* b0 = reinterpret_cast<const float*>(smem_raw + (sB - raw));
-          for (int i = 0; i < 4096; ++i) dbg[256 + i] = __float_as_uint(a0[i]);
-          for (int i = 0; i < BN * 32; ++i) dbg[256 + 4096 + i] = __float_as_uint(b0[i]);
-          __threadfence_system();
-        }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = make_smem_desc(sA + s * A_BYTES + k * 32, 0, 1024, SWZ_128B);
-          const uint64_t bd = make_smem_desc(sB + s * B_BYTES + k * 32, 0, 1024, SWZ_128B);
+          const uint64_t ad = make_smem_desc(sA + s * A_BYTES + k * 1024, lbo, sbo, SWZ_128B_BASE32B);
+          const uint64_t bd = make_smem_desc(sB + s * B_BYTES + k * 1024, lbo, sbo, SWZ_128B_BASE32B);
           mma_tf32(tmem_base, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
         }
-        dbg_set(dbg, 2, 2 * it + 1);
         mma_commit(bars + 8 * (STAGES + s));
         dbg_set(dbg, 2, 2 * it + 2);
       }
@@ -440,40 +436,28 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     const int q = warp & 3;
     const int n = q * 32 + lane;
     float* prow = p.part + ((((int64_t)split * gridDim.y + blockIdx.y) * p.Npad) + n0 + n) * p.Cpad + c0;
+    bool acc_ok = true;
     if (kiters > 0) {
-      if (!mbar_wait(acc_full, 0, soft) && threadIdx.x == 64) dbg_set(dbg, 4, 0x300u);
+      acc_ok = mbar_wait(acc_full, 0, soft);
+      if (!acc_ok && threadIdx.x == 64) dbg_set(dbg, 4, 0x300u);
       tc_fence_after();
-      if (threadIdx.x == 64) dbg_set(dbg, 3, 1);
     }
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (BN >= 32) {
 #pragma unroll 1
-      for (int cc = 0; cc < BN; cc += 32) {
-        float r[32];
-        if (kiters > 0) {
-          tmem_ld_32x32(tlane + cc, r);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(prow + cc + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-      }
-    } else {
-      float r[16];
-      if (kiters > 0) {
-        tmem_ld_32x16(tlane, r);
+    for (int cc = 0; cc < BN; cc += 32) {
+      float r[32];
+      if (kiters > 0 && acc_ok) {
+        tmem_ld_32x32(tlane + cc, r);
         tmem_ld_wait();
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = 0.f;
+        for (int j = 0; j < 32; ++j) r[j] = 0.f;
       }
 #pragma unroll
-      for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<float4*>(prow + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(prow + cc + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
     }
+    if (threadIdx.x == 64) dbg_set(dbg, 3, 2);
   }
   tc_fence_before();
   __syncthreads();
@@ -513,43 +497,43 @@ tc_red_reduce_kernel(const RedReduceParams p) {
 // ------------------------------------------------------------------------------------------------
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-static int pick_bn(int n) {
-  if (n > 128) return 256;
-  if (n > 64) return 128;
-  if (n > 32) return 64;
-  if (n > 16) return 32;
-  return 16;
+static int pick_bn(int n, int min_bn) {
+  int bn = 16;
+  if (n > 128) bn = 256;
+  else if (n > 64) bn = 128;
+  else if (n > 32) bn = 64;
+  else if (n > 16) bn = 32;
+  return bn < min_bn ? min_bn : bn;
 }
-static int stages_for(int bn) {
-  const int per = 16384 + bn * 128;
-  int s = (200 * 1024) / per;
-  return s > 6 ? 6 : s;
+
+static bool view_tma_ok(const void* base, const View4& v) {
+  return al16(base) && v.sc == 1 && (v.sx % 4 == 0) && (v.sy % 4 == 0) && (v.sb % 4 == 0);
 }
 
 bool tc_pixgemm_supported(const PixGemm& g) {
   if (!tc_available()) return false;
-  if (g.ntaps <= 0 || g.ntaps > kMaxTaps || g.Cr <= 0 || g.N <= 0 || g.B <= 0) return false;
-  if (g.in_sy != 1 || g.in_sx != 1) return false;
-  if (g.PW < 32 || g.PH < 1 || g.IW < 32) return false;   // 32-pixel M atoms (see kernel)
-  if (!al16(g.in) || (g.in_pitch & 3) || (g.in_sc & 3) || (g.in_sb & 3)) return false;
-  if (g.B > 65535) return false;
+  if (g.ntaps <= 0 || g.ntaps > kMaxTaps || g.Cr <= 0 || g.N <= 0 || g.B <= 0 || g.B > 65535) return false;
+  if (g.my != 1 || g.mx != 1) return false;
+  if (g.PW < 1 || g.PH < 1) return false;
+  if (!view_tma_ok(g.in, g.is)) return false;
   return true;
 }
 
 size_t tc_pixgemm_workspace(const PixGemm& g) {
-  const int BN = pick_bn(g.N);
+  const int BN = pick_bn(g.N, 16);
   const int64_t Npad = round_up(g.N, BN), Cpad = round_up(g.Cr, 32);
   const int64_t BW = g.w_sb != 0 ? g.B : 1;
   return (size_t)(BW * g.ntaps * Npad * Cpad) * sizeof(float) + 256;
 }
 
-template <int AW, int BN>
+template <int BN>
 static int launch_pix(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPixParams& p, dim3 grid,
                       cudaStream_t st) {
   constexpr int STAGES = (BN == 256) ? 4 : 6;
   constexpr size_t smem = (size_t)STAGES * (16384 + BN * 128) + 16 * STAGES + 64 + 1024;
-  auto kfn = tc_pixgemm_kernel<AW, BN, STAGES>;
+  auto kfn = tc_pixgemm_kernel<BN, STAGES>;
   static bool attr_done = false;
   if (!attr_done) {
     MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -565,7 +549,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   const size_t need = tc_pixgemm_workspace(g);
   if (!ws || ws_bytes < need) return fail(MSG_ERR_WORKSPACE, "conv pixgemm(tcgen05): workspace %zu < %zu", ws_bytes, need);
   float* wt = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  const int BN = pick_bn(g.N);
+  const int BN = pick_bn(g.N, 16);
   const int Npad = round_up(g.N, BN), Cpad = round_up(g.Cr, 32);
   const int BW = g.w_sb != 0 ? g.B : 1;
 
@@ -581,14 +565,15 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     MSG_CHECK_LAUNCH("conv weight transform");
   }
 
-  const int AW = 32;
-  const int AH = 128 / AW;
+  int wt_log2 = ilog2_ceil(g.PW);
+  if (wt_log2 > 7) wt_log2 = 7;
+  const int Wt = 1 << wt_log2, Ht = 128 >> wt_log2;
   CUtensorMap tmA, tmB;
   {
-    const uint64_t dims[4] = {(uint64_t)g.IW, (uint64_t)g.Cr, (uint64_t)g.IH, (uint64_t)g.B};
-    const uint64_t strides[3] = {(uint64_t)g.in_sc * 4, (uint64_t)g.in_pitch * 4, (uint64_t)g.in_sb * 4};
-    const uint32_t box[4] = {(uint32_t)AW, 32, (uint32_t)AH, 1};
-    int rc = make_tmap(&tmA, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    const uint64_t dims[4] = {(uint64_t)g.Cr, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4};
+    const uint32_t box[4] = {32, (uint32_t)Wt, (uint32_t)Ht, 1};
+    int rc = make_tmap(&tmA, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
   {
@@ -602,48 +587,52 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.ntaps = g.ntaps; p.cchunks = Cpad / 32;
   for (int t = 0; t < g.ntaps; ++t) { p.tap_dy[t] = g.tap_dy[t]; p.tap_dx[t] = g.tap_dx[t]; }
   p.PH = g.PH; p.PW = g.PW; p.N = g.N;
-  p.tiles_x = (int)ceil_div(g.PW, AW);
-  const int tiles_y = (int)ceil_div(g.PH, AH);
-  p.out = g.out; p.out_sb = g.out_sb; p.out_sn = g.out_sn; p.out_pitch = g.out_pitch;
-  p.out_sy = g.out_sy; p.out_sx = g.out_sx; p.out_oy = g.out_oy; p.out_ox = g.out_ox;
-  p.alpha = g.alpha; p.w_per_sample = g.w_sb != 0; p.variant = tc_variant(); p.dbg = tc_debug_buffer();
+  p.wt_log2 = wt_log2;
+  p.tiles_x = (int)ceil_div(g.PW, Wt);
+  const int tiles_y = (int)ceil_div(g.PH, Ht);
+  p.out = g.out; p.os = g.os;
+  p.out_my = g.out_my; p.out_mx = g.out_mx; p.out_oy = g.out_oy; p.out_ox = g.out_ox;
+  p.alpha = g.alpha; p.w_per_sample = g.w_sb != 0; p.dbg = tc_debug_buffer();
+  p.vec_store = (g.os.sc == 1 && al16(g.out) && g.os.sx % 4 == 0 && g.os.sy % 4 == 0 && g.os.sb % 4 == 0) ? 1 : 0;
   dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)(Npad / BN), (unsigned)g.B);
   if (grid.y > 65535) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): too many N tiles");
-
-#define PIX_CASE(AW_, BN_) if (AW == AW_ && BN == BN_) return launch_pix<AW_, BN_>(tmA, tmB, p, grid, st)
-  PIX_CASE(32, 256); PIX_CASE(32, 128); PIX_CASE(32, 64); PIX_CASE(32, 32); PIX_CASE(32, 16);
-#undef PIX_CASE
-  return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): no kernel for AW=%d BN=%d", AW, BN);
+  switch (BN) {
+    case 256: return launch_pix<256>(tmA, tmB, p, grid, st);
+    case 128: return launch_pix<128>(tmA, tmB, p, grid, st);
+    case 64: return launch_pix<64>(tmA, tmB, p, grid, st);
+    case 32: return launch_pix<32>(tmA, tmB, p, grid, st);
+    default: return launch_pix<16>(tmA, tmB, p, grid, st);
+  }
 }
 
 // ---- RedGemm host -------------------------------------------------------------------------------
 bool tc_redgemm_supported(const RedGemm& g) {
   if (!tc_available()) return false;
   if (g.ntaps <= 0 || g.ntaps > kMaxTaps || g.C <= 0 || g.N <= 0 || g.B <= 0) return false;
-  if (g.in_sy != 1 || g.in_sx != 1) return false;
-  if (g.PW < 16 || g.IW < 16 || g.PH < 2 || g.IH < 2) return false;
-  if (!al16(g.in) || (g.in_pitch & 3) || (g.in_sc & 3) || (g.in_sb & 3)) return false;
-  if (!al16(g.g) || (g.g_pitch & 3) || (g.g_sn & 3) || (g.g_sb & 3)) return false;
+  if (g.my != 1 || g.mx != 1) return false;
+  if (g.PW < 1 || g.PH < 1) return false;
+  if (!view_tma_ok(g.in, g.is) || !view_tma_ok(g.g, g.gs)) return false;
   const int BS = g.dw_sb != 0 ? g.B : 1;
   if ((int64_t)g.ntaps * BS > 65535) return false;
   return true;
 }
 
 struct RedPlan {
-  int AW, BN, Npad, Cpad, BS, splits, chunks_x, chunks_y;
+  int BN, Npad, Cpad, BS, splits, wk_log2, chunks_x, chunks_y;
   size_t part_bytes;
 };
 
 static RedPlan red_plan(const RedGemm& g) {
   RedPlan pl{};
-  pl.AW = g.PW >= 32 ? 32 : 16;
-  pl.BN = pick_bn(g.C);
+  pl.BN = pick_bn(g.C, 32);
   pl.Npad = round_up(g.N, 128);
   pl.Cpad = round_up(g.C, pl.BN);
   pl.BS = g.dw_sb != 0 ? g.B : 1;
-  const int KH = 32 / pl.AW;
-  pl.chunks_x = (int)ceil_div(g.PW, pl.AW);
-  pl.chunks_y = (int)ceil_div(g.PH, KH);
+  pl.wk_log2 = ilog2_ceil(g.PW);
+  if (pl.wk_log2 > 5) pl.wk_log2 = 5;
+  const int Wk = 1 << pl.wk_log2, Hk = 32 >> pl.wk_log2;
+  pl.chunks_x = (int)ceil_div(g.PW, Wk);
+  pl.chunks_y = (int)ceil_div(g.PH, Hk);
   const int64_t kiters = (int64_t)pl.chunks_x * pl.chunks_y * (g.dw_sb != 0 ? 1 : g.B);
   const int64_t tiles = (int64_t)(pl.Npad / 128) * (pl.Cpad / pl.BN) * g.ntaps * pl.BS;
   int64_t splits = ceil_div(2 * (int64_t)num_sms(), tiles);
@@ -658,12 +647,12 @@ static RedPlan red_plan(const RedGemm& g) {
 
 size_t tc_redgemm_workspace(const RedGemm& g) { return red_plan(g).part_bytes + 256; }
 
-template <int AW, int BN>
+template <int BN>
 static int launch_red(const CUtensorMap& tmG, const CUtensorMap& tmI, const TcRedParams& p, dim3 grid,
                       cudaStream_t st) {
   constexpr int STAGES = (BN == 256) ? 4 : 6;
   constexpr size_t smem = (size_t)STAGES * (16384 + BN * 128) + 16 * STAGES + 64 + 1024;
-  auto kfn = tc_redgemm_kernel<AW, BN, STAGES>;
+  auto kfn = tc_redgemm_kernel<BN, STAGES>;
   static bool attr_done = false;
   if (!attr_done) {
     MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -680,36 +669,38 @@ int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!ws || ws_bytes < pl.part_bytes + 256)
     return fail(MSG_ERR_WORKSPACE, "conv wgrad(tcgen05): workspace %zu < %zu", ws_bytes, pl.part_bytes + 256);
   float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  const int KH = 32 / pl.AW;
+  const int Wk = 1 << pl.wk_log2, Hk = 32 >> pl.wk_log2;
   CUtensorMap tmG, tmI;
   {
-    const uint64_t dims[4] = {(uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.N, (uint64_t)g.B};
-    const uint64_t strides[3] = {(uint64_t)g.g_pitch * 4, (uint64_t)g.g_sn * 4, (uint64_t)g.g_sb * 4};
-    const uint32_t box[4] = {(uint32_t)pl.AW, (uint32_t)KH, 128, 1};
-    int rc = make_tmap(&tmG, g.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)g.gs.sx * 4, (uint64_t)g.gs.sy * 4, (uint64_t)g.gs.sb * 4};
+    const uint32_t box[4] = {32, (uint32_t)Wk, (uint32_t)Hk, 1};
+    int rc = make_tmap(&tmG, g.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   {
-    const uint64_t dims[4] = {(uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.C, (uint64_t)g.B};
-    const uint64_t strides[3] = {(uint64_t)g.in_pitch * 4, (uint64_t)g.in_sc * 4, (uint64_t)g.in_sb * 4};
-    const uint32_t box[4] = {(uint32_t)pl.AW, (uint32_t)KH, (uint32_t)pl.BN, 1};
-    int rc = make_tmap(&tmI, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    const uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4};
+    const uint32_t box[4] = {32, (uint32_t)Wk, (uint32_t)Hk, 1};
+    int rc = make_tmap(&tmI, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   }
   TcRedParams p{};
   p.ntaps = g.ntaps;
   for (int t = 0; t < g.ntaps; ++t) { p.tap_dy[t] = g.tap_dy[t]; p.tap_dx[t] = g.tap_dx[t]; }
   p.B = g.B; p.per_sample = g.dw_sb != 0;
-  p.chunks_x = pl.chunks_x; p.chunks_y = pl.chunks_y;
+  p.wk_log2 = pl.wk_log2; p.chunks_x = pl.chunks_x; p.chunks_y = pl.chunks_y;
   p.ctiles = pl.Cpad / pl.BN;
-  p.Npad = pl.Npad; p.Cpad = pl.Cpad; p.splits = pl.splits; p.part = part; p.dbg = tc_debug_buffer();
+  p.Npad = pl.Npad; p.Cpad = pl.Cpad; p.splits = pl.splits; p.part = part;
+  p.variant = tc_variant(); p.dbg = tc_debug_buffer();
   dim3 grid((unsigned)((pl.Npad / 128) * p.ctiles), (unsigned)(g.ntaps * pl.BS), (unsigned)pl.splits);
-  int rc = MSG_ERR_UNSUPPORTED;
-  const int AW = pl.AW, BN = pl.BN;
-#define RED_CASE(AW_, BN_) if (AW == AW_ && BN == BN_) rc = launch_red<AW_, BN_>(tmG, tmI, p, grid, st)
-  RED_CASE(32, 256); RED_CASE(32, 128); RED_CASE(32, 64); RED_CASE(32, 32); RED_CASE(32, 16);
-  RED_CASE(16, 256); RED_CASE(16, 128); RED_CASE(16, 64); RED_CASE(16, 32); RED_CASE(16, 16);
-#undef RED_CASE
+  int rc;
+  switch (pl.BN) {
+    case 256: rc = launch_red<256>(tmG, tmI, p, grid, st); break;
+    case 128: rc = launch_red<128>(tmG, tmI, p, grid, st); break;
+    case 64: rc = launch_red<64>(tmG, tmI, p, grid, st); break;
+    default: rc = launch_red<32>(tmG, tmI, p, grid, st); break;
+  }
   if (rc) return rc;
 
   RedReduceParams rp{};

@@ -43,12 +43,13 @@ def make(shape, seed=0):
     return x, w, y, dy
 
 
-def run_engine(shape, flags, tol):
+def run_engine(shape, flags, tol, channels_last=True):
     from multi_stylegan_b200 import _C, _lib
     B, C, O, H, W, k, s, p, per = shape
     x, w, y, dy = make(shape)
-    old = _C.conv_flags
+    old = _C.conv_flags, _C.conv_channels_last
     _C.conv_flags = flags
+    _C.conv_channels_last = channels_last
     try:
         got = _C.conv2d_forward(x.to(dev()), w.to(dev()), s, p)
         eng_f = _C.conv2d_last_engine()
@@ -63,24 +64,32 @@ def run_engine(shape, flags, tol):
         assert rel_err(got, want) < tol, ("wgrad", eng_w, rel_err(got, want))
         torch.cuda.synchronize()
     finally:
-        _C.conv_flags = old
+        _C.conv_flags, _C.conv_channels_last = old
     return eng_f, eng_d, eng_w
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-def test_conv_cuda_core_engine_exact_fp32(built_library, shape):
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_conv_cuda_core_engine_exact_fp32(built_library, shape, channels_last):
     from multi_stylegan_b200 import _lib
-    engines = run_engine(shape, _lib.CONV_FORCE_SIMT, 1e-4)
+    engines = run_engine(shape, _lib.CONV_FORCE_SIMT, 1e-4, channels_last)
     assert engines == ("simt", "simt", "simt")
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-def test_conv_auto_engine_tf32(built_library, shape):
+def test_conv_tensor_core_engine_tf32(built_library, shape):
+    """Channels-last activations: every layer shape of G and D must run on tcgen05 (TF32, 1e-2)."""
     from multi_stylegan_b200 import _C, _lib
-    engines = run_engine(shape, _lib.CONV_AUTO, 1e-2)
-    B, C, O, H, W, k, s, p, per = shape
-    if _C.tensor_core_path_available() and min(H, W) >= 32:
-        assert "tcgen05" in engines, engines
+    if not _C.tensor_core_path_available():
+        pytest.skip("not an sm_100 device")
+    engines = run_engine(shape, _lib.CONV_FORCE_TC, 1e-2)
+    assert engines == ("tcgen05", "tcgen05", "tcgen05"), engines
+
+
+def test_conv_nchw_inputs_use_cuda_cores(built_library):
+    from multi_stylegan_b200 import _lib
+    engines = run_engine(SHAPES[3], _lib.CONV_AUTO, 1e-4, channels_last=False)
+    assert engines == ("simt", "simt", "simt")
 
 
 def test_transposed_conv_is_dgrad(built_library):

@@ -4,6 +4,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 CASES = {  # name: (B, C, O, H, W, k, pad, per_sample)
+    "3x3_same": (2, 64, 64, 32, 32, 3, 1, True),
+    "3x3_same_16": (2, 64, 64, 16, 16, 3, 1, True),
+    "3x3_same_4": (2, 64, 64, 4, 4, 3, 1, True),
+    "3x3_same_128_bigN": (1, 96, 272, 128, 128, 3, 1, False),
+    "1x1_N3": (2, 64, 3, 32, 32, 1, 0, True),
+    "3x3_C6": (2, 6, 32, 64, 64, 3, 1, False),
     "3x1_valid_Hshift": (1, 32, 64, 34, 32, (3, 1), 0, False),
     "1x3_valid_Wshift": (1, 32, 64, 32, 34, (1, 3), 0, False),
     "3x1_same_negH": (1, 32, 64, 32, 32, (3, 1), (1, 0), False),
