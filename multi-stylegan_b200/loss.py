@@ -41,7 +41,7 @@ class R1Regularization(nn.Module):
         outputs = prediction_real.sum() if prediction_real_pixel_wise is None \
             else (prediction_real.sum(), prediction_real_pixel_wise.sum())
         grad_real, = autograd.grad(outputs=outputs, inputs=image_real, create_graph=True)
-        return 0.5 * grad_real.pow(2).view(grad_real.shape[0], -1).sum(1).mean()
+        return 0.5 * grad_real.pow(2).reshape(grad_real.shape[0], -1).sum(1).mean()
 
 
 class PathLengthRegularization(nn.Module):

@@ -68,7 +68,7 @@ def modulated_conv(sd: SD, p: str, x: torch.Tensor, style: torch.Tensor, demodul
         y = ops.conv_transpose2d(x, w.transpose(1, 2), stride=2, padding=0)           # :393-401
         k = blur_kernel_2d(gain=4.0)                                                  # :325,:601-602
         pf = (4 - 2) + (kh - 1)                                                       # :615-616
-        y = fir(y, k.to(y.dtype), pad=((pf + 1) // 2, pf // 2))                       # :403
+        y = fir(y, k.to(y), pad=((pf + 1) // 2, pf // 2))                       # :403
     else:
         y = ops.conv2d(x, w, stride=1, padding=(kh // 2, kw // 2))                    # :406-411
     return y, s
@@ -78,7 +78,7 @@ def styled_conv(sd: SD, p: str, x, style, noise, upsampling: bool):
     """multi_stylegan_generator.py:452-469 (+ :281-292 noise, fused_act.py:84-85 activation)."""
     y, s = modulated_conv(sd, p + ".modulated_convolution", x, style, True, upsampling)
     if noise is None:
-        noise = torch.randn(y.shape[0], 1, y.shape[2], y.shape[3], dtype=torch.float32)
+        noise = torch.randn(y.shape[0], 1, y.shape[2], y.shape[3], dtype=torch.float32, device=y.device)
     y = y + sd[p + ".noise_injection.weight"] * noise
     return lrelu_bias(y, sd[p + ".activation.bias"]), s
 
@@ -88,7 +88,7 @@ def output_block(sd: SD, p: str, x, style, skip=None):
     y, s = modulated_conv(sd, p + ".modulated_convolution", x, style, False, False)
     y = y + sd[p + ".bias"]
     if skip is not None:
-        y = y + fir(skip, blur_kernel_2d().to(skip.dtype), up=2, pad=(2, 1))
+        y = y + fir(skip, blur_kernel_2d().to(skip), up=2, pad=(2, 1))
     return y, s
 
 
@@ -205,12 +205,12 @@ def discriminator_forward(sd: SD, images: torch.Tensor) -> Tuple[torch.Tensor, t
         if i != n_enc - 1:
             feats.append(x)
             x = eq_conv2d(sd, "downscale_convolutions.%d.0" % i, x, stride=2, padding=0)   # :59-62
-            x = fir(x, k1.to(x.dtype), pad=(2, 2))                                         # Blur() :62,:306-307
+            x = fir(x, k1.to(x), pad=(2, 2))                                         # Blur() :62,:306-307
     h = x.mean(dim=(2, 3))                                                             # :66-67
     h = lrelu_bias(eq_linear(sd, "classification_head.2", h), sd["classification_head.3.bias"])
     scalar = eq_linear(sd, "classification_head.4", h)                                 # :70
     for j, skip in enumerate(reversed(feats)):                                         # :135-137
-        u = fir(x, k1.to(x.dtype), up=2, pad=(2, 1))                                   # Upsample() :87,:236-242
+        u = fir(x, k1.to(x), up=2, pad=(2, 1))                                   # Upsample() :87,:236-242
         u = eq_conv2d(sd, "transposed_convolutions.%d.1" % j, u)
         x = _block(sd, "decoder_blocks.%d" % j, torch.cat([u, skip], dim=1))
     x = lrelu_bias(x, sd["final_mapping.0.bias"])                                      # :94-97

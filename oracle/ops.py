@@ -42,8 +42,8 @@ def upfirdn2d(x: torch.Tensor, kernel: torch.Tensor, up_x: int, up_y: int, down_
     canvas = x.new_zeros(major, minor, max(full_h, 0), max(full_w, 0))
     src = x.permute(0, 3, 1, 2)
     # position of input sample (iy, ix) on the padded, zero-inserted canvas
-    ys = torch.arange(in_h) * up_y + pad_y0
-    xs = torch.arange(in_w) * up_x + pad_x0
+    ys = torch.arange(in_h, device=x.device) * up_y + pad_y0
+    xs = torch.arange(in_w, device=x.device) * up_x + pad_x0
     my = (ys >= 0) & (ys < full_h)
     mx = (xs >= 0) & (xs < full_w)
     if my.any() and mx.any():
@@ -52,7 +52,7 @@ def upfirdn2d(x: torch.Tensor, kernel: torch.Tensor, up_x: int, up_y: int, down_
     out_w = upfirdn2d_out_size(in_w, up_x, down_x, pad_x0, pad_x1, kw)
     if out_h <= 0 or out_w <= 0 or full_h < kh or full_w < kw:
         return x.new_zeros(major, max(out_h, 0), max(out_w, 0), minor)
-    w = torch.flip(kernel, [0, 1]).to(x.dtype).view(1, 1, kh, kw)
+    w = torch.flip(kernel, [0, 1]).to(device=x.device, dtype=x.dtype).view(1, 1, kh, kw)
     y = F.conv2d(canvas.reshape(major * minor, 1, full_h, full_w), w)
     y = y[:, :, ::down_y, ::down_x].reshape(major, minor, out_h, out_w)
     return y.permute(0, 2, 3, 1).contiguous()
