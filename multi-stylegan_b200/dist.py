@@ -1,0 +1,74 @@
+"""Batch-sharded data parallelism: one process per GPU, replicated parameters, one flat all-reduce of the
+gradients per optimiser step over NCCL/NVLink (gloo on CPU for tests).  Replaces the reference's
+single-process nn.DataParallel (train_multi_stylegan.py:67-70), which re-broadcasts both models on every
+forward."""
+import os
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend: Optional[str] = None) -> int:
+    """Initialise torch.distributed from torchrun's environment; returns the local rank (0 if single)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local_rank)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group(backend=backend)
+    return local_rank
+
+
+def world_size(group=None) -> int:
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank(group=None) -> int:
+    return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
+@torch.no_grad()
+def broadcast_parameters(modules: Iterable[torch.nn.Module], src: int = 0, group=None) -> None:
+    """Once at start-up (the reference's DataParallel does this on every forward call)."""
+    if world_size(group) == 1:
+        return
+    for m in modules:
+        tensors = [p.data for p in m.parameters()] + [b.data for b in m.buffers()]
+        if not tensors:
+            continue
+        flat = torch._utils._flatten_dense_tensors(tensors)
+        dist.broadcast(flat, src=src, group=group)
+        for t, f in zip(tensors, torch._utils._unflatten_dense_tensors(flat, tensors)):
+            t.copy_(f)
+
+
+@torch.no_grad()
+def all_reduce_gradients(parameters: Iterable[torch.nn.Parameter], group=None) -> int:
+    """Average gradients across ranks with ONE collective on a flat fp32 buffer.  Parameters that never
+    receive a gradient (the generator's unobservable second branch) are skipped on every rank alike.
+    Returns the number of elements reduced."""
+    ws = world_size(group)
+    if ws == 1:
+        return 0
+    grads: List[torch.Tensor] = [p.grad for p in parameters if p.grad is not None]
+    if not grads:
+        return 0
+    flat = torch._utils._flatten_dense_tensors(grads)
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(ws)
+    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+        g.copy_(f)
+    return flat.numel()
+
+
+@torch.no_grad()
+def all_reduce_mean_(t: torch.Tensor, group=None) -> torch.Tensor:
+    ws = world_size(group)
+    if ws > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t.div_(ws)
+    return t

@@ -1,0 +1,198 @@
+"""The G+D training step of the reference's trainer (multi_stylegan/model_wrapper.py:245-451), same order of
+sub-steps and the same lazy-regularisation cadence, restructured for one-process-per-GPU execution:
+
+  * `train_step(real_images)` = one iteration of `_gan_training`: D step -> lazy R1 (every 16th) ->
+    [CutMix augmentation + consistency, probability 0 in epoch 0] -> G step -> lazy path length (every 16th,
+    half batch) -> EMA.  Losses are returned as device scalars; nothing calls `.item()` on the hot path
+    (the reference syncs 6-9 times per iteration for logging, :300-305,:327-329,:414-416,:442-444).
+  * gradients are averaged across ranks with one flat all-reduce per optimiser step (dist.py); the
+    path-length running mean is averaged too (the reference computes it from DataParallel's gathered batch).
+  * the generator's unobservable second branch (multi_stylegan_generator.py:184,187,189) is not evaluated.
+"""
+import copy
+import random
+from typing import Any, Callable, Dict, Iterable, Optional
+
+import torch
+import torch.nn as nn
+
+from . import config as default_config
+from . import dist as mdist
+from . import loss, misc
+from .u_net_2d_discriminator import (generate_cut_mix_augmentation_data, generate_cut_mix_transformation_data)
+
+
+class ModelWrapper(object):
+    def __init__(self,
+                 generator: nn.Module,
+                 discriminator: nn.Module,
+                 generator_optimizer: torch.optim.Optimizer,
+                 discriminator_optimizer: torch.optim.Optimizer,
+                 training_dataset: Optional[Iterable[torch.Tensor]] = None,
+                 hyperparameters: Dict[str, Any] = default_config.generation_hyperparameters,
+                 trap_weights_map: Optional[torch.Tensor] = None,
+                 generator_loss: nn.Module = None,
+                 discriminator_loss: nn.Module = None,
+                 discriminator_regularization_loss: nn.Module = None,
+                 cut_mix_augmentation_loss: nn.Module = None,
+                 cut_mix_regularization_loss: nn.Module = None,
+                 path_length_regularization: nn.Module = None,
+                 generator_ema: Optional[nn.Module] = None,
+                 device: str = "cuda",
+                 process_group=None) -> None:
+        self.generator, self.discriminator = generator, discriminator
+        self.generator_optimizer, self.discriminator_optimizer = generator_optimizer, discriminator_optimizer
+        self.training_dataset = training_dataset
+        self.hyperparameters = hyperparameters
+        self.trap_weights_map = trap_weights_map
+        self.generator_loss = generator_loss or loss.NonSaturatingLogisticGeneratorLoss()
+        self.discriminator_loss = discriminator_loss or loss.NonSaturatingLogisticDiscriminatorLoss()
+        self.discriminator_regularization_loss = discriminator_regularization_loss or loss.R1Regularization()
+        self.cut_mix_augmentation_loss = cut_mix_augmentation_loss or loss.NonSaturatingLogisticDiscriminatorLossCutMix()
+        self.cut_mix_regularization_loss = cut_mix_regularization_loss or nn.MSELoss(reduction="mean")
+        self.path_length_regularization = path_length_regularization or loss.PathLengthRegularization()
+        self.device = device
+        self.process_group = process_group
+        if generator_ema is None:
+            generator_ema = copy.deepcopy(generator)
+        self.generator_ema = generator_ema.eval()
+        self.latent_dimensions = generator.latent_dimensions
+        self.iteration = 0           # == the reference's progress_bar.n after update(n=1) (:255)
+        self.epoch, self.epochs = 0, 1
+        self.resume_training = False
+        self.top_k: Callable = nn.Identity()
+
+    # ---- helpers ------------------------------------------------------------------------------------
+    def _noise(self, batch: int):
+        return misc.get_noise(batch_size=batch, latent_dimension=self.latent_dimensions,
+                              p_mixed_noise=self.hyperparameters["p_mixed_noise"], device=self.device)
+
+    def _d_params(self):
+        return [p for p in self.discriminator.parameters()]
+
+    def _optimize(self, params, optimizer) -> None:
+        mdist.all_reduce_gradients(params, self.process_group)
+        torch.nn.utils.clip_grad_norm_(params, max_norm=5.)
+        optimizer.step()
+
+    def _zero(self) -> None:
+        self.discriminator_optimizer.zero_grad()
+        self.generator_optimizer.zero_grad()
+
+    def _trap(self):
+        use = self.hyperparameters["trap_weight"] * self.epochs <= self.epoch or self.resume_training
+        return self.trap_weights_map if use else None
+
+    # ---- one iteration of _gan_training (model_wrapper.py:253-451) -----------------------------------
+    def train_step(self, real_images: torch.Tensor, z_d=None, z_g=None, z_pl=None,
+                   pl_noise=None) -> Dict[str, torch.Tensor]:
+        """real_images [B, 2, 3, H, W] on the device.  z_* optionally fix the latent draws (parity tests)."""
+        hp = self.hyperparameters
+        out: Dict[str, torch.Tensor] = {}
+        self.iteration += 1
+        B = real_images.shape[0]
+        g_params = [p for p in self.generator.parameters()]
+        d_params = self._d_params()
+
+        # ---------------- discriminator step (:258-305) ----------------
+        self._zero()
+        with torch.no_grad():
+            fake_images = self.generator(input=self._noise(B) if z_d is None else z_d)
+        if self.epoch >= hp["wrong_order_start"] * self.epochs or self.resume_training:
+            n = max(1, int(hp["batch_factor_wrong_order"] * B))
+            fake_images = torch.cat([fake_images, real_images[:n, :, misc.random_permutation(real_images.shape[2])]], 0)
+        real_pred, real_pred_px = self.discriminator(real_images, is_real=True, is_cut_mix=False)
+        fake_pred, fake_pred_px = self.discriminator(fake_images, is_real=False, is_cut_mix=False)
+        l_real, l_fake = self.discriminator_loss(real_pred, fake_pred)
+        l_real_px, l_fake_px = self.discriminator_loss(real_pred_px, fake_pred_px, weight=self._trap())
+        (l_real + l_fake + l_real_px + l_fake_px).backward()
+        self._optimize(d_params, self.discriminator_optimizer)
+        out.update(loss_discriminator_real=l_real.detach(), loss_discriminator_fake=l_fake.detach(),
+                   loss_discriminator_real_pixel_wise=l_real_px.detach(),
+                   loss_discriminator_fake_pixel_wise=l_fake_px.detach())
+
+        # ---------------- lazy R1 (:307-329) ----------------
+        if self.iteration % hp["lazy_discriminator_regularization"] == 0:
+            self._zero()
+            real_r1 = real_images.detach().requires_grad_(True)
+            rp, rp_px = self.discriminator(real_r1, is_real=False, is_cut_mix=True)
+            r1 = self.discriminator_regularization_loss(rp, real_r1, rp_px)
+            (hp["w_discriminator_regularization_r1"] * r1).backward()
+            self._optimize(d_params, self.discriminator_optimizer)
+            out["loss_discriminator_regularization"] = r1.detach()
+
+        # ---------------- CutMix augmentation + consistency (:331-376) ----------------
+        if (random.random() <= ((0.5 / float(self.epochs)) * float(self.epoch))) \
+                or (self.resume_training and random.random() <= 0.5):
+            self._zero()
+            images, label = generate_cut_mix_augmentation_data(real_images, fake_images)
+            _, pred = self.discriminator(images, is_cut_mix=True)
+            cm_real, cm_fake = self.cut_mix_augmentation_loss(pred, label)
+            (hp["w_discriminator_regularization"] * (cm_real + cm_fake)).backward()
+            self._optimize(d_params, self.discriminator_optimizer)
+            out["loss_cut_mix_augmentation"] = (cm_real + cm_fake).detach()
+            self.discriminator_optimizer.zero_grad()
+            images, label = generate_cut_mix_transformation_data(real_images.detach(), fake_images.detach(),
+                                                                 real_pred_px.detach(), fake_pred_px.detach())
+            _, pred = self.discriminator(images, is_cut_mix=True)
+            cm_reg = self.cut_mix_regularization_loss(pred, label)
+            (hp["w_discriminator_regularization"] * cm_reg).backward()
+            self._optimize(d_params, self.discriminator_optimizer)
+            out["loss_cut_mix_regularization"] = cm_reg.detach()
+
+        # ---------------- generator step (:377-416) ----------------
+        self._zero()
+        fake_images = self.generator(input=self._noise(B) if z_g is None else z_g)
+        fake_pred, fake_pred_px = self.discriminator(fake_images, is_real=False, is_cut_mix=False)
+        top = self.top_k(fake_pred)
+        if isinstance(top, tuple):
+            fake_pred, indexes = top
+            fake_pred_px = fake_pred_px[indexes]
+        else:
+            fake_pred = top
+        l_g = self.generator_loss(fake_pred)
+        l_g_px = self.generator_loss(fake_pred_px, weight=self._trap())
+        (l_g + l_g_px).backward()
+        self._optimize(g_params, self.generator_optimizer)
+        out.update(loss_generator=l_g.detach(), loss_generator_pixel_wise=l_g_px.detach())
+
+        # ---------------- lazy path length (:418-444) ----------------
+        if self.iteration % hp["lazy_generator_regularization"] == 0:
+            self._zero()
+            n = max(1, int(hp["batch_size_shrink_path_length_regularization"] * B))
+            grads = self.generator(input=self._noise(n) if z_pl is None else z_pl, return_path_length_grads=True,
+                                   path_length_noise=pl_noise)
+            pl_loss, path_length = self.path_length_regularization(grads)
+            (hp["w_generator_regularization"] * pl_loss).backward()
+            mdist.all_reduce_mean_(self.path_length_regularization.mean_path_length, self.process_group)
+            self._optimize(g_params, self.generator_optimizer)
+            out.update(path_length=path_length.detach().mean(), loss_path_length_regularization=pl_loss.detach())
+
+        # ---------------- EMA (:446) ----------------
+        misc.exponential_moving_average(model_ema=self.generator_ema, model_train=self.generator)
+        return out
+
+    def _gan_training(self, resume_training: bool = False, top_k: nn.Module = nn.Identity()):
+        """One epoch over `training_dataset` (model_wrapper.py:245-253); yields the per-iteration scalars."""
+        self.resume_training, self.top_k = resume_training, top_k
+        history = []
+        for real_images in self.training_dataset:
+            history.append(self.train_step(real_images.to(self.device, non_blocking=True)))
+        return history
+
+    def train(self, epochs: int = 20, resume_training: bool = False, top_k: bool = False):
+        """Epoch loop (model_wrapper.py:104-145) without the logging / validation / checkpoint shell."""
+        self.epochs = epochs
+        tk = nn.Identity()
+        if top_k:
+            n = len(self.training_dataset)
+            tk = loss.TopK(starting_iteration=int(self.hyperparameters["top_k_start"] * epochs * n),
+                           final_iteration=int(self.hyperparameters["top_k_finish"] * epochs * n))
+            if resume_training:
+                tk.starting_iteration, tk.final_iteration = 0, 1
+        history = []
+        for self.epoch in range(epochs):
+            self.generator.train()
+            self.discriminator.train()
+            history.extend(self._gan_training(resume_training=resume_training, top_k=tk))
+        return history

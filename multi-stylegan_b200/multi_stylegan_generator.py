@@ -272,7 +272,7 @@ class Generator(nn.Module):
     def forward(self, input: Union[List[torch.Tensor], torch.Tensor], return_main_style_vectors: bool = False,
                 noise: Optional[List[torch.Tensor]] = None, randomize_noise: bool = True,
                 inject_index: Optional[int] = None, input_is_latent: bool = False,
-                return_path_length_grads: bool = False):
+                return_path_length_grads: bool = False, path_length_noise: Optional[torch.Tensor] = None):
         n_main = len(self.main_convolutions_1)
         if noise is None:
             if randomize_noise:
@@ -302,7 +302,9 @@ class Generator(nn.Module):
             skip_2 = self.output_blocks_2[i](out_1, style, skip=skip_2)     # branch-1 features (reference :189)
         image = torch.stack([skip_1, skip_2], dim=1)
         if return_path_length_grads:
-            pl_noise = torch.randn(image.shape, device=image.device, dtype=torch.float32, requires_grad=True) \
+            # reference :195-196; `path_length_noise` (an extension) injects the N(0,1) draw for parity tests
+            pl_noise = (torch.randn(image.shape, device=image.device, dtype=torch.float32, requires_grad=True)
+                        if path_length_noise is None else path_length_noise) \
                 / math.sqrt(image.shape[2] * image.shape[3] * image.shape[4])
             return autograd.grad(outputs=(image * pl_noise).sum(), inputs=latent, create_graph=True,
                                  retain_graph=True, only_inputs=True)[0]

@@ -152,3 +152,31 @@ class Discriminator(nn.Module):
         for block, up, skip in zip(self.decoder_blocks, self.transposed_convolutions, reversed(features)):
             x = block(torch.cat([up(x), skip], dim=1))
         return classification, self.final_mapping(x).unsqueeze(dim=2)
+
+
+# ---- CutMix helpers (u_net_2d_discriminator.py:384-448) ------------------------------------------------
+def _generate_binary_cut_mix_map(height: int, width: int, device="cpu") -> torch.Tensor:
+    import random
+    binary_map = torch.zeros(1, 1, 1, height, width, dtype=torch.float, device=device)
+    ch = int(torch.randint(int(0.1 * height), int(0.9 * height), size=(1,)))
+    cw = int(torch.randint(int(0.1 * width), int(0.9 * width), size=(1,)))
+    if random.random() > 0.5:
+        binary_map[..., ch:, cw:] = 1.0
+    else:
+        binary_map[..., :ch, :cw] = 1.0
+    if random.random() > 0.5:
+        binary_map = -binary_map + 1.
+    return binary_map
+
+
+def generate_cut_mix_augmentation_data(image_real: torch.Tensor, image_fake: torch.Tensor):
+    image_fake = image_fake[:image_real.shape[0]]
+    target = _generate_binary_cut_mix_map(image_real.shape[-2], image_fake.shape[-1], image_real.device)
+    return image_real * target + image_fake * (-target + 1.), target
+
+
+def generate_cut_mix_transformation_data(image_real, image_fake, prediction_real, prediction_fake):
+    image_fake = image_fake[:image_real.shape[0]]
+    prediction_fake = prediction_fake[:image_real.shape[0]]
+    m = _generate_binary_cut_mix_map(image_real.shape[-2], image_fake.shape[-1], image_real.device)
+    return image_real * m + image_fake * (-m + 1.), prediction_real * m + prediction_fake * (-m + 1.)

@@ -1,0 +1,79 @@
+"""Oracle restatement of one iteration of the reference trainer (model_wrapper.py:253-451, epoch-0 behaviour:
+no ADA, no CutMix, no wrong-order fakes, no top-k) on reference-named parameter dicts, CPU fp32.
+TEST INFRASTRUCTURE ONLY."""
+import math
+from typing import Dict, List
+
+import torch
+
+from oracle import model as om
+
+
+def _clip_(params: List[torch.Tensor], grads: List[torch.Tensor], max_norm: float = 5.0):
+    """torch.nn.utils.clip_grad_norm_ (model_wrapper.py:296,323,410,438) on explicit grads."""
+    total = torch.sqrt(sum(g.pow(2).sum() for g in grads if g is not None))
+    coef = (max_norm / (total + 1e-6)).clamp(max=1.0)
+    return [None if g is None else g * coef for g in grads]
+
+
+class OracleTrainer:
+    def __init__(self, sd_g: Dict[str, torch.Tensor], sd_d: Dict[str, torch.Tensor], g_groups, lr_d: float, betas, hp):
+        self.sd_g = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.startswith("noises.")
+                                                 and not k.endswith(".kernel")) for k, v in sd_g.items()}
+        self.sd_d = {k: v.clone().requires_grad_(not k.endswith(".kernel")) for k, v in sd_d.items()}
+        self.g_names = [k for k, v in self.sd_g.items() if v.requires_grad]
+        self.d_names = [k for k, v in self.sd_d.items() if v.requires_grad]
+        # same parameter groups as Generator.get_parameters (lr_style for the mapping network)
+        self.opt_g = torch.optim.Adam([{"params": [self.sd_g[k] for k in self.g_names if not k.startswith("style_mapping.")], "lr": g_groups[0]},
+                                       {"params": [self.sd_g[k] for k in self.g_names if k.startswith("style_mapping.")], "lr": g_groups[1]}],
+                                      betas=betas)
+        self.opt_d = torch.optim.Adam([self.sd_d[k] for k in self.d_names], lr=lr_d, betas=betas)
+        self.ema = {k: v.detach().clone() for k, v in self.sd_g.items()}
+        self.hp = hp
+        self.mean_pl = torch.zeros(1)
+        self.iteration = 0
+
+    def _apply(self, sd, names, loss, opt):
+        params = [sd[k] for k in names]
+        grads = torch.autograd.grad(loss, params, allow_unused=True)
+        grads = _clip_(params, list(grads))
+        for p, g in zip(params, grads):
+            p.grad = g
+        opt.step()
+        for p in params:
+            p.grad = None
+
+    def step(self, real, z_d, z_g, z_pl, noise_d, noise_g, noise_pl, inject, pl_noise):
+        hp, out = self.hp, {}
+        self.iteration += 1
+        with torch.no_grad():
+            fake = om.generator_forward({k: v.detach() for k, v in self.sd_g.items()}, z_d, noise_d, inject)
+        rs, rp = om.discriminator_forward(self.sd_d, real)
+        fs, fp = om.discriminator_forward(self.sd_d, fake)
+        lr_, lf_ = om.ns_discriminator_loss(rs, fs)
+        lrp, lfp = om.ns_discriminator_loss(rp, fp)
+        out.update(loss_discriminator_real=lr_.detach(), loss_discriminator_fake=lf_.detach(),
+                   loss_discriminator_real_pixel_wise=lrp.detach(), loss_discriminator_fake_pixel_wise=lfp.detach())
+        self._apply(self.sd_d, self.d_names, lr_ + lf_ + lrp + lfp, self.opt_d)
+        if self.iteration % hp["lazy_discriminator_regularization"] == 0:
+            r1 = om.r1_penalty(self.sd_d, real)
+            out["loss_discriminator_regularization"] = r1.detach()
+            self._apply(self.sd_d, self.d_names, hp["w_discriminator_regularization_r1"] * r1, self.opt_d)
+        fake = om.generator_forward(self.sd_g, z_g, noise_g, inject)
+        fs, fp = om.discriminator_forward(self.sd_d, fake)
+        lg, lgp = om.ns_generator_loss(fs), om.ns_generator_loss(fp)
+        out.update(loss_generator=lg.detach(), loss_generator_pixel_wise=lgp.detach())
+        self._apply(self.sd_g, self.g_names, lg + lgp, self.opt_g)
+        if self.iteration % hp["lazy_generator_regularization"] == 0:
+            n_lat = sum(1 for k in self.sd_g if k.startswith("main_convolutions_1.") and k.endswith("modulated_convolution.weight")) + 2
+            latent = om.generator_latent(self.sd_g, z_pl, inject, n_lat)
+            image = om.generator_forward(self.sd_g, latent=latent, noise=noise_pl)
+            scale = math.sqrt(image.shape[2] * image.shape[3] * image.shape[4])
+            g = torch.autograd.grad((image * (pl_noise / scale)).sum(), latent, create_graph=True)[0]
+            pen, pl, self.mean_pl = om.path_length_penalty(g, self.mean_pl.detach())
+            out.update(path_length=pl.detach(), loss_path_length_regularization=pen.detach())
+            self._apply(self.sd_g, self.g_names, hp["w_generator_regularization"] * pen, self.opt_g)
+        with torch.no_grad():      # misc.py:195-199 — parameters only, buffers are not averaged
+            for k in self.g_names:
+                self.ema[k].mul_(0.999).add_(self.sd_g[k].detach(), alpha=0.001)
+        return out

@@ -1,0 +1,167 @@
+"""Train-step parity (one iteration of model_wrapper._gan_training incl. lazy R1 + path length) against the
+oracle restatement, and the data-parallel plumbing on world_size 2 (gloo, CPU)."""
+import os
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from oracle.make_golden import TINY_D, TINY_G, randomize
+from tests.conftest import rel_err
+from tests.oracle_step import OracleTrainer
+
+HP = None
+
+
+def _hp():
+    from multi_stylegan_b200 import config
+    hp = dict(config.generation_hyperparameters)
+    hp["lazy_discriminator_regularization"] = 2      # so the second iteration runs R1 and path length
+    hp["lazy_generator_regularization"] = 2
+    hp["p_mixed_noise"] = 1.0
+    return hp
+
+
+class FixedNoiseGenerator(torch.nn.Module):
+    """Pins the per-layer noise maps and inject_index so oracle and product see the same draws."""
+
+    def __init__(self, net, noise, inject):
+        super().__init__()
+        self.net, self.noise, self.inject = net, noise, inject
+        self.latent_dimensions = net.latent_dimensions
+
+    def parameters(self, recurse=True):
+        return self.net.parameters(recurse)
+
+    def forward(self, input, **kw):
+        b = input[0].shape[0] if isinstance(input, list) else input.shape[0]
+        return self.net(input, noise=[n[:b] for n in self.noise], inject_index=self.inject, **kw)
+
+
+def build(dev, seed=0):
+    import multi_stylegan_b200.multi_stylegan_generator as G_mod
+    import multi_stylegan_b200.u_net_2d_discriminator as D_mod
+    torch.manual_seed(seed)
+    G = G_mod.Generator(TINY_G, compute_dead_branch=False)
+    D = D_mod.Discriminator(TINY_D, no_rfp=True)
+    randomize(G, 1), randomize(D, 2)
+    return G.to(dev), D.to(dev)
+
+
+def run_parity(dev, tol, n_iter=2):
+    from multi_stylegan_b200.model_wrapper import ModelWrapper
+    hp = _hp()
+    G, D = build("cpu")
+    sd_g = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    sd_d = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    G, D = G.to(dev), D.to(dev)
+    gen = torch.Generator().manual_seed(3)
+    B = 2
+    noise = [torch.randn(B, 1, 4, 4, generator=gen)] + \
+            [torch.randn(B, 1, 2 ** (i // 2 + 3), 2 ** (i // 2 + 3), generator=gen) for i in range(6)]
+    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"])
+    opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"])
+    wrapped = FixedNoiseGenerator(G, [n.to(dev) for n in noise], 3)
+    mw = ModelWrapper(wrapped, D, opt_g, opt_d, hyperparameters=hp, generator_ema=__import__("copy").deepcopy(G), device=dev)
+    mw.generator_ema_ref = G
+    oracle = OracleTrainer(sd_g, sd_d, (2e-3, 2e-5), 6e-3, hp["betas"], hp)
+    # EMA must follow the real generator, not the wrapper
+    import multi_stylegan_b200.misc as misc
+    for it in range(n_iter):
+        real = torch.rand(B, 2, 3, 32, 32, generator=gen)
+        zs = [[torch.randn(B, 16, generator=gen), torch.randn(B, 16, generator=gen)] for _ in range(2)]
+        z_pl = [torch.randn(1, 16, generator=gen), torch.randn(1, 16, generator=gen)]
+        pl_noise = torch.randn(1, 2, 3, 32, 32, generator=gen)
+        want = oracle.step(real, zs[0], zs[1], z_pl, noise, noise, [n[:1] for n in noise], 3, pl_noise)
+        mw.generator_ema, keep = torch.nn.Identity(), mw.generator_ema     # EMA checked separately below
+        import unittest.mock as um
+        with um.patch.object(misc, "exponential_moving_average", lambda **kw: None):
+            got = mw.train_step(real.to(dev), z_d=[z.to(dev) for z in zs[0]], z_g=[z.to(dev) for z in zs[1]],
+                                z_pl=[z.to(dev) for z in z_pl], pl_noise=pl_noise.to(dev).requires_grad_(True))
+        mw.generator_ema = keep
+        misc.exponential_moving_average(model_ema=keep, model_train=G)
+        assert set(got) == set(want), (sorted(got), sorted(want))
+        for k in want:
+            assert rel_err(got[k], want[k]) < tol, (it, k, float(got[k]), float(want[k]))
+    worst = 0.0
+    for n, p in G.named_parameters():
+        worst = max(worst, rel_err(p, oracle.sd_g[n]))
+        assert rel_err(dict(keep.named_parameters())[n], oracle.ema[n]) < max(tol, 1e-5), n
+    for n, p in D.named_parameters():
+        worst = max(worst, rel_err(p, oracle.sd_d[n]))
+    return worst
+
+
+def test_train_step_host_logic_matches_oracle(oracle_backend):
+    assert run_parity("cpu", 2e-4) < 2e-3
+
+
+@pytest.mark.gpu
+def test_train_step_cuda_core_engine_matches_oracle(built_library):
+    from multi_stylegan_b200 import _C, _lib
+    old = _C.conv_flags
+    _C.conv_flags = _lib.CONV_FORCE_SIMT
+    try:
+        assert run_parity("cuda:0", 5e-4) < 5e-3
+    finally:
+        _C.conv_flags = old
+
+
+@pytest.mark.gpu
+def test_train_step_tensor_core_engine_matches_oracle(built_library):
+    # losses within the TF32 tolerance; updated weights move by lr * sign-like Adam steps, so compare loosely
+    assert run_parity("cuda:0", 2e-2) < 0.2
+
+
+# ---- data parallel: world_size 2 over gloo ---------------------------------------------------------------
+def _dp_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from tests import backend_oracle
+    from multi_stylegan_b200 import _C, dist as mdist
+    for name in backend_oracle.__all__:
+        setattr(_C, name, getattr(backend_oracle, name))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        G, D = build("cpu", seed=rank)             # different init per rank: broadcast must fix it
+        mdist.broadcast_parameters([G, D])
+        gen = torch.Generator().manual_seed(5)
+        x = torch.rand(world * 2, 2, 3, 32, 32, generator=gen)
+        shard = x[rank * 2:(rank + 1) * 2]
+        s, p = D(shard)
+        (torch.nn.functional.softplus(-s).mean() + torch.nn.functional.softplus(-p).mean()).backward()
+        n = mdist.all_reduce_gradients(list(D.parameters()))
+        r = torch.tensor([float(rank)])
+        mdist.all_reduce_mean_(r)
+        torch.save({"grads": {k: v.grad.clone() for k, v in D.named_parameters()}, "n": n, "r": r,
+                    "w0": next(iter(D.parameters())).detach().clone()}, os.path.join(tmp, "rank%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_allreduce_gloo(tmp_path, oracle_backend):
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_dp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(os.path.join(str(tmp_path), "rank%d.pt" % r), weights_only=False) for r in range(world)]
+    # single-process reference: mean over shards of the per-shard gradients (MinibatchStdDev is per shard,
+    # exactly as under the reference's DataParallel, u_net_2d_discriminator.py:212-214)
+    G, D = build("cpu", seed=0)
+    gen = torch.Generator().manual_seed(5)
+    x = torch.rand(world * 2, 2, 3, 32, 32, generator=gen)
+    acc = None
+    for r in range(world):
+        D.zero_grad()
+        s, p = D(x[r * 2:(r + 1) * 2])
+        (torch.nn.functional.softplus(-s).mean() + torch.nn.functional.softplus(-p).mean()).backward()
+        g = {k: v.grad.clone() / world for k, v in D.named_parameters()}
+        acc = g if acc is None else {k: acc[k] + g[k] for k in g}
+    for o in outs:
+        assert o["n"] == sum(p.numel() for p in D.parameters())
+        assert abs(float(o["r"]) - 0.5) < 1e-6
+        assert torch.equal(o["w0"], next(iter(D.parameters())).detach())      # broadcast from rank 0
+        for k in acc:
+            assert rel_err(o["grads"][k], acc[k]) < 1e-5, k
+    for k in acc:
+        assert torch.equal(outs[0]["grads"][k], outs[1]["grads"][k])
