@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""bench.py — G+D train-step throughput (sequences/s) of the B200-native Multi-StyleGAN hot path.
+
+  python bench.py --gpus N --steps K --warmup W            # this package (CUDA, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPUs
+
+Workload (BASELINE.json config 3): full generator + U-Net discriminator training iteration of
+model_wrapper._gan_training — D step, lazy R1 (every 16th), G step, lazy path length (every 16th, half
+batch), EMA — default 512-channel / 256x256 model, batch 8 per GPU (weak scaling), synthetic data,
+random-init weights, no ADA / CutMix (epoch-0 behaviour).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train_step_sequences_per_sec"
+UNIT = "sequences/s"
+
+
+def workload_config(args, world):
+    return {"workload": "full G+D train step (BASELINE config 3): default 512ch/256x256 Multi-StyleGAN generator + "
+                        "U-Net discriminator, NS-logistic loss, lazy R1 + path length every 16th iteration, EMA",
+            "per_gpu_batch": args.batch, "global_batch": args.batch * world, "resolution": 256,
+            "parallelism": "dp%d" % world, "ada": bool(args.ada),
+            "l2_policy": "working set per step (>= 10 GiB of activations) >> 126 MB L2; inputs rotate over a pool"}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return p.get("hbm_gbs", 6650.0), p.get("bf16_tflops", 1590.0), p.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown," \
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown," \
+             "clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm (oracle port) on the host cores
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(max_steps: int, warmup: int, budget_s: float):
+    """One *plain* training iteration (D step + G step + EMA, no lazy regularisers) of the reference
+    algorithm at batch 1 on the default model, all host threads.  Returns (seconds per step, steps timed)."""
+    import torch
+    from multi_stylegan_b200 import config
+    import multi_stylegan_b200.multi_stylegan_generator as G_mod
+    import multi_stylegan_b200.u_net_2d_discriminator as D_mod
+    from oracle.train_step import OracleTrainer
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    G = G_mod.Generator(config.multi_style_gan_generator_config)        # parameter containers only (CPU)
+    D = D_mod.Discriminator(config.u_net_2d_discriminator_config, no_rfp=True)
+    hp = dict(config.generation_hyperparameters)
+    hp["lazy_discriminator_regularization"] = 10 ** 9
+    hp["lazy_generator_regularization"] = 10 ** 9
+    tr = OracleTrainer(dict(G.state_dict()), dict(D.state_dict()), (2e-4, 2e-6), 6e-4, hp["betas"], hp,
+                       dead_branch=True)
+    del G, D
+    times = []
+    t_start = time.time()
+    for i in range(warmup + max_steps):
+        real = torch.rand(1, 2, 3, 256, 256)
+        z = [[torch.randn(1, 512), torch.randn(1, 512)] for _ in range(2)]
+        t0 = time.time()
+        tr.step(real, z[0], z[1], None, None, None, None, 7, None)
+        dt = time.time() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.time() - t_start > budget_s and times:
+            break
+    return min(times), len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    sec, n = cpu_reference_step_time(max(1, args.steps), min(args.warmup, 1) if args.steps > 1 else 0, args.cpu_budget)
+    value = 1.0 / sec
+    cores = os.cpu_count() or 1
+    sample = "oracle port of the reference trainer (oracle/train_step.py over oracle/model.py; the reference's own " \
+             "modules are not available on this box), one plain iteration (D step + G step, dead second branch " \
+             "evaluated as the reference does, no lazy regularisers) at batch 1, best of %d, torch %s CPU" % (n, torch.__version__)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1), "impl": "reference",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as tdist
+    from multi_stylegan_b200 import _C, _lib, config, dist as mdist
+    import multi_stylegan_b200.multi_stylegan_generator as G_mod
+    import multi_stylegan_b200.u_net_2d_discriminator as D_mod
+    from multi_stylegan_b200.adaptive_discriminator_augmentation import AdaptiveDiscriminatorAugmentation
+    from multi_stylegan_b200.model_wrapper import ModelWrapper
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    _lib.lib()
+    local_rank = mdist.init_from_env()
+    world, rank = mdist.world_size(), mdist.rank()
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    torch.manual_seed(0)
+    B = args.batch
+    G = G_mod.Generator(config.multi_style_gan_generator_config, compute_dead_branch=False).to(dev)
+    D = D_mod.Discriminator(config.u_net_2d_discriminator_config, no_rfp=True).to(dev)
+    mdist.broadcast_parameters([G, D])
+    hp = dict(config.generation_hyperparameters)
+    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-4, lr_style=2e-6), betas=hp["betas"])
+    opt_d = torch.optim.Adam(D.parameters(), lr=6e-4, betas=hp["betas"])
+    Dw = AdaptiveDiscriminatorAugmentation(D) if args.ada else D
+    if args.ada:
+        Dw.p = 0.5
+    mw = ModelWrapper(G, Dw, opt_g, opt_d, hyperparameters=hp, device=dev)
+    mw._d_params = lambda: list(D.parameters())
+    torch.manual_seed(1234 + rank)
+    pool = [torch.rand(B, 2, 3, 256, 256, device=dev) for _ in range(4)]
+    host_pool = [p.cpu().pin_memory() for p in pool]
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up: W plain iterations + one iteration with both lazy regularisers (their kernels and shapes)
+    for i in range(max(args.warmup, 3)):
+        mw.iteration = 14 if i == 0 else 0
+        mw.train_step(pool[i % len(pool)])
+    barrier()
+
+    def timed(e2e: bool):
+        mw.iteration = 0
+        launches0 = _C.launch_count()
+        _C.profile_enable(not e2e)
+        sampler = ClockSampler(local_rank)
+        if not e2e and rank == 0:
+            sampler.start()
+        barrier()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        start.record()
+        last = None
+        for i in range(args.steps):
+            if e2e:
+                real = host_pool[i % len(host_pool)].to(dev, non_blocking=True)
+                out = mw.train_step(real)
+                last = {k: float(v) for k, v in out.items()}           # device -> host read of the step's losses
+            else:
+                mw.train_step(pool[i % len(pool)])
+        end.record()
+        barrier()
+        wall = time.time() - t0
+        ms = start.elapsed_time(end)
+        clocks = sampler.stop() if (not e2e and rank == 0) else None
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        prof = _C.profile_summary() if not e2e else None
+        _C.profile_enable(False)
+        return float(t.item()), _C.launch_count() - launches0, clocks, prof, last, wall
+
+    ms, launches, clocks, prof, _, wall = timed(False)
+    ms_e2e, _, _, _, last_losses, _ = timed(True)
+
+    if rank != 0:
+        return
+    seqs = world * B * args.steps
+    value = seqs / (ms / 1e3)
+    lazy = args.steps // hp["lazy_generator_regularization"]
+    cfg = workload_config(args, world)
+    cfg["lazy_r1_and_pl_steps_in_timed_region"] = lazy
+    hbm, bf16_burst, bf16_sust, src = peaks()
+    tf32_peak = bf16_sust / 2.0
+    roof = None
+    if prof:
+        top = max(prof, key=lambda e: e["ms_total"])
+        achieved = top["flops_per_launch"] * top["launches"] / (top["ms_total"] * 1e-3) / 1e12
+        conv_ms = sum(e["ms_total"] for e in prof)
+        conv_flops = sum(e["flops_per_launch"] * e["launches"] for e in prof)
+        roof = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                "frac": achieved / tf32_peak, "traffic": None,
+                "kernel": "tc_%s (tcgen05 kind::tf32) taps=%d K=%d N=%d pixels=%d" % (
+                    top["kind"], top["taps"], top["k_channels"], top["n_channels"], top["pixels"]),
+                "launches": top["launches"], "avg_ms": top["ms_total"] / top["launches"],
+                "share_of_step": top["ms_total"] / ms,
+                "peak_note": "TF32 dense = 1/2 of the %s bf16 sustained rate (%.0f TFLOP/s) in MEASURED_PEAKS.json" % (src, bf16_sust),
+                "all_tcgen05_conv_kernels": {"ms": conv_ms, "share_of_step": conv_ms / ms,
+                                             "tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None}}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic", "config": cfg,
+            "e2e": {"value": seqs / (ms_e2e / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": B * 2 * 3 * 256 * 256 * 4, "d2h_bytes_per_step": 4 * len(last_losses or {})},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "conv_engine": _C.conv2d_last_engine()}
+    if world == 1 and not args.no_cpu_baseline:
+        sec, n = cpu_reference_step_time(1, 0, args.cpu_budget)
+        import torch as _t
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "oracle port, one plain iteration (D step + G step, no lazy regularisers, dead "
+                                          "branch evaluated like the reference) at batch 1, %d run(s)" % n}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
+    ap.add_argument("--ada", action="store_true", help="wrap D in adaptive discriminator augmentation (config 4)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU work allowed for the reference arm")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,20 @@ int msg_tensor_core_path_available(void);
  * every tcgen05 kernel fills with progress markers and its first shared-memory operand tiles. */
 const uint32_t* msg_debug_buffer(size_t* words);
 
+/* Per-kernel timing of the tcgen05 conv kernels with CUDA events recorded on the launching stream.
+ * msg_profile_enable(1) resets and starts; after the caller has synchronised the stream(s),
+ * msg_profile_summary() fills one entry per distinct (kind, taps, K channels, N channels, pixels). */
+typedef struct {
+  int kind;                 /* 0 = pixel-major GEMM (forward / dgrad), 1 = pixel-reduction GEMM (wgrad) */
+  int taps, k_channels, n_channels;
+  int64_t pixels;           /* B * PH * PW of one launch                                            */
+  int64_t launches;
+  double ms_total;          /* sum of event-measured durations                                      */
+  double flops_per_launch;  /* algorithmic: 2 * pixels * n_channels * k_channels * taps             */
+} msg_profile_entry;
+void msg_profile_enable(int on);
+int msg_profile_summary(msg_profile_entry* out, int max_entries);
+
 /* -------------------------------------------------------------------------------------------
  * fused_bias_act  — replaces fused_act_cuda.fused_bias_act
  *   multi_stylegan/op_static/fused_bias_act.cpp:11-20, fused_bias_act_kernel.cu:18-99

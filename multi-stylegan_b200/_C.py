@@ -291,6 +291,23 @@ def tensor_core_path_available() -> bool:
     return bool(_lib.lib().msg_tensor_core_path_available())
 
 
+def profile_enable(on: bool) -> None:
+    _lib.lib().msg_profile_enable(1 if on else 0)
+
+
+def profile_summary():
+    """List of dicts, one per distinct tcgen05 conv launch shape (call after torch.cuda.synchronize())."""
+    buf = (_lib.ProfileEntry * 256)()
+    n = _lib.lib().msg_profile_summary(buf, 256)
+    out = []
+    for e in buf[:n]:
+        if e.launches:
+            out.append(dict(kind="pixgemm" if e.kind == 0 else "redgemm", taps=e.taps, k_channels=e.k_channels,
+                            n_channels=e.n_channels, pixels=e.pixels, launches=e.launches, ms_total=e.ms_total,
+                            flops_per_launch=e.flops_per_launch))
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.lib().msg_launch_count())
 

@@ -30,6 +30,13 @@ class ConvDesc(ctypes.Structure):
                 ("w_batch_stride", ctypes.c_int64), ("layout", ctypes.c_int)]
 
 
+class ProfileEntry(ctypes.Structure):
+    """msg_profile_entry (include/msg_b200.h)."""
+    _fields_ = [("kind", ctypes.c_int), ("taps", ctypes.c_int), ("k_channels", ctypes.c_int),
+                ("n_channels", ctypes.c_int), ("pixels", ctypes.c_int64), ("launches", ctypes.c_int64),
+                ("ms_total", ctypes.c_double), ("flops_per_launch", ctypes.c_double)]
+
+
 def sources():
     return sorted(os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith(".cu"))
 
@@ -60,6 +67,8 @@ _SIGNATURES = {
     "msg_launch_count": (_c.c_uint64, []),
     "msg_tensor_core_path_available": (_c.c_int, []),
     "msg_debug_buffer": (_c.POINTER(_c.c_uint32), [_c.POINTER(_c.c_size_t)]),
+    "msg_profile_enable": (None, [_c.c_int]),
+    "msg_profile_summary": (_c.c_int, [_c.POINTER(ProfileEntry), _c.c_int]),
     "msg_fused_bias_act": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                       _c.c_double, _c.c_double, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int,
                                       _c.c_void_p]),

@@ -62,6 +62,8 @@ int simt_redgemm(const RedGemm& g, cudaStream_t st);
 
 bool tc_available();
 uint32_t* tc_debug_host(size_t* words);
+void tc_profile_enable(int on);
+int tc_profile_summary(msg_profile_entry* out, int max_entries);
 bool tc_pixgemm_supported(const PixGemm& g);
 size_t tc_pixgemm_workspace(const PixGemm& g);
 int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "conv_common.cuh"
 #include "sm100_ptx.cuh"
@@ -99,6 +101,68 @@ static uint32_t tc_variant() {
     v = e ? atoi(e) : 0;
   }
   return (uint32_t)v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-kernel timing with CUDA events on the launching stream (bench.py's roofline numbers).
+// ------------------------------------------------------------------------------------------------
+struct ProfSlot { msg_profile_entry e; };
+static bool g_prof_on = false;
+static std::vector<ProfSlot> g_prof_slots;
+struct ProfPair { cudaEvent_t a, b; int slot; };
+static std::vector<ProfPair> g_prof_pending;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pool;
+static std::mutex g_prof_mu;
+
+static int prof_begin(int kind, int taps, int k_channels, int n_channels, int64_t pixels, double flops,
+                      cudaStream_t st, cudaEvent_t* stop_out) {
+  if (!g_prof_on) return -1;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  int slot = -1;
+  for (size_t i = 0; i < g_prof_slots.size(); ++i) {
+    const msg_profile_entry& e = g_prof_slots[i].e;
+    if (e.kind == kind && e.taps == taps && e.k_channels == k_channels && e.n_channels == n_channels &&
+        e.pixels == pixels) { slot = (int)i; break; }
+  }
+  if (slot < 0) {
+    if (g_prof_slots.size() >= 256) return -1;
+    ProfSlot s{}; s.e.kind = kind; s.e.taps = taps; s.e.k_channels = k_channels; s.e.n_channels = n_channels;
+    s.e.pixels = pixels; s.e.flops_per_launch = flops;
+    g_prof_slots.push_back(s);
+    slot = (int)g_prof_slots.size() - 1;
+  }
+  cudaEvent_t a, b;
+  if (!g_prof_pool.empty()) { a = g_prof_pool.back().first; b = g_prof_pool.back().second; g_prof_pool.pop_back(); }
+  else if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return -1;
+  cudaEventRecord(a, st);
+  g_prof_pending.push_back({a, b, slot});
+  *stop_out = b;
+  return slot;
+}
+static void prof_end(int slot, cudaEvent_t stop, cudaStream_t st) { if (slot >= 0) cudaEventRecord(stop, st); }
+
+void tc_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  for (auto& p : g_prof_pending) g_prof_pool.push_back({p.a, p.b});
+  g_prof_pending.clear();
+  g_prof_slots.clear();
+}
+int tc_profile_summary(msg_profile_entry* out, int max_entries) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& p : g_prof_pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+      g_prof_slots[p.slot].e.launches += 1;
+      g_prof_slots[p.slot].e.ms_total += ms;
+    }
+    g_prof_pool.push_back({p.a, p.b});
+  }
+  (void)cudaGetLastError();
+  g_prof_pending.clear();
+  int n = 0;
+  for (auto& s : g_prof_slots) { if (n < max_entries) out[n++] = s.e; }
+  return n;
 }
 
 // 4-D fp32 tensor map; dims[0] is the contiguous dimension, strides_bytes for dims 1..3.
@@ -596,13 +660,19 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.vec_store = (g.os.sc == 1 && al16(g.out) && g.os.sx % 4 == 0 && g.os.sy % 4 == 0 && g.os.sb % 4 == 0) ? 1 : 0;
   dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)(Npad / BN), (unsigned)g.B);
   if (grid.y > 65535) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): too many N tiles");
+  cudaEvent_t pstop;
+  const int pslot = prof_begin(0, g.ntaps, g.Cr, g.N, (int64_t)g.B * g.PH * g.PW,
+                               2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);
+  int rc;
   switch (BN) {
-    case 256: return launch_pix<256>(tmA, tmB, p, grid, st);
-    case 128: return launch_pix<128>(tmA, tmB, p, grid, st);
-    case 64: return launch_pix<64>(tmA, tmB, p, grid, st);
-    case 32: return launch_pix<32>(tmA, tmB, p, grid, st);
-    default: return launch_pix<16>(tmA, tmB, p, grid, st);
+    case 256: rc = launch_pix<256>(tmA, tmB, p, grid, st); break;
+    case 128: rc = launch_pix<128>(tmA, tmB, p, grid, st); break;
+    case 64: rc = launch_pix<64>(tmA, tmB, p, grid, st); break;
+    case 32: rc = launch_pix<32>(tmA, tmB, p, grid, st); break;
+    default: rc = launch_pix<16>(tmA, tmB, p, grid, st); break;
   }
+  prof_end(pslot, pstop, st);
+  return rc;
 }
 
 // ---- RedGemm host -------------------------------------------------------------------------------
@@ -694,6 +764,9 @@ int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.Npad = pl.Npad; p.Cpad = pl.Cpad; p.splits = pl.splits; p.part = part;
   p.variant = tc_variant(); p.dbg = tc_debug_buffer();
   dim3 grid((unsigned)((pl.Npad / 128) * p.ctiles), (unsigned)(g.ntaps * pl.BS), (unsigned)pl.splits);
+  cudaEvent_t pstop;
+  const int pslot = prof_begin(1, g.ntaps, g.C, g.N, (int64_t)g.B * g.PH * g.PW,
+                               2.0 * g.B * g.PH * g.PW * (double)g.N * g.C * g.ntaps, st, &pstop);
   int rc;
   switch (pl.BN) {
     case 256: rc = launch_red<256>(tmG, tmI, p, grid, st); break;
@@ -701,6 +774,7 @@ int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     case 64: rc = launch_red<64>(tmG, tmI, p, grid, st); break;
     default: rc = launch_red<32>(tmG, tmI, p, grid, st); break;
   }
+  prof_end(pslot, pstop, st);
   if (rc) return rc;
 
   RedReduceParams rp{};

@@ -122,6 +122,11 @@ extern "C" const char* msg_last_error(void) { return g_last_error; }
 extern "C" uint64_t msg_launch_count(void) { return g_launch_count.load(); }
 extern "C" int msg_tensor_core_path_available(void) { return tc_available() ? 1 : 0; }
 extern "C" const uint32_t* msg_debug_buffer(size_t* words) { return tc_debug_host(words); }
+extern "C" void msg_profile_enable(int on) { tc_profile_enable(on); }
+extern "C" int msg_profile_summary(msg_profile_entry* out, int max_entries) {
+  if (!out || max_entries <= 0) return 0;
+  return tc_profile_summary(out, max_entries);
+}
 
 extern "C" int msg_modulate_weights(float* w_mod, float* demod_out, const float* W, const float* s, int B, int O,
                                     int C, int taps, float scale, int demodulate, msg_stream_t stream) {

@@ -17,7 +17,9 @@ def _clip_(params: List[torch.Tensor], grads: List[torch.Tensor], max_norm: floa
 
 
 class OracleTrainer:
-    def __init__(self, sd_g: Dict[str, torch.Tensor], sd_d: Dict[str, torch.Tensor], g_groups, lr_d: float, betas, hp):
+    def __init__(self, sd_g: Dict[str, torch.Tensor], sd_d: Dict[str, torch.Tensor], g_groups, lr_d: float, betas, hp,
+                 dead_branch: bool = False):
+        self.dead_branch = dead_branch
         self.sd_g = {k: v.clone().requires_grad_(v.dtype.is_floating_point and not k.startswith("noises.")
                                                  and not k.endswith(".kernel")) for k, v in sd_g.items()}
         self.sd_d = {k: v.clone().requires_grad_(not k.endswith(".kernel")) for k, v in sd_d.items()}
@@ -47,7 +49,8 @@ class OracleTrainer:
         hp, out = self.hp, {}
         self.iteration += 1
         with torch.no_grad():
-            fake = om.generator_forward({k: v.detach() for k, v in self.sd_g.items()}, z_d, noise_d, inject)
+            fake = om.generator_forward({k: v.detach() for k, v in self.sd_g.items()}, z_d, noise_d, inject,
+                                        dead_branch=self.dead_branch)
         rs, rp = om.discriminator_forward(self.sd_d, real)
         fs, fp = om.discriminator_forward(self.sd_d, fake)
         lr_, lf_ = om.ns_discriminator_loss(rs, fs)
@@ -59,7 +62,7 @@ class OracleTrainer:
             r1 = om.r1_penalty(self.sd_d, real)
             out["loss_discriminator_regularization"] = r1.detach()
             self._apply(self.sd_d, self.d_names, hp["w_discriminator_regularization_r1"] * r1, self.opt_d)
-        fake = om.generator_forward(self.sd_g, z_g, noise_g, inject)
+        fake = om.generator_forward(self.sd_g, z_g, noise_g, inject, dead_branch=self.dead_branch)
         fs, fp = om.discriminator_forward(self.sd_d, fake)
         lg, lgp = om.ns_generator_loss(fs), om.ns_generator_loss(fp)
         out.update(loss_generator=lg.detach(), loss_generator_pixel_wise=lgp.detach())

@@ -8,7 +8,7 @@ import torch.multiprocessing as mp
 
 from oracle.make_golden import TINY_D, TINY_G, randomize
 from tests.conftest import rel_err
-from tests.oracle_step import OracleTrainer
+from oracle.train_step import OracleTrainer
 
 HP = None
 
