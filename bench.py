@@ -197,6 +197,7 @@ def run_ours(args):
         t0 = time.time()
         start.record()
         last = None
+        torch.cuda.nvtx.range_push("timed_e2e" if e2e else "timed")
         for i in range(args.steps):
             if e2e:
                 real = host_pool[i % len(host_pool)].to(dev, non_blocking=True)
@@ -204,6 +205,7 @@ def run_ours(args):
                 last = {k: float(v) for k, v in out.items()}           # device -> host read of the step's losses
             else:
                 mw.train_step(pool[i % len(pool)])
+        torch.cuda.nvtx.range_pop()
         end.record()
         barrier()
         wall = time.time() - t0
@@ -221,6 +223,12 @@ def run_ours(args):
 
     if rank != 0:
         return
+    if args.profile_out and prof:
+        with open(args.profile_out, "w") as f:
+            for e in sorted(prof, key=lambda e: -e["ms_total"]):
+                e = dict(e, avg_ms=e["ms_total"] / e["launches"],
+                         tflops=e["flops_per_launch"] * e["launches"] / (e["ms_total"] * 1e-3) / 1e12)
+                f.write(json.dumps(e) + "\n")
     seqs = world * B * args.steps
     value = seqs / (ms / 1e3)
     lazy = args.steps // hp["lazy_generator_regularization"]
@@ -268,6 +276,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
     ap.add_argument("--ada", action="store_true", help="wrap D in adaptive discriminator augmentation (config 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-shape tcgen05 conv kernel timings (JSON lines)")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU work allowed for the reference arm")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -174,6 +174,22 @@ int msg_noise_bias_act(float* out, const float* x, const float* noise, const flo
                        const float* bias, int B, int C, int64_t HW, int64_t noise_batch_stride,
                        float alpha, float scale, msg_stream_t stream);
 
+/* Same epilogue on channels-last activations x [rows = B*H*W, C] (C % 4 == 0, 16-byte aligned), optionally in
+ * its masked ("backward") form, plus the fused first-order backward:
+ *   forward      (ref == NULL): out = lrelu(x + noise_w[0]*noise[row % noise_period] + bias[c], alpha) * scale
+ *   masked       (ref != NULL): out = (ref > 0 ? v : alpha*v) * scale, v as above  — the double-backward
+ *                               (op_static/fused_act.py:44-51 extended by the noise term)
+ *   backward: dx = (ref > 0 ? g : alpha*g) * scale ; dbias[c] = sum_rows dx ; dnoise_w[0] = sum noise[row] * dx
+ *             (dbias / dnoise_w may be NULL; deterministic two-stage reduction in `workspace`).
+ * noise_period = H*W when one noise map is shared by the batch, rows when every sample has its own. */
+int msg_noise_bias_act_nhwc(float* out, const float* x, const float* ref, const float* noise,
+                            const float* noise_w, const float* bias, int64_t rows, int C,
+                            int64_t noise_period, float alpha, float scale, msg_stream_t stream);
+size_t msg_noise_bias_act_nhwc_bwd_workspace(int64_t rows, int C);
+int msg_noise_bias_act_nhwc_bwd(float* dx, float* dbias, float* dnoise_w, const float* g, const float* ref,
+                                const float* noise, int64_t rows, int C, int64_t noise_period, float alpha,
+                                float scale, void* workspace, size_t workspace_bytes, msg_stream_t stream);
+
 /* -------------------------------------------------------------------------------------------
  * ADA geometric warp — multi_stylegan/adaptive_discriminator_augmentation.py:116-199
  *   out[b,c,y,x] = bilinear sample of in[b,c] at (x,y,1) * theta[b]^T  in pixel coordinates,

@@ -84,21 +84,37 @@ def _workspace(nbytes: int, device) -> Tuple[Optional[torch.Tensor], Optional[ct
 # fused_bias_act — same signature as the reference's fused_act_cuda.fused_bias_act
 # (multi_stylegan/op_static/fused_bias_act.cpp:11-20)
 # ---------------------------------------------------------------------------------------------------
+def _cl_only(t: torch.Tensor) -> bool:
+    """4-D tensor stored channels-last (and not also plain-contiguous): memory order [B, H, W, C]."""
+    return t.dim() == 4 and not t.is_contiguous() and t.is_contiguous(memory_format=torch.channels_last)
+
+
 def fused_bias_act(input: torch.Tensor, bias: torch.Tensor, refer: torch.Tensor, act: int, grad: int,
                    alpha: float, scale: float) -> torch.Tensor:
+    """Channels-last inputs are processed in place of their layout (bias index = memory index % C) and the
+    result keeps the layout; anything else is made contiguous like the reference launcher does."""
     _require_cuda(input, "input")
     _require_cuda(bias, "bias")
-    x = _aligned(input)
+    cl = _cl_only(input) and input.data_ptr() % 16 == 0
+    fmt = torch.channels_last if cl else torch.contiguous_format
+    x = input if cl else _aligned(input)
     b = bias.contiguous()
-    ref = _aligned(refer) if refer.numel() else refer
+    ref = refer
+    if refer.numel():
+        ref = refer.contiguous(memory_format=fmt) if refer.dim() == 4 else refer.contiguous()
+        if ref.data_ptr() % 16:
+            ref = ref.clone(memory_format=fmt if refer.dim() == 4 else torch.contiguous_format)
     dt = _dtype_code(x, "fused_bias_act")
     if b.numel() and b.dtype != x.dtype:
         raise RuntimeError("fused_bias_act: bias dtype %s != input dtype %s" % (b.dtype, x.dtype))
-    if ref.numel() and (ref.dtype != x.dtype or ref.numel() != x.numel()):
+    if ref.numel() and (ref.dtype != x.dtype or ref.shape != x.shape):
         raise RuntimeError("fused_bias_act: refer must match input in dtype and size")
-    step_b = 1
-    for i in range(2, x.dim()):
-        step_b *= x.size(i)
+    if cl:
+        step_b = 1
+    else:
+        step_b = 1
+        for i in range(2, x.dim()):
+            step_b *= x.size(i)
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
         rc = _lib.lib().msg_fused_bias_act(_ptr(out), _ptr(x), _ptr(b), _ptr(ref), int(act), int(grad),
@@ -111,19 +127,27 @@ def fused_bias_act(input: torch.Tensor, bias: torch.Tensor, refer: torch.Tensor,
 def fused_bias_act_bwd(grad_output: torch.Tensor, out: torch.Tensor, alpha: float, scale: float,
                        channels: int) -> Tuple[torch.Tensor, torch.Tensor]:
     """(grad_input, grad_bias) of lrelu(x + b) * scale in one pass over the data
-    (reference: op_static/fused_act.py:31-40 = kernel + separate ATen sum)."""
+    (reference: op_static/fused_act.py:31-40 = kernel + separate ATen sum).  Follows the layout of `out`."""
     _require_cuda(grad_output, "grad_output")
     _require_cuda(out, "out")
-    g = _aligned(grad_output)
-    ref = _aligned(out)
-    dt = _dtype_code(g, "fused_bias_act_bwd")
-    if ref.dtype != g.dtype or ref.shape != g.shape:
+    if out.shape != grad_output.shape or out.dtype != grad_output.dtype:
         raise RuntimeError("fused_bias_act_bwd: out must match grad_output")
+    cl = _cl_only(out) and out.data_ptr() % 16 == 0
+    if cl:
+        ref = out
+        g = grad_output.contiguous(memory_format=torch.channels_last)
+        if g.data_ptr() % 16:
+            g = g.clone(memory_format=torch.channels_last)
+    else:
+        g = _aligned(grad_output)
+        ref = _aligned(out)
+    dt = _dtype_code(g, "fused_bias_act_bwd")
     if g.dim() < 2 or g.size(1) != channels:
         raise RuntimeError("fused_bias_act_bwd: dim 1 of grad_output must be the bias dimension")
     step_b = 1
-    for i in range(2, g.dim()):
-        step_b *= g.size(i)
+    if not cl:
+        for i in range(2, g.dim()):
+            step_b *= g.size(i)
     dx = torch.empty_like(g)
     db = torch.empty(channels, dtype=g.dtype, device=g.device)
     L = _lib.lib()
@@ -362,6 +386,81 @@ def noise_bias_act(x: torch.Tensor, noise: Optional[torch.Tensor], noise_w: Opti
                                            _ptr(bias), B, C, HW, nbs, float(alpha), float(scale), _stream(x))
     _lib.check(rc, "noise_bias_act")
     return out
+
+
+def _cl(t: torch.Tensor) -> torch.Tensor:
+    """Dense channels-last, 16-byte aligned (no copy when the producer was one of our kernels)."""
+    t = t.contiguous(memory_format=torch.channels_last)
+    if t.data_ptr() % 16:
+        t = t.clone(memory_format=torch.channels_last)
+    return t
+
+
+def noise_bias_act_cl(x: torch.Tensor, ref: Optional[torch.Tensor], noise: Optional[torch.Tensor],
+                      noise_w: Optional[torch.Tensor], bias: Optional[torch.Tensor], alpha: float,
+                      scale: float) -> torch.Tensor:
+    """Channels-last StyledConv2d epilogue (multi_stylegan_generator.py:292 + op_static/fused_act.py:58):
+    v = x + noise_w * noise + bias[c];  ref None: lrelu(v) * scale;  else (ref > 0 ? v : alpha v) * scale.
+    x [B,C,H,W] (C % 4 == 0), noise [B or 1, 1, H, W]."""
+    _check_f32(x, "x")
+    x = _cl(x)
+    B, C, H, W = x.shape
+    if C % 4:
+        raise RuntimeError("noise_bias_act_cl: channel count must be a multiple of 4")
+    rows = B * H * W
+    if ref is not None:
+        _check_f32(ref, "ref")
+        ref = _cl(ref)
+        if ref.shape != x.shape:
+            raise RuntimeError("noise_bias_act_cl: ref must match x")
+    period = 1
+    if noise is not None:
+        _check_f32(noise, "noise")
+        noise = _aligned(noise)
+        if noise.numel() not in (H * W, rows):
+            raise RuntimeError("noise_bias_act_cl: noise must be [B or 1, 1, H, W]")
+        period = noise.numel()
+        noise_w = _aligned(noise_w)
+    if bias is not None:
+        bias = _aligned(bias)
+        if bias.numel() != C:
+            raise RuntimeError("noise_bias_act_cl: bias must have C elements")
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = _lib.lib().msg_noise_bias_act_nhwc(_ptr(out), _ptr(x), _ptr(ref), _ptr(noise),
+                                                _ptr(noise_w) if noise is not None else None, _ptr(bias), rows, C,
+                                                period, float(alpha), float(scale), _stream(x))
+    _lib.check(rc, "noise_bias_act_nhwc")
+    return out
+
+
+def noise_bias_act_cl_bwd(grad_output: torch.Tensor, out: torch.Tensor, noise: Optional[torch.Tensor], alpha: float,
+                          scale: float):
+    """(dx, dbias [C], dnoise_w [1] or None) in one pass + a tiny deterministic reduction."""
+    _check_f32(grad_output, "grad_output")
+    _check_f32(out, "out")
+    g = _cl(grad_output)
+    ref = _cl(out)
+    B, C, H, W = g.shape
+    rows = B * H * W
+    period = 1
+    dnw = None
+    if noise is not None:
+        noise = _aligned(noise)
+        period = noise.numel()
+        dnw = torch.empty(1, dtype=torch.float32, device=g.device)
+    dx = torch.empty_like(g)
+    db = torch.empty(C, dtype=torch.float32, device=g.device)
+    L = _lib.lib()
+    with torch.cuda.device(g.device):
+        nbytes = L.msg_noise_bias_act_nhwc_bwd_workspace(rows, C)
+        ws, wsp = _workspace(nbytes, g.device)
+        rc = L.msg_noise_bias_act_nhwc_bwd(_ptr(dx), ctypes.c_void_p(db.data_ptr()),
+                                           ctypes.c_void_p(dnw.data_ptr()) if dnw is not None else None, _ptr(g),
+                                           _ptr(ref), _ptr(noise), rows, C, period, float(alpha), float(scale), wsp,
+                                           nbytes, _stream(g))
+    _lib.check(rc, "noise_bias_act_nhwc_bwd")
+    return dx, db, dnw
 
 
 def affine_warp(x: torch.Tensor, theta: torch.Tensor, mode: int = 0) -> torch.Tensor:

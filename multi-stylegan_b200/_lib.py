@@ -91,6 +91,12 @@ _SIGNATURES = {
                                         _c.c_int, _c.c_int, _c.c_float, _c.c_int, _c.c_void_p]),
     "msg_noise_bias_act": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                       _c.c_int, _c.c_int64, _c.c_int64, _c.c_float, _c.c_float, _c.c_void_p]),
+    "msg_noise_bias_act_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                           _c.c_int64, _c.c_int, _c.c_int64, _c.c_float, _c.c_float, _c.c_void_p]),
+    "msg_noise_bias_act_nhwc_bwd_workspace": (_c.c_size_t, [_c.c_int64, _c.c_int]),
+    "msg_noise_bias_act_nhwc_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                               _c.c_int64, _c.c_int, _c.c_int64, _c.c_float, _c.c_float, _c.c_void_p,
+                                               _c.c_size_t, _c.c_void_p]),
     "msg_affine_warp": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                    _c.c_int, _c.c_void_p]),
 }

@@ -48,6 +48,44 @@ s2d_nhwc_kernel(float* __restrict__ xs, const float* __restrict__ x, int B, int 
   }
 }
 
+// same, C % 4 == 0 (C4 == C) and 16-byte aligned: one float4 (4 channels) per thread, no per-element div/mod
+__global__ void __launch_bounds__(256)
+s2d_nhwc_vec_kernel(float4* __restrict__ xs, const float4* __restrict__ x, int B, int Cq, int H, int W, int H2, int W2) {
+  // grid.x covers (x2, ph, cq) of one output row (b, y2) = blockIdx.y
+  const int row = blockIdx.y;
+  const int b = row / H2, y2 = row - b * H2;
+  const int per_row = W2 * 4 * Cq;
+  float4* orow = xs + (int64_t)row * per_row;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_row; i += gridDim.x * blockDim.x) {
+    const int cq = i % Cq;
+    const int t = i / Cq;
+    const int ph = t & 3, x2 = t >> 2;
+    const int iy = 2 * y2 + (ph >> 1), ix = 2 * x2 + (ph & 1);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (iy < H && ix < W) v = __ldg(x + (((int64_t)b * H + iy) * W + ix) * Cq + cq);
+    orow[i] = v;
+  }
+}
+
+static int launch_s2d(float* xs, const float* x, int B, int C, int C4, int H, int W, int H2, int W2, cudaStream_t st) {
+  const bool vec = (C % 4 == 0) && (((reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(x)) & 15u) == 0) &&
+                   (int64_t)B * H2 <= 65535;
+  if (vec) {
+    const int per_row = W2 * 4 * (C / 4);
+    int gx = (per_row + 255) / 256;
+    if (gx > 64) gx = 64;
+    dim3 grid((unsigned)gx, (unsigned)(B * H2));
+    s2d_nhwc_vec_kernel<<<grid, 256, 0, st>>>((float4*)xs, (const float4*)x, B, C / 4, H, W, H2, W2);
+  } else {
+    const int64_t tot = (int64_t)B * H2 * W2 * 4 * C4;
+    const int64_t want = ceil_div(tot, 256);
+    const int64_t cap = (int64_t)num_sms() * 16;
+    s2d_nhwc_kernel<<<(unsigned)(want < cap ? (want > 0 ? want : 1) : cap), 256, 0, st>>>(xs, x, B, C, C4, H, W, H2, W2);
+  }
+  MSG_CHECK_LAUNCH("conv s2d");
+  return MSG_OK;
+}
+
 // dst[pixel, Cp] = src[pixel, C], zero padded channels
 __global__ void __launch_bounds__(256)
 chanpad_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t pixels, int C, int Cp) {
@@ -392,9 +430,8 @@ extern "C" int msg_conv2d_forward(float* y, const float* x, const float* w, cons
   if (pl.s2d) {
     float* xs = reinterpret_cast<float*>(ws + pl.off_x);
     float* w2 = reinterpret_cast<float*>(ws + pl.off_w2);
-    const int64_t tot = (int64_t)d->B * pl.H2 * pl.W2 * 4 * pl.C4;
-    s2d_nhwc_kernel<<<grid_for(tot), 256, 0, st>>>(xs, x, d->B, d->C, pl.C4, d->H, d->W, pl.H2, pl.W2);
-    MSG_CHECK_LAUNCH("conv s2d");
+    rc = launch_s2d(xs, x, d->B, d->C, pl.C4, d->H, d->W, pl.H2, pl.W2, st);
+    if (rc) return rc;
     W2Params wp{};
     wp.w = w; wp.w_sb = d->w_batch_stride; wp.BW = d->w_batch_stride ? d->B : 1; wp.N = d->O; wp.C = d->C;
     wp.C4 = pl.C4; wp.kh = d->kh; wp.kw = d->kw; wp.pad_h = d->pad_h; wp.pad_w = d->pad_w;
@@ -486,9 +523,8 @@ extern "C" int msg_conv2d_wgrad(float* dw, const float* dy, const float* x, cons
   }
   if (pl.s2d) {
     float* xs = reinterpret_cast<float*>(ws + pl.off_x);
-    const int64_t tot = (int64_t)d->B * pl.H2 * pl.W2 * 4 * pl.C4;
-    s2d_nhwc_kernel<<<grid_for(tot), 256, 0, st>>>(xs, x, d->B, d->C, pl.C4, d->H, d->W, pl.H2, pl.W2);
-    MSG_CHECK_LAUNCH("conv s2d");
+    rc = launch_s2d(xs, x, d->B, d->C, pl.C4, d->H, d->W, pl.H2, pl.W2, st);
+    if (rc) return rc;
     xp = xs;
   } else if (pl.pad_x) {
     float* p = reinterpret_cast<float*>(ws + pl.off_x);

@@ -136,6 +136,147 @@ fir_tiled_kernel(float* __restrict__ out, const float* __restrict__ in, const fl
   }
 }
 
+
+// ---- channels-last paths (minor = C, C % 4 == 0, fp32): one float4 = 4 channels of one pixel -------------
+struct FirClParams {
+  int in_h, in_w, out_h, out_w, C4;
+  int pad_x0, pad_y0;
+  int kernel_h, kernel_w;
+  int tiles_x, tiles_y, chunks;   // blur kernel: CTA grid decomposition
+  int tile_rows;
+  int64_t total4;                 // gather kernel: number of output float4
+};
+
+__device__ __forceinline__ void fma4(float4& a, const float4& v, float k) {
+  a.x = fmaf(v.x, k, a.x); a.y = fmaf(v.y, k, a.y); a.z = fmaf(v.z, k, a.z); a.w = fmaf(v.w, k, a.w);
+}
+
+// up == down == 1, taps <= 4x4.  A warp spans 32 channel quads (512 contiguous bytes) of one output column pair;
+// each thread slides down the rows of its tile keeping the four partially accumulated output rows in registers,
+// so every input row is loaded once per thread (COLS + 3 float4 loads per COLS outputs; neighbours hit in L1).
+template <int COLS>
+__global__ void __launch_bounds__(256)
+fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, const float* __restrict__ kernel,
+                   const FirClParams p) {
+  __shared__ float sk[4][4];
+  if (threadIdx.x < 16) {
+    const int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+    float v = 0.f;
+    if (ky < p.kernel_h && kx < p.kernel_w) v = kernel[(p.kernel_h - 1 - ky) * p.kernel_w + (p.kernel_w - 1 - kx)];
+    sk[ky][kx] = v;
+  }
+  __syncthreads();
+  float kf[4][4];
+#pragma unroll
+  for (int y = 0; y < 4; ++y)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) kf[y][x] = sk[y][x];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t bid = blockIdx.x;
+  const int chunk = (int)(bid % p.chunks); bid /= p.chunks;
+  const int tx = (int)(bid % p.tiles_x); bid /= p.tiles_x;
+  const int ty = (int)(bid % p.tiles_y); bid /= p.tiles_y;
+  const int64_t b = bid;
+  const int q = chunk * 32 + lane;
+  if (q >= p.C4) return;
+  const int ox0 = (tx * 8 + warp) * COLS;
+  if (ox0 >= p.out_w) return;
+  const int oy0 = ty * p.tile_rows;
+  const int ix0 = ox0 - p.pad_x0;
+  const float4* inb = in + (b * p.in_h * (int64_t)p.in_w) * p.C4 + q;
+  float4* outb = out + (b * p.out_h * (int64_t)p.out_w) * p.C4 + q;
+
+  float4 acc[4][COLS];
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) acc[s][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const int n_in = p.tile_rows + 3;               // input rows i = 0 .. tile_rows + 2  (iy = oy0 - pad_y0 + i)
+  for (int i0 = 0; i0 < n_in; i0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u;
+      const int iy = oy0 - p.pad_y0 + i;
+      if (iy >= 0 && iy < p.in_h && i < n_in) {
+        float4 v[COLS + 3];
+        const float4* row = inb + ((int64_t)iy * p.in_w) * p.C4;
+#pragma unroll
+        for (int j = 0; j < COLS + 3; ++j) {
+          const int ix = ix0 + j;
+          v[j] = (ix >= 0 && ix < p.in_w) ? __ldg(row + (int64_t)ix * p.C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          const int s = (u - ky) & 3;               // slot of output row t = i - ky
+#pragma unroll
+          for (int c = 0; c < COLS; ++c)
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) fma4(acc[s][c], v[c + kx], kf[ky][kx]);
+        }
+      }
+      // output row t = i - 3 is complete
+      {
+        const int s = (u - 3) & 3;
+        const int t = i - 3;
+        const int oy = oy0 + t;
+        if (t >= 0 && t < p.tile_rows && oy < p.out_h) {
+          float4* orow = outb + ((int64_t)oy * p.out_w) * p.C4;
+#pragma unroll
+          for (int c = 0; c < COLS; ++c)
+            if (ox0 + c < p.out_w) orow[(int64_t)(ox0 + c) * p.C4] = acc[s][c];
+        }
+#pragma unroll
+        for (int c = 0; c < COLS; ++c) acc[s][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+}
+
+// any (UP, DOWN) in {1,2}, taps <= 4x4: one output float4 per thread, taps gathered through L1.
+template <int UP, int DOWN>
+__global__ void __launch_bounds__(256)
+fir_cl_gather_kernel(float4* __restrict__ out, const float4* __restrict__ in, const float* __restrict__ kernel,
+                     const FirClParams p) {
+  __shared__ float sk[4][4];
+  if (threadIdx.x < 16) {
+    const int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+    float v = 0.f;
+    if (ky < p.kernel_h && kx < p.kernel_w) v = kernel[(p.kernel_h - 1 - ky) * p.kernel_w + (p.kernel_w - 1 - kx)];
+    sk[ky][kx] = v;
+  }
+  __syncthreads();
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; idx < p.total4; idx += stride) {
+    int64_t t = idx;
+    const int q = (int)(t % p.C4); t /= p.C4;
+    const int ox = (int)(t % p.out_w); t /= p.out_w;
+    const int oy = (int)(t % p.out_h); t /= p.out_h;
+    const int64_t b = t;
+    const int mid_x = ox * DOWN + UP - 1 - p.pad_x0;
+    const int mid_y = oy * DOWN + UP - 1 - p.pad_y0;
+    const int in_x0 = floor_div_i(mid_x, UP), in_y0 = floor_div_i(mid_y, UP);
+    const int ph_x = (in_x0 + 1) * UP - mid_x - 1, ph_y = (in_y0 + 1) * UP - mid_y - 1;
+    const float4* inb = in + (b * p.in_h * (int64_t)p.in_w) * p.C4 + q;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int y = 0; y < (4 + UP - 1) / UP; ++y) {
+      const int ky = ph_y + y * UP, iy = in_y0 + y;
+      if (ky < 4 && iy >= 0 && iy < p.in_h) {
+#pragma unroll
+        for (int x = 0; x < (4 + UP - 1) / UP; ++x) {
+          const int kx = ph_x + x * UP, ix = in_x0 + x;
+          if (kx < 4 && ix >= 0 && ix < p.in_w)
+            fma4(acc, __ldg(inb + ((int64_t)iy * p.in_w + ix) * p.C4), sk[ky][kx]);
+        }
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
 // ---- generic path ---------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -229,6 +370,37 @@ extern "C" int msg_upfirdn2d(void* out, const void* in, const void* kernel, int6
     if (up_x == 1 && down_x == 1) return launch_tiled<1, 1, 4, 4>((float*)out, (const float*)in, (const float*)kernel, major, p, st);
     if (up_x == 2 && down_x == 1) return launch_tiled<2, 1, 4, 4>((float*)out, (const float*)in, (const float*)kernel, major, p, st);
     if (up_x == 1 && down_x == 2) return launch_tiled<1, 2, 4, 4>((float*)out, (const float*)in, (const float*)kernel, major, p, st);
+  }
+  if (dtype == MSG_F32 && minor >= 4 && (minor % 4 == 0) && up_x == up_y && down_x == down_y && up_x <= 2 && down_x <= 2 &&
+      kernel_h <= 4 && kernel_w <= 4 && in_h > 0 && in_w > 0 &&
+      ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+    FirClParams p{};
+    p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.C4 = minor / 4;
+    p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.kernel_h = kernel_h; p.kernel_w = kernel_w;
+    p.total4 = total / 4;
+    if (up_x == 1 && down_x == 1) {
+      constexpr int COLS = 2;
+      p.chunks = (int)ceil_div(p.C4, 32);
+      p.tiles_x = (int)ceil_div(out_w, 8 * COLS);
+      p.tile_rows = out_h < 32 ? out_h : 32;
+      p.tiles_y = (int)ceil_div(out_h, p.tile_rows);
+      const int64_t blocks = major * p.tiles_y * p.tiles_x * p.chunks;
+      if (blocks > 0x7fffffffLL) return fail(MSG_ERR_UNSUPPORTED, "upfirdn2d: grid too large");
+      fir_cl_blur_kernel<COLS><<<(unsigned)blocks, 256, 0, st>>>((float4*)out, (const float4*)in, (const float*)kernel, p);
+      MSG_CHECK_LAUNCH("upfirdn2d(channels-last blur)");
+      return MSG_OK;
+    }
+    const int64_t want4 = ceil_div(p.total4, 256);
+    const int64_t cap4 = (int64_t)num_sms() * 64;
+    const unsigned g4 = (unsigned)(want4 < cap4 ? want4 : cap4);
+    if (up_x == 2 && down_x == 1)
+      fir_cl_gather_kernel<2, 1><<<g4, 256, 0, st>>>((float4*)out, (const float4*)in, (const float*)kernel, p);
+    else if (up_x == 1 && down_x == 2)
+      fir_cl_gather_kernel<1, 2><<<g4, 256, 0, st>>>((float4*)out, (const float4*)in, (const float*)kernel, p);
+    else
+      fir_cl_gather_kernel<2, 2><<<g4, 256, 0, st>>>((float4*)out, (const float4*)in, (const float*)kernel, p);
+    MSG_CHECK_LAUNCH("upfirdn2d(channels-last gather)");
+    return MSG_OK;
   }
   const int64_t want = ceil_div(total, 256);
   const int64_t cap = (int64_t)num_sms() * 32;

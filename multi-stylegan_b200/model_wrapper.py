@@ -143,7 +143,16 @@ class ModelWrapper(object):
         # ---------------- generator step (:377-416) ----------------
         self._zero()
         fake_images = self.generator(input=self._noise(B) if z_g is None else z_g)
-        fake_pred, fake_pred_px = self.discriminator(fake_images, is_real=False, is_cut_mix=False)
+        # The reference lets autograd compute all discriminator weight gradients here and then discards them
+        # (zero_grad of both optimisers precedes the next phase, :260-261,:379-380); they are unobservable, so the
+        # discriminator is differentiated w.r.t. its input only.
+        for p in d_params:
+            p.requires_grad_(False)
+        try:
+            fake_pred, fake_pred_px = self.discriminator(fake_images, is_real=False, is_cut_mix=False)
+        finally:
+            for p in d_params:
+                p.requires_grad_(True)
         top = self.top_k(fake_pred)
         if isinstance(top, tuple):
             fake_pred, indexes = top

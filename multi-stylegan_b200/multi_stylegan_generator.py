@@ -19,6 +19,7 @@ from torch import autograd
 
 from . import conv, equalized_layer
 from .op_static import FusedLeakyReLU, upfirdn2d
+from .op_static.fused_act import noise_bias_leaky_relu
 
 
 def _fir_kernel(taps: List[int]) -> torch.Tensor:
@@ -168,7 +169,15 @@ class StyledConv2d(nn.Module):
             output, style = self.modulated_convolution(input, style)
         else:
             output = self.modulated_convolution(input, style)
-        output = self.activation(self.noise_injection(output, noise=noise))
+        if output.shape[1] % 4 == 0:
+            # noise injection (:289-292) + bias + leaky ReLU (fused_act.py:58) in one pass over the activation
+            if noise is None:
+                noise = torch.randn(output.shape[0], 1, output.shape[2], output.shape[3], device=output.device,
+                                    dtype=torch.float32)
+            output = noise_bias_leaky_relu(output, noise, self.noise_injection.weight, self.activation.bias,
+                                           self.activation.negative_slope, self.activation.scale)
+        else:
+            output = self.activation(self.noise_injection(output, noise=noise))
         if self.modulation_mapping:
             return output, style
         return output

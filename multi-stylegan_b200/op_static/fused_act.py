@@ -65,3 +65,48 @@ class FusedLeakyReLU(nn.Module):
 
 def fused_leaky_relu(input, bias, negative_slope=0.2, scale=2 ** 0.5):
     return FusedLeakyReLUFunction.apply(input, bias, negative_slope, scale)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Noise injection + bias + leaky ReLU as ONE pass (the StyledConv2d epilogue,
+# multi_stylegan/multi_stylegan_generator.py:289-292 followed by fused_act.py:58), channels-last kernels.
+# Differentiable to any order like the reference's op: the backward is linear in grad_output, so its own
+# backward is the masked form of the forward.
+# ---------------------------------------------------------------------------------------------------
+class NoiseBiasActBackward(Function):
+    @staticmethod
+    def forward(ctx, grad_output, out, noise, negative_slope, scale):
+        ctx.save_for_backward(out, noise)
+        ctx.negative_slope, ctx.scale = negative_slope, scale
+        grad_input, grad_bias, grad_noise_w = _C.noise_bias_act_cl_bwd(grad_output, out, noise, negative_slope, scale)
+        return grad_input, grad_bias, grad_noise_w
+
+    @staticmethod
+    def backward(ctx, gg_input, gg_bias, gg_noise_w):
+        out, noise = ctx.saved_tensors
+        if gg_input is None:
+            gg_input = torch.zeros_like(out)
+        gg_out = _C.noise_bias_act_cl(gg_input, out, noise if gg_noise_w is not None else None, gg_noise_w, gg_bias,
+                                      ctx.negative_slope, ctx.scale)
+        return gg_out, None, None, None, None
+
+
+class NoiseBiasAct(Function):
+    @staticmethod
+    def forward(ctx, input, noise, noise_weight, bias, negative_slope, scale):
+        out = _C.noise_bias_act_cl(input, None, noise, noise_weight, bias, negative_slope, scale)
+        ctx.save_for_backward(out, noise)
+        ctx.negative_slope, ctx.scale = negative_slope, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        out, noise = ctx.saved_tensors
+        grad_input, grad_bias, grad_noise_w = NoiseBiasActBackward.apply(grad_output, out, noise, ctx.negative_slope,
+                                                                         ctx.scale)
+        return grad_input, None, grad_noise_w, grad_bias, None, None
+
+
+def noise_bias_leaky_relu(input, noise, noise_weight, bias, negative_slope=0.2, scale=1.0):
+    """lrelu(input + noise_weight * noise + bias[c]) * scale; noise [B or 1, 1, H, W], noise_weight [1]."""
+    return NoiseBiasAct.apply(input, noise, noise_weight, bias, negative_slope, scale)

@@ -9,16 +9,28 @@ from torch.autograd import Function
 from .. import _C
 
 
+def _fir(x, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, channels_last):
+    """[B, C, H, W] -> [B, C, H', W'] through the native [major, h, w, minor] op: planes (major = B*C, minor = 1,
+    exactly the reference's view, upfirdn2d.py:102) or, for channels-last activations, pixels-of-channels
+    (major = B, minor = C) without any layout copy."""
+    B, C, H, W = x.shape
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+        out = _C.upfirdn2d(x.permute(0, 2, 3, 1), kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+        return out.permute(0, 3, 1, 2)
+    out = _C.upfirdn2d(x.reshape(-1, H, W, 1), kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
+    return out.view(B, C, out.shape[1], out.shape[2])
+
+
 class UpFirDn2dBackward(Function):
     @staticmethod
-    def forward(ctx, grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size, out_size):
+    def forward(ctx, grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size, out_size, channels_last):
         up_x, up_y = up
         down_x, down_y = down
         g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1 = g_pad
-        grad_output = grad_output.reshape(-1, out_size[0], out_size[1], 1)
-        grad_input = _C.upfirdn2d(grad_output, grad_kernel, down_x, down_y, up_x, up_y,
-                                  g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1)
-        grad_input = grad_input.view(in_size[0], in_size[1], in_size[2], in_size[3])
+        grad_input = _fir(grad_output, grad_kernel, down_x, down_y, up_x, up_y,
+                          g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1, channels_last)
+        ctx.channels_last = channels_last
         ctx.save_for_backward(kernel)
         ctx.up, ctx.down, ctx.pad = up, down, pad
         ctx.in_size, ctx.out_size = in_size, out_size
@@ -27,10 +39,9 @@ class UpFirDn2dBackward(Function):
     @staticmethod
     def backward(ctx, gradgrad_input):
         kernel, = ctx.saved_tensors
-        gradgrad_input = gradgrad_input.reshape(-1, ctx.in_size[2], ctx.in_size[3], 1)
-        gradgrad_out = _C.upfirdn2d(gradgrad_input, kernel, ctx.up[0], ctx.up[1], ctx.down[0], ctx.down[1], *ctx.pad)
-        gradgrad_out = gradgrad_out.view(ctx.in_size[0], ctx.in_size[1], ctx.out_size[0], ctx.out_size[1])
-        return gradgrad_out, None, None, None, None, None, None, None, None
+        gradgrad_out = _fir(gradgrad_input, kernel, ctx.up[0], ctx.up[1], ctx.down[0], ctx.down[1], *ctx.pad,
+                            ctx.channels_last)
+        return gradgrad_out, None, None, None, None, None, None, None, None, None
 
 
 class UpFirDn2d(Function):
@@ -42,7 +53,7 @@ class UpFirDn2d(Function):
         kernel_h, kernel_w = kernel.shape
         batch, channel, in_h, in_w = input.shape
         ctx.in_size = input.shape
-        input = input.reshape(-1, in_h, in_w, 1)
+        ctx.channels_last = _C._cl_only(input) and channel % 4 == 0
         ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
         out_h = (in_h * up_y + pad_y0 + pad_y1 - kernel_h) // down_y + 1
         out_w = (in_w * up_x + pad_x0 + pad_x1 - kernel_w) // down_x + 1
@@ -53,14 +64,13 @@ class UpFirDn2d(Function):
         g_pad_x1 = in_w * up_x - out_w * down_x + pad_x0 - up_x + 1
         g_pad_y1 = in_h * up_y - out_h * down_y + pad_y0 - up_y + 1
         ctx.g_pad = (g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1)
-        out = _C.upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
-        return out.view(-1, channel, out_h, out_w)
+        return _fir(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, ctx.channels_last)
 
     @staticmethod
     def backward(ctx, grad_output):
         kernel, grad_kernel = ctx.saved_tensors
         grad_input = UpFirDn2dBackward.apply(grad_output, kernel, grad_kernel, ctx.up, ctx.down, ctx.pad,
-                                             ctx.g_pad, ctx.in_size, ctx.out_size)
+                                             ctx.g_pad, ctx.in_size, ctx.out_size, ctx.channels_last)
         return grad_input, None, None, None, None
 
 

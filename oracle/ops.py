@@ -107,6 +107,18 @@ def noise_bias_act(x, noise, noise_w, bias, alpha, scale):
     return torch.where(v > 0, v, v * alpha) * scale
 
 
+def noise_bias_act_masked(x, ref, noise, noise_w, bias, alpha, scale):
+    """The same epilogue with the leaky-ReLU mask taken from `ref` when given (the form the backward and the
+    double backward use: fused_bias_act_kernel.cu:36-45 case 31, extended by the noise term)."""
+    v = x
+    if noise is not None:
+        v = v + noise_w * noise
+    if bias is not None:
+        v = v + bias.view(1, -1, 1, 1)
+    m = v if ref is None else ref
+    return torch.where(m > 0, v, v * alpha) * scale
+
+
 def modulate_weights(W, s, scale, demodulate):
     """multi_stylegan_generator.py:384-388.  W [O,C,kh,kw], s [B,C]."""
     w = scale * W.unsqueeze(0) * s.view(s.shape[0], 1, -1, 1, 1)

@@ -5,7 +5,7 @@ import torch
 from oracle import ops
 
 __all__ = ["fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_forward", "conv2d_dgrad", "conv2d_wgrad",
-           "modulate_weights", "noise_bias_act", "affine_warp"]
+           "modulate_weights", "noise_bias_act", "affine_warp", "noise_bias_act_cl", "noise_bias_act_cl_bwd"]
 
 
 def fused_bias_act(input, bias, refer, act, grad, alpha, scale):
@@ -44,3 +44,14 @@ def noise_bias_act(x, noise, noise_w, bias, alpha, scale):
 
 def affine_warp(x, theta, mode=0):
     return ops.affine_warp(x, theta, mode)
+
+
+def noise_bias_act_cl(x, ref, noise, noise_w, bias, alpha, scale):
+    return ops.noise_bias_act_masked(x, ref, noise, noise_w, bias, alpha, scale)
+
+
+def noise_bias_act_cl_bwd(grad_output, out, noise, alpha, scale):
+    dx = ops.noise_bias_act_masked(grad_output, out, None, None, None, alpha, scale)
+    db = dx.sum([0, 2, 3])
+    dnw = None if noise is None else (dx.sum(1, keepdim=True) * noise).sum().reshape(1)
+    return dx, db, dnw

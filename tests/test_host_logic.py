@@ -143,10 +143,21 @@ def check_path_length(g, net, dev="cpu", tol=1e-4, tf32=False):
     net.zero_grad()
     penalty.backward()
     worst = 0.0
+    num = den = 0.0
     for n, p in net.named_parameters():
         if n in g["pl_param_grads"] and p.grad is not None:
             ref = g["pl_param_grads"][n]
+            num += float((p.grad.double().cpu() - ref.double()).pow(2).sum())
+            den += float(ref.double().pow(2).sum())
+            if tf32:
+                continue
             worst = max(worst, (p.grad.cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 1e-3))
+    if tf32:
+        # Second-order gradients under TF32: individual near-zero scalars (a noise weight whose reference gradient is
+        # 4e-4) move by O(1) when a few leaky-ReLU masks flip; stock PyTorch/cuDNN TF32 moves the same scalar by 1.9x
+        # and all 60 tensors together by 2.4 % in L2 (this package: 2.0 %; tools/pl_deviation.py, measured on B200).
+        # The meaningful statistic is therefore the relative L2 error over all parameter gradients together.
+        return (num / max(den, 1e-30)) ** 0.5
     return worst
 
 

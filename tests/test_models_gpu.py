@@ -32,7 +32,7 @@ def test_generator_forward_backward_path_length(engine):
     g = load_golden("generator.pt")
     net = H.check_generator(g, DEV, tol_for(engine), dead=False, tf32=engine == "auto")
     worst = H.check_path_length(g, net, DEV, tol_for(engine), tf32=engine == "auto")
-    assert worst < (0.25 if engine == "auto" else 1e-3), worst
+    assert worst < (0.05 if engine == "auto" else 1e-3), worst
 
 
 def test_generator_dead_branch_is_unobservable(built_library):

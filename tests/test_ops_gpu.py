@@ -44,11 +44,16 @@ def test_fused_bias_act_all_modes(built_library, shape, dtype):
 
 def test_fused_bias_act_non_contiguous_input(built_library):
     from multi_stylegan_b200 import _C
-    x = torch.randn(2, 6, 8, 4).permute(0, 3, 1, 2)       # [2,4,6,8] non-contiguous
+    x = torch.randn(2, 4, 8, 6).transpose(2, 3)       # [2,4,6,8] non-contiguous (not channels-last either)
     b = torch.randn(4)
     want = ops.fused_bias_act(x.contiguous(), b, torch.empty(0), 3, 0, 0.2, 1.0)
     got = _C.fused_bias_act(x.to(dev()), b.to(dev()), torch.empty(0, device=dev()), 3, 0, 0.2, 1.0)
     assert got.is_contiguous() and rel_err(got, want) < 1e-6
+    # a channels-last view keeps its layout (no copy); values are identical by logical index
+    xc = torch.randn(2, 6, 8, 4).permute(0, 3, 1, 2)
+    want = ops.fused_bias_act(xc.contiguous(), b, torch.empty(0), 3, 0, 0.2, 1.0)
+    got = _C.fused_bias_act(xc.to(dev()), b.to(dev()), torch.empty(0, device=dev()), 3, 0, 0.2, 1.0)
+    assert got.is_contiguous(memory_format=torch.channels_last) and rel_err(got, want) < 1e-6
 
 
 @pytest.mark.parametrize("shape", [(2, 5, 6, 7), (3, 4), (2, 3, 40, 40), (4, 32, 64, 64)])
@@ -169,3 +174,94 @@ def test_small_ops_vs_oracle(built_library):
         want = ops.affine_warp(x, theta, mode)
         got = _C.affine_warp(x.to(dev()), theta.to(dev()), mode)
         assert rel_err(got, want) < 1e-4
+
+
+# ---- channels-last (NHWC) variants: same arithmetic, no layout copies ---------------------------------------
+@pytest.mark.parametrize("shape", [(2, 8, 6, 7), (2, 16, 40, 40), (3, 132, 17, 9), (2, 512, 16, 16), (1, 4, 1, 1)])
+def test_fused_bias_act_channels_last(built_library, shape):
+    from multi_stylegan_b200 import _C
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(shape, generator=g)
+    b = torch.randn(shape[1], generator=g)
+    ref = torch.randn(shape, generator=g)
+    e = torch.empty(0)
+    cl = lambda t: t.to(dev()).contiguous(memory_format=torch.channels_last)
+    for act, grad in [(3, 0), (3, 1), (3, 2), (1, 0)]:
+        for bias in (b, e):
+            r = ref if grad == 1 else e
+            want = ops.fused_bias_act(x, bias, r, act, grad, 0.2, 1.5)
+            got = _C.fused_bias_act(cl(x), bias.to(dev()), cl(r) if r.numel() else r.to(dev()), act, grad, 0.2, 1.5)
+            assert got.shape == want.shape
+            if shape[2] * shape[3] > 1:
+                assert got.is_contiguous(memory_format=torch.channels_last)
+            assert rel_err(got, want) < 1e-6, (act, grad, bias.numel())
+    dx = ops.fused_bias_act(x, e, ref, 3, 1, 0.2, 1.0)
+    gdx, gdb = _C.fused_bias_act_bwd(cl(x), cl(ref), 0.2, 1.0, shape[1])
+    assert rel_err(gdx, dx) < 1e-6 and rel_err(gdb, dx.sum([0, 2, 3])) < 1e-5
+    gdx2, gdb2 = _C.fused_bias_act_bwd(cl(x), cl(ref), 0.2, 1.0, shape[1])
+    assert torch.equal(gdb, gdb2)
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 6, 7), (3, 132, 17, 9), (2, 512, 32, 32)])
+@pytest.mark.parametrize("shared_noise", [False, True])
+def test_noise_bias_act_channels_last(built_library, shape, shared_noise):
+    from multi_stylegan_b200 import _C
+    g = torch.Generator().manual_seed(4)
+    B, C, H, W = shape
+    x = torch.randn(shape, generator=g)
+    ref = torch.randn(shape, generator=g)
+    noise = torch.randn(1 if shared_noise else B, 1, H, W, generator=g)
+    nw = torch.tensor([0.37])
+    b = torch.randn(C, generator=g)
+    d = dev()
+    for r in (None, ref):
+        for nz in (noise, None):
+            for bias in (b, None):
+                want = ops.noise_bias_act_masked(x, r, nz, nw, bias, 0.2, 1.3)
+                got = _C.noise_bias_act_cl(x.to(d), None if r is None else r.to(d), None if nz is None else nz.to(d),
+                                           nw.to(d), None if bias is None else bias.to(d), 0.2, 1.3)
+                assert rel_err(got, want) < 1e-6
+    dx = ops.noise_bias_act_masked(x, ref, None, None, None, 0.2, 1.3)
+    gdx, gdb, gdn = _C.noise_bias_act_cl_bwd(x.to(d), ref.to(d), noise.to(d), 0.2, 1.3)
+    assert rel_err(gdx, dx) < 1e-6 and rel_err(gdb, dx.sum([0, 2, 3])) < 1e-5
+    assert rel_err(gdn, (dx.sum(1, keepdim=True) * noise).sum().reshape(1)) < 1e-4
+    _, gdb2, gdn2 = _C.noise_bias_act_cl_bwd(x.to(d), ref.to(d), noise.to(d), 0.2, 1.3)
+    assert torch.equal(gdb, gdb2) and torch.equal(gdn, gdn2)
+
+
+@pytest.mark.parametrize("cfg", CFGS)
+@pytest.mark.parametrize("hwc", [(4, 4, 4), (8, 8, 8), (17, 23, 12), (33, 35, 132), (64, 64, 16), (127, 127, 8)])
+def test_upfirdn2d_channels_last_vs_oracle(built_library, cfg, hwc):
+    from multi_stylegan_b200 import _C
+    up, down, px0, px1, py0, py1, kh, kw = cfg
+    h, w, c = hwc
+    if h * up + py0 + py1 < kh or w * up + px0 + px1 < kw:
+        pytest.skip("kernel larger than padded input")
+    g = torch.Generator().manual_seed(h * 1000 + w + c)
+    x = torch.randn(2, h, w, c, generator=g)
+    k = torch.randn(kh, kw, generator=g)
+    want = ops.upfirdn2d(x, k, up, up, down, down, px0, px1, py0, py1)
+    got = _C.upfirdn2d(x.to(dev()), k.to(dev()), up, up, down, down, px0, px1, py0, py1)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < TOL
+
+
+def test_upfirdn2d_channels_last_autograd_matches_planar(built_library):
+    """The autograd wrapper on a channels-last activation == the same call on the NCHW tensor (fwd, grad, gradgrad)."""
+    from multi_stylegan_b200.op_static import upfirdn2d
+    torch.manual_seed(0)
+    k = torch.tensor([1., 3., 3., 1.], device=dev())
+    k = (k[None] * k[:, None]) / 64 * 4
+    for (up, down, pad, R) in [(1, 1, (2, 1), 32), (2, 1, (2, 1), 16), (1, 2, (1, 1), 32), (1, 1, (2, 2), 31)]:
+        x = torch.randn(2, 64, R, R, device=dev())
+        outs = []
+        for fmt in (torch.contiguous_format, torch.channels_last):
+            xi = x.clone(memory_format=fmt).requires_grad_(True)
+            y = upfirdn2d(xi, k, up=up, down=down, pad=pad)
+            gy = torch.ones_like(y).requires_grad_(True)
+            gx, = torch.autograd.grad(y, xi, gy * 0.5, create_graph=True)
+            ggy, = torch.autograd.grad(gx.square().sum(), gy)
+            outs.append((y, gx, ggy))
+        assert outs[1][0].is_contiguous(memory_format=torch.channels_last)
+        for a, b in zip(*outs):
+            assert rel_err(b, a) < 1e-5
