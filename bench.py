@@ -197,7 +197,8 @@ def run_ours(args):
         t0 = time.time()
         start.record()
         last = None
-        torch.cuda.nvtx.range_push("timed_e2e" if e2e else "timed")
+        torch.cuda.nvtx.range_push("timed_e2e" if e2e else "timed")            # main-thread kernels (forward passes)
+        nvtx_id = torch.cuda.nvtx.range_start("step_e2e" if e2e else "step")    # process-wide: autograd thread too
         for i in range(args.steps):
             if e2e:
                 real = host_pool[i % len(host_pool)].to(dev, non_blocking=True)
@@ -205,6 +206,8 @@ def run_ours(args):
                 last = {k: float(v) for k, v in out.items()}           # device -> host read of the step's losses
             else:
                 mw.train_step(pool[i % len(pool)])
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_end(nvtx_id)
         torch.cuda.nvtx.range_pop()
         end.record()
         barrier()

@@ -143,7 +143,27 @@ enum {
   MSG_CONV_FORCE_TC = 2     /* fail with MSG_ERR_UNSUPPORTED if the shape does not tile */
 };
 
+/* Output transform fused into the forward kernel's epilogue (accumulators are read from TMEM once and never
+ * round-trip through HBM before the activation) — the tail of StyledConv2d.forward
+ * (multi_stylegan_generator.py:289-292 noise, op_static/fused_act.py:58 bias + leaky ReLU + gain) and of
+ * ResNetBlock.forward (u_net_2d_discriminator.py:174-186: activation, residual add, 1/sqrt(2)):
+ *   v = alpha * conv ; v += noise_w[0] * noise[b * noise_batch_stride + oy * OW + ox] ; v += bias[o]
+ *   v = act ? (v > 0 ? v : slope * v) : v ; v += add[b, o, oy, ox] ; y = v * gain
+ * Null pointers skip their term; `add` has the layout of y. */
+typedef struct {
+  const float* bias;            /* [O]                                                  */
+  const float* noise;           /* [B or 1, 1, OH, OW]                                   */
+  const float* noise_w;         /* device scalar (NoiseInjection.weight)                 */
+  int64_t noise_batch_stride;   /* OH*OW, or 0 when one map is shared by the batch       */
+  const float* add;             /* tensor added after the activation, layout of y        */
+  int act;                      /* 0 = linear, 1 = leaky ReLU                            */
+  float slope, gain;
+} msg_conv_epilogue;
+
 size_t msg_conv2d_workspace(const msg_conv_desc* d, int which /*0 fwd,1 dgrad,2 wgrad*/, int flags);
+int msg_conv2d_forward_fused(float* y, const float* x, const float* w, const msg_conv_desc* d,
+                             float alpha, const msg_conv_epilogue* epilogue, void* workspace,
+                             size_t workspace_bytes, int flags, msg_stream_t stream);
 int msg_conv2d_forward(float* y, const float* x, const float* w, const msg_conv_desc* d,
                        float alpha, void* workspace, size_t workspace_bytes, int flags,
                        msg_stream_t stream);

@@ -232,7 +232,12 @@ def _w_dims(w: torch.Tensor, B: int):
     raise RuntimeError("conv2d: weight must be [O,C,kh,kw] or [B,O,C,kh,kw]")
 
 
-def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha: float = 1.0) -> torch.Tensor:
+def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha: float = 1.0,
+                   bias: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
+                   noise_w: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None, act: bool = False,
+                   slope: float = 0.2, gain: float = 1.0) -> torch.Tensor:
+    """y = epilogue(alpha * conv(x, w)); the optional epilogue (noise, bias, leaky ReLU, residual add, gain) runs
+    inside the conv kernel (msg_conv_epilogue, include/msg_b200.h)."""
     _check_f32(x, "x")
     _check_f32(w, "w")
     x, layout = _act(x)
@@ -243,13 +248,47 @@ def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha:
         raise RuntimeError("conv2d: weight has %d input channels, input has %d" % (Cw, C))
     d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout)
     y = _empty_act((B, O, d.OH, d.OW), layout, x.device)
+    fused = bias is not None or noise is not None or add is not None or act or gain != 1.0
+    ep = None
+    keep = []
+    if fused:
+        ep = _lib.ConvEpilogue()
+        ep.act, ep.slope, ep.gain = (1 if act else 0), float(slope), float(gain)
+        if bias is not None:
+            _check_f32(bias, "bias")
+            bias = _aligned(bias)
+            if bias.numel() != O:
+                raise RuntimeError("conv2d: epilogue bias must have %d elements" % O)
+            ep.bias = bias.data_ptr()
+        if noise is not None:
+            _check_f32(noise, "noise")
+            noise, noise_w = _aligned(noise), _aligned(noise_w)
+            if noise.numel() == d.OH * d.OW:
+                ep.noise_batch_stride = 0
+            elif noise.numel() == B * d.OH * d.OW:
+                ep.noise_batch_stride = d.OH * d.OW
+            else:
+                raise RuntimeError("conv2d: epilogue noise must be [B or 1, 1, OH, OW]")
+            ep.noise, ep.noise_w = noise.data_ptr(), noise_w.data_ptr()
+        if add is not None:
+            _check_f32(add, "add")
+            if add.shape != y.shape:
+                raise RuntimeError("conv2d: epilogue add must have the output's shape")
+            add = add.contiguous(memory_format=torch.channels_last if layout == _lib.LAYOUT_NHWC
+                                 else torch.contiguous_format)
+            if add.data_ptr() % 16:
+                add = add.clone()
+            ep.add = add.data_ptr()
+        keep = [bias, noise, noise_w, add]
     L = _lib.lib()
     with torch.cuda.device(x.device):
         nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 0, conv_flags)
         ws, wsp = _workspace(nbytes, x.device)
-        rc = L.msg_conv2d_forward(_ptr(y), _ptr(x), _ptr(w), ctypes.byref(d), float(alpha), wsp, nbytes,
-                                  conv_flags, _stream(x))
+        rc = L.msg_conv2d_forward_fused(_ptr(y), _ptr(x), _ptr(w), ctypes.byref(d), float(alpha),
+                                        ctypes.byref(ep) if ep is not None else None, wsp, nbytes, conv_flags,
+                                        _stream(x))
     _lib.check(rc, "conv2d_forward")
+    del keep
     return y
 
 

@@ -30,6 +30,13 @@ class ConvDesc(ctypes.Structure):
                 ("w_batch_stride", ctypes.c_int64), ("layout", ctypes.c_int)]
 
 
+class ConvEpilogue(ctypes.Structure):
+    """msg_conv_epilogue (include/msg_b200.h)."""
+    _fields_ = [("bias", ctypes.c_void_p), ("noise", ctypes.c_void_p), ("noise_w", ctypes.c_void_p),
+                ("noise_batch_stride", ctypes.c_int64), ("add", ctypes.c_void_p), ("act", ctypes.c_int),
+                ("slope", ctypes.c_float), ("gain", ctypes.c_float)]
+
+
 class ProfileEntry(ctypes.Structure):
     """msg_profile_entry (include/msg_b200.h)."""
     _fields_ = [("kind", ctypes.c_int), ("taps", ctypes.c_int), ("k_channels", ctypes.c_int),
@@ -82,6 +89,8 @@ _SIGNATURES = {
     "msg_conv2d_workspace": (_c.c_size_t, [_c.POINTER(ConvDesc), _c.c_int, _c.c_int]),
     "msg_conv2d_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc), _c.c_float,
                                       _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
+    "msg_conv2d_forward_fused": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc), _c.c_float,
+                                            _c.POINTER(ConvEpilogue), _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
     "msg_conv2d_dgrad": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc), _c.c_float,
                                     _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
     "msg_conv2d_wgrad": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc), _c.c_float,

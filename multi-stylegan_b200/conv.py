@@ -76,6 +76,70 @@ class _ConvWgrad(Function):
         return g_dy, g_x, None, None, None, None
 
 
+class _ConvBiasAct(Function):
+    """out = lrelu(conv(x, w) + noise_w * noise + bias) * gain with the whole tail in the conv kernel's epilogue.
+    The backward is composed of differentiable pieces (the masked activation backward of
+    op_static/fused_act.py, then dgrad / wgrad), so gradients of any order exist."""
+
+    @staticmethod
+    def forward(ctx, x, w, noise, noise_w, bias, stride, padding, slope, gain):
+        out = _C.conv2d_forward(x, w, stride, padding, bias=bias, noise=noise, noise_w=noise_w, act=True,
+                                slope=slope, gain=gain)
+        ctx.save_for_backward(x, w, out, noise if noise is not None else x.new_empty(0))
+        ctx.has_noise = noise is not None
+        ctx.has_bias = bias is not None
+        ctx.stride, ctx.padding, ctx.slope, ctx.gain = stride, padding, slope, gain
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        from .op_static.fused_act import NoiseBiasActBackward
+        x, w, out, noise = ctx.saved_tensors
+        noise = noise if ctx.has_noise else None
+        g_pre, g_bias, g_noise_w = NoiseBiasActBackward.apply(gout, out, noise, ctx.slope, ctx.gain)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = _ConvDgrad.apply(g_pre, w, tuple(x.shape[2:]), ctx.stride, ctx.padding)
+        if ctx.needs_input_grad[1]:
+            dw = _ConvWgrad.apply(g_pre, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5)
+        return (dx, dw, None, g_noise_w if ctx.has_noise else None, g_bias if ctx.has_bias else None,
+                None, None, None, None)
+
+
+def conv2d_bias_act(x: torch.Tensor, w: torch.Tensor, bias=None, noise=None, noise_w=None, stride=1, padding=0,
+                    negative_slope: float = 0.2, gain: float = 1.0) -> torch.Tensor:
+    """Fused conv -> (+ noise_w * noise) -> (+ bias[c]) -> leaky ReLU -> * gain (channel count must be a multiple
+    of 4 for the channels-last activation-backward kernel)."""
+    return _ConvBiasAct.apply(x, w, noise, noise_w, bias, _pair(stride), _pair(padding), negative_slope, gain)
+
+
+class _ConvAddScale(Function):
+    """out = (conv(x, w) + other) * gain — the residual join of ResNetBlock / NonLocalBlock
+    (u_net_2d_discriminator.py:186,381) inside the conv epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, w, other, stride, padding, gain):
+        ctx.save_for_backward(x, w)
+        ctx.stride, ctx.padding, ctx.gain = stride, padding, gain
+        return _C.conv2d_forward(x, w, stride, padding, add=other, gain=gain)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, w = ctx.saved_tensors
+        g = gout * ctx.gain
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx = _ConvDgrad.apply(g, w, tuple(x.shape[2:]), ctx.stride, ctx.padding)
+        if ctx.needs_input_grad[1]:
+            dw = _ConvWgrad.apply(g, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5)
+        return dx, dw, (g if ctx.needs_input_grad[2] else None), None, None, None
+
+
+def conv2d_add_scale(x: torch.Tensor, w: torch.Tensor, other: torch.Tensor, stride=1, padding=0,
+                     gain: float = 1.0) -> torch.Tensor:
+    return _ConvAddScale.apply(x, w, other, _pair(stride), _pair(padding), gain)
+
+
 def conv2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0) -> torch.Tensor:
     """x [B,C,H,W]; w [O,C,kh,kw] or [B,O,C,kh,kw]."""
     return _ConvForward.apply(x, w, _pair(stride), _pair(padding))

@@ -178,7 +178,8 @@ struct FwdPlan {
   PixGemm g;
 };
 
-static FwdPlan plan_forward(const msg_conv_desc* d, const float* x, const float* w, float* y, float alpha, int flags) {
+static FwdPlan plan_forward(const msg_conv_desc* d, const float* x, const float* w, float* y, float alpha, int flags,
+                            const msg_conv_epilogue* ep = nullptr) {
   FwdPlan pl{};
   PixGemm& g = pl.g;
   const int s = d->stride_h;
@@ -186,6 +187,12 @@ static FwdPlan plan_forward(const msg_conv_desc* d, const float* x, const float*
   g.B = d->B; g.N = d->O; g.PH = d->OH; g.PW = d->OW;
   g.out = y; g.os = dense_view(d->layout, d->O, d->OH, d->OW);
   g.out_my = 1; g.out_mx = 1; g.out_oy = 0; g.out_ox = 0; g.alpha = alpha;
+  g.ep = Epilogue{};
+  g.ep.gain = 1.f;
+  if (ep) {
+    g.ep.bias = ep->bias; g.ep.noise = ep->noise; g.ep.noise_w = ep->noise_w; g.ep.noise_sb = ep->noise_batch_stride;
+    g.ep.add = ep->add; g.ep.act = ep->act; g.ep.slope = ep->slope; g.ep.gain = ep->gain;
+  }
   g.in = x; g.Cr = d->C; g.IH = d->H; g.IW = d->W; g.is = dense_view(d->layout, d->C, d->H, d->W);
   g.my = s; g.mx = s;
   g.w = w; g.w_sb = d->w_batch_stride; g.w_sn = d->C * taps; g.w_sc = taps; g.w_st = 1;
@@ -272,6 +279,8 @@ static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float
     g.PH = (d->H - py + s - 1) / s; g.PW = (d->W - px + s - 1) / s;
     g.out = dx; g.os = dense_view(d->layout, d->C, d->H, d->W);
     g.out_my = s; g.out_mx = s; g.out_oy = py; g.out_ox = px; g.alpha = alpha;
+    g.ep = Epilogue{};
+    g.ep.gain = 1.f;
     g.ntaps = 0;
     for (int ky = 0; ky < d->kh; ++ky) {
       if ((py + d->pad_h - ky) % s != 0) continue;
@@ -413,12 +422,24 @@ extern "C" size_t msg_conv2d_workspace(const msg_conv_desc* d, int which, int fl
 
 extern "C" int msg_conv2d_forward(float* y, const float* x, const float* w, const msg_conv_desc* d, float alpha,
                                   void* workspace, size_t workspace_bytes, int flags, msg_stream_t stream) {
+  return msg_conv2d_forward_fused(y, x, w, d, alpha, nullptr, workspace, workspace_bytes, flags, stream);
+}
+
+extern "C" int msg_conv2d_forward_fused(float* y, const float* x, const float* w, const msg_conv_desc* d, float alpha,
+                                        const msg_conv_epilogue* ep, void* workspace, size_t workspace_bytes, int flags,
+                                        msg_stream_t stream) {
   int rc = check_desc(d, "conv2d_forward");
   if (rc) return rc;
   if (d->B == 0) return MSG_OK;
   if (!y || !x || !w) return fail(MSG_ERR_BAD_ARG, "conv2d_forward: null pointer");
+  if (ep) {
+    if (ep->noise && !ep->noise_w) return fail(MSG_ERR_BAD_ARG, "conv2d_forward: noise epilogue needs noise_w");
+    if (ep->act != 0 && ep->act != 1) return fail(MSG_ERR_BAD_ARG, "conv2d_forward: epilogue act must be 0 or 1");
+    if (ep->noise && ep->noise_batch_stride != 0 && ep->noise_batch_stride != (int64_t)d->OH * d->OW)
+      return fail(MSG_ERR_BAD_ARG, "conv2d_forward: noise_batch_stride must be 0 or OH*OW");
+  }
   cudaStream_t st = (cudaStream_t)stream;
-  FwdPlan pl = plan_forward(d, x, w, y, alpha, flags);
+  FwdPlan pl = plan_forward(d, x, w, y, alpha, flags, ep);
   if (!pl.tc) {
     if (flags == MSG_CONV_FORCE_TC) return fail(MSG_ERR_UNSUPPORTED, "conv2d_forward: not eligible for tcgen05 (needs NHWC)");
     g_last_engine = 1;

@@ -24,6 +24,30 @@ struct View4 {            // element strides of a [B, C, H, W] tensor
   int64_t sb, sc, sy, sx;
 };
 
+// Fused output transform of a PixGemm (StyledConv2d / ResNetBlock epilogues):
+//   v = alpha * acc
+//   v += noise_w[0] * noise[b * noise_sb + y * PW + x]         (noise != nullptr; unscattered outputs only)
+//   v += bias[n]                                               (bias != nullptr)
+//   v = v > 0 ? v : slope * v                                  (act == 1)
+//   v += add[same offset as out]                               (add != nullptr)
+//   out = v * gain
+struct Epilogue {
+  const float* bias;
+  const float* noise;
+  const float* noise_w;
+  int64_t noise_sb;
+  const float* add;
+  int act;
+  float slope, gain;
+  __host__ __device__ bool any() const { return bias || noise || add || act || gain != 1.f; }
+};
+
+__device__ __forceinline__ float apply_epilogue(const Epilogue& e, float v, float bias_n, float noise_term, float addv) {
+  v += noise_term + bias_n;
+  if (e.act) v = v > 0.f ? v : v * e.slope;
+  return (v + addv) * e.gain;
+}
+
 struct PixGemm {
   const float* in;        // [B, Cr, IH, IW]
   View4 is;
@@ -39,6 +63,7 @@ struct PixGemm {
   View4 os;
   int out_my, out_mx, out_oy, out_ox;
   float alpha;
+  Epilogue ep;            // zero-initialised = plain alpha * acc (gain must then be set to 1)
 };
 
 struct RedGemm {

@@ -80,10 +80,16 @@ pixgemm_simt_kernel(const PixGemm g) {
     if (m >= g.PH * g.PW) continue;
     const int y = m / g.PW, x = m - y * g.PW;
     const int64_t o = (int64_t)(y * g.out_my + g.out_oy) * g.os.sy + (int64_t)(x * g.out_mx + g.out_ox) * g.os.sx;
+    const float nz = g.ep.noise ? __ldg(g.ep.noise_w) * __ldg(g.ep.noise + (int64_t)b * g.ep.noise_sb + m) : 0.f;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int n = n0 + tn * 4 + i;
-      if (n < g.N) outb[(int64_t)n * g.os.sc + o] = g.alpha * acc[i][j];
+      if (n < g.N) {
+        const int64_t off = (int64_t)n * g.os.sc + o;
+        const float bn = g.ep.bias ? __ldg(g.ep.bias + n) : 0.f;
+        const float av = g.ep.add ? __ldg(g.ep.add + (int64_t)b * g.os.sb + off) : 0.f;
+        outb[off] = apply_epilogue(g.ep, g.alpha * acc[i][j], bn, nz, av);
+      }
     }
   }
 }

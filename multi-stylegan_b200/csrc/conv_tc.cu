@@ -227,48 +227,57 @@ struct TcPixParams {
   int ntaps, cchunks;
   int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
   int PH, PW, N;
-  int wt_log2, tiles_x;        // tile = (1 << wt_log2) x (128 >> wt_log2) pixels
+  int wt_log2, tiles_x, tiles_y, n_tiles;   // tile = (1 << wt_log2) x (128 >> wt_log2) pixels
+  int total_tiles;
   float* out;
   View4 os;
   int out_my, out_mx, out_oy, out_ox;
   float alpha;
   int w_per_sample;
-  int vec_store;               // NHWC output, 16-byte aligned channel runs
-  uint32_t* dbg;
+  int vec_store;               // NHWC output, 16-byte aligned channel runs, N % 4 == 0
+  Epilogue ep;
 };
 
+// Persistent, warp-specialised: CTA c works on tiles c, c + gridDim.x, ...  (n-tile fastest, so neighbouring CTAs
+// share the activation tile in L2).  Two TMEM accumulators: the epilogue warps drain tile i (TMEM -> registers ->
+// per-warp shared-memory transpose -> fused epilogue -> 128-bit coalesced stores) while the MMA warp already
+// accumulates tile i + 1 and the TMA warp runs ahead through the shared-memory ring.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const TcPixParams p) {
   constexpr uint32_t A_BYTES = 128 * 32 * 4;
   constexpr uint32_t B_BYTES = BN * 32 * 4;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
   constexpr uint32_t IDESC = make_idesc_tf32(128, BN, 0, 0);
+  constexpr int CW = BN < 32 ? BN : 32;               // columns per epilogue chunk
+  constexpr uint32_t STG_BYTES = 4 * 32 * 33 * 4;     // per-warp 32 x 33 transpose buffers
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sA = base;
   const uint32_t sB = base + STAGES * A_BYTES;
-  const uint32_t bars = sB + STAGES * B_BYTES;
-  const uint32_t acc_full = bars + 16 * STAGES;
-  const uint32_t tmem_slot = acc_full + 8;
+  const uint32_t sStg = sB + STAGES * B_BYTES;
+  const uint32_t bars = sStg + STG_BYTES;
+  const uint32_t acc_full = bars + 16 * STAGES;       // 2 barriers
+  const uint32_t acc_empty = acc_full + 16;           // 2 barriers
+  const uint32_t tmem_slot = acc_empty + 16;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* stg_all = reinterpret_cast<float*>(smem_raw + (sStg - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Wt = 1 << p.wt_log2, Ht = 128 >> p.wt_log2;
-  const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
-  const int y0 = ty * Ht, x0 = tx * Wt;
-  const int n0 = blockIdx.y * BN;
-  const int b = blockIdx.z;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bars + 8 * s, 1);             // full
       mbar_init(bars + 8 * (STAGES + s), 1);  // empty
     }
-    mbar_init(acc_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full + 8 * a, 1);
+      mbar_init(acc_empty + 8 * a, 4);        // one arrival per epilogue warp
+    }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -281,95 +290,162 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-
   const int kiters = p.ntaps * p.cchunks;
-  uint32_t* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? p.dbg : nullptr;
-  const bool soft = p.dbg != nullptr;
-  if (threadIdx.x == 0) { dbg_set(dbg, 0, 0xC0FFEE01u); dbg_set(dbg, 5, tmem_base); dbg_set(dbg, 6, (uint32_t)kiters); }
 
   if (warp == 0) {
     if (lane == 0) {
-      const int bw = p.w_per_sample ? b : 0;
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        if (!mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u, soft)) { dbg_set(dbg, 4, 0x100u | (it << 12)); break; }
-        const int t = it / p.cchunks;
-        const int c0 = (it - t * p.cchunks) * 32;
-        const uint32_t full = bars + 8 * s;
-        mbar_expect_tx(full, A_BYTES + B_BYTES);
-        tma_load_4d(sA + s * A_BYTES, &tmA, full, c0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b);
-        tma_load_4d(sB + s * B_BYTES, &tmB, full, c0, n0, t, bw);
-        dbg_set(dbg, 1, 2 * it + 2);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int r = tile;
+        const int nt = r % p.n_tiles; r /= p.n_tiles;
+        const int tx = r % p.tiles_x; r /= p.tiles_x;
+        const int ty = r % p.tiles_y;
+        const int b = r / p.tiles_y;
+        const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN;
+        const int bw = p.w_per_sample ? b : 0;
+        for (int k = 0; k < kiters; ++k, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u);
+          const int t = k / p.cchunks;
+          const int c0 = (k - t * p.cchunks) * 32;
+          const uint32_t full = bars + 8 * s;
+          mbar_expect_tx(full, A_BYTES + B_BYTES);
+          tma_load_4d(sA + s * A_BYTES, &tmA, full, c0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b);
+          tma_load_4d(sB + s * B_BYTES, &tmB, full, c0, n0, t, bw);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        if (!mbar_wait(bars + 8 * s, ph, soft)) { dbg_set(dbg, 4, 0x200u | (it << 12)); break; }
+      uint32_t it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t a = lt & 1u;
+        mbar_wait(acc_empty + 8 * a, ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
         tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int k = 0; k < kiters; ++k, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(bars + 8 * s, ph);
+          tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = make_smem_desc(sA + s * A_BYTES + k * 32, 0, 1024, SWZ_128B);
-          const uint64_t bd = make_smem_desc(sB + s * B_BYTES + k * 32, 0, 1024, SWZ_128B);
-          mma_tf32(tmem_base, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t ad = make_smem_desc(sA + s * A_BYTES + kk * 32, 0, 1024, SWZ_128B);
+            const uint64_t bd = make_smem_desc(sB + s * B_BYTES + kk * 32, 0, 1024, SWZ_128B);
+            mma_tf32(d_tmem, ad, bd, IDESC, (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          mma_commit(bars + 8 * (STAGES + s));  // smem stage reusable once these MMAs retire
         }
-        mma_commit(bars + 8 * (STAGES + s));  // smem stage reusable once these MMAs retire
-        dbg_set(dbg, 2, 2 * it + 2);
+        mma_commit(acc_full + 8 * a);
       }
-      mma_commit(acc_full);
-      dbg_set(dbg, 2, 0x80000000u | (uint32_t)kiters);
     }
   } else {
-    const int q = warp & 3;
-    const int m = q * 32 + lane;
-    const int row = m >> p.wt_log2, col = m & (Wt - 1);
-    const int y = y0 + row, x = x0 + col;
-    const bool valid = (y < p.PH) && (x < p.PW);
-    float* optr = p.out + (int64_t)b * p.os.sb + (int64_t)(y * p.out_my + p.out_oy) * p.os.sy +
-                  (int64_t)(x * p.out_mx + p.out_ox) * p.os.sx;
-    const bool acc_ok = mbar_wait(acc_full, 0, soft);
-    if (!acc_ok && threadIdx.x == 64) dbg_set(dbg, 4, 0x300u);
-    tc_fence_after();
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
-    if (!acc_ok) {
-      // drained in debug mode: leave the output untouched
-    } else if (BN >= 32) {
+    const int q = warp & 3;                             // TMEM lane quarter this warp may read
+    float* stg = stg_all + q * (32 * 33);
+    const float nw = p.ep.noise ? __ldg(p.ep.noise_w) : 0.f;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      int r = tile;
+      const int nt = r % p.n_tiles; r /= p.n_tiles;
+      const int tx = r % p.tiles_x; r /= p.tiles_x;
+      const int ty = r % p.tiles_y;
+      const int b = r / p.tiles_y;
+      const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN;
+      const uint32_t a = lt & 1u;
+      mbar_wait(acc_full + 8 * a, (lt >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN;
+
+      if (p.vec_store && CW == 32) {
+        // coalesced path: after the transpose lane l owns channels (l & 7) * 4 .. + 3 of pixels i * 4 + (l >> 3)
+        const int sub = lane >> 3, ch4 = (lane & 7) * 4;
+        int64_t poff[8];
+        float pnz[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = q * 32 + i * 4 + sub;
+          const int y = y0 + (m >> p.wt_log2), x = x0 + (m & (Wt - 1));
+          const bool valid = (y < p.PH) && (x < p.PW);
+          poff[i] = valid ? (int64_t)b * p.os.sb + (int64_t)(y * p.out_my + p.out_oy) * p.os.sy +
+                                (int64_t)(x * p.out_mx + p.out_ox) * p.os.sx
+                          : -1;
+          pnz[i] = (valid && p.ep.noise) ? nw * __ldg(p.ep.noise + (int64_t)b * p.ep.noise_sb + (int64_t)y * p.PW + x) : 0.f;
+        }
 #pragma unroll 1
-      for (int cc = 0; cc < BN; cc += 32) {
-        float r[32];
-        tmem_ld_32x32(tlane + cc, r);
-        tmem_ld_wait();
-        const int nb = n0 + cc;
-        if (p.vec_store && nb + 32 <= p.N) {
-          if (valid) {
-            float4* o4 = reinterpret_cast<float4*>(optr + nb);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o4[j] = make_float4(p.alpha * r[4 * j], p.alpha * r[4 * j + 1], p.alpha * r[4 * j + 2],
-                                  p.alpha * r[4 * j + 3]);
+        for (int cc = 0; cc < BN; cc += 32) {
+          float rr[32];
+          tmem_ld_32x32(tlane + cc, rr);
+          tmem_ld_wait();
+          if (cc + 32 >= BN) {
+            // last TMEM read of this accumulator: hand it back to the MMA warp before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * a);
           }
-        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            if (valid && n < p.N) optr[(int64_t)n * p.os.sc] = p.alpha * r[j];
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = rr[j];
+          __syncwarp();
+          const int n = n0 + cc + ch4;
+          if (n < p.N) {
+            float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.ep.bias) bz = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (poff[i] >= 0) {
+                const float* sp = stg + (i * 4 + sub) * 33 + ch4;
+                const int64_t off = poff[i] + n;
+                float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.ep.add) av = __ldg(reinterpret_cast<const float4*>(p.ep.add + off));
+                float4 o;
+                o.x = apply_epilogue(p.ep, p.alpha * sp[0], bz.x, pnz[i], av.x);
+                o.y = apply_epilogue(p.ep, p.alpha * sp[1], bz.y, pnz[i], av.y);
+                o.z = apply_epilogue(p.ep, p.alpha * sp[2], bz.z, pnz[i], av.z);
+                o.w = apply_epilogue(p.ep, p.alpha * sp[3], bz.w, pnz[i], av.w);
+                *reinterpret_cast<float4*>(p.out + off) = o;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // generic path (N tails, N < 32, scattered / non-NHWC outputs): thread = pixel, scalar stores
+        const int m = q * 32 + lane;
+        const int y = y0 + (m >> p.wt_log2), x = x0 + (m & (Wt - 1));
+        const bool valid = (y < p.PH) && (x < p.PW);
+        const int64_t obase = (int64_t)b * p.os.sb + (int64_t)(y * p.out_my + p.out_oy) * p.os.sy +
+                              (int64_t)(x * p.out_mx + p.out_ox) * p.os.sx;
+        const float nz = (valid && p.ep.noise) ? nw * __ldg(p.ep.noise + (int64_t)b * p.ep.noise_sb + (int64_t)y * p.PW + x) : 0.f;
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += CW) {
+          float rr[32];
+          if (CW == 32) {
+            tmem_ld_32x32(tlane + cc, rr);
+          } else {
+            float r16[16];
+            tmem_ld_32x16(tlane + cc, r16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rr[j] = r16[j];
+          }
+          tmem_ld_wait();
+          if (cc + CW >= BN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * a);
+          }
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const int n = n0 + cc + j;
+            if (valid && n < p.N) {
+              const int64_t off = obase + (int64_t)n * p.os.sc;
+              const float bn = p.ep.bias ? __ldg(p.ep.bias + n) : 0.f;
+              const float av = p.ep.add ? __ldg(p.ep.add + off) : 0.f;
+              p.out[off] = apply_epilogue(p.ep, p.alpha * rr[j], bn, nz, av);
+            }
           }
         }
       }
-    } else {
-      float r[16];
-      tmem_ld_32x16(tlane, r);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int n = n0 + j;
-        if (valid && n < p.N) optr[(int64_t)n * p.os.sc] = p.alpha * r[j];
-      }
     }
-    if (threadIdx.x == 64) dbg_set(dbg, 3, 2);
   }
   tc_fence_before();
   __syncthreads();
@@ -593,17 +669,19 @@ size_t tc_pixgemm_workspace(const PixGemm& g) {
 }
 
 template <int BN>
-static int launch_pix(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPixParams& p, dim3 grid,
-                      cudaStream_t st) {
+static int launch_pix(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPixParams& p, cudaStream_t st) {
   constexpr int STAGES = (BN == 256) ? 4 : 6;
-  constexpr size_t smem = (size_t)STAGES * (16384 + BN * 128) + 16 * STAGES + 64 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (16384 + BN * 128) + 4 * 32 * 33 * 4 + 16 * STAGES + 64 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   auto kfn = tc_pixgemm_kernel<BN, STAGES>;
   static bool attr_done = false;
   if (!attr_done) {
     MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  kfn<<<grid, 192, smem, st>>>(tmA, tmB, p);
+  // one persistent CTA per SM (two co-resident ones would have to share TMEM columns and the smem ring)
+  const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  kfn<<<ctas, 192, smem, st>>>(tmA, tmB, p);
   MSG_CHECK_LAUNCH("conv pixgemm(tcgen05)");
   return MSG_OK;
 }
@@ -653,23 +731,29 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.PH = g.PH; p.PW = g.PW; p.N = g.N;
   p.wt_log2 = wt_log2;
   p.tiles_x = (int)ceil_div(g.PW, Wt);
-  const int tiles_y = (int)ceil_div(g.PH, Ht);
+  p.tiles_y = (int)ceil_div(g.PH, Ht);
+  p.n_tiles = Npad / BN;
+  const int64_t total_tiles = (int64_t)p.tiles_x * p.tiles_y * p.n_tiles * g.B;
+  if (total_tiles > 0x7fffffffLL) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): too many tiles");
+  p.total_tiles = (int)total_tiles;
   p.out = g.out; p.os = g.os;
   p.out_my = g.out_my; p.out_mx = g.out_mx; p.out_oy = g.out_oy; p.out_ox = g.out_ox;
-  p.alpha = g.alpha; p.w_per_sample = g.w_sb != 0; p.dbg = tc_debug_buffer();
-  p.vec_store = (g.os.sc == 1 && al16(g.out) && g.os.sx % 4 == 0 && g.os.sy % 4 == 0 && g.os.sb % 4 == 0) ? 1 : 0;
-  dim3 grid((unsigned)(p.tiles_x * tiles_y), (unsigned)(Npad / BN), (unsigned)g.B);
-  if (grid.y > 65535) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): too many N tiles");
+  p.alpha = g.alpha; p.w_per_sample = g.w_sb != 0;
+  p.ep = g.ep;
+  if (p.ep.noise && (g.out_my != 1 || g.out_mx != 1))
+    return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): noise epilogue on a scattered output");
+  p.vec_store = (g.os.sc == 1 && (g.N % 4 == 0) && al16(g.out) && g.os.sx % 4 == 0 && g.os.sy % 4 == 0 && g.os.sb % 4 == 0 &&
+                 (!p.ep.bias || al16(p.ep.bias)) && (!p.ep.add || al16(p.ep.add))) ? 1 : 0;
   cudaEvent_t pstop;
   const int pslot = prof_begin(0, g.ntaps, g.Cr, g.N, (int64_t)g.B * g.PH * g.PW,
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);
   int rc;
   switch (BN) {
-    case 256: rc = launch_pix<256>(tmA, tmB, p, grid, st); break;
-    case 128: rc = launch_pix<128>(tmA, tmB, p, grid, st); break;
-    case 64: rc = launch_pix<64>(tmA, tmB, p, grid, st); break;
-    case 32: rc = launch_pix<32>(tmA, tmB, p, grid, st); break;
-    default: rc = launch_pix<16>(tmA, tmB, p, grid, st); break;
+    case 256: rc = launch_pix<256>(tmA, tmB, p, st); break;
+    case 128: rc = launch_pix<128>(tmA, tmB, p, st); break;
+    case 64: rc = launch_pix<64>(tmA, tmB, p, st); break;
+    case 32: rc = launch_pix<32>(tmA, tmB, p, st); break;
+    default: rc = launch_pix<16>(tmA, tmB, p, st); break;
   }
   prof_end(pslot, pstop, st);
   return rc;
@@ -705,12 +789,19 @@ static RedPlan red_plan(const RedGemm& g) {
   pl.chunks_y = (int)ceil_div(g.PH, Hk);
   const int64_t kiters = (int64_t)pl.chunks_x * pl.chunks_y * (g.dw_sb != 0 ? 1 : g.B);
   const int64_t tiles = (int64_t)(pl.Npad / 128) * (pl.Cpad / pl.BN) * g.ntaps * pl.BS;
-  int64_t splits = ceil_div(2 * (int64_t)num_sms(), tiles);
-  const int64_t max_by_k = kiters / 8 > 0 ? kiters / 8 : 1;   // keep >= 8 k-iterations per CTA
-  if (splits > max_by_k) splits = max_by_k;
-  if (splits > 64) splits = 64;
-  if (splits < 1) splits = 1;
-  pl.splits = (int)splits;
+  // split-K factor: fill whole waves of SMs (a grid of 324 CTAs on 148 SMs runs three rounds for 2.2 rounds of work),
+  // keep >= 8 k-iterations per CTA, and among equally full grids prefer fewer splits (less partial-sum traffic).
+  const int64_t max_by_k = kiters / 8 > 0 ? kiters / 8 : 1;
+  const int64_t sms = num_sms();
+  int64_t best = 1;
+  double best_t = 1e300;
+  for (int64_t sp = 1; sp <= 64 && sp <= max_by_k; ++sp) {
+    const int64_t rounds = ceil_div(tiles * sp, sms);
+    // time ~ rounds x (k-iterations per CTA + ~24 iterations of fixed per-CTA cost) + the partial-sum reduction
+    const double t = (double)rounds * ((double)kiters / (double)sp + 24.0) + 2.0 * (double)sp;
+    if (t < best_t * 0.98) { best_t = t; best = sp; }
+  }
+  pl.splits = (int)best;
   pl.part_bytes = (size_t)pl.splits * pl.BS * g.ntaps * pl.Npad * pl.Cpad * sizeof(float);
   return pl;
 }

@@ -126,10 +126,8 @@ class ModulatedConv2d(nn.Module):
         return "{}, {}, kernel_size={}, stride={}, padding={}, upsampling={}".format(
             self.in_channels, self.out_channels, self.kernel_size, self.stride, self.padding, self.upsampling)
 
-    def forward(self, input: torch.Tensor, style: torch.Tensor):
-        batch_size, features, height, width = input.shape
-        assert features == self.in_channels, \
-            "Expect input feature shape of {} but get {}.".format(self.in_channels, features)
+    def modulated_weight(self, style: torch.Tensor, batch_size: int):
+        """Per-sample filter banks [B, O, C, kh, kw] (reference :379-388) and the modulated style [B,1,C,1,1]."""
         if self.modulation_mapping is not None:
             modulated_style = self.modulation_mapping(style).view(batch_size, 1, self.in_channels, 1, 1)
         else:
@@ -138,6 +136,13 @@ class ModulatedConv2d(nn.Module):
         if self.demodulate:
             demodulation = torch.rsqrt(torch.sum(weight ** 2, dim=[2, 3, 4]) + 1e-08)
             weight = weight * demodulation.view(batch_size, self.out_channels, 1, 1, 1)
+        return weight, modulated_style
+
+    def forward(self, input: torch.Tensor, style: torch.Tensor):
+        batch_size, features, height, width = input.shape
+        assert features == self.in_channels, \
+            "Expect input feature shape of {} but get {}.".format(self.in_channels, features)
+        weight, modulated_style = self.modulated_weight(style, batch_size)
         if self.upsampling:
             output = conv.conv_transpose2d(input, weight.transpose(1, 2), stride=self.stride, padding=self.padding)
             output = self.blur(output)
@@ -165,6 +170,21 @@ class StyledConv2d(nn.Module):
         self.activation = FusedLeakyReLU(out_channels)
 
     def forward(self, input: torch.Tensor, style: torch.Tensor, noise: torch.Tensor = None):
+        mc = self.modulated_convolution
+        if not mc.upsampling and mc.out_channels % 4 == 0:
+            # conv -> noise (:289-292) -> bias + leaky ReLU (fused_act.py:58): one kernel, epilogue on the accumulators
+            batch_size, features, height, width = input.shape
+            assert features == mc.in_channels, \
+                "Expect input feature shape of {} but get {}.".format(mc.in_channels, features)
+            weight, style = mc.modulated_weight(style, batch_size)
+            if noise is None:
+                noise = torch.randn(batch_size, 1, height, width, device=input.device, dtype=torch.float32)
+            output = conv.conv2d_bias_act(input, weight, bias=self.activation.bias, noise=noise,
+                                          noise_w=self.noise_injection.weight, stride=mc.stride, padding=mc.padding,
+                                          negative_slope=self.activation.negative_slope, gain=self.activation.scale)
+            if self.modulation_mapping:
+                return output, style
+            return output
         if self.modulation_mapping:
             output, style = self.modulated_convolution(input, style)
         else:

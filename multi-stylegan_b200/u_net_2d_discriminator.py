@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import equalized_layer
+from . import conv, equalized_layer
 from .multi_stylegan_generator import _fir_kernel
 from .op_static import FusedLeakyReLU, upfirdn2d
 
@@ -72,8 +72,22 @@ class ResNetBlock(nn.Module):
             if in_channels != out_channels else nn.Identity()
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
-        output = self.main_mapping(self.mini_batch_std_dev(input))
-        return (output + self.residual_mapping(input)) / math.sqrt(2)
+        c1, a1, c2, a2 = self.main_mapping
+        res = self.residual_mapping
+        fusable = (c1.weight.shape[0] % 4 == 0 and c1.bias is None and c2.bias is None
+                   and isinstance(res, equalized_layer.EqualizedConv2d) and res.bias is None)
+        if not fusable:
+            output = self.main_mapping(self.mini_batch_std_dev(input))
+            return (output + self.residual_mapping(input)) / math.sqrt(2)
+        # (lrelu(conv(lrelu(conv(x)))) + conv1x1(x)) / sqrt(2) in three kernels: both activations and the residual
+        # join run in the conv epilogues (reference :174-186)
+        x = self.mini_batch_std_dev(input)
+        h = conv.conv2d_bias_act(x, c1.weight * c1.scale, bias=a1.bias, stride=c1.stride, padding=c1.padding,
+                                 negative_slope=a1.negative_slope, gain=a1.scale)
+        h = conv.conv2d_bias_act(h, c2.weight * c2.scale, bias=a2.bias, stride=c2.stride, padding=c2.padding,
+                                 negative_slope=a2.negative_slope, gain=a2.scale)
+        return conv.conv2d_add_scale(input, res.weight * res.scale, h, stride=res.stride, padding=res.padding,
+                                     gain=1.0 / math.sqrt(2))
 
 
 class NonLocalBlock(nn.Module):

@@ -22,8 +22,18 @@ def upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0,
     return ops.upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
 
 
-def conv2d_forward(x, w, stride=1, padding=0, alpha=1.0):
-    return ops.conv2d(x, w, stride, padding) * alpha
+def conv2d_forward(x, w, stride=1, padding=0, alpha=1.0, bias=None, noise=None, noise_w=None, add=None, act=False,
+                   slope=0.2, gain=1.0):
+    v = ops.conv2d(x, w, stride, padding) * alpha
+    if noise is not None:
+        v = v + noise_w * noise
+    if bias is not None:
+        v = v + bias.view(1, -1, 1, 1)
+    if act:
+        v = torch.where(v > 0, v, v * slope)
+    if add is not None:
+        v = v + add
+    return v * gain
 
 
 def conv2d_dgrad(dy, w, in_hw, stride=1, padding=0, alpha=1.0):
