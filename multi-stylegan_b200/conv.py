@@ -22,73 +22,73 @@ def _pair(v) -> Tuple[int, int]:
 
 class _ConvForward(Function):
     @staticmethod
-    def forward(ctx, x, w, stride, padding):
+    def forward(ctx, x, w, stride, padding, alpha):
         ctx.save_for_backward(x, w)
-        ctx.stride, ctx.padding = stride, padding
-        return _C.conv2d_forward(x, w, stride, padding)
+        ctx.stride, ctx.padding, ctx.alpha = stride, padding, alpha
+        return _C.conv2d_forward(x, w, stride, padding, alpha=alpha)
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = _ConvDgrad.apply(dy, w, tuple(x.shape[2:]), ctx.stride, ctx.padding)
+            dx = _ConvDgrad.apply(dy, w, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
         if ctx.needs_input_grad[1]:
-            dw = _ConvWgrad.apply(dy, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5)
-        return dx, dw, None, None
+            dw = _ConvWgrad.apply(dy, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha)
+        return dx, dw, None, None, None
 
 
 class _ConvDgrad(Function):
-    """dx = conv^T(dy, w); as a function of (dy, w) it is the transposed convolution."""
+    """dx = alpha * conv^T(dy, w); as a function of (dy, w) it is the transposed convolution."""
 
     @staticmethod
-    def forward(ctx, dy, w, in_hw, stride, padding):
+    def forward(ctx, dy, w, in_hw, stride, padding, alpha):
         ctx.save_for_backward(dy, w)
-        ctx.in_hw, ctx.stride, ctx.padding = in_hw, stride, padding
-        return _C.conv2d_dgrad(dy, w, in_hw, stride, padding)
+        ctx.in_hw, ctx.stride, ctx.padding, ctx.alpha = in_hw, stride, padding, alpha
+        return _C.conv2d_dgrad(dy, w, in_hw, stride, padding, alpha=alpha)
 
     @staticmethod
     def backward(ctx, ddx):
         dy, w = ctx.saved_tensors
         g_dy = g_w = None
         if ctx.needs_input_grad[0]:
-            g_dy = _ConvForward.apply(ddx, w, ctx.stride, ctx.padding)
+            g_dy = _ConvForward.apply(ddx, w, ctx.stride, ctx.padding, ctx.alpha)
         if ctx.needs_input_grad[1]:
-            g_w = _ConvWgrad.apply(dy, ddx, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5)
-        return g_dy, g_w, None, None, None
+            g_w = _ConvWgrad.apply(dy, ddx, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha)
+        return g_dy, g_w, None, None, None, None
 
 
 class _ConvWgrad(Function):
     @staticmethod
-    def forward(ctx, dy, x, khw, stride, padding, per_sample):
+    def forward(ctx, dy, x, khw, stride, padding, per_sample, alpha):
         ctx.save_for_backward(dy, x)
-        ctx.stride, ctx.padding = stride, padding
-        return _C.conv2d_wgrad(dy, x, khw, stride, padding, per_sample)
+        ctx.stride, ctx.padding, ctx.alpha = stride, padding, alpha
+        return _C.conv2d_wgrad(dy, x, khw, stride, padding, per_sample, alpha=alpha)
 
     @staticmethod
     def backward(ctx, ddw):
         dy, x = ctx.saved_tensors
         g_dy = g_x = None
         if ctx.needs_input_grad[0]:
-            g_dy = _ConvForward.apply(x, ddw, ctx.stride, ctx.padding)
+            g_dy = _ConvForward.apply(x, ddw, ctx.stride, ctx.padding, ctx.alpha)
         if ctx.needs_input_grad[1]:
-            g_x = _ConvDgrad.apply(dy, ddw, tuple(x.shape[2:]), ctx.stride, ctx.padding)
-        return g_dy, g_x, None, None, None, None
+            g_x = _ConvDgrad.apply(dy, ddw, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
+        return g_dy, g_x, None, None, None, None, None
 
 
 class _ConvBiasAct(Function):
-    """out = lrelu(conv(x, w) + noise_w * noise + bias) * gain with the whole tail in the conv kernel's epilogue.
-    The backward is composed of differentiable pieces (the masked activation backward of
+    """out = lrelu(alpha * conv(x, w) + noise_w * noise + bias) * gain with the whole tail in the conv kernel's
+    epilogue.  The backward is composed of differentiable pieces (the masked activation backward of
     op_static/fused_act.py, then dgrad / wgrad), so gradients of any order exist."""
 
     @staticmethod
-    def forward(ctx, x, w, noise, noise_w, bias, stride, padding, slope, gain):
-        out = _C.conv2d_forward(x, w, stride, padding, bias=bias, noise=noise, noise_w=noise_w, act=True,
+    def forward(ctx, x, w, noise, noise_w, bias, stride, padding, slope, gain, alpha):
+        out = _C.conv2d_forward(x, w, stride, padding, alpha=alpha, bias=bias, noise=noise, noise_w=noise_w, act=True,
                                 slope=slope, gain=gain)
         ctx.save_for_backward(x, w, out, noise if noise is not None else x.new_empty(0))
         ctx.has_noise = noise is not None
         ctx.has_bias = bias is not None
-        ctx.stride, ctx.padding, ctx.slope, ctx.gain = stride, padding, slope, gain
+        ctx.stride, ctx.padding, ctx.slope, ctx.gain, ctx.alpha = stride, padding, slope, gain, alpha
         return out
 
     @staticmethod
@@ -99,29 +99,30 @@ class _ConvBiasAct(Function):
         g_pre, g_bias, g_noise_w = NoiseBiasActBackward.apply(gout, out, noise, ctx.slope, ctx.gain)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = _ConvDgrad.apply(g_pre, w, tuple(x.shape[2:]), ctx.stride, ctx.padding)
+            dx = _ConvDgrad.apply(g_pre, w, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
         if ctx.needs_input_grad[1]:
-            dw = _ConvWgrad.apply(g_pre, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5)
+            dw = _ConvWgrad.apply(g_pre, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha)
         return (dx, dw, None, g_noise_w if ctx.has_noise else None, g_bias if ctx.has_bias else None,
-                None, None, None, None)
+                None, None, None, None, None)
 
 
 def conv2d_bias_act(x: torch.Tensor, w: torch.Tensor, bias=None, noise=None, noise_w=None, stride=1, padding=0,
-                    negative_slope: float = 0.2, gain: float = 1.0) -> torch.Tensor:
-    """Fused conv -> (+ noise_w * noise) -> (+ bias[c]) -> leaky ReLU -> * gain (channel count must be a multiple
-    of 4 for the channels-last activation-backward kernel)."""
-    return _ConvBiasAct.apply(x, w, noise, noise_w, bias, _pair(stride), _pair(padding), negative_slope, gain)
+                    negative_slope: float = 0.2, gain: float = 1.0, alpha: float = 1.0) -> torch.Tensor:
+    """Fused alpha * conv -> (+ noise_w * noise) -> (+ bias[c]) -> leaky ReLU -> * gain (channel count must be a
+    multiple of 4 for the channels-last activation-backward kernel)."""
+    return _ConvBiasAct.apply(x, w, noise, noise_w, bias, _pair(stride), _pair(padding), negative_slope, gain,
+                              float(alpha))
 
 
 class _ConvAddScale(Function):
-    """out = (conv(x, w) + other) * gain — the residual join of ResNetBlock / NonLocalBlock
+    """out = (alpha * conv(x, w) + other) * gain — the residual join of ResNetBlock / NonLocalBlock
     (u_net_2d_discriminator.py:186,381) inside the conv epilogue."""
 
     @staticmethod
-    def forward(ctx, x, w, other, stride, padding, gain):
+    def forward(ctx, x, w, other, stride, padding, gain, alpha):
         ctx.save_for_backward(x, w)
-        ctx.stride, ctx.padding, ctx.gain = stride, padding, gain
-        return _C.conv2d_forward(x, w, stride, padding, add=other, gain=gain)
+        ctx.stride, ctx.padding, ctx.gain, ctx.alpha = stride, padding, gain, alpha
+        return _C.conv2d_forward(x, w, stride, padding, alpha=alpha, add=other, gain=gain)
 
     @staticmethod
     def backward(ctx, gout):
@@ -129,20 +130,20 @@ class _ConvAddScale(Function):
         g = gout * ctx.gain
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = _ConvDgrad.apply(g, w, tuple(x.shape[2:]), ctx.stride, ctx.padding)
+            dx = _ConvDgrad.apply(g, w, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
         if ctx.needs_input_grad[1]:
-            dw = _ConvWgrad.apply(g, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5)
-        return dx, dw, (g if ctx.needs_input_grad[2] else None), None, None, None
+            dw = _ConvWgrad.apply(g, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha)
+        return dx, dw, (g if ctx.needs_input_grad[2] else None), None, None, None, None
 
 
 def conv2d_add_scale(x: torch.Tensor, w: torch.Tensor, other: torch.Tensor, stride=1, padding=0,
-                     gain: float = 1.0) -> torch.Tensor:
-    return _ConvAddScale.apply(x, w, other, _pair(stride), _pair(padding), gain)
+                     gain: float = 1.0, alpha: float = 1.0) -> torch.Tensor:
+    return _ConvAddScale.apply(x, w, other, _pair(stride), _pair(padding), gain, float(alpha))
 
 
-def conv2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0) -> torch.Tensor:
-    """x [B,C,H,W]; w [O,C,kh,kw] or [B,O,C,kh,kw]."""
-    return _ConvForward.apply(x, w, _pair(stride), _pair(padding))
+def conv2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha: float = 1.0) -> torch.Tensor:
+    """alpha * conv(x, w); x [B,C,H,W]; w [O,C,kh,kw] or [B,O,C,kh,kw]."""
+    return _ConvForward.apply(x, w, _pair(stride), _pair(padding), float(alpha))
 
 
 def conv_transpose2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0) -> torch.Tensor:
@@ -152,4 +153,4 @@ def conv_transpose2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0) -> t
     ph, pw = _pair(padding)
     kh, kw = w.shape[-2:]
     out_hw = ((x.shape[2] - 1) * sh - 2 * ph + kh, (x.shape[3] - 1) * sw - 2 * pw + kw)
-    return _ConvDgrad.apply(x, w, out_hw, (sh, sw), (ph, pw))
+    return _ConvDgrad.apply(x, w, out_hw, (sh, sw), (ph, pw), 1.0)

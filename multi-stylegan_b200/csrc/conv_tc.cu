@@ -202,21 +202,34 @@ __device__ __forceinline__ float to_tf32_rna(float v) {
   return __uint_as_float(u);
 }
 
+// One block = a 32 (n) x 32 (c) tile, all taps.  Global reads run along whichever of n / c is the weight tensor's
+// faster dimension (forward: c, dgrad: n; the `taps` floats in between stay in L1 for the following tap passes),
+// the tile is transposed through shared memory, and the writes are 128-byte runs along c.
 __global__ void __launch_bounds__(256)
 tc_weight_transform_kernel(float* __restrict__ wt, const WtParams p) {
-  const int64_t total = (int64_t)p.BW * p.ntaps * p.Npad * p.Cpad;
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    int64_t r = i;
-    const int c = (int)(r % p.Cpad); r /= p.Cpad;
-    const int n = (int)(r % p.Npad); r /= p.Npad;
-    const int t = (int)(r % p.ntaps); r /= p.ntaps;
-    const int b = (int)r;
-    float v = 0.f;
-    if (c < p.Cr && n < p.N)
-      v = to_tf32_rna(__ldg(p.w + b * p.w_sb + n * p.w_sn + c * p.w_sc + p.tap_wi[t] * p.w_st));
-    wt[i] = v;
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 32, b = blockIdx.z;
+  const int a = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const bool c_fast = p.w_sc <= p.w_sn;
+  const float* wb = p.w + (int64_t)b * p.w_sb;
+  for (int t = 0; t < p.ntaps; ++t) {
+    const int64_t toff = (int64_t)p.tap_wi[t] * p.w_st;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int nl = c_fast ? r + 8 * k : a, cl = c_fast ? a : r + 8 * k;
+      const int n = n0 + nl, c = c0 + cl;
+      float v = 0.f;
+      if (c < p.Cr && n < p.N) v = to_tf32_rna(__ldg(wb + (int64_t)n * p.w_sn + (int64_t)c * p.w_sc + toff));
+      tile[nl][cl] = v;
+    }
+    __syncthreads();
+    float* dst = wt + (((int64_t)b * p.ntaps + t) * p.Npad + n0) * p.Cpad + c0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int nl = r + 8 * k;
+      if (n0 + nl < p.Npad) dst[(int64_t)nl * p.Cpad + a] = tile[nl][a];
+    }
+    __syncthreads();
   }
 }
 
@@ -374,6 +387,14 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
 #pragma unroll 1
         for (int cc = 0; cc < BN; cc += 32) {
+          // residual operand of this chunk: all eight loads in flight before the TMEM read and the transpose
+          float4 av[8];
+          const bool nok = (n0 + cc + ch4) < p.N;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.ep.add && nok && poff[i] >= 0) av[i] = __ldg(reinterpret_cast<const float4*>(p.ep.add + poff[i] + n0 + cc + ch4));
+          }
           float rr[32];
           tmem_ld_32x32(tlane + cc, rr);
           tmem_ld_wait();
@@ -395,13 +416,11 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (poff[i] >= 0) {
                 const float* sp = stg + (i * 4 + sub) * 33 + ch4;
                 const int64_t off = poff[i] + n;
-                float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (p.ep.add) av = __ldg(reinterpret_cast<const float4*>(p.ep.add + off));
                 float4 o;
-                o.x = apply_epilogue(p.ep, p.alpha * sp[0], bz.x, pnz[i], av.x);
-                o.y = apply_epilogue(p.ep, p.alpha * sp[1], bz.y, pnz[i], av.y);
-                o.z = apply_epilogue(p.ep, p.alpha * sp[2], bz.z, pnz[i], av.z);
-                o.w = apply_epilogue(p.ep, p.alpha * sp[3], bz.w, pnz[i], av.w);
+                o.x = apply_epilogue(p.ep, p.alpha * sp[0], bz.x, pnz[i], av[i].x);
+                o.y = apply_epilogue(p.ep, p.alpha * sp[1], bz.y, pnz[i], av[i].y);
+                o.z = apply_epilogue(p.ep, p.alpha * sp[2], bz.z, pnz[i], av[i].z);
+                o.w = apply_epilogue(p.ep, p.alpha * sp[3], bz.w, pnz[i], av[i].w);
                 *reinterpret_cast<float4*>(p.out + off) = o;
               }
             }
@@ -526,27 +545,28 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   if (threadIdx.x == 0) { dbg_set(dbg, 0, 0xC0FFEE02u); dbg_set(dbg, 5, tmem_base); dbg_set(dbg, 6, (uint32_t)kiters); }
 
   if (warp == 0) {
-    if (lane == 0) {
-      const int dy = p.tap_dy[t], dx = p.tap_dx[t];
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        if (!mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u, soft)) { dbg_set(dbg, 4, 0x100u | (it << 12)); break; }
-        const int kk = k_begin + it;
-        const int bl = kk / per;
-        const int r = kk - bl * per;
-        const int yc = r / p.chunks_x, xc = r - yc * p.chunks_x;
-        const int b = p.per_sample ? bs : bl;
-        const uint32_t full = bars + 8 * s;
-        mbar_expect_tx(full, A_BYTES + B_BYTES);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          tma_load_4d(sA + s * A_BYTES + j * ATOM_BYTES, &tmG, full, n0 + 32 * j, xc * Wk, yc * Hk, b);
-#pragma unroll
-        for (int j = 0; j < BN / 32; ++j)
-          tma_load_4d(sB + s * B_BYTES + j * ATOM_BYTES, &tmI, full, c0 + 32 * j, xc * Wk + dx, yc * Hk + dy, b);
-        dbg_set(dbg, 1, 2 * it + 2);
-      }
+    // One TMA box per 32-channel atom: 4 + BN/32 boxes per stage.  They are issued by that many lanes in parallel
+    // (a single thread issuing 12 bulk-tensor copies per 512-cycle MMA group was the measured limiter).
+    constexpr int NBOX = 4 + BN / 32;
+    const int dy = p.tap_dy[t], dx = p.tap_dx[t];
+    for (int it = 0; it < kiters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      if (!mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u, soft)) { dbg_set(dbg, 4, 0x100u | (it << 12)); break; }
+      const int kk = k_begin + it;
+      const int bl = kk / per;
+      const int r = kk - bl * per;
+      const int yc = r / p.chunks_x, xc = r - yc * p.chunks_x;
+      const int b = p.per_sample ? bs : bl;
+      const uint32_t full = bars + 8 * s;
+      if (lane == 0) mbar_expect_tx(full, A_BYTES + B_BYTES);
+      __syncwarp();
+      if (lane < 4)
+        tma_load_4d(sA + s * A_BYTES + lane * ATOM_BYTES, &tmG, full, n0 + 32 * lane, xc * Wk, yc * Hk, b);
+      else if (lane < NBOX)
+        tma_load_4d(sB + s * B_BYTES + (lane - 4) * ATOM_BYTES, &tmI, full, c0 + 32 * (lane - 4), xc * Wk + dx,
+                    yc * Hk + dy, b);
+      if (lane == 0) dbg_set(dbg, 1, 2 * it + 2);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -613,9 +633,11 @@ struct RedReduceParams {
   float alpha;
 };
 
+// thread = one (bs, n, c): sums the split-K partials of every tap (reads coalesced along c) and writes the taps of
+// its filter element as one contiguous run (dw is [.., n, c, t] with t fastest for all callers).
 __global__ void __launch_bounds__(256)
 tc_red_reduce_kernel(const RedReduceParams p) {
-  const int64_t total = (int64_t)p.BS * p.ntaps * p.N * p.C;
+  const int64_t total = (int64_t)p.BS * p.N * p.C;
   const int64_t slab = (int64_t)p.BS * p.ntaps * p.Npad * p.Cpad;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -623,12 +645,14 @@ tc_red_reduce_kernel(const RedReduceParams p) {
     int64_t r = i;
     const int c = (int)(r % p.C); r /= p.C;
     const int n = (int)(r % p.N); r /= p.N;
-    const int t = (int)(r % p.ntaps); r /= p.ntaps;
     const int bs = (int)r;
-    const int64_t off = (((int64_t)bs * p.ntaps + t) * p.Npad + n) * p.Cpad + c;
-    float acc = 0.f;
-    for (int s = 0; s < p.splits; ++s) acc += p.part[s * slab + off];
-    p.dw[bs * p.dw_sb + n * p.dw_sn + c * p.dw_sc + p.tap_wi[t] * p.dw_st] = p.alpha * acc;
+    float* dst = p.dw + bs * p.dw_sb + n * p.dw_sn + c * p.dw_sc;
+    for (int t = 0; t < p.ntaps; ++t) {
+      const int64_t off = (((int64_t)bs * p.ntaps + t) * p.Npad + n) * p.Cpad + c;
+      float acc = 0.f;
+      for (int s = 0; s < p.splits; ++s) acc += __ldg(p.part + s * slab + off);
+      dst[p.tap_wi[t] * p.dw_st] = p.alpha * acc;
+    }
   }
 }
 
@@ -700,10 +724,12 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   wp.N = g.N; wp.Cr = g.Cr; wp.Npad = Npad; wp.Cpad = Cpad; wp.ntaps = g.ntaps; wp.BW = BW;
   for (int t = 0; t < g.ntaps; ++t) wp.tap_wi[t] = g.tap_wi[t];
   {
-    const int64_t total = (int64_t)BW * g.ntaps * Npad * Cpad;
-    const int64_t want = ceil_div(total, 256);
-    const int64_t cap = (int64_t)num_sms() * 16;
-    tc_weight_transform_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(wt, wp);
+    // Npad is a multiple of BN (>= 16) and the tiles are 32 wide: round the tile grid up and let the bounds checks
+    // of the kernel (n < N) cover the remainder; Npad itself is a multiple of 32 whenever BN >= 32.
+    if (Npad % 32 != 0 && Npad != 16) return fail(MSG_ERR_UNSUPPORTED, "conv weight transform: Npad %d", Npad);
+    dim3 grid((unsigned)(Cpad / 32), (unsigned)((Npad + 31) / 32), (unsigned)BW);
+    if (BW > 65535) return fail(MSG_ERR_UNSUPPORTED, "conv weight transform: batch > 65535");
+    tc_weight_transform_kernel<<<grid, 256, 0, st>>>(wt, wp);
     MSG_CHECK_LAUNCH("conv weight transform");
   }
 
@@ -873,7 +899,7 @@ int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   rp.splits = pl.splits; rp.BS = pl.BS; rp.ntaps = g.ntaps; rp.N = g.N; rp.C = g.C; rp.Npad = pl.Npad; rp.Cpad = pl.Cpad;
   for (int t = 0; t < g.ntaps; ++t) rp.tap_wi[t] = g.tap_wi[t];
   rp.alpha = g.alpha;
-  const int64_t total = (int64_t)pl.BS * g.ntaps * g.N * g.C;
+  const int64_t total = (int64_t)pl.BS * g.N * g.C;
   const int64_t want = ceil_div(total, 256);
   const int64_t cap = (int64_t)num_sms() * 16;
   tc_red_reduce_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(rp);

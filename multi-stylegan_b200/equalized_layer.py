@@ -33,7 +33,7 @@ class EqualizedConv2d(nn.Module):
             i, o, kh, kw, self.stride, self.padding, self.bias is not None)
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
-        output = conv.conv2d(input, self.weight * self.scale, self.stride, self.padding)
+        output = conv.conv2d(input, self.weight, self.stride, self.padding, alpha=self.scale)   # scale folded into the kernel
         if self.bias is not None:
             output = output + (self.bias * self.scale_bias).view(1, -1, 1, 1)
         return output

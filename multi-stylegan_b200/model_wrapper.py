@@ -39,7 +39,8 @@ class ModelWrapper(object):
                  path_length_regularization: nn.Module = None,
                  generator_ema: Optional[nn.Module] = None,
                  device: str = "cuda",
-                 process_group=None) -> None:
+                 process_group=None,
+                 allow_tf32_matmul: bool = True) -> None:
         self.generator, self.discriminator = generator, discriminator
         self.generator_optimizer, self.discriminator_optimizer = generator_optimizer, discriminator_optimizer
         self.training_dataset = training_dataset
@@ -53,6 +54,10 @@ class ModelWrapper(object):
         self.path_length_regularization = path_length_regularization or loss.PathLengthRegularization()
         self.device = device
         self.process_group = process_group
+        # The reference environment (PyTorch 1.8.1, requirements.txt:1) runs every CUDA matmul with TF32 enabled by
+        # default; newer PyTorch turned that off, which sends the non-local block's bmm and its backward to an fp32
+        # CUDA-core sgemm.  Restore the reference's setting for the library GEMMs that stay on torch.
+        torch.backends.cuda.matmul.allow_tf32 = bool(allow_tf32_matmul)
         if generator_ema is None:
             generator_ema = copy.deepcopy(generator)
         self.generator_ema = generator_ema.eval()

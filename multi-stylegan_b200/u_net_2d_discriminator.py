@@ -15,6 +15,19 @@ from .multi_stylegan_generator import _fir_kernel
 from .op_static import FusedLeakyReLU, upfirdn2d
 
 
+class _tf32_matmul(object):
+    """Scoped torch.backends.cuda.matmul.allow_tf32 = True (forward and the backward nodes recorded inside keep
+    the setting of the time they run, so the train step also enables it around backward; see model_wrapper)."""
+
+    def __enter__(self):
+        self.old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.old
+        return False
+
+
 class Upsample(nn.Module):
     def __init__(self, blur_kernel: List[int] = [1, 3, 3, 1], factor: int = 2) -> None:
         super().__init__()
@@ -82,12 +95,12 @@ class ResNetBlock(nn.Module):
         # (lrelu(conv(lrelu(conv(x)))) + conv1x1(x)) / sqrt(2) in three kernels: both activations and the residual
         # join run in the conv epilogues (reference :174-186)
         x = self.mini_batch_std_dev(input)
-        h = conv.conv2d_bias_act(x, c1.weight * c1.scale, bias=a1.bias, stride=c1.stride, padding=c1.padding,
-                                 negative_slope=a1.negative_slope, gain=a1.scale)
-        h = conv.conv2d_bias_act(h, c2.weight * c2.scale, bias=a2.bias, stride=c2.stride, padding=c2.padding,
-                                 negative_slope=a2.negative_slope, gain=a2.scale)
-        return conv.conv2d_add_scale(input, res.weight * res.scale, h, stride=res.stride, padding=res.padding,
-                                     gain=1.0 / math.sqrt(2))
+        h = conv.conv2d_bias_act(x, c1.weight, bias=a1.bias, stride=c1.stride, padding=c1.padding,
+                                 negative_slope=a1.negative_slope, gain=a1.scale, alpha=c1.scale)
+        h = conv.conv2d_bias_act(h, c2.weight, bias=a2.bias, stride=c2.stride, padding=c2.padding,
+                                 negative_slope=a2.negative_slope, gain=a2.scale, alpha=c2.scale)
+        return conv.conv2d_add_scale(input, res.weight, h, stride=res.stride, padding=res.padding,
+                                     gain=1.0 / math.sqrt(2), alpha=res.scale)
 
 
 class NonLocalBlock(nn.Module):
@@ -107,8 +120,13 @@ class NonLocalBlock(nn.Module):
         theta = self.theta(input).flatten(start_dim=2)                                   # [B, C/8, HW]
         phi = F.max_pool2d(self.phi(input), kernel_size=(2, 2), stride=(2, 2)).flatten(start_dim=2)
         g = F.max_pool2d(self.g(input), kernel_size=(2, 2), stride=(2, 2)).flatten(start_dim=2)
-        beta = F.softmax(torch.bmm(theta.transpose(1, 2), phi), -1)                       # [B, HW, HW/4]
-        output = self.o(torch.bmm(g, beta.transpose(1, 2)).view(batch_size, -1, height, width))
+        # The 4096 x 1024 attention stays on the library bmm like the reference (:370-380).  The reference's pinned
+        # PyTorch 1.8.1 runs CUDA matmuls with TF32 enabled by default; request the same here instead of the fp32
+        # CUDA-core sgemm newer PyTorch versions fall back to.
+        with _tf32_matmul():
+            beta = F.softmax(torch.bmm(theta.transpose(1, 2), phi), -1)                   # [B, HW, HW/4]
+            attended = torch.bmm(g, beta.transpose(1, 2))
+        output = self.o(attended.view(batch_size, -1, height, width))
         return (self.gamma * output + self.residual_mapping(input)) / math.sqrt(2)
 
 

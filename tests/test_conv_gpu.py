@@ -122,3 +122,86 @@ def test_conv_autograd_double_backward_on_device(built_library):
     got = run(lambda x, w: conv.conv2d(x, w, 1, 1), xd, wd)
     for a, b in zip(got, want):
         assert rel_err(a, b) < 2e-2
+
+
+EPI_SHAPES = [
+    (2, 64, 64, 32, 32, 3, 1, 1, True),      # StyledConv2d 3x3
+    (2, 32, 48, 16, 16, 3, 1, 1, True),
+    (3, 64, 128, 40, 24, 3, 1, 1, False),    # ragged tile edges, several n-chunks
+    (2, 64, 320, 16, 16, 1, 1, 0, False),    # two n-tiles of 256 (second one partial)
+    (2, 16, 20, 8, 8, 3, 1, 1, False),       # N < 32: scalar-store epilogue
+    (9, 32, 32, 64, 64, 3, 1, 1, False),     # more tiles than fit one round of accumulators per CTA
+]
+
+
+@pytest.mark.parametrize("shape", EPI_SHAPES)
+@pytest.mark.parametrize("engine", ["tc", "simt"])
+def test_conv_fused_epilogue(built_library, shape, engine):
+    """conv + noise + bias + leaky ReLU + residual add + gain in the kernel epilogue == the same ops applied to
+    the oracle's convolution (multi_stylegan_generator.py:289-292, fused_act.py:58, u_net_2d_discriminator.py:186)."""
+    from multi_stylegan_b200 import _C, _lib
+    from tests import backend_oracle
+    B, C, O, H, W, k, s, p, per = shape
+    x, w, y, dy = make(shape, seed=3)
+    g = torch.Generator().manual_seed(9)
+    bias = torch.randn(O, generator=g)
+    nw = torch.tensor([0.41])
+    add = torch.randn(y.shape, generator=g)
+    d = dev()
+    old = _C.conv_flags
+    _C.conv_flags = _lib.CONV_FORCE_TC if engine == "tc" else _lib.CONV_FORCE_SIMT
+    tol = 1e-2 if engine == "tc" else 1e-4
+    try:
+        for noise in (torch.randn(B, 1, y.shape[2], y.shape[3], generator=g), torch.randn(1, 1, y.shape[2], y.shape[3], generator=g), None):
+            for kw in (dict(bias=bias, act=True, gain=1.0), dict(act=True, gain=2 ** 0.5), dict(add=add, gain=0.5 ** 0.5),
+                       dict(bias=bias, add=add, act=True, gain=0.7)):
+                if noise is not None and "add" in kw:
+                    continue
+                kwargs = dict(kw, noise=noise, noise_w=nw if noise is not None else None)
+                want = backend_oracle.conv2d_forward(x, w, s, p, alpha=0.9, **kwargs)
+                dk = {k2: (v.to(d) if isinstance(v, torch.Tensor) else v) for k2, v in kwargs.items()}
+                got = _C.conv2d_forward(x.to(d), w.to(d), s, p, alpha=0.9, **dk)
+                assert got.shape == want.shape and rel_err(got, want) < tol, (engine, kw.keys(), rel_err(got, want))
+        torch.cuda.synchronize()
+    finally:
+        _C.conv_flags = old
+
+
+def test_conv_bias_act_autograd_on_device(built_library):
+    """Fused conv+epilogue Function: forward, gradients and a second-order gradient against torch on the CPU."""
+    import torch.nn.functional as F
+    from multi_stylegan_b200 import conv
+    torch.manual_seed(1)
+    x = torch.randn(2, 32, 16, 16, requires_grad=True)
+    w = (torch.randn(2, 48, 32, 3, 3) / 17).requires_grad_(True)
+    b = torch.randn(48, requires_grad=True)
+    nw = torch.tensor([0.3], requires_grad=True)
+    noise = torch.randn(2, 1, 16, 16)
+
+    def ref(x, w, b, nw):
+        y = F.conv2d(x.reshape(1, -1, 16, 16), w.reshape(-1, 32, 3, 3), padding=1, groups=2).reshape(2, 48, 16, 16)
+        return F.leaky_relu(y + nw * noise + b.view(1, -1, 1, 1), 0.2)
+
+    def run(fn, args):
+        y = fn(*args)
+        gs = torch.autograd.grad((y ** 2).sum(), args, create_graph=True)
+        gg = torch.autograd.grad(sum((g ** 2).sum() for g in gs), args[1])[0]
+        return (y,) + gs + (gg,)
+    want = run(ref, (x, w, b, nw))
+    d = dev()
+    nd = noise.to(d)
+    from multi_stylegan_b200 import _C, _lib
+    old = _C.conv_flags
+    try:
+        # exact-fp32 engine: every order to 1e-3.  TF32 engine: outputs / first-order gradients to 2e-2; the
+        # second-order term differentiates through leaky-ReLU masks that TF32 rounding flips, so it is checked in L2.
+        for flags, tol in ((_lib.CONV_FORCE_SIMT, 1e-3), (_lib.CONV_AUTO, 2e-2)):
+            _C.conv_flags = flags
+            args = tuple(t.detach().to(d).requires_grad_(True) for t in (x, w, b, nw))
+            got = run(lambda x, w, b, nw: conv.conv2d_bias_act(x, w, bias=b, noise=nd, noise_w=nw, stride=1, padding=1), args)
+            for a, r in zip(got[:-1], want[:-1]):
+                assert rel_err(a, r) < tol, (flags, rel_err(a, r))
+            gg, rg = got[-1].double().cpu(), want[-1].double()
+            assert ((gg - rg).norm() / rg.norm()).item() < (1e-3 if flags == _lib.CONV_FORCE_SIMT else 0.1)
+    finally:
+        _C.conv_flags = old
