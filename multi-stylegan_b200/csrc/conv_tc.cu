@@ -186,6 +186,25 @@ static int make_tmap(CUtensorMap* m, const void* base, const uint64_t dims[4], c
   return MSG_OK;
 }
 
+// 5-D fp32 tensor map (channel atoms as the slowest box dimension, see tc_redgemm_kernel).
+static int make_tmap5(CUtensorMap* m, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                      const uint32_t box[5], CUtensorMapSwizzle swz) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return fail(MSG_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t gd[5] = {dims[0], dims[1], dims[2], dims[3], dims[4]};
+  cuuint64_t gs[4] = {strides_bytes[0], strides_bytes[1], strides_bytes[2], strides_bytes[3]};
+  cuuint32_t bx[5] = {box[0], box[1], box[2], box[3], box[4]};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(MSG_ERR_CUDA, "cuTensorMapEncodeTiled(5d) failed (%d): dims %llu,%llu,%llu,%llu,%llu box %u,%u,%u,%u,%u",
+                (int)r, (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)gd[2],
+                (unsigned long long)gd[3], (unsigned long long)gd[4], bx[0], bx[1], bx[2], bx[3], bx[4]);
+  return MSG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Weight transform for PixGemm: wt[bw][t][n][c] = tf32_rna(w(b, n, c, tap_wi[t])), zero padded.
 // ------------------------------------------------------------------------------------------------
@@ -483,6 +502,7 @@ struct TcRedParams {
   int ctiles;               // number of BN-wide tiles along C
   int Npad, Cpad, splits;
   float* part;              // [splits][BS][ntaps][Npad][Cpad]
+  int atoms5d;              // 1: tensor maps are 5-D (32 ch, W, H, B, C/32) -> one TMA box per operand and stage
   uint32_t variant;
   uint32_t* dbg;
 };
@@ -559,6 +579,15 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       const int yc = r / p.chunks_x, xc = r - yc * p.chunks_x;
       const int b = p.per_sample ? bs : bl;
       const uint32_t full = bars + 8 * s;
+      if (p.atoms5d) {
+        // all channel atoms of an operand in one box: [atom][32 px][32 ch] is exactly the MN-major atom layout
+        if (lane == 0) {
+          mbar_expect_tx(full, A_BYTES + B_BYTES);
+          tma_load_5d(sA + s * A_BYTES, &tmG, full, 0, xc * Wk, yc * Hk, b, n0 >> 5);
+          tma_load_5d(sB + s * B_BYTES, &tmI, full, 0, xc * Wk + dx, yc * Hk + dy, b, c0 >> 5);
+        }
+        continue;
+      }
       if (lane == 0) mbar_expect_tx(full, A_BYTES + B_BYTES);
       __syncwarp();
       if (lane < 4)
@@ -858,19 +887,40 @@ int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
   const int Wk = 1 << pl.wk_log2, Hk = 32 >> pl.wk_log2;
   CUtensorMap tmG, tmI;
-  {
-    const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B};
-    const uint64_t strides[3] = {(uint64_t)g.gs.sx * 4, (uint64_t)g.gs.sy * 4, (uint64_t)g.gs.sb * 4};
-    const uint32_t box[4] = {32, (uint32_t)Wk, (uint32_t)Hk, 1};
-    int rc = make_tmap(&tmG, g.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    if (rc) return rc;
-  }
-  {
-    const uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
-    const uint64_t strides[3] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4};
-    const uint32_t box[4] = {32, (uint32_t)Wk, (uint32_t)Hk, 1};
-    int rc = make_tmap(&tmI, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-    if (rc) return rc;
+  // Channel counts that are whole 32-channel atoms: 5-D maps (32 ch, W, H, B, atoms) with the atom index as the slowest
+  // box dimension, so ONE box per operand fills a stage (a bulk-tensor copy costs ~55 cycles + ~1.4 per 128-byte row;
+  // twelve 4 KB boxes per stage made the producer the bottleneck).  Otherwise one 4-D box per atom.
+  const bool atoms5d = (g.N % 32 == 0) && (g.C % 32 == 0) && !(tc_variant() & 2u);
+  if (atoms5d) {
+    {
+      const uint64_t dims[5] = {32, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B, (uint64_t)(g.N / 32)};
+      const uint64_t strides[4] = {(uint64_t)g.gs.sx * 4, (uint64_t)g.gs.sy * 4, (uint64_t)g.gs.sb * 4, 128};
+      const uint32_t box[5] = {32, (uint32_t)Wk, (uint32_t)Hk, 1, 4};
+      int rc = make_tmap5(&tmG, g.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+      if (rc) return rc;
+    }
+    {
+      const uint64_t dims[5] = {32, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B, (uint64_t)(g.C / 32)};
+      const uint64_t strides[4] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4, 128};
+      const uint32_t box[5] = {32, (uint32_t)Wk, (uint32_t)Hk, 1, (uint32_t)(pl.BN / 32)};
+      int rc = make_tmap5(&tmI, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+      if (rc) return rc;
+    }
+  } else {
+    {
+      const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B};
+      const uint64_t strides[3] = {(uint64_t)g.gs.sx * 4, (uint64_t)g.gs.sy * 4, (uint64_t)g.gs.sb * 4};
+      const uint32_t box[4] = {32, (uint32_t)Wk, (uint32_t)Hk, 1};
+      int rc = make_tmap(&tmG, g.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+      if (rc) return rc;
+    }
+    {
+      const uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
+      const uint64_t strides[3] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4};
+      const uint32_t box[4] = {32, (uint32_t)Wk, (uint32_t)Hk, 1};
+      int rc = make_tmap(&tmI, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+      if (rc) return rc;
+    }
   }
   TcRedParams p{};
   p.ntaps = g.ntaps;
@@ -880,6 +930,7 @@ int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.ctiles = pl.Cpad / pl.BN;
   p.Npad = pl.Npad; p.Cpad = pl.Cpad; p.splits = pl.splits; p.part = part;
   p.variant = tc_variant(); p.dbg = tc_debug_buffer();
+  p.atoms5d = atoms5d ? 1 : 0;
   dim3 grid((unsigned)((pl.Npad / 128) * p.ctiles), (unsigned)(g.ntaps * pl.BS), (unsigned)pl.splits);
   cudaEvent_t pstop;
   const int pslot = prof_begin(1, g.ntaps, g.C, g.N, (int64_t)g.B * g.PH * g.PW,
