@@ -185,6 +185,14 @@ int msg_modulate_weights(float* w_mod, float* demod_out, const float* W, const f
                          int B, int O, int C, int taps, float scale, int demodulate,
                          msg_stream_t stream);
 
+/* First-order backward of the above (what autograd derives from multi_stylegan_generator.py:384-388):
+ * given g = dL/dw_mod [B,O,C,taps], the shared weight W, the styles s [B,C] and the demodulation factors the forward
+ * returned, writes dW [O,C,taps] and ds [B,C].  workspace: msg_modulate_weights_bwd_workspace() bytes. */
+size_t msg_modulate_weights_bwd_workspace(int B, int O, int C, int taps);
+int msg_modulate_weights_bwd(float* dW, float* ds, const float* g, const float* W, const float* s,
+                             const float* demod, int B, int O, int C, int taps, float scale, int demodulate,
+                             void* workspace, size_t workspace_bytes, msg_stream_t stream);
+
 /* -------------------------------------------------------------------------------------------
  * Fused StyledConv2d epilogue — multi_stylegan_generator.py:292 (noise) + op_static/fused_act.py:58
  *   out[b,c,p] = lrelu(x[b,c,p] + noise_w * noise[b or 0, p] + bias[c], alpha) * scale

@@ -398,6 +398,31 @@ def modulate_weights(W: torch.Tensor, s: torch.Tensor, scale: float, demodulate:
     return out, dm
 
 
+def modulate_weights_bwd(g: torch.Tensor, W: torch.Tensor, s: torch.Tensor, demod: Optional[torch.Tensor],
+                         scale: float, demodulate: bool):
+    """(dW [O,C,kh,kw], ds [B,C]) from g = dL/dw_mod [B,O,C,kh,kw] (first-order backward of modulate_weights)."""
+    _check_f32(g, "g")
+    _check_f32(W, "W")
+    _check_f32(s, "s")
+    g, W, s = _aligned(g), _aligned(W), _aligned(s)
+    O, C, kh, kw = W.shape
+    B = s.size(0)
+    if g.shape != (B, O, C, kh, kw):
+        raise RuntimeError("modulate_weights_bwd: g must be [B,O,C,kh,kw]")
+    if demodulate:
+        demod = _aligned(demod)
+    dW = torch.empty_like(W)
+    ds = torch.empty_like(s)
+    L = _lib.lib()
+    with torch.cuda.device(W.device):
+        nbytes = L.msg_modulate_weights_bwd_workspace(B, O, C, kh * kw)
+        ws, wsp = _workspace(nbytes, W.device)
+        rc = L.msg_modulate_weights_bwd(_ptr(dW), _ptr(ds), _ptr(g), _ptr(W), _ptr(s), _ptr(demod) if demodulate else None,
+                                        B, O, C, kh * kw, float(scale), 1 if demodulate else 0, wsp, nbytes, _stream(W))
+    _lib.check(rc, "modulate_weights_bwd")
+    return dW, ds
+
+
 def noise_bias_act(x: torch.Tensor, noise: Optional[torch.Tensor], noise_w: Optional[torch.Tensor],
                    bias: Optional[torch.Tensor], alpha: float, scale: float) -> torch.Tensor:
     """lrelu(x + noise_w * noise + bias[c]) * scale — multi_stylegan_generator.py:292 fused with

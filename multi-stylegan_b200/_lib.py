@@ -98,6 +98,10 @@ _SIGNATURES = {
     "msg_conv2d_last_engine": (_c.c_int, []),
     "msg_modulate_weights": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                         _c.c_int, _c.c_int, _c.c_float, _c.c_int, _c.c_void_p]),
+    "msg_modulate_weights_bwd_workspace": (_c.c_size_t, [_c.c_int, _c.c_int, _c.c_int, _c.c_int]),
+    "msg_modulate_weights_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                            _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_int, _c.c_void_p,
+                                            _c.c_size_t, _c.c_void_p]),
     "msg_noise_bias_act": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int,
                                       _c.c_int, _c.c_int64, _c.c_int64, _c.c_float, _c.c_float, _c.c_void_p]),
     "msg_noise_bias_act_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,

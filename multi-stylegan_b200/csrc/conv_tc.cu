@@ -274,13 +274,17 @@ struct TcPixParams {
 // share the activation tile in L2).  Two TMEM accumulators: the epilogue warps drain tile i (TMEM -> registers ->
 // per-warp shared-memory transpose -> fused epilogue -> 128-bit coalesced stores) while the MMA warp already
 // accumulates tile i + 1 and the TMA warp runs ahead through the shared-memory ring.
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(192, 1)
 tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                   const TcPixParams p) {
-  constexpr uint32_t A_BYTES = 128 * 32 * 4;
+  // MT = 128-pixel sub-tiles per CTA tile: narrow-N layers (BN <= 128) take two, which halves the weight bytes and
+  // TMA boxes per FLOP (one A box of 256 pixels, one B box, two MMAs per k-step sharing the B descriptor).
+  constexpr uint32_t A_BYTES = MT * 128 * 32 * 4;
   constexpr uint32_t B_BYTES = BN * 32 * 4;
-  constexpr uint32_t TMEM_COLS = (2 * BN) < 32 ? 32 : 2 * BN;
+  constexpr uint32_t ACC_COLS = MT * BN;               // one accumulator set
+  constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) < 32 ? 32 : 2 * ACC_COLS;
+  static_assert(2 * ACC_COLS <= 512, "TMEM columns");
   constexpr uint32_t IDESC = make_idesc_tf32(128, BN, 0, 0);
   constexpr int CW = BN < 32 ? BN : 32;               // columns per epilogue chunk
   constexpr uint32_t STG_BYTES = 4 * 32 * 33 * 4;     // per-warp 32 x 33 transpose buffers
@@ -299,7 +303,7 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   float* stg_all = reinterpret_cast<float*>(smem_raw + (sStg - raw));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Wt = 1 << p.wt_log2, Ht = 128 >> p.wt_log2;
+  const int Wt = 1 << p.wt_log2, Ht = (128 * MT) >> p.wt_log2;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -355,7 +359,7 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t a = lt & 1u;
         mbar_wait(acc_empty + 8 * a, ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * BN;
+        const uint32_t d_tmem = tmem_base + a * ACC_COLS;
         for (int k = 0; k < kiters; ++k, ++it) {
           const uint32_t s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
@@ -363,9 +367,12 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t ad = make_smem_desc(sA + s * A_BYTES + kk * 32, 0, 1024, SWZ_128B);
             const uint64_t bd = make_smem_desc(sB + s * B_BYTES + kk * 32, 0, 1024, SWZ_128B);
-            mma_tf32(d_tmem, ad, bd, IDESC, (k > 0 || kk > 0) ? 1u : 0u);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub) {
+              const uint64_t ad = make_smem_desc(sA + s * A_BYTES + sub * (128 * 32 * 4) + kk * 32, 0, 1024, SWZ_128B);
+              mma_tf32(d_tmem + sub * BN, ad, bd, IDESC, (k > 0 || kk > 0) ? 1u : 0u);
+            }
           }
           mma_commit(bars + 8 * (STAGES + s));  // smem stage reusable once these MMAs retire
         }
@@ -387,16 +394,19 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t a = lt & 1u;
       mbar_wait(acc_full + 8 * a, (lt >> 1) & 1u);
       tc_fence_after();
-      const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN;
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+      const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + a * ACC_COLS + sub * BN;
+      const bool last_sub = sub == MT - 1;
 
       if (p.vec_store && CW == 32) {
         // coalesced path: after the transpose lane l owns channels (l & 7) * 4 .. + 3 of pixels i * 4 + (l >> 3)
-        const int sub = lane >> 3, ch4 = (lane & 7) * 4;
+        const int psub = lane >> 3, ch4 = (lane & 7) * 4;
         int64_t poff[8];
         float pnz[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int m = q * 32 + i * 4 + sub;
+          const int m = sub * 128 + q * 32 + i * 4 + psub;
           const int y = y0 + (m >> p.wt_log2), x = x0 + (m & (Wt - 1));
           const bool valid = (y < p.PH) && (x < p.PW);
           poff[i] = valid ? (int64_t)b * p.os.sb + (int64_t)(y * p.out_my + p.out_oy) * p.os.sy +
@@ -417,7 +427,7 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           float rr[32];
           tmem_ld_32x32(tlane + cc, rr);
           tmem_ld_wait();
-          if (cc + 32 >= BN) {
+          if (last_sub && cc + 32 >= BN) {
             // last TMEM read of this accumulator: hand it back to the MMA warp before the stores
             tc_fence_before();
             __syncwarp();
@@ -433,7 +443,7 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               if (poff[i] >= 0) {
-                const float* sp = stg + (i * 4 + sub) * 33 + ch4;
+                const float* sp = stg + (i * 4 + psub) * 33 + ch4;
                 const int64_t off = poff[i] + n;
                 float4 o;
                 o.x = apply_epilogue(p.ep, p.alpha * sp[0], bz.x, pnz[i], av[i].x);
@@ -448,7 +458,7 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       } else {
         // generic path (N tails, N < 32, scattered / non-NHWC outputs): thread = pixel, scalar stores
-        const int m = q * 32 + lane;
+        const int m = sub * 128 + q * 32 + lane;
         const int y = y0 + (m >> p.wt_log2), x = x0 + (m & (Wt - 1));
         const bool valid = (y < p.PH) && (x < p.PW);
         const int64_t obase = (int64_t)b * p.os.sb + (int64_t)(y * p.out_my + p.out_oy) * p.os.sy +
@@ -466,7 +476,7 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 16; ++j) rr[j] = r16[j];
           }
           tmem_ld_wait();
-          if (cc + CW >= BN) {
+          if (last_sub && cc + CW >= BN) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * a);
@@ -483,6 +493,7 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
       }
+      }  // sub
     }
   }
   tc_fence_before();
@@ -721,12 +732,12 @@ size_t tc_pixgemm_workspace(const PixGemm& g) {
   return (size_t)(BW * g.ntaps * Npad * Cpad) * sizeof(float) + 256;
 }
 
-template <int BN>
+template <int BN, int MT>
 static int launch_pix(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPixParams& p, cudaStream_t st) {
-  constexpr int STAGES = (BN == 256) ? 4 : 6;
-  constexpr size_t smem = (size_t)STAGES * (16384 + BN * 128) + 4 * 32 * 33 * 4 + 16 * STAGES + 64 + 1024;
+  constexpr int STAGES = (BN == 256 || MT == 2) ? 4 : 6;
+  constexpr size_t smem = (size_t)STAGES * (MT * 16384 + BN * 128) + 4 * 32 * 33 * 4 + 16 * STAGES + 64 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  auto kfn = tc_pixgemm_kernel<BN, STAGES>;
+  auto kfn = tc_pixgemm_kernel<BN, STAGES, MT>;
   static bool attr_done = false;
   if (!attr_done) {
     MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -737,6 +748,16 @@ static int launch_pix(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPi
   kfn<<<ctas, 192, smem, st>>>(tmA, tmB, p);
   MSG_CHECK_LAUNCH("conv pixgemm(tcgen05)");
   return MSG_OK;
+}
+
+// two 128-pixel sub-tiles per CTA tile pay off for narrow N once there is more than a round of such tiles
+static int pick_mt(const PixGemm& g, int BN) {
+  if (BN > 128) return 1;
+  int wl = ilog2_ceil(g.PW);
+  if (wl > 7) wl = 7;
+  const int Wt = 1 << wl, Ht2 = 256 >> wl;
+  const int64_t tiles2 = ceil_div(g.PW, Wt) * ceil_div(g.PH, Ht2) * (int64_t)(round_up(g.N, BN) / BN) * g.B;
+  return tiles2 >= num_sms() ? 2 : 1;
 }
 
 int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -764,7 +785,8 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
 
   int wt_log2 = ilog2_ceil(g.PW);
   if (wt_log2 > 7) wt_log2 = 7;
-  const int Wt = 1 << wt_log2, Ht = 128 >> wt_log2;
+  const int MT = pick_mt(g, BN);
+  const int Wt = 1 << wt_log2, Ht = (128 * MT) >> wt_log2;
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[4] = {(uint64_t)g.Cr, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
@@ -803,12 +825,21 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int pslot = prof_begin(0, g.ntaps, g.Cr, g.N, (int64_t)g.B * g.PH * g.PW,
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);
   int rc;
-  switch (BN) {
-    case 256: rc = launch_pix<256>(tmA, tmB, p, st); break;
-    case 128: rc = launch_pix<128>(tmA, tmB, p, st); break;
-    case 64: rc = launch_pix<64>(tmA, tmB, p, st); break;
-    case 32: rc = launch_pix<32>(tmA, tmB, p, st); break;
-    default: rc = launch_pix<16>(tmA, tmB, p, st); break;
+  if (MT == 2) {
+    switch (BN) {
+      case 128: rc = launch_pix<128, 2>(tmA, tmB, p, st); break;
+      case 64: rc = launch_pix<64, 2>(tmA, tmB, p, st); break;
+      case 32: rc = launch_pix<32, 2>(tmA, tmB, p, st); break;
+      default: rc = launch_pix<16, 2>(tmA, tmB, p, st); break;
+    }
+  } else {
+    switch (BN) {
+      case 256: rc = launch_pix<256, 1>(tmA, tmB, p, st); break;
+      case 128: rc = launch_pix<128, 1>(tmA, tmB, p, st); break;
+      case 64: rc = launch_pix<64, 1>(tmA, tmB, p, st); break;
+      case 32: rc = launch_pix<32, 1>(tmA, tmB, p, st); break;
+      default: rc = launch_pix<16, 1>(tmA, tmB, p, st); break;
+    }
   }
   prof_end(pslot, pstop, st);
   return rc;

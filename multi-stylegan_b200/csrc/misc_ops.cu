@@ -35,6 +35,73 @@ modulate_weights_kernel(float* __restrict__ w_mod, float* __restrict__ demod_out
   for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] *= dm;
 }
 
+// ---- backward of the modulation (first order; the double backward is composed on the host) --------------------
+// u = scale*W*s, d = rsqrt(sum_{c,t} u^2 + 1e-8), w_mod = u*d.  Given g = dL/dw_mod:
+//   dd[b,o] = sum_{c,t} g*u ;  du = d*(g - d^2*dd*u)   (demodulated)      du = g   (not demodulated)
+//   dW[o,c,t] = scale * sum_b s[b,c]*du[b,o,c,t] ;  ds[b,c] = scale * sum_{o,t} W[o,c,t]*du[b,o,c,t]
+// K1: one block per (b,o): du and part[b,o,c] = sum_t W*du.   K2: dW over the batch.   K3: ds over o.
+__global__ void __launch_bounds__(256)
+modulate_bwd_du_kernel(float* __restrict__ du, float* __restrict__ part, const float* __restrict__ g,
+                       const float* __restrict__ W, const float* __restrict__ s, const float* __restrict__ demod, int O,
+                       int C, int taps, float scale, int demodulate) {
+  const int o = blockIdx.x, b = blockIdx.y;
+  const int n = C * taps;
+  const float* Wo = W + (int64_t)o * n;
+  const float* sb = s + (int64_t)b * C;
+  const float* gb = g + ((int64_t)b * O + o) * n;
+  float* dub = du + ((int64_t)b * O + o) * n;
+  float dm = 1.f, coef = 0.f;
+  if (demodulate) {
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      acc = fmaf(__ldg(gb + i), scale * __ldg(Wo + i) * __ldg(sb + i / taps), acc);
+    __shared__ float scratch[32];
+    __shared__ float ddsh;
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) ddsh = acc;
+    __syncthreads();
+    dm = __ldg(demod + (int64_t)b * O + o);
+    coef = dm * dm * ddsh;
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float gv = __ldg(gb + i);
+    float v = gv;
+    if (demodulate) v = dm * (gv - coef * (scale * __ldg(Wo + i) * __ldg(sb + i / taps)));
+    dub[i] = v;
+  }
+  __syncthreads();
+  // part[b,o,c] = sum_t W[o,c,t] * du[b,o,c,t]   (du re-read from L1/L2: this block just wrote it)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int t = 0; t < taps; ++t) acc = fmaf(__ldg(Wo + c * taps + t), dub[c * taps + t], acc);
+    part[((int64_t)b * O + o) * C + c] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+modulate_bwd_dw_kernel(float* __restrict__ dW, const float* __restrict__ du, const float* __restrict__ s, int B, int O,
+                       int C, int taps, float scale) {
+  const int64_t n = (int64_t)O * C * taps;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const int c = (int)((i / taps) % C);
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(__ldg(s + (int64_t)b * C + c), __ldg(du + (int64_t)b * n + i), acc);
+    dW[i] = scale * acc;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+modulate_bwd_ds_kernel(float* __restrict__ ds, const float* __restrict__ part, int B, int O, int C, float scale) {
+  const int b = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int o = 0; o < O; ++o) acc += __ldg(part + ((int64_t)b * O + o) * C + c);
+  ds[(int64_t)b * C + c] = scale * acc;
+}
+
 // ---- noise + bias + leaky ReLU ------------------------------------------------------------------------
 // grid: (chunks of HW/4, B*C)
 __global__ void __launch_bounds__(256)
@@ -137,6 +204,40 @@ extern "C" int msg_modulate_weights(float* w_mod, float* demod_out, const float*
   dim3 grid((unsigned)O, (unsigned)B);
   modulate_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w_mod, demod_out, W, s, O, C, taps, scale, demodulate);
   MSG_CHECK_LAUNCH("modulate_weights");
+  return MSG_OK;
+}
+
+extern "C" size_t msg_modulate_weights_bwd_workspace(int B, int O, int C, int taps) {
+  if (B <= 0 || O <= 0 || C <= 0 || taps <= 0) return 16;
+  return ((size_t)B * O * C * taps + (size_t)B * O * C) * sizeof(float) + 256;
+}
+
+extern "C" int msg_modulate_weights_bwd(float* dW, float* ds, const float* g, const float* W, const float* s,
+                                        const float* demod, int B, int O, int C, int taps, float scale, int demodulate,
+                                        void* workspace, size_t workspace_bytes, msg_stream_t stream) {
+  if (B < 0 || O <= 0 || C <= 0 || taps <= 0) return fail(MSG_ERR_BAD_ARG, "modulate_weights_bwd: bad sizes");
+  if (!dW || !ds) return fail(MSG_ERR_BAD_ARG, "modulate_weights_bwd: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (B == 0) {
+    MSG_CHECK_CUDA(cudaMemsetAsync(dW, 0, (size_t)O * C * taps * sizeof(float), st));
+    return MSG_OK;
+  }
+  if (!g || !W || !s || (demodulate && !demod)) return fail(MSG_ERR_BAD_ARG, "modulate_weights_bwd: null pointer");
+  if (B > 65535) return fail(MSG_ERR_UNSUPPORTED, "modulate_weights_bwd: batch > 65535");
+  const size_t need = msg_modulate_weights_bwd_workspace(B, O, C, taps);
+  if (!workspace || workspace_bytes < need)
+    return fail(MSG_ERR_WORKSPACE, "modulate_weights_bwd: workspace %zu < %zu", workspace_bytes, need);
+  float* du = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  float* part = du + (size_t)B * O * C * taps;
+  modulate_bwd_du_kernel<<<dim3((unsigned)O, (unsigned)B), 256, 0, st>>>(du, part, g, W, s, demod, O, C, taps, scale, demodulate);
+  MSG_CHECK_LAUNCH("modulate_weights_bwd(du)");
+  const int64_t n = (int64_t)O * C * taps;
+  const int64_t want = ceil_div(n, 256);
+  const int64_t cap = (int64_t)num_sms() * 16;
+  modulate_bwd_dw_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(dW, du, s, B, O, C, taps, scale);
+  MSG_CHECK_LAUNCH("modulate_weights_bwd(dW)");
+  modulate_bwd_ds_kernel<<<dim3((unsigned)ceil_div(C, 256), (unsigned)B), 256, 0, st>>>(ds, part, B, O, C, scale);
+  MSG_CHECK_LAUNCH("modulate_weights_bwd(ds)");
   return MSG_OK;
 }
 

@@ -95,6 +95,40 @@ class NoiseInjection(nn.Module):
         return input + self.weight * noise
 
 
+class _ModulateWeights(autograd.Function):
+    """w_mod[b,o,c,:,:] = scale * W[o,c,:,:] * s[b,c] (* rsqrt(sum_{c,kh,kw}(.)^2 + 1e-8)) — reference :384-388 as one
+    kernel, with a fused first-order backward.  When the backward itself is being recorded (create_graph=True: the
+    path-length regulariser, :193-200) it is evaluated with differentiable tensor ops instead, so gradients of any
+    order stay available."""
+
+    @staticmethod
+    def forward(ctx, W, s, scale, demodulate):
+        from . import _C
+        w_mod, d = _C.modulate_weights(W, s, scale, demodulate)
+        ctx.save_for_backward(W, s, d if d is not None else W.new_empty(0))
+        ctx.scale, ctx.demodulate = scale, demodulate
+        return w_mod
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _C
+        W, s, d = ctx.saved_tensors
+        if not torch.is_grad_enabled():
+            dW, ds = _C.modulate_weights_bwd(g, W, s, d if ctx.demodulate else None, ctx.scale, ctx.demodulate)
+            return dW, ds, None, None
+        sb = s.view(s.shape[0], 1, s.shape[1], 1, 1)
+        u = ctx.scale * W.unsqueeze(0) * sb
+        if ctx.demodulate:
+            dm = torch.rsqrt((u * u).sum(dim=[2, 3, 4]) + 1e-08).view(s.shape[0], W.shape[0], 1, 1, 1)
+            dd = (g * u).sum(dim=[2, 3, 4]).view(s.shape[0], W.shape[0], 1, 1, 1)
+            du = dm * (g - dm * dm * dd * u)
+        else:
+            du = g
+        dW = ctx.scale * (du * sb).sum(dim=0)
+        ds = ctx.scale * (du * W.unsqueeze(0)).sum(dim=[1, 3, 4])
+        return dW, ds, None, None
+
+
 class ModulatedConv2d(nn.Module):
     """Weight-modulated / demodulated per-sample convolution — reference :295-414.
 
@@ -132,10 +166,8 @@ class ModulatedConv2d(nn.Module):
             modulated_style = self.modulation_mapping(style).view(batch_size, 1, self.in_channels, 1, 1)
         else:
             modulated_style = style
-        weight = self.scale * self.weight * modulated_style                      # [B, O, C, kh, kw]
-        if self.demodulate:
-            demodulation = torch.rsqrt(torch.sum(weight ** 2, dim=[2, 3, 4]) + 1e-08)
-            weight = weight * demodulation.view(batch_size, self.out_channels, 1, 1, 1)
+        weight = _ModulateWeights.apply(self.weight[0], modulated_style.reshape(batch_size, self.in_channels),
+                                        self.scale, self.demodulate)             # [B, O, C, kh, kw]
         return weight, modulated_style
 
     def forward(self, input: torch.Tensor, style: torch.Tensor):

@@ -5,7 +5,7 @@ import torch
 from oracle import ops
 
 __all__ = ["fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_forward", "conv2d_dgrad", "conv2d_wgrad",
-           "modulate_weights", "noise_bias_act", "affine_warp", "noise_bias_act_cl", "noise_bias_act_cl_bwd"]
+           "modulate_weights", "noise_bias_act", "affine_warp", "noise_bias_act_cl", "noise_bias_act_cl_bwd", "modulate_weights_bwd"]
 
 
 def fused_bias_act(input, bias, refer, act, grad, alpha, scale):
@@ -65,3 +65,12 @@ def noise_bias_act_cl_bwd(grad_output, out, noise, alpha, scale):
     db = dx.sum([0, 2, 3])
     dnw = None if noise is None else (dx.sum(1, keepdim=True) * noise).sum().reshape(1)
     return dx, db, dnw
+
+
+def modulate_weights_bwd(g, W, s, demod, scale, demodulate):
+    Wd = W.detach().clone().requires_grad_(True)
+    sd = s.detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        w, _ = ops.modulate_weights(Wd, sd, scale, demodulate)
+        dW, ds = torch.autograd.grad(w, (Wd, sd), g)
+    return dW, ds

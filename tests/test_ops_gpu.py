@@ -265,3 +265,23 @@ def test_upfirdn2d_channels_last_autograd_matches_planar(built_library):
         assert outs[1][0].is_contiguous(memory_format=torch.channels_last)
         for a, b in zip(*outs):
             assert rel_err(b, a) < 1e-5
+
+
+@pytest.mark.parametrize("shape", [(3, 12, 8, 3), (2, 64, 48, 1), (8, 512, 512, 3), (4, 3, 64, 1)])
+@pytest.mark.parametrize("demod", [True, False])
+def test_modulate_weights_backward_vs_autograd(built_library, shape, demod):
+    """Fused backward of the weight modulation == autograd through the reference's arithmetic (:384-388)."""
+    from multi_stylegan_b200 import _C
+    from tests import backend_oracle
+    B, O, C, k = shape
+    g = torch.Generator().manual_seed(7)
+    W = torch.randn(O, C, k, k, generator=g)
+    s = torch.randn(B, C, generator=g)
+    go = torch.randn(B, O, C, k, k, generator=g)
+    scale = 0.05
+    want_w, want_d = ops.modulate_weights(W, s, scale, demod)
+    want_dW, want_ds = backend_oracle.modulate_weights_bwd(go, W, s, want_d, scale, demod)
+    got_w, got_d = _C.modulate_weights(W.to(dev()), s.to(dev()), scale, demod)
+    assert rel_err(got_w, want_w) < 1e-5
+    got_dW, got_ds = _C.modulate_weights_bwd(go.to(dev()), W.to(dev()), s.to(dev()), got_d, scale, demod)
+    assert rel_err(got_dW, want_dW) < 1e-4 and rel_err(got_ds, want_ds) < 1e-4
