@@ -83,7 +83,10 @@ def run_parity(dev, tol, n_iter=2, tf32_matmul=True):
         misc.exponential_moving_average(model_ema=keep, model_train=G)
         assert set(got) == set(want), (sorted(got), sorted(want))
         for k in want:
-            assert rel_err(got[k], want[k]) < tol, (it, k, float(got[k]), float(want[k]))
+            # the path-length penalty is (l - mean)^2 with mean = 0.01 l on the first lazy step: it doubles the
+            # relative error of the path length l itself
+            ktol = 3 * tol if k == "loss_path_length_regularization" else tol
+            assert rel_err(got[k], want[k]) < ktol, (it, k, float(got[k]), float(want[k]))
     worst = 0.0
     for n, p in G.named_parameters():
         worst = max(worst, rel_err(p, oracle.sd_g[n]))
