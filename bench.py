@@ -152,6 +152,8 @@ def run_ours(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version there)
     _lib.lib()
     local_rank = mdist.init_from_env()
     world, rank = mdist.world_size(), mdist.rank()
@@ -163,8 +165,9 @@ def run_ours(args):
     D = D_mod.Discriminator(config.u_net_2d_discriminator_config, no_rfp=True).to(dev)
     mdist.broadcast_parameters([G, D])
     hp = dict(config.generation_hyperparameters)
-    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-4, lr_style=2e-6), betas=hp["betas"])
-    opt_d = torch.optim.Adam(D.parameters(), lr=6e-4, betas=hp["betas"])
+    # same Adam as train_multi_stylegan.py:53-57; fused=True only selects PyTorch's single-kernel implementation
+    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-4, lr_style=2e-6), betas=hp["betas"], fused=True)
+    opt_d = torch.optim.Adam(D.parameters(), lr=6e-4, betas=hp["betas"], fused=True)
     Dw = AdaptiveDiscriminatorAugmentation(D) if args.ada else D
     if args.ada:
         Dw.p = 0.5
@@ -224,6 +227,9 @@ def run_ours(args):
     ms, launches, clocks, prof, _, wall = timed(False)
     ms_e2e, _, _, _, last_losses, _ = timed(True)
 
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
     if rank != 0:
         return
     if args.profile_out and prof:

@@ -270,6 +270,110 @@ struct TcPixParams {
   Epilogue ep;
 };
 
+// Epilogue of one 128-pixel x BN accumulator (one TMEM lane quarter per warp): TMEM -> registers -> per-warp 32x33
+// shared-memory transpose -> fused output transform -> 128-bit stores (8 lanes cover one pixel's 128 contiguous bytes).
+// `release`: after the last TMEM read arrive on `release_bar` (hands the accumulator back to the MMA warp).
+template <int BN, bool REMOTE>
+__device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, uint32_t tlane, int q, int lane, int b, int y0,
+                                             int x0, int n0, int sub, float nw, bool release, uint32_t release_bar) {
+  constexpr int CW = BN < 32 ? BN : 32;
+  const int Wt = 1 << p.wt_log2;
+      if (p.vec_store && CW == 32) {
+        // coalesced path: after the transpose lane l owns channels (l & 7) * 4 .. + 3 of pixels i * 4 + (l >> 3)
+        const int psub = lane >> 3, ch4 = (lane & 7) * 4;
+        int64_t poff[8];
+        float pnz[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = sub * 128 + q * 32 + i * 4 + psub;
+          const int y = y0 + (m >> p.wt_log2), x = x0 + (m & (Wt - 1));
+          const bool valid = (y < p.PH) && (x < p.PW);
+          poff[i] = valid ? (int64_t)b * p.os.sb + (int64_t)(y * p.out_my + p.out_oy) * p.os.sy +
+                                (int64_t)(x * p.out_mx + p.out_ox) * p.os.sx
+                          : -1;
+          pnz[i] = (valid && p.ep.noise) ? nw * __ldg(p.ep.noise + (int64_t)b * p.ep.noise_sb + (int64_t)y * p.PW + x) : 0.f;
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += 32) {
+          // residual operand of this chunk: all eight loads in flight before the TMEM read and the transpose
+          float4 av[8];
+          const bool nok = (n0 + cc + ch4) < p.N;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.ep.add && nok && poff[i] >= 0) av[i] = __ldg(reinterpret_cast<const float4*>(p.ep.add + poff[i] + n0 + cc + ch4));
+          }
+          float rr[32];
+          tmem_ld_32x32(tlane + cc, rr);
+          tmem_ld_wait();
+          if (release && cc + 32 >= BN) {
+            // last TMEM read of this accumulator: hand it back to the MMA warp before the stores
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (REMOTE) mbar_arrive_cluster(release_bar); else mbar_arrive(release_bar); }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = rr[j];
+          __syncwarp();
+          const int n = n0 + cc + ch4;
+          if (n < p.N) {
+            float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.ep.bias) bz = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (poff[i] >= 0) {
+                const float* sp = stg + (i * 4 + psub) * 33 + ch4;
+                const int64_t off = poff[i] + n;
+                float4 o;
+                o.x = apply_epilogue(p.ep, p.alpha * sp[0], bz.x, pnz[i], av[i].x);
+                o.y = apply_epilogue(p.ep, p.alpha * sp[1], bz.y, pnz[i], av[i].y);
+                o.z = apply_epilogue(p.ep, p.alpha * sp[2], bz.z, pnz[i], av[i].z);
+                o.w = apply_epilogue(p.ep, p.alpha * sp[3], bz.w, pnz[i], av[i].w);
+                *reinterpret_cast<float4*>(p.out + off) = o;
+              }
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // generic path (N tails, N < 32, scattered / non-NHWC outputs): thread = pixel, scalar stores
+        const int m = sub * 128 + q * 32 + lane;
+        const int y = y0 + (m >> p.wt_log2), x = x0 + (m & (Wt - 1));
+        const bool valid = (y < p.PH) && (x < p.PW);
+        const int64_t obase = (int64_t)b * p.os.sb + (int64_t)(y * p.out_my + p.out_oy) * p.os.sy +
+                              (int64_t)(x * p.out_mx + p.out_ox) * p.os.sx;
+        const float nz = (valid && p.ep.noise) ? nw * __ldg(p.ep.noise + (int64_t)b * p.ep.noise_sb + (int64_t)y * p.PW + x) : 0.f;
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += CW) {
+          float rr[32];
+          if (CW == 32) {
+            tmem_ld_32x32(tlane + cc, rr);
+          } else {
+            float r16[16];
+            tmem_ld_32x16(tlane + cc, r16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) rr[j] = r16[j];
+          }
+          tmem_ld_wait();
+          if (release && cc + CW >= BN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (REMOTE) mbar_arrive_cluster(release_bar); else mbar_arrive(release_bar); }
+          }
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const int n = n0 + cc + j;
+            if (valid && n < p.N) {
+              const int64_t off = obase + (int64_t)n * p.os.sc;
+              const float bn = p.ep.bias ? __ldg(p.ep.bias + n) : 0.f;
+              const float av = p.ep.add ? __ldg(p.ep.add + off) : 0.f;
+              p.out[off] = apply_epilogue(p.ep, p.alpha * rr[j], bn, nz, av);
+            }
+          }
+        }
+      }
+}
+
 // Persistent, warp-specialised: CTA c works on tiles c, c + gridDim.x, ...  (n-tile fastest, so neighbouring CTAs
 // share the activation tile in L2).  Two TMEM accumulators: the epilogue warps drain tile i (TMEM -> registers ->
 // per-warp shared-memory transpose -> fused epilogue -> 128-bit coalesced stores) while the MMA warp already
@@ -286,7 +390,6 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) < 32 ? 32 : 2 * ACC_COLS;
   static_assert(2 * ACC_COLS <= 512, "TMEM columns");
   constexpr uint32_t IDESC = make_idesc_tf32(128, BN, 0, 0);
-  constexpr int CW = BN < 32 ? BN : 32;               // columns per epilogue chunk
   constexpr uint32_t STG_BYTES = 4 * 32 * 33 * 4;     // per-warp 32 x 33 transpose buffers
 
   extern __shared__ uint8_t smem_raw[];
@@ -399,106 +502,154 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + a * ACC_COLS + sub * BN;
       const bool last_sub = sub == MT - 1;
 
-      if (p.vec_store && CW == 32) {
-        // coalesced path: after the transpose lane l owns channels (l & 7) * 4 .. + 3 of pixels i * 4 + (l >> 3)
-        const int psub = lane >> 3, ch4 = (lane & 7) * 4;
-        int64_t poff[8];
-        float pnz[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int m = sub * 128 + q * 32 + i * 4 + psub;
-          const int y = y0 + (m >> p.wt_log2), x = x0 + (m & (Wt - 1));
-          const bool valid = (y < p.PH) && (x < p.PW);
-          poff[i] = valid ? (int64_t)b * p.os.sb + (int64_t)(y * p.out_my + p.out_oy) * p.os.sy +
-                                (int64_t)(x * p.out_mx + p.out_ox) * p.os.sx
-                          : -1;
-          pnz[i] = (valid && p.ep.noise) ? nw * __ldg(p.ep.noise + (int64_t)b * p.ep.noise_sb + (int64_t)y * p.PW + x) : 0.f;
-        }
-#pragma unroll 1
-        for (int cc = 0; cc < BN; cc += 32) {
-          // residual operand of this chunk: all eight loads in flight before the TMEM read and the transpose
-          float4 av[8];
-          const bool nok = (n0 + cc + ch4) < p.N;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.ep.add && nok && poff[i] >= 0) av[i] = __ldg(reinterpret_cast<const float4*>(p.ep.add + poff[i] + n0 + cc + ch4));
-          }
-          float rr[32];
-          tmem_ld_32x32(tlane + cc, rr);
-          tmem_ld_wait();
-          if (last_sub && cc + 32 >= BN) {
-            // last TMEM read of this accumulator: hand it back to the MMA warp before the stores
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + 8 * a);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = rr[j];
-          __syncwarp();
-          const int n = n0 + cc + ch4;
-          if (n < p.N) {
-            float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.ep.bias) bz = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (poff[i] >= 0) {
-                const float* sp = stg + (i * 4 + psub) * 33 + ch4;
-                const int64_t off = poff[i] + n;
-                float4 o;
-                o.x = apply_epilogue(p.ep, p.alpha * sp[0], bz.x, pnz[i], av[i].x);
-                o.y = apply_epilogue(p.ep, p.alpha * sp[1], bz.y, pnz[i], av[i].y);
-                o.z = apply_epilogue(p.ep, p.alpha * sp[2], bz.z, pnz[i], av[i].z);
-                o.w = apply_epilogue(p.ep, p.alpha * sp[3], bz.w, pnz[i], av[i].w);
-                *reinterpret_cast<float4*>(p.out + off) = o;
-              }
-            }
-          }
-          __syncwarp();
-        }
-      } else {
-        // generic path (N tails, N < 32, scattered / non-NHWC outputs): thread = pixel, scalar stores
-        const int m = sub * 128 + q * 32 + lane;
-        const int y = y0 + (m >> p.wt_log2), x = x0 + (m & (Wt - 1));
-        const bool valid = (y < p.PH) && (x < p.PW);
-        const int64_t obase = (int64_t)b * p.os.sb + (int64_t)(y * p.out_my + p.out_oy) * p.os.sy +
-                              (int64_t)(x * p.out_mx + p.out_ox) * p.os.sx;
-        const float nz = (valid && p.ep.noise) ? nw * __ldg(p.ep.noise + (int64_t)b * p.ep.noise_sb + (int64_t)y * p.PW + x) : 0.f;
-#pragma unroll 1
-        for (int cc = 0; cc < BN; cc += CW) {
-          float rr[32];
-          if (CW == 32) {
-            tmem_ld_32x32(tlane + cc, rr);
-          } else {
-            float r16[16];
-            tmem_ld_32x16(tlane + cc, r16);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) rr[j] = r16[j];
-          }
-          tmem_ld_wait();
-          if (last_sub && cc + CW >= BN) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty + 8 * a);
-          }
-#pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const int n = n0 + cc + j;
-            if (valid && n < p.N) {
-              const int64_t off = obase + (int64_t)n * p.os.sc;
-              const float bn = p.ep.bias ? __ldg(p.ep.bias + n) : 0.f;
-              const float av = p.ep.add ? __ldg(p.ep.add + off) : 0.f;
-              p.out[off] = apply_epilogue(p.ep, p.alpha * rr[j], bn, nz, av);
-            }
-          }
-        }
-      }
+      pix_epilogue<BN, false>(p, stg, tlane, q, lane, b, y0, x0, n0, sub, nw, last_sub, acc_empty + 8 * a);
       }  // sub
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// PixGemm on CTA pairs (N > 128): tcgen05.mma.cta_group::2, M = 256 = the pair's two 128-pixel tiles, N = 256.
+// Each CTA loads its own activation tile (16 KB) and HALF of the weight tile (128 of the 256 rows, 16 KB) per stage; the
+// tensor core of the pair reads both halves, so the weight bytes and TMA rows per FLOP halve and the 32 KB stages leave
+// room for a 6-deep ring.  Protocol: both producers signal the LEADER's full barrier (cp.async.bulk.tensor.cta_group::2);
+// the leader's MMA thread issues for the pair and releases a stage with a multicast commit onto both CTAs' empty
+// barriers; accumulators (2 x 256 columns in each CTA's TMEM) are published the same way, and every epilogue warp of
+// both CTAs arrives on the leader's acc_empty barrier when it has drained its lane quarter.
+// ------------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+tc_pixgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const TcPixParams p) {
+  constexpr int BN = 256;
+  constexpr uint32_t A_BYTES = 128 * 32 * 4;
+  constexpr uint32_t B_BYTES = (BN / 2) * 32 * 4;
+  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t IDESC = make_idesc_tf32(256, BN, 0, 0);
+  constexpr uint32_t STG_BYTES = 4 * 32 * 33 * 4;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + STAGES * A_BYTES;
+  const uint32_t sStg = sB + STAGES * B_BYTES;
+  const uint32_t bars = sStg + STG_BYTES;
+  const uint32_t acc_full = bars + 16 * STAGES;
+  const uint32_t acc_empty = acc_full + 16;
+  const uint32_t tmem_slot = acc_empty + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* stg_all = reinterpret_cast<float*>(smem_raw + (sStg - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int Wt = 1 << p.wt_log2, Ht = 128 >> p.wt_log2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);             // full  (used in the leader: its producer's arrive + both CTAs' bytes)
+      mbar_init(bars + 8 * (STAGES + s), 1);  // empty (one multicast commit per phase, in each CTA)
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full + 8 * a, 1);         // multicast commit, in each CTA
+      mbar_init(acc_empty + 8 * a, 8);        // used in the leader: 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int kiters = p.ntaps * p.cchunks;
+  const int npairs = gridDim.x >> 1;
+  const int pair = blockIdx.x >> 1;
+  const int ptiles = p.tiles_x * p.tiles_y;          // 128-pixel tiles per sample
+  const int ppairs = (ptiles + 1) >> 1;              // pixel-tile pairs per sample (the last one may be half empty)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t full_leader = mapa_cluster(bars, 0);
+      uint32_t it = 0;
+      for (int tile = pair; tile < p.total_tiles; tile += npairs) {
+        int r = tile;
+        const int nt = r % p.n_tiles; r /= p.n_tiles;
+        const int pp = r % ppairs;
+        const int b = r / ppairs;
+        const int pt = 2 * pp + (int)rank;           // >= ptiles: out of the image, TMA fills zeros, nothing is stored
+        const int ty = pt / p.tiles_x, tx = pt - ty * p.tiles_x;
+        const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN + (int)rank * (BN / 2);
+        const int bw = p.w_per_sample ? b : 0;
+        for (int k = 0; k < kiters; ++k, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u);
+          const int t = k / p.cchunks;
+          const int c0 = (k - t * p.cchunks) * 32;
+          if (leader) mbar_expect_tx(bars + 8 * s, 2 * (A_BYTES + B_BYTES));
+          tma_load_4d_2cta(sA + s * A_BYTES, &tmA, full_leader + 8 * s, c0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b);
+          tma_load_4d_2cta(sB + s * B_BYTES, &tmB, full_leader + 8 * s, c0, n0, t, bw);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      uint32_t it = 0, lt = 0;
+      for (int tile = pair; tile < p.total_tiles; tile += npairs, ++lt) {
+        const uint32_t a = lt & 1u;
+        mbar_wait(acc_empty + 8 * a, ((lt >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int k = 0; k < kiters; ++k, ++it) {
+          const uint32_t s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(bars + 8 * s, ph);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t ad = make_smem_desc(sA + s * A_BYTES + kk * 32, 0, 1024, SWZ_128B);
+            const uint64_t bd = make_smem_desc(sB + s * B_BYTES + kk * 32, 0, 1024, SWZ_128B);
+            mma_tf32_2cta(d_tmem, ad, bd, IDESC, (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          mma_commit_2cta(bars + 8 * (STAGES + s), 3);
+        }
+        mma_commit_2cta(acc_full + 8 * a, 3);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float* stg = stg_all + q * (32 * 33);
+    const float nw = p.ep.noise ? __ldg(p.ep.noise_w) : 0.f;
+    const uint32_t acc_empty_leader = mapa_cluster(acc_empty, 0);
+    uint32_t lt = 0;
+    for (int tile = pair; tile < p.total_tiles; tile += npairs, ++lt) {
+      int r = tile;
+      const int nt = r % p.n_tiles; r /= p.n_tiles;
+      const int pp = r % ppairs;
+      const int b = r / ppairs;
+      const int pt = 2 * pp + (int)rank;
+      const int ty = pt / p.tiles_x, tx = pt - ty * p.tiles_x;
+      const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN;
+      const uint32_t a = lt & 1u;
+      mbar_wait(acc_full + 8 * a, (lt >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN;
+      pix_epilogue<BN, true>(p, stg, tlane, q, lane, b, y0, x0, n0, 0, nw, true, acc_empty_leader + 8 * a);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -750,6 +901,37 @@ static int launch_pix(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPi
   return MSG_OK;
 }
 
+static int max_active_pairs(const void* kfn, size_t smem) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (unsigned)num_sms());
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kfn, &cfg) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = 0; }
+  return n;
+}
+
+static int launch_pix2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPixParams& p, cudaStream_t st) {
+  constexpr int STAGES = 6;
+  constexpr size_t smem = (size_t)STAGES * (16384 + 128 * 128) + 4 * 32 * 33 * 4 + 16 * STAGES + 64 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  auto kfn = tc_pixgemm2_kernel<STAGES>;
+  static int pairs_max = -1;
+  if (pairs_max < 0) {
+    MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pairs_max = max_active_pairs(reinterpret_cast<const void*>(kfn), smem);
+  }
+  if (pairs_max <= 0) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05, CTA pairs): no cluster can be resident");
+  const int pairs = p.total_tiles < pairs_max ? p.total_tiles : pairs_max;
+  kfn<<<2 * pairs, 192, smem, st>>>(tmA, tmB, p);
+  MSG_CHECK_LAUNCH("conv pixgemm(tcgen05, CTA pairs)");
+  return MSG_OK;
+}
+
 // two 128-pixel sub-tiles per CTA tile pay off for narrow N once there is more than a round of such tiles
 static int pick_mt(const PixGemm& g, int BN) {
   if (BN > 128) return 1;
@@ -787,6 +969,13 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (wt_log2 > 7) wt_log2 = 7;
   const int MT = pick_mt(g, BN);
   const int Wt = 1 << wt_log2, Ht = (128 * MT) >> wt_log2;
+  // CTA pairs for wide N (BN == 256) when there are enough pixel-tile pairs to fill the machine
+  const int64_t ptiles = ceil_div(g.PW, Wt) * ceil_div(g.PH, Ht);
+  const int64_t pair_tiles = ((ptiles + 1) / 2) * (Npad / BN) * (int64_t)g.B;
+  // Measured on B200 (tools/conv_bench.py): no gain over the single-CTA kernel at 256^2 (3.07 vs 3.13 ms — that kernel
+  // already runs at the MMA issue rate the power-capped clock allows) and a loss at <= 128^2 (coarser tiles), so the pair
+  // kernel is opt-in: MSG_B200_TC_VARIANT=4.
+  const bool pairs = BN == 256 && MT == 1 && (tc_variant() & 4u) && pair_tiles >= num_sms() / 2;
   CUtensorMap tmA, tmB;
   {
     const uint64_t dims[4] = {(uint64_t)g.Cr, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
@@ -798,7 +987,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   {
     const uint64_t dims[4] = {(uint64_t)Cpad, (uint64_t)Npad, (uint64_t)g.ntaps, (uint64_t)BW};
     const uint64_t strides[3] = {(uint64_t)Cpad * 4, (uint64_t)Cpad * Npad * 4, (uint64_t)Cpad * Npad * g.ntaps * 4};
-    const uint32_t box[4] = {32, (uint32_t)BN, 1, 1};
+    const uint32_t box[4] = {32, (uint32_t)(pairs ? BN / 2 : BN), 1, 1};     // a CTA of a pair loads half of the rows
     int rc = make_tmap(&tmB, wt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -810,7 +999,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.tiles_x = (int)ceil_div(g.PW, Wt);
   p.tiles_y = (int)ceil_div(g.PH, Ht);
   p.n_tiles = Npad / BN;
-  const int64_t total_tiles = (int64_t)p.tiles_x * p.tiles_y * p.n_tiles * g.B;
+  const int64_t total_tiles = pairs ? pair_tiles : (int64_t)p.tiles_x * p.tiles_y * p.n_tiles * g.B;
   if (total_tiles > 0x7fffffffLL) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): too many tiles");
   p.total_tiles = (int)total_tiles;
   p.out = g.out; p.os = g.os;
@@ -825,7 +1014,9 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int pslot = prof_begin(0, g.ntaps, g.Cr, g.N, (int64_t)g.B * g.PH * g.PW,
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);
   int rc;
-  if (MT == 2) {
+  if (pairs) {
+    rc = launch_pix2(tmA, tmB, p, st);
+  } else if (MT == 2) {
     switch (BN) {
       case 128: rc = launch_pix<128, 2>(tmA, tmB, p, st); break;
       case 64: rc = launch_pix<64, 2>(tmA, tmB, p, st); break;

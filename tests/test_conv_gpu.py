@@ -205,3 +205,27 @@ def test_conv_bias_act_autograd_on_device(built_library):
             assert ((gg - rg).norm() / rg.norm()).item() < (1e-3 if flags == _lib.CONV_FORCE_SIMT else 0.1)
     finally:
         _C.conv_flags = old
+
+
+def test_conv_cta_pair_kernel_subprocess(built_library):
+    """The opt-in cta_group::2 kernel (MSG_B200_TC_VARIANT=4, read once per process) against the oracle."""
+    import os
+    import subprocess
+    import sys
+    from tests.conftest import ROOT
+    code = (
+        "import sys, torch; sys.path.insert(0, %r)\n"
+        "from multi_stylegan_b200 import _C, _lib\n"
+        "from oracle import ops\n"
+        "_C.conv_flags = _lib.CONV_FORCE_TC\n"
+        "g = torch.Generator().manual_seed(0)\n"
+        "for (B, C, O, H, W, k) in [(2, 64, 320, 40, 24, 3), (3, 32, 512, 64, 64, 1), (1, 96, 256, 130, 130, 3)]:\n"
+        "    x = torch.randn(B, C, H, W, generator=g); w = torch.randn(B, O, C, k, k, generator=g) / (C * k * k) ** 0.5\n"
+        "    want = ops.conv2d(x, w, 1, k // 2)\n"
+        "    got = _C.conv2d_forward(x.cuda(), w.cuda(), 1, k // 2).cpu()\n"
+        "    err = ((got - want).abs().max() / want.abs().max()).item()\n"
+        "    assert err < 1e-2, err\n"
+        "torch.cuda.synchronize(); print('PAIR_OK')\n" % ROOT)
+    env = dict(os.environ, MSG_B200_TC_VARIANT="4")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert "PAIR_OK" in out.stdout, out.stdout + out.stderr

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--lazy", action="store_true", help="profile an iteration that runs R1 + path length")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "step_profile.txt"))
     ap.add_argument("--rows", type=int, default=70)
+    ap.add_argument("--shapes", action="store_true", help="also list torch copy / elementwise ops grouped by input shape")
     args = ap.parse_args()
 
     from multi_stylegan_b200 import config
@@ -33,15 +34,17 @@ def main():
     G = G_mod.Generator(config.multi_style_gan_generator_config, compute_dead_branch=False).to(dev)
     D = D_mod.Discriminator(config.u_net_2d_discriminator_config, no_rfp=True).to(dev)
     hp = dict(config.generation_hyperparameters)
-    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-4, lr_style=2e-6), betas=hp["betas"])
-    opt_d = torch.optim.Adam(D.parameters(), lr=6e-4, betas=hp["betas"])
+    # same Adam as train_multi_stylegan.py:53-57; fused=True only selects PyTorch's single-kernel implementation
+    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-4, lr_style=2e-6), betas=hp["betas"], fused=True)
+    opt_d = torch.optim.Adam(D.parameters(), lr=6e-4, betas=hp["betas"], fused=True)
     mw = ModelWrapper(G, D, opt_g, opt_d, hyperparameters=hp, device=dev)
     real = torch.rand(args.batch, 2, 3, 256, 256, device=dev)
     for i in range(3):
         mw.iteration = 14 if (i == 0 and args.lazy) else 0
         mw.train_step(real)
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    import time as _time
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=args.shapes) as prof:
         for i in range(args.steps):
             mw.iteration = 15 if args.lazy else 0
             mw.train_step(real)
@@ -56,10 +59,20 @@ def main():
     for e in events[:args.rows]:
         lines.append("%10.3f %6.2f%% %6d %9.1f  %s" % (e.device_time_total / 1e3, 100.0 * e.device_time_total / total,
                                                        e.count, e.device_time_total / e.count, e.key[:150]))
+    if args.shapes:
+        ops = [e for e in prof.key_averages(group_by_input_shape=True)
+               if e.key in ("aten::copy_", "aten::add", "aten::add_", "aten::mul", "aten::cat", "aten::sum", "aten::div",
+                            "aten::mul_", "aten::clone", "aten::repeat", "aten::sub", "aten::neg", "aten::fill_", "aten::zero_")
+               and e.device_time_total > 0]
+        ops.sort(key=lambda e: -e.device_time_total)
+        lines.append("")
+        lines.append("torch elementwise / copy ops by input shape (device time, %d step(s))" % args.steps)
+        for e in ops[:45]:
+            lines.append("%10.3f ms %5d calls  %-14s %s" % (e.device_time_total / 1e3, e.count, e.key, str(e.input_shapes)[:120]))
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         f.write("\n".join(lines) + "\n")
-    print("\n".join(lines[:45]))
+    print("\n".join(lines[:45] if not args.shapes else lines[-46:]))
 
 
 if __name__ == "__main__":
