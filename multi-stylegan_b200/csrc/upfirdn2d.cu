@@ -234,6 +234,141 @@ fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, cons
   }
 }
 
+// up == 2, down == 1, taps <= 4x4 (polyphase: every output reads 2x2 inputs).  The two outputs per axis that share an
+// input pair are produced together: a thread loads one 2x2 input patch (4 float4) and writes a 2x2 output block.
+__global__ void __launch_bounds__(256)
+fir_cl_up2_kernel(float4* __restrict__ out, const float4* __restrict__ in, const float* __restrict__ kernel,
+                  const FirClParams p, int mx_min, int my_min, int nmx, int nmy) {
+  __shared__ float sk[4][4];
+  if (threadIdx.x < 16) {
+    const int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+    float v = 0.f;
+    if (ky < p.kernel_h && kx < p.kernel_w) v = kernel[(p.kernel_h - 1 - ky) * p.kernel_w + (p.kernel_w - 1 - kx)];
+    sk[ky][kx] = v;
+  }
+  __syncthreads();
+  float kf[4][4];
+#pragma unroll
+  for (int y = 0; y < 4; ++y)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) kf[y][x] = sk[y][x];
+  const int64_t total = (int64_t)p.total4;            // here: number of (b, jy, jx, q) work items
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; idx < total; idx += stride) {
+    int64_t t = idx;
+    const int q = (int)(t % p.C4); t /= p.C4;
+    const int jx = (int)(t % nmx); t /= nmx;
+    const int jy = (int)(t % nmy); t /= nmy;
+    const int64_t b = t;
+    const int mx = mx_min + jx, my = my_min + jy;     // input coordinates of the patch's top-left element
+    const float4* inb = in + (b * p.in_h * (int64_t)p.in_w) * p.C4 + q;
+    float4 I[2][2];
+#pragma unroll
+    for (int y = 0; y < 2; ++y)
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int iy = my + y, ix = mx + x;
+        I[y][x] = (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) ? __ldg(inb + ((int64_t)iy * p.in_w + ix) * p.C4)
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    float4* outb = out + (b * p.out_h * (int64_t)p.out_w) * p.C4 + q;
+    // outputs o = 2m - 1 + pad0 (tap phase 1) and o = 2m + pad0 (tap phase 0)
+#pragma unroll
+    for (int ay = 0; ay < 2; ++ay) {
+      const int oy = 2 * my - 1 + p.pad_y0 + ay;
+      if (oy < 0 || oy >= p.out_h) continue;
+      const int phy = 1 - ay;
+#pragma unroll
+      for (int ax = 0; ax < 2; ++ax) {
+        const int ox = 2 * mx - 1 + p.pad_x0 + ax;
+        if (ox < 0 || ox >= p.out_w) continue;
+        const int phx = 1 - ax;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int y = 0; y < 2; ++y)
+#pragma unroll
+          for (int x = 0; x < 2; ++x) fma4(acc, I[y][x], kf[phy + 2 * y][phx + 2 * x]);
+        outb[((int64_t)oy * p.out_w + ox) * p.C4] = acc;
+      }
+    }
+  }
+}
+
+// up == 1, down == 2, taps <= 4x4.  Same thread layout as the blur kernel; a thread walks down its strip of output
+// rows, loads two input rows per output row and adds them to the two output rows they touch (taps 0,1 of the current
+// row, taps 2,3 of the previous one): 3 * COLS + ... float4 loads per output instead of 16.
+template <int COLS>
+__global__ void __launch_bounds__(256)
+fir_cl_down2_kernel(float4* __restrict__ out, const float4* __restrict__ in, const float* __restrict__ kernel,
+                    const FirClParams p) {
+  __shared__ float sk[4][4];
+  if (threadIdx.x < 16) {
+    const int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+    float v = 0.f;
+    if (ky < p.kernel_h && kx < p.kernel_w) v = kernel[(p.kernel_h - 1 - ky) * p.kernel_w + (p.kernel_w - 1 - kx)];
+    sk[ky][kx] = v;
+  }
+  __syncthreads();
+  float kf[4][4];
+#pragma unroll
+  for (int y = 0; y < 4; ++y)
+#pragma unroll
+    for (int x = 0; x < 4; ++x) kf[y][x] = sk[y][x];
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t bid = blockIdx.x;
+  const int chunk = (int)(bid % p.chunks); bid /= p.chunks;
+  const int tx = (int)(bid % p.tiles_x); bid /= p.tiles_x;
+  const int ty = (int)(bid % p.tiles_y); bid /= p.tiles_y;
+  const int64_t b = bid;
+  const int q = chunk * 32 + lane;
+  if (q >= p.C4) return;
+  const int ox0 = (tx * 8 + warp) * COLS;
+  if (ox0 >= p.out_w) return;
+  const int oy0 = ty * p.tile_rows;
+  const int ix0 = 2 * ox0 - p.pad_x0;
+  constexpr int NIN = 2 * COLS + 2;
+  const float4* inb = in + (b * p.in_h * (int64_t)p.in_w) * p.C4 + q;
+  float4* outb = out + (b * p.out_h * (int64_t)p.out_w) * p.C4 + q;
+
+  float4 prev[COLS], cur[COLS];
+#pragma unroll
+  for (int c = 0; c < COLS; ++c) prev[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = oy0; i <= oy0 + p.tile_rows && i <= p.out_h; ++i) {
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) cur[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int iy = 2 * i - p.pad_y0 + rr;
+      if (iy < 0 || iy >= p.in_h) continue;
+      const float4* row = inb + ((int64_t)iy * p.in_w) * p.C4;
+      float4 v[NIN];
+#pragma unroll
+      for (int j = 0; j < NIN; ++j) {
+        const int ix = ix0 + j;
+        v[j] = (ix >= 0 && ix < p.in_w) ? __ldg(row + (int64_t)ix * p.C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int c = 0; c < COLS; ++c)
+#pragma unroll
+        for (int kx = 0; kx < 4; ++kx) {
+          fma4(cur[c], v[2 * c + kx], kf[rr][kx]);          // taps 0,1 of output row i
+          fma4(prev[c], v[2 * c + kx], kf[rr + 2][kx]);     // taps 2,3 of output row i - 1
+        }
+    }
+    const int oy = i - 1;
+    if (oy >= oy0 && oy < p.out_h) {
+      float4* orow = outb + ((int64_t)oy * p.out_w) * p.C4;
+#pragma unroll
+      for (int c = 0; c < COLS; ++c)
+        if (ox0 + c < p.out_w) orow[(int64_t)(ox0 + c) * p.C4] = prev[c];
+    }
+#pragma unroll
+    for (int c = 0; c < COLS; ++c) prev[c] = cur[c];
+  }
+}
+
 // any (UP, DOWN) in {1,2}, taps <= 4x4: one output float4 per thread, taps gathered through L1.
 template <int UP, int DOWN>
 __global__ void __launch_bounds__(256)
@@ -382,7 +517,10 @@ extern "C" int msg_upfirdn2d(void* out, const void* in, const void* kernel, int6
       constexpr int COLS = 2;
       p.chunks = (int)ceil_div(p.C4, 32);
       p.tiles_x = (int)ceil_div(out_w, 8 * COLS);
+      // strips of 32 output rows (3 halo rows each); shorter strips when that leaves too few CTAs to fill the machine
       p.tile_rows = out_h < 32 ? out_h : 32;
+      while (p.tile_rows > 8 && major * ceil_div(out_h, p.tile_rows) * p.tiles_x * p.chunks < 8 * (int64_t)num_sms())
+        p.tile_rows >>= 1;
       p.tiles_y = (int)ceil_div(out_h, p.tile_rows);
       const int64_t blocks = major * p.tiles_y * p.tiles_x * p.chunks;
       if (blocks > 0x7fffffffLL) return fail(MSG_ERR_UNSUPPORTED, "upfirdn2d: grid too large");
@@ -393,6 +531,34 @@ extern "C" int msg_upfirdn2d(void* out, const void* in, const void* kernel, int6
     const int64_t want4 = ceil_div(p.total4, 256);
     const int64_t cap4 = (int64_t)num_sms() * 64;
     const unsigned g4 = (unsigned)(want4 < cap4 ? want4 : cap4);
+    if (up_x == 2 && down_x == 1) {
+      // input patches m with outputs {2m - 1 + pad0, 2m + pad0} intersecting [0, out)
+      const int mx_min = floor_div_i(1 - pad_x0, 2), mx_max = floor_div_i(out_w - pad_x0, 2);
+      const int my_min = floor_div_i(1 - pad_y0, 2), my_max = floor_div_i(out_h - pad_y0, 2);
+      const int nmx = mx_max - mx_min + 1, nmy = my_max - my_min + 1;
+      FirClParams pu = p;
+      pu.total4 = major * nmy * (int64_t)nmx * p.C4;
+      const int64_t wantu = ceil_div(pu.total4, 256);
+      const unsigned gu = (unsigned)(wantu < cap4 ? wantu : cap4);
+      fir_cl_up2_kernel<<<gu, 256, 0, st>>>((float4*)out, (const float4*)in, (const float*)kernel, pu, mx_min, my_min, nmx, nmy);
+      MSG_CHECK_LAUNCH("upfirdn2d(channels-last up2)");
+      return MSG_OK;
+    }
+    if (up_x == 1 && down_x == 2) {
+      constexpr int COLS = 2;
+      FirClParams pd = p;
+      pd.chunks = (int)ceil_div(p.C4, 32);
+      pd.tiles_x = (int)ceil_div(out_w, 8 * COLS);
+      pd.tile_rows = out_h < 32 ? out_h : 32;
+      while (pd.tile_rows > 8 && major * ceil_div(out_h, pd.tile_rows) * pd.tiles_x * pd.chunks < 8 * (int64_t)num_sms())
+        pd.tile_rows >>= 1;
+      pd.tiles_y = (int)ceil_div(out_h, pd.tile_rows);
+      const int64_t blocks = major * pd.tiles_y * pd.tiles_x * pd.chunks;
+      if (blocks > 0x7fffffffLL) return fail(MSG_ERR_UNSUPPORTED, "upfirdn2d: grid too large");
+      fir_cl_down2_kernel<COLS><<<(unsigned)blocks, 256, 0, st>>>((float4*)out, (const float4*)in, (const float*)kernel, pd);
+      MSG_CHECK_LAUNCH("upfirdn2d(channels-last down2)");
+      return MSG_OK;
+    }
     if (up_x == 2 && down_x == 1)
       fir_cl_gather_kernel<2, 1><<<g4, 256, 0, st>>>((float4*)out, (const float4*)in, (const float*)kernel, p);
     else if (up_x == 1 && down_x == 2)
