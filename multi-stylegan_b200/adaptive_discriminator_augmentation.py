@@ -117,6 +117,29 @@ class AdaptiveDiscriminatorAugmentation(nn.Module):
             r = r / dist.get_world_size(self.process_group)
         return r
 
+    def _update_p(self) -> None:
+        if len(self.r) >= self.r_update:
+            r = float(torch.stack(self.r).mean().item())          # the only host sync: once per r_update calls
+            self.p = self.p + self.p_step if r > self.r_target else self.p - self.p_step
+            self.p = min(max(self.p, 0.), self.p_max)
+            self.r = []
+            self.r_history.append(r)
+
+    def forward_pair(self, real: torch.Tensor, fake: torch.Tensor, draws_real=None, draws_fake=None):
+        """forward(real, is_real=True) and forward(fake, is_real=False) with one batched discriminator pass: both halves
+        are augmented separately (real first, the order in which the reference consumes the host RNGs), `p` cannot change
+        between the two calls of a step (it only moves after a fake call), so the results are those of the two calls."""
+        pair = getattr(self.discriminator, "forward_pair", None)
+        if pair is None or real.shape != fake.shape:
+            return self.forward(real, is_real=True, draws=draws_real), self.forward(fake, is_real=False, draws=draws_fake)
+        shape = real.shape
+        a = self.augmentation_pipeline(real.flatten(start_dim=1, end_dim=2), self.p, draws_real).reshape(shape)
+        b = self.augmentation_pipeline(fake.flatten(start_dim=1, end_dim=2), self.p, draws_fake).reshape(shape)
+        out_real, out_fake = pair(a, b)
+        self.r.append(self._calc_r(out_fake[0].detach(), out_fake[1].detach()))
+        self._update_p()
+        return out_real, out_fake
+
     def forward(self, images: torch.Tensor, is_real: bool = False, is_cut_mix: bool = False,
                 draws: Optional[Dict[str, object]] = None):
         if is_cut_mix:
@@ -127,10 +150,5 @@ class AdaptiveDiscriminatorAugmentation(nn.Module):
         prediction_scalar, prediction_pixel_wise = self.discriminator(flat.reshape(original_shape))
         if not is_real:
             self.r.append(self._calc_r(prediction_scalar.detach(), prediction_pixel_wise.detach()))
-        if len(self.r) >= self.r_update:
-            r = float(torch.stack(self.r).mean().item())          # the only host sync: once per r_update calls
-            self.p = self.p + self.p_step if r > self.r_target else self.p - self.p_step
-            self.p = min(max(self.p, 0.), self.p_max)
-            self.r = []
-            self.r_history.append(r)
+        self._update_p()
         return prediction_scalar, prediction_pixel_wise

@@ -106,8 +106,13 @@ class ModelWrapper(object):
         if self.epoch >= hp["wrong_order_start"] * self.epochs or self.resume_training:
             n = max(1, int(hp["batch_factor_wrong_order"] * B))
             fake_images = torch.cat([fake_images, real_images[:n, :, misc.random_permutation(real_images.shape[2])]], 0)
-        real_pred, real_pred_px = self.discriminator(real_images, is_real=True, is_cut_mix=False)
-        fake_pred, fake_pred_px = self.discriminator(fake_images, is_real=False, is_cut_mix=False)
+        pair = getattr(self.discriminator, "forward_pair", None)
+        if pair is not None and fake_images.shape == real_images.shape:
+            # the reference's two calls (:279-283) as one batched pass with identical results (see forward_pair)
+            (real_pred, real_pred_px), (fake_pred, fake_pred_px) = pair(real_images, fake_images)
+        else:
+            real_pred, real_pred_px = self.discriminator(real_images, is_real=True, is_cut_mix=False)
+            fake_pred, fake_pred_px = self.discriminator(fake_images, is_real=False, is_cut_mix=False)
         l_real, l_fake = self.discriminator_loss(real_pred, fake_pred)
         l_real_px, l_fake_px = self.discriminator_loss(real_pred_px, fake_pred_px, weight=self._trap())
         (l_real + l_fake + l_real_px + l_fake_px).backward()

@@ -62,8 +62,16 @@ class MinibatchStdDev(nn.Module):
     def __init__(self, alpha: float = 1e-8) -> None:
         super().__init__()
         self.alpha = alpha
+        self.groups = 1      # > 1: the batch is `groups` independent sub-batches (Discriminator.forward_pair)
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
+        if self.groups > 1:
+            G, Bg = self.groups, input.shape[0] // self.groups
+            x = input.reshape(G, Bg, *input.shape[1:])
+            centred = x - x.mean(dim=1, keepdim=True)
+            std = torch.sqrt((centred ** 2).mean(dim=1).clamp(min=self.alpha)).mean(dim=(1, 2, 3))      # [G]
+            plane = std.view(G, 1, 1, 1, 1).expand(G, Bg, 1, input.shape[2], input.shape[3])
+            return torch.cat((input, plane.reshape(input.shape[0], 1, input.shape[2], input.shape[3])), 1)
         centred = input - input.mean(dim=0, keepdim=True)
         std = torch.sqrt((centred ** 2).mean(dim=0).clamp(min=self.alpha)).mean().view(1, 1, 1)
         return torch.cat((input, std.repeat(input.shape[0], 1, input.shape[2], input.shape[3])), 1)
@@ -184,6 +192,23 @@ class Discriminator(nn.Module):
         for block, up, skip in zip(self.decoder_blocks, self.transposed_convolutions, reversed(features)):
             x = block(torch.cat([up(x), skip], dim=1))
         return classification, self.final_mapping(x).unsqueeze(dim=2)
+
+
+    def forward_pair(self, first: torch.Tensor, second: torch.Tensor):
+        """(D(first), D(second)) as ONE batched pass.  Every operation of the network is per-sample except
+        MinibatchStdDev, which is evaluated per half, so the results equal two separate calls (the train step's
+        real / fake passes, model_wrapper.py:279-283) with half the launches and better-filled small layers."""
+        assert first.shape == second.shape, "forward_pair needs two batches of the same shape"
+        n = first.shape[0]
+        stds = [m for m in self.modules() if isinstance(m, MinibatchStdDev)]
+        for m in stds:
+            m.groups = 2
+        try:
+            classification, pixel_wise = self.forward(torch.cat([first, second], dim=0))
+        finally:
+            for m in stds:
+                m.groups = 1
+        return (classification[:n], pixel_wise[:n]), (classification[n:], pixel_wise[n:])
 
 
 # ---- CutMix helpers (u_net_2d_discriminator.py:384-448) ------------------------------------------------

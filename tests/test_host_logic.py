@@ -254,3 +254,26 @@ def test_conv_functions_close_under_differentiation(oracle_backend):
     b = run_t(lambda x, w: ops.conv_transpose2d(x, w, stride=2))
     for u, v in zip(a, b):
         assert rel_err(u, v) < 1e-4
+
+
+def test_discriminator_forward_pair_equals_two_calls(oracle_backend):
+    """One batched real+fake pass (MinibatchStdDev per half) == the reference's two calls (model_wrapper.py:279-283)."""
+    g = load_golden("discriminator.pt")
+    net = D_mod.Discriminator(g["config"], no_rfp=True)
+    net.load_state_dict(g["state_dict"])
+    torch.manual_seed(0)
+    a = g["x"]
+    b = torch.rand_like(a)
+    (sa, pa), (sb, pb) = net.forward_pair(a, b)
+    ra, rb = net(a), net(b)
+    for got, want in ((sa, ra[0]), (pa, ra[1]), (sb, rb[0]), (pb, rb[1])):
+        assert got.shape == want.shape and rel_err(got, want) < 1e-5
+    # gradients of a loss over both halves
+    net.zero_grad()
+    (sa.sum() + pa.mean() - sb.sum() - pb.mean()).backward()
+    gp = {n: p.grad.clone() for n, p in net.named_parameters()}
+    net.zero_grad()
+    (ra[0].sum() + ra[1].mean() - rb[0].sum() - rb[1].mean()).backward()
+    for n, p in net.named_parameters():
+        assert rel_err(gp[n], p.grad) < 1e-4, n
+    assert all(m.groups == 1 for m in net.modules() if isinstance(m, D_mod.MinibatchStdDev))
