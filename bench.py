@@ -246,15 +246,23 @@ def run_ours(args):
     hbm, bf16_burst, bf16_sust, src = peaks()
     tf32_peak = bf16_sust / 2.0
     roof = None
+    traffic_table = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu captures
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic_table = json.load(f)
     if prof:
         top = max(prof, key=lambda e: e["ms_total"])
         achieved = top["flops_per_launch"] * top["launches"] / (top["ms_total"] * 1e-3) / 1e12
         conv_ms = sum(e["ms_total"] for e in prof)
         conv_flops = sum(e["flops_per_launch"] * e["launches"] for e in prof)
+        kname = "tc_%s (tcgen05 kind::tf32) taps=%d K=%d N=%d pixels=%d" % (
+            top["kind"], top["taps"], top["k_channels"], top["n_channels"], top["pixels"])
         roof = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                "frac": achieved / tf32_peak, "traffic": None,
-                "kernel": "tc_%s (tcgen05 kind::tf32) taps=%d K=%d N=%d pixels=%d" % (
-                    top["kind"], top["taps"], top["k_channels"], top["n_channels"], top["pixels"]),
+                "frac": achieved / tf32_peak, "traffic": traffic_table.get(kname),
+                "kernel": kname,
+                "algorithmic_flops_per_launch": top["flops_per_launch"],
+                "frac_of_burst_peak": achieved / (bf16_burst / 2.0),
                 "launches": top["launches"], "avg_ms": top["ms_total"] / top["launches"],
                 "share_of_step": top["ms_total"] / ms,
                 "peak_note": "TF32 dense = 1/2 of the %s bf16 sustained rate (%.0f TFLOP/s) in MEASURED_PEAKS.json" % (src, bf16_sust),
