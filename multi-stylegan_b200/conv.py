@@ -31,6 +31,9 @@ class _ConvForward(Function):
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
         dx = dw = None
+        if ctx.needs_input_grad[0] and ctx.needs_input_grad[1] and _C.conv_channels_last and dy.is_cuda:
+            # a channel slice of a concatenation's gradient is a strided view: densify it once for both kernels
+            dy = dy.contiguous(memory_format=torch.channels_last)
         if ctx.needs_input_grad[0]:
             dx = _ConvDgrad.apply(dy, w, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
         if ctx.needs_input_grad[1]:

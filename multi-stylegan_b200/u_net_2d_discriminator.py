@@ -190,7 +190,11 @@ class Discriminator(nn.Module):
                 x = self.downscale_convolutions[index](x)
         classification = self.classification_head(x)
         for block, up, skip in zip(self.decoder_blocks, self.transposed_convolutions, reversed(features)):
-            x = block(torch.cat([up(x), skip], dim=1))
+            # reference: conv1x1(Upsample(x)) (:87,:135-137).  A 1x1 convolution (per pixel, across channels) and the
+            # FIR upsampling (per channel, across pixels) commute exactly, so the convolution runs first, on a quarter
+            # of the pixels, and the upsampling on the smaller channel count.
+            upsample, conv1x1 = up[0], up[1]
+            x = block(torch.cat([upsample(conv1x1(x)), skip], dim=1))
         return classification, self.final_mapping(x).unsqueeze(dim=2)
 
 
