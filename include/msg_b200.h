@@ -103,6 +103,15 @@ int msg_upfirdn2d(void* out, const void* in, const void* kernel,
                   int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                   int dtype, msg_stream_t stream);
 
+/* FIR (up = down = 1) with the StyledConv2d tail fused into the store — the blur that follows an up-convolution
+ * (multi_stylegan_generator.py:403) + noise (:289-292) + bias / leaky ReLU / gain (op_static/fused_act.py:58):
+ *   out[b,y,x,c] = act(fir(in)[b,y,x,c] + noise_w[0]*noise[b*noise_batch_stride + y*out_w + x] + bias[c]) * gain
+ * fp32 channels-last data only (in [major=B, h, w, minor=C], C % 4 == 0); MSG_ERR_UNSUPPORTED otherwise. */
+int msg_upfirdn2d_bias_act(float* out, const float* in, const float* kernel, int64_t major, int in_h, int in_w,
+                           int minor, int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                           const float* noise, const float* noise_w, int64_t noise_batch_stride,
+                           const float* bias, int act, float slope, float gain, msg_stream_t stream);
+
 /* -------------------------------------------------------------------------------------------
  * Dense / per-sample ("grouped by batch") 2-D convolution primitives, fp32 storage, TF32 tensor
  * cores (tcgen05) with fp32 accumulation for the shapes the implicit-GEMM kernels tile, an fp32

@@ -191,6 +191,42 @@ def upfirdn2d(input: torch.Tensor, kernel: torch.Tensor, up_x: int, up_y: int, d
     return out
 
 
+def blur_noise_bias_act(x: torch.Tensor, kernel: torch.Tensor, pad: Sequence[int], noise: Optional[torch.Tensor],
+                        noise_w: Optional[torch.Tensor], bias: Optional[torch.Tensor], slope: float,
+                        gain: float) -> torch.Tensor:
+    """lrelu(fir(x) + noise_w * noise + bias[c]) * gain in the channels-last blur kernel (up = down = 1).
+    x [B,C,H,W] (C % 4 == 0), kernel [kh,kw] <= 4x4, pad (x0, x1, y0, y1), noise [B or 1, 1, OH, OW]."""
+    _check_f32(x, "x")
+    _require_cuda(kernel, "kernel")
+    x = _cl(x)
+    k = kernel.contiguous().to(torch.float32)
+    B, C, H, W = x.shape
+    kh, kw = k.shape
+    px0, px1, py0, py1 = [int(v) for v in pad]
+    L = _lib.lib()
+    out_h = L.msg_upfirdn2d_out_size(H, 1, 1, py0, py1, kh)
+    out_w = L.msg_upfirdn2d_out_size(W, 1, 1, px0, px1, kw)
+    if out_h < 0 or out_w < 0:
+        raise RuntimeError("blur_noise_bias_act: negative output size")
+    out = torch.empty((B, C, out_h, out_w), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    nbs = 0
+    if noise is not None:
+        _check_f32(noise, "noise")
+        noise, noise_w = _aligned(noise), _aligned(noise_w)
+        if noise.numel() == B * out_h * out_w:
+            nbs = out_h * out_w
+        elif noise.numel() != out_h * out_w:
+            raise RuntimeError("blur_noise_bias_act: noise must be [B or 1, 1, OH, OW]")
+    if bias is not None:
+        bias = _aligned(bias)
+    with torch.cuda.device(x.device):
+        rc = L.msg_upfirdn2d_bias_act(_ptr(out), _ptr(x), _ptr(k), B, H, W, C, kh, kw, px0, px1, py0, py1, _ptr(noise),
+                                      _ptr(noise_w) if noise is not None else None, nbs, _ptr(bias), 1, float(slope),
+                                      float(gain), _stream(x))
+    _lib.check(rc, "upfirdn2d_bias_act")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # conv primitives (fp32).  w is [O, C, kh, kw] (shared) or [B, O, C, kh, kw] (one filter bank per sample,
 # the reference's groups=B trick, multi_stylegan_generator.py:390-411).

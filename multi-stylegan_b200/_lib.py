@@ -86,6 +86,9 @@ _SIGNATURES = {
     "msg_upfirdn2d_out_size": (_c.c_int, [_c.c_int] * 6),
     "msg_upfirdn2d": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64] + [_c.c_int] * 13 +
                       [_c.c_int, _c.c_void_p]),
+    "msg_upfirdn2d_bias_act": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64] + [_c.c_int] * 9 +
+                               [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_float, _c.c_float,
+                                _c.c_void_p]),
     "msg_conv2d_workspace": (_c.c_size_t, [_c.POINTER(ConvDesc), _c.c_int, _c.c_int]),
     "msg_conv2d_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc), _c.c_float,
                                       _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),

@@ -145,6 +145,14 @@ struct FirClParams {
   int tiles_x, tiles_y, chunks;   // blur kernel: CTA grid decomposition
   int tile_rows;
   int64_t total4;                 // gather kernel: number of output float4
+  // optional fused tail of the blur kernel (StyledConv2d after an up-conv): + noise_w * noise[b, oy, ox] + bias[c],
+  // leaky ReLU, gain  (multi_stylegan_generator.py:289-292, op_static/fused_act.py:58)
+  const float* ep_noise;
+  const float* ep_noise_w;
+  const float* ep_bias;
+  int64_t ep_noise_bs;
+  int ep_act;
+  float ep_slope, ep_gain;
 };
 
 __device__ __forceinline__ void fma4(float4& a, const float4& v, float k) {
@@ -192,6 +200,11 @@ fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, cons
   for (int s = 0; s < 4; ++s)
 #pragma unroll
     for (int c = 0; c < COLS; ++c) acc[s][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const bool fused = p.ep_act || p.ep_bias || p.ep_noise;
+  float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.ep_bias) bz = __ldg(reinterpret_cast<const float4*>(p.ep_bias) + q);
+  const float nw = p.ep_noise ? __ldg(p.ep_noise_w) : 0.f;
+  const float* nzb = p.ep_noise ? p.ep_noise + b * p.ep_noise_bs : nullptr;
 
   const int n_in = p.tile_rows + 3;               // input rows i = 0 .. tile_rows + 2  (iy = oy0 - pad_y0 + i)
   for (int i0 = 0; i0 < n_in; i0 += 4) {
@@ -225,7 +238,19 @@ fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, cons
           float4* orow = outb + ((int64_t)oy * p.out_w) * p.C4;
 #pragma unroll
           for (int c = 0; c < COLS; ++c)
-            if (ox0 + c < p.out_w) orow[(int64_t)(ox0 + c) * p.C4] = acc[s][c];
+            if (ox0 + c < p.out_w) {
+              float4 v = acc[s][c];
+              if (fused) {
+                const float add = nzb ? nw * __ldg(nzb + (int64_t)oy * p.out_w + ox0 + c) : 0.f;
+                v.x += add + bz.x; v.y += add + bz.y; v.z += add + bz.z; v.w += add + bz.w;
+                if (p.ep_act) {
+                  v.x = v.x > 0.f ? v.x : v.x * p.ep_slope; v.y = v.y > 0.f ? v.y : v.y * p.ep_slope;
+                  v.z = v.z > 0.f ? v.z : v.z * p.ep_slope; v.w = v.w > 0.f ? v.w : v.w * p.ep_slope;
+                }
+                v.x *= p.ep_gain; v.y *= p.ep_gain; v.z *= p.ep_gain; v.w *= p.ep_gain;
+              }
+              orow[(int64_t)(ox0 + c) * p.C4] = v;
+            }
         }
 #pragma unroll
         for (int c = 0; c < COLS; ++c) acc[s][c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -481,10 +506,39 @@ extern "C" int msg_upfirdn2d_out_size(int in_size, int up, int down, int pad0, i
   return (in_size * up + pad0 + pad1 - ksize + down) / down;
 }
 
+struct FirEpilogue {
+  const float* noise; const float* noise_w; const float* bias; int64_t noise_bs; int act; float slope, gain;
+};
+
+static int upfirdn2d_impl(void* out, const void* in, const void* kernel, int64_t major, int in_h,
+                          int in_w, int minor, int kernel_h, int kernel_w, int up_x, int up_y,
+                          int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                          int dtype, msg_stream_t stream, const FirEpilogue* ep);
+
 extern "C" int msg_upfirdn2d(void* out, const void* in, const void* kernel, int64_t major, int in_h,
                              int in_w, int minor, int kernel_h, int kernel_w, int up_x, int up_y,
                              int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
                              int dtype, msg_stream_t stream) {
+  return upfirdn2d_impl(out, in, kernel, major, in_h, in_w, minor, kernel_h, kernel_w, up_x, up_y, down_x, down_y, pad_x0,
+                        pad_x1, pad_y0, pad_y1, dtype, stream, nullptr);
+}
+
+extern "C" int msg_upfirdn2d_bias_act(float* out, const float* in, const float* kernel, int64_t major, int in_h, int in_w,
+                                      int minor, int kernel_h, int kernel_w, int pad_x0, int pad_x1, int pad_y0,
+                                      int pad_y1, const float* noise, const float* noise_w, int64_t noise_batch_stride,
+                                      const float* bias, int act, float slope, float gain, msg_stream_t stream) {
+  if (noise && !noise_w) return fail(MSG_ERR_BAD_ARG, "upfirdn2d_bias_act: noise needs noise_w");
+  if (act != 0 && act != 1) return fail(MSG_ERR_BAD_ARG, "upfirdn2d_bias_act: act must be 0 or 1");
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15u)) return fail(MSG_ERR_BAD_ARG, "upfirdn2d_bias_act: bias must be 16-byte aligned");
+  FirEpilogue ep{noise, noise_w, bias, noise_batch_stride, act, slope, gain};
+  return upfirdn2d_impl(out, in, kernel, major, in_h, in_w, minor, kernel_h, kernel_w, 1, 1, 1, 1, pad_x0, pad_x1, pad_y0,
+                        pad_y1, MSG_F32, stream, &ep);
+}
+
+static int upfirdn2d_impl(void* out, const void* in, const void* kernel, int64_t major, int in_h,
+                          int in_w, int minor, int kernel_h, int kernel_w, int up_x, int up_y,
+                          int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1,
+                          int dtype, msg_stream_t stream, const FirEpilogue* ep) {
   if (major < 0 || in_h < 0 || in_w < 0 || minor < 0) return fail(MSG_ERR_BAD_ARG, "upfirdn2d: negative size");
   if (up_x < 1 || up_y < 1 || down_x < 1 || down_y < 1) return fail(MSG_ERR_BAD_ARG, "upfirdn2d: up/down must be >= 1");
   if (kernel_h < 1 || kernel_w < 1) return fail(MSG_ERR_BAD_ARG, "upfirdn2d: empty FIR kernel");
@@ -497,6 +551,13 @@ extern "C" int msg_upfirdn2d(void* out, const void* in, const void* kernel, int6
   if (!out || !in || !kernel) return fail(MSG_ERR_BAD_ARG, "upfirdn2d: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
 
+  if (ep) {
+    // the fused tail lives in the channels-last blur kernel only
+    const bool ok = dtype == MSG_F32 && minor >= 4 && (minor % 4 == 0) && up_x == 1 && up_y == 1 && down_x == 1 && down_y == 1 &&
+                    kernel_h <= 4 && kernel_w <= 4 && in_h > 0 && in_w > 0 &&
+                    ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    if (!ok) return fail(MSG_ERR_UNSUPPORTED, "upfirdn2d_bias_act: needs fp32 channels-last data (minor %% 4 == 0), up = down = 1, taps <= 4x4");
+  }
   if (dtype == MSG_F32 && minor == 1 && up_x == up_y && down_x == down_y && kernel_h <= 4 && kernel_w <= 4 &&
       in_h > 0 && in_w > 0) {
     FirParams p{};
@@ -513,6 +574,11 @@ extern "C" int msg_upfirdn2d(void* out, const void* in, const void* kernel, int6
     p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.C4 = minor / 4;
     p.pad_x0 = pad_x0; p.pad_y0 = pad_y0; p.kernel_h = kernel_h; p.kernel_w = kernel_w;
     p.total4 = total / 4;
+    p.ep_gain = 1.f;
+    if (ep) {
+      p.ep_noise = ep->noise; p.ep_noise_w = ep->noise_w; p.ep_bias = ep->bias; p.ep_noise_bs = ep->noise_bs;
+      p.ep_act = ep->act; p.ep_slope = ep->slope; p.ep_gain = ep->gain;
+    }
     if (up_x == 1 && down_x == 1) {
       constexpr int COLS = 2;
       p.chunks = (int)ceil_div(p.C4, 32);

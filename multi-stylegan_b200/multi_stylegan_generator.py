@@ -20,6 +20,7 @@ from torch import autograd
 from . import conv, equalized_layer
 from .op_static import FusedLeakyReLU, upfirdn2d
 from .op_static.fused_act import noise_bias_leaky_relu
+from .op_static.upfirdn2d import blur_noise_bias_leaky_relu
 
 
 def _fir_kernel(taps: List[int]) -> torch.Tensor:
@@ -214,6 +215,22 @@ class StyledConv2d(nn.Module):
             output = conv.conv2d_bias_act(input, weight, bias=self.activation.bias, noise=noise,
                                           noise_w=self.noise_injection.weight, stride=mc.stride, padding=mc.padding,
                                           negative_slope=self.activation.negative_slope, gain=self.activation.scale)
+            if self.modulation_mapping:
+                return output, style
+            return output
+        if mc.upsampling and mc.out_channels % 4 == 0:
+            # transposed conv (:393-401) -> [blur (:403) + noise + bias + leaky ReLU] as one FIR pass
+            batch_size = input.shape[0]
+            weight, style = mc.modulated_weight(style, batch_size)
+            output = conv.conv_transpose2d(input, weight.transpose(1, 2), stride=mc.stride, padding=mc.padding)
+            kh, kw = mc.blur.kernel.shape
+            oh = output.shape[2] + sum(mc.blur.padding) - kh + 1
+            ow = output.shape[3] + sum(mc.blur.padding) - kw + 1
+            if noise is None:
+                noise = torch.randn(batch_size, 1, oh, ow, device=input.device, dtype=torch.float32)
+            output = blur_noise_bias_leaky_relu(output, mc.blur.kernel, mc.blur.padding, noise,
+                                                self.noise_injection.weight, self.activation.bias,
+                                                self.activation.negative_slope, self.activation.scale)
             if self.modulation_mapping:
                 return output, style
             return output

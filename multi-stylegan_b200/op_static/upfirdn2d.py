@@ -76,3 +76,41 @@ class UpFirDn2d(Function):
 
 def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
     return UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]))
+
+
+class BlurNoiseBiasAct(Function):
+    """lrelu(upfirdn2d(x, kernel, pad=pad) + noise_weight * noise + bias) * scale — the blur after an up-convolution and
+    the StyledConv2d tail (multi_stylegan_generator.py:403, :289-292, fused_act.py:58) in one pass.  The backward is
+    composed of the differentiable activation backward and the FIR adjoint, so any order of gradient exists."""
+
+    @staticmethod
+    def forward(ctx, input, kernel, pad, noise, noise_weight, bias, negative_slope, scale):
+        pad_x0, pad_x1, pad_y0, pad_y1 = pad
+        kernel_h, kernel_w = kernel.shape
+        out = _C.blur_noise_bias_act(input, kernel, pad, noise, noise_weight, bias, negative_slope, scale)
+        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]), out, noise if noise is not None else out.new_empty(0))
+        ctx.has_noise, ctx.has_bias = noise is not None, bias is not None
+        ctx.negative_slope, ctx.scale, ctx.pad = negative_slope, scale, pad
+        ctx.in_size, ctx.out_size = input.shape, (out.shape[2], out.shape[3])
+        in_h, in_w = input.shape[2], input.shape[3]
+        ctx.g_pad = (kernel_w - pad_x0 - 1, in_w - out.shape[3] + pad_x0, kernel_h - pad_y0 - 1,
+                     in_h - out.shape[2] + pad_y0)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        from .fused_act import NoiseBiasActBackward
+        kernel, grad_kernel, out, noise = ctx.saved_tensors
+        noise = noise if ctx.has_noise else None
+        g_pre, g_bias, g_noise_w = NoiseBiasActBackward.apply(grad_output, out, noise, ctx.negative_slope, ctx.scale)
+        grad_input = None
+        if ctx.needs_input_grad[0]:
+            grad_input = UpFirDn2dBackward.apply(g_pre, kernel, grad_kernel, (1, 1), (1, 1), ctx.pad, ctx.g_pad,
+                                                 ctx.in_size, ctx.out_size, True)
+        return (grad_input, None, None, None, g_noise_w if ctx.has_noise else None, g_bias if ctx.has_bias else None,
+                None, None)
+
+
+def blur_noise_bias_leaky_relu(input, kernel, pad, noise, noise_weight, bias, negative_slope=0.2, scale=1.0):
+    return BlurNoiseBiasAct.apply(input, kernel, (pad[0], pad[1], pad[0], pad[1]), noise, noise_weight, bias,
+                                  negative_slope, scale)

@@ -285,3 +285,25 @@ def test_modulate_weights_backward_vs_autograd(built_library, shape, demod):
     assert rel_err(got_w, want_w) < 1e-5
     got_dW, got_ds = _C.modulate_weights_bwd(go.to(dev()), W.to(dev()), s.to(dev()), got_d, scale, demod)
     assert rel_err(got_dW, want_dW) < 1e-4 and rel_err(got_ds, want_ds) < 1e-4
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 9, 7), (2, 132, 33, 35), (2, 512, 64, 64)])
+@pytest.mark.parametrize("pad", [(2, 1), (1, 2), (2, 2)])
+def test_blur_noise_bias_act_fused(built_library, shape, pad):
+    """Blur + noise + bias + leaky ReLU in the FIR kernel's store == the three reference ops in sequence."""
+    from multi_stylegan_b200 import _C
+    from tests import backend_oracle
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(shape, generator=g)
+    k = torch.tensor([1., 3., 3., 1.])
+    k = k[None] * k[:, None] / 16
+    oh, ow = H + sum(pad) - 3, W + sum(pad) - 3
+    bias = torch.randn(C, generator=g)
+    nw = torch.tensor([0.3])
+    d = dev()
+    for noise in (torch.randn(B, 1, oh, ow, generator=g), torch.randn(1, 1, oh, ow, generator=g), None):
+        p4 = (pad[0], pad[1], pad[0], pad[1])
+        want = backend_oracle.blur_noise_bias_act(x, k, p4, noise, nw, bias, 0.2, 1.25)
+        got = _C.blur_noise_bias_act(x.to(d), k.to(d), p4, None if noise is None else noise.to(d), nw.to(d), bias.to(d), 0.2, 1.25)
+        assert got.shape == want.shape and rel_err(got, want) < TOL
