@@ -35,8 +35,34 @@ def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr())
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(t: torch.Tensor):
+    """torch's current stream on the tensor's device as a raw cudaStream_t (host-side cost matters: the train step issues
+    ~600 of our launches per iteration)."""
+    if _raw_stream is not None:
+        idx = t.device.index
+        return ctypes.c_void_p(_raw_stream(idx if idx is not None else torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+class _on_device(object):
+    """Device guard that costs nothing when the tensor already lives on the current device (the usual case)."""
+    __slots__ = ("guard",)
+
+    def __init__(self, device: torch.device) -> None:
+        idx = device.index
+        self.guard = None if (idx is None or idx == torch.cuda.current_device()) else torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            return self.guard.__exit__(*exc)
+        return False
 
 
 def _aligned(t: torch.Tensor) -> torch.Tensor:
@@ -116,7 +142,7 @@ def fused_bias_act(input: torch.Tensor, bias: torch.Tensor, refer: torch.Tensor,
         for i in range(2, x.dim()):
             step_b *= x.size(i)
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         rc = _lib.lib().msg_fused_bias_act(_ptr(out), _ptr(x), _ptr(b), _ptr(ref), int(act), int(grad),
                                            float(alpha), float(scale), x.numel(), step_b, b.numel(), dt,
                                            _stream(x))
@@ -151,7 +177,7 @@ def fused_bias_act_bwd(grad_output: torch.Tensor, out: torch.Tensor, alpha: floa
     dx = torch.empty_like(g)
     db = torch.empty(channels, dtype=g.dtype, device=g.device)
     L = _lib.lib()
-    with torch.cuda.device(g.device):
+    with _on_device(g.device):
         nbytes = L.msg_fused_bias_act_bwd_workspace(g.numel(), step_b, channels, dt)
         ws, wsp = _workspace(nbytes, g.device)
         rc = L.msg_fused_bias_act_bwd(_ptr(dx), ctypes.c_void_p(db.data_ptr()), _ptr(g), _ptr(ref), float(alpha),
@@ -184,7 +210,7 @@ def upfirdn2d(input: torch.Tensor, kernel: torch.Tensor, up_x: int, up_y: int, d
     if out_h < 0 or out_w < 0:
         raise RuntimeError("upfirdn2d: negative output size (%d, %d)" % (out_h, out_w))
     out = torch.empty((major, out_h, out_w, minor), dtype=x.dtype, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         rc = L.msg_upfirdn2d(_ptr(out), _ptr(x), _ptr(k), major, in_h, in_w, minor, kh, kw, up_x, up_y, down_x,
                              down_y, pad_x0, pad_x1, pad_y0, pad_y1, dt, _stream(x))
     _lib.check(rc, "upfirdn2d")
@@ -219,7 +245,7 @@ def blur_noise_bias_act(x: torch.Tensor, kernel: torch.Tensor, pad: Sequence[int
             raise RuntimeError("blur_noise_bias_act: noise must be [B or 1, 1, OH, OW]")
     if bias is not None:
         bias = _aligned(bias)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         rc = L.msg_upfirdn2d_bias_act(_ptr(out), _ptr(x), _ptr(k), B, H, W, C, kh, kw, px0, px1, py0, py1, _ptr(noise),
                                       _ptr(noise_w) if noise is not None else None, nbs, _ptr(bias), 1, float(slope),
                                       float(gain), _stream(x))
@@ -317,7 +343,7 @@ def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha:
             ep.add = add.data_ptr()
         keep = [bias, noise, noise_w, add]
     L = _lib.lib()
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 0, conv_flags)
         ws, wsp = _workspace(nbytes, x.device)
         rc = L.msg_conv2d_forward_fused(_ptr(y), _ptr(x), _ptr(w), ctypes.byref(d), float(alpha),
@@ -345,7 +371,7 @@ def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Sequence[int], stride
         raise RuntimeError("conv2d_dgrad: dy spatial size (%d,%d) inconsistent with input size (%d,%d)" % (OH, OW, H, W))
     dx = _empty_act((B, C, H, W), layout, dy.device)
     L = _lib.lib()
-    with torch.cuda.device(dy.device):
+    with _on_device(dy.device):
         nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 1, conv_flags)
         ws, wsp = _workspace(nbytes, dy.device)
         rc = L.msg_conv2d_dgrad(_ptr(dx), _ptr(dy), _ptr(w), ctypes.byref(d), float(alpha), wsp, nbytes,
@@ -373,7 +399,7 @@ def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, khw: Sequence[int], stride=1
     shape = (B, O, C, kh, kw) if per_sample else (O, C, kh, kw)
     dw = torch.empty(shape, dtype=torch.float32, device=x.device)
     L = _lib.lib()
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 2, conv_flags)
         ws, wsp = _workspace(nbytes, x.device)
         rc = L.msg_conv2d_wgrad(_ptr(dw), _ptr(dy), _ptr(x), ctypes.byref(d), float(alpha), wsp, nbytes,
@@ -427,7 +453,7 @@ def modulate_weights(W: torch.Tensor, s: torch.Tensor, scale: float, demodulate:
         raise RuntimeError("modulate_weights: style must be [B, C]")
     out = torch.empty((B, O, C, kh, kw), dtype=torch.float32, device=W.device)
     dm = torch.empty((B, O), dtype=torch.float32, device=W.device) if demodulate else None
-    with torch.cuda.device(W.device):
+    with _on_device(W.device):
         rc = _lib.lib().msg_modulate_weights(_ptr(out), _ptr(dm), _ptr(W), _ptr(s), B, O, C, kh * kw, float(scale),
                                              1 if demodulate else 0, _stream(W))
     _lib.check(rc, "modulate_weights")
@@ -450,7 +476,7 @@ def modulate_weights_bwd(g: torch.Tensor, W: torch.Tensor, s: torch.Tensor, demo
     dW = torch.empty_like(W)
     ds = torch.empty_like(s)
     L = _lib.lib()
-    with torch.cuda.device(W.device):
+    with _on_device(W.device):
         nbytes = L.msg_modulate_weights_bwd_workspace(B, O, C, kh * kw)
         ws, wsp = _workspace(nbytes, W.device)
         rc = L.msg_modulate_weights_bwd(_ptr(dW), _ptr(ds), _ptr(g), _ptr(W), _ptr(s), _ptr(demod) if demodulate else None,
@@ -481,7 +507,7 @@ def noise_bias_act(x: torch.Tensor, noise: Optional[torch.Tensor], noise_w: Opti
     if bias is not None:
         bias = _aligned(bias)
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         rc = _lib.lib().msg_noise_bias_act(_ptr(out), _ptr(x), _ptr(noise), _ptr(noise_w) if noise is not None else None,
                                            _ptr(bias), B, C, HW, nbs, float(alpha), float(scale), _stream(x))
     _lib.check(rc, "noise_bias_act")
@@ -526,7 +552,7 @@ def noise_bias_act_cl(x: torch.Tensor, ref: Optional[torch.Tensor], noise: Optio
         if bias.numel() != C:
             raise RuntimeError("noise_bias_act_cl: bias must have C elements")
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         rc = _lib.lib().msg_noise_bias_act_nhwc(_ptr(out), _ptr(x), _ptr(ref), _ptr(noise),
                                                 _ptr(noise_w) if noise is not None else None, _ptr(bias), rows, C,
                                                 period, float(alpha), float(scale), _stream(x))
@@ -552,7 +578,7 @@ def noise_bias_act_cl_bwd(grad_output: torch.Tensor, out: torch.Tensor, noise: O
     dx = torch.empty_like(g)
     db = torch.empty(C, dtype=torch.float32, device=g.device)
     L = _lib.lib()
-    with torch.cuda.device(g.device):
+    with _on_device(g.device):
         nbytes = L.msg_noise_bias_act_nhwc_bwd_workspace(rows, C)
         ws, wsp = _workspace(nbytes, g.device)
         rc = L.msg_noise_bias_act_nhwc_bwd(_ptr(dx), ctypes.c_void_p(db.data_ptr()),
@@ -573,7 +599,7 @@ def affine_warp(x: torch.Tensor, theta: torch.Tensor, mode: int = 0) -> torch.Te
     if theta.shape != (B, 2, 3):
         raise RuntimeError("affine_warp: theta must be [B, 2, 3]")
     out = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on_device(x.device):
         rc = _lib.lib().msg_affine_warp(_ptr(out), _ptr(x), _ptr(theta), B, C, H, W, int(mode), _stream(x))
     _lib.check(rc, "affine_warp")
     return out

@@ -172,6 +172,7 @@ static const float* const kAligned = reinterpret_cast<const float*>(256);   // p
 // A plan is computed identically by the workspace query and by the call.
 struct FwdPlan {
   bool tc, s2d, pad_in;
+  bool strided;            // stride 2 through strided phase views of x (no space-to-depth copy)
   int C4, H2, W2;
   int ay0, ax0, nay, nax;
   size_t off_x, off_w2, off_eng, total;
@@ -226,6 +227,18 @@ static FwdPlan plan_forward(const msg_conv_desc* d, const float* x, const float*
       PixGemm t = g;
       t.in = kAligned; t.Cr = 4 * pl.C4; t.IH = pl.H2; t.IW = pl.W2;
       t.is = dense_view(MSG_LAYOUT_NHWC, 4 * pl.C4, pl.H2, pl.W2);
+      // whole 32-channel chunks per input phase: read the phases x[b, 2y+py, 2x+px, :] in place through doubled strides
+      const bool strided = (d->C % 32 == 0) && al16(x) && d->H >= 2 && d->W >= 2;
+      if (strided) {
+        t.nphase = 4;
+        t.is.sb = (int64_t)d->H * d->W * d->C; t.is.sc = 1; t.is.sy = (int64_t)2 * d->W * d->C; t.is.sx = (int64_t)2 * d->C;
+        for (int ph = 0; ph < 4; ++ph) {
+          const int py = ph >> 1, px = ph & 1;
+          t.in_ph[ph] = x + ((int64_t)py * d->W + px) * d->C;
+          t.IH_ph[ph] = (d->H - py + 1) / 2; t.IW_ph[ph] = (d->W - px + 1) / 2;
+        }
+        t.in = x;
+      }
       t.my = 1; t.mx = 1;
       t.ntaps = nt;
       for (int a = 0; a < nt && a < kMaxTaps; ++a) {
@@ -234,9 +247,9 @@ static FwdPlan plan_forward(const msg_conv_desc* d, const float* x, const float*
       t.w_sn = (int64_t)4 * pl.C4 * nt; t.w_sc = nt; t.w_st = 1;
       t.w_sb = d->w_batch_stride ? (int64_t)d->O * 4 * pl.C4 * nt : 0;
       if (nt <= kMaxTaps && tc_pixgemm_supported(t)) {
-        pl.tc = true; pl.s2d = true;
+        pl.tc = true; pl.s2d = true; pl.strided = strided;
         pl.off_x = off;
-        off += r256((size_t)d->B * pl.H2 * pl.W2 * 4 * pl.C4 * sizeof(float));
+        if (!strided) off += r256((size_t)d->B * pl.H2 * pl.W2 * 4 * pl.C4 * sizeof(float));
         pl.off_w2 = off;
         const int64_t BW = d->w_batch_stride ? d->B : 1;
         off += r256((size_t)BW * d->O * 4 * pl.C4 * nt * sizeof(float));
@@ -317,6 +330,7 @@ static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float
 
 struct WgradPlan {
   bool tc, s2d, pad_g, pad_x;
+  bool strided;            // stride 2 on strided phase views of x itself (no space-to-depth copy)
   int nprob, O4, C4, H2, W2;
   RedGemm g[4];
   size_t off_g, off_x, off_eng, eng_each, total;
@@ -356,13 +370,22 @@ static WgradPlan plan_wgrad(const msg_conv_desc* d, const float* dy, const float
       }
     } else {
       pl.H2 = (d->H + 1) / 2; pl.W2 = (d->W + 1) / 2;
+      // Input phase (py, px) of a stride-2 conv is the view x[b, 2*y2 + py, 2*x2 + px, c]: TMA reads it in place through
+      // doubled strides when the channel count keeps every address 16-byte aligned; otherwise it is gathered into a
+      // space-to-depth copy first.
+      const bool strided = (d->C % 4 == 0) && al16(x);
       bool ok = true;
       RedGemm ph_g[4];
       for (int ph = 0; ph < 4 && ok; ++ph) {
         RedGemm q = t;
         const int py = ph >> 1, px = ph & 1;
         q.in = kAligned;
-        q.IH = pl.H2; q.IW = pl.W2; q.is = dense_view(MSG_LAYOUT_NHWC, 4 * pl.C4, pl.H2, pl.W2);
+        if (strided) {
+          q.IH = (d->H - py + 1) / 2; q.IW = (d->W - px + 1) / 2;
+          q.is.sb = (int64_t)d->H * d->W * d->C; q.is.sc = 1; q.is.sy = (int64_t)2 * d->W * d->C; q.is.sx = (int64_t)2 * d->C;
+        } else {
+          q.IH = pl.H2; q.IW = pl.W2; q.is = dense_view(MSG_LAYOUT_NHWC, 4 * pl.C4, pl.H2, pl.W2);
+        }
         q.my = 1; q.mx = 1;
         q.ntaps = 0;
         for (int ky = 0; ky < d->kh; ++ky) {
@@ -379,7 +402,7 @@ static WgradPlan plan_wgrad(const msg_conv_desc* d, const float* dy, const float
         if (q.ntaps > 0 && !tc_redgemm_supported(q)) ok = false;
       }
       if (ok) {
-        pl.tc = true; pl.s2d = true; pl.pad_g = pg;
+        pl.tc = true; pl.s2d = !strided; pl.strided = strided; pl.pad_g = pg;
         pl.nprob = 4;
         for (int ph = 0; ph < 4; ++ph) pl.g[ph] = ph_g[ph];
       }
@@ -451,8 +474,10 @@ extern "C" int msg_conv2d_forward_fused(float* y, const float* x, const float* w
   if (pl.s2d) {
     float* xs = reinterpret_cast<float*>(ws + pl.off_x);
     float* w2 = reinterpret_cast<float*>(ws + pl.off_w2);
-    rc = launch_s2d(xs, x, d->B, d->C, pl.C4, d->H, d->W, pl.H2, pl.W2, st);
-    if (rc) return rc;
+    if (!pl.strided) {
+      rc = launch_s2d(xs, x, d->B, d->C, pl.C4, d->H, d->W, pl.H2, pl.W2, st);
+      if (rc) return rc;
+    }
     W2Params wp{};
     wp.w = w; wp.w_sb = d->w_batch_stride; wp.BW = d->w_batch_stride ? d->B : 1; wp.N = d->O; wp.C = d->C;
     wp.C4 = pl.C4; wp.kh = d->kh; wp.kw = d->kw; wp.pad_h = d->pad_h; wp.pad_w = d->pad_w;
@@ -460,7 +485,7 @@ extern "C" int msg_conv2d_forward_fused(float* y, const float* x, const float* w
     const int64_t wtot = (int64_t)wp.BW * d->O * 4 * pl.C4 * pl.nay * pl.nax;
     s2d_weight_kernel<<<grid_for(wtot), 256, 0, st>>>(w2, wp);
     MSG_CHECK_LAUNCH("conv s2d weights");
-    pl.g.in = xs;
+    if (!pl.strided) pl.g.in = xs;
     pl.g.w = w2;
   } else if (pl.pad_in) {
     float* xp = reinterpret_cast<float*>(ws + pl.off_x);
@@ -559,7 +584,9 @@ extern "C" int msg_conv2d_wgrad(float* dw, const float* dy, const float* x, cons
     RedGemm& g = pl.g[i];
     if (g.ntaps == 0) continue;
     g.g = gp;
-    g.in = pl.s2d ? xp + (int64_t)i * pl.C4 : xp;     // phase i = channel block i of the s2d tensor
+    if (pl.s2d) g.in = xp + (int64_t)i * pl.C4;       // phase i = channel block i of the s2d tensor
+    else if (pl.strided) g.in = x + ((int64_t)(i >> 1) * d->W + (i & 1)) * d->C;   // phase i = strided view of x
+    else g.in = xp;
     rc = tc_redgemm(g, ws + pl.off_eng + i * pl.eng_each, pl.eng_each, st);
     if (rc) return rc;
   }

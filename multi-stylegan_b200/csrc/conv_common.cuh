@@ -53,6 +53,12 @@ struct PixGemm {
   View4 is;
   int B, Cr, IH, IW;
   int my, mx;             // input coordinate = pixel * m + tap_d (tcgen05 engine: 1 only)
+  // tcgen05 engine, stride-2 convolutions without a space-to-depth copy: the K dimension is nphase groups of
+  // Cr / nphase channels and group ph is read from its own strided view in_ph[ph] [B, Cr/nphase, IH_ph, IW_ph]
+  // (strides `is`) — the input phase x[b, 2*y + py, 2*x + px, c].  nphase == 0: the single view `in`.
+  int nphase;
+  const float* in_ph[4];
+  int IH_ph[4], IW_ph[4];
   const float* w;         // w(b,n,c,t) = w[b*w_sb + n*w_sn + c*w_sc + t*w_st]
   int64_t w_sb, w_sn, w_sc, w_st;
   int N;

@@ -255,8 +255,11 @@ tc_weight_transform_kernel(float* __restrict__ wt, const WtParams p) {
 // ------------------------------------------------------------------------------------------------
 // PixGemm kernel (K-major A from NHWC, K-major B)
 // ------------------------------------------------------------------------------------------------
+struct TMapSet { CUtensorMap m[4]; };   // activation views (one per stride-2 input phase; m[0] otherwise)
+
 struct TcPixParams {
   int ntaps, cchunks;
+  int chunks_per_phase;         // > 0: K chunk cc reads activation view cc / chunks_per_phase (stride-2 phases)
   int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
   int PH, PW, N;
   int wt_log2, tiles_x, tiles_y, n_tiles;   // tile = (1 << wt_log2) x (128 >> wt_log2) pixels
@@ -380,7 +383,7 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
 // accumulates tile i + 1 and the TMA warp runs ahead through the shared-memory ring.
 template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(192, 1)
-tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ CUtensorMap tmB,
                   const TcPixParams p) {
   // MT = 128-pixel sub-tiles per CTA tile: narrow-N layers (BN <= 128) take two, which halves the weight bytes and
   // TMA boxes per FLOP (one A box of 256 pixels, one B box, two MMAs per k-step sharing the B descriptor).
@@ -418,7 +421,7 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_init(acc_empty + 8 * a, 4);        // one arrival per epilogue warp
     }
     fence_barrier_init();
-    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmAs.m[0]);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1) {
@@ -447,11 +450,13 @@ tc_pixgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t ph = (it / STAGES) & 1u;
           mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u);
           const int t = k / p.cchunks;
-          const int c0 = (k - t * p.cchunks) * 32;
+          const int cc = k - t * p.cchunks;
+          int view = 0, ca = cc;
+          if (p.chunks_per_phase) { view = cc / p.chunks_per_phase; ca = cc - view * p.chunks_per_phase; }
           const uint32_t full = bars + 8 * s;
           mbar_expect_tx(full, A_BYTES + B_BYTES);
-          tma_load_4d(sA + s * A_BYTES, &tmA, full, c0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b);
-          tma_load_4d(sB + s * B_BYTES, &tmB, full, c0, n0, t, bw);
+          tma_load_4d(sA + s * A_BYTES, &tmAs.m[view], full, ca * 32, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b);
+          tma_load_4d(sB + s * B_BYTES, &tmB, full, cc * 32, n0, t, bw);
         }
       }
     }
@@ -872,6 +877,12 @@ bool tc_pixgemm_supported(const PixGemm& g) {
   if (g.ntaps <= 0 || g.ntaps > kMaxTaps || g.Cr <= 0 || g.N <= 0 || g.B <= 0 || g.B > 65535) return false;
   if (g.my != 1 || g.mx != 1) return false;
   if (g.PW < 1 || g.PH < 1) return false;
+  if (g.nphase != 0) {
+    if (g.nphase != 4 || g.Cr % (32 * 4) != 0) return false;
+    for (int v = 0; v < 4; ++v)
+      if (!view_tma_ok(g.in_ph[v], g.is) || g.IH_ph[v] < 1 || g.IW_ph[v] < 1) return false;
+    return true;
+  }
   if (!view_tma_ok(g.in, g.is)) return false;
   return true;
 }
@@ -884,7 +895,7 @@ size_t tc_pixgemm_workspace(const PixGemm& g) {
 }
 
 template <int BN, int MT>
-static int launch_pix(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPixParams& p, cudaStream_t st) {
+static int launch_pix(const TMapSet& tmA, const CUtensorMap& tmB, const TcPixParams& p, cudaStream_t st) {
   constexpr int STAGES = (BN == 256 || MT == 2) ? 4 : 6;
   constexpr size_t smem = (size_t)STAGES * (MT * 16384 + BN * 128) + 4 * 32 * 33 * 4 + 16 * STAGES + 64 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
@@ -975,14 +986,23 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   // Measured on B200 (tools/conv_bench.py): no gain over the single-CTA kernel at 256^2 (3.07 vs 3.13 ms — that kernel
   // already runs at the MMA issue rate the power-capped clock allows) and a loss at <= 128^2 (coarser tiles), so the pair
   // kernel is opt-in: MSG_B200_TC_VARIANT=4.
-  const bool pairs = BN == 256 && MT == 1 && (tc_variant() & 4u) && pair_tiles >= num_sms() / 2;
-  CUtensorMap tmA, tmB;
-  {
-    const uint64_t dims[4] = {(uint64_t)g.Cr, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
+  const bool pairs = BN == 256 && MT == 1 && (tc_variant() & 4u) && pair_tiles >= num_sms() / 2 && g.nphase == 0;
+  TMapSet tmA;
+  CUtensorMap tmB;
+  const int nviews = g.nphase > 0 ? g.nphase : 1;
+  for (int v = 0; v < 4; ++v) {
+    const int vv = v < nviews ? v : 0;
+    const float* basep = g.nphase > 0 ? g.in_ph[vv] : g.in;
+    const int ih = g.nphase > 0 ? g.IH_ph[vv] : g.IH, iw = g.nphase > 0 ? g.IW_ph[vv] : g.IW;
+    const uint64_t dims[4] = {(uint64_t)(g.Cr / nviews), (uint64_t)iw, (uint64_t)ih, (uint64_t)g.B};
     const uint64_t strides[3] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4};
     const uint32_t box[4] = {32, (uint32_t)Wt, (uint32_t)Ht, 1};
-    int rc = make_tmap(&tmA, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (rc) return rc;
+    if (v < nviews) {
+      int rc = make_tmap(&tmA.m[v], basep, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (rc) return rc;
+    } else {
+      tmA.m[v] = tmA.m[0];
+    }
   }
   {
     const uint64_t dims[4] = {(uint64_t)Cpad, (uint64_t)Npad, (uint64_t)g.ntaps, (uint64_t)BW};
@@ -993,6 +1013,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   }
   TcPixParams p{};
   p.ntaps = g.ntaps; p.cchunks = Cpad / 32;
+  p.chunks_per_phase = g.nphase > 0 ? (g.Cr / g.nphase) / 32 : 0;
   for (int t = 0; t < g.ntaps; ++t) { p.tap_dy[t] = g.tap_dy[t]; p.tap_dx[t] = g.tap_dx[t]; }
   p.PH = g.PH; p.PW = g.PW; p.N = g.N;
   p.wt_log2 = wt_log2;
@@ -1015,7 +1036,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);
   int rc;
   if (pairs) {
-    rc = launch_pix2(tmA, tmB, p, st);
+    rc = launch_pix2(tmA.m[0], tmB, p, st);
   } else if (MT == 2) {
     switch (BN) {
       case 128: rc = launch_pix<128, 2>(tmA, tmB, p, st); break;
