@@ -236,6 +236,10 @@ int msg_noise_bias_act_nhwc_bwd(float* dx, float* dbias, float* dnoise_w, const 
  * ------------------------------------------------------------------------------------------- */
 int msg_affine_warp(float* out, const float* in, const float* theta, int B, int C, int H, int W,
                     int mode, msg_stream_t stream);
+/* Gradient of the warp w.r.t. its input image (the generator step differentiates through the augmentation like the
+ * reference's kornia warps do): dx = A^T g with the same bilinear weights, scattered with fp32 atomics. */
+int msg_affine_warp_bwd(float* dx, const float* g, const float* theta, int B, int C, int H, int W,
+                        int mode, msg_stream_t stream);
 
 #ifdef __cplusplus
 }

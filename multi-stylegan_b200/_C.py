@@ -603,3 +603,19 @@ def affine_warp(x: torch.Tensor, theta: torch.Tensor, mode: int = 0) -> torch.Te
         rc = _lib.lib().msg_affine_warp(_ptr(out), _ptr(x), _ptr(theta), B, C, H, W, int(mode), _stream(x))
     _lib.check(rc, "affine_warp")
     return out
+
+
+def affine_warp_bwd(grad_output: torch.Tensor, theta: torch.Tensor, mode: int = 0) -> torch.Tensor:
+    """Gradient of affine_warp w.r.t. its input image."""
+    _check_f32(grad_output, "grad_output")
+    _check_f32(theta, "theta")
+    g = _aligned(grad_output)
+    theta = _aligned(theta)
+    B, C, H, W = g.shape
+    if theta.shape != (B, 2, 3):
+        raise RuntimeError("affine_warp_bwd: theta must be [B, 2, 3]")
+    dx = torch.empty_like(g)
+    with _on_device(g.device):
+        rc = _lib.lib().msg_affine_warp_bwd(_ptr(dx), _ptr(g), _ptr(theta), B, C, H, W, int(mode), _stream(g))
+    _lib.check(rc, "affine_warp_bwd")
+    return dx

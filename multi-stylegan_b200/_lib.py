@@ -115,6 +115,8 @@ _SIGNATURES = {
                                                _c.c_size_t, _c.c_void_p]),
     "msg_affine_warp": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                    _c.c_int, _c.c_void_p]),
+    "msg_affine_warp_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
+                                       _c.c_int, _c.c_void_p]),
 }
 
 

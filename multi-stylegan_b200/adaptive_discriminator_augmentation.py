@@ -23,6 +23,40 @@ import torch.nn as nn
 from . import _C
 
 
+class _AffineWarpBackward(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, grad_output, theta, mode):
+        ctx.save_for_backward(theta)
+        ctx.mode = mode
+        return _C.affine_warp_bwd(grad_output, theta, mode)
+
+    @staticmethod
+    def backward(ctx, gg):
+        theta, = ctx.saved_tensors
+        return _AffineWarp.apply(gg, theta, ctx.mode), None, None
+
+
+class _AffineWarp(torch.autograd.Function):
+    """Bilinear warp (csrc/misc_ops.cu), differentiable w.r.t. the image: the generator step back-propagates through
+    the augmentation exactly as it does through the reference's kornia warps (:133,:152,:168,:187).  The warp is linear
+    in the image, so its backward is the adjoint kernel and the backward of that is the warp again."""
+
+    @staticmethod
+    def forward(ctx, images, theta, mode):
+        ctx.save_for_backward(theta)
+        ctx.mode = mode
+        return _C.affine_warp(images, theta, mode)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        theta, = ctx.saved_tensors
+        return _AffineWarpBackward.apply(grad_output, theta, ctx.mode), None, None
+
+
+def affine_warp(images: torch.Tensor, theta: torch.Tensor, mode: int = 0) -> torch.Tensor:
+    return _AffineWarp.apply(images, theta, mode)
+
+
 def _select(gate: torch.Tensor) -> List[int]:
     return [i for i, v in enumerate(gate.tolist()) if v]
 
@@ -78,7 +112,7 @@ class AugmentationPipeline(nn.Module):
             ang = float(d["rot90_angle"])
             th = affine_inverse_theta(len(d["rot90"]), list(range(len(d["rot90"]))), [-ang] * len(d["rot90"]),
                                       [(1., 1.)] * len(d["rot90"]), ((W - 1) / 2, (H - 1) / 2))
-            images[d["rot90"]] = _C.affine_warp(images[d["rot90"]], th.to(images.device), mode=1)
+            images[d["rot90"]] = affine_warp(images[d["rot90"]], th.to(images.device), mode=1)
         if d["roll"]:
             shift = (int(H * d["roll_frac"][0]), int(W * d["roll_frac"][1]))
             images[d["roll"]] = torch.roll(images[d["roll"]], shifts=shift, dims=(-2, -1))
@@ -90,7 +124,7 @@ class AugmentationPipeline(nn.Module):
         for idx, angles, scales in stages:
             if idx:
                 theta = affine_inverse_theta(B, idx, angles, scales, centre).to(images.device)
-                images = _C.affine_warp(images, theta, mode=0)
+                images = affine_warp(images, theta, mode=0)
         return images
 
 

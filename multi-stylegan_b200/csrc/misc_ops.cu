@@ -180,6 +180,36 @@ affine_warp_kernel(float* __restrict__ out, const float* __restrict__ in, const 
   }
 }
 
+// Adjoint of the warp (the gradient w.r.t. the warped image; theta is a constant): every output pixel scatters its
+// gradient to the four source pixels with the same bilinear weights.  fp32 atomics (12.6 MB tensors: not a hot spot).
+__global__ void __launch_bounds__(128)
+affine_warp_bwd_kernel(float* __restrict__ dx, const float* __restrict__ g, const float* __restrict__ theta, int C,
+                       int H, int W, int mode) {
+  const int b = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= W) return;
+  const float* th = theta + b * 6;
+  float sx = th[0] * x + th[1] * y + th[2];
+  float sy = th[3] * x + th[4] * y + th[5];
+  if (mode == 0) { sx = reflect_coord(sx, W); sy = reflect_coord(sy, H); }
+  const float fx = floorf(sx), fy = floorf(sy);
+  const int x0 = (int)fx, y0 = (int)fy, x1 = x0 + 1, y1 = y0 + 1;
+  const float wx1 = sx - fx, wy1 = sy - fy, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+  const bool vx0 = x0 >= 0 && x0 < W, vx1 = x1 >= 0 && x1 < W, vy0 = y0 >= 0 && y0 < H, vy1 = y1 >= 0 && y1 < H;
+  const int64_t plane = (int64_t)H * W;
+  float* dp = dx + (int64_t)b * C * plane;
+  const float* gp = g + (int64_t)b * C * plane + (int64_t)y * W + x;
+  for (int c = 0; c < C; ++c) {
+    const float gv = gp[c * plane];
+    float* p = dp + c * plane;
+    if (vy0 && vx0) atomicAdd(p + (int64_t)y0 * W + x0, gv * (wy0 * wx0));
+    if (vy0 && vx1) atomicAdd(p + (int64_t)y0 * W + x1, gv * (wy0 * wx1));
+    if (vy1 && vx0) atomicAdd(p + (int64_t)y1 * W + x0, gv * (wy1 * wx0));
+    if (vy1 && vx1) atomicAdd(p + (int64_t)y1 * W + x1, gv * (wy1 * wx1));
+  }
+}
+
 }  // namespace msg
 
 using namespace msg;
@@ -272,5 +302,21 @@ extern "C" int msg_affine_warp(float* out, const float* in, const float* theta, 
   dim3 grid((unsigned)ceil_div(W, 128), (unsigned)H, (unsigned)B);
   affine_warp_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(out, in, theta, C, H, W, mode);
   MSG_CHECK_LAUNCH("affine_warp");
+  return MSG_OK;
+}
+
+extern "C" int msg_affine_warp_bwd(float* dx, const float* g, const float* theta, int B, int C, int H, int W, int mode,
+                                   msg_stream_t stream) {
+  if (B < 0 || C <= 0 || H <= 0 || W <= 0) return fail(MSG_ERR_BAD_ARG, "affine_warp_bwd: bad sizes");
+  if (mode != 0 && mode != 1) return fail(MSG_ERR_BAD_ARG, "affine_warp_bwd: mode must be 0 (reflection) or 1 (zeros)");
+  if (B == 0) return MSG_OK;
+  if (!dx || !g || !theta) return fail(MSG_ERR_BAD_ARG, "affine_warp_bwd: null pointer");
+  if (dx == g) return fail(MSG_ERR_BAD_ARG, "affine_warp_bwd: in-place not supported");
+  if (B > 65535 || H > 65535) return fail(MSG_ERR_UNSUPPORTED, "affine_warp_bwd: B or H > 65535");
+  cudaStream_t st = (cudaStream_t)stream;
+  MSG_CHECK_CUDA(cudaMemsetAsync(dx, 0, (size_t)B * C * H * W * sizeof(float), st));
+  dim3 grid((unsigned)ceil_div(W, 128), (unsigned)H, (unsigned)B);
+  affine_warp_bwd_kernel<<<grid, 128, 0, st>>>(dx, g, theta, C, H, W, mode);
+  MSG_CHECK_LAUNCH("affine_warp_bwd");
   return MSG_OK;
 }

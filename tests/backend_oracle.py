@@ -5,7 +5,7 @@ import torch
 from oracle import ops
 
 __all__ = ["fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_forward", "conv2d_dgrad", "conv2d_wgrad",
-           "modulate_weights", "noise_bias_act", "affine_warp", "noise_bias_act_cl", "noise_bias_act_cl_bwd", "modulate_weights_bwd", "blur_noise_bias_act"]
+           "modulate_weights", "noise_bias_act", "affine_warp", "noise_bias_act_cl", "noise_bias_act_cl_bwd", "modulate_weights_bwd", "blur_noise_bias_act", "affine_warp_bwd"]
 
 
 def fused_bias_act(input, bias, refer, act, grad, alpha, scale):
@@ -82,3 +82,10 @@ def blur_noise_bias_act(x, kernel, pad, noise, noise_w, bias, slope, gain):
     y = ops.upfirdn2d(x.reshape(-1, H, W, 1), kernel, 1, 1, 1, 1, px0, px1, py0, py1)
     y = y.view(B, C, y.shape[1], y.shape[2])
     return ops.noise_bias_act_masked(y, None, noise, noise_w, bias, slope, gain)
+
+
+def affine_warp_bwd(grad_output, theta, mode=0):
+    x = torch.zeros_like(grad_output, requires_grad=True)
+    with torch.enable_grad():
+        y = ops.affine_warp(x, theta, mode)
+        return torch.autograd.grad(y, x, grad_output)[0]
