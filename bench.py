@@ -152,8 +152,7 @@ def run_ours(args):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version there)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line, NCCL's banner goes to stderr
     _lib.lib()
     local_rank = mdist.init_from_env()
     world, rank = mdist.world_size(), mdist.rank()
