@@ -125,16 +125,28 @@ class NonLocalBlock(nn.Module):
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
         batch_size, _, height, width = input.shape
-        theta = self.theta(input).flatten(start_dim=2)                                   # [B, C/8, HW]
-        phi = F.max_pool2d(self.phi(input), kernel_size=(2, 2), stride=(2, 2)).flatten(start_dim=2)
-        g = F.max_pool2d(self.g(input), kernel_size=(2, 2), stride=(2, 2)).flatten(start_dim=2)
-        # The 4096 x 1024 attention stays on the library bmm like the reference (:370-380).  The reference's pinned
-        # PyTorch 1.8.1 runs CUDA matmuls with TF32 enabled by default; request the same here instead of the fp32
-        # CUDA-core sgemm newer PyTorch versions fall back to.
+
+        def rows(t: torch.Tensor) -> torch.Tensor:
+            """[B, C, h, w] -> [B, h*w, C]: a free view of a channels-last activation (its memory order)."""
+            return t.permute(0, 2, 3, 1).reshape(t.shape[0], t.shape[2] * t.shape[3], t.shape[1])
+        theta = rows(self.theta(input))                                                   # [B, HW, C/8]   = theta^T
+        phi = rows(F.max_pool2d(self.phi(input), kernel_size=(2, 2), stride=(2, 2)))      # [B, HW/4, C/8] = phi^T
+        g = rows(F.max_pool2d(self.g(input), kernel_size=(2, 2), stride=(2, 2)))          # [B, HW/4, C/2] = g^T
+        # The 4096 x 1024 attention stays on the library bmm like the reference (:370-380), written on the transposed
+        # operands so that no layout copy is needed: beta = softmax(theta^T phi), (g beta^T)^T = beta g^T, and
+        # [B, HW, C/2] is already the channels-last image of the result.  The reference's pinned PyTorch 1.8.1 runs CUDA
+        # matmuls with TF32 enabled by default; request the same here instead of the fp32 CUDA-core sgemm newer
+        # PyTorch versions fall back to.
         with _tf32_matmul():
-            beta = F.softmax(torch.bmm(theta.transpose(1, 2), phi), -1)                   # [B, HW, HW/4]
-            attended = torch.bmm(g, beta.transpose(1, 2))
-        output = self.o(attended.view(batch_size, -1, height, width))
+            beta = F.softmax(torch.bmm(theta, phi.transpose(1, 2)), -1)                   # [B, HW, HW/4]
+            attended = torch.bmm(beta, g)                                                 # [B, HW, C/2]
+        attended = attended.view(batch_size, height, width, -1).permute(0, 3, 1, 2)       # [B, C/2, H, W] channels-last
+        output = self.o(attended)
+        res = self.residual_mapping
+        if isinstance(res, equalized_layer.EqualizedConv2d) and res.bias is None:
+            # (gamma * o + conv1x1(x)) / sqrt(2) with the join in the residual conv's epilogue (:381)
+            return conv.conv2d_add_scale(input, res.weight, self.gamma * output, stride=res.stride, padding=res.padding,
+                                         gain=1.0 / math.sqrt(2), alpha=res.scale)
         return (self.gamma * output + self.residual_mapping(input)) / math.sqrt(2)
 
 
