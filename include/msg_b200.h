@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define MSG_B200_ABI_VERSION 1
+#define MSG_B200_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -144,6 +144,8 @@ typedef struct {
   int OH, OW;              /* output activation extent (must match the formula)  */
   int64_t w_batch_stride;  /* 0 = shared weights, else elements between samples  */
   int layout;              /* memory layout of x, y, dx, dy: MSG_LAYOUT_*        */
+  int w_transposed;        /* 0: filters [O, C, kh, kw]; 1: [C, O, kh, kw] — the layout of conv_transpose2d's weight
+                              (multi_stylegan_generator.py:393-398), read / written in place by all three kernels */
 } msg_conv_desc;
 
 enum {

@@ -263,7 +263,7 @@ def _pair(v) -> Tuple[int, int]:
     return int(v), int(v)
 
 
-def _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout) -> ConvDesc:
+def _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout, w_transposed=False) -> ConvDesc:
     sh, sw = _pair(stride)
     ph, pw = _pair(padding)
     if H + 2 * ph < kh or W + 2 * pw < kw:
@@ -275,6 +275,7 @@ def _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout) -> Co
     d.OW = (W + 2 * pw - kw) // sw + 1
     d.w_batch_stride = O * C * kh * kw if per_sample else 0
     d.layout = layout
+    d.w_transposed = 1 if w_transposed else 0
     return d
 
 
@@ -284,20 +285,24 @@ def _check_f32(t: torch.Tensor, name: str) -> None:
         raise RuntimeError("conv2d: %s must be float32, got %s" % (name, t.dtype))
 
 
-def _w_dims(w: torch.Tensor, B: int):
+def _w_dims(w: torch.Tensor, B: int, w_transposed: bool = False):
+    """(per_sample, O, C, kh, kw) of a filter tensor [O,C,kh,kw] / [B,O,C,kh,kw]; with w_transposed the two channel
+    dimensions are stored the other way round ([C,O,kh,kw]: conv_transpose2d's weight layout)."""
     if w.dim() == 5:
         if w.size(0) != B:
             raise RuntimeError("conv2d: per-sample weight batch %d != input batch %d" % (w.size(0), B))
-        return True, w.size(1), w.size(2), w.size(3), w.size(4)
+        a, b = w.size(1), w.size(2)
+        return (True, b, a, w.size(3), w.size(4)) if w_transposed else (True, a, b, w.size(3), w.size(4))
     if w.dim() == 4:
-        return False, w.size(0), w.size(1), w.size(2), w.size(3)
+        a, b = w.size(0), w.size(1)
+        return (False, b, a, w.size(2), w.size(3)) if w_transposed else (False, a, b, w.size(2), w.size(3))
     raise RuntimeError("conv2d: weight must be [O,C,kh,kw] or [B,O,C,kh,kw]")
 
 
 def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha: float = 1.0,
                    bias: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                    noise_w: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None, act: bool = False,
-                   slope: float = 0.2, gain: float = 1.0) -> torch.Tensor:
+                   slope: float = 0.2, gain: float = 1.0, w_transposed: bool = False) -> torch.Tensor:
     """y = epilogue(alpha * conv(x, w)); the optional epilogue (noise, bias, leaky ReLU, residual add, gain) runs
     inside the conv kernel (msg_conv_epilogue, include/msg_b200.h)."""
     _check_f32(x, "x")
@@ -305,10 +310,10 @@ def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha:
     x, layout = _act(x)
     w = _aligned(w)
     B, C, H, W = x.shape
-    per_sample, O, Cw, kh, kw = _w_dims(w, B)
+    per_sample, O, Cw, kh, kw = _w_dims(w, B, w_transposed)
     if Cw != C:
         raise RuntimeError("conv2d: weight has %d input channels, input has %d" % (Cw, C))
-    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout)
+    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout, w_transposed)
     y = _empty_act((B, O, d.OH, d.OW), layout, x.device)
     fused = bias is not None or noise is not None or add is not None or act or gain != 1.0
     ep = None
@@ -355,18 +360,18 @@ def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha:
 
 
 def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Sequence[int], stride=1, padding=0,
-                 alpha: float = 1.0) -> torch.Tensor:
+                 alpha: float = 1.0, w_transposed: bool = False) -> torch.Tensor:
     """dx of conv2d(x, w) given dy; also conv_transpose2d(dy, w) with output size in_hw."""
     _check_f32(dy, "dy")
     _check_f32(w, "w")
     dy, layout = _act(dy)
     w = _aligned(w)
     B, O, OH, OW = dy.shape
-    per_sample, Ow, C, kh, kw = _w_dims(w, B)
+    per_sample, Ow, C, kh, kw = _w_dims(w, B, w_transposed)
     if Ow != O:
         raise RuntimeError("conv2d_dgrad: weight has %d output channels, dy has %d" % (Ow, O))
     H, W = int(in_hw[0]), int(in_hw[1])
-    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout)
+    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout, w_transposed)
     if (d.OH, d.OW) != (OH, OW):
         raise RuntimeError("conv2d_dgrad: dy spatial size (%d,%d) inconsistent with input size (%d,%d)" % (OH, OW, H, W))
     dx = _empty_act((B, C, H, W), layout, dy.device)
@@ -381,7 +386,7 @@ def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Sequence[int], stride
 
 
 def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, khw: Sequence[int], stride=1, padding=0,
-                 per_sample: bool = False, alpha: float = 1.0) -> torch.Tensor:
+                 per_sample: bool = False, alpha: float = 1.0, w_transposed: bool = False) -> torch.Tensor:
     _check_f32(dy, "dy")
     _check_f32(x, "x")
     x, layout = _act(x)
@@ -393,10 +398,11 @@ def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, khw: Sequence[int], stride=1
         raise RuntimeError("conv2d_wgrad: batch mismatch")
     O = dy.size(1)
     kh, kw = int(khw[0]), int(khw[1])
-    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout)
+    d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout, w_transposed)
     if (d.OH, d.OW) != (dy.size(2), dy.size(3)):
         raise RuntimeError("conv2d_wgrad: dy spatial size inconsistent with x")
-    shape = (B, O, C, kh, kw) if per_sample else (O, C, kh, kw)
+    oc = (C, O) if w_transposed else (O, C)
+    shape = (B,) + oc + (kh, kw) if per_sample else oc + (kh, kw)
     dw = torch.empty(shape, dtype=torch.float32, device=x.device)
     L = _lib.lib()
     with _on_device(x.device):

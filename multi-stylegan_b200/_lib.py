@@ -27,7 +27,7 @@ class ConvDesc(ctypes.Structure):
                 ("stride_h", ctypes.c_int), ("stride_w", ctypes.c_int),
                 ("pad_h", ctypes.c_int), ("pad_w", ctypes.c_int),
                 ("OH", ctypes.c_int), ("OW", ctypes.c_int),
-                ("w_batch_stride", ctypes.c_int64), ("layout", ctypes.c_int)]
+                ("w_batch_stride", ctypes.c_int64), ("layout", ctypes.c_int), ("w_transposed", ctypes.c_int)]
 
 
 class ConvEpilogue(ctypes.Structure):

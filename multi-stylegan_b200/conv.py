@@ -20,12 +20,19 @@ def _pair(v) -> Tuple[int, int]:
     return (int(v[0]), int(v[1])) if isinstance(v, (tuple, list)) else (int(v), int(v))
 
 
+def _khw(w: torch.Tensor):
+    return tuple(w.shape[-2:])
+
+
 class _ConvForward(Function):
+    """`wt`: the filter tensor stores its two channel dimensions transposed ([C, O, kh, kw], the layout of
+    conv_transpose2d's weight); every kernel reads / writes that layout in place."""
+
     @staticmethod
-    def forward(ctx, x, w, stride, padding, alpha):
+    def forward(ctx, x, w, stride, padding, alpha, wt=False):
         ctx.save_for_backward(x, w)
-        ctx.stride, ctx.padding, ctx.alpha = stride, padding, alpha
-        return _C.conv2d_forward(x, w, stride, padding, alpha=alpha)
+        ctx.stride, ctx.padding, ctx.alpha, ctx.wt = stride, padding, alpha, wt
+        return _C.conv2d_forward(x, w, stride, padding, alpha=alpha, w_transposed=wt)
 
     @staticmethod
     def backward(ctx, dy):
@@ -35,48 +42,48 @@ class _ConvForward(Function):
             # a channel slice of a concatenation's gradient is a strided view: densify it once for both kernels
             dy = dy.contiguous(memory_format=torch.channels_last)
         if ctx.needs_input_grad[0]:
-            dx = _ConvDgrad.apply(dy, w, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
+            dx = _ConvDgrad.apply(dy, w, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha, ctx.wt)
         if ctx.needs_input_grad[1]:
-            dw = _ConvWgrad.apply(dy, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha)
-        return dx, dw, None, None, None
+            dw = _ConvWgrad.apply(dy, x, _khw(w), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha, ctx.wt)
+        return dx, dw, None, None, None, None
 
 
 class _ConvDgrad(Function):
     """dx = alpha * conv^T(dy, w); as a function of (dy, w) it is the transposed convolution."""
 
     @staticmethod
-    def forward(ctx, dy, w, in_hw, stride, padding, alpha):
+    def forward(ctx, dy, w, in_hw, stride, padding, alpha, wt=False):
         ctx.save_for_backward(dy, w)
-        ctx.in_hw, ctx.stride, ctx.padding, ctx.alpha = in_hw, stride, padding, alpha
-        return _C.conv2d_dgrad(dy, w, in_hw, stride, padding, alpha=alpha)
+        ctx.in_hw, ctx.stride, ctx.padding, ctx.alpha, ctx.wt = in_hw, stride, padding, alpha, wt
+        return _C.conv2d_dgrad(dy, w, in_hw, stride, padding, alpha=alpha, w_transposed=wt)
 
     @staticmethod
     def backward(ctx, ddx):
         dy, w = ctx.saved_tensors
         g_dy = g_w = None
         if ctx.needs_input_grad[0]:
-            g_dy = _ConvForward.apply(ddx, w, ctx.stride, ctx.padding, ctx.alpha)
+            g_dy = _ConvForward.apply(ddx, w, ctx.stride, ctx.padding, ctx.alpha, ctx.wt)
         if ctx.needs_input_grad[1]:
-            g_w = _ConvWgrad.apply(dy, ddx, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha)
-        return g_dy, g_w, None, None, None, None
+            g_w = _ConvWgrad.apply(dy, ddx, _khw(w), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha, ctx.wt)
+        return g_dy, g_w, None, None, None, None, None
 
 
 class _ConvWgrad(Function):
     @staticmethod
-    def forward(ctx, dy, x, khw, stride, padding, per_sample, alpha):
+    def forward(ctx, dy, x, khw, stride, padding, per_sample, alpha, wt=False):
         ctx.save_for_backward(dy, x)
-        ctx.stride, ctx.padding, ctx.alpha = stride, padding, alpha
-        return _C.conv2d_wgrad(dy, x, khw, stride, padding, per_sample, alpha=alpha)
+        ctx.stride, ctx.padding, ctx.alpha, ctx.wt = stride, padding, alpha, wt
+        return _C.conv2d_wgrad(dy, x, khw, stride, padding, per_sample, alpha=alpha, w_transposed=wt)
 
     @staticmethod
     def backward(ctx, ddw):
         dy, x = ctx.saved_tensors
         g_dy = g_x = None
         if ctx.needs_input_grad[0]:
-            g_dy = _ConvForward.apply(x, ddw, ctx.stride, ctx.padding, ctx.alpha)
+            g_dy = _ConvForward.apply(x, ddw, ctx.stride, ctx.padding, ctx.alpha, ctx.wt)
         if ctx.needs_input_grad[1]:
-            g_x = _ConvDgrad.apply(dy, ddw, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
-        return g_dy, g_x, None, None, None, None, None
+            g_x = _ConvDgrad.apply(dy, ddw, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha, ctx.wt)
+        return g_dy, g_x, None, None, None, None, None, None
 
 
 class _ConvBiasAct(Function):
@@ -149,11 +156,13 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha: float =
     return _ConvForward.apply(x, w, _pair(stride), _pair(padding), float(alpha))
 
 
-def conv_transpose2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0) -> torch.Tensor:
-    """x [B,Cin,H,W]; w [Cin,Cout,kh,kw] or [B,Cin,Cout,kh,kw] (torch's conv_transpose2d weight layout,
-    which is the layout of the conv whose input-gradient this is).  output_padding = 0."""
+def conv_transpose2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, weight_is_conv_layout: bool = False) -> torch.Tensor:
+    """x [B,Cin,H,W]; w [Cin,Cout,kh,kw] or [B,Cin,Cout,kh,kw] (torch's conv_transpose2d weight layout, which is the
+    layout of the conv whose input-gradient this is).  With weight_is_conv_layout the filters come as
+    [(B,) Cout, Cin, kh, kw] (the generator's modulated banks, :384-398) and are read in place instead of being
+    transposed and copied.  output_padding = 0."""
     sh, sw = _pair(stride)
     ph, pw = _pair(padding)
     kh, kw = w.shape[-2:]
     out_hw = ((x.shape[2] - 1) * sh - 2 * ph + kh, (x.shape[3] - 1) * sw - 2 * pw + kw)
-    return _ConvDgrad.apply(x, w, out_hw, (sh, sw), (ph, pw), 1.0)
+    return _ConvDgrad.apply(x, w, out_hw, (sh, sw), (ph, pw), 1.0, bool(weight_is_conv_layout))

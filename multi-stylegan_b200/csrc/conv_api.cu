@@ -103,6 +103,7 @@ chanpad_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t p
 struct W2Params {
   const float* w;
   int64_t w_sb;     // 0 or O*C*kh*kw
+  int64_t w_sn, w_sc;   // element strides of the output- / input-channel index (weight stored [O,C,..] or [C,O,..])
   int BW, N, C, C4, kh, kw, pad_h, pad_w;
   int ay0, ax0, nay, nax;
 };
@@ -123,7 +124,7 @@ s2d_weight_kernel(float* __restrict__ w2, const W2Params p) {
     const int ky = 2 * ay + (ph >> 1) + p.pad_h, kx = 2 * ax + (ph & 1) + p.pad_w;
     float v = 0.f;
     if (c < p.C && ky >= 0 && ky < p.kh && kx >= 0 && kx < p.kw)
-      v = __ldg(p.w + bw * p.w_sb + (((int64_t)n * p.C + c) * p.kh + ky) * p.kw + kx);
+      v = __ldg(p.w + bw * p.w_sb + (int64_t)n * p.w_sn + (int64_t)c * p.w_sc + ky * p.kw + kx);
     w2[i] = v;
   }
 }
@@ -145,6 +146,7 @@ static int check_desc(const msg_conv_desc* d, const char* who) {
   if (d->kh * d->kw > kMaxTaps) return fail(MSG_ERR_UNSUPPORTED, "%s: filter larger than %d taps", who, kMaxTaps);
   if (d->layout != MSG_LAYOUT_NCHW && d->layout != MSG_LAYOUT_NHWC)
     return fail(MSG_ERR_BAD_ARG, "%s: unknown layout %d", who, d->layout);
+  if (d->w_transposed != 0 && d->w_transposed != 1) return fail(MSG_ERR_BAD_ARG, "%s: w_transposed must be 0 or 1", who);
   const int oh = (d->H + 2 * d->pad_h - d->kh) / d->stride_h + 1;
   const int ow = (d->W + 2 * d->pad_w - d->kw) / d->stride_w + 1;
   if (d->H + 2 * d->pad_h < d->kh || d->W + 2 * d->pad_w < d->kw || oh != d->OH || ow != d->OW)
@@ -154,6 +156,11 @@ static int check_desc(const msg_conv_desc* d, const char* who) {
     return fail(MSG_ERR_BAD_ARG, "%s: w_batch_stride must be 0 or O*C*kh*kw", who);
   return MSG_OK;
 }
+
+// element strides of (output channel o, input channel c) in the filter tensor: [O,C,kh,kw] or, with
+// w_transposed, [C,O,kh,kw] (the layout torch's conv_transpose2d uses and the generator's up-conv hands over)
+static inline int64_t w_stride_o(const msg_conv_desc* d) { return d->w_transposed ? (int64_t)d->kh * d->kw : (int64_t)d->C * d->kh * d->kw; }
+static inline int64_t w_stride_c(const msg_conv_desc* d) { return d->w_transposed ? (int64_t)d->O * d->kh * d->kw : (int64_t)d->kh * d->kw; }
 
 static inline bool want_tc(const msg_conv_desc* d, int flags) {
   return flags != MSG_CONV_FORCE_SIMT && d->layout == MSG_LAYOUT_NHWC && tc_available();
@@ -196,7 +203,7 @@ static FwdPlan plan_forward(const msg_conv_desc* d, const float* x, const float*
   }
   g.in = x; g.Cr = d->C; g.IH = d->H; g.IW = d->W; g.is = dense_view(d->layout, d->C, d->H, d->W);
   g.my = s; g.mx = s;
-  g.w = w; g.w_sb = d->w_batch_stride; g.w_sn = d->C * taps; g.w_sc = taps; g.w_st = 1;
+  g.w = w; g.w_sb = d->w_batch_stride; g.w_sn = w_stride_o(d); g.w_sc = w_stride_c(d); g.w_st = 1;
   g.ntaps = (int)taps;
   for (int ky = 0; ky < d->kh; ++ky)
     for (int kx = 0; kx < d->kw; ++kx) {
@@ -288,7 +295,7 @@ static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float
     g.B = d->B; g.N = d->C; g.Cr = d->O;
     g.in = dy; g.IH = d->OH; g.IW = d->OW; g.is = dense_view(d->layout, d->O, d->OH, d->OW);
     g.my = 1; g.mx = 1;
-    g.w = w; g.w_sb = d->w_batch_stride; g.w_sn = taps; g.w_sc = d->C * taps; g.w_st = 1;
+    g.w = w; g.w_sb = d->w_batch_stride; g.w_sn = w_stride_c(d); g.w_sc = w_stride_o(d); g.w_st = 1;
     g.PH = (d->H - py + s - 1) / s; g.PW = (d->W - px + s - 1) / s;
     g.out = dx; g.os = dense_view(d->layout, d->C, d->H, d->W);
     g.out_my = s; g.out_mx = s; g.out_oy = py; g.out_ox = px; g.alpha = alpha;
@@ -346,7 +353,7 @@ static WgradPlan plan_wgrad(const msg_conv_desc* d, const float* dy, const float
   base.gs = dense_view(d->layout, d->O, d->OH, d->OW);
   base.in = x; base.C = d->C; base.IH = d->H; base.IW = d->W; base.is = dense_view(d->layout, d->C, d->H, d->W);
   base.my = s; base.mx = s;
-  base.dw = dw; base.dw_sb = d->w_batch_stride; base.dw_sn = d->C * taps; base.dw_sc = taps; base.dw_st = 1;
+  base.dw = dw; base.dw_sb = d->w_batch_stride; base.dw_sn = w_stride_o(d); base.dw_sc = w_stride_c(d); base.dw_st = 1;
   base.alpha = alpha;
   base.ntaps = (int)taps;
   for (int ky = 0; ky < d->kh; ++ky)
@@ -480,6 +487,7 @@ extern "C" int msg_conv2d_forward_fused(float* y, const float* x, const float* w
     }
     W2Params wp{};
     wp.w = w; wp.w_sb = d->w_batch_stride; wp.BW = d->w_batch_stride ? d->B : 1; wp.N = d->O; wp.C = d->C;
+    wp.w_sn = w_stride_o(d); wp.w_sc = w_stride_c(d);
     wp.C4 = pl.C4; wp.kh = d->kh; wp.kw = d->kw; wp.pad_h = d->pad_h; wp.pad_w = d->pad_w;
     wp.ay0 = pl.ay0; wp.ax0 = pl.ax0; wp.nay = pl.nay; wp.nax = pl.nax;
     const int64_t wtot = (int64_t)wp.BW * d->O * 4 * pl.C4 * pl.nay * pl.nax;

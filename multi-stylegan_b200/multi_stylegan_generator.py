@@ -177,7 +177,8 @@ class ModulatedConv2d(nn.Module):
             "Expect input feature shape of {} but get {}.".format(self.in_channels, features)
         weight, modulated_style = self.modulated_weight(style, batch_size)
         if self.upsampling:
-            output = conv.conv_transpose2d(input, weight.transpose(1, 2), stride=self.stride, padding=self.padding)
+            output = conv.conv_transpose2d(input, weight, stride=self.stride, padding=self.padding,
+                                           weight_is_conv_layout=True)
             output = self.blur(output)
         else:
             output = conv.conv2d(input, weight, stride=self.stride, padding=self.padding)
@@ -222,7 +223,7 @@ class StyledConv2d(nn.Module):
             # transposed conv (:393-401) -> [blur (:403) + noise + bias + leaky ReLU] as one FIR pass
             batch_size = input.shape[0]
             weight, style = mc.modulated_weight(style, batch_size)
-            output = conv.conv_transpose2d(input, weight.transpose(1, 2), stride=mc.stride, padding=mc.padding)
+            output = conv.conv_transpose2d(input, weight, stride=mc.stride, padding=mc.padding, weight_is_conv_layout=True)
             kh, kw = mc.blur.kernel.shape
             oh = output.shape[2] + sum(mc.blur.padding) - kh + 1
             ow = output.shape[3] + sum(mc.blur.padding) - kw + 1

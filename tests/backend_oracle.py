@@ -22,9 +22,13 @@ def upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0,
     return ops.upfirdn2d(input, kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
 
 
+def _wt(w, w_transposed):
+    return w.transpose(-4, -3) if w_transposed else w
+
+
 def conv2d_forward(x, w, stride=1, padding=0, alpha=1.0, bias=None, noise=None, noise_w=None, add=None, act=False,
-                   slope=0.2, gain=1.0):
-    v = ops.conv2d(x, w, stride, padding) * alpha
+                   slope=0.2, gain=1.0, w_transposed=False):
+    v = ops.conv2d(x, _wt(w, w_transposed), stride, padding) * alpha
     if noise is not None:
         v = v + noise_w * noise
     if bias is not None:
@@ -36,12 +40,12 @@ def conv2d_forward(x, w, stride=1, padding=0, alpha=1.0, bias=None, noise=None, 
     return v * gain
 
 
-def conv2d_dgrad(dy, w, in_hw, stride=1, padding=0, alpha=1.0):
-    return ops.conv2d_dgrad(dy, w, in_hw, stride, padding) * alpha
+def conv2d_dgrad(dy, w, in_hw, stride=1, padding=0, alpha=1.0, w_transposed=False):
+    return ops.conv2d_dgrad(dy, _wt(w, w_transposed), in_hw, stride, padding) * alpha
 
 
-def conv2d_wgrad(dy, x, khw, stride=1, padding=0, per_sample=False, alpha=1.0):
-    return ops.conv2d_wgrad(dy, x, khw, stride, padding, per_sample) * alpha
+def conv2d_wgrad(dy, x, khw, stride=1, padding=0, per_sample=False, alpha=1.0, w_transposed=False):
+    return _wt(ops.conv2d_wgrad(dy, x, khw, stride, padding, per_sample) * alpha, w_transposed)
 
 
 def modulate_weights(W, s, scale, demodulate):

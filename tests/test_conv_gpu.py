@@ -229,3 +229,29 @@ def test_conv_cta_pair_kernel_subprocess(built_library):
     env = dict(os.environ, MSG_B200_TC_VARIANT="4")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert "PAIR_OK" in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("shape", [(2, 48, 40, 32, 32, 2, 2, 0, True), (2, 64, 64, 32, 32, 3, 1, 1, True),
+                                   (2, 32, 64, 64, 64, 3, 2, 0, False)])
+@pytest.mark.parametrize("engine", ["tc", "simt"])
+def test_conv_transposed_weight_layout(built_library, shape, engine):
+    """w_transposed: the filters are stored [C, O, kh, kw] (conv_transpose2d's layout) and read / written in place."""
+    from multi_stylegan_b200 import _C, _lib
+    B, C, O, H, W, k, s, p, per = shape
+    x, w, y, dy = make(shape, seed=5)
+    wt = w.transpose(-4, -3).contiguous()
+    d = dev()
+    old = _C.conv_flags
+    _C.conv_flags = _lib.CONV_FORCE_TC if engine == "tc" else _lib.CONV_FORCE_SIMT
+    tol = 1e-2 if engine == "tc" else 1e-4
+    try:
+        got = _C.conv2d_forward(x.to(d), wt.to(d), s, p, w_transposed=True)
+        assert rel_err(got, y) < tol
+        got = _C.conv2d_dgrad(dy.to(d), wt.to(d), (H, W), s, p, w_transposed=True)
+        assert rel_err(got, ops.conv2d_dgrad(dy, w, (H, W), s, p)) < tol
+        got = _C.conv2d_wgrad(dy.to(d), x.to(d), (k, k), s, p, per, w_transposed=True)
+        want = ops.conv2d_wgrad(dy, x, (k, k), s, p, per).transpose(-4, -3)
+        assert got.shape == want.shape and rel_err(got, want) < tol
+        torch.cuda.synchronize()
+    finally:
+        _C.conv_flags = old
