@@ -282,7 +282,6 @@ struct DgradPlan {
 static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float* w, float* dx, float alpha, int flags) {
   DgradPlan pl{};
   const int s = d->stride_h;
-  const int64_t taps = (int64_t)d->kh * d->kw;
   pl.nph = s * s;
   pl.O4 = r4(d->O);
   bool any_tc = false;
