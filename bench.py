@@ -182,9 +182,13 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # warm-up: W plain iterations + one iteration with both lazy regularisers (their kernels and shapes)
+    lazy_every = hp["lazy_generator_regularization"]
     for i in range(max(args.warmup, 3)):
-        mw.iteration = 14 if i == 0 else 0
-        mw.train_step(pool[i % len(pool)])
+        mw.iteration = lazy_every - 1 if i == 0 else 0       # train_step increments first: iteration 16 runs R1 + PL
+        out = mw.train_step(pool[i % len(pool)])
+        if i == 0:
+            assert "loss_path_length_regularization" in out and "loss_discriminator_regularization" in out, \
+                "warm-up did not exercise the lazy regularisers"
     barrier()
 
     def timed(e2e: bool):
