@@ -348,6 +348,24 @@ class Generator(nn.Module):
             return input.repeat(1, n_latent, 1)
         return input
 
+    @staticmethod
+    def _paired_output(block_1: "OutputBlock", block_2: "OutputBlock", features: torch.Tensor, w: torch.Tensor,
+                       skip_12: torch.Tensor):
+        """output_blocks_1[i](x, w, skip_1) and output_blocks_2[i](x, style, skip_2) (reference :188-189, :509-526) as ONE
+        1x1 modulated convolution with the two 3-channel filter banks stacked (both read the same 512-channel
+        features) and ONE skip upsampling on the stacked [B, 6, H, W] image; returns the stacked result and the style."""
+        batch = features.shape[0]
+        weight_1, style = block_1.modulated_convolution.modulated_weight(w, batch)
+        weight_2, _ = block_2.modulated_convolution.modulated_weight(style, batch)
+        mc = block_1.modulated_convolution
+        output = conv.conv2d(features, torch.cat([weight_1, weight_2], dim=1), stride=mc.stride, padding=mc.padding)
+        c = weight_1.shape[1]
+        bias = torch.cat([block_1.bias.expand(1, c, 1, 1), block_2.bias.expand(1, c, 1, 1)], dim=1)
+        output = output + bias
+        if skip_12 is not None:
+            output = output + block_1.upsampling(skip_12)
+        return output, style
+
     def forward(self, input: Union[List[torch.Tensor], torch.Tensor], return_main_style_vectors: bool = False,
                 noise: Optional[List[torch.Tensor]] = None, randomize_noise: bool = True,
                 inject_index: Optional[int] = None, input_is_latent: bool = False,
@@ -370,6 +388,8 @@ class Generator(nn.Module):
         out_2 = self.starting_convolution_2(out_2, style, noise=noise_start)
         skip_1, style = self.starting_output_block_1(out_1, latent[:, 1])
         skip_2 = self.starting_output_block_2(out_2, style)
+        paired = not dead            # both tRGB blocks of a level read branch-1 features (:188-189): evaluate them jointly
+        skip_12 = torch.cat([skip_1, skip_2], dim=1) if paired else None
         for i in range(n_main // 2):
             out_1, style = self.main_convolutions_1[2 * i](out_1, latent[:, 2 * i + 1], noise=noise[2 * i])
             if dead:
@@ -377,9 +397,16 @@ class Generator(nn.Module):
             out_1, style = self.main_convolutions_1[2 * i + 1](out_1, latent[:, 2 * i + 2], noise=noise[2 * i + 1])
             if dead:
                 out_2 = self.main_convolutions_2[2 * i + 1](out_2, style, noise=noise[2 * i + 1])
-            skip_1, style = self.output_blocks_1[i](out_1, latent[:, 2 * i + 3], skip=skip_1)
-            skip_2 = self.output_blocks_2[i](out_1, style, skip=skip_2)     # branch-1 features (reference :189)
-        image = torch.stack([skip_1, skip_2], dim=1)
+            if paired:
+                skip_12, style = self._paired_output(self.output_blocks_1[i], self.output_blocks_2[i], out_1,
+                                                     latent[:, 2 * i + 3], skip_12)
+            else:
+                skip_1, style = self.output_blocks_1[i](out_1, latent[:, 2 * i + 3], skip=skip_1)
+                skip_2 = self.output_blocks_2[i](out_1, style, skip=skip_2)     # branch-1 features (reference :189)
+        if paired:
+            image = skip_12.reshape(skip_12.shape[0], 2, self.out_channels, skip_12.shape[2], skip_12.shape[3])
+        else:
+            image = torch.stack([skip_1, skip_2], dim=1)
         if return_path_length_grads:
             # reference :195-196; `path_length_noise` (an extension) injects the N(0,1) draw for parity tests
             pl_noise = (torch.randn(image.shape, device=image.device, dtype=torch.float32, requires_grad=True)
