@@ -669,12 +669,15 @@ struct TcRedParams {
   int ctiles;               // number of BN-wide tiles along C
   int Npad, Cpad, splits;
   float* part;              // [splits][BS][ntaps][Npad][Cpad]
-  int atoms5d;              // 1: tensor maps are 5-D (32 ch, W, H, B, C/32) -> one TMA box per operand and stage
+  int a5d, b5d;             // operand tensor map is 5-D (32 ch, W, H, B, C/32) -> one TMA box per stage for that operand
   uint32_t variant;
   uint32_t* dbg;
 };
 
-template <int BN, int STAGES>
+// TG filter taps per CTA (narrow C tiles): the dy tile (A) is loaded once per stage and multiplied against the TG shifted
+// x tiles, each tap accumulating into its own BN TMEM columns — one A box + TG B boxes per TG MMAs groups instead of a
+// full (A, B) pair per tap.
+template <int BN, int STAGES, int TG>
 __global__ void __launch_bounds__(192, 1)
 tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmI,
                   const TcRedParams p) {
@@ -682,7 +685,8 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   constexpr uint32_t ATOM_BYTES = 32 * 32 * 4;        // 32 pixels x 32 channels
   constexpr uint32_t A_BYTES = 4 * ATOM_BYTES;        // 128 output channels
   constexpr uint32_t B_BYTES = (BN / 32) * ATOM_BYTES;
-  constexpr uint32_t TMEM_COLS = BN;
+  constexpr uint32_t TMEM_COLS = (TG * BN <= 32) ? 32 : (TG * BN <= 64) ? 64 : (TG * BN <= 128) ? 128 : (TG * BN <= 256) ? 256 : 512;
+  static_assert(TG * BN <= 512, "TMEM columns");
   constexpr uint32_t IDESC = make_idesc_tf32(128, BN, 1, 1);
 
   extern __shared__ uint8_t smem_raw[];
@@ -690,7 +694,7 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t sA = base;
   const uint32_t sB = base + STAGES * A_BYTES;
-  const uint32_t bars = sB + STAGES * B_BYTES;
+  const uint32_t bars = sB + STAGES * TG * B_BYTES;
   const uint32_t acc_full = bars + 16 * STAGES;
   const uint32_t tmem_slot = acc_full + 8;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
@@ -698,8 +702,10 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntile = blockIdx.x / p.ctiles, ctile = blockIdx.x - ntile * p.ctiles;
   const int n0 = ntile * 128, c0 = ctile * BN;
-  const int t = blockIdx.y % p.ntaps;
-  const int bs = blockIdx.y / p.ntaps;      // sample index when per_sample, else 0
+  const int tgroups = (p.ntaps + TG - 1) / TG;
+  const int tg0 = (blockIdx.y % tgroups) * TG;           // first tap of this CTA's group
+  const int ntg = (TG == 1) ? 1 : ((p.ntaps - tg0) < TG ? (p.ntaps - tg0) : TG);
+  const int bs = blockIdx.y / tgroups;      // sample index when per_sample, else 0
   const int split = blockIdx.z;
   const int Wk = 1 << p.wk_log2, Hk = 32 >> p.wk_log2;
 
@@ -735,7 +741,6 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     // One TMA box per 32-channel atom: 4 + BN/32 boxes per stage.  They are issued by that many lanes in parallel
     // (a single thread issuing 12 bulk-tensor copies per 512-cycle MMA group was the measured limiter).
     constexpr int NBOX = 4 + BN / 32;
-    const int dy = p.tap_dy[t], dx = p.tap_dx[t];
     for (int it = 0; it < kiters; ++it) {
       const int s = it % STAGES;
       const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -746,22 +751,28 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       const int yc = r / p.chunks_x, xc = r - yc * p.chunks_x;
       const int b = p.per_sample ? bs : bl;
       const uint32_t full = bars + 8 * s;
-      if (p.atoms5d) {
-        // all channel atoms of an operand in one box: [atom][32 px][32 ch] is exactly the MN-major atom layout
-        if (lane == 0) {
-          mbar_expect_tx(full, A_BYTES + B_BYTES);
-          tma_load_5d(sA + s * A_BYTES, &tmG, full, 0, xc * Wk, yc * Hk, b, n0 >> 5);
-          tma_load_5d(sB + s * B_BYTES, &tmI, full, 0, xc * Wk + dx, yc * Hk + dy, b, c0 >> 5);
-        }
-        continue;
-      }
-      if (lane == 0) mbar_expect_tx(full, A_BYTES + B_BYTES);
+      if (lane == 0) mbar_expect_tx(full, A_BYTES + ntg * B_BYTES);
       __syncwarp();
-      if (lane < 4)
+      // 5-D maps: all channel atoms of an operand in one box ([atom][32 px][32 ch] is exactly the MN-major atom
+      // layout); otherwise one 4-D box per atom, issued by consecutive lanes
+      if (p.a5d) {
+        if (lane == 0) tma_load_5d(sA + s * A_BYTES, &tmG, full, 0, xc * Wk, yc * Hk, b, n0 >> 5);
+      } else if (lane < 4) {
         tma_load_4d(sA + s * A_BYTES + lane * ATOM_BYTES, &tmG, full, n0 + 32 * lane, xc * Wk, yc * Hk, b);
-      else if (lane < NBOX)
-        tma_load_4d(sB + s * B_BYTES + (lane - 4) * ATOM_BYTES, &tmI, full, c0 + 32 * (lane - 4), xc * Wk + dx,
-                    yc * Hk + dy, b);
+      }
+#pragma unroll
+      for (int g = 0; g < TG; ++g) {
+        if (g < ntg) {
+          if (p.b5d) {
+            if (lane == 0)
+              tma_load_5d(sB + (s * TG + g) * B_BYTES, &tmI, full, 0, xc * Wk + p.tap_dx[tg0 + g],
+                          yc * Hk + p.tap_dy[tg0 + g], b, c0 >> 5);
+          } else if (lane >= 4 && lane < NBOX) {
+            tma_load_4d(sB + (s * TG + g) * B_BYTES + (lane - 4) * ATOM_BYTES, &tmI, full, c0 + 32 * (lane - 4),
+                        xc * Wk + p.tap_dx[tg0 + g], yc * Hk + p.tap_dy[tg0 + g], b);
+          }
+        }
+      }
       if (lane == 0) dbg_set(dbg, 1, 2 * it + 2);
     }
   } else if (warp == 1) {
@@ -779,8 +790,13 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t ad = make_smem_desc(sA + s * A_BYTES + k * 1024, lbo, sbo, SWZ_128B_BASE32B);
-          const uint64_t bd = make_smem_desc(sB + s * B_BYTES + k * 1024, lbo, sbo, SWZ_128B_BASE32B);
-          mma_tf32(tmem_base, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int g = 0; g < TG; ++g) {
+            if (g < ntg) {
+              const uint64_t bd = make_smem_desc(sB + (s * TG + g) * B_BYTES + k * 1024, lbo, sbo, SWZ_128B_BASE32B);
+              mma_tf32(tmem_base + g * BN, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+            }
+          }
         }
         mma_commit(bars + 8 * (STAGES + s));
         dbg_set(dbg, 2, 2 * it + 2);
@@ -791,7 +807,6 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   } else {
     const int q = warp & 3;
     const int n = q * 32 + lane;
-    float* prow = p.part + ((((int64_t)split * gridDim.y + blockIdx.y) * p.Npad) + n0 + n) * p.Cpad + c0;
     bool acc_ok = true;
     if (kiters > 0) {
       acc_ok = mbar_wait(acc_full, 0, soft);
@@ -799,19 +814,25 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       tc_fence_after();
     }
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int64_t slots_y = (int64_t)(gridDim.y / tgroups) * p.ntaps;      // (sample, tap) slabs per split
 #pragma unroll 1
-    for (int cc = 0; cc < BN; cc += 32) {
-      float r[32];
-      if (kiters > 0 && acc_ok) {
-        tmem_ld_32x32(tlane + cc, r);
-        tmem_ld_wait();
-      } else {
+    for (int g = 0; g < ntg; ++g) {
+      const int64_t slot = (int64_t)bs * p.ntaps + tg0 + g;
+      float* prow = p.part + ((((int64_t)split * slots_y + slot) * p.Npad) + n0 + n) * p.Cpad + c0;
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        float r[32];
+        if (kiters > 0 && acc_ok) {
+          tmem_ld_32x32(tlane + g * BN + cc, r);
+          tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0.f;
+          for (int j = 0; j < 32; ++j) r[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(prow + cc + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
       }
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(prow + cc + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
     }
     if (threadIdx.x == 64) dbg_set(dbg, 3, 2);
   }
@@ -1071,6 +1092,7 @@ bool tc_redgemm_supported(const RedGemm& g) {
 
 struct RedPlan {
   int BN, Npad, Cpad, BS, splits, wk_log2, chunks_x, chunks_y;
+  int TG;                   // filter taps per CTA
   size_t part_bytes;
 };
 
@@ -1086,14 +1108,24 @@ static RedPlan red_plan(const RedGemm& g) {
   pl.chunks_x = (int)ceil_div(g.PW, Wk);
   pl.chunks_y = (int)ceil_div(g.PH, Hk);
   const int64_t kiters = (int64_t)pl.chunks_x * pl.chunks_y * (g.dw_sb != 0 ? 1 : g.B);
-  const int64_t tiles = (int64_t)(pl.Npad / 128) * (pl.Cpad / pl.BN) * g.ntaps * pl.BS;
+  // narrow C tiles share the dy tile among several taps (one A box per TG taps)
+  pl.TG = 1;
+  if (g.ntaps > 1 && !(tc_variant() & 8u)) {
+    if (pl.BN == 128) pl.TG = 3;
+    else if (pl.BN == 64) pl.TG = 4;
+    else if (pl.BN == 32) pl.TG = g.ntaps < 9 ? (g.ntaps >= 4 ? 4 : 1) : 9;
+    if (pl.TG == 3 && g.ntaps < 3) pl.TG = 1;
+    if (pl.TG == 4 && g.ntaps < 4) pl.TG = 1;
+  }
+  const int64_t tgroups = ceil_div(g.ntaps, pl.TG);
+  const int64_t tiles = (int64_t)(pl.Npad / 128) * (pl.Cpad / pl.BN) * tgroups * pl.BS;
   // split-K factor: fill whole waves of SMs (a grid of 324 CTAs on 148 SMs runs three rounds for 2.2 rounds of work),
   // keep >= 8 k-iterations per CTA, and among equally full grids prefer fewer splits (less partial-sum traffic).
   const int64_t max_by_k = kiters / 8 > 0 ? kiters / 8 : 1;
   const int64_t sms = num_sms();
   int64_t best = 1;
   double best_t = 1e300;
-  for (int64_t sp = 1; sp <= 64 && sp <= max_by_k; ++sp) {
+  for (int64_t sp = 1; sp <= 2 * sms && sp <= max_by_k; ++sp) {
     const int64_t rounds = ceil_div(tiles * sp, sms);
     // time ~ rounds x (k-iterations per CTA + ~24 iterations of fixed per-CTA cost) + the partial-sum reduction
     const double t = (double)rounds * ((double)kiters / (double)sp + 24.0) + 2.0 * (double)sp;
@@ -1106,12 +1138,14 @@ static RedPlan red_plan(const RedGemm& g) {
 
 size_t tc_redgemm_workspace(const RedGemm& g) { return red_plan(g).part_bytes + 256; }
 
-template <int BN>
+template <int BN, int TG>
 static int launch_red(const CUtensorMap& tmG, const CUtensorMap& tmI, const TcRedParams& p, dim3 grid,
                       cudaStream_t st) {
-  constexpr int STAGES = (BN == 256) ? 4 : 6;
-  constexpr size_t smem = (size_t)STAGES * (16384 + BN * 128) + 16 * STAGES + 64 + 1024;
-  auto kfn = tc_redgemm_kernel<BN, STAGES>;
+  constexpr size_t per_stage = 16384 + (size_t)TG * BN * 128;
+  constexpr int STAGES = (per_stage * 6 + 4096 <= 227 * 1024) ? 6 : (per_stage * 4 + 4096 <= 227 * 1024) ? 4 : 3;
+  constexpr size_t smem = (size_t)STAGES * per_stage + 16 * STAGES + 64 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  auto kfn = tc_redgemm_kernel<BN, STAGES, TG>;
   static bool attr_done = false;
   if (!attr_done) {
     MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1133,37 +1167,33 @@ int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   // Channel counts that are whole 32-channel atoms: 5-D maps (32 ch, W, H, B, atoms) with the atom index as the slowest
   // box dimension, so ONE box per operand fills a stage (a bulk-tensor copy costs ~55 cycles + ~1.4 per 128-byte row;
   // twelve 4 KB boxes per stage made the producer the bottleneck).  Otherwise one 4-D box per atom.
-  const bool atoms5d = (g.N % 32 == 0) && (g.C % 32 == 0) && !(tc_variant() & 2u);
-  if (atoms5d) {
-    {
-      const uint64_t dims[5] = {32, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B, (uint64_t)(g.N / 32)};
-      const uint64_t strides[4] = {(uint64_t)g.gs.sx * 4, (uint64_t)g.gs.sy * 4, (uint64_t)g.gs.sb * 4, 128};
-      const uint32_t box[5] = {32, (uint32_t)Wk, (uint32_t)Hk, 1, 4};
-      int rc = make_tmap5(&tmG, g.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-      if (rc) return rc;
-    }
-    {
-      const uint64_t dims[5] = {32, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B, (uint64_t)(g.C / 32)};
-      const uint64_t strides[4] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4, 128};
-      const uint32_t box[5] = {32, (uint32_t)Wk, (uint32_t)Hk, 1, (uint32_t)(pl.BN / 32)};
-      int rc = make_tmap5(&tmI, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-      if (rc) return rc;
-    }
+  const bool a5d = (g.N % 32 == 0) && !(tc_variant() & 2u);
+  const bool b5d = (g.C % 32 == 0) && !(tc_variant() & 2u);
+  if (a5d) {
+    const uint64_t dims[5] = {32, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B, (uint64_t)(g.N / 32)};
+    const uint64_t strides[4] = {(uint64_t)g.gs.sx * 4, (uint64_t)g.gs.sy * 4, (uint64_t)g.gs.sb * 4, 128};
+    const uint32_t box[5] = {32, (uint32_t)Wk, (uint32_t)Hk, 1, 4};
+    int rc = make_tmap5(&tmG, g.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
   } else {
-    {
-      const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B};
-      const uint64_t strides[3] = {(uint64_t)g.gs.sx * 4, (uint64_t)g.gs.sy * 4, (uint64_t)g.gs.sb * 4};
-      const uint32_t box[4] = {32, (uint32_t)Wk, (uint32_t)Hk, 1};
-      int rc = make_tmap(&tmG, g.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-      if (rc) return rc;
-    }
-    {
-      const uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
-      const uint64_t strides[3] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4};
-      const uint32_t box[4] = {32, (uint32_t)Wk, (uint32_t)Hk, 1};
-      int rc = make_tmap(&tmI, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
-      if (rc) return rc;
-    }
+    const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)g.gs.sx * 4, (uint64_t)g.gs.sy * 4, (uint64_t)g.gs.sb * 4};
+    const uint32_t box[4] = {32, (uint32_t)Wk, (uint32_t)Hk, 1};
+    int rc = make_tmap(&tmG, g.g, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  }
+  if (b5d) {
+    const uint64_t dims[5] = {32, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B, (uint64_t)(g.C / 32)};
+    const uint64_t strides[4] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4, 128};
+    const uint32_t box[5] = {32, (uint32_t)Wk, (uint32_t)Hk, 1, (uint32_t)(pl.BN / 32)};
+    int rc = make_tmap5(&tmI, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
+  } else {
+    const uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4};
+    const uint32_t box[4] = {32, (uint32_t)Wk, (uint32_t)Hk, 1};
+    int rc = make_tmap(&tmI, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    if (rc) return rc;
   }
   TcRedParams p{};
   p.ntaps = g.ntaps;
@@ -1173,17 +1203,22 @@ int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.ctiles = pl.Cpad / pl.BN;
   p.Npad = pl.Npad; p.Cpad = pl.Cpad; p.splits = pl.splits; p.part = part;
   p.variant = tc_variant(); p.dbg = tc_debug_buffer();
-  p.atoms5d = atoms5d ? 1 : 0;
-  dim3 grid((unsigned)((pl.Npad / 128) * p.ctiles), (unsigned)(g.ntaps * pl.BS), (unsigned)pl.splits);
+  p.a5d = a5d ? 1 : 0; p.b5d = b5d ? 1 : 0;
+  dim3 grid((unsigned)((pl.Npad / 128) * p.ctiles), (unsigned)(ceil_div(g.ntaps, pl.TG) * pl.BS), (unsigned)pl.splits);
   cudaEvent_t pstop;
   const int pslot = prof_begin(1, g.ntaps, g.C, g.N, (int64_t)g.B * g.PH * g.PW,
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.C * g.ntaps, st, &pstop);
   int rc;
-  switch (pl.BN) {
-    case 256: rc = launch_red<256>(tmG, tmI, p, grid, st); break;
-    case 128: rc = launch_red<128>(tmG, tmI, p, grid, st); break;
-    case 64: rc = launch_red<64>(tmG, tmI, p, grid, st); break;
-    default: rc = launch_red<32>(tmG, tmI, p, grid, st); break;
+  switch (pl.BN * 16 + pl.TG) {
+    case 256 * 16 + 1: rc = launch_red<256, 1>(tmG, tmI, p, grid, st); break;
+    case 128 * 16 + 1: rc = launch_red<128, 1>(tmG, tmI, p, grid, st); break;
+    case 128 * 16 + 3: rc = launch_red<128, 3>(tmG, tmI, p, grid, st); break;
+    case 64 * 16 + 1: rc = launch_red<64, 1>(tmG, tmI, p, grid, st); break;
+    case 64 * 16 + 4: rc = launch_red<64, 4>(tmG, tmI, p, grid, st); break;
+    case 32 * 16 + 1: rc = launch_red<32, 1>(tmG, tmI, p, grid, st); break;
+    case 32 * 16 + 4: rc = launch_red<32, 4>(tmG, tmI, p, grid, st); break;
+    case 32 * 16 + 9: rc = launch_red<32, 9>(tmG, tmI, p, grid, st); break;
+    default: return fail(MSG_ERR_UNSUPPORTED, "conv wgrad(tcgen05): no kernel for BN %d x %d taps per CTA", pl.BN, pl.TG);
   }
   prof_end(pslot, pstop, st);
   if (rc) return rc;
