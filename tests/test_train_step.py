@@ -169,3 +169,29 @@ def test_data_parallel_gradient_allreduce_gloo(tmp_path, oracle_backend):
             assert rel_err(o["grads"][k], acc[k]) < 1e-5, k
     for k in acc:
         assert torch.equal(outs[0]["grads"][k], outs[1]["grads"][k])
+
+
+def test_late_epoch_branches_host_logic(oracle_backend):
+    """CutMix augmentation + consistency steps, wrong-order fakes and top-k filtering (model_wrapper.py:272-277,331-376,
+    392-401; probability 0 in epoch 0, so the benchmark never runs them): one iteration with all of them switched on."""
+    import random
+    from multi_stylegan_b200 import loss
+    from multi_stylegan_b200.model_wrapper import ModelWrapper
+    hp = _hp()
+    G, D = build("cpu")
+    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"])
+    opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"])
+    mw = ModelWrapper(G, D, opt_g, opt_d, hyperparameters=hp, device="cpu")
+    mw.epochs, mw.epoch = 10, 9                 # wrong-order fakes on, CutMix probability 0.45
+    mw.top_k = loss.TopK(starting_iteration=0, final_iteration=1)
+    random.seed(0)
+    torch.manual_seed(0)
+    before = {n: p.detach().clone() for n, p in D.named_parameters()}
+    seen = set()
+    for it in range(6):
+        out = mw.train_step(torch.rand(4, 2, 3, 32, 32))
+        assert all(torch.isfinite(v).all() for v in out.values())
+        seen |= set(out)
+    assert {"loss_cut_mix_augmentation", "loss_cut_mix_regularization", "loss_generator",
+            "loss_discriminator_real"} <= seen
+    assert any(not torch.equal(before[n], p.detach()) for n, p in D.named_parameters())
