@@ -135,7 +135,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -284,7 +284,29 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "oracle port, one plain iteration (D step + G step, no lazy regularisers, dead "
                                           "branch evaluated like the reference) at batch 1, %d run(s)" % n}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _capture_stdout():
+    """Route everything libraries print on fd 1 (NCCL's version banner, ...) to stderr; emit() writes the one JSON line
+    to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -299,6 +321,7 @@ def main():
     ap.add_argument("--profile-out", default=None, help="write the per-shape tcgen05 conv kernel timings (JSON lines)")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU work allowed for the reference arm")
     args = ap.parse_args()
+    _capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
