@@ -51,6 +51,11 @@ class EqualizedLinear(nn.Module):
         return "{}, {}, bias={}".format(self.weight.shape[1], self.weight.shape[0], self.bias is not None)
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
+        if input.dim() == 2:
+            # x (W*scale)^T + b*scale_bias (reference :250-254) as ONE library GEMM: the two constants are its alpha / beta
+            if self.bias is not None:
+                return torch.addmm(self.bias, input, self.weight.t(), beta=self.scale_bias, alpha=self.scale)
+            return torch.mm(input, self.weight.t()) * self.scale
         bias = None if self.bias is None else self.bias * self.scale_bias
         return F.linear(input, self.weight * self.scale, bias)
 

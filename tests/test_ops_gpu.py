@@ -307,3 +307,81 @@ def test_blur_noise_bias_act_fused(built_library, shape, pad):
         want = backend_oracle.blur_noise_bias_act(x, k, p4, noise, nw, bias, 0.2, 1.25)
         got = _C.blur_noise_bias_act(x.to(d), k.to(d), p4, None if noise is None else noise.to(d), nw.to(d), bias.to(d), 0.2, 1.25)
         assert got.shape == want.shape and rel_err(got, want) < TOL
+
+
+def test_kernels_do_not_write_out_of_bounds(built_library):
+    """compute-sanitizer is not available on the GPU pool, so the kernels are called through the raw C-ABI with the
+    output (and the conv workspace) embedded in NaN-filled guard bands, on ragged sizes; the bands must stay untouched."""
+    import ctypes
+    from multi_stylegan_b200 import _lib
+    L = _lib.lib()
+    d = dev()
+    G = 4096                                                    # guard floats on each side
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def guarded(n):
+        buf = torch.full((n + 2 * G,), float("nan"), device=d)
+        return buf, buf[G:G + n]
+
+    def check(buf, n, what):
+        torch.cuda.synchronize()
+        assert torch.isnan(buf[:G]).all() and torch.isnan(buf[G + n:]).all(), what
+        assert not torch.isnan(buf[G:G + n]).any(), what
+
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    k = torch.rand(4, 4, device=d)
+    for (B, H, W, C) in [(2, 33, 35, 12), (1, 7, 5, 132), (3, 64, 64, 8)]:
+        x = torch.randn(B, H, W, C, device=d)
+        for (up, down, p0, p1) in [(1, 1, 2, 1), (1, 1, 2, 2), (2, 1, 2, 1), (1, 2, 1, 1), (2, 2, 0, 1)]:
+            oh = L.msg_upfirdn2d_out_size(H, up, down, p0, p1, 4)
+            ow = L.msg_upfirdn2d_out_size(W, up, down, p0, p1, 4)
+            n = B * oh * ow * C
+            buf, out = guarded(n)
+            rc = L.msg_upfirdn2d(ptr(out), ptr(x), ptr(k), B, H, W, C, 4, 4, up, up, down, down, p0, p1, p0, p1, 0, st)
+            assert rc == 0
+            check(buf, n, ("fir", B, H, W, C, up, down))
+        # fused blur tail
+        oh, ow = H + 3 - 3, W + 3 - 3
+        n = B * oh * ow * C
+        buf, out = guarded(n)
+        noise = torch.randn(B, oh, ow, device=d)
+        nw = torch.tensor([0.2], device=d)
+        bias = torch.randn(C, device=d)
+        rc = L.msg_upfirdn2d_bias_act(ptr(out), ptr(x), ptr(k), B, H, W, C, 4, 4, 2, 1, 2, 1, ptr(noise), ptr(nw), oh * ow,
+                                      ptr(bias), 1, 0.2, 1.0, st)
+        assert rc == 0
+        check(buf, n, ("blur+act", B, H, W, C))
+        # channel-inner activation forward / backward
+        n = B * H * W * C
+        buf, out = guarded(n)
+        rc = L.msg_noise_bias_act_nhwc(ptr(out), ptr(x), None, None, None, ptr(bias), B * H * W, C, 1, 0.2, 1.0, st)
+        assert rc == 0
+        check(buf, n, ("nba", B, H, W, C))
+    # conv forward / dgrad / wgrad: outputs and workspace in guard bands (tcgen05 engine, ragged shapes)
+    for (B, C, O, H, W, kk, s, p, per) in [(2, 36, 40, 19, 23, 3, 1, 1, True), (2, 32, 48, 17, 18, 3, 2, 0, False),
+                                           (1, 6, 20, 9, 9, 3, 1, 1, False), (3, 64, 132, 8, 8, 1, 1, 0, False)]:
+        dsc = _lib.ConvDesc()
+        dsc.B, dsc.C, dsc.H, dsc.W, dsc.O, dsc.kh, dsc.kw = B, C, H, W, O, kk, kk
+        dsc.stride_h = dsc.stride_w = s
+        dsc.pad_h = dsc.pad_w = p
+        dsc.OH, dsc.OW = (H + 2 * p - kk) // s + 1, (W + 2 * p - kk) // s + 1
+        dsc.w_batch_stride = O * C * kk * kk if per else 0
+        dsc.layout = _lib.LAYOUT_NHWC
+        x = torch.randn(B, H, W, C, device=d)
+        w = torch.randn((B if per else 1) * O * C * kk * kk, device=d)
+        dy = torch.randn(B, dsc.OH, dsc.OW, O, device=d)
+        for which, n_out in ((0, B * dsc.OH * dsc.OW * O), (1, B * H * W * C), (2, w.numel())):
+            wsn = L.msg_conv2d_workspace(ctypes.byref(dsc), which, _lib.CONV_FORCE_TC)
+            wbuf = torch.full((wsn // 4 + 2 * G,), float("nan"), device=d)
+            ws = wbuf[G:]
+            buf, out = guarded(n_out)
+            if which == 0:
+                rc = L.msg_conv2d_forward(ptr(out), ptr(x), ptr(w), ctypes.byref(dsc), 1.0, ptr(ws), wsn, _lib.CONV_FORCE_TC, st)
+            elif which == 1:
+                rc = L.msg_conv2d_dgrad(ptr(out), ptr(dy), ptr(w), ctypes.byref(dsc), 1.0, ptr(ws), wsn, _lib.CONV_FORCE_TC, st)
+            else:
+                rc = L.msg_conv2d_wgrad(ptr(out), ptr(dy), ptr(x), ctypes.byref(dsc), 1.0, ptr(ws), wsn, _lib.CONV_FORCE_TC, st)
+            assert rc == 0, (which, L.msg_last_error())
+            check(buf, n_out, ("conv", which, B, C, O, H, W, kk, s))
+            torch.cuda.synchronize()
+            assert torch.isnan(wbuf[:G]).all() and torch.isnan(wbuf[G + wsn // 4:]).all(), ("conv workspace", which)
