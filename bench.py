@@ -271,12 +271,38 @@ def run_ours(args):
                 "peak_note": "TF32 dense = 1/2 of the %s bf16 sustained rate (%.0f TFLOP/s) in MEASURED_PEAKS.json" % (src, bf16_sust),
                 "all_tcgen05_conv_kernels": {"ms": conv_ms, "share_of_step": conv_ms / ms,
                                              "tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None}}
+    # secondary roofline (north star: upfirdn2d against HBM): the generator's 256^2 blur, CUDA events, inputs rotate over
+    # 3 x 1 GiB (> L2); algorithmic bytes = 4 * (N_in + N_out)
+    roof_hbm = None
+    if world == 1:
+        try:
+            k4 = torch.tensor([1., 3., 3., 1.], device=dev)
+            k2d = (k4[None] * k4[:, None]) / 16
+            xs = [torch.randn(B, 256, 256, 512, device=dev) for _ in range(3)]
+            for i in range(3):
+                _C.upfirdn2d(xs[i], k2d, 1, 1, 1, 1, 2, 1, 2, 1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(12):
+                _C.upfirdn2d(xs[i % 3], k2d, 1, 1, 1, 1, 2, 1, 2, 1)
+            e1.record()
+            torch.cuda.synchronize()
+            blur_ms = e0.elapsed_time(e1) / 12
+            nbytes = 2 * xs[0].numel() * 4
+            roof_hbm = {"bound": "hbm", "kernel": "fir_cl_blur_kernel: upfirdn2d 4x4 pad (2,1) on [%d,512,256,256] fp32 channels-last" % B,
+                        "achieved": nbytes / (blur_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": nbytes / (blur_ms * 1e-3) / 1e9 / hbm, "traffic": traffic_table.get("fir_cl_blur 256"),
+                        "avg_ms": blur_ms, "algorithmic_bytes_per_launch": nbytes}
+            del xs
+        except Exception as exc:                                         # never lose the headline line to the extra
+            roof_hbm = {"error": str(exc)[:200]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic", "config": cfg,
             "e2e": {"value": seqs / (ms_e2e / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": B * 2 * 3 * 256 * 256 * 4, "d2h_bytes_per_step": 4 * len(last_losses or {})},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
             "conv_engine": _C.conv2d_last_engine()}
     if world == 1 and not args.no_cpu_baseline:
         sec, n = cpu_reference_step_time(1, 0, args.cpu_budget)

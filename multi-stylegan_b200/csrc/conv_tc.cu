@@ -877,6 +877,12 @@ tc_red_reduce_kernel(const RedReduceParams p) {
 // Host side
 // ------------------------------------------------------------------------------------------------
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// per-device "already configured" flags (function attributes belong to the device's context)
+static inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return dev;
+}
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
@@ -921,10 +927,11 @@ static int launch_pix(const TMapSet& tmA, const CUtensorMap& tmB, const TcPixPar
   constexpr size_t smem = (size_t)STAGES * (MT * 16384 + BN * 128) + 4 * 32 * 33 * 4 + 16 * STAGES + 64 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   auto kfn = tc_pixgemm_kernel<BN, STAGES, MT>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  const int slot = current_device_slot();
+  if (!attr_done[slot]) {
     MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done[slot] = true;
   }
   // one persistent CTA per SM (two co-resident ones would have to share TMEM columns and the smem ring)
   const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
@@ -952,11 +959,14 @@ static int launch_pix2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcP
   constexpr size_t smem = (size_t)STAGES * (16384 + 128 * 128) + 4 * 32 * 33 * 4 + 16 * STAGES + 64 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   auto kfn = tc_pixgemm2_kernel<STAGES>;
-  static int pairs_max = -1;
-  if (pairs_max < 0) {
+  static int pairs_max_dev[64] = {};          // 0 = not queried yet, < 0 = no cluster fits
+  const int slot = current_device_slot();
+  if (pairs_max_dev[slot] == 0) {
     MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pairs_max = max_active_pairs(reinterpret_cast<const void*>(kfn), smem);
+    const int n = max_active_pairs(reinterpret_cast<const void*>(kfn), smem);
+    pairs_max_dev[slot] = n > 0 ? n : -1;
   }
+  const int pairs_max = pairs_max_dev[slot];
   if (pairs_max <= 0) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05, CTA pairs): no cluster can be resident");
   const int pairs = p.total_tiles < pairs_max ? p.total_tiles : pairs_max;
   kfn<<<2 * pairs, 192, smem, st>>>(tmA, tmB, p);
@@ -1146,10 +1156,11 @@ static int launch_red(const CUtensorMap& tmG, const CUtensorMap& tmI, const TcRe
   constexpr size_t smem = (size_t)STAGES * per_stage + 16 * STAGES + 64 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   auto kfn = tc_redgemm_kernel<BN, STAGES, TG>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  const int slot = current_device_slot();
+  if (!attr_done[slot]) {
     MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done[slot] = true;
   }
   kfn<<<grid, 192, smem, st>>>(tmG, tmI, p);
   MSG_CHECK_LAUNCH("conv redgemm(tcgen05)");
