@@ -163,7 +163,7 @@ __device__ __forceinline__ void fma4(float4& a, const float4& v, float k) {
 // each thread slides down the rows of its tile keeping the four partially accumulated output rows in registers,
 // so every input row is loaded once per thread (COLS + 3 float4 loads per COLS outputs; neighbours hit in L1).
 template <int COLS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, const float* __restrict__ kernel,
                    const FirClParams p) {
   __shared__ float sk[4][4];
