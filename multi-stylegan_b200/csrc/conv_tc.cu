@@ -270,6 +270,7 @@ struct TcPixParams {
   float alpha;
   int w_per_sample;
   int vec_store;               // NHWC output, 16-byte aligned channel runs, N % 4 == 0
+  int tma_store;               // epilogue writes 32-pixel x 32-channel boxes with TMA (no residual operand)
   Epilogue ep;
 };
 
@@ -278,10 +279,58 @@ struct TcPixParams {
 // `release`: after the last TMEM read arrive on `release_bar` (hands the accumulator back to the MMA warp).
 template <int BN, bool REMOTE>
 __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, uint32_t tlane, int q, int lane, int b, int y0,
-                                             int x0, int n0, int sub, float nw, bool release, uint32_t release_bar) {
+                                             int x0, int n0, int sub, float nw, bool release, uint32_t release_bar,
+                                             const CUtensorMap* tm_out = nullptr, uint32_t stage_smem = 0) {
   constexpr int CW = BN < 32 ? BN : 32;
   const int Wt = 1 << p.wt_log2;
-      if (p.vec_store && CW == 32) {
+      if (tm_out != nullptr && p.tma_store && CW == 32) {
+        // TMA-store path: thread = pixel; the fused transform is applied in registers, the 32-channel run of each pixel
+        // goes to a 128-byte row of a swizzled staging box (conflict-free 128-bit stores) and ONE bulk tensor store per
+        // warp and chunk writes the 32-pixel x 32-channel box (tile edges and channel tails are clipped by the map).
+        const int m0 = sub * 128 + q * 32;
+        const int m = m0 + lane;
+        const int y = y0 + (m >> p.wt_log2), x = x0 + (m & (Wt - 1));
+        const bool valid = (y < p.PH) && (x < p.PW);
+        const float nz = (valid && p.ep.noise) ? nw * __ldg(p.ep.noise + (int64_t)b * p.ep.noise_sb + (int64_t)y * p.PW + x) : 0.f;
+        const int by = y0 + (m0 >> p.wt_log2), bx = x0 + (m0 & (Wt - 1));
+        int buf = 0;
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += 32) {
+          float rr[32];
+          tmem_ld_32x32(tlane + cc, rr);
+          tmem_ld_wait();
+          if (release && cc + 32 >= BN) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { if (REMOTE) mbar_arrive_cluster(release_bar); else mbar_arrive(release_bar); }
+          }
+          const int nb = n0 + cc;
+          if (nb < p.N) {
+            if (lane == 0) tma_store_wait_read<1>();        // the box stored two chunks ago has left this buffer
+            __syncwarp();
+            const uint32_t dst = stage_smem + buf * 4096 + lane * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.ep.bias && nb + 4 * j < p.N) bz = __ldg(reinterpret_cast<const float4*>(p.ep.bias + nb) + j);
+              float4 o;
+              o.x = apply_epilogue(p.ep, p.alpha * rr[4 * j + 0], bz.x, nz, 0.f);
+              o.y = apply_epilogue(p.ep, p.alpha * rr[4 * j + 1], bz.y, nz, 0.f);
+              o.z = apply_epilogue(p.ep, p.alpha * rr[4 * j + 2], bz.z, nz, 0.f);
+              o.w = apply_epilogue(p.ep, p.alpha * rr[4 * j + 3], bz.w, nz, 0.f);
+              const uint32_t a = dst + ((uint32_t)(j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(tm_out, stage_smem + buf * 4096, nb, bx, by, b);
+              tma_store_commit();
+            }
+            buf ^= 1;
+          }
+        }
+      } else if (p.vec_store && CW == 32) {
         // coalesced path: after the transpose lane l owns channels (l & 7) * 4 .. + 3 of pixels i * 4 + (l >> 3)
         const int psub = lane >> 3, ch4 = (lane & 7) * 4;
         int64_t poff[8];
@@ -384,7 +433,7 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
 template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(192, 1)
 tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ CUtensorMap tmB,
-                  const TcPixParams p) {
+                  const __grid_constant__ CUtensorMap tmOut, const TcPixParams p) {
   // MT = 128-pixel sub-tiles per CTA tile: narrow-N layers (BN <= 128) take two, which halves the weight bytes and
   // TMA boxes per FLOP (one A box of 256 pixels, one B box, two MMAs per k-step sharing the B descriptor).
   constexpr uint32_t A_BYTES = MT * 128 * 32 * 4;
@@ -393,7 +442,8 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
   constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) < 32 ? 32 : 2 * ACC_COLS;
   static_assert(2 * ACC_COLS <= 512, "TMEM columns");
   constexpr uint32_t IDESC = make_idesc_tf32(128, BN, 0, 0);
-  constexpr uint32_t STG_BYTES = 4 * 32 * 33 * 4;     // per-warp 32 x 33 transpose buffers
+  constexpr uint32_t STG_BYTES = 4 * 2 * 4096;        // per epilogue warp: two 32 px x 128 B boxes (TMA store, 1024-byte
+                                                      // aligned) or one 32 x 33 float transpose buffer (direct stores)
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -423,6 +473,7 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
     fence_barrier_init();
     tma_prefetch_desc(&tmAs.m[0]);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmOut);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, TMEM_COLS);
@@ -489,7 +540,8 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
     }
   } else {
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
-    float* stg = stg_all + q * (32 * 33);
+    float* stg = stg_all + q * (2 * 4096 / 4);
+    const uint32_t stage_smem = sStg + q * (2 * 4096);
     const float nw = p.ep.noise ? __ldg(p.ep.noise_w) : 0.f;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
@@ -507,9 +559,10 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
       const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + a * ACC_COLS + sub * BN;
       const bool last_sub = sub == MT - 1;
 
-      pix_epilogue<BN, false>(p, stg, tlane, q, lane, b, y0, x0, n0, sub, nw, last_sub, acc_empty + 8 * a);
+      pix_epilogue<BN, false>(p, stg, tlane, q, lane, b, y0, x0, n0, sub, nw, last_sub, acc_empty + 8 * a, &tmOut, stage_smem);
       }  // sub
     }
+    if (p.tma_store && lane == 0) tma_store_wait_read<0>();   // staging buffers must outlive their bulk stores
   }
   tc_fence_before();
   __syncthreads();
@@ -922,9 +975,10 @@ size_t tc_pixgemm_workspace(const PixGemm& g) {
 }
 
 template <int BN, int MT>
-static int launch_pix(const TMapSet& tmA, const CUtensorMap& tmB, const TcPixParams& p, cudaStream_t st) {
+static int launch_pix(const TMapSet& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const TcPixParams& p,
+                      cudaStream_t st) {
   constexpr int STAGES = (BN == 256 || MT == 2) ? 4 : 6;
-  constexpr size_t smem = (size_t)STAGES * (MT * 16384 + BN * 128) + 4 * 32 * 33 * 4 + 16 * STAGES + 64 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (MT * 16384 + BN * 128) + 4 * 2 * 4096 + 16 * STAGES + 64 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   auto kfn = tc_pixgemm_kernel<BN, STAGES, MT>;
   static bool attr_done[64] = {};
@@ -935,7 +989,7 @@ static int launch_pix(const TMapSet& tmA, const CUtensorMap& tmB, const TcPixPar
   }
   // one persistent CTA per SM (two co-resident ones would have to share TMEM columns and the smem ring)
   const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  kfn<<<ctas, 192, smem, st>>>(tmA, tmB, p);
+  kfn<<<ctas, 192, smem, st>>>(tmA, tmB, tmOut, p);
   MSG_CHECK_LAUNCH("conv pixgemm(tcgen05)");
   return MSG_OK;
 }
@@ -1062,6 +1116,19 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): noise epilogue on a scattered output");
   p.vec_store = (g.os.sc == 1 && (g.N % 4 == 0) && al16(g.out) && g.os.sx % 4 == 0 && g.os.sy % 4 == 0 && g.os.sb % 4 == 0 &&
                  (!p.ep.bias || al16(p.ep.bias)) && (!p.ep.add || al16(p.ep.add))) ? 1 : 0;
+  // output tensor map for the TMA-store epilogue: the (possibly phase-scattered) NHWC output as a 4-D view
+  // (N, PW, PH, B) whose pixel strides carry out_mx / out_my and whose base carries the phase offset
+  CUtensorMap tmOut;
+  memset(&tmOut, 0, sizeof(tmOut));
+  p.tma_store = 0;
+  if (p.vec_store && !p.ep.add && BN >= 32 && !pairs && !(tc_variant() & 16u)) {
+    const int bw = Wt < 32 ? Wt : 32;
+    const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)g.os.sx * g.out_mx * 4, (uint64_t)g.os.sy * g.out_my * 4, (uint64_t)g.os.sb * 4};
+    const uint32_t box[4] = {32, (uint32_t)bw, (uint32_t)(32 / bw), 1};
+    float* obase = g.out + (int64_t)g.out_oy * g.os.sy + (int64_t)g.out_ox * g.os.sx;
+    if (al16(obase) && make_tmap(&tmOut, obase, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) == MSG_OK) p.tma_store = 1;
+  }
   cudaEvent_t pstop;
   const int pslot = prof_begin(0, g.ntaps, g.Cr, g.N, (int64_t)g.B * g.PH * g.PW,
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);
@@ -1070,18 +1137,18 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     rc = launch_pix2(tmA.m[0], tmB, p, st);
   } else if (MT == 2) {
     switch (BN) {
-      case 128: rc = launch_pix<128, 2>(tmA, tmB, p, st); break;
-      case 64: rc = launch_pix<64, 2>(tmA, tmB, p, st); break;
-      case 32: rc = launch_pix<32, 2>(tmA, tmB, p, st); break;
-      default: rc = launch_pix<16, 2>(tmA, tmB, p, st); break;
+      case 128: rc = launch_pix<128, 2>(tmA, tmB, tmOut, p, st); break;
+      case 64: rc = launch_pix<64, 2>(tmA, tmB, tmOut, p, st); break;
+      case 32: rc = launch_pix<32, 2>(tmA, tmB, tmOut, p, st); break;
+      default: rc = launch_pix<16, 2>(tmA, tmB, tmOut, p, st); break;
     }
   } else {
     switch (BN) {
-      case 256: rc = launch_pix<256, 1>(tmA, tmB, p, st); break;
-      case 128: rc = launch_pix<128, 1>(tmA, tmB, p, st); break;
-      case 64: rc = launch_pix<64, 1>(tmA, tmB, p, st); break;
-      case 32: rc = launch_pix<32, 1>(tmA, tmB, p, st); break;
-      default: rc = launch_pix<16, 1>(tmA, tmB, p, st); break;
+      case 256: rc = launch_pix<256, 1>(tmA, tmB, tmOut, p, st); break;
+      case 128: rc = launch_pix<128, 1>(tmA, tmB, tmOut, p, st); break;
+      case 64: rc = launch_pix<64, 1>(tmA, tmB, tmOut, p, st); break;
+      case 32: rc = launch_pix<32, 1>(tmA, tmB, tmOut, p, st); break;
+      default: rc = launch_pix<16, 1>(tmA, tmB, tmOut, p, st); break;
     }
   }
   prof_end(pslot, pstop, st);
