@@ -280,7 +280,9 @@ struct TcPixParams {
 template <int BN, bool REMOTE>
 __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, uint32_t tlane, int q, int lane, int b, int y0,
                                              int x0, int n0, int sub, float nw, bool release, uint32_t release_bar,
-                                             const CUtensorMap* tm_out = nullptr, uint32_t stage_smem = 0) {
+                                             const CUtensorMap* tm_out = nullptr, uint32_t stage_smem = 0,
+                                             const CUtensorMap* tm_add = nullptr, uint32_t add_bar = 0,
+                                             uint32_t* add_phase = nullptr) {
   constexpr int CW = BN < 32 ? BN : 32;
   const int Wt = 1 << p.wt_log2;
       if (tm_out != nullptr && p.tma_store && CW == 32) {
@@ -294,6 +296,17 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
         const float nz = (valid && p.ep.noise) ? nw * __ldg(p.ep.noise + (int64_t)b * p.ep.noise_sb + (int64_t)y * p.PW + x) : 0.f;
         const int by = y0 + (m0 >> p.wt_log2), bx = x0 + (m0 & (Wt - 1));
         int buf = 0;
+        // residual operand (ResNetBlock / NonLocalBlock join): its 32 x 32 box is fetched by TMA into the second
+        // staging buffer while the accumulator chunk is read, so the output uses a single buffer in that mode
+        const bool with_add = tm_add != nullptr && p.ep.add != nullptr;
+        if (with_add && n0 < p.N) {
+          __syncwarp();                                     // every lane is done reading the previous tile's box
+          if (lane == 0) {
+            fence_proxy_async_smem();
+            mbar_expect_tx(add_bar, 4096);
+            tma_load_4d(stage_smem + 4096, tm_add, add_bar, n0, bx, by, b);
+          }
+        }
 #pragma unroll 1
         for (int cc = 0; cc < BN; cc += 32) {
           float rr[32];
@@ -306,7 +319,29 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
           }
           const int nb = n0 + cc;
           if (nb < p.N) {
-            if (lane == 0) tma_store_wait_read<1>();        // the box stored two chunks ago has left this buffer
+            float4 av[8];
+            if (with_add) {
+              mbar_wait(add_bar, *add_phase & 1u);
+              *add_phase += 1;
+              const uint32_t src = stage_smem + 4096 + lane * 128;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t a = src + ((uint32_t)(j ^ (lane & 7)) << 4);
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(av[j].x), "=f"(av[j].y), "=f"(av[j].z), "=f"(av[j].w) : "r"(a) : "memory");
+              }
+              __syncwarp();
+              // the landing buffer is free again: fetch the next chunk's residual box behind the math and the store
+              if (lane == 0 && cc + 32 < BN && nb + 32 < p.N) {
+                fence_proxy_async_smem();
+                mbar_expect_tx(add_bar, 4096);
+                tma_load_4d(stage_smem + 4096, tm_add, add_bar, nb + 32, bx, by, b);
+              }
+              if (lane == 0) tma_store_wait_read<0>();      // single output buffer in this mode
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (lane == 0) tma_store_wait_read<1>();      // the box stored two chunks ago has left this buffer
+            }
             __syncwarp();
             const uint32_t dst = stage_smem + buf * 4096 + lane * 128;
 #pragma unroll
@@ -314,10 +349,10 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
               float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
               if (p.ep.bias && nb + 4 * j < p.N) bz = __ldg(reinterpret_cast<const float4*>(p.ep.bias + nb) + j);
               float4 o;
-              o.x = apply_epilogue(p.ep, p.alpha * rr[4 * j + 0], bz.x, nz, 0.f);
-              o.y = apply_epilogue(p.ep, p.alpha * rr[4 * j + 1], bz.y, nz, 0.f);
-              o.z = apply_epilogue(p.ep, p.alpha * rr[4 * j + 2], bz.z, nz, 0.f);
-              o.w = apply_epilogue(p.ep, p.alpha * rr[4 * j + 3], bz.w, nz, 0.f);
+              o.x = apply_epilogue(p.ep, p.alpha * rr[4 * j + 0], bz.x, nz, av[j].x);
+              o.y = apply_epilogue(p.ep, p.alpha * rr[4 * j + 1], bz.y, nz, av[j].y);
+              o.z = apply_epilogue(p.ep, p.alpha * rr[4 * j + 2], bz.z, nz, av[j].z);
+              o.w = apply_epilogue(p.ep, p.alpha * rr[4 * j + 3], bz.w, nz, av[j].w);
               const uint32_t a = dst + ((uint32_t)(j ^ (lane & 7)) << 4);
               asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
             }
@@ -327,7 +362,7 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
               tma_store_4d(tm_out, stage_smem + buf * 4096, nb, bx, by, b);
               tma_store_commit();
             }
-            buf ^= 1;
+            if (!with_add) buf ^= 1;
           }
         }
       } else if (p.vec_store && CW == 32) {
@@ -433,7 +468,8 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
 template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(192, 1)
 tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ CUtensorMap tmB,
-                  const __grid_constant__ CUtensorMap tmOut, const TcPixParams p) {
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
+                  const TcPixParams p) {
   // MT = 128-pixel sub-tiles per CTA tile: narrow-N layers (BN <= 128) take two, which halves the weight bytes and
   // TMA boxes per FLOP (one A box of 256 pixels, one B box, two MMAs per k-step sharing the B descriptor).
   constexpr uint32_t A_BYTES = MT * 128 * 32 * 4;
@@ -455,6 +491,7 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
   const uint32_t acc_full = bars + 16 * STAGES;       // 2 barriers
   const uint32_t acc_empty = acc_full + 16;           // 2 barriers
   const uint32_t tmem_slot = acc_empty + 16;
+  const uint32_t add_bars = tmem_slot + 16;           // one mbarrier per epilogue warp (residual boxes)
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* stg_all = reinterpret_cast<float*>(smem_raw + (sStg - raw));
 
@@ -470,6 +507,7 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
       mbar_init(acc_full + 8 * a, 1);
       mbar_init(acc_empty + 8 * a, 4);        // one arrival per epilogue warp
     }
+    for (int w = 0; w < 4; ++w) mbar_init(add_bars + 8 * w, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmAs.m[0]);
     tma_prefetch_desc(&tmB);
@@ -542,6 +580,7 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
     const int q = warp & 3;                             // TMEM lane quarter this warp may read
     float* stg = stg_all + q * (2 * 4096 / 4);
     const uint32_t stage_smem = sStg + q * (2 * 4096);
+    uint32_t add_phase = 0;
     const float nw = p.ep.noise ? __ldg(p.ep.noise_w) : 0.f;
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
@@ -559,7 +598,8 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
       const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + a * ACC_COLS + sub * BN;
       const bool last_sub = sub == MT - 1;
 
-      pix_epilogue<BN, false>(p, stg, tlane, q, lane, b, y0, x0, n0, sub, nw, last_sub, acc_empty + 8 * a, &tmOut, stage_smem);
+      pix_epilogue<BN, false>(p, stg, tlane, q, lane, b, y0, x0, n0, sub, nw, last_sub, acc_empty + 8 * a, &tmOut, stage_smem,
+                              &tmAdd, add_bars + 8 * q, &add_phase);
       }  // sub
     }
     if (p.tma_store && lane == 0) tma_store_wait_read<0>();   // staging buffers must outlive their bulk stores
@@ -975,10 +1015,10 @@ size_t tc_pixgemm_workspace(const PixGemm& g) {
 }
 
 template <int BN, int MT>
-static int launch_pix(const TMapSet& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const TcPixParams& p,
-                      cudaStream_t st) {
+static int launch_pix(const TMapSet& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAdd,
+                      const TcPixParams& p, cudaStream_t st) {
   constexpr int STAGES = (BN == 256 || MT == 2) ? 4 : 6;
-  constexpr size_t smem = (size_t)STAGES * (MT * 16384 + BN * 128) + 4 * 2 * 4096 + 16 * STAGES + 64 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (MT * 16384 + BN * 128) + 4 * 2 * 4096 + 16 * STAGES + 128 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   auto kfn = tc_pixgemm_kernel<BN, STAGES, MT>;
   static bool attr_done[64] = {};
@@ -989,7 +1029,7 @@ static int launch_pix(const TMapSet& tmA, const CUtensorMap& tmB, const CUtensor
   }
   // one persistent CTA per SM (two co-resident ones would have to share TMEM columns and the smem ring)
   const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  kfn<<<ctas, 192, smem, st>>>(tmA, tmB, tmOut, p);
+  kfn<<<ctas, 192, smem, st>>>(tmA, tmB, tmOut, tmAdd, p);
   MSG_CHECK_LAUNCH("conv pixgemm(tcgen05)");
   return MSG_OK;
 }
@@ -1121,13 +1161,20 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   CUtensorMap tmOut;
   memset(&tmOut, 0, sizeof(tmOut));
   p.tma_store = 0;
-  if (p.vec_store && !p.ep.add && BN >= 32 && !pairs && !(tc_variant() & 16u)) {
+  CUtensorMap tmAdd;
+  memset(&tmAdd, 0, sizeof(tmAdd));
+  if (p.vec_store && BN >= 32 && !pairs && !(tc_variant() & 16u)) {
     const int bw = Wt < 32 ? Wt : 32;
     const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B};
     const uint64_t strides[3] = {(uint64_t)g.os.sx * g.out_mx * 4, (uint64_t)g.os.sy * g.out_my * 4, (uint64_t)g.os.sb * 4};
     const uint32_t box[4] = {32, (uint32_t)bw, (uint32_t)(32 / bw), 1};
-    float* obase = g.out + (int64_t)g.out_oy * g.os.sy + (int64_t)g.out_ox * g.os.sx;
-    if (al16(obase) && make_tmap(&tmOut, obase, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) == MSG_OK) p.tma_store = 1;
+    const int64_t view_off = (int64_t)g.out_oy * g.os.sy + (int64_t)g.out_ox * g.os.sx;
+    float* obase = g.out + view_off;
+    bool ok = al16(obase) && make_tmap(&tmOut, obase, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) == MSG_OK;
+    if (ok && p.ep.add)       // the residual operand has the layout of the output: same view, other base
+      ok = al16(p.ep.add + view_off) &&
+           make_tmap(&tmAdd, p.ep.add + view_off, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) == MSG_OK;
+    p.tma_store = ok ? 1 : 0;
   }
   cudaEvent_t pstop;
   const int pslot = prof_begin(0, g.ntaps, g.Cr, g.N, (int64_t)g.B * g.PH * g.PW,
@@ -1137,18 +1184,18 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     rc = launch_pix2(tmA.m[0], tmB, p, st);
   } else if (MT == 2) {
     switch (BN) {
-      case 128: rc = launch_pix<128, 2>(tmA, tmB, tmOut, p, st); break;
-      case 64: rc = launch_pix<64, 2>(tmA, tmB, tmOut, p, st); break;
-      case 32: rc = launch_pix<32, 2>(tmA, tmB, tmOut, p, st); break;
-      default: rc = launch_pix<16, 2>(tmA, tmB, tmOut, p, st); break;
+      case 128: rc = launch_pix<128, 2>(tmA, tmB, tmOut, tmAdd, p, st); break;
+      case 64: rc = launch_pix<64, 2>(tmA, tmB, tmOut, tmAdd, p, st); break;
+      case 32: rc = launch_pix<32, 2>(tmA, tmB, tmOut, tmAdd, p, st); break;
+      default: rc = launch_pix<16, 2>(tmA, tmB, tmOut, tmAdd, p, st); break;
     }
   } else {
     switch (BN) {
-      case 256: rc = launch_pix<256, 1>(tmA, tmB, tmOut, p, st); break;
-      case 128: rc = launch_pix<128, 1>(tmA, tmB, tmOut, p, st); break;
-      case 64: rc = launch_pix<64, 1>(tmA, tmB, tmOut, p, st); break;
-      case 32: rc = launch_pix<32, 1>(tmA, tmB, tmOut, p, st); break;
-      default: rc = launch_pix<16, 1>(tmA, tmB, tmOut, p, st); break;
+      case 256: rc = launch_pix<256, 1>(tmA, tmB, tmOut, tmAdd, p, st); break;
+      case 128: rc = launch_pix<128, 1>(tmA, tmB, tmOut, tmAdd, p, st); break;
+      case 64: rc = launch_pix<64, 1>(tmA, tmB, tmOut, tmAdd, p, st); break;
+      case 32: rc = launch_pix<32, 1>(tmA, tmB, tmOut, tmAdd, p, st); break;
+      default: rc = launch_pix<16, 1>(tmA, tmB, tmOut, tmAdd, p, st); break;
     }
   }
   prof_end(pslot, pstop, st);
