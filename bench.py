@@ -30,6 +30,7 @@ def workload_config(args, world):
                         "U-Net discriminator, NS-logistic loss, lazy R1 + path length every 16th iteration, EMA",
             "per_gpu_batch": args.batch, "global_batch": args.batch * world, "resolution": 256,
             "parallelism": "dp%d" % world, "ada": bool(args.ada),
+            "cuda_graphs": bool(not args.no_graphs and not args.ada),
             "l2_policy": "working set per step (>= 10 GiB of activations) >> 126 MB L2; inputs rotate over a pool"}
 
 
@@ -165,12 +166,14 @@ def run_ours(args):
     mdist.broadcast_parameters([G, D])
     hp = dict(config.generation_hyperparameters)
     # same Adam as train_multi_stylegan.py:53-57; fused=True only selects PyTorch's single-kernel implementation
-    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-4, lr_style=2e-6), betas=hp["betas"], fused=True)
-    opt_d = torch.optim.Adam(D.parameters(), lr=6e-4, betas=hp["betas"], fused=True)
+    # (capturable=True keeps Adam's step counters on the device so that an iteration can be replayed as a CUDA graph)
+    graphs = not args.no_graphs and not args.ada          # ADA draws its augmentations on the host every call
+    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-4, lr_style=2e-6), betas=hp["betas"], fused=True, capturable=graphs)
+    opt_d = torch.optim.Adam(D.parameters(), lr=6e-4, betas=hp["betas"], fused=True, capturable=graphs)
     Dw = AdaptiveDiscriminatorAugmentation(D) if args.ada else D
     if args.ada:
         Dw.p = 0.5
-    mw = ModelWrapper(G, Dw, opt_g, opt_d, hyperparameters=hp, device=dev)
+    mw = ModelWrapper(G, Dw, opt_g, opt_d, hyperparameters=hp, device=dev, cuda_graphs=graphs)
     mw._d_params = lambda: list(D.parameters())
     torch.manual_seed(1234 + rank)
     pool = [torch.rand(B, 2, 3, 256, 256, device=dev) for _ in range(4)]
@@ -182,21 +185,33 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # warm-up: W plain iterations + one iteration with both lazy regularisers (their kernels and shapes)
+    # (with CUDA graphs: the first lazy / plain iteration runs eagerly, the second one of each kind is captured)
     lazy_every = hp["lazy_generator_regularization"]
-    for i in range(max(args.warmup, 3)):
-        mw.iteration = lazy_every - 1 if i == 0 else 0       # train_step increments first: iteration 16 runs R1 + PL
+    setup = 4 if graphs else 1
+    for i in range(setup + max(args.warmup, 3)):
+        is_lazy = i < setup and i % 2 == 0
+        mw.iteration = lazy_every - 1 if is_lazy else 0      # train_step increments first: iteration 16 runs R1 + PL
         out = mw.train_step(pool[i % len(pool)])
-        if i == 0:
+        if is_lazy:
             assert "loss_path_length_regularization" in out and "loss_discriminator_regularization" in out, \
                 "warm-up did not exercise the lazy regularisers"
     barrier()
+    if graphs:
+        assert mw.graph_replays >= 2 + max(args.warmup, 3), "CUDA graphs requested but the iterations ran eagerly"
 
-    def timed(e2e: bool):
+    def timed(e2e: bool, profile: bool = False):
+        # profile=True: the same K iterations issued eagerly with a CUDA-event pair around every conv launch (roofline)
+        mw.cuda_graphs = graphs and not profile
+        if graphs and profile:
+            # graph capture emptied the caching allocator: refill the eager pool (one lazy + one plain iteration) untimed
+            for it0 in (lazy_every - 1, 0):
+                mw.iteration = it0
+                mw.train_step(pool[0])
         mw.iteration = 0
-        launches0 = _C.launch_count()
-        _C.profile_enable(not e2e)
+        launches0 = _C.launch_count() + mw.graph_launches
+        _C.profile_enable(profile)
         sampler = ClockSampler(local_rank)
-        if not e2e and rank == 0:
+        if not e2e and not profile and rank == 0:
             sampler.start()
         barrier()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -219,16 +234,23 @@ def run_ours(args):
         barrier()
         wall = time.time() - t0
         ms = start.elapsed_time(end)
-        clocks = sampler.stop() if (not e2e and rank == 0) else None
+        clocks = sampler.stop() if (not e2e and not profile and rank == 0) else None
         t = torch.tensor([ms], device=dev)
         if world > 1:
             tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
-        prof = _C.profile_summary() if not e2e else None
+        prof = _C.profile_summary() if profile else None
         _C.profile_enable(False)
-        return float(t.item()), _C.launch_count() - launches0, clocks, prof, last, wall
+        mw.cuda_graphs = graphs
+        return float(t.item()), _C.launch_count() + mw.graph_launches - launches0, clocks, prof, last, wall
 
-    ms, launches, clocks, prof, _, wall = timed(False)
-    ms_e2e, _, _, _, last_losses, _ = timed(True)
+    if graphs:
+        ms, launches, clocks, _, _, wall = timed(False)
+        ms_e2e, _, _, _, last_losses, _ = timed(True)
+        ms_prof, _, _, prof, _, _ = timed(False, profile=True)
+    else:
+        ms, launches, clocks, prof, _, wall = timed(False, profile=True)
+        ms_e2e, _, _, _, last_losses, _ = timed(True)
+        ms_prof = ms
 
     if world > 1:
         tdist.barrier()
@@ -267,9 +289,12 @@ def run_ours(args):
                 "algorithmic_flops_per_launch": top["flops_per_launch"],
                 "frac_of_burst_peak": achieved / (bf16_burst / 2.0),
                 "launches": top["launches"], "avg_ms": top["ms_total"] / top["launches"],
-                "share_of_step": top["ms_total"] / ms,
+                "share_of_step": top["ms_total"] / ms_prof,
+                "measured_in": ("an eager pass of the same %d iterations (%.1f ms/step) with a CUDA-event pair around each conv "
+                                "launch; the timed region itself replays CUDA graphs" % (args.steps, ms_prof / args.steps))
+                if graphs else "the timed region",
                 "peak_note": "TF32 dense = 1/2 of the %s bf16 sustained rate (%.0f TFLOP/s) in MEASURED_PEAKS.json" % (src, bf16_sust),
-                "all_tcgen05_conv_kernels": {"ms": conv_ms, "share_of_step": conv_ms / ms,
+                "all_tcgen05_conv_kernels": {"ms": conv_ms, "share_of_step": conv_ms / ms_prof,
                                              "tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None}}
     # secondary roofline (north star: upfirdn2d against HBM): the generator's 256^2 blur, CUDA events, inputs rotate over
     # 3 x 1 GiB (> L2); algorithmic bytes = 4 * (N_in + N_out)
@@ -343,6 +368,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=8, help="per-GPU batch")
     ap.add_argument("--ada", action="store_true", help="wrap D in adaptive discriminator augmentation (config 4)")
+    ap.add_argument("--no-graphs", action="store_true", help="issue every iteration eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-shape tcgen05 conv kernel timings (JSON lines)")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU work allowed for the reference arm")

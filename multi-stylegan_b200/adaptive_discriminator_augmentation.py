@@ -129,6 +129,8 @@ class AugmentationPipeline(nn.Module):
 
 
 class AdaptiveDiscriminatorAugmentation(nn.Module):
+    graph_capturable = False         # the pipeline draws its per-call decisions on the host (ModelWrapper.cuda_graphs)
+
     def __init__(self, discriminator: nn.Module, r_target: float = 0.6, p_step: float = 5e-03, r_update: int = 8,
                  p_max: float = 0.8, process_group=None) -> None:
         super().__init__()

@@ -8,11 +8,19 @@ sub-steps and the same lazy-regularisation cadence, restructured for one-process
   * gradients are averaged across ranks with one flat all-reduce per optimiser step (dist.py); the
     path-length running mean is averaged too (the reference computes it from DataParallel's gathered batch).
   * the generator's unobservable second branch (multi_stylegan_generator.py:184,187,189) is not evaluated.
+  * `cuda_graphs=True` replays an iteration as ONE CUDA graph (~2300 kernel launches of the plain iteration; one
+    graph per (input shape, lazy R1, lazy path length, wrong-order) variant, captured the second time the variant
+    occurs).  Host-side random decisions stay on the host and enter the graph through device scalars: the
+    style-mixing crossover index (misc.py:244-252 + multi_stylegan_generator.py:162-169) and the wrong-order frame
+    permutation (:268-273).  Iterations the graph cannot express (a CutMix draw, top-k, fixed latents, the ADA
+    wrapper's per-call host decisions) run eagerly on the same parameters and optimiser state.
 """
 import copy
 import random
+from types import SimpleNamespace
 from typing import Any, Callable, Dict, Iterable, Optional
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -40,7 +48,8 @@ class ModelWrapper(object):
                  generator_ema: Optional[nn.Module] = None,
                  device: str = "cuda",
                  process_group=None,
-                 allow_tf32_matmul: bool = True) -> None:
+                 allow_tf32_matmul: bool = True,
+                 cuda_graphs: bool = False) -> None:
         self.generator, self.discriminator = generator, discriminator
         self.generator_optimizer, self.discriminator_optimizer = generator_optimizer, discriminator_optimizer
         self.training_dataset = training_dataset
@@ -66,6 +75,10 @@ class ModelWrapper(object):
         self.epoch, self.epochs = 0, 1
         self.resume_training = False
         self.top_k: Callable = nn.Identity()
+        self.cuda_graphs = bool(cuda_graphs)
+        self._graphs: Dict[Any, Any] = {}        # variant key -> None (seen once, ran eagerly) | captured state
+        self.graph_replays = 0
+        self.graph_launches = 0                  # kernels of this library replayed from graphs (bench accounting)
 
     # ---- helpers ------------------------------------------------------------------------------------
     def _noise(self, batch: int):
@@ -91,10 +104,92 @@ class ModelWrapper(object):
     # ---- one iteration of _gan_training (model_wrapper.py:253-451) -----------------------------------
     def train_step(self, real_images: torch.Tensor, z_d=None, z_g=None, z_pl=None,
                    pl_noise=None) -> Dict[str, torch.Tensor]:
-        """real_images [B, 2, 3, H, W] on the device.  z_* optionally fix the latent draws (parity tests)."""
+        """real_images [B, 2, 3, H, W] on the device.  z_* optionally fix the latent draws (parity tests).
+        With `cuda_graphs` the returned scalars live in the graph's static memory: read them before the next call."""
+        hp = self.hyperparameters
+        self.iteration += 1
+        lazy_r1 = self.iteration % hp["lazy_discriminator_regularization"] == 0
+        lazy_pl = self.iteration % hp["lazy_generator_regularization"] == 0
+        wrong_order = bool(self.epoch >= hp["wrong_order_start"] * self.epochs or self.resume_training)
+        cut_mix = (random.random() <= ((0.5 / float(self.epochs)) * float(self.epoch))) \
+            or (self.resume_training and random.random() <= 0.5)
+        if self.cuda_graphs and self._graphable(real_images, cut_mix, z_d, z_g, z_pl, pl_noise):
+            return self._train_step_graphed(real_images, lazy_r1, lazy_pl, wrong_order)
+        return self._iteration(real_images, lazy_r1, lazy_pl, wrong_order, cut_mix, z_d, z_g, z_pl, pl_noise)
+
+    # ---- CUDA-graph replay of one iteration ----------------------------------------------------------
+    def _graphable(self, real_images, cut_mix, *fixed) -> bool:
+        return (real_images.is_cuda and not cut_mix and all(f is None for f in fixed)
+                and isinstance(self.top_k, nn.Identity)
+                and getattr(self.discriminator, "graph_capturable", True)
+                and getattr(self.generator, "graph_capturable", True))
+
+    def _draw_inject_index(self) -> int:
+        """The host half of misc.get_noise + Generator._latent: a crossover index in [1, n_latent - 2] with probability
+        p_mixed_noise, otherwise n_latent (= every layer takes the first latent, i.e. no mixing)."""
+        n_latent = self.generator.n_latent
+        p = self.hyperparameters["p_mixed_noise"]
+        if (p > 0) and (random.random() < p):
+            return int(np.random.randint(1, n_latent - 1))
+        return n_latent
+
+    def _train_step_graphed(self, real_images, lazy_r1, lazy_pl, wrong_order) -> Dict[str, torch.Tensor]:
+        from . import _C
+        key = (tuple(real_images.shape), real_images.dtype, lazy_r1, lazy_pl, wrong_order)
+        if key not in self._graphs:
+            # first occurrence: eager, which also creates optimiser state, running means and kernel attributes
+            self._graphs[key] = None
+            inject = torch.tensor([self._draw_inject_index() for _ in range(3 if lazy_pl else 2)] + [0] * (0 if lazy_pl else 1),
+                                  dtype=torch.int64).to(real_images.device)
+            return self._iteration(real_images, lazy_r1, lazy_pl, wrong_order, False, None, None, None, None,
+                                   inject=inject)
+        st = self._graphs[key]
+        if st is None:
+            for opt in (self.generator_optimizer, self.discriminator_optimizer):
+                if not all(g.get("capturable", False) for g in opt.param_groups):
+                    raise RuntimeError("cuda_graphs=True needs optimisers constructed with capturable=True")
+            st = SimpleNamespace()
+            st.real = real_images.detach().clone()
+            st.inject = torch.zeros(3, dtype=torch.int64, device=real_images.device)
+            st.perm = torch.arange(real_images.shape[2], dtype=torch.int64, device=real_images.device)
+            plr = self.path_length_regularization
+            st.mean_path_length = plr.mean_path_length.detach().to(real_images.device).clone()
+            torch.cuda.synchronize(real_images.device)
+            launches0 = _C.launch_count()
+            st.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(st.graph):
+                plr.mean_path_length = st.mean_path_length
+                st.out = self._iteration(st.real, lazy_r1, lazy_pl, wrong_order, False, None, None, None, None,
+                                         inject=st.inject, perm=st.perm)
+                if lazy_pl:      # the running mean is rebound by the loss module; keep it in the graph's static slot
+                    st.mean_path_length.copy_(plr.mean_path_length.detach())
+            st.launches = _C.launch_count() - launches0
+            self._graphs[key] = st
+        # per-replay host decisions -> device scalars (fill kernels take the value as a launch argument: no host buffer)
+        for i in range(3 if lazy_pl else 2):
+            st.inject[i].fill_(self._draw_inject_index())
+        if wrong_order:
+            from . import misc as _misc
+            for i, v in enumerate(_misc.random_permutation(real_images.shape[2]).tolist()):
+                st.perm[i].fill_(int(v))
+        st.real.copy_(real_images, non_blocking=True)
+        st.graph.replay()
+        self.path_length_regularization.mean_path_length = st.mean_path_length
+        self.graph_replays += 1
+        self.graph_launches += st.launches
+        return dict(st.out)
+
+    def _generate(self, batch: int, z, inject, slot: int, **kw):
+        if z is None and inject is not None:
+            # graph form of the mixed-noise draw: both latents always, crossover index from the device
+            z2 = torch.randn(2, batch, self.latent_dimensions, dtype=torch.float32, device=self.device)
+            return self.generator(input=list(z2.unbind(0)), inject_index=inject[slot], **kw)
+        return self.generator(input=self._noise(batch) if z is None else z, **kw)
+
+    def _iteration(self, real_images, lazy_r1, lazy_pl, wrong_order, cut_mix, z_d, z_g, z_pl, pl_noise,
+                   inject=None, perm=None) -> Dict[str, torch.Tensor]:
         hp = self.hyperparameters
         out: Dict[str, torch.Tensor] = {}
-        self.iteration += 1
         B = real_images.shape[0]
         g_params = [p for p in self.generator.parameters()]
         d_params = self._d_params()
@@ -102,10 +197,11 @@ class ModelWrapper(object):
         # ---------------- discriminator step (:258-305) ----------------
         self._zero()
         with torch.no_grad():
-            fake_images = self.generator(input=self._noise(B) if z_d is None else z_d)
-        if self.epoch >= hp["wrong_order_start"] * self.epochs or self.resume_training:
+            fake_images = self._generate(B, z_d, inject, 0)
+        if wrong_order:
             n = max(1, int(hp["batch_factor_wrong_order"] * B))
-            fake_images = torch.cat([fake_images, real_images[:n, :, misc.random_permutation(real_images.shape[2])]], 0)
+            order = misc.random_permutation(real_images.shape[2]) if perm is None else perm
+            fake_images = torch.cat([fake_images, real_images[:n, :, order]], 0)
         pair = getattr(self.discriminator, "forward_pair", None)
         if pair is not None and fake_images.shape == real_images.shape:
             # the reference's two calls (:279-283) as one batched pass with identical results (see forward_pair)
@@ -122,7 +218,7 @@ class ModelWrapper(object):
                    loss_discriminator_fake_pixel_wise=l_fake_px.detach())
 
         # ---------------- lazy R1 (:307-329) ----------------
-        if self.iteration % hp["lazy_discriminator_regularization"] == 0:
+        if lazy_r1:
             self._zero()
             real_r1 = real_images.detach().requires_grad_(True)
             rp, rp_px = self.discriminator(real_r1, is_real=False, is_cut_mix=True)
@@ -132,8 +228,7 @@ class ModelWrapper(object):
             out["loss_discriminator_regularization"] = r1.detach()
 
         # ---------------- CutMix augmentation + consistency (:331-376) ----------------
-        if (random.random() <= ((0.5 / float(self.epochs)) * float(self.epoch))) \
-                or (self.resume_training and random.random() <= 0.5):
+        if cut_mix:
             self._zero()
             images, label = generate_cut_mix_augmentation_data(real_images, fake_images)
             _, pred = self.discriminator(images, is_cut_mix=True)
@@ -152,7 +247,7 @@ class ModelWrapper(object):
 
         # ---------------- generator step (:377-416) ----------------
         self._zero()
-        fake_images = self.generator(input=self._noise(B) if z_g is None else z_g)
+        fake_images = self._generate(B, z_g, inject, 1)
         # The reference lets autograd compute all discriminator weight gradients here and then discards them
         # (zero_grad of both optimisers precedes the next phase, :260-261,:379-380); they are unobservable, so the
         # discriminator is differentiated w.r.t. its input only.
@@ -176,11 +271,10 @@ class ModelWrapper(object):
         out.update(loss_generator=l_g.detach(), loss_generator_pixel_wise=l_g_px.detach())
 
         # ---------------- lazy path length (:418-444) ----------------
-        if self.iteration % hp["lazy_generator_regularization"] == 0:
+        if lazy_pl:
             self._zero()
             n = max(1, int(hp["batch_size_shrink_path_length_regularization"] * B))
-            grads = self.generator(input=self._noise(n) if z_pl is None else z_pl, return_path_length_grads=True,
-                                   path_length_noise=pl_noise)
+            grads = self._generate(n, z_pl, inject, 2, return_path_length_grads=True, path_length_noise=pl_noise)
             pl_loss, path_length = self.path_length_regularization(grads)
             (hp["w_generator_regularization"] * pl_loss).backward()
             mdist.all_reduce_mean_(self.path_length_regularization.mean_path_length, self.process_group)

@@ -331,11 +331,19 @@ class Generator(nn.Module):
         groups.append({"params": self.style_mapping.parameters(), "lr": lr_style})
         return groups
 
-    def _latent(self, input, input_is_latent: bool, inject_index: Optional[int]) -> torch.Tensor:
-        n_latent = len(self.main_convolutions_1) + 2
+    @property
+    def n_latent(self) -> int:
+        return len(self.main_convolutions_1) + 2
+
+    def _latent(self, input, input_is_latent: bool, inject_index) -> torch.Tensor:
+        n_latent = self.n_latent
         if not input_is_latent:
             if isinstance(input, list):
                 styles = [self.style_mapping(z) for z in input]
+                if torch.is_tensor(inject_index):
+                    # crossover index held on the device (CUDA-graph replay): the same [B, n_latent, L] tensor as below
+                    first = torch.arange(n_latent, device=styles[0].device).view(1, n_latent, 1) < inject_index
+                    return torch.where(first, styles[0].unsqueeze(1), styles[1].unsqueeze(1))
                 if inject_index is None:
                     inject_index = np.random.randint(1, n_latent - 1)
                 return torch.cat((styles[0].unsqueeze(1).repeat(1, inject_index, 1),

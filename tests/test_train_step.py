@@ -195,3 +195,54 @@ def test_late_epoch_branches_host_logic(oracle_backend):
     assert {"loss_cut_mix_augmentation", "loss_cut_mix_regularization", "loss_generator",
             "loss_discriminator_real"} <= seen
     assert any(not torch.equal(before[n], p.detach()) for n, p in D.named_parameters())
+
+
+def test_device_inject_index_matches_host_index(oracle_backend):
+    """Generator._latent with the crossover index as a device scalar (CUDA-graph form) == the reference's int form
+    (multi_stylegan_generator.py:162-169), including the 'no mixing' encoding inject_index = n_latent."""
+    G, _ = build("cpu")
+    z = [torch.randn(3, G.latent_dimensions), torch.randn(3, G.latent_dimensions)]
+    for idx in range(1, G.n_latent - 1):
+        assert torch.equal(G._latent(z, False, idx), G._latent(z, False, torch.tensor(idx)))
+    assert torch.equal(G._latent(z[0], False, None), G._latent(z, False, torch.tensor(G.n_latent)))
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_matches_eager(built_library):
+    """ModelWrapper(cuda_graphs=True): captured + replayed iterations (plain and lazy variants) give the same losses and
+    the same parameters as the eager execution of the same iterations with the same host / device random streams."""
+    import random
+    import numpy as np
+    from multi_stylegan_b200.model_wrapper import ModelWrapper
+    dev = torch.device("cuda:0")
+    hp = _hp()
+    hp["p_mixed_noise"] = 0.6
+    runs = []
+    for graphed in (False, True):
+        G, D = build(dev)
+        opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"], fused=True, capturable=True)
+        opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"], fused=True, capturable=True)
+        mw = ModelWrapper(G, D, opt_g, opt_d, hyperparameters=hp, device=dev, cuda_graphs=True)
+        random.seed(7), np.random.seed(7), torch.manual_seed(7)
+        gen = torch.Generator().manual_seed(11)
+        hist = []
+        for it in range(6):
+            if not graphed:
+                mw._graphs.clear()              # every iteration is a "first occurrence": eager execution
+            real = torch.rand(4, 2, 3, 32, 32, generator=gen).to(dev)
+            hist.append({k: v.detach().clone() for k, v in mw.train_step(real).items()})
+        torch.cuda.synchronize()
+        assert mw.graph_replays == (4 if graphed else 0)
+        if graphed:
+            assert mw.graph_launches > 0
+        runs.append((hist, [p.detach().clone() for p in list(G.parameters()) + list(D.parameters())],
+                     mw.path_length_regularization.mean_path_length.clone()))
+    (h0, p0, m0), (h1, p1, m1) = runs
+    for a, b in zip(h0, h1):
+        assert set(a) == set(b)
+        for k in a:
+            assert torch.allclose(a[k], b[k], rtol=2e-3, atol=1e-5), (k, a[k], b[k])
+    assert "loss_path_length_regularization" in h1[-1] and "loss_discriminator_regularization" in h1[-1]
+    assert torch.allclose(m0, m1, rtol=2e-3)
+    for a, b in zip(p0, p1):
+        assert rel_err(b, a) < 2e-3
