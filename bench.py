@@ -25,6 +25,9 @@ METRIC = "train_step_sequences_per_sec"
 UNIT = "sequences/s"
 
 
+VERBOSE = bool(os.environ.get("MSG_BENCH_VERBOSE"))
+
+
 def workload_config(args, world):
     return {"workload": "full G+D train step (BASELINE config 3): default 512ch/256x256 Multi-StyleGAN generator + "
                         "U-Net discriminator, NS-logistic loss, lazy R1 + path length every 16th iteration, EMA",
@@ -192,6 +195,10 @@ def run_ours(args):
         is_lazy = i < setup and i % 2 == 0
         mw.iteration = lazy_every - 1 if is_lazy else 0      # train_step increments first: iteration 16 runs R1 + PL
         out = mw.train_step(pool[i % len(pool)])
+        if VERBOSE:
+            torch.cuda.synchronize()
+            print("[bench rank %d] warm-up iteration %d done (replays so far: %d)" % (rank, i, mw.graph_replays),
+                  file=sys.stderr, flush=True)
         if is_lazy:
             assert "loss_path_length_regularization" in out and "loss_discriminator_regularization" in out, \
                 "warm-up did not exercise the lazy regularisers"
@@ -238,6 +245,9 @@ def run_ours(args):
         t = torch.tensor([ms], device=dev)
         if world > 1:
             tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        if VERBOSE:
+            print("[bench rank %d] pass e2e=%s profile=%s: %.1f ms/step" % (rank, e2e, profile, ms / args.steps),
+                  file=sys.stderr, flush=True)
         prof = _C.profile_summary() if profile else None
         _C.profile_enable(False)
         mw.cuda_graphs = graphs

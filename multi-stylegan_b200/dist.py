@@ -47,22 +47,27 @@ def broadcast_parameters(modules: Iterable[torch.nn.Module], src: int = 0, group
 
 
 @torch.no_grad()
-def all_reduce_gradients(parameters: Iterable[torch.nn.Parameter], group=None) -> int:
-    """Average gradients across ranks with ONE collective on a flat fp32 buffer.  Parameters that never
-    receive a gradient (the generator's unobservable second branch) are skipped on every rank alike.
-    Returns the number of elements reduced."""
+def all_reduce_tensors(tensors: List[torch.Tensor], group=None) -> int:
+    """Average the given tensors across ranks in place with ONE collective on a flat fp32 buffer; returns the
+    number of elements reduced."""
     ws = world_size(group)
-    if ws == 1:
+    if ws == 1 or not tensors:
         return 0
-    grads: List[torch.Tensor] = [p.grad for p in parameters if p.grad is not None]
-    if not grads:
-        return 0
-    flat = torch._utils._flatten_dense_tensors(grads)
+    flat = torch._utils._flatten_dense_tensors(tensors)
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat.div_(ws)
-    for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+    for g, f in zip(tensors, torch._utils._unflatten_dense_tensors(flat, tensors)):
         g.copy_(f)
     return flat.numel()
+
+
+@torch.no_grad()
+def all_reduce_gradients(parameters: Iterable[torch.nn.Parameter], group=None) -> int:
+    """Average gradients across ranks with ONE collective.  Parameters that never receive a gradient (the
+    generator's unobservable second branch) are skipped on every rank alike."""
+    if world_size(group) == 1:
+        return 0
+    return all_reduce_tensors([p.grad for p in parameters if p.grad is not None], group)
 
 
 @torch.no_grad()

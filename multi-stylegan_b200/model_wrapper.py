@@ -10,7 +10,8 @@ sub-steps and the same lazy-regularisation cadence, restructured for one-process
   * the generator's unobservable second branch (multi_stylegan_generator.py:184,187,189) is not evaluated.
   * `cuda_graphs=True` replays an iteration as ONE CUDA graph (~2300 kernel launches of the plain iteration; one
     graph per (input shape, lazy R1, lazy path length, wrong-order) variant, captured the second time the variant
-    occurs).  Host-side random decisions stay on the host and enter the graph through device scalars: the
+    occurs).  With several ranks the gradient all-reduces are graph breaks: the iteration becomes 2-4 graph segments in
+    one memory pool with the NCCL calls issued eagerly between their replays.  Host-side random decisions stay on the host and enter the graph through device scalars: the
     style-mixing crossover index (misc.py:244-252 + multi_stylegan_generator.py:162-169) and the wrong-order frame
     permutation (:268-273).  Iterations the graph cannot express (a CutMix draw, top-k, fixed latents, the ADA
     wrapper's per-call host decisions) run eagerly on the same parameters and optimiser state.
@@ -77,6 +78,8 @@ class ModelWrapper(object):
         self.top_k: Callable = nn.Identity()
         self.cuda_graphs = bool(cuda_graphs)
         self._graphs: Dict[Any, Any] = {}        # variant key -> None (seen once, ran eagerly) | captured state
+        self._capture = None                     # the program being captured (graph segments + eager collectives)
+        self._always_break = False               # tests: cut the capture at every optimiser step on a single rank too
         self.graph_replays = 0
         self.graph_launches = 0                  # kernels of this library replayed from graphs (bench accounting)
 
@@ -88,10 +91,36 @@ class ModelWrapper(object):
     def _d_params(self):
         return [p for p in self.discriminator.parameters()]
 
-    def _optimize(self, params, optimizer) -> None:
-        mdist.all_reduce_gradients(params, self.process_group)
+    def _optimize(self, params, optimizer, extra=()) -> None:
+        """Cross-rank average of the gradients (and of `extra` state tensors), clip, step.  While an iteration is being
+        captured the collective is a graph break: the capture is cut into segments and the all-reduce is issued eagerly
+        between their replays on the tensors the segments produce (static addresses in the shared graph pool)."""
+        if mdist.world_size(self.process_group) > 1 or self._always_break:
+            prog = self._capture
+            if prog is None:
+                mdist.all_reduce_gradients(params, self.process_group)
+                mdist.all_reduce_tensors(list(extra), self.process_group)
+            else:
+                self._segment_end(prog)
+                tensors = [p.grad for p in params if p.grad is not None] + list(extra)
+                prog.items.append(lambda t=tensors, g=self.process_group: mdist.all_reduce_tensors(t, g))
+                self._segment_begin(prog)
         torch.nn.utils.clip_grad_norm_(params, max_norm=5.)
         optimizer.step()
+
+    @staticmethod
+    def _segment_begin(prog) -> None:
+        graph = torch.cuda.CUDAGraph()
+        ctx = torch.cuda.graph(graph, pool=prog.pool, stream=prog.stream)
+        ctx.__enter__()
+        prog.open = (graph, ctx)
+
+    @staticmethod
+    def _segment_end(prog) -> None:
+        graph, ctx = prog.open
+        ctx.__exit__(None, None, None)
+        prog.items.append(graph)
+        prog.open = None
 
     def _zero(self) -> None:
         self.discriminator_optimizer.zero_grad()
@@ -156,13 +185,20 @@ class ModelWrapper(object):
             st.mean_path_length = plr.mean_path_length.detach().to(real_images.device).clone()
             torch.cuda.synchronize(real_images.device)
             launches0 = _C.launch_count()
-            st.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(st.graph):
+            prog = SimpleNamespace(items=[], pool=torch.cuda.graph_pool_handle(), stream=torch.cuda.Stream(), open=None)
+            self._capture = prog
+            self._segment_begin(prog)
+            try:
                 plr.mean_path_length = st.mean_path_length
                 st.out = self._iteration(st.real, lazy_r1, lazy_pl, wrong_order, False, None, None, None, None,
                                          inject=st.inject, perm=st.perm)
                 if lazy_pl:      # the running mean is rebound by the loss module; keep it in the graph's static slot
                     st.mean_path_length.copy_(plr.mean_path_length.detach())
+            finally:
+                self._capture = None
+                if prog.open is not None:
+                    self._segment_end(prog)
+            st.program = prog.items      # CUDA graphs in capture order (one shared pool), eager collectives in between
             st.launches = _C.launch_count() - launches0
             self._graphs[key] = st
         # per-replay host decisions -> device scalars (fill kernels take the value as a launch argument: no host buffer)
@@ -173,7 +209,11 @@ class ModelWrapper(object):
             for i, v in enumerate(_misc.random_permutation(real_images.shape[2]).tolist()):
                 st.perm[i].fill_(int(v))
         st.real.copy_(real_images, non_blocking=True)
-        st.graph.replay()
+        for item in st.program:
+            if isinstance(item, torch.cuda.CUDAGraph):
+                item.replay()
+            else:
+                item()
         self.path_length_regularization.mean_path_length = st.mean_path_length
         self.graph_replays += 1
         self.graph_launches += st.launches
@@ -277,8 +317,7 @@ class ModelWrapper(object):
             grads = self._generate(n, z_pl, inject, 2, return_path_length_grads=True, path_length_noise=pl_noise)
             pl_loss, path_length = self.path_length_regularization(grads)
             (hp["w_generator_regularization"] * pl_loss).backward()
-            mdist.all_reduce_mean_(self.path_length_regularization.mean_path_length, self.process_group)
-            self._optimize(g_params, self.generator_optimizer)
+            self._optimize(g_params, self.generator_optimizer, extra=[self.path_length_regularization.mean_path_length])
             out.update(path_length=path_length.detach().mean(), loss_path_length_regularization=pl_loss.detach())
 
         # ---------------- EMA (:446) ----------------

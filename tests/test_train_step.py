@@ -208,9 +208,11 @@ def test_device_inject_index_matches_host_index(oracle_backend):
 
 
 @pytest.mark.gpu
-def test_cuda_graph_replay_matches_eager(built_library):
-    """ModelWrapper(cuda_graphs=True): captured + replayed iterations (plain and lazy variants) give the same losses and
-    the same parameters as the eager execution of the same iterations with the same host / device random streams."""
+@pytest.mark.parametrize("segmented", [False, True])
+def test_cuda_graph_replay_matches_eager(built_library, segmented):
+    """ModelWrapper(cuda_graphs=True): captured + replayed iterations (plain and lazy variants; as one graph, and as the
+    multi-rank program of graph segments cut at every gradient all-reduce) give the same losses and the same parameters
+    as the eager execution of the same iterations with the same host / device random streams."""
     import random
     import numpy as np
     from multi_stylegan_b200.model_wrapper import ModelWrapper
@@ -223,6 +225,7 @@ def test_cuda_graph_replay_matches_eager(built_library):
         opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"], fused=True, capturable=True)
         opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"], fused=True, capturable=True)
         mw = ModelWrapper(G, D, opt_g, opt_d, hyperparameters=hp, device=dev, cuda_graphs=True)
+        mw._always_break = segmented            # the multi-rank form: graph segments around the (here no-op) all-reduces
         random.seed(7), np.random.seed(7), torch.manual_seed(7)
         gen = torch.Generator().manual_seed(11)
         hist = []
@@ -235,6 +238,8 @@ def test_cuda_graph_replay_matches_eager(built_library):
         assert mw.graph_replays == (4 if graphed else 0)
         if graphed:
             assert mw.graph_launches > 0
+            n_graphs = {k[2:4]: sum(isinstance(i, torch.cuda.CUDAGraph) for i in st.program) for k, st in mw._graphs.items()}
+            assert n_graphs == ({(False, False): 3, (True, True): 5} if segmented else {(False, False): 1, (True, True): 1})
         runs.append((hist, [p.detach().clone() for p in list(G.parameters()) + list(D.parameters())],
                      mw.path_length_regularization.mean_path_length.clone()))
     (h0, p0, m0), (h1, p1, m1) = runs
