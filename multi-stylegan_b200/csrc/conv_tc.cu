@@ -270,9 +270,40 @@ struct TcPixParams {
   float alpha;
   int w_per_sample;
   int vec_store;               // NHWC output, 16-byte aligned channel runs, N % 4 == 0
-  int tma_store;               // epilogue writes 32-pixel x 32-channel boxes with TMA (no residual operand)
+  int tma_store;               // epilogue writes 32-pixel x 32-channel boxes with TMA
+  int debug;                   // MSG_B200_TC_VARIANT bits 32/64 (timing experiments only): 1 = no stores, 2 = no proxy fence (wrong results)
   Epilogue ep;
 };
+
+// One 32-channel chunk of the TMA-store epilogue: fused transform in registers, then the pixel's 128-byte row goes to
+// the swizzled staging box.  The epilogue warps are one warp per scheduler, so this loop is bound by its instruction
+// count: the three common transforms are compiled select-free (NB = noise/bias term, ACT = leaky ReLU, ADD = residual).
+template <bool NB, bool ACT, bool ADD>
+__device__ __forceinline__ void epi_chunk_to_smem(const float (&rr)[32], const float4 (&av)[8], const float* bias_nb,
+                                                  int nvalid4, float nz, float alpha, float slope, float gain,
+                                                  uint32_t dst, int lane) {
+  const float a2 = (!NB && !ACT && !ADD) ? alpha * gain : alpha;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float v[4] = {rr[4 * j + 0] * a2, rr[4 * j + 1] * a2, rr[4 * j + 2] * a2, rr[4 * j + 3] * a2};
+    if (NB) {
+      float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias_nb != nullptr && j < nvalid4) bz = __ldg(reinterpret_cast<const float4*>(bias_nb) + j);
+      v[0] += nz + bz.x; v[1] += nz + bz.y; v[2] += nz + bz.z; v[3] += nz + bz.w;
+    }
+    if (ACT) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
+    }
+    if (ADD) { v[0] += av[j].x; v[1] += av[j].y; v[2] += av[j].z; v[3] += av[j].w; }
+    if (NB || ACT || ADD) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] *= gain;
+    }
+    const uint32_t a = dst + ((uint32_t)(j ^ (lane & 7)) << 4);
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+  }
+}
 
 // Epilogue of one 128-pixel x BN accumulator (one TMEM lane quarter per warp): TMEM -> registers -> per-warp 32x33
 // shared-memory transpose -> fused output transform -> 128-bit stores (8 lanes cover one pixel's 128 contiguous bytes).
@@ -299,6 +330,8 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
         // residual operand (ResNetBlock / NonLocalBlock join): its 32 x 32 box is fetched by TMA into the second
         // staging buffer while the accumulator chunk is read, so the output uses a single buffer in that mode
         const bool with_add = tm_add != nullptr && p.ep.add != nullptr;
+        const bool has_bias = p.ep.bias != nullptr, has_nb = has_bias || p.ep.noise != nullptr, has_act = p.ep.act != 0;
+        const float ep_alpha = p.alpha, ep_slope = p.ep.slope, ep_gain = p.ep.gain;
         if (with_add && n0 < p.N) {
           __syncwarp();                                     // every lane is done reading the previous tile's box
           if (lane == 0) {
@@ -339,26 +372,26 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
               if (lane == 0) tma_store_wait_read<0>();      // single output buffer in this mode
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) av[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int j = 0; j < 8; ++j) av[j] = make_float4(0.f, 0.f, 0.f, 0.f);   // (dead in the ADD = false variants)
               if (lane == 0) tma_store_wait_read<1>();      // the box stored two chunks ago has left this buffer
             }
             __syncwarp();
             const uint32_t dst = stage_smem + buf * 4096 + lane * 128;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.ep.bias && nb + 4 * j < p.N) bz = __ldg(reinterpret_cast<const float4*>(p.ep.bias + nb) + j);
-              float4 o;
-              o.x = apply_epilogue(p.ep, p.alpha * rr[4 * j + 0], bz.x, nz, av[j].x);
-              o.y = apply_epilogue(p.ep, p.alpha * rr[4 * j + 1], bz.y, nz, av[j].y);
-              o.z = apply_epilogue(p.ep, p.alpha * rr[4 * j + 2], bz.z, nz, av[j].z);
-              o.w = apply_epilogue(p.ep, p.alpha * rr[4 * j + 3], bz.w, nz, av[j].w);
-              const uint32_t a = dst + ((uint32_t)(j ^ (lane & 7)) << 4);
-              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
-            }
-            fence_proxy_async_smem();
+            const float* bias_nb = has_bias ? p.ep.bias + nb : nullptr;
+            const int nvalid4 = (p.N - nb + 3) >> 2;
+            if (!has_nb && !has_act && !with_add)
+              epi_chunk_to_smem<false, false, false>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
+            else if (has_nb && has_act && !with_add)
+              epi_chunk_to_smem<true, true, false>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
+            else if (!has_nb && !has_act && with_add)
+              epi_chunk_to_smem<false, false, true>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
+            else if (has_act)
+              epi_chunk_to_smem<true, true, true>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
+            else
+              epi_chunk_to_smem<true, false, true>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
+            if (!(p.debug & 2)) fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && !(p.debug & 1)) {
               tma_store_4d(tm_out, stage_smem + buf * 4096, nb, bx, by, b);
               tma_store_commit();
             }
@@ -1175,6 +1208,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
       ok = al16(p.ep.add + view_off) &&
            make_tmap(&tmAdd, p.ep.add + view_off, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) == MSG_OK;
     p.tma_store = ok ? 1 : 0;
+    p.debug = (int)((tc_variant() >> 5) & 3u);
   }
   cudaEvent_t pstop;
   const int pslot = prof_begin(0, g.ntaps, g.Cr, g.N, (int64_t)g.B * g.PH * g.PW,
