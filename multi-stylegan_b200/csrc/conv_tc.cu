@@ -557,56 +557,63 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
   const int kiters = p.ntaps * p.cchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int r = tile;
-        const int nt = r % p.n_tiles; r /= p.n_tiles;
-        const int tx = r % p.tiles_x; r /= p.tiles_x;
-        const int ty = r % p.tiles_y;
-        const int b = r / p.tiles_y;
-        const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN;
-        const int bw = p.w_per_sample ? b : 0;
-        for (int k = 0; k < kiters; ++k, ++it) {
-          const uint32_t s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
+    // producer: the whole warp runs the loop converged (tile / tap / chunk counters stay in uniform registers, no
+    // division per k-iteration) and one elected lane issues the two bulk tensor loads of a stage
+    uint32_t s = 0, ph = 0;
+    const int cpp = p.chunks_per_phase;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int nt = r % p.n_tiles; r /= p.n_tiles;
+      const int tx = r % p.tiles_x; r /= p.tiles_x;
+      const int ty = r % p.tiles_y;
+      const int b = r / p.tiles_y;
+      const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN;
+      const int bw = p.w_per_sample ? b : 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int xx = x0 + p.tap_dx[t], yy = y0 + p.tap_dy[t];
+        int view = 0, ca = 0;
+        for (int cc = 0; cc < p.cchunks; ++cc) {
           mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u);
-          const int t = k / p.cchunks;
-          const int cc = k - t * p.cchunks;
-          int view = 0, ca = cc;
-          if (p.chunks_per_phase) { view = cc / p.chunks_per_phase; ca = cc - view * p.chunks_per_phase; }
-          const uint32_t full = bars + 8 * s;
-          mbar_expect_tx(full, A_BYTES + B_BYTES);
-          tma_load_4d(sA + s * A_BYTES, &tmAs.m[view], full, ca * 32, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b);
-          tma_load_4d(sB + s * B_BYTES, &tmB, full, cc * 32, n0, t, bw);
+          if (elect_one()) {
+            const uint32_t full = bars + 8 * s;
+            mbar_expect_tx(full, A_BYTES + B_BYTES);
+            tma_load_4d(sA + s * A_BYTES, &tmAs.m[view], full, ca * 32, xx, yy, b);
+            tma_load_4d(sB + s * B_BYTES, &tmB, full, cc * 32, n0, t, bw);
+          }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+          if (++ca == cpp) { ca = 0; ++view; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t it = 0, lt = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
-        const uint32_t a = lt & 1u;
-        mbar_wait(acc_empty + 8 * a, ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
+    // MMA issuer: converged warp, one elected lane issues the four K = 8 MMAs of a stage and the commits
+    constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(SWZ_128B & 7) << 61);
+    uint32_t s = 0, ph = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t a = lt & 1u;
+      mbar_wait(acc_empty + 8 * a, ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + a * ACC_COLS;
+      for (int k = 0; k < kiters; ++k) {
+        mbar_wait(bars + 8 * s, ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + a * ACC_COLS;
-        for (int k = 0; k < kiters; ++k, ++it) {
-          const uint32_t s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
-          mbar_wait(bars + 8 * s, ph);
-          tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a_lo = ((sA + s * A_BYTES) >> 4) & 0x3FFF, b_lo = ((sB + s * B_BYTES) >> 4) & 0x3FFF;
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t bd = make_smem_desc(sB + s * B_BYTES + kk * 32, 0, 1024, SWZ_128B);
+            const uint64_t bd = DESC_HI | (uint64_t)(b_lo + kk * 2);
 #pragma unroll
             for (int sub = 0; sub < MT; ++sub) {
-              const uint64_t ad = make_smem_desc(sA + s * A_BYTES + sub * (128 * 32 * 4) + kk * 32, 0, 1024, SWZ_128B);
+              const uint64_t ad = DESC_HI | (uint64_t)(a_lo + sub * (128 * 32 * 4 / 16) + kk * 2);
               mma_tf32(d_tmem + sub * BN, ad, bd, IDESC, (k > 0 || kk > 0) ? 1u : 0u);
             }
           }
           mma_commit(bars + 8 * (STAGES + s));  // smem stage reusable once these MMAs retire
+          if (k == kiters - 1) mma_commit(acc_full + 8 * a);
         }
-        mma_commit(acc_full + 8 * a);
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else {

@@ -52,6 +52,18 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, bool so
   return true;
 }
 
+// One lane of a converged warp (the same lane every time).  Loops that issue TMA / tcgen05 instructions run with the
+// whole warp converged and elect around the issue, so that addresses and descriptors stay in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
