@@ -1028,6 +1028,19 @@ static int pick_bn(int n, int min_bn) {
   return bn < min_bn ? min_bn : bn;
 }
 
+// Column tile for a PixGemm: the widest tile the channel count allows, narrowed (down to 64) while the whole problem
+// still fits in one wave of CTAs — small-pixel layers (4x4 ... 16x16 images, per-sample weights) otherwise leave most of
+// the machine idle while a few CTAs walk the whole K loop.
+static int pick_bn_pix(const PixGemm& g) {
+  int bn = pick_bn(g.N, 16);
+  int wt_log2 = ilog2_ceil(g.PW);
+  if (wt_log2 > 7) wt_log2 = 7;
+  const int Wt = 1 << wt_log2, Ht = 128 >> wt_log2;
+  const int64_t ptiles = ceil_div(g.PW, Wt) * ceil_div(g.PH, Ht) * (int64_t)g.B;
+  while (bn > 64 && ptiles * ceil_div(g.N, bn / 2) <= num_sms()) bn /= 2;
+  return bn;
+}
+
 static bool view_tma_ok(const void* base, const View4& v) {
   return al16(base) && v.sc == 1 && (v.sx % 4 == 0) && (v.sy % 4 == 0) && (v.sb % 4 == 0);
 }
@@ -1048,7 +1061,7 @@ bool tc_pixgemm_supported(const PixGemm& g) {
 }
 
 size_t tc_pixgemm_workspace(const PixGemm& g) {
-  const int BN = pick_bn(g.N, 16);
+  const int BN = pick_bn_pix(g);
   const int64_t Npad = round_up(g.N, BN), Cpad = round_up(g.Cr, 32);
   const int64_t BW = g.w_sb != 0 ? g.B : 1;
   return (size_t)(BW * g.ntaps * Npad * Cpad) * sizeof(float) + 256;
@@ -1123,7 +1136,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   const size_t need = tc_pixgemm_workspace(g);
   if (!ws || ws_bytes < need) return fail(MSG_ERR_WORKSPACE, "conv pixgemm(tcgen05): workspace %zu < %zu", ws_bytes, need);
   float* wt = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  const int BN = pick_bn(g.N, 16);
+  const int BN = pick_bn_pix(g);
   const int Npad = round_up(g.N, BN), Cpad = round_up(g.Cr, 32);
   const int BW = g.w_sb != 0 ? g.B : 1;
 
