@@ -175,6 +175,13 @@ size_t msg_conv2d_workspace(const msg_conv_desc* d, int which /*0 fwd,1 dgrad,2 
 int msg_conv2d_forward_fused(float* y, const float* x, const float* w, const msg_conv_desc* d,
                              float alpha, const msg_conv_epilogue* epilogue, void* workspace,
                              size_t workspace_bytes, int flags, msg_stream_t stream);
+/* y = epilogue(alpha * conv([x1 | x2], w)): the channel concatenation of two NHWC tensors (c1 and C - c1 channels,
+ * both multiples of 32) is read in place by the K loop — replaces torch.cat + conv at
+ * u_net_2d_discriminator.py:137,174-186.  tcgen05 engine, stride 1 only; workspace = msg_conv2d_workspace(d, 0, flags).
+ * MSG_ERR_UNSUPPORTED otherwise (the caller concatenates and uses msg_conv2d_forward_fused). */
+int msg_conv2d_forward_cat2(float* y, const float* x1, int c1, const float* x2, const float* w,
+                            const msg_conv_desc* d, float alpha, const msg_conv_epilogue* epilogue,
+                            void* workspace, size_t workspace_bytes, int flags, msg_stream_t stream);
 int msg_conv2d_forward(float* y, const float* x, const float* w, const msg_conv_desc* d,
                        float alpha, void* workspace, size_t workspace_bytes, int flags,
                        msg_stream_t stream);

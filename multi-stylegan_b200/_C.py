@@ -302,14 +302,23 @@ def _w_dims(w: torch.Tensor, B: int, w_transposed: bool = False):
 def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha: float = 1.0,
                    bias: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                    noise_w: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None, act: bool = False,
-                   slope: float = 0.2, gain: float = 1.0, w_transposed: bool = False) -> torch.Tensor:
+                   slope: float = 0.2, gain: float = 1.0, w_transposed: bool = False,
+                   x2: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = epilogue(alpha * conv(x, w)); the optional epilogue (noise, bias, leaky ReLU, residual add, gain) runs
-    inside the conv kernel (msg_conv_epilogue, include/msg_b200.h)."""
+    inside the conv kernel (msg_conv_epilogue, include/msg_b200.h).  With `x2` the convolution is applied to the channel
+    concatenation [x | x2] without materialising it (msg_conv2d_forward_cat2; see cat2_supported)."""
     _check_f32(x, "x")
     _check_f32(w, "w")
     x, layout = _act(x)
     w = _aligned(w)
-    B, C, H, W = x.shape
+    c1 = x.shape[1]
+    if x2 is not None:
+        _check_f32(x2, "x2")
+        x2, layout2 = _act(x2)
+        if layout2 != layout or x2.shape[0] != x.shape[0] or x2.shape[2:] != x.shape[2:]:
+            raise RuntimeError("conv2d: x and x2 must share batch, spatial size and memory format")
+    B, _, H, W = x.shape
+    C = c1 + (x2.shape[1] if x2 is not None else 0)
     per_sample, O, Cw, kh, kw = _w_dims(w, B, w_transposed)
     if Cw != C:
         raise RuntimeError("conv2d: weight has %d input channels, input has %d" % (Cw, C))
@@ -351,12 +360,25 @@ def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha:
     with _on_device(x.device):
         nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 0, conv_flags)
         ws, wsp = _workspace(nbytes, x.device)
-        rc = L.msg_conv2d_forward_fused(_ptr(y), _ptr(x), _ptr(w), ctypes.byref(d), float(alpha),
-                                        ctypes.byref(ep) if ep is not None else None, wsp, nbytes, conv_flags,
-                                        _stream(x))
+        if x2 is None:
+            rc = L.msg_conv2d_forward_fused(_ptr(y), _ptr(x), _ptr(w), ctypes.byref(d), float(alpha),
+                                            ctypes.byref(ep) if ep is not None else None, wsp, nbytes, conv_flags,
+                                            _stream(x))
+        else:
+            rc = L.msg_conv2d_forward_cat2(_ptr(y), _ptr(x), int(c1), _ptr(x2), _ptr(w), ctypes.byref(d), float(alpha),
+                                           ctypes.byref(ep) if ep is not None else None, wsp, nbytes, conv_flags,
+                                           _stream(x))
     _lib.check(rc, "conv2d_forward")
     del keep
     return y
+
+
+def cat2_supported(x: torch.Tensor, x2: torch.Tensor, stride=1) -> bool:
+    """Whether conv2d_forward(x, w, x2=x2) can read the concatenation in place (msg_conv2d_forward_cat2): tcgen05
+    engine, channels-last CUDA tensors, stride 1, both channel counts multiples of 32."""
+    s = stride if isinstance(stride, int) else stride[0]
+    return (conv_channels_last and conv_flags != _lib.CONV_FORCE_SIMT and x.is_cuda and x2.is_cuda and s == 1
+            and x.shape[1] % 32 == 0 and x2.shape[1] % 32 == 0 and x.dtype == torch.float32 and x2.dtype == torch.float32)
 
 
 def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Sequence[int], stride=1, padding=0,

@@ -94,6 +94,9 @@ _SIGNATURES = {
                                       _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
     "msg_conv2d_forward_fused": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc), _c.c_float,
                                             _c.POINTER(ConvEpilogue), _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
+    "msg_conv2d_forward_cat2": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                           _c.POINTER(ConvDesc), _c.c_float, _c.POINTER(ConvEpilogue), _c.c_void_p,
+                                           _c.c_size_t, _c.c_int, _c.c_void_p]),
     "msg_conv2d_dgrad": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc), _c.c_float,
                                     _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
     "msg_conv2d_wgrad": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc), _c.c_float,

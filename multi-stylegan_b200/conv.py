@@ -24,6 +24,39 @@ def _khw(w: torch.Tensor):
     return tuple(w.shape[-2:])
 
 
+def _cat2_backward(g, x, x2, w, stride, padding, alpha, need_x, need_x2, need_w):
+    """Gradients of conv([x | x2], w) w.r.t. x, x2 and w from the gradient g of the (pre-epilogue) convolution output:
+    two dgrads against the two channel slices of the filter and two wgrads, all differentiable."""
+    c1 = x.shape[1]
+    dx = dx2 = dw = None
+    if need_x:
+        dx = _ConvDgrad.apply(g, w[:, :c1], tuple(x.shape[2:]), stride, padding, alpha)
+    if need_x2:
+        dx2 = _ConvDgrad.apply(g, w[:, c1:], tuple(x2.shape[2:]), stride, padding, alpha)
+    if need_w:
+        dw = torch.cat([_ConvWgrad.apply(g, x, _khw(w), stride, padding, False, alpha),
+                        _ConvWgrad.apply(g, x2, _khw(w), stride, padding, False, alpha)], dim=1)
+    return dx, dx2, dw
+
+
+class _ConvForward2(Function):
+    """alpha * conv([x | x2], w) with the concatenation read in place by the kernel's K loop (shared 4-D filters)."""
+
+    @staticmethod
+    def forward(ctx, x, x2, w, stride, padding, alpha):
+        ctx.save_for_backward(x, x2, w)
+        ctx.stride, ctx.padding, ctx.alpha = stride, padding, alpha
+        return _C.conv2d_forward(x, w, stride, padding, alpha=alpha, x2=x2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, x2, w = ctx.saved_tensors
+        if _C.conv_channels_last and dy.is_cuda:
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dx, dx2, dw = _cat2_backward(dy, x, x2, w, ctx.stride, ctx.padding, ctx.alpha, *ctx.needs_input_grad[:3])
+        return dx, dx2, dw, None, None, None
+
+
 class _ConvForward(Function):
     """`wt`: the filter tensor stores its two channel dimensions transposed ([C, O, kh, kw], the layout of
     conv_transpose2d's weight); every kernel reads / writes that layout in place."""
@@ -92,36 +125,43 @@ class _ConvBiasAct(Function):
     op_static/fused_act.py, then dgrad / wgrad), so gradients of any order exist."""
 
     @staticmethod
-    def forward(ctx, x, w, noise, noise_w, bias, stride, padding, slope, gain, alpha):
+    def forward(ctx, x, w, noise, noise_w, bias, stride, padding, slope, gain, alpha, x2=None):
         out = _C.conv2d_forward(x, w, stride, padding, alpha=alpha, bias=bias, noise=noise, noise_w=noise_w, act=True,
-                                slope=slope, gain=gain)
-        ctx.save_for_backward(x, w, out, noise if noise is not None else x.new_empty(0))
+                                slope=slope, gain=gain, x2=x2)
+        ctx.save_for_backward(x, w, out, noise if noise is not None else x.new_empty(0),
+                              x2 if x2 is not None else x.new_empty(0))
         ctx.has_noise = noise is not None
         ctx.has_bias = bias is not None
+        ctx.has_x2 = x2 is not None
         ctx.stride, ctx.padding, ctx.slope, ctx.gain, ctx.alpha = stride, padding, slope, gain, alpha
         return out
 
     @staticmethod
     def backward(ctx, gout):
         from .op_static.fused_act import NoiseBiasActBackward
-        x, w, out, noise = ctx.saved_tensors
+        x, w, out, noise, x2 = ctx.saved_tensors
         noise = noise if ctx.has_noise else None
         g_pre, g_bias, g_noise_w = NoiseBiasActBackward.apply(gout, out, noise, ctx.slope, ctx.gain)
-        dx = dw = None
-        if ctx.needs_input_grad[0]:
-            dx = _ConvDgrad.apply(g_pre, w, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
-        if ctx.needs_input_grad[1]:
-            dw = _ConvWgrad.apply(g_pre, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha)
+        dx = dw = dx2 = None
+        if ctx.has_x2:
+            dx, dx2, dw = _cat2_backward(g_pre, x, x2, w, ctx.stride, ctx.padding, ctx.alpha, ctx.needs_input_grad[0],
+                                         ctx.needs_input_grad[10], ctx.needs_input_grad[1])
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = _ConvDgrad.apply(g_pre, w, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
+            if ctx.needs_input_grad[1]:
+                dw = _ConvWgrad.apply(g_pre, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha)
         return (dx, dw, None, g_noise_w if ctx.has_noise else None, g_bias if ctx.has_bias else None,
-                None, None, None, None, None)
+                None, None, None, None, None, dx2)
 
 
 def conv2d_bias_act(x: torch.Tensor, w: torch.Tensor, bias=None, noise=None, noise_w=None, stride=1, padding=0,
-                    negative_slope: float = 0.2, gain: float = 1.0, alpha: float = 1.0) -> torch.Tensor:
+                    negative_slope: float = 0.2, gain: float = 1.0, alpha: float = 1.0, x2=None) -> torch.Tensor:
     """Fused alpha * conv -> (+ noise_w * noise) -> (+ bias[c]) -> leaky ReLU -> * gain (channel count must be a
-    multiple of 4 for the channels-last activation-backward kernel)."""
+    multiple of 4 for the channels-last activation-backward kernel).  `x2`: convolve the channel concatenation
+    [x | x2] in place (shared filters; _C.cat2_supported)."""
     return _ConvBiasAct.apply(x, w, noise, noise_w, bias, _pair(stride), _pair(padding), negative_slope, gain,
-                              float(alpha))
+                              float(alpha), x2)
 
 
 class _ConvAddScale(Function):
@@ -129,30 +169,37 @@ class _ConvAddScale(Function):
     (u_net_2d_discriminator.py:186,381) inside the conv epilogue."""
 
     @staticmethod
-    def forward(ctx, x, w, other, stride, padding, gain, alpha):
-        ctx.save_for_backward(x, w)
+    def forward(ctx, x, w, other, stride, padding, gain, alpha, x2=None):
+        ctx.save_for_backward(x, w, x2 if x2 is not None else x.new_empty(0))
+        ctx.has_x2 = x2 is not None
         ctx.stride, ctx.padding, ctx.gain, ctx.alpha = stride, padding, gain, alpha
-        return _C.conv2d_forward(x, w, stride, padding, alpha=alpha, add=other, gain=gain)
+        return _C.conv2d_forward(x, w, stride, padding, alpha=alpha, add=other, gain=gain, x2=x2)
 
     @staticmethod
     def backward(ctx, gout):
-        x, w = ctx.saved_tensors
+        x, w, x2 = ctx.saved_tensors
         g = gout * ctx.gain
-        dx = dw = None
-        if ctx.needs_input_grad[0]:
-            dx = _ConvDgrad.apply(g, w, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
-        if ctx.needs_input_grad[1]:
-            dw = _ConvWgrad.apply(g, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha)
-        return dx, dw, (g if ctx.needs_input_grad[2] else None), None, None, None, None
+        dx = dw = dx2 = None
+        if ctx.has_x2:
+            dx, dx2, dw = _cat2_backward(g, x, x2, w, ctx.stride, ctx.padding, ctx.alpha, ctx.needs_input_grad[0],
+                                         ctx.needs_input_grad[7], ctx.needs_input_grad[1])
+        else:
+            if ctx.needs_input_grad[0]:
+                dx = _ConvDgrad.apply(g, w, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
+            if ctx.needs_input_grad[1]:
+                dw = _ConvWgrad.apply(g, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha)
+        return dx, dw, (g if ctx.needs_input_grad[2] else None), None, None, None, None, dx2
 
 
 def conv2d_add_scale(x: torch.Tensor, w: torch.Tensor, other: torch.Tensor, stride=1, padding=0,
-                     gain: float = 1.0, alpha: float = 1.0) -> torch.Tensor:
-    return _ConvAddScale.apply(x, w, other, _pair(stride), _pair(padding), gain, float(alpha))
+                     gain: float = 1.0, alpha: float = 1.0, x2=None) -> torch.Tensor:
+    return _ConvAddScale.apply(x, w, other, _pair(stride), _pair(padding), gain, float(alpha), x2)
 
 
-def conv2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha: float = 1.0) -> torch.Tensor:
-    """alpha * conv(x, w); x [B,C,H,W]; w [O,C,kh,kw] or [B,O,C,kh,kw]."""
+def conv2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha: float = 1.0, x2=None) -> torch.Tensor:
+    """alpha * conv(x, w); x [B,C,H,W]; w [O,C,kh,kw] or [B,O,C,kh,kw].  `x2`: convolve [x | x2] (see conv2d_bias_act)."""
+    if x2 is not None:
+        return _ConvForward2.apply(x, x2, w, _pair(stride), _pair(padding), float(alpha))
     return _ConvForward.apply(x, w, _pair(stride), _pair(padding), float(alpha))
 
 

@@ -505,6 +505,40 @@ extern "C" int msg_conv2d_forward_fused(float* y, const float* x, const float* w
   return tc_pixgemm(pl.g, ws + pl.off_eng, r256(tc_pixgemm_workspace(pl.g)), st);
 }
 
+// Convolution of the channel concatenation [x1 | x2] without materialising it (the U-Net decoder's
+// torch.cat([upsampled, skip], dim=1) followed by a ResNetBlock, u_net_2d_discriminator.py:137,174-186): the K loop of
+// the implicit GEMM takes its first c1 / 32 chunks from x1 and the rest from x2.
+extern "C" int msg_conv2d_forward_cat2(float* y, const float* x1, int c1, const float* x2, const float* w,
+                                       const msg_conv_desc* d, float alpha, const msg_conv_epilogue* ep, void* workspace,
+                                       size_t workspace_bytes, int flags, msg_stream_t stream) {
+  int rc = check_desc(d, "conv2d_forward_cat2");
+  if (rc) return rc;
+  if (d->B == 0) return MSG_OK;
+  if (!y || !x1 || !x2 || !w) return fail(MSG_ERR_BAD_ARG, "conv2d_forward_cat2: null pointer");
+  const int c2 = d->C - c1;
+  if (c1 <= 0 || c2 <= 0) return fail(MSG_ERR_BAD_ARG, "conv2d_forward_cat2: c1 = %d of C = %d", c1, d->C);
+  if (ep) {
+    if (ep->noise && !ep->noise_w) return fail(MSG_ERR_BAD_ARG, "conv2d_forward_cat2: noise epilogue needs noise_w");
+    if (ep->act != 0 && ep->act != 1) return fail(MSG_ERR_BAD_ARG, "conv2d_forward_cat2: epilogue act must be 0 or 1");
+  }
+  if (d->layout != MSG_LAYOUT_NHWC || d->stride_h != 1 || c1 % 32 != 0 || c2 % 32 != 0 || !al16(x1) || !al16(x2) ||
+      flags == MSG_CONV_FORCE_SIMT || !tc_available())
+    return fail(MSG_ERR_UNSUPPORTED, "conv2d_forward_cat2: needs the tcgen05 engine, NHWC, stride 1 and channel counts "
+                                     "that are multiples of 32 (got %d + %d)", c1, c2);
+  cudaStream_t st = (cudaStream_t)stream;
+  FwdPlan pl = plan_forward(d, x1, w, y, alpha, flags, ep);
+  if (!pl.tc || pl.pad_in || pl.s2d) return fail(MSG_ERR_UNSUPPORTED, "conv2d_forward_cat2: shape not eligible");
+  if (!workspace || workspace_bytes < pl.total)
+    return fail(MSG_ERR_WORKSPACE, "conv2d_forward_cat2: workspace %zu < %zu", workspace_bytes, pl.total);
+  pl.g.nsrc = 2;
+  pl.g.in_src[0] = x1; pl.g.in_src[1] = x2;
+  pl.g.C_src[0] = c1; pl.g.C_src[1] = c2;
+  if (!tc_pixgemm_supported(pl.g)) return fail(MSG_ERR_UNSUPPORTED, "conv2d_forward_cat2: shape not eligible");
+  uint8_t* ws = ws_base(workspace);
+  g_last_engine = 2;
+  return tc_pixgemm(pl.g, ws + pl.off_eng, r256(tc_pixgemm_workspace(pl.g)), st);
+}
+
 extern "C" int msg_conv2d_dgrad(float* dx, const float* dy, const float* w, const msg_conv_desc* d, float alpha,
                                 void* workspace, size_t workspace_bytes, int flags, msg_stream_t stream) {
   int rc = check_desc(d, "conv2d_dgrad");

@@ -59,6 +59,11 @@ struct PixGemm {
   int nphase;
   const float* in_ph[4];
   int IH_ph[4], IW_ph[4];
+  // tcgen05 engine, channel concatenation without a copy (U-Net decoder, u_net_2d_discriminator.py:137): nsrc == 2 reads
+  // the K chunks [0, C_src[0] / 32) from the dense NHWC tensor in_src[0] and the remaining ones from in_src[1].
+  int nsrc;
+  const float* in_src[2];
+  int C_src[2];
   const float* w;         // w(b,n,c,t) = w[b*w_sb + n*w_sn + c*w_sc + t*w_st]
   int64_t w_sb, w_sn, w_sc, w_st;
   int N;

@@ -259,7 +259,7 @@ struct TMapSet { CUtensorMap m[4]; };   // activation views (one per stride-2 in
 
 struct TcPixParams {
   int ntaps, cchunks;
-  int chunks_per_phase;         // > 0: K chunk cc reads activation view cc / chunks_per_phase (stride-2 phases)
+  int cpv[4];                   // K chunks served by activation view 0..3 in turn (stride-2 phases, concatenated sources)
   int tap_dy[kMaxTaps], tap_dx[kMaxTaps];
   int PH, PW, N;
   int wt_log2, tiles_x, tiles_y, n_tiles;   // tile = (1 << wt_log2) x (128 >> wt_log2) pixels
@@ -560,7 +560,6 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
     // producer: the whole warp runs the loop converged (tile / tap / chunk counters stay in uniform registers, no
     // division per k-iteration) and one elected lane issues the two bulk tensor loads of a stage
     uint32_t s = 0, ph = 0;
-    const int cpp = p.chunks_per_phase;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int r = tile;
       const int nt = r % p.n_tiles; r /= p.n_tiles;
@@ -582,7 +581,7 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
           }
           __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1u; }
-          if (++ca == cpp) { ca = 0; ++view; }
+          if (++ca == p.cpv[view]) { ca = 0; ++view; }
         }
       }
     }
@@ -1056,6 +1055,12 @@ bool tc_pixgemm_supported(const PixGemm& g) {
       if (!view_tma_ok(g.in_ph[v], g.is) || g.IH_ph[v] < 1 || g.IW_ph[v] < 1) return false;
     return true;
   }
+  if (g.nsrc != 0) {
+    if (g.nsrc != 2 || g.C_src[0] + g.C_src[1] != g.Cr) return false;
+    for (int v = 0; v < 2; ++v)
+      if (g.C_src[v] <= 0 || g.C_src[v] % 32 != 0 || !al16(g.in_src[v])) return false;
+    return true;
+  }
   if (!view_tma_ok(g.in, g.is)) return false;
   return true;
 }
@@ -1164,16 +1169,18 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   // Measured on B200 (tools/conv_bench.py): no gain over the single-CTA kernel at 256^2 (3.07 vs 3.13 ms — that kernel
   // already runs at the MMA issue rate the power-capped clock allows) and a loss at <= 128^2 (coarser tiles), so the pair
   // kernel is opt-in: MSG_B200_TC_VARIANT=4.
-  const bool pairs = BN == 256 && MT == 1 && (tc_variant() & 4u) && pair_tiles >= num_sms() / 2 && g.nphase == 0;
+  const bool pairs = BN == 256 && MT == 1 && (tc_variant() & 4u) && pair_tiles >= num_sms() / 2 && g.nphase == 0 && g.nsrc == 0;
   TMapSet tmA;
   CUtensorMap tmB;
-  const int nviews = g.nphase > 0 ? g.nphase : 1;
+  const int nviews = g.nphase > 0 ? g.nphase : (g.nsrc == 2 ? 2 : 1);
   for (int v = 0; v < 4; ++v) {
     const int vv = v < nviews ? v : 0;
-    const float* basep = g.nphase > 0 ? g.in_ph[vv] : g.in;
+    const float* basep = g.nphase > 0 ? g.in_ph[vv] : (g.nsrc == 2 ? g.in_src[vv] : g.in);
     const int ih = g.nphase > 0 ? g.IH_ph[vv] : g.IH, iw = g.nphase > 0 ? g.IW_ph[vv] : g.IW;
-    const uint64_t dims[4] = {(uint64_t)(g.Cr / nviews), (uint64_t)iw, (uint64_t)ih, (uint64_t)g.B};
-    const uint64_t strides[3] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4};
+    const int cv = g.nsrc == 2 ? g.C_src[vv] : g.Cr / nviews;
+    const View4 vs = g.nsrc == 2 ? View4{(int64_t)ih * iw * cv, 1, (int64_t)iw * cv, cv} : g.is;
+    const uint64_t dims[4] = {(uint64_t)cv, (uint64_t)iw, (uint64_t)ih, (uint64_t)g.B};
+    const uint64_t strides[3] = {(uint64_t)vs.sx * 4, (uint64_t)vs.sy * 4, (uint64_t)vs.sb * 4};
     const uint32_t box[4] = {32, (uint32_t)Wt, (uint32_t)Ht, 1};
     if (v < nviews) {
       int rc = make_tmap(&tmA.m[v], basep, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -1191,7 +1198,8 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   }
   TcPixParams p{};
   p.ntaps = g.ntaps; p.cchunks = Cpad / 32;
-  p.chunks_per_phase = g.nphase > 0 ? (g.Cr / g.nphase) / 32 : 0;
+  for (int v = 0; v < 4; ++v)
+    p.cpv[v] = g.nphase > 0 ? (g.Cr / g.nphase) / 32 : (g.nsrc == 2 ? (v < 2 ? g.C_src[v] / 32 : 1) : Cpad / 32);
   for (int t = 0; t < g.ntaps; ++t) { p.tap_dy[t] = g.tap_dy[t]; p.tap_dx[t] = g.tap_dx[t]; }
   p.PH = g.PH; p.PW = g.PW; p.N = g.N;
   p.wt_log2 = wt_log2;

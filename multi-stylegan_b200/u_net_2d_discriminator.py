@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import conv, equalized_layer
+from . import _C, conv, equalized_layer
 from .multi_stylegan_generator import _fir_kernel
 from .op_static import FusedLeakyReLU, upfirdn2d
 
@@ -92,11 +92,18 @@ class ResNetBlock(nn.Module):
             in_channels, out_channels, kernel_size=1, stride=1, padding=0, bias=False) \
             if in_channels != out_channels else nn.Identity()
 
-    def forward(self, input: torch.Tensor) -> torch.Tensor:
+    def forward(self, input: torch.Tensor, input_2: torch.Tensor = None) -> torch.Tensor:
+        """`input_2` (an extension used by the U-Net decoder): the block is applied to the channel concatenation
+        [input | input_2] (reference :137) without materialising it — the two convolutions that consume the block input
+        read both tensors through the K loop of the implicit GEMM, and the backward yields the two input gradients as
+        separate dense tensors instead of strided slices of one."""
         c1, a1, c2, a2 = self.main_mapping
         res = self.residual_mapping
         fusable = (c1.weight.shape[0] % 4 == 0 and c1.bias is None and c2.bias is None
                    and isinstance(res, equalized_layer.EqualizedConv2d) and res.bias is None)
+        if input_2 is not None and not (fusable and isinstance(self.mini_batch_std_dev, nn.Identity)
+                                        and _C.cat2_supported(input, input_2, c1.stride)):
+            input, input_2 = torch.cat([input, input_2], dim=1), None
         if not fusable:
             output = self.main_mapping(self.mini_batch_std_dev(input))
             return (output + self.residual_mapping(input)) / math.sqrt(2)
@@ -104,11 +111,11 @@ class ResNetBlock(nn.Module):
         # join run in the conv epilogues (reference :174-186)
         x = self.mini_batch_std_dev(input)
         h = conv.conv2d_bias_act(x, c1.weight, bias=a1.bias, stride=c1.stride, padding=c1.padding,
-                                 negative_slope=a1.negative_slope, gain=a1.scale, alpha=c1.scale)
+                                 negative_slope=a1.negative_slope, gain=a1.scale, alpha=c1.scale, x2=input_2)
         h = conv.conv2d_bias_act(h, c2.weight, bias=a2.bias, stride=c2.stride, padding=c2.padding,
                                  negative_slope=a2.negative_slope, gain=a2.scale, alpha=c2.scale)
         return conv.conv2d_add_scale(input, res.weight, h, stride=res.stride, padding=res.padding,
-                                     gain=1.0 / math.sqrt(2), alpha=res.scale)
+                                     gain=1.0 / math.sqrt(2), alpha=res.scale, x2=input_2)
 
 
 class NonLocalBlock(nn.Module):
@@ -206,7 +213,8 @@ class Discriminator(nn.Module):
             # FIR upsampling (per channel, across pixels) commute exactly, so the convolution runs first, on a quarter
             # of the pixels, and the upsampling on the smaller channel count.
             upsample, conv1x1 = up[0], up[1]
-            x = block(torch.cat([upsample(conv1x1(x)), skip], dim=1))
+            up_x = upsample(conv1x1(x))
+            x = block(up_x, skip) if isinstance(block, ResNetBlock) else block(torch.cat([up_x, skip], dim=1))
         return classification, self.final_mapping(x).unsqueeze(dim=2)
 
 

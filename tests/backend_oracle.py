@@ -27,7 +27,9 @@ def _wt(w, w_transposed):
 
 
 def conv2d_forward(x, w, stride=1, padding=0, alpha=1.0, bias=None, noise=None, noise_w=None, add=None, act=False,
-                   slope=0.2, gain=1.0, w_transposed=False):
+                   slope=0.2, gain=1.0, w_transposed=False, x2=None):
+    if x2 is not None:
+        x = torch.cat([x, x2], dim=1)
     v = ops.conv2d(x, _wt(w, w_transposed), stride, padding) * alpha
     if noise is not None:
         v = v + noise_w * noise

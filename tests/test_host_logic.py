@@ -277,3 +277,31 @@ def test_discriminator_forward_pair_equals_two_calls(oracle_backend):
     for n, p in net.named_parameters():
         assert rel_err(gp[n], p.grad) < 1e-4, n
     assert all(m.groups == 1 for m in net.modules() if isinstance(m, D_mod.MinibatchStdDev))
+
+
+def test_two_source_conv_functions_match_concat(oracle_backend):
+    """conv.conv2d / conv2d_bias_act / conv2d_add_scale with `x2` (the decoder's in-place concatenation): same values and
+    gradients (first and second order) as the same Functions applied to torch.cat([x, x2], 1)."""
+    import torch
+    from multi_stylegan_b200 import conv
+    torch.manual_seed(4)
+    x1 = torch.randn(2, 8, 9, 9, requires_grad=True)
+    x2 = torch.randn(2, 12, 9, 9, requires_grad=True)
+    w = (torch.randn(6, 20, 3, 3) / 13).requires_grad_(True)
+    b = torch.randn(6, requires_grad=True)
+    o = torch.randn(2, 6, 9, 9, requires_grad=True)
+
+    def run(fn):
+        y = fn()
+        gs = torch.autograd.grad((y ** 2).sum(), (x1, x2, w), create_graph=True)
+        gg = torch.autograd.grad(sum((g ** 2).sum() for g in gs), (x1, x2, w))
+        return (y,) + gs + gg
+    cat = lambda: torch.cat([x1, x2], 1)
+    pairs = [(lambda: conv.conv2d(x1, w, padding=1, alpha=0.7, x2=x2), lambda: conv.conv2d(cat(), w, padding=1, alpha=0.7)),
+             (lambda: conv.conv2d_bias_act(x1, w, bias=b, padding=1, gain=1.3, alpha=0.7, x2=x2),
+              lambda: conv.conv2d_bias_act(cat(), w, bias=b, padding=1, gain=1.3, alpha=0.7)),
+             (lambda: conv.conv2d_add_scale(x1, w, o, padding=1, gain=0.6, alpha=0.7, x2=x2),
+              lambda: conv.conv2d_add_scale(cat(), w, o, padding=1, gain=0.6, alpha=0.7))]
+    for two, one in pairs:
+        for a, r in zip(run(two), run(one)):
+            assert a.shape == r.shape and ((a - r).abs().max() / r.abs().max()).item() < 1e-4
