@@ -589,8 +589,9 @@ def noise_bias_act_cl(x: torch.Tensor, ref: Optional[torch.Tensor], noise: Optio
 
 
 def noise_bias_act_cl_bwd(grad_output: torch.Tensor, out: torch.Tensor, noise: Optional[torch.Tensor], alpha: float,
-                          scale: float):
-    """(dx, dbias [C], dnoise_w [1] or None) in one pass + a tiny deterministic reduction."""
+                          scale: float, want_param_grads: bool = True):
+    """(dx, dbias [C], dnoise_w [1] or None) in one pass + a tiny deterministic reduction; with
+    want_param_grads=False only dx (no reduction)."""
     _check_f32(grad_output, "grad_output")
     _check_f32(out, "out")
     g = _cl(grad_output)
@@ -599,17 +600,17 @@ def noise_bias_act_cl_bwd(grad_output: torch.Tensor, out: torch.Tensor, noise: O
     rows = B * H * W
     period = 1
     dnw = None
-    if noise is not None:
+    if noise is not None and want_param_grads:
         noise = _aligned(noise)
         period = noise.numel()
         dnw = torch.empty(1, dtype=torch.float32, device=g.device)
     dx = torch.empty_like(g)
-    db = torch.empty(C, dtype=torch.float32, device=g.device)
+    db = torch.empty(C, dtype=torch.float32, device=g.device) if want_param_grads else None
     L = _lib.lib()
     with _on_device(g.device):
         nbytes = L.msg_noise_bias_act_nhwc_bwd_workspace(rows, C)
         ws, wsp = _workspace(nbytes, g.device)
-        rc = L.msg_noise_bias_act_nhwc_bwd(_ptr(dx), ctypes.c_void_p(db.data_ptr()),
+        rc = L.msg_noise_bias_act_nhwc_bwd(_ptr(dx), ctypes.c_void_p(db.data_ptr()) if db is not None else None,
                                            ctypes.c_void_p(dnw.data_ptr()) if dnw is not None else None, _ptr(g),
                                            _ptr(ref), _ptr(noise), rows, C, period, float(alpha), float(scale), wsp,
                                            nbytes, _stream(g))

@@ -141,7 +141,11 @@ class _ConvBiasAct(Function):
         from .op_static.fused_act import NoiseBiasActBackward
         x, w, out, noise, x2 = ctx.saved_tensors
         noise = noise if ctx.has_noise else None
-        g_pre, g_bias, g_noise_w = NoiseBiasActBackward.apply(gout, out, noise, ctx.slope, ctx.gain)
+        # parameter gradients nobody asked for (the discriminator inside the generator step) skip their reduction
+        want = (ctx.has_bias and ctx.needs_input_grad[4]) or (ctx.has_noise and ctx.needs_input_grad[3])
+        g_pre, g_bias, g_noise_w = NoiseBiasActBackward.apply(gout, out, noise, ctx.slope, ctx.gain, want)
+        if not want:
+            g_bias = g_noise_w = None
         dx = dw = dx2 = None
         if ctx.has_x2:
             dx, dx2, dw = _cat2_backward(g_pre, x, x2, w, ctx.stride, ctx.padding, ctx.alpha, ctx.needs_input_grad[0],
@@ -151,8 +155,8 @@ class _ConvBiasAct(Function):
                 dx = _ConvDgrad.apply(g_pre, w, tuple(x.shape[2:]), ctx.stride, ctx.padding, ctx.alpha)
             if ctx.needs_input_grad[1]:
                 dw = _ConvWgrad.apply(g_pre, x, tuple(w.shape[-2:]), ctx.stride, ctx.padding, w.dim() == 5, ctx.alpha)
-        return (dx, dw, None, g_noise_w if ctx.has_noise else None, g_bias if ctx.has_bias else None,
-                None, None, None, None, None, dx2)
+        return (dx, dw, None, g_noise_w if (ctx.has_noise and want) else None,
+                g_bias if (ctx.has_bias and want) else None, None, None, None, None, None, dx2)
 
 
 def conv2d_bias_act(x: torch.Tensor, w: torch.Tensor, bias=None, noise=None, noise_w=None, stride=1, padding=0,

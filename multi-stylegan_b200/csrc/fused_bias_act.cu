@@ -552,6 +552,13 @@ extern "C" int msg_noise_bias_act_nhwc_bwd(float* dx, float* dbias, float* dnois
   float* partial_n = partial + (size_t)gy * C;
   const int64_t rpb = ceil_div(rows, gy);
   dim3 grid((unsigned)gx, (unsigned)gy);
+  if (!dbias && !dnoise_w) {
+    // no parameter gradient wanted (the discriminator inside the generator step): the plain masked pass, no reduction
+    fba_inner_kernel<FBA_LRELU_REF, false><<<grid, 256, 0, st>>>(dx, g, nullptr, ref, alpha, scale, rows, C, rpb, nullptr,
+                                                                 nullptr, nullptr, 1, nullptr);
+    MSG_CHECK_LAUNCH("noise_bias_act_nhwc_bwd(dx only)");
+    return MSG_OK;
+  }
   // dx = mask(ref) * g * scale; the per-row term only enters through its gradient (rowv_w == nullptr -> adds 0)
   fba_inner_kernel<FBA_LRELU_REF, true><<<grid, 256, 0, st>>>(dx, g, nullptr, ref, alpha, scale, rows, C, rpb, partial,
                                                               dnoise_w ? noise : nullptr, nullptr,

@@ -75,10 +75,13 @@ def fused_leaky_relu(input, bias, negative_slope=0.2, scale=2 ** 0.5):
 # ---------------------------------------------------------------------------------------------------
 class NoiseBiasActBackward(Function):
     @staticmethod
-    def forward(ctx, grad_output, out, noise, negative_slope, scale):
+    def forward(ctx, grad_output, out, noise, negative_slope, scale, want_param_grads=True):
         ctx.save_for_backward(out, noise)
         ctx.negative_slope, ctx.scale = negative_slope, scale
-        grad_input, grad_bias, grad_noise_w = _C.noise_bias_act_cl_bwd(grad_output, out, noise, negative_slope, scale)
+        grad_input, grad_bias, grad_noise_w = _C.noise_bias_act_cl_bwd(grad_output, out, noise, negative_slope, scale,
+                                                                       want_param_grads)
+        if not want_param_grads:     # (autograd needs tensors for the declared outputs; these are never used)
+            grad_bias = grad_input.new_zeros(0)
         return grad_input, grad_bias, grad_noise_w
 
     @staticmethod
@@ -88,7 +91,7 @@ class NoiseBiasActBackward(Function):
             gg_input = torch.zeros_like(out)
         gg_out = _C.noise_bias_act_cl(gg_input, out, noise if gg_noise_w is not None else None, gg_noise_w, gg_bias,
                                       ctx.negative_slope, ctx.scale)
-        return gg_out, None, None, None, None
+        return gg_out, None, None, None, None, None
 
 
 class NoiseBiasAct(Function):

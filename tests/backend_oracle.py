@@ -66,8 +66,10 @@ def noise_bias_act_cl(x, ref, noise, noise_w, bias, alpha, scale):
     return ops.noise_bias_act_masked(x, ref, noise, noise_w, bias, alpha, scale)
 
 
-def noise_bias_act_cl_bwd(grad_output, out, noise, alpha, scale):
+def noise_bias_act_cl_bwd(grad_output, out, noise, alpha, scale, want_param_grads=True):
     dx = ops.noise_bias_act_masked(grad_output, out, None, None, None, alpha, scale)
+    if not want_param_grads:
+        return dx, None, None
     db = dx.sum([0, 2, 3])
     dnw = None if noise is None else (dx.sum(1, keepdim=True) * noise).sum().reshape(1)
     return dx, db, dnw
