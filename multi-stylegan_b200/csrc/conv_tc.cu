@@ -660,13 +660,14 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
 template <int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 tc_pixgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
                    const TcPixParams p) {
   constexpr int BN = 256;
   constexpr uint32_t A_BYTES = 128 * 32 * 4;
   constexpr uint32_t B_BYTES = (BN / 2) * 32 * 4;
   constexpr uint32_t TMEM_COLS = 512;
   constexpr uint32_t IDESC = make_idesc_tf32(256, BN, 0, 0);
-  constexpr uint32_t STG_BYTES = 4 * 32 * 33 * 4;
+  constexpr uint32_t STG_BYTES = 4 * 2 * 4096;        // per epilogue warp: two 32-pixel x 128-byte staging boxes
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -678,6 +679,7 @@ tc_pixgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t acc_full = bars + 16 * STAGES;
   const uint32_t acc_empty = acc_full + 16;
   const uint32_t tmem_slot = acc_empty + 16;
+  const uint32_t add_bars = tmem_slot + 16;           // one mbarrier per epilogue warp (residual boxes)
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* stg_all = reinterpret_cast<float*>(smem_raw + (sStg - raw));
 
@@ -695,9 +697,11 @@ tc_pixgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_init(acc_full + 8 * a, 1);         // multicast commit, in each CTA
       mbar_init(acc_empty + 8 * a, 8);        // used in the leader: 4 epilogue warps x 2 CTAs
     }
+    for (int w = 0; w < 4; ++w) mbar_init(add_bars + 8 * w, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmOut);
   }
   __syncthreads();
   if (warp == 1) {
@@ -715,57 +719,63 @@ tc_pixgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int ppairs = (ptiles + 1) >> 1;              // pixel-tile pairs per sample (the last one may be half empty)
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t full_leader = mapa_cluster(bars, 0);
-      uint32_t it = 0;
-      for (int tile = pair; tile < p.total_tiles; tile += npairs) {
-        int r = tile;
-        const int nt = r % p.n_tiles; r /= p.n_tiles;
-        const int pp = r % ppairs;
-        const int b = r / ppairs;
-        const int pt = 2 * pp + (int)rank;           // >= ptiles: out of the image, TMA fills zeros, nothing is stored
-        const int ty = pt / p.tiles_x, tx = pt - ty * p.tiles_x;
-        const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN + (int)rank * (BN / 2);
-        const int bw = p.w_per_sample ? b : 0;
-        for (int k = 0; k < kiters; ++k, ++it) {
-          const uint32_t s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
+    // producers of both CTAs: converged warp, one elected lane issues (see tc_pixgemm_kernel)
+    const uint32_t full_leader = mapa_cluster(bars, 0);
+    uint32_t s = 0, ph = 0;
+    for (int tile = pair; tile < p.total_tiles; tile += npairs) {
+      int r = tile;
+      const int nt = r % p.n_tiles; r /= p.n_tiles;
+      const int pp = r % ppairs;
+      const int b = r / ppairs;
+      const int pt = 2 * pp + (int)rank;           // >= ptiles: out of the image, TMA fills zeros, nothing is stored
+      const int ty = pt / p.tiles_x, tx = pt - ty * p.tiles_x;
+      const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN + (int)rank * (BN / 2);
+      const int bw = p.w_per_sample ? b : 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int xx = x0 + p.tap_dx[t], yy = y0 + p.tap_dy[t];
+        for (int cc = 0; cc < p.cchunks; ++cc) {
           mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u);
-          const int t = k / p.cchunks;
-          const int c0 = (k - t * p.cchunks) * 32;
-          if (leader) mbar_expect_tx(bars + 8 * s, 2 * (A_BYTES + B_BYTES));
-          tma_load_4d_2cta(sA + s * A_BYTES, &tmA, full_leader + 8 * s, c0, x0 + p.tap_dx[t], y0 + p.tap_dy[t], b);
-          tma_load_4d_2cta(sB + s * B_BYTES, &tmB, full_leader + 8 * s, c0, n0, t, bw);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(bars + 8 * s, 2 * (A_BYTES + B_BYTES));
+            tma_load_4d_2cta(sA + s * A_BYTES, &tmA, full_leader + 8 * s, cc * 32, xx, yy, b);
+            tma_load_4d_2cta(sB + s * B_BYTES, &tmB, full_leader + 8 * s, cc * 32, n0, t, bw);
+          }
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      uint32_t it = 0, lt = 0;
+    if (leader) {
+      constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(SWZ_128B & 7) << 61);
+      uint32_t s = 0, ph = 0, lt = 0;
       for (int tile = pair; tile < p.total_tiles; tile += npairs, ++lt) {
         const uint32_t a = lt & 1u;
         mbar_wait(acc_empty + 8 * a, ((lt >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + a * BN;
-        for (int k = 0; k < kiters; ++k, ++it) {
-          const uint32_t s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1u;
+        for (int k = 0; k < kiters; ++k) {
           mbar_wait(bars + 8 * s, ph);
           tc_fence_after();
+          if (elect_one()) {
+            const uint32_t a_lo = ((sA + s * A_BYTES) >> 4) & 0x3FFF, b_lo = ((sB + s * B_BYTES) >> 4) & 0x3FFF;
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t ad = make_smem_desc(sA + s * A_BYTES + kk * 32, 0, 1024, SWZ_128B);
-            const uint64_t bd = make_smem_desc(sB + s * B_BYTES + kk * 32, 0, 1024, SWZ_128B);
-            mma_tf32_2cta(d_tmem, ad, bd, IDESC, (k > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk)
+              mma_tf32_2cta(d_tmem, DESC_HI | (uint64_t)(a_lo + kk * 2), DESC_HI | (uint64_t)(b_lo + kk * 2), IDESC,
+                            (k > 0 || kk > 0) ? 1u : 0u);
+            mma_commit_2cta(bars + 8 * (STAGES + s), 3);
+            if (k == kiters - 1) mma_commit_2cta(acc_full + 8 * a, 3);
           }
-          mma_commit_2cta(bars + 8 * (STAGES + s), 3);
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
-        mma_commit_2cta(acc_full + 8 * a, 3);
       }
     }
   } else {
     const int q = warp & 3;
-    float* stg = stg_all + q * (32 * 33);
+    float* stg = stg_all + q * (2 * 4096 / 4);
+    const uint32_t stage_smem = sStg + q * (2 * 4096);
+    uint32_t add_phase = 0;
     const float nw = p.ep.noise ? __ldg(p.ep.noise_w) : 0.f;
     const uint32_t acc_empty_leader = mapa_cluster(acc_empty, 0);
     uint32_t lt = 0;
@@ -781,8 +791,10 @@ tc_pixgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       mbar_wait(acc_full + 8 * a, (lt >> 1) & 1u);
       tc_fence_after();
       const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN;
-      pix_epilogue<BN, true>(p, stg, tlane, q, lane, b, y0, x0, n0, 0, nw, true, acc_empty_leader + 8 * a);
+      pix_epilogue<BN, true>(p, stg, tlane, q, lane, b, y0, x0, n0, 0, nw, true, acc_empty_leader + 8 * a, &tmOut,
+                             stage_smem, &tmAdd, add_bars + 8 * q, &add_phase);
     }
+    if (p.tma_store && lane == 0) tma_store_wait_read<0>();   // staging buffers must outlive their bulk stores
   }
   tc_fence_before();
   cluster_sync_all();
@@ -1106,9 +1118,10 @@ static int max_active_pairs(const void* kfn, size_t smem) {
   return n;
 }
 
-static int launch_pix2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcPixParams& p, cudaStream_t st) {
+static int launch_pix2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAdd,
+                       const TcPixParams& p, cudaStream_t st) {
   constexpr int STAGES = 6;
-  constexpr size_t smem = (size_t)STAGES * (16384 + 128 * 128) + 4 * 32 * 33 * 4 + 16 * STAGES + 64 + 1024;
+  constexpr size_t smem = (size_t)STAGES * (16384 + 128 * 128) + 4 * 2 * 4096 + 16 * STAGES + 128 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
   auto kfn = tc_pixgemm2_kernel<STAGES>;
   static int pairs_max_dev[64] = {};          // 0 = not queried yet, < 0 = no cluster fits
@@ -1121,7 +1134,7 @@ static int launch_pix2(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcP
   const int pairs_max = pairs_max_dev[slot];
   if (pairs_max <= 0) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05, CTA pairs): no cluster can be resident");
   const int pairs = p.total_tiles < pairs_max ? p.total_tiles : pairs_max;
-  kfn<<<2 * pairs, 192, smem, st>>>(tmA, tmB, p);
+  kfn<<<2 * pairs, 192, smem, st>>>(tmA, tmB, tmOut, tmAdd, p);
   MSG_CHECK_LAUNCH("conv pixgemm(tcgen05, CTA pairs)");
   return MSG_OK;
 }
@@ -1166,10 +1179,12 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   // CTA pairs for wide N (BN == 256) when there are enough pixel-tile pairs to fill the machine
   const int64_t ptiles = ceil_div(g.PW, Wt) * ceil_div(g.PH, Ht);
   const int64_t pair_tiles = ((ptiles + 1) / 2) * (Npad / BN) * (int64_t)g.B;
-  // Measured on B200 (tools/conv_bench.py): no gain over the single-CTA kernel at 256^2 (3.07 vs 3.13 ms — that kernel
-  // already runs at the MMA issue rate the power-capped clock allows) and a loss at <= 128^2 (coarser tiles), so the pair
-  // kernel is opt-in: MSG_B200_TC_VARIANT=4.
-  const bool pairs = BN == 256 && MT == 1 && (tc_variant() & 4u) && pair_tiles >= num_sms() / 2 && g.nphase == 0 && g.nsrc == 0;
+  // Measured on B200 (tools/conv_bench.py, tools/epi_probe.py) with the TMA-store epilogue in both kernels: the pair kernel
+  // is 3 % faster on the 3x3 512->512 layers (2.95 vs 3.05 ms at 256^2: half the weight bytes per CTA under a power-capped
+  // clock) and 24 % faster on the load-path-bound 1x1 512->512 layers (125 vs 164 us back to back), slower when there are
+  // fewer than two rounds of pair tiles (768->768 at 32^2).  MSG_B200_TC_VARIANT bit 4 disables it.
+  const int64_t pair_min = (tc_variant() & 256u) ? 1 : num_sms();       // bit 256 (tests): pairs for any eligible shape
+  const bool pairs = BN == 256 && MT == 1 && !(tc_variant() & 4u) && pair_tiles >= pair_min && g.nphase == 0 && g.nsrc == 0;
   TMapSet tmA;
   CUtensorMap tmB;
   const int nviews = g.nphase > 0 ? g.nphase : (g.nsrc == 2 ? 2 : 1);
@@ -1224,7 +1239,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.tma_store = 0;
   CUtensorMap tmAdd;
   memset(&tmAdd, 0, sizeof(tmAdd));
-  if (p.vec_store && BN >= 32 && !pairs && !(tc_variant() & 16u)) {
+  if (p.vec_store && BN >= 32 && !(tc_variant() & 16u)) {
     const int bw = Wt < 32 ? Wt : 32;
     const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B};
     const uint64_t strides[3] = {(uint64_t)g.os.sx * g.out_mx * 4, (uint64_t)g.os.sy * g.out_my * 4, (uint64_t)g.os.sb * 4};
@@ -1243,7 +1258,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);
   int rc;
   if (pairs) {
-    rc = launch_pix2(tmA.m[0], tmB, p, st);
+    rc = launch_pix2(tmA.m[0], tmB, tmOut, tmAdd, p, st);
   } else if (MT == 2) {
     switch (BN) {
       case 128: rc = launch_pix<128, 2>(tmA, tmB, tmOut, tmAdd, p, st); break;

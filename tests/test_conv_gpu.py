@@ -208,7 +208,9 @@ def test_conv_bias_act_autograd_on_device(built_library):
 
 
 def test_conv_cta_pair_kernel_subprocess(built_library):
-    """The opt-in cta_group::2 kernel (MSG_B200_TC_VARIANT=4, read once per process) against the oracle."""
+    """The cta_group::2 kernel (default for wide layers with >= two rounds of tile pairs; MSG_B200_TC_VARIANT bit 256,
+    read once per process, selects it for every eligible shape) against the oracle: plain, with the fused epilogues,
+    per-sample and shared filters, odd tile counts."""
     import os
     import subprocess
     import sys
@@ -217,17 +219,24 @@ def test_conv_cta_pair_kernel_subprocess(built_library):
         "import sys, torch; sys.path.insert(0, %r)\n"
         "from multi_stylegan_b200 import _C, _lib\n"
         "from oracle import ops\n"
+        "from tests import backend_oracle\n"
         "_C.conv_flags = _lib.CONV_FORCE_TC\n"
         "g = torch.Generator().manual_seed(0)\n"
-        "for (B, C, O, H, W, k) in [(2, 64, 320, 40, 24, 3), (3, 32, 512, 64, 64, 1), (1, 96, 256, 130, 130, 3)]:\n"
-        "    x = torch.randn(B, C, H, W, generator=g); w = torch.randn(B, O, C, k, k, generator=g) / (C * k * k) ** 0.5\n"
-        "    want = ops.conv2d(x, w, 1, k // 2)\n"
-        "    got = _C.conv2d_forward(x.cuda(), w.cuda(), 1, k // 2).cpu()\n"
-        "    err = ((got - want).abs().max() / want.abs().max()).item()\n"
-        "    assert err < 1e-2, err\n"
+        "for (B, C, O, H, W, k, per) in [(2, 64, 320, 40, 24, 3, True), (3, 32, 512, 64, 64, 1, True), (1, 96, 256, 130, 130, 3, False),\n"
+        "                                (2, 64, 256, 24, 40, 3, False)]:\n"
+        "    x = torch.randn(B, C, H, W, generator=g)\n"
+        "    w = torch.randn((B, O, C, k, k) if per else (O, C, k, k), generator=g) / (C * k * k) ** 0.5\n"
+        "    bias = torch.randn(O, generator=g); add = torch.randn(B, O, H, W, generator=g)\n"
+        "    noise = torch.randn(B, 1, H, W, generator=g); nw = torch.tensor([0.3])\n"
+        "    for kw in (dict(), dict(bias=bias, act=True, gain=1.4, noise=noise, noise_w=nw), dict(add=add, gain=0.7)):\n"
+        "        want = backend_oracle.conv2d_forward(x, w, 1, k // 2, alpha=0.9, **kw)\n"
+        "        dk = {a: (v.cuda() if isinstance(v, torch.Tensor) else v) for a, v in kw.items()}\n"
+        "        got = _C.conv2d_forward(x.cuda(), w.cuda(), 1, k // 2, alpha=0.9, **dk).cpu()\n"
+        "        err = ((got - want).abs().max() / want.abs().max()).item()\n"
+        "        assert err < 1e-2, (B, C, O, H, W, k, list(kw), err)\n"
         "torch.cuda.synchronize(); print('PAIR_OK')\n" % ROOT)
-    env = dict(os.environ, MSG_B200_TC_VARIANT="4")
-    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    env = dict(os.environ, MSG_B200_TC_VARIANT="256")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert "PAIR_OK" in out.stdout, out.stdout + out.stderr
 
 
