@@ -885,14 +885,12 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     // One TMA box per 32-channel atom: 4 + BN/32 boxes per stage.  They are issued by that many lanes in parallel
     // (a single thread issuing 12 bulk-tensor copies per 512-cycle MMA group was the measured limiter).
     constexpr int NBOX = 4 + BN / 32;
+    // K chunk counters (sample, chunk row, chunk column) advance incrementally: no division per k-iteration
+    int bl = k_begin / per;
+    int yc = (k_begin - bl * per) / p.chunks_x, xc = (k_begin - bl * per) - yc * p.chunks_x;
+    uint32_t s = 0, ph = 0;
     for (int it = 0; it < kiters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
       if (!mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u, soft)) { dbg_set(dbg, 4, 0x100u | (it << 12)); break; }
-      const int kk = k_begin + it;
-      const int bl = kk / per;
-      const int r = kk - bl * per;
-      const int yc = r / p.chunks_x, xc = r - yc * p.chunks_x;
       const int b = p.per_sample ? bs : bl;
       const uint32_t full = bars + 8 * s;
       if (lane == 0) mbar_expect_tx(full, A_BYTES + ntg * B_BYTES);
@@ -918,36 +916,48 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         }
       }
       if (lane == 0) dbg_set(dbg, 1, 2 * it + 2);
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+      if (++xc == p.chunks_x) { xc = 0; if (++yc == p.chunks_y) { yc = 0; ++bl; } }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // MN-major BASE32B: M/N atoms (32 channels) are ATOM_BYTES apart (LBO), K atoms (4 pixel rows of
-      // 128 bytes) 512 bytes apart (SBO); one K=8 MMA covers 2 K atoms = 1024 bytes.
-      const bool swap = p.variant & 1u;
-      const uint32_t lbo = swap ? 512u : ATOM_BYTES;
-      const uint32_t sbo = swap ? ATOM_BYTES : 512u;
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        if (!mbar_wait(bars + 8 * s, ph, soft)) { dbg_set(dbg, 4, 0x200u | (it << 12)); break; }
-        tc_fence_after();
+    // MN-major BASE32B: M/N atoms (32 channels) are ATOM_BYTES apart (LBO), K atoms (4 pixel rows of
+    // 128 bytes) 512 bytes apart (SBO); one K=8 MMA covers 2 K atoms = 1024 bytes.
+    // Converged warp, one elected lane issues (descriptors stay in uniform registers, see tc_pixgemm_kernel).
+    const bool swap = p.variant & 1u;
+    const uint32_t lbo = swap ? 512u : ATOM_BYTES;
+    const uint32_t sbo = swap ? ATOM_BYTES : 512u;
+    const uint64_t desc_hi = ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+                             ((uint64_t)1 << 46) | ((uint64_t)(SWZ_128B_BASE32B & 7) << 61);
+    uint32_t s = 0, ph = 0;
+    bool ok = true;
+    for (int it = 0; it < kiters; ++it) {
+      if (!mbar_wait(bars + 8 * s, ph, soft)) { if (lane == 0) dbg_set(dbg, 4, 0x200u | (it << 12)); ok = false; break; }
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a_lo = ((sA + s * A_BYTES) >> 4) & 0x3FFF;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint64_t ad = make_smem_desc(sA + s * A_BYTES + k * 1024, lbo, sbo, SWZ_128B_BASE32B);
+          const uint64_t ad = desc_hi | (uint64_t)(a_lo + k * 64);
 #pragma unroll
           for (int g = 0; g < TG; ++g) {
             if (g < ntg) {
-              const uint64_t bd = make_smem_desc(sB + (s * TG + g) * B_BYTES + k * 1024, lbo, sbo, SWZ_128B_BASE32B);
-              mma_tf32(tmem_base + g * BN, ad, bd, IDESC, (it > 0 || k > 0) ? 1u : 0u);
+              const uint32_t b_lo = ((sB + (s * TG + g) * B_BYTES) >> 4) & 0x3FFF;
+              mma_tf32(tmem_base + g * BN, ad, desc_hi | (uint64_t)(b_lo + k * 64), IDESC, (it > 0 || k > 0) ? 1u : 0u);
             }
           }
         }
         mma_commit(bars + 8 * (STAGES + s));
         dbg_set(dbg, 2, 2 * it + 2);
       }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+    }
+    (void)ok;
+    if (elect_one()) {
       mma_commit(acc_full);
       dbg_set(dbg, 2, 0x80000000u | (uint32_t)kiters);
     }
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int n = q * 32 + lane;
