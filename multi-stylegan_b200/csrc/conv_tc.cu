@@ -893,12 +893,13 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       if (!mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u, soft)) { dbg_set(dbg, 4, 0x100u | (it << 12)); break; }
       const int b = p.per_sample ? bs : bl;
       const uint32_t full = bars + 8 * s;
-      if (lane == 0) mbar_expect_tx(full, A_BYTES + ntg * B_BYTES);
+      const bool issuer = elect_one();                  // same lane every time; keeps the 5-D loads' operands uniform
+      if (issuer) mbar_expect_tx(full, A_BYTES + ntg * B_BYTES);
       __syncwarp();
       // 5-D maps: all channel atoms of an operand in one box ([atom][32 px][32 ch] is exactly the MN-major atom
       // layout); otherwise one 4-D box per atom, issued by consecutive lanes
       if (p.a5d) {
-        if (lane == 0) tma_load_5d(sA + s * A_BYTES, &tmG, full, 0, xc * Wk, yc * Hk, b, n0 >> 5);
+        if (issuer) tma_load_5d(sA + s * A_BYTES, &tmG, full, 0, xc * Wk, yc * Hk, b, n0 >> 5);
       } else if (lane < 4) {
         tma_load_4d(sA + s * A_BYTES + lane * ATOM_BYTES, &tmG, full, n0 + 32 * lane, xc * Wk, yc * Hk, b);
       }
@@ -906,7 +907,7 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       for (int g = 0; g < TG; ++g) {
         if (g < ntg) {
           if (p.b5d) {
-            if (lane == 0)
+            if (issuer)
               tma_load_5d(sB + (s * TG + g) * B_BYTES, &tmI, full, 0, xc * Wk + p.tap_dx[tg0 + g],
                           yc * Hk + p.tap_dy[tg0 + g], b, c0 >> 5);
           } else if (lane >= 4 && lane < NBOX) {
