@@ -252,6 +252,44 @@ tc_weight_transform_kernel(float* __restrict__ wt, const WtParams p) {
   }
 }
 
+// The same transform for filters whose taps are contiguous (w_st == 1, T = kh * kw floats per (n, c) pair, every tap
+// used): one block = a 32 x 32 (n, c) tile; each of its 32 rows along the slower of n / c is ONE contiguous run of 32 * T
+// floats in the filter tensor, read fully coalesced in a single pass into shared memory (row pitch 32 * T + 1 floats keeps
+// both read-out orders bank-conflict free), then written per tap as 128-byte rows along c.  The kernel above touches every
+// 128-byte line T times through L1 (3 TB/s); this one streams (the per-sample 512 x 512 x 9 banks of the generator are
+// 75 MB each way).
+__global__ void __launch_bounds__(256)
+tc_weight_transform_runs_kernel(float* __restrict__ wt, const WtParams p, int T) {
+  extern __shared__ float runs[];                     // [32][32 * T + 1]
+  const int pitch = 32 * T + 1;
+  const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 32, b = blockIdx.z;
+  const int a = threadIdx.x & 31, r = threadIdx.x >> 5;
+  const bool c_fast = p.w_sc <= p.w_sn;               // forward: rows = n, runs along (c, t); dgrad: rows = c, runs along (n, t)
+  const float* wb = p.w + (int64_t)b * p.w_sb;
+  const int slow0 = c_fast ? n0 : c0, fast0 = c_fast ? c0 : n0;
+  const int slow_n = c_fast ? p.N : p.Cr, fast_n = c_fast ? p.Cr : p.N;
+  const int64_t slow_stride = c_fast ? p.w_sn : p.w_sc;
+  const int run = 32 * T;
+  const int run_valid = (fast_n - fast0 < 32 ? (fast_n - fast0 > 0 ? fast_n - fast0 : 0) : 32) * T;
+  for (int row = r; row < 32; row += 8) {
+    const bool row_ok = slow0 + row < slow_n;
+    const float* src = wb + (int64_t)(slow0 + row) * slow_stride + (int64_t)fast0 * T;
+    for (int i = a; i < run; i += 32)
+      runs[row * pitch + i] = (row_ok && i < run_valid) ? to_tf32_rna(__ldg(src + i)) : 0.f;
+  }
+  __syncthreads();
+  for (int t = 0; t < p.ntaps; ++t) {
+    const int ti = p.tap_wi[t];
+    float* dst = wt + (((int64_t)b * p.ntaps + t) * p.Npad + n0) * p.Cpad + c0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int nl = r + 8 * k;
+      const float v = c_fast ? runs[nl * pitch + a * T + ti] : runs[a * pitch + nl * T + ti];
+      if (n0 + nl < p.Npad) dst[(int64_t)nl * p.Cpad + a] = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // PixGemm kernel (K-major A from NHWC, K-major B)
 // ------------------------------------------------------------------------------------------------
@@ -1179,7 +1217,16 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (Npad % 32 != 0 && Npad != 16) return fail(MSG_ERR_UNSUPPORTED, "conv weight transform: Npad %d", Npad);
     dim3 grid((unsigned)(Cpad / 32), (unsigned)((Npad + 31) / 32), (unsigned)BW);
     if (BW > 65535) return fail(MSG_ERR_UNSUPPORTED, "conv weight transform: batch > 65535");
-    tc_weight_transform_kernel<<<grid, 256, 0, st>>>(wt, wp);
+    // contiguous taps, all of them used, two or more: the streaming variant
+    const int64_t T = wp.w_sc <= wp.w_sn ? wp.w_sc : wp.w_sn;
+    bool all_taps = wp.w_st == 1 && T == g.ntaps && T >= 2 && T <= 9;
+    for (int t = 0; t < g.ntaps && all_taps; ++t) all_taps = wp.tap_wi[t] >= 0 && wp.tap_wi[t] < T;
+    if (all_taps && !(tc_variant() & 512u)) {
+      const size_t sm = (size_t)32 * (32 * T + 1) * sizeof(float);
+      tc_weight_transform_runs_kernel<<<grid, 256, sm, st>>>(wt, wp, (int)T);
+    } else {
+      tc_weight_transform_kernel<<<grid, 256, 0, st>>>(wt, wp);
+    }
     MSG_CHECK_LAUNCH("conv weight transform");
   }
 
