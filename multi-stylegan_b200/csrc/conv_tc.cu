@@ -637,11 +637,12 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a_lo = ((sA + s * A_BYTES) >> 4) & 0x3FFF, b_lo = ((sB + s * B_BYTES) >> 4) & 0x3FFF;
+          // (sub-tile outer: consecutive MMAs accumulate into the same TMEM columns)
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t bd = DESC_HI | (uint64_t)(b_lo + kk * 2);
+          for (int sub = 0; sub < MT; ++sub) {
 #pragma unroll
-            for (int sub = 0; sub < MT; ++sub) {
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t bd = DESC_HI | (uint64_t)(b_lo + kk * 2);
               const uint64_t ad = DESC_HI | (uint64_t)(a_lo + sub * (128 * 32 * 4 / 16) + kk * 2);
               mma_tf32(d_tmem + sub * BN, ad, bd, IDESC, (k > 0 || kk > 0) ? 1u : 0u);
             }
@@ -695,15 +696,15 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
 // barriers; accumulators (2 x 256 columns in each CTA's TMEM) are published the same way, and every epilogue warp of
 // both CTAs arrives on the leader's acc_empty barrier when it has drained its lane quarter.
 // ------------------------------------------------------------------------------------------------
-template <int STAGES>
+template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 tc_pixgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
                    const TcPixParams p) {
-  constexpr int BN = 256;
+  static_assert(BN == 256 || BN == 128, "pair tiles are 256 pixels x 256 or 128 channels");
   constexpr uint32_t A_BYTES = 128 * 32 * 4;
   constexpr uint32_t B_BYTES = (BN / 2) * 32 * 4;
-  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
   constexpr uint32_t IDESC = make_idesc_tf32(256, BN, 0, 0);
   constexpr uint32_t STG_BYTES = 4 * 2 * 4096;        // per epilogue warp: two 32-pixel x 128-byte staging boxes
 
@@ -1167,12 +1168,13 @@ static int max_active_pairs(const void* kfn, size_t smem) {
   return n;
 }
 
+template <int BN>
 static int launch_pix2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAdd,
                        const TcPixParams& p, cudaStream_t st) {
-  constexpr int STAGES = 6;
-  constexpr size_t smem = (size_t)STAGES * (16384 + 128 * 128) + 4 * 2 * 4096 + 16 * STAGES + 128 + 1024;
+  constexpr int STAGES = BN == 256 ? 6 : 8;
+  constexpr size_t smem = (size_t)STAGES * (16384 + (BN / 2) * 128) + 4 * 2 * 4096 + 16 * STAGES + 128 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  auto kfn = tc_pixgemm2_kernel<STAGES>;
+  auto kfn = tc_pixgemm2_kernel<BN, STAGES>;
   static int pairs_max_dev[64] = {};          // 0 = not queried yet, < 0 = no cluster fits
   const int slot = current_device_slot();
   if (pairs_max_dev[slot] == 0) {
@@ -1232,17 +1234,21 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
 
   int wt_log2 = ilog2_ceil(g.PW);
   if (wt_log2 > 7) wt_log2 = 7;
-  const int MT = pick_mt(g, BN);
-  const int Wt = 1 << wt_log2, Ht = (128 * MT) >> wt_log2;
-  // CTA pairs for wide N (BN == 256) when there are enough pixel-tile pairs to fill the machine
-  const int64_t ptiles = ceil_div(g.PW, Wt) * ceil_div(g.PH, Ht);
+  // CTA pairs (two 128-pixel tiles, BN = 256 or 128) when there are enough pixel-tile pairs to fill the machine
+  const int64_t ptiles = ceil_div(g.PW, 1 << wt_log2) * ceil_div(g.PH, 128 >> wt_log2);
   const int64_t pair_tiles = ((ptiles + 1) / 2) * (Npad / BN) * (int64_t)g.B;
   // Measured on B200 (tools/conv_bench.py, tools/epi_probe.py) with the TMA-store epilogue in both kernels: the pair kernel
   // is 3 % faster on the 3x3 512->512 layers (2.95 vs 3.05 ms at 256^2: half the weight bytes per CTA under a power-capped
   // clock) and 24 % faster on the load-path-bound 1x1 512->512 layers (125 vs 164 us back to back), slower when there are
   // fewer than two rounds of pair tiles (768->768 at 32^2).  MSG_B200_TC_VARIANT bit 4 disables it.
   const int64_t pair_min = (tc_variant() & 256u) ? 1 : num_sms();       // bit 256 (tests): pairs for any eligible shape
-  const bool pairs = BN == 256 && MT == 1 && !(tc_variant() & 4u) && pair_tiles >= pair_min && g.nphase == 0 && g.nsrc == 0;
+  // BN = 128 pairs exist (bit 1024) but measured the same as the 256-pixel single-CTA tiles (608 vs 607 and 659 vs 644
+  // TFLOP/s on the discriminator's 128-channel 3x3 layers at 256^2; ncu: tensor pipe 69 % active either way), so they
+  // stay opt-in.
+  const bool pairs = (BN == 256 || (BN == 128 && (tc_variant() & 1024u))) && !(tc_variant() & 4u) &&
+                     pair_tiles >= pair_min && g.nphase == 0 && g.nsrc == 0;
+  const int MT = pairs ? 1 : pick_mt(g, BN);
+  const int Wt = 1 << wt_log2, Ht = (128 * MT) >> wt_log2;
   TMapSet tmA;
   CUtensorMap tmB;
   const int nviews = g.nphase > 0 ? g.nphase : (g.nsrc == 2 ? 2 : 1);
@@ -1316,7 +1322,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);
   int rc;
   if (pairs) {
-    rc = launch_pix2(tmA.m[0], tmB, tmOut, tmAdd, p, st);
+    rc = BN == 256 ? launch_pix2<256>(tmA.m[0], tmB, tmOut, tmAdd, p, st) : launch_pix2<128>(tmA.m[0], tmB, tmOut, tmAdd, p, st);
   } else if (MT == 2) {
     switch (BN) {
       case 128: rc = launch_pix<128, 2>(tmA, tmB, tmOut, tmAdd, p, st); break;

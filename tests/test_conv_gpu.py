@@ -223,7 +223,7 @@ def test_conv_cta_pair_kernel_subprocess(built_library):
         "_C.conv_flags = _lib.CONV_FORCE_TC\n"
         "g = torch.Generator().manual_seed(0)\n"
         "for (B, C, O, H, W, k, per) in [(2, 64, 320, 40, 24, 3, True), (3, 32, 512, 64, 64, 1, True), (1, 96, 256, 130, 130, 3, False),\n"
-        "                                (2, 64, 256, 24, 40, 3, False)]:\n"
+        "                                (2, 64, 256, 24, 40, 3, False), (2, 64, 128, 40, 24, 3, False), (3, 32, 96, 64, 64, 3, True)]:\n"
         "    x = torch.randn(B, C, H, W, generator=g)\n"
         "    w = torch.randn((B, O, C, k, k) if per else (O, C, k, k), generator=g) / (C * k * k) ** 0.5\n"
         "    bias = torch.randn(O, generator=g); add = torch.randn(B, O, H, W, generator=g)\n"
@@ -235,7 +235,7 @@ def test_conv_cta_pair_kernel_subprocess(built_library):
         "        err = ((got - want).abs().max() / want.abs().max()).item()\n"
         "        assert err < 1e-2, (B, C, O, H, W, k, list(kw), err)\n"
         "torch.cuda.synchronize(); print('PAIR_OK')\n" % ROOT)
-    env = dict(os.environ, MSG_B200_TC_VARIANT="256")
+    env = dict(os.environ, MSG_B200_TC_VARIANT=str(256 + 1024))      # + the opt-in 128-channel pair tiles
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert "PAIR_OK" in out.stdout, out.stdout + out.stderr
 

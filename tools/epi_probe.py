@@ -10,7 +10,8 @@ from multi_stylegan_b200 import _C
 
 CASES = [  # (B, C, H, O, k, with_bias_act)
     (8, 512, 128, 512, 1, False), (8, 512, 128, 512, 1, True), (8, 512, 64, 512, 1, False),
-    (8, 8, 256, 512, 1, False), (16, 256, 256, 128, 1, False), (16, 128, 256, 256, 1, False), (8, 512, 256, 512, 3, True)]
+    (8, 8, 256, 512, 1, False), (16, 256, 256, 128, 1, False), (16, 128, 256, 256, 1, False), (8, 512, 256, 512, 3, True),
+    (16, 128, 256, 128, 3, True), (16, 256, 256, 128, 3, True)]
 
 
 def main():
