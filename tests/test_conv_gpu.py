@@ -30,6 +30,8 @@ SHAPES = [
     (2, 32, 32, 128, 128, 3, 2, 0, False),  # 128 -> 63 (row pitch not a multiple of 16 bytes)
     (2, 32, 1, 64, 64, 1, 1, 0, False),     # pixel head (N=1)
     (2, 48, 40, 32, 32, 2, 2, 0, True),     # stride-2 2x2 (adjoint of the generator's up-conv)
+    (2, 32, 64, 160, 160, 3, 1, 1, False),  # >= 148 tiles of 256 pixels: two sub-tiles per CTA, two MMA-issuing warps
+    (1, 32, 128, 200, 200, 3, 1, 1, False),
 ]
 
 
