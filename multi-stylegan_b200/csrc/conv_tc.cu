@@ -343,8 +343,10 @@ __device__ __forceinline__ void epi_chunk_to_smem(const float (&rr)[32], const f
   }
 }
 
-// Epilogue of one 128-pixel x BN accumulator (one TMEM lane quarter per warp): TMEM -> registers -> per-warp 32x33
-// shared-memory transpose -> fused output transform -> 128-bit stores (8 lanes cover one pixel's 128 contiguous bytes).
+// Epilogue of one 128-pixel x BN accumulator (one TMEM lane quarter per warp), three paths: (1) TMA store — TMEM ->
+// registers -> fused output transform -> swizzled staging box -> one bulk tensor store per 32-pixel x 32-channel chunk;
+// (2) outputs the store map cannot describe — per-warp 32x33 shared-memory transpose -> 128-bit stores (8 lanes cover
+// one pixel's 128 contiguous bytes); (3) generic scalar stores (channel counts below 32, unaligned views).
 // `release`: after the last TMEM read arrive on `release_bar` (hands the accumulator back to the MMA warp).
 template <int BN, bool REMOTE>
 __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, uint32_t tlane, int q, int lane, int b, int y0,
@@ -534,7 +536,7 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
 
 // Persistent, warp-specialised: CTA c works on tiles c, c + gridDim.x, ...  (n-tile fastest, so neighbouring CTAs
 // share the activation tile in L2).  Two TMEM accumulators: the epilogue warps drain tile i (TMEM -> registers ->
-// per-warp shared-memory transpose -> fused epilogue -> 128-bit coalesced stores) while the MMA warp already
+// fused epilogue -> swizzled staging box -> bulk tensor store; see pix_epilogue) while the MMA warp already
 // accumulates tile i + 1 and the TMA warp runs ahead through the shared-memory ring.
 template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(192, 1)
