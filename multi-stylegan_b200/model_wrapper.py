@@ -147,6 +147,12 @@ class ModelWrapper(object):
         return self._iteration(real_images, lazy_r1, lazy_pl, wrong_order, cut_mix, z_d, z_g, z_pl, pl_noise)
 
     # ---- CUDA-graph replay of one iteration ----------------------------------------------------------
+    def reset_cuda_graphs(self) -> None:
+        """Drop every captured iteration (they are re-captured on demand).  Needed after anything that replaces the
+        tensors a graph has baked in: parameters or optimiser state re-created (`module.to(...)`, a new optimiser),
+        a different process group.  `load_state_dict` copies in place and needs no reset."""
+        self._graphs.clear()
+
     def _graphable(self, real_images, cut_mix, *fixed) -> bool:
         return (real_images.is_cuda and not cut_mix and all(f is None for f in fixed)
                 and isinstance(self.top_k, nn.Identity)
