@@ -76,6 +76,10 @@ class ModelWrapper(object):
         self.epoch, self.epochs = 0, 1
         self.resume_training = False
         self.top_k: Callable = nn.Identity()
+        # Decisions that change WHICH optimiser steps an iteration runs (the CutMix draw, :331) must agree on every rank,
+        # or the ranks would issue different sequences of gradient all-reduces: with several ranks they are drawn from a
+        # generator that is seeded identically everywhere (the reference is a single process and has one draw anyway).
+        self._structure_rng = random.Random(0x5EED)
         self.cuda_graphs = bool(cuda_graphs)
         self._graphs: Dict[Any, Any] = {}        # variant key -> None (seen once, ran eagerly) | captured state
         self._capture = None                     # the program being captured (graph segments + eager collectives)
@@ -140,8 +144,9 @@ class ModelWrapper(object):
         lazy_r1 = self.iteration % hp["lazy_discriminator_regularization"] == 0
         lazy_pl = self.iteration % hp["lazy_generator_regularization"] == 0
         wrong_order = bool(self.epoch >= hp["wrong_order_start"] * self.epochs or self.resume_training)
-        cut_mix = (random.random() <= ((0.5 / float(self.epochs)) * float(self.epoch))) \
-            or (self.resume_training and random.random() <= 0.5)
+        rng = self._structure_rng if mdist.world_size(self.process_group) > 1 else random
+        cut_mix = (rng.random() <= ((0.5 / float(self.epochs)) * float(self.epoch))) \
+            or (self.resume_training and rng.random() <= 0.5)
         if self.cuda_graphs and self._graphable(real_images, cut_mix, z_d, z_g, z_pl, pl_noise):
             return self._train_step_graphed(real_images, lazy_r1, lazy_pl, wrong_order)
         return self._iteration(real_images, lazy_r1, lazy_pl, wrong_order, cut_mix, z_d, z_g, z_pl, pl_noise)

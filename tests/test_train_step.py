@@ -171,6 +171,52 @@ def test_data_parallel_gradient_allreduce_gloo(tmp_path, oracle_backend):
         assert torch.equal(outs[0]["grads"][k], outs[1]["grads"][k])
 
 
+def _dp_structure_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import random
+    import torch.distributed as dist
+    from tests import backend_oracle
+    from multi_stylegan_b200 import _C, dist as mdist
+    from multi_stylegan_b200.model_wrapper import ModelWrapper
+    for name in backend_oracle.__all__:
+        setattr(_C, name, getattr(backend_oracle, name))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        hp = _hp()
+        G, D = build("cpu", seed=0)
+        mdist.broadcast_parameters([G, D])
+        opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"])
+        opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"])
+        mw = ModelWrapper(G, D, opt_g, opt_d, hyperparameters=hp, device="cpu")
+        mw.epochs, mw.epoch = 10, 9                  # CutMix probability 0.45, wrong-order fakes on
+        random.seed(100 + rank)                      # the ranks' own host streams differ
+        torch.manual_seed(100 + rank)
+        keys = []
+        torch.set_num_threads(4)
+        for it in range(2):                          # the shared draws give: CutMix, then no CutMix
+            out = mw.train_step(torch.rand(2, 2, 3, 32, 32))
+            keys.append(sorted(out))
+        torch.save({"keys": keys, "w": [p.detach().clone() for p in D.parameters()]}, os.path.join(tmp, "s%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_data_parallel_ranks_agree_on_step_structure_gloo(tmp_path, oracle_backend):
+    """Late-epoch iterations on 2 ranks whose host random streams differ: the CutMix draw decides how many optimiser steps
+    (= gradient all-reduces) an iteration has, so every rank must take the same decision — otherwise this test hangs in a
+    mismatched collective.  Parameters stay identical across ranks."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_dp_structure_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    a, b = [torch.load(os.path.join(str(tmp_path), "s%d.pt" % r), weights_only=False) for r in range(world)]
+    assert a["keys"] == b["keys"]
+    assert any("loss_cut_mix_augmentation" in k for k in a["keys"]) and any("loss_cut_mix_augmentation" not in k for k in a["keys"])
+    for x, y in zip(a["w"], b["w"]):
+        assert torch.equal(x, y)
+
+
 def test_late_epoch_branches_host_logic(oracle_backend):
     """CutMix augmentation + consistency steps, wrong-order fakes and top-k filtering (model_wrapper.py:272-277,331-376,
     392-401; probability 0 in epoch 0, so the benchmark never runs them): one iteration with all of them switched on."""
