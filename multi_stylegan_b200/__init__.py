@@ -1,9 +1,7 @@
-"""Import shim: the package lives in ``multi-stylegan_b200/`` (a directory name Python cannot
-import directly); this module makes it importable as ``multi_stylegan_b200``."""
-import os as _os
+"""multi_stylegan_b200 — B200-native (sm_100a) training-step hot path of Multi-StyleGAN.
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "multi-stylegan_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
-del _os, _f
+Host code is Python/PyTorch and keeps the reference's API surface; all arithmetic on the hot path
+runs in the hand-written CUDA library ``lib/libmsg_b200.so`` (C-ABI declared in ``include/msg_b200.h``).
+There is no CPU fallback: every op raises if its input is not a CUDA tensor or the library is missing.
+"""
+__version__ = "0.1.0"

@@ -3,7 +3,7 @@
 CPU restatement (plain PyTorch / numpy, fp32 or fp64) of the reference algorithm for the Multi-StyleGAN
 training-step hot path.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 `--impl reference` legs may import it, and only as the checker or the timed CPU baseline; nothing under
-`multi-stylegan_b200/` imports it.
+`multi_stylegan_b200/` imports it.
 
 Pinning: the reference ships no tests, golden vectors or fixtures.  The oracle is
 therefore pinned against *outputs of the reference itself*: `oracle/ref_loader.py` imports the

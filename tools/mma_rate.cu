@@ -1,6 +1,6 @@
 // Microbenchmark: issue rate of tcgen05.mma kind::tf32 (M=128) for the operand layouts the conv engines use,
 // with operands resident in shared memory (no TMA in the loop).  Diagnostic, not a product kernel.
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I multi-stylegan_b200/csrc -I include \
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I multi_stylegan_b200/csrc -I include \
 //        -o gpurun_out/mma_rate tools/mma_rate.cu && gpurun_out/mma_rate
 #include <cstdio>
 #include <cuda_runtime.h>
