@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define MSG_B200_ABI_VERSION 2
+#define MSG_B200_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------------------------- */
 enum {
@@ -112,6 +112,18 @@ int msg_upfirdn2d_bias_act(float* out, const float* in, const float* kernel, int
                            const float* noise, const float* noise_w, int64_t noise_batch_stride,
                            const float* bias, int act, float slope, float gain, msg_stream_t stream);
 
+/* The same pass for the shared-weight form of the modulated up-convolution (multi_stylegan_generator.py:379-403 with the
+ * modulation moved onto the activations): the demodulation factor commutes with the per-channel FIR, so
+ *   out[b,y,x,c]  = act(col_scale[b*col_scale_batch_stride + c] * fir(in)[b,y,x,c] + noise term + bias[c]) * gain
+ *   out2[b,y,x,c] = out[b,y,x,c] * out2_scale[b*out2_scale_batch_stride + c]      (optional: the next layer's input)
+ * col_scale / out2 may be NULL; pointers 16-byte aligned, batch strides multiples of 4. */
+int msg_upfirdn2d_bias_act_mod(float* out, float* out2, const float* in, const float* kernel, int64_t major,
+                               int in_h, int in_w, int minor, int kernel_h, int kernel_w, int pad_x0, int pad_x1,
+                               int pad_y0, int pad_y1, const float* col_scale, int64_t col_scale_batch_stride,
+                               const float* noise, const float* noise_w, int64_t noise_batch_stride,
+                               const float* bias, int act, float slope, float gain, const float* out2_scale,
+                               int64_t out2_scale_batch_stride, msg_stream_t stream);
+
 /* -------------------------------------------------------------------------------------------
  * Dense / per-sample ("grouped by batch") 2-D convolution primitives, fp32 storage, TF32 tensor
  * cores (tcgen05) with fp32 accumulation for the shapes the implicit-GEMM kernels tile, an fp32
@@ -160,7 +172,7 @@ enum {
  * ResNetBlock.forward (u_net_2d_discriminator.py:174-186: activation, residual add, 1/sqrt(2)):
  *   v = alpha * conv ; v += noise_w[0] * noise[b * noise_batch_stride + oy * OW + ox] ; v += bias[o]
  *   v = act ? (v > 0 ? v : slope * v) : v ; v += add[b, o, oy, ox] ; y = v * gain
- * Null pointers skip their term; `add` has the layout of y. */
+ * Null pointers skip their term; `add` has the layout of y.  (col_scale / y2: see the field comments.) */
 typedef struct {
   const float* bias;            /* [O]                                                  */
   const float* noise;           /* [B or 1, 1, OH, OW]                                   */
@@ -169,6 +181,16 @@ typedef struct {
   const float* add;             /* tensor added after the activation, layout of y        */
   int act;                      /* 0 = linear, 1 = leaky ReLU                            */
   float slope, gain;
+  /* Shared-weight form of the modulated convolution (multi_stylegan_generator.py:379-411 rewritten as
+   * y = demod[b,o] * conv(scale * W, s[b,c] * x), algebraically identical): the accumulator is multiplied by
+   * col_scale[b * col_scale_batch_stride + o] (the demodulation factor, :386-388) before the noise / bias terms, and
+   * a second tensor y2 = y * y2_scale[b * y2_scale_batch_stride + o] (the next layer's style-modulated input,
+   * :384) is written next to y.  Null pointers skip either; not combinable with `add`. */
+  const float* col_scale;       /* [B or 1, O]                                           */
+  int64_t col_scale_batch_stride;
+  float* y2;                    /* layout of y                                           */
+  const float* y2_scale;        /* [B or 1, O]                                           */
+  int64_t y2_scale_batch_stride;
 } msg_conv_epilogue;
 
 size_t msg_conv2d_workspace(const msg_conv_desc* d, int which /*0 fwd,1 dgrad,2 wgrad*/, int flags);
@@ -210,6 +232,36 @@ size_t msg_modulate_weights_bwd_workspace(int B, int O, int C, int taps);
 int msg_modulate_weights_bwd(float* dW, float* ds, const float* g, const float* W, const float* s,
                              const float* demod, int B, int O, int C, int taps, float scale, int demodulate,
                              void* workspace, size_t workspace_bytes, msg_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------
+ * Shared-weight form of the modulated convolution (multi_stylegan_generator.py:379-411):
+ *   conv(scale*W*s*demod, x) == demod[b,o] * conv(scale*W, s[b,c]*x)        (exact algebra; the survey checked it
+ * against the reference module in fp64).  The style multiplies the activations (written by the previous layer's
+ * epilogue as its second output), the demodulation factor multiplies the accumulator (msg_conv_epilogue.col_scale),
+ * and all samples share ONE weight operand, so wgrad is one batch-reduced GEMM instead of B per-sample ones.
+ *
+ * msg_demod_factors: wsq[o,c] = sum_t W[o,c,t]^2 ; d[b,o] = rsqrt(scale^2 * sum_c s[b,c]^2 * wsq[o,c] + 1e-8)  (:386-388)
+ *
+ * msg_styled_act_bwd: the non-GEMM part of the layer's first-order backward in one pass over the channels-last
+ * activation [B, rows = H*W, C] (C % 4 == 0), given the gradients w.r.t. both outputs of the forward epilogue
+ * (out = lrelu(v) * gain, out2 = out * out2_scale; v = col_scale * conv + noise_w * noise + bias):
+ *   gt = g_out + out2_scale[b,c] * g_out2 ;  gv = gt * (out > 0 ? 1 : slope) * gain ;  g_pre = gv * col_scale[b,c]
+ *   sums[0][b][c] = sum_p gv               (-> dbias)
+ *   sums[1][b][c] = sum_p gv * v           (-> d col_scale, with v recovered from out)
+ *   sums[2][b][c] = sum_p gv * noise[b,p]  (-> dnoise_w)
+ *   sums[3][b][c] = sum_p out * g_out2     (-> d out2_scale)
+ * g_out or g_out2 may be NULL (not both); col_scale NULL = 1; noise NULL = 0.  Deterministic (two-stage reduction in
+ * `workspace`, msg_styled_act_bwd_workspace bytes).  Replaces what autograd derives from :384-388, :289-292 and
+ * op_static/fused_act.py:31-40.
+ * ------------------------------------------------------------------------------------------- */
+int msg_demod_factors(float* d, float* wsq, const float* W, const float* s, int B, int O, int C, int taps,
+                      float scale, msg_stream_t stream);
+size_t msg_styled_act_bwd_workspace(int B, int64_t rows, int C);
+int msg_styled_act_bwd(float* g_pre, float* sums, const float* g_out, const float* g_out2, const float* out,
+                       const float* col_scale, int64_t col_scale_batch_stride, const float* out2_scale,
+                       int64_t out2_scale_batch_stride, const float* noise, int64_t noise_batch_stride,
+                       int B, int64_t rows, int C, float slope, float gain, void* workspace,
+                       size_t workspace_bytes, msg_stream_t stream);
 
 /* -------------------------------------------------------------------------------------------
  * Fused StyledConv2d epilogue — multi_stylegan_generator.py:292 (noise) + op_static/fused_act.py:58

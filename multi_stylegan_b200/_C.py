@@ -303,10 +303,13 @@ def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha:
                    bias: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None,
                    noise_w: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None, act: bool = False,
                    slope: float = 0.2, gain: float = 1.0, w_transposed: bool = False,
-                   x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   x2: Optional[torch.Tensor] = None, col_scale: Optional[torch.Tensor] = None,
+                   out2_scale: Optional[torch.Tensor] = None):
     """y = epilogue(alpha * conv(x, w)); the optional epilogue (noise, bias, leaky ReLU, residual add, gain) runs
     inside the conv kernel (msg_conv_epilogue, include/msg_b200.h).  With `x2` the convolution is applied to the channel
-    concatenation [x | x2] without materialising it (msg_conv2d_forward_cat2; see cat2_supported)."""
+    concatenation [x | x2] without materialising it (msg_conv2d_forward_cat2; see cat2_supported).
+    `col_scale` [B or 1, O] multiplies the accumulator per sample and output channel (the demodulation factor of the
+    shared-weight modulated convolution); with `out2_scale` [B or 1, O] the call returns (y, y * out2_scale)."""
     _check_f32(x, "x")
     _check_f32(w, "w")
     x, layout = _act(x)
@@ -324,12 +327,30 @@ def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha:
         raise RuntimeError("conv2d: weight has %d input channels, input has %d" % (Cw, C))
     d = _conv_desc(B, C, H, W, O, kh, kw, stride, padding, per_sample, layout, w_transposed)
     y = _empty_act((B, O, d.OH, d.OW), layout, x.device)
-    fused = bias is not None or noise is not None or add is not None or act or gain != 1.0
+    fused = (bias is not None or noise is not None or add is not None or act or gain != 1.0 or col_scale is not None
+             or out2_scale is not None)
     ep = None
     keep = []
+    y2 = None
     if fused:
         ep = _lib.ConvEpilogue()
         ep.act, ep.slope, ep.gain = (1 if act else 0), float(slope), float(gain)
+        if col_scale is not None:
+            _check_f32(col_scale, "col_scale")
+            col_scale = _aligned(col_scale)
+            if col_scale.numel() not in (O, B * O):
+                raise RuntimeError("conv2d: col_scale must be [B or 1, %d]" % O)
+            ep.col_scale = col_scale.data_ptr()
+            ep.col_scale_batch_stride = O if col_scale.numel() == B * O else 0
+        if out2_scale is not None:
+            _check_f32(out2_scale, "out2_scale")
+            out2_scale = _aligned(out2_scale)
+            if out2_scale.numel() not in (O, B * O):
+                raise RuntimeError("conv2d: out2_scale must be [B or 1, %d]" % O)
+            y2 = torch.empty_like(y)
+            ep.y2, ep.y2_scale = y2.data_ptr(), out2_scale.data_ptr()
+            ep.y2_scale_batch_stride = O if out2_scale.numel() == B * O else 0
+        keep += [col_scale, out2_scale]
         if bias is not None:
             _check_f32(bias, "bias")
             bias = _aligned(bias)
@@ -355,7 +376,7 @@ def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha:
             if add.data_ptr() % 16:
                 add = add.clone()
             ep.add = add.data_ptr()
-        keep = [bias, noise, noise_w, add]
+        keep += [bias, noise, noise_w, add]
     L = _lib.lib()
     with _on_device(x.device):
         nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 0, conv_flags)
@@ -370,6 +391,8 @@ def conv2d_forward(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha:
                                            _stream(x))
     _lib.check(rc, "conv2d_forward")
     del keep
+    if out2_scale is not None:
+        return y, y2
     return y
 
 
@@ -616,6 +639,129 @@ def noise_bias_act_cl_bwd(grad_output: torch.Tensor, out: torch.Tensor, noise: O
                                            nbytes, _stream(g))
     _lib.check(rc, "noise_bias_act_nhwc_bwd")
     return dx, db, dnw
+
+
+# ---------------------------------------------------------------------------------------------------
+# shared-weight form of the modulated convolution (include/msg_b200.h: msg_demod_factors, msg_styled_act_bwd,
+# msg_upfirdn2d_bias_act_mod)
+# ---------------------------------------------------------------------------------------------------
+def demod_factors(W: torch.Tensor, s: torch.Tensor, scale: float):
+    """W [O,C,kh,kw], s [B,C] -> (d [B,O] = rsqrt(scale^2 sum_c s^2 sum_t W^2 + 1e-8), wsq [O,C] = sum_t W^2)
+    (multi_stylegan_generator.py:386-388)."""
+    _check_f32(W, "W")
+    _check_f32(s, "s")
+    W, s = _aligned(W), _aligned(s)
+    O, C, kh, kw = W.shape
+    B = s.size(0)
+    if s.shape != (B, C):
+        raise RuntimeError("demod_factors: style must be [B, C]")
+    d = torch.empty((B, O), dtype=torch.float32, device=W.device)
+    wsq = torch.empty((O, C), dtype=torch.float32, device=W.device)
+    with _on_device(W.device):
+        rc = _lib.lib().msg_demod_factors(_ptr(d), _ptr(wsq), _ptr(W), _ptr(s), B, O, C, kh * kw, float(scale), _stream(W))
+    _lib.check(rc, "demod_factors")
+    return d, wsq
+
+
+def _bc_stride(t: Optional[torch.Tensor], B: int, C: int, name: str) -> int:
+    if t is None:
+        return 0
+    if t.numel() == B * C:
+        return C
+    if t.numel() == C:
+        return 0
+    raise RuntimeError("%s must be [B or 1, %d]" % (name, C))
+
+
+def styled_act_bwd(g_out: Optional[torch.Tensor], g_out2: Optional[torch.Tensor], out: torch.Tensor,
+                   col_scale: Optional[torch.Tensor], out2_scale: Optional[torch.Tensor],
+                   noise: Optional[torch.Tensor], slope: float, gain: float):
+    """(g_pre [B,C,H,W] channels-last, sums [4,B,C]) — see msg_styled_act_bwd in include/msg_b200.h."""
+    _check_f32(out, "out")
+    out = _cl(out)
+    B, C, H, W = out.shape
+    if C % 4:
+        raise RuntimeError("styled_act_bwd: channel count must be a multiple of 4")
+    if g_out is None and g_out2 is None:
+        raise RuntimeError("styled_act_bwd: at least one incoming gradient is needed")
+    if g_out is not None:
+        _check_f32(g_out, "g_out")
+        g_out = _cl(g_out)
+    if g_out2 is not None:
+        _check_f32(g_out2, "g_out2")
+        g_out2 = _cl(g_out2)
+        if out2_scale is None:
+            raise RuntimeError("styled_act_bwd: g_out2 needs out2_scale")
+    for t in (g_out, g_out2):
+        if t is not None and t.shape != out.shape:
+            raise RuntimeError("styled_act_bwd: gradients must have the shape of out")
+    if col_scale is not None:
+        col_scale = _aligned(col_scale)
+    if out2_scale is not None:
+        out2_scale = _aligned(out2_scale)
+    nbs = 0
+    if noise is not None:
+        _check_f32(noise, "noise")
+        noise = _aligned(noise)
+        if noise.numel() == B * H * W and B > 1:
+            nbs = H * W
+        elif noise.numel() != H * W:
+            raise RuntimeError("styled_act_bwd: noise must be [B or 1, 1, H, W]")
+    g_pre = torch.empty_like(out)
+    sums = torch.empty((4, B, C), dtype=torch.float32, device=out.device)
+    L = _lib.lib()
+    with _on_device(out.device):
+        nbytes = L.msg_styled_act_bwd_workspace(B, H * W, C)
+        ws, wsp = _workspace(nbytes, out.device)
+        rc = L.msg_styled_act_bwd(_ptr(g_pre), _ptr(sums), _ptr(g_out), _ptr(g_out2), _ptr(out), _ptr(col_scale),
+                                  _bc_stride(col_scale, B, C, "col_scale"), _ptr(out2_scale) if g_out2 is not None else None,
+                                  _bc_stride(out2_scale, B, C, "out2_scale"), _ptr(noise), nbs, B, H * W, C,
+                                  float(slope), float(gain), wsp, nbytes, _stream(out))
+    _lib.check(rc, "styled_act_bwd")
+    return g_pre, sums
+
+
+def blur_noise_bias_act_mod(x: torch.Tensor, kernel: torch.Tensor, pad: Sequence[int], col_scale: Optional[torch.Tensor],
+                            noise: Optional[torch.Tensor], noise_w: Optional[torch.Tensor], bias: Optional[torch.Tensor],
+                            slope: float, gain: float, out2_scale: Optional[torch.Tensor]):
+    """(out, out2 or None): out = lrelu(col_scale[b,c] * fir(x) + noise_w * noise + bias[c]) * gain,
+    out2 = out * out2_scale[b,c] — msg_upfirdn2d_bias_act_mod."""
+    _check_f32(x, "x")
+    _require_cuda(kernel, "kernel")
+    x = _cl(x)
+    k = kernel.contiguous().to(torch.float32)
+    B, C, H, W = x.shape
+    kh, kw = k.shape
+    px0, px1, py0, py1 = [int(v) for v in pad]
+    L = _lib.lib()
+    out_h = L.msg_upfirdn2d_out_size(H, 1, 1, py0, py1, kh)
+    out_w = L.msg_upfirdn2d_out_size(W, 1, 1, px0, px1, kw)
+    if out_h < 0 or out_w < 0:
+        raise RuntimeError("blur_noise_bias_act_mod: negative output size")
+    out = torch.empty((B, C, out_h, out_w), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    out2 = torch.empty_like(out) if out2_scale is not None else None
+    nbs = 0
+    if noise is not None:
+        _check_f32(noise, "noise")
+        noise, noise_w = _aligned(noise), _aligned(noise_w)
+        if noise.numel() == B * out_h * out_w and B > 1:
+            nbs = out_h * out_w
+        elif noise.numel() != out_h * out_w:
+            raise RuntimeError("blur_noise_bias_act_mod: noise must be [B or 1, 1, OH, OW]")
+    if bias is not None:
+        bias = _aligned(bias)
+    if col_scale is not None:
+        col_scale = _aligned(col_scale)
+    if out2_scale is not None:
+        out2_scale = _aligned(out2_scale)
+    with _on_device(x.device):
+        rc = L.msg_upfirdn2d_bias_act_mod(_ptr(out), _ptr(out2), _ptr(x), _ptr(k), B, H, W, C, kh, kw, px0, px1, py0, py1,
+                                          _ptr(col_scale), _bc_stride(col_scale, B, C, "col_scale"), _ptr(noise),
+                                          _ptr(noise_w) if noise is not None else None, nbs, _ptr(bias), 1, float(slope),
+                                          float(gain), _ptr(out2_scale), _bc_stride(out2_scale, B, C, "out2_scale"),
+                                          _stream(x))
+    _lib.check(rc, "upfirdn2d_bias_act_mod")
+    return out, out2
 
 
 def affine_warp(x: torch.Tensor, theta: torch.Tensor, mode: int = 0) -> torch.Tensor:

@@ -34,7 +34,9 @@ class ConvEpilogue(ctypes.Structure):
     """msg_conv_epilogue (include/msg_b200.h)."""
     _fields_ = [("bias", ctypes.c_void_p), ("noise", ctypes.c_void_p), ("noise_w", ctypes.c_void_p),
                 ("noise_batch_stride", ctypes.c_int64), ("add", ctypes.c_void_p), ("act", ctypes.c_int),
-                ("slope", ctypes.c_float), ("gain", ctypes.c_float)]
+                ("slope", ctypes.c_float), ("gain", ctypes.c_float),
+                ("col_scale", ctypes.c_void_p), ("col_scale_batch_stride", ctypes.c_int64),
+                ("y2", ctypes.c_void_p), ("y2_scale", ctypes.c_void_p), ("y2_scale_batch_stride", ctypes.c_int64)]
 
 
 class ProfileEntry(ctypes.Structure):
@@ -89,6 +91,17 @@ _SIGNATURES = {
     "msg_upfirdn2d_bias_act": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64] + [_c.c_int] * 9 +
                                [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int, _c.c_float, _c.c_float,
                                 _c.c_void_p]),
+    "msg_upfirdn2d_bias_act_mod": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64] +
+                                   [_c.c_int] * 9 + [_c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_void_p, _c.c_int64,
+                                                     _c.c_void_p, _c.c_int, _c.c_float, _c.c_float, _c.c_void_p,
+                                                     _c.c_int64, _c.c_void_p]),
+    "msg_demod_factors": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int,
+                                     _c.c_int, _c.c_float, _c.c_void_p]),
+    "msg_styled_act_bwd_workspace": (_c.c_size_t, [_c.c_int, _c.c_int64, _c.c_int]),
+    "msg_styled_act_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                      _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_void_p, _c.c_int64, _c.c_int,
+                                      _c.c_int64, _c.c_int, _c.c_float, _c.c_float, _c.c_void_p, _c.c_size_t,
+                                      _c.c_void_p]),
     "msg_conv2d_workspace": (_c.c_size_t, [_c.POINTER(ConvDesc), _c.c_int, _c.c_int]),
     "msg_conv2d_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc), _c.c_float,
                                       _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),

@@ -182,7 +182,7 @@ class _ConvAddScale(Function):
     @staticmethod
     def backward(ctx, gout):
         x, w, x2 = ctx.saved_tensors
-        g = gout * ctx.gain
+        g = gout if ctx.gain == 1.0 else gout * ctx.gain
         dx = dw = dx2 = None
         if ctx.has_x2:
             dx, dx2, dw = _cat2_backward(g, x, x2, w, ctx.stride, ctx.padding, ctx.alpha, ctx.needs_input_grad[0],

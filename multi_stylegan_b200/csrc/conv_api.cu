@@ -200,6 +200,8 @@ static FwdPlan plan_forward(const msg_conv_desc* d, const float* x, const float*
   if (ep) {
     g.ep.bias = ep->bias; g.ep.noise = ep->noise; g.ep.noise_w = ep->noise_w; g.ep.noise_sb = ep->noise_batch_stride;
     g.ep.add = ep->add; g.ep.act = ep->act; g.ep.slope = ep->slope; g.ep.gain = ep->gain;
+    g.ep.cscale = ep->col_scale; g.ep.cscale_sb = ep->col_scale_batch_stride;
+    g.ep.out2 = ep->y2; g.ep.out2_scale = ep->y2_scale; g.ep.out2_scale_sb = ep->y2_scale_batch_stride;
   }
   g.in = x; g.Cr = d->C; g.IH = d->H; g.IW = d->W; g.is = dense_view(d->layout, d->C, d->H, d->W);
   g.my = s; g.mx = s;
@@ -466,6 +468,12 @@ extern "C" int msg_conv2d_forward_fused(float* y, const float* x, const float* w
     if (ep->act != 0 && ep->act != 1) return fail(MSG_ERR_BAD_ARG, "conv2d_forward: epilogue act must be 0 or 1");
     if (ep->noise && ep->noise_batch_stride != 0 && ep->noise_batch_stride != (int64_t)d->OH * d->OW)
       return fail(MSG_ERR_BAD_ARG, "conv2d_forward: noise_batch_stride must be 0 or OH*OW");
+    if (ep->y2 && !ep->y2_scale) return fail(MSG_ERR_BAD_ARG, "conv2d_forward: y2 needs y2_scale");
+    if ((ep->y2 || ep->col_scale) && ep->add)
+      return fail(MSG_ERR_UNSUPPORTED, "conv2d_forward: col_scale / y2 cannot be combined with a residual operand");
+    if ((ep->col_scale && ep->col_scale_batch_stride != 0 && ep->col_scale_batch_stride != d->O) ||
+        (ep->y2 && ep->y2_scale_batch_stride != 0 && ep->y2_scale_batch_stride != d->O))
+      return fail(MSG_ERR_BAD_ARG, "conv2d_forward: channel-scale batch strides must be 0 or O");
   }
   cudaStream_t st = (cudaStream_t)stream;
   FwdPlan pl = plan_forward(d, x, w, y, alpha, flags, ep);

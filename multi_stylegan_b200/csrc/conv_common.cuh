@@ -25,12 +25,13 @@ struct View4 {            // element strides of a [B, C, H, W] tensor
 };
 
 // Fused output transform of a PixGemm (StyledConv2d / ResNetBlock epilogues):
-//   v = alpha * acc
+//   v = alpha * acc * cscale[b * cscale_sb + n]                (cscale != nullptr: per-sample demodulation factor)
 //   v += noise_w[0] * noise[b * noise_sb + y * PW + x]         (noise != nullptr; unscattered outputs only)
 //   v += bias[n]                                               (bias != nullptr)
 //   v = v > 0 ? v : slope * v                                  (act == 1)
 //   v += add[same offset as out]                               (add != nullptr)
 //   out = v * gain
+//   out2 = out * out2_scale[b * out2_scale_sb + n]             (out2 != nullptr: the next layer's modulated input)
 struct Epilogue {
   const float* bias;
   const float* noise;
@@ -39,7 +40,12 @@ struct Epilogue {
   const float* add;
   int act;
   float slope, gain;
-  __host__ __device__ bool any() const { return bias || noise || add || act || gain != 1.f; }
+  const float* cscale;      // [B or 1, N] multiplier of the accumulator (before noise / bias)
+  int64_t cscale_sb;
+  float* out2;              // second output with the layout of `out`
+  const float* out2_scale;  // [B or 1, N]
+  int64_t out2_scale_sb;
+  __host__ __device__ bool any() const { return bias || noise || add || act || gain != 1.f || cscale || out2; }
 };
 
 __device__ __forceinline__ float apply_epilogue(const Epilogue& e, float v, float bias_n, float noise_term, float addv) {

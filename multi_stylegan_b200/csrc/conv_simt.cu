@@ -88,7 +88,10 @@ pixgemm_simt_kernel(const PixGemm g) {
         const int64_t off = (int64_t)n * g.os.sc + o;
         const float bn = g.ep.bias ? __ldg(g.ep.bias + n) : 0.f;
         const float av = g.ep.add ? __ldg(g.ep.add + (int64_t)b * g.os.sb + off) : 0.f;
-        outb[off] = apply_epilogue(g.ep, g.alpha * acc[i][j], bn, nz, av);
+        const float cs = g.ep.cscale ? __ldg(g.ep.cscale + (int64_t)b * g.ep.cscale_sb + n) : 1.f;
+        const float o1 = apply_epilogue(g.ep, g.alpha * acc[i][j] * cs, bn, nz, av);
+        outb[off] = o1;
+        if (g.ep.out2) g.ep.out2[(int64_t)b * g.os.sb + off] = o1 * __ldg(g.ep.out2_scale + (int64_t)b * g.ep.out2_scale_sb + n);
       }
     }
   }

@@ -316,14 +316,24 @@ struct TcPixParams {
 // One 32-channel chunk of the TMA-store epilogue: fused transform in registers, then the pixel's 128-byte row goes to
 // the swizzled staging box.  The epilogue warps are one warp per scheduler, so this loop is bound by its instruction
 // count: the three common transforms are compiled select-free (NB = noise/bias term, ACT = leaky ReLU, ADD = residual).
-template <bool NB, bool ACT, bool ADD>
+template <bool NB, bool ACT, bool ADD, bool MOD = false>
 __device__ __forceinline__ void epi_chunk_to_smem(const float (&rr)[32], const float4 (&av)[8], const float* bias_nb,
                                                   int nvalid4, float nz, float alpha, float slope, float gain,
-                                                  uint32_t dst, int lane) {
-  const float a2 = (!NB && !ACT && !ADD) ? alpha * gain : alpha;
+                                                  uint32_t dst, int lane, const float* cs_nb = nullptr,
+                                                  const float* s2_nb = nullptr, uint32_t dst2 = 0) {
+  // MOD (the generator's shared-weight modulated convolution): the accumulator is scaled per output channel by the
+  // sample's demodulation factor cs[n] before the noise / bias terms, and a second box out * s2[n] (the next layer's
+  // modulated input) is staged next to the first.
+  const float a2 = (!NB && !ACT && !ADD && !MOD) ? alpha * gain : alpha;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float v[4] = {rr[4 * j + 0] * a2, rr[4 * j + 1] * a2, rr[4 * j + 2] * a2, rr[4 * j + 3] * a2};
+    if (MOD) {
+      if (cs_nb != nullptr && j < nvalid4) {
+        const float4 c4 = __ldg(reinterpret_cast<const float4*>(cs_nb) + j);
+        v[0] *= c4.x; v[1] *= c4.y; v[2] *= c4.z; v[3] *= c4.w;
+      }
+    }
     if (NB) {
       float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
       if (bias_nb != nullptr && j < nvalid4) bz = __ldg(reinterpret_cast<const float4*>(bias_nb) + j);
@@ -334,12 +344,19 @@ __device__ __forceinline__ void epi_chunk_to_smem(const float (&rr)[32], const f
       for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
     }
     if (ADD) { v[0] += av[j].x; v[1] += av[j].y; v[2] += av[j].z; v[3] += av[j].w; }
-    if (NB || ACT || ADD) {
+    if (NB || ACT || ADD || MOD) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[e] *= gain;
     }
-    const uint32_t a = dst + ((uint32_t)(j ^ (lane & 7)) << 4);
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    const uint32_t sw = (uint32_t)(j ^ (lane & 7)) << 4;
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + sw), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    if (MOD) {
+      if (dst2 != 0) {
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < nvalid4) s4 = __ldg(reinterpret_cast<const float4*>(s2_nb) + j);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst2 + sw), "f"(v[0] * s4.x), "f"(v[1] * s4.y), "f"(v[2] * s4.z), "f"(v[3] * s4.w) : "memory");
+      }
+    }
   }
 }
 
@@ -353,7 +370,7 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
                                              int x0, int n0, int sub, float nw, bool release, uint32_t release_bar,
                                              const CUtensorMap* tm_out = nullptr, uint32_t stage_smem = 0,
                                              const CUtensorMap* tm_add = nullptr, uint32_t add_bar = 0,
-                                             uint32_t* add_phase = nullptr) {
+                                             uint32_t* add_phase = nullptr, const CUtensorMap* tm_out2 = nullptr) {
   constexpr int CW = BN < 32 ? BN : 32;
   const int Wt = 1 << p.wt_log2;
       if (tm_out != nullptr && p.tma_store && CW == 32) {
@@ -372,6 +389,12 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
         const bool with_add = tm_add != nullptr && p.ep.add != nullptr;
         const bool has_bias = p.ep.bias != nullptr, has_nb = has_bias || p.ep.noise != nullptr, has_act = p.ep.act != 0;
         const float ep_alpha = p.alpha, ep_slope = p.ep.slope, ep_gain = p.ep.gain;
+        // modulated form (never combined with a residual operand, checked on the host): per-sample channel scales and
+        // the second output; both staging boxes are used per chunk
+        const bool has_mod = p.ep.cscale != nullptr || p.ep.out2 != nullptr;
+        const bool has_out2 = p.ep.out2 != nullptr && tm_out2 != nullptr;
+        const float* cs_b = p.ep.cscale ? p.ep.cscale + (int64_t)b * p.ep.cscale_sb : nullptr;
+        const float* s2_b = p.ep.out2 ? p.ep.out2_scale + (int64_t)b * p.ep.out2_scale_sb : nullptr;
         if (with_add && n0 < p.N) {
           __syncwarp();                                     // every lane is done reading the previous tile's box
           if (lane == 0) {
@@ -413,13 +436,20 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
             } else {
 #pragma unroll
               for (int j = 0; j < 8; ++j) av[j] = make_float4(0.f, 0.f, 0.f, 0.f);   // (dead in the ADD = false variants)
-              if (lane == 0) tma_store_wait_read<1>();      // the box stored two chunks ago has left this buffer
+              if (lane == 0) {
+                if (has_out2) tma_store_wait_read<0>();     // both boxes of the previous chunk have left their buffers
+                else tma_store_wait_read<1>();              // the box stored two chunks ago has left this buffer
+              }
             }
             __syncwarp();
             const uint32_t dst = stage_smem + buf * 4096 + lane * 128;
             const float* bias_nb = has_bias ? p.ep.bias + nb : nullptr;
             const int nvalid4 = (p.N - nb + 3) >> 2;
-            if (!has_nb && !has_act && !with_add)
+            if (has_mod)
+              epi_chunk_to_smem<true, true, false, true>(rr, av, bias_nb, nvalid4, nz, ep_alpha, has_act ? ep_slope : 1.f, ep_gain,
+                                                         dst, lane, cs_b ? cs_b + nb : nullptr, s2_b ? s2_b + nb : nullptr,
+                                                         has_out2 ? stage_smem + 4096 : 0u);
+            else if (!has_nb && !has_act && !with_add)
               epi_chunk_to_smem<false, false, false>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
             else if (has_nb && has_act && !with_add)
               epi_chunk_to_smem<true, true, false>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
@@ -433,9 +463,10 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
             __syncwarp();
             if (lane == 0 && !(p.debug & 1)) {
               tma_store_4d(tm_out, stage_smem + buf * 4096, nb, bx, by, b);
+              if (has_out2) tma_store_4d(tm_out2, stage_smem + 4096, nb, bx, by, b);
               tma_store_commit();
             }
-            if (!with_add) buf ^= 1;
+            if (!with_add && !has_out2) buf ^= 1;
           }
         }
       } else if (p.vec_store && CW == 32) {
@@ -479,17 +510,26 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
           if (n < p.N) {
             float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.ep.bias) bz = __ldg(reinterpret_cast<const float4*>(p.ep.bias + n));
+            float4 cs = make_float4(p.alpha, p.alpha, p.alpha, p.alpha);
+            if (p.ep.cscale) {
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.ep.cscale + (int64_t)b * p.ep.cscale_sb + n));
+              cs.x *= c4.x; cs.y *= c4.y; cs.z *= c4.z; cs.w *= c4.w;
+            }
+            float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.ep.out2) s2 = __ldg(reinterpret_cast<const float4*>(p.ep.out2_scale + (int64_t)b * p.ep.out2_scale_sb + n));
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               if (poff[i] >= 0) {
                 const float* sp = stg + (i * 4 + psub) * 33 + ch4;
                 const int64_t off = poff[i] + n;
                 float4 o;
-                o.x = apply_epilogue(p.ep, p.alpha * sp[0], bz.x, pnz[i], av[i].x);
-                o.y = apply_epilogue(p.ep, p.alpha * sp[1], bz.y, pnz[i], av[i].y);
-                o.z = apply_epilogue(p.ep, p.alpha * sp[2], bz.z, pnz[i], av[i].z);
-                o.w = apply_epilogue(p.ep, p.alpha * sp[3], bz.w, pnz[i], av[i].w);
+                o.x = apply_epilogue(p.ep, cs.x * sp[0], bz.x, pnz[i], av[i].x);
+                o.y = apply_epilogue(p.ep, cs.y * sp[1], bz.y, pnz[i], av[i].y);
+                o.z = apply_epilogue(p.ep, cs.z * sp[2], bz.z, pnz[i], av[i].z);
+                o.w = apply_epilogue(p.ep, cs.w * sp[3], bz.w, pnz[i], av[i].w);
                 *reinterpret_cast<float4*>(p.out + off) = o;
+                if (p.ep.out2)
+                  *reinterpret_cast<float4*>(p.ep.out2 + off) = make_float4(o.x * s2.x, o.y * s2.y, o.z * s2.z, o.w * s2.w);
               }
             }
           }
@@ -527,7 +567,10 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
               const int64_t off = obase + (int64_t)n * p.os.sc;
               const float bn = p.ep.bias ? __ldg(p.ep.bias + n) : 0.f;
               const float av = p.ep.add ? __ldg(p.ep.add + off) : 0.f;
-              p.out[off] = apply_epilogue(p.ep, p.alpha * rr[j], bn, nz, av);
+              const float cs = p.ep.cscale ? __ldg(p.ep.cscale + (int64_t)b * p.ep.cscale_sb + n) : 1.f;
+              const float o1 = apply_epilogue(p.ep, p.alpha * rr[j] * cs, bn, nz, av);
+              p.out[off] = o1;
+              if (p.ep.out2) p.ep.out2[off] = o1 * __ldg(p.ep.out2_scale + (int64_t)b * p.ep.out2_scale_sb + n);
             }
           }
         }
@@ -542,7 +585,7 @@ template <int BN, int STAGES, int MT>
 __global__ void __launch_bounds__(192, 1)
 tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ CUtensorMap tmB,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
-                  const TcPixParams p) {
+                  const __grid_constant__ CUtensorMap tmOut2, const TcPixParams p) {
   // MT = 128-pixel sub-tiles per CTA tile: narrow-N layers (BN <= 128) take two, which halves the weight bytes and
   // TMA boxes per FLOP (one A box of 256 pixels, one B box, two MMAs per k-step sharing the B descriptor).
   constexpr uint32_t A_BYTES = MT * 128 * 32 * 4;
@@ -679,7 +722,7 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
       const bool last_sub = sub == MT - 1;
 
       pix_epilogue<BN, false>(p, stg, tlane, q, lane, b, y0, x0, n0, sub, nw, last_sub, acc_empty + 8 * a, &tmOut, stage_smem,
-                              &tmAdd, add_bars + 8 * q, &add_phase);
+                              &tmAdd, add_bars + 8 * q, &add_phase, &tmOut2);
       }  // sub
     }
     if (p.tma_store && lane == 0) tma_store_wait_read<0>();   // staging buffers must outlive their bulk stores
@@ -702,7 +745,7 @@ template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 tc_pixgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
-                   const TcPixParams p) {
+                   const __grid_constant__ CUtensorMap tmOut2, const TcPixParams p) {
   static_assert(BN == 256 || BN == 128, "pair tiles are 256 pixels x 256 or 128 channels");
   constexpr uint32_t A_BYTES = 128 * 32 * 4;
   constexpr uint32_t B_BYTES = (BN / 2) * 32 * 4;
@@ -833,7 +876,7 @@ tc_pixgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       tc_fence_after();
       const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + a * BN;
       pix_epilogue<BN, true>(p, stg, tlane, q, lane, b, y0, x0, n0, 0, nw, true, acc_empty_leader + 8 * a, &tmOut,
-                             stage_smem, &tmAdd, add_bars + 8 * q, &add_phase);
+                             stage_smem, &tmAdd, add_bars + 8 * q, &add_phase, &tmOut2);
     }
     if (p.tma_store && lane == 0) tma_store_wait_read<0>();   // staging buffers must outlive their bulk stores
   }
@@ -1138,7 +1181,7 @@ size_t tc_pixgemm_workspace(const PixGemm& g) {
 
 template <int BN, int MT>
 static int launch_pix(const TMapSet& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAdd,
-                      const TcPixParams& p, cudaStream_t st) {
+                      const CUtensorMap& tmOut2, const TcPixParams& p, cudaStream_t st) {
   constexpr int STAGES = (BN == 256 || MT == 2) ? 4 : 6;
   constexpr size_t smem = (size_t)STAGES * (MT * 16384 + BN * 128) + 4 * 2 * 4096 + 16 * STAGES + 128 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
@@ -1151,7 +1194,7 @@ static int launch_pix(const TMapSet& tmA, const CUtensorMap& tmB, const CUtensor
   }
   // one persistent CTA per SM (two co-resident ones would have to share TMEM columns and the smem ring)
   const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  kfn<<<ctas, 192, smem, st>>>(tmA, tmB, tmOut, tmAdd, p);
+  kfn<<<ctas, 192, smem, st>>>(tmA, tmB, tmOut, tmAdd, tmOut2, p);
   MSG_CHECK_LAUNCH("conv pixgemm(tcgen05)");
   return MSG_OK;
 }
@@ -1172,7 +1215,7 @@ static int max_active_pairs(const void* kfn, size_t smem) {
 
 template <int BN>
 static int launch_pix2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAdd,
-                       const TcPixParams& p, cudaStream_t st) {
+                       const CUtensorMap& tmOut2, const TcPixParams& p, cudaStream_t st) {
   constexpr int STAGES = BN == 256 ? 6 : 8;
   constexpr size_t smem = (size_t)STAGES * (16384 + (BN / 2) * 128) + 4 * 2 * 4096 + 16 * STAGES + 128 + 1024;
   static_assert(smem <= 227 * 1024, "shared memory budget");
@@ -1187,7 +1230,7 @@ static int launch_pix2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   const int pairs_max = pairs_max_dev[slot];
   if (pairs_max <= 0) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05, CTA pairs): no cluster can be resident");
   const int pairs = p.total_tiles < pairs_max ? p.total_tiles : pairs_max;
-  kfn<<<2 * pairs, 192, smem, st>>>(tmA, tmB, tmOut, tmAdd, p);
+  kfn<<<2 * pairs, 192, smem, st>>>(tmA, tmB, tmOut, tmAdd, tmOut2, p);
   MSG_CHECK_LAUNCH("conv pixgemm(tcgen05, CTA pairs)");
   return MSG_OK;
 }
@@ -1297,7 +1340,9 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (p.ep.noise && (g.out_my != 1 || g.out_mx != 1))
     return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): noise epilogue on a scattered output");
   p.vec_store = (g.os.sc == 1 && (g.N % 4 == 0) && al16(g.out) && g.os.sx % 4 == 0 && g.os.sy % 4 == 0 && g.os.sb % 4 == 0 &&
-                 (!p.ep.bias || al16(p.ep.bias)) && (!p.ep.add || al16(p.ep.add))) ? 1 : 0;
+                 (!p.ep.bias || al16(p.ep.bias)) && (!p.ep.add || al16(p.ep.add)) &&
+                 (!p.ep.cscale || (al16(p.ep.cscale) && p.ep.cscale_sb % 4 == 0)) &&
+                 (!p.ep.out2 || (al16(p.ep.out2) && al16(p.ep.out2_scale) && p.ep.out2_scale_sb % 4 == 0))) ? 1 : 0;
   // output tensor map for the TMA-store epilogue: the (possibly phase-scattered) NHWC output as a 4-D view
   // (N, PW, PH, B) whose pixel strides carry out_mx / out_my and whose base carries the phase offset
   CUtensorMap tmOut;
@@ -1305,6 +1350,11 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.tma_store = 0;
   CUtensorMap tmAdd;
   memset(&tmAdd, 0, sizeof(tmAdd));
+  CUtensorMap tmOut2;
+  memset(&tmOut2, 0, sizeof(tmOut2));
+  if ((p.ep.cscale || p.ep.out2) && p.ep.add)
+    return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): channel scales / second output together with a residual operand");
+  if (p.ep.out2 && !p.ep.out2_scale) return fail(MSG_ERR_BAD_ARG, "conv pixgemm(tcgen05): out2 needs out2_scale");
   if (p.vec_store && BN >= 32 && !(tc_variant() & 16u)) {
     const int bw = Wt < 32 ? Wt : 32;
     const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B};
@@ -1316,6 +1366,9 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (ok && p.ep.add)       // the residual operand has the layout of the output: same view, other base
       ok = al16(p.ep.add + view_off) &&
            make_tmap(&tmAdd, p.ep.add + view_off, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) == MSG_OK;
+    if (ok && p.ep.out2)      // second output: same view, other base
+      ok = al16(p.ep.out2 + view_off) &&
+           make_tmap(&tmOut2, p.ep.out2 + view_off, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B) == MSG_OK;
     p.tma_store = ok ? 1 : 0;
     p.debug = (int)((tc_variant() >> 5) & 3u);
   }
@@ -1324,21 +1377,21 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);
   int rc;
   if (pairs) {
-    rc = BN == 256 ? launch_pix2<256>(tmA.m[0], tmB, tmOut, tmAdd, p, st) : launch_pix2<128>(tmA.m[0], tmB, tmOut, tmAdd, p, st);
+    rc = BN == 256 ? launch_pix2<256>(tmA.m[0], tmB, tmOut, tmAdd, tmOut2, p, st) : launch_pix2<128>(tmA.m[0], tmB, tmOut, tmAdd, tmOut2, p, st);
   } else if (MT == 2) {
     switch (BN) {
-      case 128: rc = launch_pix<128, 2>(tmA, tmB, tmOut, tmAdd, p, st); break;
-      case 64: rc = launch_pix<64, 2>(tmA, tmB, tmOut, tmAdd, p, st); break;
-      case 32: rc = launch_pix<32, 2>(tmA, tmB, tmOut, tmAdd, p, st); break;
-      default: rc = launch_pix<16, 2>(tmA, tmB, tmOut, tmAdd, p, st); break;
+      case 128: rc = launch_pix<128, 2>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st); break;
+      case 64: rc = launch_pix<64, 2>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st); break;
+      case 32: rc = launch_pix<32, 2>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st); break;
+      default: rc = launch_pix<16, 2>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st); break;
     }
   } else {
     switch (BN) {
-      case 256: rc = launch_pix<256, 1>(tmA, tmB, tmOut, tmAdd, p, st); break;
-      case 128: rc = launch_pix<128, 1>(tmA, tmB, tmOut, tmAdd, p, st); break;
-      case 64: rc = launch_pix<64, 1>(tmA, tmB, tmOut, tmAdd, p, st); break;
-      case 32: rc = launch_pix<32, 1>(tmA, tmB, tmOut, tmAdd, p, st); break;
-      default: rc = launch_pix<16, 1>(tmA, tmB, tmOut, tmAdd, p, st); break;
+      case 256: rc = launch_pix<256, 1>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st); break;
+      case 128: rc = launch_pix<128, 1>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st); break;
+      case 64: rc = launch_pix<64, 1>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st); break;
+      case 32: rc = launch_pix<32, 1>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st); break;
+      default: rc = launch_pix<16, 1>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st); break;
     }
   }
   prof_end(pslot, pstop, st);

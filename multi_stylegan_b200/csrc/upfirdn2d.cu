@@ -153,6 +153,13 @@ struct FirClParams {
   int64_t ep_noise_bs;
   int ep_act;
   float ep_slope, ep_gain;
+  // shared-weight modulated up-convolution: v = cscale[b, c] * fir(x) + noise + bias (demodulation commutes with the
+  // per-channel FIR), second output out2 = out * out2_scale[b, c] (the next layer's modulated input)
+  const float* ep_cscale;
+  int64_t ep_cscale_bs;
+  float4* ep_out2;
+  const float* ep_out2_scale;
+  int64_t ep_out2_scale_bs;
 };
 
 __device__ __forceinline__ void fma4(float4& a, const float4& v, float k) {
@@ -200,9 +207,14 @@ fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, cons
   for (int s = 0; s < 4; ++s)
 #pragma unroll
     for (int c = 0; c < COLS; ++c) acc[s][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool fused = p.ep_act || p.ep_bias || p.ep_noise;
+  const bool fused = p.ep_act || p.ep_bias || p.ep_noise || p.ep_cscale || p.ep_out2;
   float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
   if (p.ep_bias) bz = __ldg(reinterpret_cast<const float4*>(p.ep_bias) + q);
+  float4 cs = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (p.ep_cscale) cs = __ldg(reinterpret_cast<const float4*>(p.ep_cscale + b * p.ep_cscale_bs) + q);
+  float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.ep_out2) s2 = __ldg(reinterpret_cast<const float4*>(p.ep_out2_scale + b * p.ep_out2_scale_bs) + q);
+  float4* out2b = p.ep_out2 ? p.ep_out2 + (b * p.out_h * (int64_t)p.out_w) * p.C4 + q : nullptr;
   const float nw = p.ep_noise ? __ldg(p.ep_noise_w) : 0.f;
   const float* nzb = p.ep_noise ? p.ep_noise + b * p.ep_noise_bs : nullptr;
 
@@ -242,7 +254,8 @@ fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, cons
               float4 v = acc[s][c];
               if (fused) {
                 const float add = nzb ? nw * __ldg(nzb + (int64_t)oy * p.out_w + ox0 + c) : 0.f;
-                v.x += add + bz.x; v.y += add + bz.y; v.z += add + bz.z; v.w += add + bz.w;
+                v.x = fmaf(v.x, cs.x, add + bz.x); v.y = fmaf(v.y, cs.y, add + bz.y);
+                v.z = fmaf(v.z, cs.z, add + bz.z); v.w = fmaf(v.w, cs.w, add + bz.w);
                 if (p.ep_act) {
                   v.x = v.x > 0.f ? v.x : v.x * p.ep_slope; v.y = v.y > 0.f ? v.y : v.y * p.ep_slope;
                   v.z = v.z > 0.f ? v.z : v.z * p.ep_slope; v.w = v.w > 0.f ? v.w : v.w * p.ep_slope;
@@ -250,6 +263,8 @@ fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, cons
                 v.x *= p.ep_gain; v.y *= p.ep_gain; v.z *= p.ep_gain; v.w *= p.ep_gain;
               }
               orow[(int64_t)(ox0 + c) * p.C4] = v;
+              if (out2b)
+                out2b[((int64_t)oy * p.out_w + ox0 + c) * p.C4] = make_float4(v.x * s2.x, v.y * s2.y, v.z * s2.z, v.w * s2.w);
             }
         }
 #pragma unroll
@@ -508,6 +523,7 @@ extern "C" int msg_upfirdn2d_out_size(int in_size, int up, int down, int pad0, i
 
 struct FirEpilogue {
   const float* noise; const float* noise_w; const float* bias; int64_t noise_bs; int act; float slope, gain;
+  const float* cscale; int64_t cscale_bs; float* out2; const float* out2_scale; int64_t out2_scale_bs;
 };
 
 static int upfirdn2d_impl(void* out, const void* in, const void* kernel, int64_t major, int in_h,
@@ -530,7 +546,26 @@ extern "C" int msg_upfirdn2d_bias_act(float* out, const float* in, const float* 
   if (noise && !noise_w) return fail(MSG_ERR_BAD_ARG, "upfirdn2d_bias_act: noise needs noise_w");
   if (act != 0 && act != 1) return fail(MSG_ERR_BAD_ARG, "upfirdn2d_bias_act: act must be 0 or 1");
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 15u)) return fail(MSG_ERR_BAD_ARG, "upfirdn2d_bias_act: bias must be 16-byte aligned");
-  FirEpilogue ep{noise, noise_w, bias, noise_batch_stride, act, slope, gain};
+  FirEpilogue ep{noise, noise_w, bias, noise_batch_stride, act, slope, gain, nullptr, 0, nullptr, nullptr, 0};
+  return upfirdn2d_impl(out, in, kernel, major, in_h, in_w, minor, kernel_h, kernel_w, 1, 1, 1, 1, pad_x0, pad_x1, pad_y0,
+                        pad_y1, MSG_F32, stream, &ep);
+}
+
+extern "C" int msg_upfirdn2d_bias_act_mod(float* out, float* out2, const float* in, const float* kernel, int64_t major,
+                                          int in_h, int in_w, int minor, int kernel_h, int kernel_w, int pad_x0, int pad_x1,
+                                          int pad_y0, int pad_y1, const float* col_scale, int64_t col_scale_batch_stride,
+                                          const float* noise, const float* noise_w, int64_t noise_batch_stride,
+                                          const float* bias, int act, float slope, float gain, const float* out2_scale,
+                                          int64_t out2_scale_batch_stride, msg_stream_t stream) {
+  if (noise && !noise_w) return fail(MSG_ERR_BAD_ARG, "upfirdn2d_bias_act_mod: noise needs noise_w");
+  if (act != 0 && act != 1) return fail(MSG_ERR_BAD_ARG, "upfirdn2d_bias_act_mod: act must be 0 or 1");
+  if (out2 && !out2_scale) return fail(MSG_ERR_BAD_ARG, "upfirdn2d_bias_act_mod: out2 needs out2_scale");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(col_scale) |
+                       reinterpret_cast<uintptr_t>(out2) | reinterpret_cast<uintptr_t>(out2_scale);
+  if ((al & 15u) || (col_scale_batch_stride % 4) || (out2_scale_batch_stride % 4))
+    return fail(MSG_ERR_BAD_ARG, "upfirdn2d_bias_act_mod: bias / scales / out2 must be 16-byte aligned");
+  FirEpilogue ep{noise, noise_w, bias, noise_batch_stride, act, slope, gain, col_scale, col_scale_batch_stride,
+                 out2, out2_scale, out2_scale_batch_stride};
   return upfirdn2d_impl(out, in, kernel, major, in_h, in_w, minor, kernel_h, kernel_w, 1, 1, 1, 1, pad_x0, pad_x1, pad_y0,
                         pad_y1, MSG_F32, stream, &ep);
 }
@@ -578,6 +613,8 @@ static int upfirdn2d_impl(void* out, const void* in, const void* kernel, int64_t
     if (ep) {
       p.ep_noise = ep->noise; p.ep_noise_w = ep->noise_w; p.ep_bias = ep->bias; p.ep_noise_bs = ep->noise_bs;
       p.ep_act = ep->act; p.ep_slope = ep->slope; p.ep_gain = ep->gain;
+      p.ep_cscale = ep->cscale; p.ep_cscale_bs = ep->cscale_bs;
+      p.ep_out2 = reinterpret_cast<float4*>(ep->out2); p.ep_out2_scale = ep->out2_scale; p.ep_out2_scale_bs = ep->out2_scale_bs;
     }
     if (up_x == 1 && down_x == 1) {
       constexpr int COLS = 2;

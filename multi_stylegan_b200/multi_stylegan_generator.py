@@ -17,10 +17,31 @@ import torch
 import torch.nn as nn
 from torch import autograd
 
-from . import conv, equalized_layer
+from . import conv, equalized_layer, styled
 from .op_static import FusedLeakyReLU, upfirdn2d
 from .op_static.fused_act import noise_bias_leaky_relu
 from .op_static.upfirdn2d import blur_noise_bias_leaky_relu
+
+
+# The generator has two arithmetically equivalent execution forms (see styled.py): the shared-weight form with
+# hand-written first-order backwards (default; used by no_grad forwards and the generator step) and the reference's
+# per-sample-weight form, every piece of which is differentiable to any order (path-length regularisation).
+_higher_order = 0
+
+
+class higher_order_gradients(object):
+    """Context manager: generator forwards recorded inside can be differentiated through their backward pass
+    (autograd.grad(..., create_graph=True)); Generator.forward(return_path_length_grads=True) enters it itself."""
+
+    def __enter__(self):
+        global _higher_order
+        _higher_order += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _higher_order
+        _higher_order -= 1
+        return False
 
 
 def _fir_kernel(taps: List[int]) -> torch.Tensor:
@@ -290,6 +311,7 @@ class Generator(nn.Module):
         self.latent_dimensions: int = config["latent_dimensions"]
         self.starting_resolution: Tuple[int, int] = config["starting_resolution"]
         self.compute_dead_branch = compute_dead_branch
+        self.fused_modconv = True        # False: always the per-sample-weight formulation (tests, A/B measurements)
         L = self.latent_dimensions
         self.style_mapping = StyleMapping(latent_dimensions=L, depth=config["depth_style_mapping"])
         self.constant_input_1 = ConstantInput(channel=ch[0], size=self.starting_resolution)
@@ -389,6 +411,73 @@ class Generator(nn.Module):
             noise_start, noise = noise[0], noise[1:]
         latent = self._latent(input, input_is_latent, inject_index)
         dead = self.compute_dead_branch
+        if return_path_length_grads:
+            with higher_order_gradients():
+                return self._forward_tail(latent, noise_start, noise, dead, True, path_length_noise, False)
+        return self._forward_tail(latent, noise_start, noise, dead, False, None, return_main_style_vectors)
+
+    def _fused_eligible(self, latent: torch.Tensor) -> bool:
+        """Shared-weight fast path: live branch only, channel counts the channels-last kernels take."""
+        if self.compute_dead_branch or _higher_order > 0 or not self.fused_modconv:
+            return False
+        convs = [self.starting_convolution_1, self.starting_convolution_2] + list(self.main_convolutions_1)
+        return all(c.modulated_convolution.out_channels % 4 == 0 and c.modulated_convolution.in_channels % 4 == 0
+                   and c.modulated_convolution.demodulate for c in convs)
+
+    def _synthesis_fused(self, latent: torch.Tensor, noise_start, noise) -> torch.Tensor:
+        """The live part of the network (branch 1 + the starting block of branch 2, reference :176-189) in the
+        shared-weight form: each layer's epilogue writes its activation and the same activation multiplied by the
+        NEXT layer's style, which is that layer's GEMM operand; styles and demodulation factors are [B, C] vectors."""
+        B = latent.shape[0]
+        dev = latent.device
+
+        def style_of(block: "StyledConv2d", w: torch.Tensor) -> torch.Tensor:
+            return block.modulated_convolution.modulation_mapping(w)                       # [B, C_in]
+
+        def draw(noise_map, h, w):
+            return torch.randn(B, 1, h, w, device=dev, dtype=torch.float32) if noise_map is None else noise_map
+
+        def run(block: "StyledConv2d", xs, s, noise_map, s_next):
+            mc, act = block.modulated_convolution, block.activation
+            if mc.upsampling:
+                kh, kw = mc.blur.kernel.shape
+                oh = (xs.shape[2] - 1) * mc.stride[0] + mc.kernel_size[0] + sum(mc.blur.padding) - kh + 1
+                ow = (xs.shape[3] - 1) * mc.stride[1] + mc.kernel_size[1] + sum(mc.blur.padding) - kw + 1
+                return styled.styled_up_conv(xs, mc.weight[0], s, mc.scale, mc.demodulate, mc.blur.kernel, mc.blur.padding,
+                                             draw(noise_map, oh, ow), block.noise_injection.weight, act.bias, s_next,
+                                             mc.stride, mc.padding, act.negative_slope, act.scale)
+            return styled.styled_conv(xs, mc.weight[0], s, mc.scale, mc.demodulate, draw(noise_map, xs.shape[2], xs.shape[3]),
+                                      block.noise_injection.weight, act.bias, s_next, mc.stride, mc.padding,
+                                      act.negative_slope, act.scale)
+
+        mains = self.main_convolutions_1
+        n_main = len(mains)
+        s0 = style_of(self.starting_convolution_1, latent[:, 0])
+        s_next = style_of(mains[0], latent[:, 1]) if n_main else None
+        sb = s0.view(B, -1, 1, 1)
+        out_1, xs = run(self.starting_convolution_1, self.constant_input_1.input * sb, s0, noise_start, s_next)
+        out_2, _ = run(self.starting_convolution_2, self.constant_input_2.input * sb, s0, noise_start, None)
+        skip_1, style = self.starting_output_block_1(out_1, latent[:, 1])
+        skip_2 = self.starting_output_block_2(out_2, style)
+        skip_12 = torch.cat([skip_1, skip_2], dim=1)
+        for i in range(n_main // 2):
+            s_up = s_next
+            s_cv = style_of(mains[2 * i + 1], latent[:, 2 * i + 2])
+            _, xs = run(mains[2 * i], xs, s_up, noise[2 * i], s_cv)
+            s_next = style_of(mains[2 * i + 2], latent[:, 2 * i + 3]) if 2 * i + 2 < n_main else None
+            out_1, xs = run(mains[2 * i + 1], xs, s_cv, noise[2 * i + 1], s_next)
+            skip_12, _ = self._paired_output(self.output_blocks_1[i], self.output_blocks_2[i], out_1,
+                                             latent[:, 2 * i + 3], skip_12)
+        return skip_12.reshape(B, 2, self.out_channels, skip_12.shape[2], skip_12.shape[3])
+
+    def _forward_tail(self, latent, noise_start, noise, dead, return_path_length_grads, path_length_noise,
+                      return_main_style_vectors):
+        n_main = len(self.main_convolutions_1)
+        if self._fused_eligible(latent):
+            image = self._synthesis_fused(latent, noise_start, noise)
+            if return_main_style_vectors:
+                return image, latent
+            return image
 
         out_1 = self.constant_input_1(latent)
         out_2 = self.constant_input_2(latent)

@@ -112,10 +112,13 @@ class ResNetBlock(nn.Module):
         x = self.mini_batch_std_dev(input)
         h = conv.conv2d_bias_act(x, c1.weight, bias=a1.bias, stride=c1.stride, padding=c1.padding,
                                  negative_slope=a1.negative_slope, gain=a1.scale, alpha=c1.scale, x2=input_2)
+        # the join's 1/sqrt(2) is folded into the second activation's gain and the residual convolution's alpha, so
+        # neither the forward nor the backward spends a pass on the scaling
+        j = 1.0 / math.sqrt(2)
         h = conv.conv2d_bias_act(h, c2.weight, bias=a2.bias, stride=c2.stride, padding=c2.padding,
-                                 negative_slope=a2.negative_slope, gain=a2.scale, alpha=c2.scale)
+                                 negative_slope=a2.negative_slope, gain=a2.scale * j, alpha=c2.scale)
         return conv.conv2d_add_scale(input, res.weight, h, stride=res.stride, padding=res.padding,
-                                     gain=1.0 / math.sqrt(2), alpha=res.scale, x2=input_2)
+                                     gain=1.0, alpha=res.scale * j, x2=input_2)
 
 
 class NonLocalBlock(nn.Module):
@@ -152,8 +155,9 @@ class NonLocalBlock(nn.Module):
         res = self.residual_mapping
         if isinstance(res, equalized_layer.EqualizedConv2d) and res.bias is None:
             # (gamma * o + conv1x1(x)) / sqrt(2) with the join in the residual conv's epilogue (:381)
-            return conv.conv2d_add_scale(input, res.weight, self.gamma * output, stride=res.stride, padding=res.padding,
-                                         gain=1.0 / math.sqrt(2), alpha=res.scale)
+            j = 1.0 / math.sqrt(2)
+            return conv.conv2d_add_scale(input, res.weight, (self.gamma * j) * output, stride=res.stride,
+                                         padding=res.padding, gain=1.0, alpha=res.scale * j)
         return (self.gamma * output + self.residual_mapping(input)) / math.sqrt(2)
 
 

@@ -5,7 +5,8 @@ import torch
 from oracle import ops
 
 __all__ = ["fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_forward", "conv2d_dgrad", "conv2d_wgrad",
-           "modulate_weights", "noise_bias_act", "affine_warp", "noise_bias_act_cl", "noise_bias_act_cl_bwd", "modulate_weights_bwd", "blur_noise_bias_act", "affine_warp_bwd"]
+           "modulate_weights", "noise_bias_act", "affine_warp", "noise_bias_act_cl", "noise_bias_act_cl_bwd", "modulate_weights_bwd", "blur_noise_bias_act", "affine_warp_bwd",
+           "demod_factors", "styled_act_bwd", "blur_noise_bias_act_mod"]
 
 
 def fused_bias_act(input, bias, refer, act, grad, alpha, scale):
@@ -27,10 +28,19 @@ def _wt(w, w_transposed):
 
 
 def conv2d_forward(x, w, stride=1, padding=0, alpha=1.0, bias=None, noise=None, noise_w=None, add=None, act=False,
-                   slope=0.2, gain=1.0, w_transposed=False, x2=None):
+                   slope=0.2, gain=1.0, w_transposed=False, x2=None, col_scale=None, out2_scale=None):
     if x2 is not None:
         x = torch.cat([x, x2], dim=1)
     v = ops.conv2d(x, _wt(w, w_transposed), stride, padding) * alpha
+    if col_scale is not None:
+        v = v * col_scale.reshape(-1, v.shape[1], 1, 1)
+    if out2_scale is not None:
+        y = _tail(v, bias, noise, noise_w, add, act, slope, gain)
+        return y, y * out2_scale.reshape(-1, y.shape[1], 1, 1)
+    return _tail(v, bias, noise, noise_w, add, act, slope, gain)
+
+
+def _tail(v, bias, noise, noise_w, add, act, slope, gain):
     if noise is not None:
         v = v + noise_w * noise
     if bias is not None:
@@ -97,3 +107,35 @@ def affine_warp_bwd(grad_output, theta, mode=0):
     with torch.enable_grad():
         y = ops.affine_warp(x, theta, mode)
         return torch.autograd.grad(y, x, grad_output)[0]
+
+
+def demod_factors(W, s, scale):
+    wsq = W.pow(2).sum(dim=(2, 3))
+    return torch.rsqrt(scale * scale * (s * s) @ wsq.t() + 1e-8), wsq
+
+
+def styled_act_bwd(g_out, g_out2, out, col_scale, out2_scale, noise, slope, gain):
+    B, C = out.shape[0], out.shape[1]
+    bc = lambda t: t.reshape(-1, C, 1, 1)
+    gt = torch.zeros_like(out) if g_out is None else g_out
+    if g_out2 is not None:
+        gt = gt + bc(out2_scale) * g_out2
+    pos = out > 0
+    gv = gt * torch.where(pos, torch.full_like(out, gain), torch.full_like(out, gain * slope))
+    v = out * torch.where(pos, torch.full_like(out, 1.0 / gain), torch.full_like(out, 1.0 / (gain * slope)))
+    g_pre = gv if col_scale is None else gv * bc(col_scale)
+    nz = torch.zeros(1, 1, out.shape[2], out.shape[3]) if noise is None else noise
+    s4 = torch.zeros(B, C) if g_out2 is None else (out * g_out2).sum(dim=(2, 3))
+    sums = torch.stack([gv.sum(dim=(2, 3)), (gv * v).sum(dim=(2, 3)), (gv * nz).sum(dim=(2, 3)), s4])
+    return g_pre, sums
+
+
+def blur_noise_bias_act_mod(x, kernel, pad, col_scale, noise, noise_w, bias, slope, gain, out2_scale):
+    px0, px1, py0, py1 = pad
+    B, C, H, W = x.shape
+    y = ops.upfirdn2d(x.reshape(-1, H, W, 1), kernel, 1, 1, 1, 1, px0, px1, py0, py1)
+    y = y.view(B, C, y.shape[1], y.shape[2])
+    if col_scale is not None:
+        y = y * col_scale.reshape(-1, C, 1, 1)
+    out = ops.noise_bias_act_masked(y, None, noise, noise_w, bias, slope, gain)
+    return out, (None if out2_scale is None else out * out2_scale.reshape(-1, C, 1, 1))

@@ -40,7 +40,7 @@ def test_no_torch_types_in_abi():
 
 def test_abi_version_and_pure_functions(built_library):
     L = built_library
-    assert L.msg_abi_version() == 2
+    assert L.msg_abi_version() == 3
     # upfirdn2d_kernel.cu:167-168
     assert L.msg_upfirdn2d_out_size(8, 1, 1, 2, 1, 4) == 8
     assert L.msg_upfirdn2d_out_size(127, 1, 1, 2, 2, 4) == 128

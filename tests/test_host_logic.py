@@ -305,3 +305,55 @@ def test_two_source_conv_functions_match_concat(oracle_backend):
     for two, one in pairs:
         for a, r in zip(run(two), run(one)):
             assert a.shape == r.shape and ((a - r).abs().max() / r.abs().max()).item() < 1e-4
+
+
+def test_generator_fused_shared_weight_path_equals_per_sample_path(oracle_backend, monkeypatch):
+    """The shared-weight form (styled.py: style on the activations, demodulation in the epilogue, one batch-reduced
+    wgrad) gives the image and the parameter / latent gradients of the reference's per-sample-weight form, is the path
+    taken by default when the dead branch is skipped, and refuses to be differentiated twice."""
+    from multi_stylegan_b200 import _C, styled
+    g = load_golden("generator.pt")
+    net = G_mod.Generator(g["config"], compute_dead_branch=False)
+    net.load_state_dict(g["state_dict"], strict=True)
+    with torch.no_grad():           # exercise the noise / bias terms (the fixture leaves noise weights at their init)
+        for n, p in net.named_parameters():
+            if n.endswith("noise_injection.weight"):
+                p.fill_(0.3)
+            if n.endswith("activation.bias"):
+                p.normal_(0, 0.2)
+    calls = {"n": 0}
+    real = _C.styled_act_bwd
+
+    def counted(*a, **k):
+        calls["n"] += 1
+        return real(*a, **k)
+    monkeypatch.setattr(_C, "styled_act_bwd", counted)
+    z = [t.clone().requires_grad_(True) for t in g["z"]]
+    noise = g["noise"]
+    direction = g["direction"]
+
+    def run(fused):
+        net.fused_modconv = fused
+        net.zero_grad()
+        for t in z:
+            t.grad = None
+        image = net(z, noise=noise, inject_index=g["inject_index"])
+        (image * direction).sum().backward()
+        return image.detach(), {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}, \
+            [t.grad.clone() for t in z]
+    img_f, grads_f, gz_f = run(True)
+    n_fused = calls["n"]
+    img_p, grads_p, gz_p = run(False)
+    assert n_fused == len(net.main_convolutions_1) + 2 and calls["n"] == n_fused
+    assert rel_err(img_f, img_p) < 1e-5
+    assert sorted(grads_f) == sorted(grads_p)
+    for n in grads_p:
+        assert rel_err(grads_f[n], grads_p[n]) < 2e-4, (n, rel_err(grads_f[n], grads_p[n]))
+    for a, b in zip(gz_f, gz_p):
+        assert rel_err(a, b) < 2e-4
+    net.fused_modconv = True
+    image = net(z, noise=noise, inject_index=g["inject_index"])
+    with pytest.raises(RuntimeError, match="first-order only"):
+        torch.autograd.grad((image * direction).sum(), z[0], create_graph=True)
+    # the path-length entry point switches to the any-order form by itself
+    assert net(g["z1"], noise=noise, return_path_length_grads=True).requires_grad
