@@ -4,14 +4,21 @@
 Stage order, gates and parameter distributions follow the reference exactly, including its quirks: one
 shared 90-degree rotation and one shared integer roll for all selected samples (:122, :210-211), lognormal
 sigma (0.2 ln 2)^2 (:141, :176), centre = 0.5 * (H, W) passed as (x, y) (:137-138), four *sequential*
-bilinear resamplings (each stage re-interpolates the previous stage's output).  The bilinear /
-reflection / align_corners warps run in one CUDA kernel per stage (csrc/misc_ops.cu: affine_warp) with a
-per-sample 2x3 matrix, identity for samples the gate skipped (exact copy).
+bilinear resamplings (each stage re-interpolates the previous stage's output), and the in-place update of the
+caller's batch (:118-187 assign into a view of the input, so the train step's later uses of the same real /
+fake tensors see the augmented images).
+
+Execution is split in two: the host draws the per-call random decisions in the reference's order
+(`sample_draws`) and packs them into ONE small tensor (`build_plan`: gate masks, the shared roll, five per-sample
+2x3 inverse maps); the device applies that plan with shape-static kernels (`apply_plan`: select-flip, warp,
+select-roll, four warps; samples a gate skipped get identity maps = exact copies).  Because the device side has no
+data-dependent control flow, a captured CUDA graph replays it with a fresh plan copied into the same buffer
+(`graph_capturable`, ModelWrapper.cuda_graphs).
 
 kornia 0.4.1 (the reference's warp implementation, requirements.txt:7) is neither vendored nor installed,
 so its matrix conventions are restated from its published source and are NOT pinned by any fixture
-("parity unpinned").  All random draws can be injected (`draws=`) so the oracle and the
-kernels consume identical parameters."""
+("parity unpinned"); tests compare this pipeline with an independent restatement built on
+F.affine_grid / F.grid_sample (oracle/ada.py).  All random draws can be injected (`draws=`)."""
 import math
 import random
 from typing import Dict, List, Optional, Tuple, Union
@@ -95,71 +102,174 @@ def affine_inverse_theta(batch: int, idx: List[int], angle_deg, scale_xy, center
         sx, sy = float(scale_xy[j][0]), float(scale_xy[j][1])
         cos, sin = math.cos(a), math.sin(a)
         m = np.array([[cos * sx, sin * sy, 0.0], [-sin * sx, cos * sy, 0.0], [0.0, 0.0, 1.0]])
-        m[0, 2] = cx - (m[0, 0] * cx + m[0, 1] * cy)
-        m[1, 2] = cy - (m[1, 0] * cx + m[1, 1] * cy)
+        # kornia 0.4.1 get_rotation_matrix2d: the translation column is built from the first row only
+        # (alpha = m00, beta = m01); identical to "keep the centre fixed" for isotropic scales
+        m[0, 2] = (1.0 - m[0, 0]) * cx - m[0, 1] * cy
+        m[1, 2] = m[0, 1] * cx + (1.0 - m[0, 0]) * cy
         theta[i] = torch.from_numpy(np.linalg.inv(m)[:2])
     return theta.float()
 
 
+def plan_size(batch: int) -> int:
+    return 32 * batch + 2
+
+
+def build_plan(d: Dict[str, object], batch: int, height: int, width: int) -> torch.Tensor:
+    """Pack one call's draws into a float32 host tensor: [flip mask B | roll mask B | roll shift (y, x) | 5 x B x 6 maps]
+    (maps: the shared 90-degree rotation, then iso-scale, rotation, aniso-scale, rotation; identity where not selected)."""
+    B, H, W = batch, height, width
+    plan = torch.zeros(plan_size(B), dtype=torch.float32)
+    plan[torch.as_tensor(d["flip"], dtype=torch.long)] = 1.0
+    plan[B + torch.as_tensor(d["roll"], dtype=torch.long)] = 1.0
+    if d["roll"]:
+        plan[2 * B] = float(int(H * d["roll_frac"][0]))
+        plan[2 * B + 1] = float(int(W * d["roll_frac"][1]))
+    n90 = len(d["rot90"])
+    ang = float(d["rot90_angle"])
+    # kaf.rotate(+angle) about the tensor centre == the affine map with angle -(-angle)
+    thetas = [affine_inverse_theta(B, list(d["rot90"]), [-ang] * n90, [(1., 1.)] * n90, ((W - 1) / 2, (H - 1) / 2))]
+    centre = (0.5 * H, 0.5 * W)
+    stages = [(d["iso"], np.zeros(len(d["iso"])), np.repeat(np.asarray(d["iso_scale"]).reshape(-1, 1), 2, axis=1)),
+              (d["rot_a"], d["rot_a_angle"], np.ones((len(d["rot_a"]), 2))),
+              (d["aniso"], np.zeros(len(d["aniso"])), np.asarray(d["aniso_scale"]).reshape(-1, 2)),
+              (d["rot_b"], d["rot_b_angle"], np.ones((len(d["rot_b"]), 2)))]
+    for idx, angles, scales in stages:
+        thetas.append(affine_inverse_theta(B, list(idx), angles, scales, centre))
+    plan[2 * B + 2:] = torch.stack(thetas).reshape(-1)
+    return plan
+
+
+def apply_plan(images: torch.Tensor, plan: torch.Tensor) -> torch.Tensor:
+    """The seven stages of the reference (:116-199) driven by a device-resident plan; no host decision, no sync."""
+    B, _, H, W = images.shape
+    dev = images.device
+    flip = plan[:B].view(B, 1, 1, 1) > 0.5
+    roll = plan[B:2 * B].view(B, 1, 1, 1) > 0.5
+    shift = plan[2 * B:2 * B + 2].round().to(torch.long)
+    theta = plan[2 * B + 2:].view(5, B, 2, 3)
+    x = torch.where(flip, images.flip(dims=(-1,)), images)
+    x = affine_warp(x, theta[0], mode=1)
+    iy = torch.remainder(torch.arange(H, device=dev) - shift[0], H)            # torch.roll(x, s)[i] = x[(i - s) mod n]
+    ix = torch.remainder(torch.arange(W, device=dev) - shift[1], W)
+    x = torch.where(roll, x.index_select(2, iy).index_select(3, ix), x)
+    for k in range(1, 5):
+        x = affine_warp(x, theta[k], mode=0)
+    return x
+
+
 class AugmentationPipeline(nn.Module):
-    def forward(self, images: torch.Tensor, p: float, draws: Optional[Dict[str, object]] = None) -> torch.Tensor:
-        """images [B, C, H, W]; mutated in place for the index-type stages like the reference (:118,:124,:129)."""
+    def forward(self, images: torch.Tensor, p: float, draws: Optional[Dict[str, object]] = None,
+                plan: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """images [B, C, H, W].  Returns the augmented batch and — like the reference, whose stages assign into a view
+        of the caller's tensor — also leaves it in `images` when that tensor does not take part in autograd."""
         B, _, H, W = images.shape
-        d = sample_draws(B, p) if draws is None else draws
-        if d["flip"]:
-            images[d["flip"]] = images[d["flip"]].flip(dims=(-1,))
-        if d["rot90"]:
-            ang = float(d["rot90_angle"])
-            th = affine_inverse_theta(len(d["rot90"]), list(range(len(d["rot90"]))), [-ang] * len(d["rot90"]),
-                                      [(1., 1.)] * len(d["rot90"]), ((W - 1) / 2, (H - 1) / 2))
-            images[d["rot90"]] = affine_warp(images[d["rot90"]], th.to(images.device), mode=1)
-        if d["roll"]:
-            shift = (int(H * d["roll_frac"][0]), int(W * d["roll_frac"][1]))
-            images[d["roll"]] = torch.roll(images[d["roll"]], shifts=shift, dims=(-2, -1))
-        centre = (0.5 * H, 0.5 * W)
-        stages = [(d["iso"], np.zeros(len(d["iso"])), np.repeat(np.asarray(d["iso_scale"]).reshape(-1, 1), 2, axis=1)),
-                  (d["rot_a"], d["rot_a_angle"], np.ones((len(d["rot_a"]), 2))),
-                  (d["aniso"], np.zeros(len(d["aniso"])), np.asarray(d["aniso_scale"]).reshape(-1, 2)),
-                  (d["rot_b"], d["rot_b_angle"], np.ones((len(d["rot_b"]), 2)))]
-        for idx, angles, scales in stages:
-            if idx:
-                theta = affine_inverse_theta(B, idx, angles, scales, centre).to(images.device)
-                images = affine_warp(images, theta, mode=0)
-        return images
+        if plan is None:
+            d = sample_draws(B, p) if draws is None else draws
+            plan = build_plan(d, B, H, W).to(images.device, non_blocking=True)
+        out = apply_plan(images, plan)
+        if not images.requires_grad and not torch.is_inference(images):
+            with torch.no_grad():
+                images.copy_(out)
+        return out
 
 
 class AdaptiveDiscriminatorAugmentation(nn.Module):
-    graph_capturable = False         # the pipeline draws its per-call decisions on the host (ModelWrapper.cuda_graphs)
+    """Wraps a discriminator (:11-96).  `p` moves by +-p_step whenever r_update fake batches have been seen, from the mean
+    of their overfitting heuristic r.  r is accumulated on the device and read back once per r_update calls (the
+    reference calls .item() every time); with several ranks the accumulated value is averaged over the ranks, which is
+    what the reference's DataParallel gather computes on the global batch.
+
+    CUDA graphs (ModelWrapper.cuda_graphs): while a capture is open every pipeline call allocates a plan slot — a static
+    device tensor the captured kernels read — and `refresh_plans` fills all slots of that capture with fresh draws before
+    each replay; `after_replay` does the host side of the p controller."""
+    graph_capturable = True
 
     def __init__(self, discriminator: nn.Module, r_target: float = 0.6, p_step: float = 5e-03, r_update: int = 8,
                  p_max: float = 0.8, process_group=None) -> None:
         super().__init__()
         self.discriminator = discriminator
         self.r_target, self.p_step, self.r_update, self.p_max = r_target, p_step, r_update, p_max
-        self.r: List[torch.Tensor] = []
         self.p = 0.05
         self.r_history: List[float] = []
         self.augmentation_pipeline = AugmentationPipeline()
         self.process_group = process_group
+        self._r_sum: Optional[torch.Tensor] = None      # device accumulator of r over the fake calls since the last update
+        self._r_count = 0
+        self._capture: Optional[dict] = None
+        self._plan_event = None
+
+    @property
+    def r(self) -> List[float]:
+        """Number-of-pending-values view kept for code that inspects `len(ada.r)` like the reference's list."""
+        return [float("nan")] * self._r_count
 
     @torch.no_grad()
     def _calc_r(self, prediction_scalar: torch.Tensor, prediction_pixel_wise: torch.Tensor) -> torch.Tensor:
-        """Overfitting heuristic (:51-52), kept on the device; all-reduced across ranks when sharded."""
-        r = 0.5 * torch.mean(torch.sign(prediction_scalar)) \
+        """Overfitting heuristic (:51-52), kept on the device."""
+        return 0.5 * torch.mean(torch.sign(prediction_scalar)) \
             + 0.5 * torch.mean(torch.sign(prediction_pixel_wise.mean(dim=(-1, -2))))
-        if self.process_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(r, group=self.process_group)
-            r = r / dist.get_world_size(self.process_group)
-        return r
+
+    @torch.no_grad()
+    def _record_r(self, prediction_scalar: torch.Tensor, prediction_pixel_wise: torch.Tensor) -> None:
+        r = self._calc_r(prediction_scalar.detach(), prediction_pixel_wise.detach()).reshape(1).float()
+        if self._r_sum is None or self._r_sum.device != r.device:
+            if self._capture is not None:
+                raise RuntimeError("ADA: the first fake batch must be seen eagerly before an iteration is captured")
+            self._r_sum = torch.zeros(1, dtype=torch.float32, device=r.device)
+        self._r_sum += r
+        if self._capture is not None:
+            self._capture["fake_calls"] += 1             # the host half happens in after_replay
+        else:
+            self._r_count += 1
 
     def _update_p(self) -> None:
-        if len(self.r) >= self.r_update:
-            r = float(torch.stack(self.r).mean().item())          # the only host sync: once per r_update calls
+        if self._r_count >= self.r_update and self._capture is None:
+            from . import dist as mdist
+            total = self._r_sum.clone()
+            if mdist.world_size(self.process_group) > 1:
+                mdist.all_reduce_mean_(total, self.process_group)
+            r = float(total.item()) / self._r_count           # the only host sync: once per r_update fake calls
             self.p = self.p + self.p_step if r > self.r_target else self.p - self.p_step
             self.p = min(max(self.p, 0.), self.p_max)
-            self.r = []
+            self._r_sum.zero_()
+            self._r_count = 0
             self.r_history.append(r)
+
+    # ---- CUDA-graph support ---------------------------------------------------------------------------
+    def begin_plan_capture(self) -> None:
+        self._capture = {"slots": [], "fake_calls": 0}
+
+    def end_plan_capture(self) -> dict:
+        cap, self._capture = self._capture, None
+        return cap
+
+    def refresh_plans(self, cap: dict) -> None:
+        """Fresh draws (reference order, current p) for every pipeline call of a captured iteration, copied into the
+        static plan tensors on the current stream; call right before replaying the graphs of `cap`."""
+        if not cap["slots"]:
+            return
+        if self._plan_event is not None:
+            self._plan_event.synchronize()       # the previous upload has left the pinned staging buffers
+        for slot in cap["slots"]:
+            B, H, W = slot["shape"]
+            slot["host"].copy_(build_plan(sample_draws(B, self.p), B, H, W))
+            slot["device"].copy_(slot["host"], non_blocking=True)
+        if self._plan_event is None:
+            self._plan_event = torch.cuda.Event()
+        self._plan_event.record()
+
+    def after_replay(self, cap: dict) -> None:
+        self._r_count += cap["fake_calls"]
+        self._update_p()
+
+    def _augment(self, flat: torch.Tensor, draws) -> torch.Tensor:
+        if self._capture is None:
+            return self.augmentation_pipeline(flat, self.p, draws)
+        B, _, H, W = flat.shape
+        slot = {"shape": (B, H, W), "device": torch.empty(plan_size(B), dtype=torch.float32, device=flat.device),
+                "host": torch.empty(plan_size(B), dtype=torch.float32).pin_memory()}
+        self._capture["slots"].append(slot)
+        return self.augmentation_pipeline(flat, self.p, plan=slot["device"])
 
     def forward_pair(self, real: torch.Tensor, fake: torch.Tensor, draws_real=None, draws_fake=None):
         """forward(real, is_real=True) and forward(fake, is_real=False) with one batched discriminator pass: both halves
@@ -169,10 +279,10 @@ class AdaptiveDiscriminatorAugmentation(nn.Module):
         if pair is None or real.shape != fake.shape:
             return self.forward(real, is_real=True, draws=draws_real), self.forward(fake, is_real=False, draws=draws_fake)
         shape = real.shape
-        a = self.augmentation_pipeline(real.flatten(start_dim=1, end_dim=2), self.p, draws_real).reshape(shape)
-        b = self.augmentation_pipeline(fake.flatten(start_dim=1, end_dim=2), self.p, draws_fake).reshape(shape)
+        a = self._augment(real.flatten(start_dim=1, end_dim=2), draws_real).reshape(shape)
+        b = self._augment(fake.flatten(start_dim=1, end_dim=2), draws_fake).reshape(shape)
         out_real, out_fake = pair(a, b)
-        self.r.append(self._calc_r(out_fake[0].detach(), out_fake[1].detach()))
+        self._record_r(out_fake[0], out_fake[1])
         self._update_p()
         return out_real, out_fake
 
@@ -181,10 +291,9 @@ class AdaptiveDiscriminatorAugmentation(nn.Module):
         if is_cut_mix:
             return self.discriminator(images)
         original_shape = images.shape
-        flat = images.flatten(start_dim=1, end_dim=2)
-        flat = self.augmentation_pipeline(flat, self.p, draws)
+        flat = self._augment(images.flatten(start_dim=1, end_dim=2), draws)
         prediction_scalar, prediction_pixel_wise = self.discriminator(flat.reshape(original_shape))
         if not is_real:
-            self.r.append(self._calc_r(prediction_scalar.detach(), prediction_pixel_wise.detach()))
+            self._record_r(prediction_scalar, prediction_pixel_wise)
         self._update_p()
         return prediction_scalar, prediction_pixel_wise

@@ -175,7 +175,10 @@ class ModelWrapper(object):
 
     def _train_step_graphed(self, real_images, lazy_r1, lazy_pl, wrong_order) -> Dict[str, torch.Tensor]:
         from . import _C
-        key = (tuple(real_images.shape), real_images.dtype, lazy_r1, lazy_pl, wrong_order)
+        # every host decision the captured program bakes in is part of the key (the trap weighting switches on at
+        # trap_weight * epochs, :262-263 via _trap())
+        use_trap = self._trap() is not None
+        key = (tuple(real_images.shape), real_images.dtype, lazy_r1, lazy_pl, wrong_order, use_trap)
         if key not in self._graphs:
             # first occurrence: eager, which also creates optimiser state, running means and kernel attributes
             self._graphs[key] = None
@@ -189,6 +192,8 @@ class ModelWrapper(object):
                 if not all(g.get("capturable", False) for g in opt.param_groups):
                     raise RuntimeError("cuda_graphs=True needs optimisers constructed with capturable=True")
             st = SimpleNamespace()
+            if use_trap and self.trap_weights_map.device != real_images.device:
+                self.trap_weights_map = self.trap_weights_map.to(real_images.device)     # no H2D copy inside the capture
             st.real = real_images.detach().clone()
             st.inject = torch.zeros(3, dtype=torch.int64, device=real_images.device)
             st.perm = torch.arange(real_images.shape[2], dtype=torch.int64, device=real_images.device)
@@ -198,6 +203,9 @@ class ModelWrapper(object):
             launches0 = _C.launch_count()
             prog = SimpleNamespace(items=[], pool=torch.cuda.graph_pool_handle(), stream=torch.cuda.Stream(), open=None)
             self._capture = prog
+            ada_begin = getattr(self.discriminator, "begin_plan_capture", None)
+            if ada_begin is not None:
+                ada_begin()
             self._segment_begin(prog)
             try:
                 plr.mean_path_length = st.mean_path_length
@@ -209,6 +217,7 @@ class ModelWrapper(object):
                 self._capture = None
                 if prog.open is not None:
                     self._segment_end(prog)
+                st.ada = self.discriminator.end_plan_capture() if ada_begin is not None else None
             st.program = prog.items      # CUDA graphs in capture order (one shared pool), eager collectives in between
             st.launches = _C.launch_count() - launches0
             self._graphs[key] = st
@@ -220,12 +229,22 @@ class ModelWrapper(object):
             for i, v in enumerate(_misc.random_permutation(real_images.shape[2]).tolist()):
                 st.perm[i].fill_(int(v))
         st.real.copy_(real_images, non_blocking=True)
+        plr = self.path_length_regularization
+        if lazy_pl and plr.mean_path_length is not st.mean_path_length:
+            # an eager lazy iteration (CutMix draw, top-k, another graph variant) moved the running mean since this
+            # variant last ran: its static slot must start from the current value
+            st.mean_path_length.copy_(plr.mean_path_length.detach().to(st.mean_path_length.device), non_blocking=True)
+        if st.ada is not None:
+            self.discriminator.refresh_plans(st.ada)     # fresh augmentation draws for every ADA call of the iteration
         for item in st.program:
             if isinstance(item, torch.cuda.CUDAGraph):
                 item.replay()
             else:
                 item()
-        self.path_length_regularization.mean_path_length = st.mean_path_length
+        if st.ada is not None:
+            self.discriminator.after_replay(st.ada)
+        if lazy_pl:
+            plr.mean_path_length = st.mean_path_length
         self.graph_replays += 1
         self.graph_launches += st.launches
         return dict(st.out)
@@ -340,7 +359,9 @@ class ModelWrapper(object):
         self.resume_training, self.top_k = resume_training, top_k
         history = []
         for real_images in self.training_dataset:
-            history.append(self.train_step(real_images.to(self.device, non_blocking=True)))
+            out = self.train_step(real_images.to(self.device, non_blocking=True))
+            # with cuda_graphs the scalars alias the graph's static memory: keep values, not views of the next replay
+            history.append({k: v.detach().clone() for k, v in out.items()})
         return history
 
     def train(self, epochs: int = 20, resume_training: bool = False, top_k: bool = False):

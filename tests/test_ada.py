@@ -41,6 +41,10 @@ def run_pipeline(dev):
     want = x.clone()
     want[[0]] = torch.roll(want[[0]], shifts=(4, -4), dims=(-2, -1))
     assert torch.equal(ro.cpu(), want)
+    # the reference assigns into a view of its input (:118-187): the caller's tensor holds the augmented batch afterwards
+    xin = x.clone().to(dev)
+    res = pipe(xin, 0.5, _full_draws())
+    assert torch.equal(xin, res)
     # everything at once, differentiable w.r.t. the images
     xi = x.clone().to(dev).requires_grad_(True)
     out = pipe(xi * 1.0, 0.5, _full_draws())
@@ -48,23 +52,55 @@ def run_pipeline(dev):
     w = torch.rand(out.shape, generator=g).to(dev)
     gx, = torch.autograd.grad((out * w).sum(), xi)
     assert gx.shape == x.shape and gx.abs().sum() > 0
-    return out.detach().cpu(), gx.cpu()
+    return out.detach().cpu(), gx.cpu(), x, w.cpu()
+
+
+def _stage_draws():
+    """One dictionary per stage (each alone), then all stages together."""
+    import numpy as np
+    yield "rot90_+90", _draws(4, rot90=[0, 2], rot90_angle=90.)
+    yield "rot90_-90", _draws(4, rot90=[1], rot90_angle=-90.)
+    yield "rot90_180", _draws(4, rot90=[3], rot90_angle=180.)
+    yield "iso", _draws(4, iso=[0, 3], iso_scale=np.array([[1.05], [0.93]]))
+    yield "rot_a", _draws(4, rot_a=[1, 2], rot_a_angle=np.array([17.0, -143.0]))
+    yield "aniso", _draws(4, aniso=[0, 1], aniso_scale=np.array([[1.04, 0.95], [0.97, 1.02]]))
+    yield "rot_b", _draws(4, rot_b=[2], rot_b_angle=np.array([71.0]))
+    yield "all", _full_draws()
+
+
+def check_against_independent_oracle(dev, tol=1e-4):
+    """The product pipeline (own inverse pixel maps + own warp kernel) against oracle/ada.py (kornia's route restated
+    with F.affine_grid / F.grid_sample): outputs and the gradient w.r.t. the input images, stage by stage."""
+    from multi_stylegan_b200.adaptive_discriminator_augmentation import AugmentationPipeline
+    from oracle import ada as oada
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(4, 6, 32, 32, generator=g)
+    w = torch.rand(4, 6, 32, 32, generator=g)
+    pipe = AugmentationPipeline()
+    for name, d in _stage_draws():
+        xo = x.clone().requires_grad_(True)
+        want = oada.augmentation_pipeline(xo, d)
+        gwant, = torch.autograd.grad((want * w).sum(), xo)
+        xi = x.clone().to(dev).requires_grad_(True)
+        got = pipe(xi * 1.0, 0.5, d)
+        ggot, = torch.autograd.grad((got * w.to(dev)).sum(), xi)
+        assert rel_err(got, want) < tol, (name, rel_err(got, want))
+        assert rel_err(ggot, gwant) < tol, (name, rel_err(ggot, gwant))
 
 
 def test_pipeline_host_logic(oracle_backend):
     run_pipeline("cpu")
 
 
+def test_pipeline_matches_independent_oracle_host_logic(oracle_backend):
+    check_against_independent_oracle("cpu")
+
+
 @pytest.mark.gpu
-def test_pipeline_kernels_match_cpu_oracle(built_library):
-    """Same draws through the CUDA kernels (forward warp and its adjoint) and through the CPU oracle backend."""
-    got_out, got_gx = run_pipeline("cuda:0")
-    import unittest.mock as um
-    from tests import backend_oracle
-    from multi_stylegan_b200 import _C
-    with um.patch.multiple(_C, **{n: getattr(backend_oracle, n) for n in backend_oracle.__all__}):
-        want_out, want_gx = run_pipeline("cpu")
-    assert rel_err(got_out, want_out) < 1e-4 and rel_err(got_gx, want_gx) < 1e-4
+def test_pipeline_kernels_match_independent_oracle(built_library):
+    """CUDA warp + adjoint kernels, all seven stages with injected draws, against oracle/ada.py."""
+    run_pipeline("cuda:0")
+    check_against_independent_oracle("cuda:0")
 
 
 @pytest.mark.gpu

@@ -297,3 +297,96 @@ def test_cuda_graph_replay_matches_eager(built_library, segmented):
     assert torch.allclose(m0, m1, rtol=2e-3)
     for a, b in zip(p0, p1):
         assert rel_err(b, a) < 2e-3
+
+
+def _graph_vs_eager(make_wrapper, schedule, n_iter=6):
+    """Run the same iterations eagerly and with CUDA-graph replay (same host / device random streams) and return both
+    histories.  `schedule(mw, it)` may change wrapper state before iteration `it` and returns extra train_step kwargs."""
+    import random
+    import numpy as np
+    dev = torch.device("cuda:0")
+    runs = []
+    for graphed in (False, True):
+        mw, nets = make_wrapper(dev)
+        random.seed(7), np.random.seed(7), torch.manual_seed(7)
+        gen = torch.Generator().manual_seed(11)
+        hist = []
+        for it in range(n_iter):
+            kw = schedule(mw, it, gen)
+            if not graphed:
+                mw._graphs.clear()              # every iteration is a "first occurrence": eager execution
+            real = torch.rand(4, 2, 3, 32, 32, generator=gen).to(dev)
+            hist.append({k: v.detach().clone() for k, v in mw.train_step(real, **kw).items()})
+        torch.cuda.synchronize()
+        runs.append((mw, hist, [p.detach().clone() for net in nets for p in net.parameters()],
+                     mw.path_length_regularization.mean_path_length.clone()))
+    return runs
+
+
+def _assert_same_runs(runs, rtol=2e-3):
+    (_, h0, p0, m0), (_, h1, p1, m1) = runs
+    for i, (a, b) in enumerate(zip(h0, h1)):
+        assert set(a) == set(b), (i, sorted(a), sorted(b))
+        for k in a:
+            assert torch.allclose(a[k], b[k], rtol=rtol, atol=1e-5), (i, k, a[k], b[k])
+    assert torch.allclose(m0, m1, rtol=rtol)
+    for a, b in zip(p0, p1):
+        assert rel_err(b, a) < rtol
+
+
+@pytest.mark.gpu
+def test_cuda_graph_keys_cover_trap_weights_and_running_mean_survives_eager_iterations(built_library):
+    """(1) The trap weighting of the pixel-wise losses switches on at trap_weight * epochs (model_wrapper.py:262-263):
+    a graph captured before the switch must not be replayed after it.  (2) An eager lazy iteration (here: fixed
+    latents) between graphed ones moves the path-length running mean; the next replay must start from it."""
+    from multi_stylegan_b200.model_wrapper import ModelWrapper
+    hp = _hp()
+    hp["p_mixed_noise"] = 0.0
+    trap = torch.rand(32, 32) + 0.5
+
+    def make(dev):
+        G, D = build(dev)
+        opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"], fused=True, capturable=True)
+        opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"], fused=True, capturable=True)
+        mw = ModelWrapper(G, D, opt_g, opt_d, hyperparameters=hp, device=dev, cuda_graphs=True,
+                          trap_weights_map=trap.clone())            # a CPU map: moved to the device before capture
+        mw.epochs, mw.epoch = 4, 0
+        return mw, (G, D)
+
+    def schedule(mw, it, gen):
+        if it == 10:
+            mw.epoch = 1                       # trap_weight (0.25) * epochs (4) <= epoch: weighting on from here
+        if it == 7:                            # a lazy iteration (every 2nd) forced to run eagerly in both runs, after
+            return dict(z_pl=torch.randn(2, 16, generator=gen).to("cuda:0"))   # its variant was captured (it = 3)
+        return {}
+    runs = _graph_vs_eager(make, schedule, n_iter=14)
+    _assert_same_runs(runs)
+    mw = runs[1][0]
+    assert mw.graph_replays >= 4
+    assert {k[5] for k in mw._graphs} == {False, True}          # separate programs before / after the switch
+
+
+@pytest.mark.gpu
+def test_cuda_graph_replay_with_ada_matches_eager(built_library):
+    """The ADA wrapper is graph-capturable: its per-call draws stay on the host (reference order) and reach the captured
+    kernels through plan tensors refreshed before every replay; p moves at the same iterations as in eager execution."""
+    from multi_stylegan_b200.adaptive_discriminator_augmentation import AdaptiveDiscriminatorAugmentation
+    from multi_stylegan_b200.model_wrapper import ModelWrapper
+    hp = _hp()
+    hp["p_mixed_noise"] = 0.5
+
+    def make(dev):
+        G, D = build(dev)
+        opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"], fused=True, capturable=True)
+        opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"], fused=True, capturable=True)
+        ada = AdaptiveDiscriminatorAugmentation(D, r_update=2, p_step=0.1)
+        ada.p = 0.5
+        mw = ModelWrapper(G, ada, opt_g, opt_d, hyperparameters=hp, device=dev, cuda_graphs=True)
+        mw._d_params = lambda: list(D.parameters())
+        return mw, (G, D)
+    runs = _graph_vs_eager(make, lambda mw, it, gen: {}, n_iter=8)
+    _assert_same_runs(runs)
+    eager, graphed = runs[0][0], runs[1][0]
+    assert graphed.graph_replays >= 4
+    assert eager.discriminator.r_history == pytest.approx(graphed.discriminator.r_history)
+    assert eager.discriminator.p == pytest.approx(graphed.discriminator.p) and len(graphed.discriminator.r_history) >= 6
