@@ -28,13 +28,55 @@ UNIT = "sequences/s"
 VERBOSE = bool(os.environ.get("MSG_BENCH_VERBOSE"))
 
 
-def workload_config(args, world):
-    return {"workload": "full G+D train step (BASELINE config 3): default 512ch/256x256 Multi-StyleGAN generator + "
-                        "U-Net discriminator, NS-logistic loss, lazy R1 + path length every 16th iteration, EMA",
-            "per_gpu_batch": args.batch, "global_batch": args.batch * world, "resolution": 256,
-            "parallelism": "dp%d" % world, "ada": bool(args.ada),
-            "cuda_graphs": bool(not args.no_graphs and not args.ada),
-            "l2_policy": "working set per step (>= 10 GiB of activations) >> 126 MB L2; inputs rotate over a pool"}
+def workload_config(args, world, reference=False):
+    cfg = {"workload": "full G+D train step (BASELINE config 3): default 512ch/256x256 Multi-StyleGAN generator + "
+                       "U-Net discriminator, NS-logistic loss, lazy R1 + path length every 16th iteration, EMA",
+           "per_gpu_batch": args.batch, "global_batch": args.batch * world, "resolution": 256,
+           "parallelism": "dp%d" % world, "ada": bool(args.ada),
+           "cuda_graphs": bool(not args.no_graphs),
+           "l2_policy": "working set per step (>= 10 GiB of activations) >> 126 MB L2; inputs rotate over a pool"}
+    if reference:
+        # the CPU arm runs a bounded sample of the same workload: one plain iteration at batch 1, scaled per sequence
+        cfg.update(per_gpu_batch=1, global_batch=1, parallelism="cpu", cuda_graphs=False, ada=False, lazy=False,
+                   l2_policy="n/a (host cores)")
+    return cfg
+
+
+def measure_tf32_peak(dev, sustained_s=2.0):
+    """Dense TF32 tensor-core peak measured the way MEASURED_PEAKS.json measures bf16: torch.matmul (cuBLAS, fp32 operands
+    with TF32 allowed) on 8192^3, best of 10 (burst) and back to back for `sustained_s` seconds (sustained)."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        flops = 2.0 * n ** 3
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize(dev)
+        best = 1e30
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(sustained_s * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sust = e0.elapsed_time(e1) / reps
+        del a, b, c
+        return flops / (best * 1e-3) / 1e12, flops / (sust * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def peaks():
@@ -132,10 +174,11 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     sample = "oracle port of the reference trainer (oracle/train_step.py over oracle/model.py; the reference's own " \
              "modules are not available on this box), one plain iteration (D step + G step, dead second branch " \
-             "evaluated as the reference does, no lazy regularisers) at batch 1, best of %d, torch %s CPU" % (n, torch.__version__)
+             "evaluated as the reference does, no lazy regularisers) at batch 1, value = best of %d timed iteration(s) " \
+             "(fastest, i.e. favourable to the CPU arm), torch %s CPU, %d threads" % (n, torch.__version__, cores)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
             "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1), "impl": "reference",
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, 1, reference=True), "impl": "reference",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -168,114 +211,203 @@ def run_ours(args):
     D = D_mod.Discriminator(config.u_net_2d_discriminator_config, no_rfp=True).to(dev)
     mdist.broadcast_parameters([G, D])
     hp = dict(config.generation_hyperparameters)
+    lazy_every = hp["lazy_generator_regularization"]
+    graphs = not args.no_graphs
     # same Adam as train_multi_stylegan.py:53-57; fused=True only selects PyTorch's single-kernel implementation
     # (capturable=True keeps Adam's step counters on the device so that an iteration can be replayed as a CUDA graph)
-    graphs = not args.no_graphs and not args.ada          # ADA draws its augmentations on the host every call
-    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-4, lr_style=2e-6), betas=hp["betas"], fused=True, capturable=graphs)
-    opt_d = torch.optim.Adam(D.parameters(), lr=6e-4, betas=hp["betas"], fused=True, capturable=graphs)
-    Dw = AdaptiveDiscriminatorAugmentation(D) if args.ada else D
-    if args.ada:
-        Dw.p = 0.5
-    mw = ModelWrapper(G, Dw, opt_g, opt_d, hyperparameters=hp, device=dev, cuda_graphs=graphs)
-    mw._d_params = lambda: list(D.parameters())
+    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-4, lr_style=2e-6), betas=hp["betas"], fused=True, capturable=True)
+    opt_d = torch.optim.Adam(D.parameters(), lr=6e-4, betas=hp["betas"], fused=True, capturable=True)
+
+    def make_wrapper(ada: bool):
+        Dw = AdaptiveDiscriminatorAugmentation(D) if ada else D
+        if ada:
+            Dw.p = 0.5                          # config 4: fixed p for timing (the controller is exercised by the tests)
+            Dw.p_step = 0.0
+        w = ModelWrapper(G, Dw, opt_g, opt_d, hyperparameters=hp, device=dev, cuda_graphs=graphs)
+        w._d_params = lambda: list(D.parameters())
+        return w
+    mw = make_wrapper(bool(args.ada))
     torch.manual_seed(1234 + rank)
     pool = [torch.rand(B, 2, 3, 256, 256, device=dev) for _ in range(4)]
     host_pool = [p.cpu().pin_memory() for p in pool]
+    state = {"graphs": graphs}
 
     def barrier():
         if world > 1:
             tdist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up: W plain iterations + one iteration with both lazy regularisers (their kernels and shapes)
-    # (with CUDA graphs: the first lazy / plain iteration runs eagerly, the second one of each kind is captured)
-    lazy_every = hp["lazy_generator_regularization"]
+    def agree(flag: bool) -> bool:
+        """True on every rank iff `flag` is true on every rank (a fallback decision must not desynchronise collectives)."""
+        if world == 1:
+            return flag
+        t = torch.tensor([1 if flag else 0], device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MIN)
+        return bool(t.item())
 
-    def warm_up(setup):
-        for i in range(setup + max(args.warmup, 3)):
+    # warm-up: W plain iterations + iterations with both lazy regularisers (their kernels and shapes)
+    # (with CUDA graphs: the first lazy / plain iteration runs eagerly, the second one of each kind is captured)
+    def warm_up(w, setup, plain):
+        for i in range(setup + plain):
             is_lazy = i < setup and i % 2 == 0
-            mw.iteration = lazy_every - 1 if is_lazy else 0  # train_step increments first: iteration 16 runs R1 + PL
-            out = mw.train_step(pool[i % len(pool)])
+            w.iteration = lazy_every - 1 if is_lazy else 0  # train_step increments first: iteration 16 runs R1 + PL
+            out = w.train_step(pool[i % len(pool)])
             if VERBOSE:
                 torch.cuda.synchronize()
-                print("[bench rank %d] warm-up iteration %d done (replays so far: %d)" % (rank, i, mw.graph_replays),
+                print("[bench rank %d] warm-up iteration %d done (replays so far: %d)" % (rank, i, w.graph_replays),
                       file=sys.stderr, flush=True)
             if is_lazy:
                 assert "loss_path_length_regularization" in out and "loss_discriminator_regularization" in out, \
                     "warm-up did not exercise the lazy regularisers"
 
-    try:
-        warm_up(4 if graphs else 1)
-    except Exception as exc:                     # a capture that fails on this box must not cost the measurement
-        if not graphs:
-            raise
-        print("[bench rank %d] CUDA-graph capture failed (%s: %s); continuing with eager issue" %
-              (rank, type(exc).__name__, str(exc)[:300]), file=sys.stderr, flush=True)
-        graphs = False
-        args.no_graphs = True
-        mw.cuda_graphs = False
-        mw._graphs.clear()
-        torch.cuda.synchronize()
-        warm_up(1)
+    def warm_up_checked(w, plain):
+        ok = True
+        try:
+            warm_up(w, 4 if state["graphs"] else 1, plain)
+        except Exception as exc:                     # a capture that fails on this box must not cost the measurement
+            if not state["graphs"]:
+                raise
+            print("[bench rank %d] CUDA-graph capture failed (%s: %s)" % (rank, type(exc).__name__, str(exc)[:300]),
+                  file=sys.stderr, flush=True)
+            ok = False
+        if state["graphs"] and not agree(ok):
+            # every rank leaves graph mode together and repeats the warm-up eagerly
+            print("[bench rank %d] continuing with eager issue on all ranks" % rank, file=sys.stderr, flush=True)
+            state["graphs"] = False
+            args.no_graphs = True
+            w.cuda_graphs = False
+            w._graphs.clear()
+            torch.cuda.synchronize()
+            warm_up(w, 1, plain)
+    warm_up_checked(mw, max(args.warmup, 3))
+    graphs = state["graphs"]
     barrier()
     if graphs:
         assert mw.graph_replays >= 2 + max(args.warmup, 3), "CUDA graphs requested but the iterations ran eagerly"
 
-    def timed(e2e: bool, profile: bool = False):
+    def timed(w, steps, e2e: bool, profile: bool = False, sample_clocks: bool = False):
         # profile=True: the same K iterations issued eagerly with a CUDA-event pair around every conv launch (roofline)
-        mw.cuda_graphs = graphs and not profile
+        w.cuda_graphs = graphs and not profile
         if graphs and profile:
             # graph capture emptied the caching allocator: refill the eager pool (one lazy + one plain iteration) untimed
             for it0 in (lazy_every - 1, 0):
-                mw.iteration = it0
-                mw.train_step(pool[0])
-        mw.iteration = 0
-        launches0 = _C.launch_count() + mw.graph_launches
+                w.iteration = it0
+                w.train_step(pool[0])
+        w.iteration = 0
+        launches0 = _C.launch_count() + w.graph_launches
         _C.profile_enable(profile)
         sampler = ClockSampler(local_rank)
-        if not e2e and not profile and rank == 0:
+        if sample_clocks and rank == 0:
             sampler.start()
         barrier()
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
         t0 = time.time()
-        start.record()
+        marks[0].record()
         last = None
         torch.cuda.nvtx.range_push("timed_e2e" if e2e else "timed")            # main-thread kernels (forward passes)
         nvtx_id = torch.cuda.nvtx.range_start("step_e2e" if e2e else "step")    # process-wide: autograd thread too
-        for i in range(args.steps):
+        for i in range(steps):
             if e2e:
                 real = host_pool[i % len(host_pool)].to(dev, non_blocking=True)
-                out = mw.train_step(real)
+                out = w.train_step(real)
                 last = {k: float(v) for k, v in out.items()}           # device -> host read of the step's losses
             else:
-                mw.train_step(pool[i % len(pool)])
+                w.train_step(pool[i % len(pool)])
+            marks[i + 1].record()
         torch.cuda.synchronize()
         torch.cuda.nvtx.range_end(nvtx_id)
         torch.cuda.nvtx.range_pop()
-        end.record()
         barrier()
         wall = time.time() - t0
-        ms = start.elapsed_time(end)
-        clocks = sampler.stop() if (not e2e and not profile and rank == 0) else None
+        ms = marks[0].elapsed_time(marks[-1])
+        per_step = [marks[i].elapsed_time(marks[i + 1]) for i in range(steps)]
+        clocks = sampler.stop() if (sample_clocks and rank == 0) else None
         t = torch.tensor([ms], device=dev)
         if world > 1:
             tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
         if VERBOSE:
-            print("[bench rank %d] pass e2e=%s profile=%s: %.1f ms/step" % (rank, e2e, profile, ms / args.steps),
+            print("[bench rank %d] pass e2e=%s profile=%s: %.1f ms/step" % (rank, e2e, profile, ms / steps),
                   file=sys.stderr, flush=True)
         prof = _C.profile_summary() if profile else None
         _C.profile_enable(False)
-        mw.cuda_graphs = graphs
-        return float(t.item()), _C.launch_count() + mw.graph_launches - launches0, clocks, prof, last, wall
+        w.cuda_graphs = graphs
+        return {"ms": float(t.item()), "launches": _C.launch_count() + w.graph_launches - launches0, "clocks": clocks,
+                "prof": prof, "last": last, "wall": wall, "per_step": per_step}
 
-    if graphs:
-        ms, launches, clocks, _, _, wall = timed(False)
-        ms_e2e, _, _, _, last_losses, _ = timed(True)
-        ms_prof, _, _, prof, _, _ = timed(False, profile=True)
-    else:
-        ms, launches, clocks, prof, _, wall = timed(False, profile=True)
-        ms_e2e, _, _, _, last_losses, _ = timed(True)
-        ms_prof = ms
+    main = timed(mw, args.steps, False, profile=not graphs, sample_clocks=True)
+    e2e = timed(mw, args.steps, True)
+    pr = timed(mw, args.steps, False, profile=True) if graphs else main
+    ms, launches, clocks, prof, ms_prof = main["ms"], main["launches"], main["clocks"], pr["prof"], pr["ms"]
+    ms_e2e, last_losses = e2e["ms"], e2e["last"]
+
+    # ---- config 5: EMA-generator sampling throughput (no_grad, single-style z, fresh noise; get_gan_samples.py:40-42) ----
+    ema_line = None
+    if not args.no_extras:
+        try:
+            ema_line = {"unit": UNIT, "points": []}
+            g_ema = mw.generator_ema
+            with torch.no_grad():
+                for sb in (8, 16, 32):
+                    z = torch.randn(sb, 512, device=dev)
+                    for _ in range(3):
+                        g_ema(z)
+                    barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    reps = 8
+                    e0.record()
+                    for _ in range(reps):
+                        g_ema(torch.randn(sb, 512, device=dev))
+                    e1.record()
+                    torch.cuda.synchronize()
+                    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+                    if world > 1:
+                        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+                    ema_line["points"].append({"per_gpu_batch": sb, "global_batch": sb * world,
+                                               "value": world * sb * reps / (float(t.item()) / 1e3)})
+            ema_line["note"] = "EMA generator forward under no_grad (eager issue), sequences/s over all ranks"
+        except Exception as exc:
+            ema_line = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+            if world > 1:
+                raise
+
+    tf32_burst = tf32_sust = None
+    if not args.no_extras:
+        try:
+            tf32_burst, tf32_sust = measure_tf32_peak(dev)
+        except Exception as exc:
+            print("[bench rank %d] TF32 peak measurement failed: %s" % (rank, str(exc)[:200]), file=sys.stderr, flush=True)
+    # ---- config 4: the same step with ADA (p = 0.5) wrapped around the discriminator ------------------------------------
+    ada_line = None
+    if not args.ada and not args.no_extras:
+        try:
+            # the captured iterations of the plain wrapper own large private memory pools: release them first (an
+            # allocation that has to free cached blocks while a capture is open invalidates the capture)
+            import gc
+            g_ema = None
+            mw.reset_cuda_graphs()
+            gc.collect()
+            torch.cuda.empty_cache()
+            if VERBOSE:
+                print("[bench rank %d] memory before the ADA variant: %.1f GiB allocated, %.1f GiB reserved" %
+                      (rank, torch.cuda.memory_allocated() / 2 ** 30, torch.cuda.memory_reserved() / 2 ** 30),
+                      file=sys.stderr, flush=True)
+            mwa = make_wrapper(True)
+            state["graphs"] = graphs
+            warm_up_checked(mwa, 3)
+            if state["graphs"] == graphs:
+                ra = timed(mwa, args.steps, False)
+                ada_line = {"p": 0.5, "ms_per_step": ra["ms"] / args.steps, "value": world * B * args.steps / (ra["ms"] / 1e3),
+                            "unit": UNIT, "cuda_graphs": bool(graphs), "steps": args.steps,
+                            "relative_to_plain": (ra["ms"] / args.steps) / (ms / args.steps),
+                            "note": "BASELINE config 4: same train step, D wrapped in AdaptiveDiscriminatorAugmentation, "
+                                    "fixed p = 0.5, 3 augmentation pipelines per iteration (real, fake, fake)"}
+            else:
+                ada_line = {"error": "graph capture failed for the ADA variant"}
+            del mwa
+        except Exception as exc:
+            ada_line = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+            if world > 1:
+                raise
 
     if world > 1:
         tdist.barrier()
@@ -290,11 +422,19 @@ def run_ours(args):
                 f.write(json.dumps(e) + "\n")
     seqs = world * B * args.steps
     value = seqs / (ms / 1e3)
-    lazy = args.steps // hp["lazy_generator_regularization"]
+    lazy_idx = [i for i in range(args.steps) if (i + 1) % lazy_every == 0]
+    plain_ms = [t for i, t in enumerate(main["per_step"]) if i not in lazy_idx]
+    lazy_ms = [main["per_step"][i] for i in lazy_idx]
     cfg = workload_config(args, world)
-    cfg["lazy_r1_and_pl_steps_in_timed_region"] = lazy
+    cfg["cuda_graphs"] = bool(graphs)
+    cfg["lazy_r1_and_pl_steps_in_timed_region"] = len(lazy_idx)
     hbm, bf16_burst, bf16_sust, src = peaks()
-    tf32_peak = bf16_sust / 2.0
+    if tf32_sust is not None:
+        tf32_peak, peak_source = tf32_sust, "measured in this run: torch.matmul fp32 operands with TF32 allowed, 8192^3, " \
+            "back to back for 2 s (sustained %.0f TFLOP/s; best of 10 burst %.0f TFLOP/s) — the method of " \
+            "MEASURED_PEAKS.json applied to TF32" % (tf32_sust, tf32_burst)
+    else:
+        tf32_peak, peak_source = bf16_sust / 2.0, "1/2 of the %s bf16 sustained rate in MEASURED_PEAKS.json (TF32 not measured: --no-extras)" % src
     roof = None
     traffic_table = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")      # dram bytes per launch from the committed ncu captures
@@ -310,21 +450,22 @@ def run_ours(args):
             top["kind"], top["taps"], top["k_channels"], top["n_channels"], top["pixels"])
         roof = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
                 "frac": achieved / tf32_peak, "traffic": traffic_table.get(kname),
-                "kernel": kname,
+                "traffic_source": "profiles/traffic.json (dram bytes per launch from the committed ncu --set full capture of this launch)",
+                "kernel": kname, "peak_source": peak_source,
                 "algorithmic_flops_per_launch": top["flops_per_launch"],
-                "frac_of_burst_peak": achieved / (bf16_burst / 2.0),
+                "frac_of_burst_peak": achieved / tf32_burst if tf32_burst else None,
+                "peak_half_bf16_sustained": bf16_sust / 2.0,
                 "launches": top["launches"], "avg_ms": top["ms_total"] / top["launches"],
                 "share_of_step": top["ms_total"] / ms_prof,
                 "measured_in": ("an eager pass of the same %d iterations (%.1f ms/step) with a CUDA-event pair around each conv "
                                 "launch; the timed region itself replays CUDA graphs" % (args.steps, ms_prof / args.steps))
                 if graphs else "the timed region",
-                "peak_note": "TF32 dense = 1/2 of the %s bf16 sustained rate (%.0f TFLOP/s) in MEASURED_PEAKS.json" % (src, bf16_sust),
                 "all_tcgen05_conv_kernels": {"ms": conv_ms, "share_of_step": conv_ms / ms_prof,
                                              "tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None}}
     # secondary roofline (north star: upfirdn2d against HBM): the generator's 256^2 blur, CUDA events, inputs rotate over
     # 3 x 1 GiB (> L2); algorithmic bytes = 4 * (N_in + N_out)
     roof_hbm = None
-    if world == 1:
+    if world == 1 and not args.no_extras:
         try:
             k4 = torch.tensor([1., 3., 3., 1.], device=dev)
             k2d = (k4[None] * k4[:, None]) / 16
@@ -357,9 +498,22 @@ def run_ours(args):
                     "h2d_bytes_per_step": B * 2 * 3 * 256 * 256 * 4, "d2h_bytes_per_step": 4 * len(last_losses or {})},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "roofline_hbm": roof_hbm,
             "conv_engine": _C.conv2d_last_engine()}
+    if plain_ms:
+        t_plain = sum(plain_ms) / len(plain_ms)
+        line["plain_iteration_ms"] = t_plain
+        if lazy_ms:
+            t_lazy = sum(lazy_ms) / len(lazy_ms)
+            line["lazy_iteration_ms"] = t_lazy
+            am = ((lazy_every - 1) * t_plain + t_lazy) / lazy_every
+            line["amortised_16"] = {"ms_per_step": am, "value": world * B / (am / 1e3), "unit": UNIT,
+                                    "note": "15 plain + 1 lazy (R1 + path length) iteration, from this rank's per-step CUDA events; "
+                                            "equals `value` when --steps is a multiple of 16"}
+    if ada_line is not None:
+        line["ada"] = ada_line
+    if ema_line is not None:
+        line["ema_sampling"] = ema_line
     if world == 1 and not args.no_cpu_baseline:
         sec, n = cpu_reference_step_time(1, 0, args.cpu_budget)
-        import torch as _t
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "oracle port, one plain iteration (D step + G step, no lazy regularisers, dead "
                                           "branch evaluated like the reference) at batch 1, %d run(s)" % n}
@@ -398,6 +552,7 @@ def main():
     ap.add_argument("--ada", action="store_true", help="wrap D in adaptive discriminator augmentation (config 4)")
     ap.add_argument("--no-graphs", action="store_true", help="issue every iteration eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the ADA / EMA-sampling / TF32-peak / blur sub-measurements")
     ap.add_argument("--profile-out", default=None, help="write the per-shape tcgen05 conv kernel timings (JSON lines)")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds of CPU work allowed for the reference arm")
     args = ap.parse_args()

@@ -210,6 +210,12 @@ int msg_conv2d_forward(float* y, const float* x, const float* w, const msg_conv_
 int msg_conv2d_dgrad(float* dx, const float* dy, const float* w, const msg_conv_desc* d,
                      float alpha, void* workspace, size_t workspace_bytes, int flags,
                      msg_stream_t stream);
+/* dx = alpha * conv^T(dy, w) + add: the sum of two input gradients (a block input that feeds the main path and the
+ * residual path, u_net_2d_discriminator.py:174-186) formed in the dgrad epilogue instead of a separate pass.
+ * `add` has the layout of dx and must not alias it; NULL = msg_conv2d_dgrad. */
+int msg_conv2d_dgrad_acc(float* dx, const float* dy, const float* w, const msg_conv_desc* d,
+                         float alpha, const float* add, void* workspace, size_t workspace_bytes, int flags,
+                         msg_stream_t stream);
 int msg_conv2d_wgrad(float* dw, const float* dy, const float* x, const msg_conv_desc* d,
                      float alpha, void* workspace, size_t workspace_bytes, int flags,
                      msg_stream_t stream);

@@ -405,8 +405,9 @@ def cat2_supported(x: torch.Tensor, x2: torch.Tensor, stride=1) -> bool:
 
 
 def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Sequence[int], stride=1, padding=0,
-                 alpha: float = 1.0, w_transposed: bool = False) -> torch.Tensor:
-    """dx of conv2d(x, w) given dy; also conv_transpose2d(dy, w) with output size in_hw."""
+                 alpha: float = 1.0, w_transposed: bool = False, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx of conv2d(x, w) given dy; also conv_transpose2d(dy, w) with output size in_hw.  `add` (shape of dx) is summed
+    into the result inside the kernel's epilogue (gradient accumulation without a separate pass)."""
     _check_f32(dy, "dy")
     _check_f32(w, "w")
     dy, layout = _act(dy)
@@ -420,12 +421,19 @@ def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Sequence[int], stride
     if (d.OH, d.OW) != (OH, OW):
         raise RuntimeError("conv2d_dgrad: dy spatial size (%d,%d) inconsistent with input size (%d,%d)" % (OH, OW, H, W))
     dx = _empty_act((B, C, H, W), layout, dy.device)
+    if add is not None:
+        _check_f32(add, "add")
+        if tuple(add.shape) != (B, C, H, W):
+            raise RuntimeError("conv2d_dgrad: `add` must have the shape of dx")
+        add = add.contiguous(memory_format=torch.channels_last if layout == _lib.LAYOUT_NHWC else torch.contiguous_format)
+        if add.data_ptr() % 16:
+            add = add.clone()
     L = _lib.lib()
     with _on_device(dy.device):
         nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 1, conv_flags)
         ws, wsp = _workspace(nbytes, dy.device)
-        rc = L.msg_conv2d_dgrad(_ptr(dx), _ptr(dy), _ptr(w), ctypes.byref(d), float(alpha), wsp, nbytes,
-                                conv_flags, _stream(dy))
+        rc = L.msg_conv2d_dgrad_acc(_ptr(dx), _ptr(dy), _ptr(w), ctypes.byref(d), float(alpha), _ptr(add), wsp, nbytes,
+                                    conv_flags, _stream(dy))
     _lib.check(rc, "conv2d_dgrad")
     return dx
 

@@ -5,3 +5,5 @@ runs in the hand-written CUDA library ``lib/libmsg_b200.so`` (C-ABI declared in 
 There is no CPU fallback: every op raises if its input is not a CUDA tensor or the library is missing.
 """
 __version__ = "0.1.0"
+
+from ._mode import higher_order_gradients  # noqa: E402,F401

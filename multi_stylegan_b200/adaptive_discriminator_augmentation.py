@@ -236,11 +236,15 @@ class AdaptiveDiscriminatorAugmentation(nn.Module):
             self.r_history.append(r)
 
     # ---- CUDA-graph support ---------------------------------------------------------------------------
-    def begin_plan_capture(self) -> None:
-        self._capture = {"slots": [], "fake_calls": 0}
+    def begin_plan_capture(self, max_batch: int, device, max_calls: int = 8) -> None:
+        """Call BEFORE the capture opens: the plan tensors are allocated here, outside the graph's private memory pool
+        (they are written by eager copies between replays)."""
+        bank = [torch.zeros(plan_size(max_batch), dtype=torch.float32, device=device) for _ in range(max_calls)]
+        self._capture = {"slots": [], "fake_calls": 0, "bank": bank}
 
     def end_plan_capture(self) -> dict:
         cap, self._capture = self._capture, None
+        cap.pop("bank", None)
         return cap
 
     def refresh_plans(self, cap: dict) -> None:
@@ -252,6 +256,8 @@ class AdaptiveDiscriminatorAugmentation(nn.Module):
             self._plan_event.synchronize()       # the previous upload has left the pinned staging buffers
         for slot in cap["slots"]:
             B, H, W = slot["shape"]
+            if slot["host"] is None:
+                slot["host"] = torch.empty(plan_size(B), dtype=torch.float32).pin_memory()
             slot["host"].copy_(build_plan(sample_draws(B, self.p), B, H, W))
             slot["device"].copy_(slot["host"], non_blocking=True)
         if self._plan_event is None:
@@ -266,8 +272,11 @@ class AdaptiveDiscriminatorAugmentation(nn.Module):
         if self._capture is None:
             return self.augmentation_pipeline(flat, self.p, draws)
         B, _, H, W = flat.shape
-        slot = {"shape": (B, H, W), "device": torch.empty(plan_size(B), dtype=torch.float32, device=flat.device),
-                "host": torch.empty(plan_size(B), dtype=torch.float32).pin_memory()}
+        # (the pinned staging buffer is allocated by the first refresh: no host allocation while a capture is open)
+        bank = self._capture["bank"]
+        if not bank or bank[-1].numel() < plan_size(B) or bank[-1].device != flat.device:
+            raise RuntimeError("ADA: no pre-allocated plan tensor for a batch of %d on %s" % (B, flat.device))
+        slot = {"shape": (B, H, W), "device": bank.pop()[:plan_size(B)], "host": None}
         self._capture["slots"].append(slot)
         return self.augmentation_pipeline(flat, self.p, plan=slot["device"])
 

@@ -200,6 +200,69 @@ def conv2d_add_scale(x: torch.Tensor, w: torch.Tensor, other: torch.Tensor, stri
     return _ConvAddScale.apply(x, w, other, _pair(stride), _pair(padding), gain, float(alpha), x2)
 
 
+class ResBlockFused(Function):
+    """The discriminator's residual block (u_net_2d_discriminator.py:174-186)
+        out = (lrelu(conv3x3(lrelu(conv3x3(x) + b1)) + b2) + conv1x1(x)) / sqrt(2)
+    as three kernels forward (both activations and the join live in conv epilogues; the 1/sqrt(2) is folded into the
+    second activation's gain and the residual convolution's alpha) with a hand-written FIRST-ORDER backward: the block
+    input feeds the main and the residual path, and the sum of its two gradients is formed in the epilogue of the main
+    path's dgrad (`add` operand) instead of a separate pass; the scaling by 1/sqrt(2) never runs as a pass either.
+    `x2`: the block is applied to the channel concatenation [x | x2] read in place (U-Net decoder, reference :137).
+    R1 (which differentiates this backward) runs the composite Functions above instead (_mode.higher_order_gradients)."""
+
+    @staticmethod
+    def forward(ctx, x, x2, w1, b1, w2, b2, wr, a1, a2, ar, slope, g1, g2):
+        h1 = _C.conv2d_forward(x, w1, 1, 1, alpha=a1, bias=b1, act=True, slope=slope, gain=g1, x2=x2)
+        h2 = _C.conv2d_forward(h1, w2, 1, 1, alpha=a2, bias=b2, act=True, slope=slope, gain=g2)
+        out = _C.conv2d_forward(x, wr, 1, 0, alpha=ar, add=h2, x2=x2)
+        ctx.save_for_backward(x, x2, w1, w2, wr, h1, h2)
+        ctx.cfg = (a1, a2, ar, slope, g1, g2)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        from ._mode import NO_DOUBLE_BACKWARD
+        if torch.is_grad_enabled():
+            raise RuntimeError(NO_DOUBLE_BACKWARD)
+        x, x2, w1, w2, wr, h1, h2 = ctx.saved_tensors
+        a1, a2, ar, slope, g1, g2 = ctx.cfg
+        need = ctx.needs_input_grad
+        need_x, need_x2, need_w1, need_b1, need_w2, need_b2, need_wr = need[:7]
+        hw = tuple(x.shape[2:])
+        g2_pre, db2, _ = _C.noise_bias_act_cl_bwd(gout, h2, None, slope, g2, need_b2)
+        gh1 = _C.conv2d_dgrad(g2_pre, w2, hw, 1, 1, alpha=a2)
+        dw2 = _C.conv2d_wgrad(g2_pre, h1, (3, 3), 1, 1, False, alpha=a2) if need_w2 else None
+        g1_pre, db1, _ = _C.noise_bias_act_cl_bwd(gh1, h1, None, slope, g1, need_b1)
+        dx = dx2 = dw1 = dwr = None
+        if x2 is None:
+            if need_x:
+                dx = _C.conv2d_dgrad(g1_pre, w1, hw, 1, 1, alpha=a1, add=_C.conv2d_dgrad(gout, wr, hw, 1, 0, alpha=ar))
+            if need_w1:
+                dw1 = _C.conv2d_wgrad(g1_pre, x, (3, 3), 1, 1, False, alpha=a1)
+            if need_wr:
+                dwr = _C.conv2d_wgrad(gout, x, (1, 1), 1, 0, False, alpha=ar)
+        else:
+            c1 = x.shape[1]
+            if need_x:
+                dx = _C.conv2d_dgrad(g1_pre, w1[:, :c1], hw, 1, 1, alpha=a1,
+                                     add=_C.conv2d_dgrad(gout, wr[:, :c1], hw, 1, 0, alpha=ar))
+            if need_x2:
+                dx2 = _C.conv2d_dgrad(g1_pre, w1[:, c1:], hw, 1, 1, alpha=a1,
+                                      add=_C.conv2d_dgrad(gout, wr[:, c1:], hw, 1, 0, alpha=ar))
+            if need_w1:
+                dw1 = torch.cat([_C.conv2d_wgrad(g1_pre, x, (3, 3), 1, 1, False, alpha=a1),
+                                 _C.conv2d_wgrad(g1_pre, x2, (3, 3), 1, 1, False, alpha=a1)], dim=1)
+            if need_wr:
+                dwr = torch.cat([_C.conv2d_wgrad(gout, x, (1, 1), 1, 0, False, alpha=ar),
+                                 _C.conv2d_wgrad(gout, x2, (1, 1), 1, 0, False, alpha=ar)], dim=1)
+        return (dx, dx2, dw1, db1 if need_b1 else None, dw2, db2 if need_b2 else None, dwr,
+                None, None, None, None, None, None)
+
+
+def res_block(x, x2, w1, b1, w2, b2, wr, a1: float, a2: float, ar: float, slope: float, g1: float, g2: float):
+    return ResBlockFused.apply(x, x2, w1, b1, w2, b2, wr, float(a1), float(a2), float(ar), float(slope), float(g1), float(g2))
+
+
 def conv2d(x: torch.Tensor, w: torch.Tensor, stride=1, padding=0, alpha: float = 1.0, x2=None) -> torch.Tensor:
     """alpha * conv(x, w); x [B,C,H,W]; w [O,C,kh,kw] or [B,O,C,kh,kw].  `x2`: convolve [x | x2] (see conv2d_bias_act)."""
     if x2 is not None:

@@ -281,7 +281,8 @@ struct DgradPlan {
   size_t off_x, off_eng, eng_each, total;
 };
 
-static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float* w, float* dx, float alpha, int flags) {
+static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float* w, float* dx, float alpha, int flags,
+                            const float* add = nullptr) {
   DgradPlan pl{};
   const int s = d->stride_h;
   pl.nph = s * s;
@@ -302,6 +303,7 @@ static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float
     g.out_my = s; g.out_mx = s; g.out_oy = py; g.out_ox = px; g.alpha = alpha;
     g.ep = Epilogue{};
     g.ep.gain = 1.f;
+    g.ep.add = add;             // dx = alpha * conv^T(dy, w) + add  (gradient accumulation in the epilogue)
     g.ntaps = 0;
     for (int ky = 0; ky < d->kh; ++ky) {
       if ((py + d->pad_h - ky) % s != 0) continue;
@@ -549,12 +551,19 @@ extern "C" int msg_conv2d_forward_cat2(float* y, const float* x1, int c1, const 
 
 extern "C" int msg_conv2d_dgrad(float* dx, const float* dy, const float* w, const msg_conv_desc* d, float alpha,
                                 void* workspace, size_t workspace_bytes, int flags, msg_stream_t stream) {
+  return msg_conv2d_dgrad_acc(dx, dy, w, d, alpha, nullptr, workspace, workspace_bytes, flags, stream);
+}
+
+extern "C" int msg_conv2d_dgrad_acc(float* dx, const float* dy, const float* w, const msg_conv_desc* d, float alpha,
+                                    const float* add, void* workspace, size_t workspace_bytes, int flags,
+                                    msg_stream_t stream) {
   int rc = check_desc(d, "conv2d_dgrad");
   if (rc) return rc;
   if (d->B == 0) return MSG_OK;
   if (!dx || !dy || !w) return fail(MSG_ERR_BAD_ARG, "conv2d_dgrad: null pointer");
+  if (add == dx) return fail(MSG_ERR_BAD_ARG, "conv2d_dgrad: `add` must not alias dx");
   cudaStream_t st = (cudaStream_t)stream;
-  DgradPlan pl = plan_dgrad(d, dy, w, dx, alpha, flags);
+  DgradPlan pl = plan_dgrad(d, dy, w, dx, alpha, flags, add);
   if (!pl.tc && flags == MSG_CONV_FORCE_TC)
     return fail(MSG_ERR_UNSUPPORTED, "conv2d_dgrad: not eligible for tcgen05 (needs NHWC)");
   uint8_t* ws = nullptr;

@@ -448,7 +448,7 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
             if (has_mod)
               epi_chunk_to_smem<true, true, false, true>(rr, av, bias_nb, nvalid4, nz, ep_alpha, has_act ? ep_slope : 1.f, ep_gain,
                                                          dst, lane, cs_b ? cs_b + nb : nullptr, s2_b ? s2_b + nb : nullptr,
-                                                         has_out2 ? stage_smem + 4096 : 0u);
+                                                         has_out2 ? stage_smem + 4096 + lane * 128 : 0u);
             else if (!has_nb && !has_act && !with_add)
               epi_chunk_to_smem<false, false, false>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
             else if (has_nb && has_act && !with_add)

@@ -28,6 +28,7 @@ import torch.nn as nn
 from . import config as default_config
 from . import dist as mdist
 from . import loss, misc
+from ._mode import higher_order_gradients
 from .u_net_2d_discriminator import (generate_cut_mix_augmentation_data, generate_cut_mix_transformation_data)
 
 
@@ -205,7 +206,7 @@ class ModelWrapper(object):
             self._capture = prog
             ada_begin = getattr(self.discriminator, "begin_plan_capture", None)
             if ada_begin is not None:
-                ada_begin()
+                ada_begin(2 * real_images.shape[0], real_images.device)
             self._segment_begin(prog)
             try:
                 plr.mean_path_length = st.mean_path_length
@@ -218,6 +219,9 @@ class ModelWrapper(object):
                 if prog.open is not None:
                     self._segment_end(prog)
                 st.ada = self.discriminator.end_plan_capture() if ada_begin is not None else None
+            # the loss module was rebound to tensors of the capture (never computed: capturing does not execute); the
+            # running mean lives in the static slot the graph reads and writes
+            plr.mean_path_length = st.mean_path_length
             st.program = prog.items      # CUDA graphs in capture order (one shared pool), eager collectives in between
             st.launches = _C.launch_count() - launches0
             self._graphs[key] = st
@@ -291,7 +295,8 @@ class ModelWrapper(object):
         if lazy_r1:
             self._zero()
             real_r1 = real_images.detach().requires_grad_(True)
-            rp, rp_px = self.discriminator(real_r1, is_real=False, is_cut_mix=True)
+            with higher_order_gradients():      # R1 differentiates the discriminator's input gradient (loss.py:311-316)
+                rp, rp_px = self.discriminator(real_r1, is_real=False, is_cut_mix=True)
             r1 = self.discriminator_regularization_loss(rp, real_r1, rp_px)
             (hp["w_discriminator_regularization_r1"] * r1).backward()
             self._optimize(d_params, self.discriminator_optimizer)

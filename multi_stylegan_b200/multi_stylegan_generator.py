@@ -23,25 +23,11 @@ from .op_static.fused_act import noise_bias_leaky_relu
 from .op_static.upfirdn2d import blur_noise_bias_leaky_relu
 
 
-# The generator has two arithmetically equivalent execution forms (see styled.py): the shared-weight form with
+# The generator has two arithmetically equivalent execution forms (see styled.py, _mode.py): the shared-weight form with
 # hand-written first-order backwards (default; used by no_grad forwards and the generator step) and the reference's
 # per-sample-weight form, every piece of which is differentiable to any order (path-length regularisation).
-_higher_order = 0
-
-
-class higher_order_gradients(object):
-    """Context manager: generator forwards recorded inside can be differentiated through their backward pass
-    (autograd.grad(..., create_graph=True)); Generator.forward(return_path_length_grads=True) enters it itself."""
-
-    def __enter__(self):
-        global _higher_order
-        _higher_order += 1
-        return self
-
-    def __exit__(self, *exc):
-        global _higher_order
-        _higher_order -= 1
-        return False
+from ._mode import higher_order_gradients  # noqa: E402,F401  (re-exported)
+from . import _mode  # noqa: E402
 
 
 def _fir_kernel(taps: List[int]) -> torch.Tensor:
@@ -418,7 +404,7 @@ class Generator(nn.Module):
 
     def _fused_eligible(self, latent: torch.Tensor) -> bool:
         """Shared-weight fast path: live branch only, channel counts the channels-last kernels take."""
-        if self.compute_dead_branch or _higher_order > 0 or not self.fused_modconv:
+        if self.compute_dead_branch or _mode.higher_order() or not self.fused_modconv:
             return False
         convs = [self.starting_convolution_1, self.starting_convolution_2] + list(self.main_convolutions_1)
         return all(c.modulated_convolution.out_channels % 4 == 0 and c.modulated_convolution.in_channels % 4 == 0

@@ -13,7 +13,7 @@ transformed or differentiated, and the weight gradient is one batch-reduced GEMM
 Functions here have hand-written first-order backwards (one sweep `_C.styled_act_bwd` + shared dgrad / wgrad).  They are
 NOT differentiable twice: the path-length regulariser (multi_stylegan_generator.py:193-200), which differentiates the
 generator's backward, runs the per-sample-weight formulation in multi_stylegan_generator.py, whose every piece is
-differentiable to any order."""
+differentiable to any order (_mode.higher_order_gradients)."""
 from typing import Optional, Tuple
 
 import torch
@@ -21,9 +21,7 @@ from torch.autograd import Function
 
 from . import _C
 
-_NO_DOUBLE = ("multi_stylegan_b200.styled: the fused shared-weight path is first-order only; run the forward under "
-              "multi_stylegan_generator.higher_order_gradients() (Generator.forward does that itself for "
-              "return_path_length_grads=True) to differentiate through a backward pass")
+from ._mode import NO_DOUBLE_BACKWARD as _NO_DOUBLE
 
 
 def _check_first_order() -> None:
@@ -84,6 +82,7 @@ class StyledConvFused(Function):
         out, out2 = r if s_next is not None else (r, None)
         ctx.save_for_backward(xs, W, d, out, noise, nw, bias, s_next)
         ctx.cfg = (stride, padding, slope, gain, scale)
+        ctx.set_materialize_grads(False)     # an unused output must reach backward as None, not as a tensor of zeros
         if out2 is None:
             return out, None
         return out, out2
@@ -123,6 +122,7 @@ class StyledUpConvFused(Function):
         out, out2 = _C.blur_noise_bias_act_mod(y, kernel, pad, d, noise, nw, bias, slope, gain, s_next)
         ctx.save_for_backward(xs, W, d, out, noise, nw, bias, s_next, kernel)
         ctx.cfg = (stride, padding, slope, gain, scale, pad, tuple(y.shape))
+        ctx.set_materialize_grads(False)
         return out, out2
 
     @staticmethod

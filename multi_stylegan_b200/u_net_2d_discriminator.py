@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _C, conv, equalized_layer
+from . import _C, _mode, conv, equalized_layer
 from .multi_stylegan_generator import _fir_kernel
 from .op_static import FusedLeakyReLU, upfirdn2d
 
@@ -109,12 +109,20 @@ class ResNetBlock(nn.Module):
             return (output + self.residual_mapping(input)) / math.sqrt(2)
         # (lrelu(conv(lrelu(conv(x)))) + conv1x1(x)) / sqrt(2) in three kernels: both activations and the residual
         # join run in the conv epilogues (reference :174-186)
+        j = 1.0 / math.sqrt(2)
+        if (isinstance(self.mini_batch_std_dev, nn.Identity) and not _mode.higher_order()
+                and tuple(c1.weight.shape[-2:]) == (3, 3) and tuple(c2.weight.shape[-2:]) == (3, 3)
+                and tuple(res.weight.shape[-2:]) == (1, 1) and c1.stride == (1, 1) and c1.padding == (1, 1)
+                and c2.stride == (1, 1) and c2.padding == (1, 1) and res.stride == (1, 1) and res.padding == (0, 0)
+                and a1.negative_slope == a2.negative_slope):
+            # first-order form: one Function for the block, input gradients summed in the dgrad epilogue (conv.ResBlockFused)
+            return conv.res_block(input, input_2, c1.weight, a1.bias, c2.weight, a2.bias, res.weight, c1.scale, c2.scale,
+                                  res.scale * j, a1.negative_slope, a1.scale, a2.scale * j)
         x = self.mini_batch_std_dev(input)
         h = conv.conv2d_bias_act(x, c1.weight, bias=a1.bias, stride=c1.stride, padding=c1.padding,
                                  negative_slope=a1.negative_slope, gain=a1.scale, alpha=c1.scale, x2=input_2)
         # the join's 1/sqrt(2) is folded into the second activation's gain and the residual convolution's alpha, so
         # neither the forward nor the backward spends a pass on the scaling
-        j = 1.0 / math.sqrt(2)
         h = conv.conv2d_bias_act(h, c2.weight, bias=a2.bias, stride=c2.stride, padding=c2.padding,
                                  negative_slope=a2.negative_slope, gain=a2.scale * j, alpha=c2.scale)
         return conv.conv2d_add_scale(input, res.weight, h, stride=res.stride, padding=res.padding,

@@ -52,8 +52,9 @@ def _tail(v, bias, noise, noise_w, add, act, slope, gain):
     return v * gain
 
 
-def conv2d_dgrad(dy, w, in_hw, stride=1, padding=0, alpha=1.0, w_transposed=False):
-    return ops.conv2d_dgrad(dy, _wt(w, w_transposed), in_hw, stride, padding) * alpha
+def conv2d_dgrad(dy, w, in_hw, stride=1, padding=0, alpha=1.0, w_transposed=False, add=None):
+    dx = ops.conv2d_dgrad(dy, _wt(w, w_transposed), in_hw, stride, padding) * alpha
+    return dx if add is None else dx + add
 
 
 def conv2d_wgrad(dy, x, khw, stride=1, padding=0, per_sample=False, alpha=1.0, w_transposed=False):

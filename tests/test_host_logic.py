@@ -130,7 +130,8 @@ def check_path_length(g, net, dev="cpu", tol=1e-4, tf32=False):
     else:
         # reproduce forward's internals with the fixture's direction (device RNG streams differ)
         latent = net._latent(g["z1"].to(dev), False, None)
-        image = net(latent, noise=noise, input_is_latent=True)
+        with G_mod.higher_order_gradients():         # (Generator.forward enters this itself for return_path_length_grads)
+            image = net(latent, noise=noise, input_is_latent=True)
         pl_grad = torch.autograd.grad((image * g["pl_noise"].to(dev)).sum(), latent, create_graph=True)[0]
     if tf32:
         assert l2_err(pl_grad, g["pl_grad"]) < 0.05, l2_err(pl_grad, g["pl_grad"])
@@ -180,7 +181,9 @@ def check_discriminator(g, dev="cpu", tol=1e-5, tf32=False):
 
 def check_r1(g, net, dev="cpu"):
     xr = g["x"].to(dev).clone().requires_grad_(True)
-    s, p = net(xr, is_real=False, is_cut_mix=True)
+    from multi_stylegan_b200 import higher_order_gradients
+    with higher_order_gradients():          # R1 differentiates D's backward: the any-order execution form (_mode.py)
+        s, p = net(xr, is_real=False, is_cut_mix=True)
     r1 = loss.R1Regularization()(s, xr, p)
     err = rel_err(r1, g["r1"])
     net.zero_grad()
@@ -357,3 +360,15 @@ def test_generator_fused_shared_weight_path_equals_per_sample_path(oracle_backen
         torch.autograd.grad((image * direction).sum(), z[0], create_graph=True)
     # the path-length entry point switches to the any-order form by itself
     assert net(g["z1"], noise=noise, return_path_length_grads=True).requires_grad
+
+
+def test_discriminator_first_order_form_refuses_double_backward(oracle_backend):
+    """The residual blocks' fused first-order backward (conv.ResBlockFused) is what a plain forward records; R1 needs the
+    any-order form and gets a clear error otherwise."""
+    g = load_golden("discriminator.pt")
+    net = D_mod.Discriminator(g["config"], no_rfp=True)
+    net.load_state_dict(g["state_dict"], strict=True)
+    xr = g["x"].clone().requires_grad_(True)
+    s, p = net(xr)
+    with pytest.raises(RuntimeError, match="first-order only"):
+        loss.R1Regularization()(s, xr, p)

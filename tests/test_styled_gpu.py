@@ -210,3 +210,28 @@ def test_fused_layer_matches_reference_layer(built_library, up, engine):
             assert err < 5e-2, (name, err)
         else:
             assert rel_err(got, want) < tol, (name, rel_err(got, want))
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 64, 32, 32, 3, 1, 1), (2, 64, 128, 16, 16, 1, 1, 0), (2, 32, 32, 64, 64, 3, 2, 0),
+                                   (2, 48, 40, 32, 32, 2, 2, 0), (2, 6, 32, 64, 64, 3, 1, 1), (1, 256, 256, 64, 64, 3, 1, 1)])
+@pytest.mark.parametrize("engine", ["tc", "simt"])
+def test_dgrad_accumulate_operand(built_library, shape, engine):
+    """msg_conv2d_dgrad_acc: dx = alpha * conv^T(dy, w) + add, the sum formed in the kernel's epilogue (stride 1 and the
+    phase-scattered stride-2 form; C = 6 takes the unaligned store path)."""
+    from multi_stylegan_b200 import _C, _lib
+    if engine == "tc" and not _C.tensor_core_path_available():
+        pytest.skip("not an sm_100 device")
+    B, C, O, H, W, k, s, p = shape
+    g = torch.Generator().manual_seed(C + O)
+    w = torch.randn(O, C, k, k, generator=g) / math.sqrt(C * k * k)
+    OH, OW = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+    dy = torch.randn(B, O, OH, OW, generator=g)
+    add = torch.randn(B, C, H, W, generator=g)
+    want = ops.conv2d_dgrad(dy, w, (H, W), s, p) * 0.6 + add
+    old = _C.conv_flags
+    _C.conv_flags = _lib.CONV_FORCE_TC if engine == "tc" else _lib.CONV_FORCE_SIMT
+    try:
+        got = _C.conv2d_dgrad(cl(dy), w.to(dev()), (H, W), s, p, alpha=0.6, add=cl(add))
+    finally:
+        _C.conv_flags = old
+    assert rel_err(got, want) < (1e-2 if engine == "tc" else 1e-4), rel_err(got, want)
