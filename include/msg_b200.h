@@ -61,6 +61,10 @@ typedef struct {
 void msg_profile_enable(int on);
 int msg_profile_summary(msg_profile_entry* out, int max_entries);
 
+/* Roofline probe (bench.py): one launch of `iters` x 4 back-to-back tcgen05.mma.kind::tf32 (128 x 256 x 8, operands in
+ * shared memory, one CTA per SM); *flops receives the FLOPs of the launch.  sink: >= 32 * #SMs floats or NULL. */
+int msg_tf32_mma_rate_probe(int iters, float* sink, double* flops, msg_stream_t stream);
+
 /* -------------------------------------------------------------------------------------------
  * fused_bias_act  — replaces fused_act_cuda.fused_bias_act
  *   multi_stylegan/op_static/fused_bias_act.cpp:11-20, fused_bias_act_kernel.cu:18-99

@@ -492,6 +492,18 @@ def profile_summary():
     return out
 
 
+def tf32_mma_rate_probe(iters: int, device) -> float:
+    """Launch the tensor-core issue-rate probe (csrc/mma_rate.cu) on torch's current stream; returns its FLOPs."""
+    flops = ctypes.c_double(0.0)
+    dev = torch.device(device)
+    with _on_device(dev):
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        stream = ctypes.c_void_p(_raw_stream(idx)) if _raw_stream is not None else ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        rc = _lib.lib().msg_tf32_mma_rate_probe(int(iters), None, ctypes.byref(flops), stream)
+    _lib.check(rc, "tf32_mma_rate_probe")
+    return float(flops.value)
+
+
 def launch_count() -> int:
     return int(_lib.lib().msg_launch_count())
 

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "msg_debug_buffer": (_c.POINTER(_c.c_uint32), [_c.POINTER(_c.c_size_t)]),
     "msg_profile_enable": (None, [_c.c_int]),
     "msg_profile_summary": (_c.c_int, [_c.POINTER(ProfileEntry), _c.c_int]),
+    "msg_tf32_mma_rate_probe": (_c.c_int, [_c.c_int, _c.c_void_p, _c.POINTER(_c.c_double), _c.c_void_p]),
     "msg_fused_bias_act": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                       _c.c_double, _c.c_double, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int,
                                       _c.c_void_p]),

@@ -32,6 +32,19 @@ from ._mode import higher_order_gradients
 from .u_net_2d_discriminator import (generate_cut_mix_augmentation_data, generate_cut_mix_transformation_data)
 
 
+_CAPTURE_STREAMS: Dict[Any, Any] = {}
+
+
+def _capture_stream(device) -> "torch.cuda.Stream":
+    """One capture stream per device for every wrapper and graph variant of the process: autograd's AccumulateGrad nodes
+    remember the stream they were created on, and a capture that has to synchronise with another (non-capturing) side
+    stream of an earlier capture is invalidated."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _CAPTURE_STREAMS:
+        _CAPTURE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _CAPTURE_STREAMS[key]
+
+
 class ModelWrapper(object):
     def __init__(self,
                  generator: nn.Module,
@@ -202,7 +215,8 @@ class ModelWrapper(object):
             st.mean_path_length = plr.mean_path_length.detach().to(real_images.device).clone()
             torch.cuda.synchronize(real_images.device)
             launches0 = _C.launch_count()
-            prog = SimpleNamespace(items=[], pool=torch.cuda.graph_pool_handle(), stream=torch.cuda.Stream(), open=None)
+            prog = SimpleNamespace(items=[], pool=torch.cuda.graph_pool_handle(),
+                                   stream=_capture_stream(real_images.device), open=None)
             self._capture = prog
             ada_begin = getattr(self.discriminator, "begin_plan_capture", None)
             if ada_begin is not None:

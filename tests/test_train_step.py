@@ -385,7 +385,9 @@ def test_cuda_graph_replay_with_ada_matches_eager(built_library):
         mw._d_params = lambda: list(D.parameters())
         return mw, (G, D)
     runs = _graph_vs_eager(make, lambda mw, it, gen: {}, n_iter=8)
-    _assert_same_runs(runs)
+    # the adjoint of the warp scatters with fp32 atomics (summation order varies between launches); Adam's normalised
+    # steps amplify those last-bit differences over the iterations, hence the looser bound than for the atomics-free step
+    _assert_same_runs(runs, rtol=3e-2)
     eager, graphed = runs[0][0], runs[1][0]
     assert graphed.graph_replays >= 4
     assert eager.discriminator.r_history == pytest.approx(graphed.discriminator.r_history)

@@ -1,4 +1,4 @@
-"""Diagnostic: which operation of the ADA pipeline breaks CUDA-graph capture (each step captured on its own)."""
+"""Diagnostic: which operation of the ADA path breaks CUDA-graph capture (each step captured on its own)."""
 import os
 import sys
 
@@ -23,23 +23,33 @@ def attempt(name, fn):
             out = fn()
         g.replay()
         torch.cuda.synchronize()
-        print("OK   ", name)
+        print("OK   ", name, flush=True)
         return out
     except Exception as exc:
-        print("FAIL ", name, type(exc).__name__, str(exc)[:160].replace("\n", " "))
-        torch.cuda.synchronize()
+        print("FAIL ", name, type(exc).__name__, str(exc)[:200].replace("\n", " "), flush=True)
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
         return None
 
 
+def fwd_bwd(fn):
+    def run():
+        xi = x.clone().requires_grad_(True)
+        out = fn(xi * 1.0)
+        out.sum().backward()
+        return xi.grad
+    return run
+
+
+th = plan[2 * B + 2:].view(5, B, 2, 3)
 fn_list = [
-    ("flip-select", lambda: torch.where(plan[:B].view(B, 1, 1, 1) > 0.5, x.flip(dims=(-1,)), x)),
-    ("theta view + clone", lambda: plan[2 * B + 2:].view(5, B, 2, 3)[0].clone()),
-    ("warp", lambda: A.affine_warp(x, plan[2 * B + 2:].view(5, B, 2, 3)[1], mode=0)),
-    ("shift", lambda: plan[2 * B:2 * B + 2].round().to(torch.long)),
-    ("arange-roll", lambda: torch.remainder(torch.arange(H, device=dev) - plan[2 * B:2 * B + 2].round().to(torch.long)[0], H)),
-    ("index_select", lambda: x.index_select(2, torch.remainder(torch.arange(H, device=dev) - 3, H))),
-    ("apply_plan", lambda: A.apply_plan(x, plan)),
-    ("pipeline(plan)", lambda: A.AugmentationPipeline()(x, 0.5, plan=plan)),
+    ("flip fwd+bwd", fwd_bwd(lambda t: torch.where(plan[:B].view(B, 1, 1, 1) > 0.5, t.flip(dims=(-1,)), t))),
+    ("warp fwd+bwd", fwd_bwd(lambda t: A.affine_warp(t, th[1], mode=0))),
+    ("index_select fwd+bwd", fwd_bwd(lambda t: t.index_select(2, torch.remainder(torch.arange(H, device=dev) - 3, H)))),
+    ("index_select dim3 fwd+bwd", fwd_bwd(lambda t: t.index_select(3, torch.remainder(torch.arange(W, device=dev) - 3, W)))),
+    ("apply_plan fwd+bwd", fwd_bwd(lambda t: A.apply_plan(t, plan))),
 ]
 for name, fn in fn_list:
     fn()
