@@ -297,6 +297,9 @@ def run_ours(args):
                 raise
             print("[bench rank %d] CUDA-graph capture failed (%s: %s)" % (rank, type(exc).__name__, str(exc)[:300]),
                   file=sys.stderr, flush=True)
+            if VERBOSE:
+                import traceback
+                traceback.print_exc(file=sys.stderr)
             ok = False
         if state["graphs"] and not agree(ok):
             # every rank leaves graph mode together and repeats the warm-up eagerly
@@ -413,9 +416,14 @@ def run_ours(args):
             # allocation that has to free cached blocks while a capture is open invalidates the capture)
             import gc
             g_ema = None
-            mw.reset_cuda_graphs()
-            gc.collect()
-            torch.cuda.empty_cache()
+            if VERBOSE:
+                print("[bench rank %d] memory with the plain wrapper's graphs: %.1f GiB allocated, %.1f GiB reserved" %
+                      (rank, torch.cuda.memory_allocated() / 2 ** 30, torch.cuda.memory_reserved() / 2 ** 30),
+                      file=sys.stderr, flush=True)
+            if os.environ.get("MSG_BENCH_KEEP_GRAPHS") != "1":
+                mw.reset_cuda_graphs()
+                gc.collect()
+                torch.cuda.empty_cache()
             if VERBOSE:
                 print("[bench rank %d] memory before the ADA variant: %.1f GiB allocated, %.1f GiB reserved" %
                       (rank, torch.cuda.memory_allocated() / 2 ** 30, torch.cuda.memory_reserved() / 2 ** 30),
@@ -459,7 +467,7 @@ def run_ours(args):
     cfg["lazy_r1_and_pl_steps_in_timed_region"] = len(lazy_idx)
     hbm, bf16_burst, bf16_sust, src = peaks()
     if mma_sust is not None:
-        tf32_peak, peak_source = mma_sust, "measured in this run: tcgen05.mma.kind::tf32 128x256x8 issue rate on all SMs, operands " \
+        tf32_peak, peak_source = max(mma_sust, mma_burst), "measured in this run: tcgen05.mma.kind::tf32 128x256x8 issue rate on all SMs, operands " \
             "in shared memory (csrc/mma_rate.cu), launches back to back for 1.5 s: sustained %.0f TFLOP/s (best of 10 burst " \
             "%.0f).  The method of MEASURED_PEAKS.json applied to TF32 through cuBLAS (torch.matmul 8192^3, TF32 allowed) " \
             "gives %.0f sustained / %.0f burst TFLOP/s on this box — slower than this kernel, so it cannot serve as a peak; " \

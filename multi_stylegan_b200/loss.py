@@ -54,10 +54,16 @@ class PathLengthRegularization(nn.Module):
         self.mean_path_length = torch.zeros(1, dtype=torch.float)
 
     def forward(self, grad: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-        self.mean_path_length = self.mean_path_length.detach().to(grad.device)
+        mean = self.mean_path_length.detach().to(grad.device)
         path_lengths = torch.sqrt(grad.pow(2).sum(2).mean(1) + 1e-08).mean()
-        self.mean_path_length = self.mean_path_length + self.decay * (path_lengths.mean() - self.mean_path_length)
-        return torch.mean((path_lengths - self.mean_path_length) ** 2), path_lengths
+        mean = mean + self.decay * (path_lengths.mean() - mean)
+        penalty = torch.mean((path_lengths - mean) ** 2)        # the gradient flows through the updated mean (:392-394)
+        # The reference keeps the attribute attached to the graph until the next call detaches it (:385).  The values
+        # are the same with the attribute detached right away, and the generator's whole double-backward graph — and
+        # with it the parameters' AccumulateGrad nodes, which are bound to the stream they were created on and would
+        # break a later CUDA-graph capture — is released as soon as the penalty's backward has run.
+        self.mean_path_length = mean.detach()
+        return penalty, path_lengths
 
 
 class TopK(nn.Module):

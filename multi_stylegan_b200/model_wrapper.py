@@ -17,6 +17,7 @@ sub-steps and the same lazy-regularisation cadence, restructured for one-process
     wrapper's per-call host decisions) run eagerly on the same parameters and optimiser state.
 """
 import copy
+import os
 import random
 from types import SimpleNamespace
 from typing import Any, Callable, Dict, Iterable, Optional
@@ -129,7 +130,10 @@ class ModelWrapper(object):
     @staticmethod
     def _segment_begin(prog) -> None:
         graph = torch.cuda.CUDAGraph()
-        ctx = torch.cuda.graph(graph, pool=prog.pool, stream=prog.stream)
+        # thread_local: CUDA calls of other threads (the pinned-memory allocator's event queries, autograd worker
+        # threads of an earlier eager pass, NCCL's watchdog) do not invalidate this thread's capture
+        ctx = torch.cuda.graph(graph, pool=prog.pool, stream=prog.stream,
+                               capture_error_mode=os.environ.get("MSG_B200_CAPTURE_MODE", "thread_local"))
         ctx.__enter__()
         prog.open = (graph, ctx)
 
