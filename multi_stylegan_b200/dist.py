@@ -46,19 +46,47 @@ def broadcast_parameters(modules: Iterable[torch.nn.Module], src: int = 0, group
             t.copy_(f)
 
 
+class PendingReduce(object):
+    """An averaging all-reduce in flight: `wait()` orders the current stream after the collective and writes the
+    averages back into the tensors (one multi-tensor copy)."""
+
+    def __init__(self, tensors, flat, work, divide_by):
+        self.tensors, self.flat, self.work, self.divide_by = tensors, flat, work, divide_by
+
+    @torch.no_grad()
+    def wait(self) -> int:
+        if self.work is not None:
+            self.work.wait()
+        if self.divide_by != 1:
+            self.flat.div_(self.divide_by)
+        views = torch._utils._unflatten_dense_tensors(self.flat, self.tensors)
+        if self.flat.is_cuda:
+            torch._foreach_copy_(list(self.tensors), list(views))
+        else:
+            for g, f in zip(self.tensors, views):
+                g.copy_(f)
+        return self.flat.numel()
+
+
+@torch.no_grad()
+def all_reduce_tensors_begin(tensors: List[torch.Tensor], group=None) -> Optional[PendingReduce]:
+    """Start averaging the given tensors across ranks with ONE collective on a flat fp32 buffer (NCCL: ReduceOp.AVG,
+    asynchronous on NCCL's stream, so kernels issued before `wait()` overlap the transfer)."""
+    ws = world_size(group)
+    if ws == 1 or not tensors:
+        return None
+    flat = torch._utils._flatten_dense_tensors(tensors)
+    nccl = dist.get_backend(group) == "nccl"
+    work = dist.all_reduce(flat, op=dist.ReduceOp.AVG if nccl else dist.ReduceOp.SUM, group=group, async_op=True)
+    return PendingReduce(tensors, flat, work, 1 if nccl else ws)
+
+
 @torch.no_grad()
 def all_reduce_tensors(tensors: List[torch.Tensor], group=None) -> int:
     """Average the given tensors across ranks in place with ONE collective on a flat fp32 buffer; returns the
     number of elements reduced."""
-    ws = world_size(group)
-    if ws == 1 or not tensors:
-        return 0
-    flat = torch._utils._flatten_dense_tensors(tensors)
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat.div_(ws)
-    for g, f in zip(tensors, torch._utils._unflatten_dense_tensors(flat, tensors)):
-        g.copy_(f)
-    return flat.numel()
+    pending = all_reduce_tensors_begin(tensors, group)
+    return 0 if pending is None else pending.wait()
 
 
 @torch.no_grad()

@@ -110,10 +110,42 @@ class ModelWrapper(object):
     def _d_params(self):
         return [p for p in self.discriminator.parameters()]
 
+    def _reduce_begin(self, params, extra=()):
+        """Start the cross-rank average of the gradients (and of `extra` state tensors); returns a token for
+        `_reduce_end`.  The collective is asynchronous, so what the caller issues before `_reduce_end` overlaps the
+        transfer.  While an iteration is being captured the collective is a graph break: the capture is cut into segments
+        and the all-reduce is issued eagerly between their replays on the tensors the segments produce (static
+        addresses in the shared graph pool)."""
+        if not (mdist.world_size(self.process_group) > 1 or self._always_break):
+            return None
+        tensors = [p.grad for p in params if p.grad is not None] + list(extra)
+        prog = self._capture
+        if prog is None:
+            return ("eager", mdist.all_reduce_tensors_begin(tensors, self.process_group))
+        box = {}
+        self._segment_end(prog)
+        prog.items.append(lambda t=tensors, g=self.process_group, b=box: b.__setitem__("p", mdist.all_reduce_tensors_begin(t, g)))
+        self._segment_begin(prog)
+        return ("graph", box)
+
+    def _reduce_end(self, token, params, optimizer) -> None:
+        """Wait for the averaged gradients, clip, step."""
+        if token is not None:
+            kind, state = token
+            if kind == "eager":
+                if state is not None:
+                    state.wait()
+            else:
+                prog = self._capture
+                self._segment_end(prog)
+                prog.items.append(lambda b=state: b["p"].wait() if b.get("p") is not None else None)
+                self._segment_begin(prog)
+        torch.nn.utils.clip_grad_norm_(params, max_norm=5.)
+        optimizer.step()
+
     def _optimize(self, params, optimizer, extra=()) -> None:
-        """Cross-rank average of the gradients (and of `extra` state tensors), clip, step.  While an iteration is being
-        captured the collective is a graph break: the capture is cut into segments and the all-reduce is issued eagerly
-        between their replays on the tensors the segments produce (static addresses in the shared graph pool)."""
+        """Cross-rank average of the gradients (and of `extra` state tensors), clip, step — without anything in between
+        (one graph break instead of two while capturing)."""
         if mdist.world_size(self.process_group) > 1 or self._always_break:
             prog = self._capture
             if prog is None:
@@ -304,7 +336,13 @@ class ModelWrapper(object):
         l_real, l_fake = self.discriminator_loss(real_pred, fake_pred)
         l_real_px, l_fake_px = self.discriminator_loss(real_pred_px, fake_pred_px, weight=self._trap())
         (l_real + l_fake + l_real_px + l_fake_px).backward()
-        self._optimize(d_params, self.discriminator_optimizer)
+        # With several ranks and nothing between this step and the generator step that needs the updated discriminator
+        # (no lazy R1, no CutMix), the gradient all-reduce overlaps the generator step's generator forward, which does
+        # not depend on the discriminator (same results, different issue order).
+        overlap = not lazy_r1 and not cut_mix
+        pending = self._reduce_begin(d_params) if overlap else None
+        if not overlap:
+            self._optimize(d_params, self.discriminator_optimizer)
         out.update(loss_discriminator_real=l_real.detach(), loss_discriminator_fake=l_fake.detach(),
                    loss_discriminator_real_pixel_wise=l_real_px.detach(),
                    loss_discriminator_fake_pixel_wise=l_fake_px.detach())
@@ -339,8 +377,15 @@ class ModelWrapper(object):
             out["loss_cut_mix_regularization"] = cm_reg.detach()
 
         # ---------------- generator step (:377-416) ----------------
-        self._zero()
-        fake_images = self._generate(B, z_g, inject, 1)
+        if overlap:
+            # (the generator's gradients are still None from the zero_grad before the discriminator step, whose generator
+            # pass ran under no_grad: the forward can be recorded before this phase's zero_grad)
+            fake_images = self._generate(B, z_g, inject, 1)
+            self._reduce_end(pending, d_params, self.discriminator_optimizer)
+            self._zero()
+        else:
+            self._zero()
+            fake_images = self._generate(B, z_g, inject, 1)
         # The reference lets autograd compute all discriminator weight gradients here and then discards them
         # (zero_grad of both optimisers precedes the next phase, :260-261,:379-380); they are unobservable, so the
         # discriminator is differentiated w.r.t. its input only.

@@ -1,5 +1,10 @@
-"""Oracle restatement of one iteration of the reference trainer (model_wrapper.py:253-451, epoch-0 behaviour:
-no ADA, no CutMix, no wrong-order fakes, no top-k) on reference-named parameter dicts, CPU fp32.
+"""Oracle restatement of one iteration of the reference trainer (model_wrapper.py:253-451) on reference-named
+parameter dicts, CPU fp32.  Epoch-0 behaviour by default (no CutMix, no wrong-order fakes, no top-k, no trap weights);
+`late` switches the late-epoch branches on with every random draw injected:
+    late = {"perm": frame permutation (:268-273), "n_wrong": number of wrong-order reals appended to the fakes,
+            "cut_mix": (binary map of the augmentation step, binary map of the consistency step) (:331-376,
+                        u_net_2d_discriminator.py:384-448), "top_k_v": fraction kept in the generator step (:392-401,
+                        loss.py:420-444), "trap": pixel-wise loss weight map or None (:262-263,:404-405)}
 TEST INFRASTRUCTURE ONLY."""
 import math
 from typing import Dict, List
@@ -45,16 +50,24 @@ class OracleTrainer:
         for p in params:
             p.grad = None
 
-    def step(self, real, z_d, z_g, z_pl, noise_d, noise_g, noise_pl, inject, pl_noise):
+    def step(self, real, z_d, z_g, z_pl, noise_d, noise_g, noise_pl, inject, pl_noise, late=None):
+        import torch.nn.functional as F
         hp, out = self.hp, {}
+        late = late or {}
+        trap = late.get("trap")
+
+        def weighted(v):                                     # loss.py:116-131,146-170 with `weight`
+            return v if trap is None else v * trap.view(1, 1, 1, trap.shape[-2], trap.shape[-1])
         self.iteration += 1
         with torch.no_grad():
             fake = om.generator_forward({k: v.detach() for k, v in self.sd_g.items()}, z_d, noise_d, inject,
                                         dead_branch=self.dead_branch)
+            if late.get("n_wrong"):                          # model_wrapper.py:268-273
+                fake = torch.cat([fake, real[:late["n_wrong"]][:, :, late["perm"]]], dim=0)
         rs, rp = om.discriminator_forward(self.sd_d, real)
         fs, fp = om.discriminator_forward(self.sd_d, fake)
         lr_, lf_ = om.ns_discriminator_loss(rs, fs)
-        lrp, lfp = om.ns_discriminator_loss(rp, fp)
+        lrp, lfp = weighted(F.softplus(-rp)).mean(), weighted(F.softplus(fp)).mean()
         out.update(loss_discriminator_real=lr_.detach(), loss_discriminator_fake=lf_.detach(),
                    loss_discriminator_real_pixel_wise=lrp.detach(), loss_discriminator_fake_pixel_wise=lfp.detach())
         self._apply(self.sd_d, self.d_names, lr_ + lf_ + lrp + lfp, self.opt_d)
@@ -62,9 +75,28 @@ class OracleTrainer:
             r1 = om.r1_penalty(self.sd_d, real)
             out["loss_discriminator_regularization"] = r1.detach()
             self._apply(self.sd_d, self.d_names, hp["w_discriminator_regularization_r1"] * r1, self.opt_d)
+        if late.get("cut_mix") is not None:                  # model_wrapper.py:331-376
+            w = hp["w_discriminator_regularization"]
+            map_a, map_b = late["cut_mix"]
+            n = real.shape[0]
+            mixed = real * map_a + fake[:n] * (1.0 - map_a)                              # u_net_2d_discriminator.py:395-401
+            _, pred = om.discriminator_forward(self.sd_d, mixed)
+            cm = (F.softplus(-pred) * map_a).mean() + (F.softplus(pred) * (1.0 - map_a)).mean()   # loss.py:189-195
+            out["loss_cut_mix_augmentation"] = cm.detach()
+            self._apply(self.sd_d, self.d_names, w * cm, self.opt_d)
+            mixed = real * map_b + fake[:n] * (1.0 - map_b)                              # :416-425 (predictions of the D step)
+            target = rp.detach() * map_b + fp.detach()[:n] * (1.0 - map_b)
+            _, pred = om.discriminator_forward(self.sd_d, mixed)
+            reg = F.mse_loss(pred, target)
+            out["loss_cut_mix_regularization"] = reg.detach()
+            self._apply(self.sd_d, self.d_names, w * reg, self.opt_d)
         fake = om.generator_forward(self.sd_g, z_g, noise_g, inject, dead_branch=self.dead_branch)
         fs, fp = om.discriminator_forward(self.sd_d, fake)
-        lg, lgp = om.ns_generator_loss(fs), om.ns_generator_loss(fp)
+        if late.get("top_k_v") is not None:                  # model_wrapper.py:392-401, loss.py:436-443
+            flat = fs.view(-1)
+            fs, idx = torch.topk(flat, k=max(1, int(flat.shape[0] * late["top_k_v"])))
+            fp = fp[idx]
+        lg, lgp = om.ns_generator_loss(fs), weighted(F.softplus(-fp)).mean()
         out.update(loss_generator=lg.detach(), loss_generator_pixel_wise=lgp.detach())
         self._apply(self.sd_g, self.g_names, lg + lgp, self.opt_g)
         if self.iteration % hp["lazy_generator_regularization"] == 0:

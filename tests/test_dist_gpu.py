@@ -1,0 +1,126 @@
+"""GPU, >= 2 devices: data-parallel parity over NCCL.
+
+Two ranks x b samples, gradients all-reduced over NCCL/NVLink by ModelWrapper, against ONE GPU x 2b samples with
+MinibatchStdDev evaluated per b-sized group (which is what each DataParallel replica of the reference computes,
+u_net_2d_discriminator.py:212-214).  The single-GPU side runs the two shards as two lock-stepped trainers in one process
+whose "collective" is an in-process mean — the same arithmetic as one 2b batch with per-group statistics, and
+independent of NCCL.  Two iterations (plain + lazy R1 / path length), fixed latents and noise maps, real kernels."""
+import os
+import threading
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from tests.conftest import rel_err
+from tests.test_train_step import FixedNoiseGenerator, _hp, build
+
+pytestmark = pytest.mark.gpu
+B, WORLD, ITERS = 2, 2, 2
+
+
+def _inputs(rank):
+    gen = torch.Generator().manual_seed(1000 + rank)
+    noise = [torch.randn(B, 1, 4, 4, generator=gen)] + \
+            [torch.randn(B, 1, 2 ** (i // 2 + 3), 2 ** (i // 2 + 3), generator=gen) for i in range(6)]
+    steps = []
+    for _ in range(ITERS):
+        steps.append(dict(real=torch.rand(B, 2, 3, 32, 32, generator=gen),
+                          z_d=[torch.randn(B, 16, generator=gen), torch.randn(B, 16, generator=gen)],
+                          z_g=[torch.randn(B, 16, generator=gen), torch.randn(B, 16, generator=gen)],
+                          z_pl=[torch.randn(1, 16, generator=gen), torch.randn(1, 16, generator=gen)],
+                          pl_noise=torch.randn(1, 2, 3, 32, 32, generator=gen)))
+    return noise, steps
+
+
+def _train(rank, dev, process_group=None):
+    from multi_stylegan_b200.model_wrapper import ModelWrapper
+    hp = _hp()
+    G, D = build(dev, seed=0)
+    noise, steps = _inputs(rank)
+    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"])
+    opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"])
+    mw = ModelWrapper(FixedNoiseGenerator(G, [n.to(dev) for n in noise], 3), D, opt_g, opt_d, hyperparameters=hp,
+                      generator_ema=__import__("copy").deepcopy(G), device=dev, process_group=process_group)
+    losses = []
+    for s in steps:
+        out = mw.train_step(s["real"].to(dev), z_d=[z.to(dev) for z in s["z_d"]], z_g=[z.to(dev) for z in s["z_g"]],
+                            z_pl=[z.to(dev) for z in s["z_pl"]], pl_noise=s["pl_noise"].to(dev).requires_grad_(True))
+        losses.append({k: v.detach().cpu() for k, v in out.items()})
+    torch.cuda.synchronize(dev)
+    return {"losses": losses, "g": [p.detach().cpu() for p in G.parameters()], "d": [p.detach().cpu() for p in D.parameters()],
+            "pl_mean": mw.path_length_regularization.mean_path_length.detach().cpu()}
+
+
+def _nccl_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        torch.save(_train(rank, torch.device("cuda", rank)), os.path.join(tmp, "nccl%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+class _Lockstep:
+    """In-process stand-in for the collective: every participant contributes its flat buffer, all receive the mean."""
+
+    def __init__(self, n):
+        self.n, self.barrier, self.slots, self.local = n, threading.Barrier(n), [None] * n, threading.local()
+
+    def all_reduce_tensors(self, tensors, group=None):
+        if not tensors:
+            return 0
+        flat = torch._utils._flatten_dense_tensors(tensors)
+        torch.cuda.synchronize()
+        self.slots[self.local.rank] = flat
+        self.barrier.wait()
+        total = sum(self.slots[1:], self.slots[0].clone()) / self.n
+        self.barrier.wait()
+        for t, f in zip(tensors, torch._utils._unflatten_dense_tensors(total, tensors)):
+            t.copy_(f)
+        return flat.numel()
+
+
+@pytest.mark.timeout(900)
+def test_two_ranks_over_nccl_equal_one_gpu_with_per_group_statistics(built_library, tmp_path):
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs %d GPUs" % WORLD)
+    import unittest.mock as um
+    from multi_stylegan_b200 import dist as mdist
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_nccl_worker, args=(WORLD, port, str(tmp_path)), nprocs=WORLD, join=True)
+    nccl = [torch.load(os.path.join(str(tmp_path), "nccl%d.pt" % r), weights_only=False) for r in range(WORLD)]
+
+    ls = _Lockstep(WORLD)
+    results, errors = [None] * WORLD, []
+
+    def run(rank):
+        try:
+            ls.local.rank = rank
+            results[rank] = _train(rank, torch.device("cuda", 0))
+        except BaseException as exc:            # a dead participant must not leave the other one in the barrier
+            errors.append(exc)
+            ls.barrier.abort()
+    with um.patch.object(mdist, "world_size", lambda group=None: WORLD), \
+            um.patch.object(mdist, "all_reduce_tensors", ls.all_reduce_tensors):
+        threads = [threading.Thread(target=run, args=(r,)) for r in range(WORLD)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    assert not errors, errors
+    for r in range(WORLD):
+        # replicas stay identical across ranks, and equal the single-GPU emulation of the 2b batch
+        for a, b in zip(nccl[r]["g"] + nccl[r]["d"], nccl[0]["g"] + nccl[0]["d"]):
+            assert torch.equal(a, b)
+        for a, b in zip(nccl[r]["g"] + nccl[r]["d"], results[r]["g"] + results[r]["d"]):
+            assert rel_err(a, b) < 1e-4, rel_err(a, b)
+        assert rel_err(nccl[r]["pl_mean"], results[r]["pl_mean"]) < 1e-4
+        for la, lb in zip(nccl[r]["losses"], results[r]["losses"]):
+            assert set(la) == set(lb)
+            for k in la:
+                assert rel_err(la[k], lb[k]) < 1e-3, (k, la[k], lb[k])
+    assert "loss_path_length_regularization" in nccl[0]["losses"][-1]

@@ -285,7 +285,9 @@ def test_cuda_graph_replay_matches_eager(built_library, segmented):
         if graphed:
             assert mw.graph_launches > 0
             n_graphs = {k[2:4]: sum(isinstance(i, torch.cuda.CUDAGraph) for i in st.program) for k, st in mw._graphs.items()}
-            assert n_graphs == ({(False, False): 3, (True, True): 5} if segmented else {(False, False): 1, (True, True): 1})
+            # plain: D fwd/bwd | G fwd (overlaps the D all-reduce) | D update .. G bwd | G update + EMA; lazy: one break per
+            # optimiser step (the lazy regularisers need the updated networks, nothing to overlap)
+            assert n_graphs == ({(False, False): 4, (True, True): 5} if segmented else {(False, False): 1, (True, True): 1})
         runs.append((hist, [p.detach().clone() for p in list(G.parameters()) + list(D.parameters())],
                      mw.path_length_regularization.mean_path_length.clone()))
     (h0, p0, m0), (h1, p1, m1) = runs
@@ -392,3 +394,84 @@ def test_cuda_graph_replay_with_ada_matches_eager(built_library):
     assert graphed.graph_replays >= 4
     assert eager.discriminator.r_history == pytest.approx(graphed.discriminator.r_history)
     assert eager.discriminator.p == pytest.approx(graphed.discriminator.p) and len(graphed.discriminator.r_history) >= 6
+
+
+def run_late_epoch_parity(dev, tol):
+    """One iteration with wrong-order fakes, trap-weighted pixel-wise losses, both CutMix steps and top-k filtering
+    (model_wrapper.py:262-277,331-376,392-405) against the oracle trainer with the same draws injected."""
+    import unittest.mock as um
+    from multi_stylegan_b200 import loss, misc
+    from multi_stylegan_b200 import model_wrapper as MW
+    from multi_stylegan_b200.model_wrapper import ModelWrapper
+    hp = _hp()
+    hp["lazy_discriminator_regularization"] = 10 ** 6
+    hp["lazy_generator_regularization"] = 10 ** 6
+    G, D = build("cpu")
+    sd_g = {k: v.detach().clone() for k, v in G.state_dict().items()}
+    sd_d = {k: v.detach().clone() for k, v in D.state_dict().items()}
+    G, D = G.to(dev), D.to(dev)
+    gen = torch.Generator().manual_seed(5)
+    B = 4
+    noise = [torch.randn(B, 1, 4, 4, generator=gen)] + \
+            [torch.randn(B, 1, 2 ** (i // 2 + 3), 2 ** (i // 2 + 3), generator=gen) for i in range(6)]
+    trap = torch.rand(32, 32, generator=gen) + 0.5
+    perm = torch.tensor([2, 0, 2])                                  # with replacement, like misc.random_permutation
+    maps = []
+    for (ch, cw, low, invert) in ((9, 20, True, False), (21, 7, False, True)):
+        m = torch.zeros(1, 1, 1, 32, 32)
+        if low:
+            m[..., ch:, cw:] = 1.0
+        else:
+            m[..., :ch, :cw] = 1.0
+        maps.append(1.0 - m if invert else m)
+    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"])
+    opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"])
+    wrapped = FixedNoiseGenerator(G, [n.to(dev) for n in noise], 3)
+    mw = ModelWrapper(wrapped, D, opt_g, opt_d, hyperparameters=hp, generator_ema=__import__("copy").deepcopy(G), device=dev,
+                      trap_weights_map=trap.to(dev))
+    mw.epochs, mw.epoch = 10, 9                                     # wrong order on (>= 0.5 * epochs), trap on, CutMix p = 0.45
+    mw.top_k = loss.TopK(starting_iteration=0, final_iteration=1)   # v = 0.5
+    oracle = OracleTrainer(sd_g, sd_d, (2e-3, 2e-5), 6e-3, hp["betas"], hp)
+    real = torch.rand(B, 2, 3, 32, 32, generator=gen)
+    zs = [[torch.randn(B, 16, generator=gen), torch.randn(B, 16, generator=gen)] for _ in range(2)]
+    n_wrong = max(1, int(hp["batch_factor_wrong_order"] * B))
+    want = oracle.step(real, zs[0], zs[1], None, noise, noise, None, 3, None,
+                       late=dict(perm=perm, n_wrong=n_wrong, cut_mix=tuple(maps), top_k_v=0.5, trap=trap))
+    map_iter = iter([m.to(dev) for m in maps])
+    with um.patch.object(misc, "random_permutation", lambda n: perm), \
+            um.patch.object(MW.random, "random", lambda: 0.0), \
+            um.patch("multi_stylegan_b200.u_net_2d_discriminator._generate_binary_cut_mix_map",
+                     lambda height, width, device="cpu": next(map_iter)), \
+            um.patch.object(misc, "exponential_moving_average", lambda **kw: None):
+        # the wrong-order reals make the fake batch larger than the real one: the generator's noise maps must cover it
+        got = mw.train_step(real.to(dev), z_d=[z.to(dev) for z in zs[0]], z_g=[z.to(dev) for z in zs[1]])
+    assert set(got) == set(want), (sorted(got), sorted(want))
+    assert {"loss_cut_mix_augmentation", "loss_cut_mix_regularization"} <= set(got)
+    for k in want:
+        assert rel_err(got[k], want[k]) < tol, (k, float(got[k]), float(want[k]))
+    worst = 0.0
+    for n, p in D.named_parameters():
+        worst = max(worst, rel_err(p, oracle.sd_d[n]))
+    for n, p in G.named_parameters():
+        worst = max(worst, rel_err(p, oracle.sd_g[n]))
+    return worst
+
+
+def test_late_epoch_branches_match_oracle_host_logic(oracle_backend):
+    assert run_late_epoch_parity("cpu", 2e-4) < 2e-3
+
+
+@pytest.mark.gpu
+def test_late_epoch_branches_match_oracle_cuda_core_engine(built_library):
+    from multi_stylegan_b200 import _C, _lib
+    old = _C.conv_flags
+    _C.conv_flags = _lib.CONV_FORCE_SIMT
+    try:
+        assert run_late_epoch_parity("cuda:0", 1e-3) < 1e-2
+    finally:
+        _C.conv_flags = old
+
+
+@pytest.mark.gpu
+def test_late_epoch_branches_match_oracle_tensor_core_engine(built_library):
+    assert run_late_epoch_parity("cuda:0", 2e-2) < 0.2
