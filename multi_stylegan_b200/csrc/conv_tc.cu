@@ -310,6 +310,7 @@ struct TcPixParams {
   int vec_store;               // NHWC output, 16-byte aligned channel runs, N % 4 == 0
   int tma_store;               // epilogue writes 32-pixel x 32-channel boxes with TMA
   int debug;                   // MSG_B200_TC_VARIANT bits 32/64 (timing experiments only): 1 = no stores, 2 = no proxy fence (wrong results)
+  int kw;                      // row-tap kernel: taps per filter row (taps are stored row-major, dx consecutive)
   Epilogue ep;
 };
 
@@ -726,6 +727,193 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
       }  // sub
     }
     if (p.tma_store && lane == 0) tma_store_wait_read<0>();   // staging buffers must outlive their bulk stores
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// PixGemm with activation reuse across the taps of a filter row (3x3 / stride 1, image rows of >= 65 pixels, N <= 128).
+//
+// In the kernel above every (tap, 32-channel chunk) step loads its own 128-pixel activation box, so a 3x3 layer pulls
+// each activation 9 times from L2; for N <= 128 that load path (96 B/clk per SM against 512 cycles of MMA per 48 KB
+// stage) is what bounds the layer (tensor pipe 69 % active).  Here ONE box per (filter row,
+// chunk) covers the 128 + kw - 1 pixels all kw taps of that row read: the taps are the same shared-memory image entered
+// one pixel row (128 bytes) later.  That works because the 128-byte swizzle of both TMA and the UMMA descriptors is a
+// function of the shared-memory ADDRESS (bits 7..9 XOR-ed into bits 4..6): an operand may start at any 128-byte row of a
+// 1024-byte-aligned image with the descriptor's base-offset field left 0 (measured: tools/umma_rowshift_probe.cu, every
+// row offset 0..12 exact; base offset = row & 7 gives wrong data).  Activation bytes per MMA drop 3x, total fill traffic
+// for N = 128 from 96 to 53 B/clk.  Two rings: activation boxes (2 stages, one per filter row and chunk) and weight tiles
+// (one per tap and chunk).  Tiles are MT image-row segments of 128 pixels (the box has MT rows); everything else —
+// persistent tile loop, two TMEM accumulators, epilogue — is the kernel above.
+// ------------------------------------------------------------------------------------------------
+template <int BN, int MT, int KW>
+__global__ void __launch_bounds__(192, 1)
+tc_pixgemm_rows_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
+                       const __grid_constant__ CUtensorMap tmOut2, const TcPixParams p) {
+  constexpr int WROW = 128 + KW - 1;                        // pixels per box row
+  constexpr uint32_t A_BOX = (uint32_t)WROW * MT * 128;     // bytes the TMA delivers per activation box
+  constexpr uint32_t A_STAGE = (A_BOX + 1023u) & ~1023u;
+  constexpr uint32_t B_BYTES = BN * 32 * 4;
+  constexpr int SA = 2;
+  constexpr int SB = (BN >= 128) ? 6 : 8;
+  constexpr uint32_t ACC_COLS = MT * BN;
+  constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) < 32 ? 32 : 2 * ACC_COLS;
+  static_assert(2 * ACC_COLS <= 512, "TMEM columns");
+  constexpr uint32_t IDESC = make_idesc_tf32(128, BN, 0, 0);
+  constexpr uint32_t STG_BYTES = 4 * 2 * 4096;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + SA * A_STAGE;
+  const uint32_t sStg = sB + SB * B_BYTES;
+  const uint32_t barA = sStg + STG_BYTES;                 // SA full + SA empty
+  const uint32_t barB = barA + 16 * SA;                   // SB full + SB empty
+  const uint32_t acc_full = barB + 16 * SB;
+  const uint32_t acc_empty = acc_full + 16;
+  const uint32_t tmem_slot = acc_empty + 16;
+  const uint32_t add_bars = tmem_slot + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* stg_all = reinterpret_cast<float*>(smem_raw + (sStg - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int Wt = 128, Ht = MT;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(barA + 8 * s, 1); mbar_init(barA + 8 * (SA + s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(barB + 8 * s, 1); mbar_init(barB + 8 * (SB + s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(acc_full + 8 * a, 1); mbar_init(acc_empty + 8 * a, 4); }
+    for (int w = 0; w < 4; ++w) mbar_init(add_bars + 8 * w, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmAs.m[0]);
+    tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmOut);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int nrows = p.ntaps / KW;                         // filter rows
+
+  if (warp == 0) {
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int r = tile;
+      const int nt = r % p.n_tiles; r /= p.n_tiles;
+      const int tx = r % p.tiles_x; r /= p.tiles_x;
+      const int ty = r % p.tiles_y;
+      const int b = r / p.tiles_y;
+      const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN;
+      const int bw = p.w_per_sample ? b : 0;
+      for (int fr = 0; fr < nrows; ++fr) {
+        const int t0 = fr * KW;
+        // the box starts at the leftmost tap of the row (forward: the first one, dgrad: the last one)
+        const int dx_lo = p.tap_dx[t0] < p.tap_dx[t0 + KW - 1] ? p.tap_dx[t0] : p.tap_dx[t0 + KW - 1];
+        const int xx = x0 + dx_lo, yy = y0 + p.tap_dy[t0];
+        int view = 0, ca = 0;
+        for (int cc = 0; cc < p.cchunks; ++cc) {
+          mbar_wait(barA + 8 * (SA + sa), pha ^ 1u);
+          if (elect_one()) {
+            const uint32_t full = barA + 8 * sa;
+            mbar_expect_tx(full, A_BOX);
+            tma_load_4d(sA + sa * A_STAGE, &tmAs.m[view], full, ca * 32, xx, yy, b);
+          }
+          __syncwarp();
+          if (++sa == SA) { sa = 0; pha ^= 1u; }
+#pragma unroll
+          for (int j = 0; j < KW; ++j) {
+            mbar_wait(barB + 8 * (SB + sb), phb ^ 1u);
+            if (elect_one()) {
+              const uint32_t full = barB + 8 * sb;
+              mbar_expect_tx(full, B_BYTES);
+              tma_load_4d(sB + sb * B_BYTES, &tmB, full, cc * 32, n0, t0 + j, bw);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; phb ^= 1u; }
+          }
+          if (++ca == p.cpv[view]) { ca = 0; ++view; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(SWZ_128B & 7) << 61);
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0, lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t a = lt & 1u;
+      mbar_wait(acc_empty + 8 * a, ((lt >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + a * ACC_COLS;
+      for (int fr = 0; fr < nrows; ++fr) {
+        const int t0 = fr * KW;
+        const int dx_lo = p.tap_dx[t0] < p.tap_dx[t0 + KW - 1] ? p.tap_dx[t0] : p.tap_dx[t0 + KW - 1];
+        for (int cc = 0; cc < p.cchunks; ++cc) {
+          const bool first = fr == 0 && cc == 0, last = fr == nrows - 1 && cc == p.cchunks - 1;
+          mbar_wait(barA + 8 * sa, pha);
+          tc_fence_after();
+          const uint32_t a_lo = ((sA + sa * A_STAGE) >> 4) & 0x3FFF;
+#pragma unroll
+          for (int j = 0; j < KW; ++j) {
+            mbar_wait(barB + 8 * sb, phb);
+            tc_fence_after();
+            // tap j of this filter row = the same box entered (dx_j - dx_lo) pixel rows (128 bytes each) later
+            const uint32_t row_off = (uint32_t)(p.tap_dx[t0 + j] - dx_lo);
+            if (elect_one()) {
+              const uint32_t b_lo = ((sB + sb * B_BYTES) >> 4) & 0x3FFF;
+#pragma unroll
+              for (int sub = 0; sub < MT; ++sub) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t bd = DESC_HI | (uint64_t)(b_lo + kk * 2);
+                  const uint64_t ad = DESC_HI | (uint64_t)(a_lo + (sub * WROW + row_off) * (128 / 16) + kk * 2);
+                  mma_tf32(d_tmem + sub * BN, ad, bd, IDESC, (!first || j > 0 || kk > 0) ? 1u : 0u);
+                }
+              }
+              mma_commit(barB + 8 * (SB + sb));
+              if (j == KW - 1) {
+                mma_commit(barA + 8 * (SA + sa));
+                if (last) mma_commit(acc_full + 8 * a);
+              }
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; phb ^= 1u; }
+          }
+          if (++sa == SA) { sa = 0; pha ^= 1u; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float* stg = stg_all + q * (2 * 4096 / 4);
+    const uint32_t stage_smem = sStg + q * (2 * 4096);
+    uint32_t add_phase = 0;
+    const float nw = p.ep.noise ? __ldg(p.ep.noise_w) : 0.f;
+    uint32_t lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      int r = tile;
+      const int nt = r % p.n_tiles; r /= p.n_tiles;
+      const int tx = r % p.tiles_x; r /= p.tiles_x;
+      const int ty = r % p.tiles_y;
+      const int b = r / p.tiles_y;
+      const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN;
+      const uint32_t a = lt & 1u;
+      mbar_wait(acc_full + 8 * a, (lt >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + a * ACC_COLS + sub * BN;
+        pix_epilogue<BN, false>(p, stg, tlane, q, lane, b, y0, x0, n0, sub, nw, sub == MT - 1, acc_empty + 8 * a, &tmOut,
+                                stage_smem, &tmAdd, add_bars + 8 * q, &add_phase, &tmOut2);
+      }
+    }
+    if (p.tma_store && lane == 0) tma_store_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -1199,6 +1387,27 @@ static int launch_pix(const TMapSet& tmA, const CUtensorMap& tmB, const CUtensor
   return MSG_OK;
 }
 
+template <int BN, int MT>
+static int launch_pix_rows(const TMapSet& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAdd,
+                           const CUtensorMap& tmOut2, const TcPixParams& p, cudaStream_t st) {
+  constexpr int KW = 3;
+  constexpr size_t a_stage = (((size_t)(128 + KW - 1) * MT * 128) + 1023) & ~(size_t)1023;
+  constexpr int SB = (BN >= 128) ? 6 : 8;
+  constexpr size_t smem = 2 * a_stage + (size_t)SB * BN * 128 + 4 * 2 * 4096 + 16 * 2 + 16 * SB + 128 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  auto kfn = tc_pixgemm_rows_kernel<BN, MT, KW>;
+  static bool attr_done[64] = {};
+  const int slot = current_device_slot();
+  if (!attr_done[slot]) {
+    MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[slot] = true;
+  }
+  const int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  kfn<<<ctas, 192, smem, st>>>(tmA, tmB, tmOut, tmAdd, tmOut2, p);
+  MSG_CHECK_LAUNCH("conv pixgemm(tcgen05, row taps)");
+  return MSG_OK;
+}
+
 static int max_active_pairs(const void* kfn, size_t smem) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * (unsigned)num_sms());
@@ -1294,6 +1503,14 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
                      pair_tiles >= pair_min && g.nphase == 0 && g.nsrc == 0;
   const int MT = pairs ? 1 : pick_mt(g, BN);
   const int Wt = 1 << wt_log2, Ht = (128 * MT) >> wt_log2;
+  // Row-tap kernel (activation box shared by the 3 taps of a filter row): 3-tap filter rows stored row-major with
+  // consecutive dx, tiles that are whole 128-pixel image-row segments, N <= 128.  MSG_B200_TC_VARIANT bit 2048 disables it.
+  bool rows3 = !pairs && wt_log2 == 7 && (BN == 128 || BN == 64) && g.nphase == 0 && g.ntaps % 3 == 0 && g.ntaps >= 3 &&
+               !(tc_variant() & 2048u);
+  for (int t = 0; t < g.ntaps && rows3; ++t) {
+    const int t0 = t - t % 3, step = g.tap_dx[t0 + 1] - g.tap_dx[t0];       // +1 (forward) or -1 (dgrad) within a row
+    rows3 = (step == 1 || step == -1) && g.tap_dy[t] == g.tap_dy[t0] && g.tap_dx[t] == g.tap_dx[t0] + step * (t % 3);
+  }
   TMapSet tmA;
   CUtensorMap tmB;
   const int nviews = g.nphase > 0 ? g.nphase : (g.nsrc == 2 ? 2 : 1);
@@ -1305,7 +1522,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     const View4 vs = g.nsrc == 2 ? View4{(int64_t)ih * iw * cv, 1, (int64_t)iw * cv, cv} : g.is;
     const uint64_t dims[4] = {(uint64_t)cv, (uint64_t)iw, (uint64_t)ih, (uint64_t)g.B};
     const uint64_t strides[3] = {(uint64_t)vs.sx * 4, (uint64_t)vs.sy * 4, (uint64_t)vs.sb * 4};
-    const uint32_t box[4] = {32, (uint32_t)Wt, (uint32_t)Ht, 1};
+    const uint32_t box[4] = {32, (uint32_t)(rows3 ? Wt + 2 : Wt), (uint32_t)Ht, 1};
     if (v < nviews) {
       int rc = make_tmap(&tmA.m[v], basep, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
       if (rc) return rc;
@@ -1375,8 +1592,14 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   cudaEvent_t pstop;
   const int pslot = prof_begin(0, g.ntaps, g.Cr, g.N, (int64_t)g.B * g.PH * g.PW,
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);
+  p.kw = rows3 ? 3 : 0;
   int rc;
-  if (pairs) {
+  if (rows3) {
+    if (BN == 128) rc = MT == 2 ? launch_pix_rows<128, 2>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st)
+                                : launch_pix_rows<128, 1>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st);
+    else rc = MT == 2 ? launch_pix_rows<64, 2>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st)
+                      : launch_pix_rows<64, 1>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st);
+  } else if (pairs) {
     rc = BN == 256 ? launch_pix2<256>(tmA.m[0], tmB, tmOut, tmAdd, tmOut2, p, st) : launch_pix2<128>(tmA.m[0], tmB, tmOut, tmAdd, tmOut2, p, st);
   } else if (MT == 2) {
     switch (BN) {

@@ -326,3 +326,50 @@ def test_conv_two_source_autograd_on_device(built_library):
             assert a.shape == r.shape and rel_err(a, r) < 2e-2, rel_err(a, r)
         gg, rg = got[-1].double().cpu(), want[-1].double()
         assert ((gg - rg).norm() / rg.norm()).item() < 0.1
+
+
+@pytest.mark.parametrize("case", [
+    # (B, C, O, H, W, per_sample): image rows of > 64 pixels, N <= 128 -> the row-tap kernel (one activation box per filter
+    # row and chunk, the three taps entered at shifted rows of it)
+    (2, 64, 128, 70, 130, False),      # ragged right / bottom edges, two tiles per image row
+    (1, 128, 128, 129, 256, False),    # odd number of rows: the second row of the last 256-pixel tile is out of the image
+    (2, 32, 64, 96, 96, True),         # per-sample filters, N = 64
+    (8, 32, 128, 130, 200, False),     # enough tiles for two sub-tiles per CTA
+    (3, 96, 100, 67, 65, False),       # N with a tail inside the last 32-channel chunk
+])
+def test_conv_row_tap_kernel(built_library, case):
+    from multi_stylegan_b200 import _C, _lib
+    from tests import backend_oracle
+    if not _C.tensor_core_path_available():
+        pytest.skip("not an sm_100 device")
+    B, C, O, H, W, per = case
+    g = torch.Generator().manual_seed(H * W)
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn((B, O, C, 3, 3) if per else (O, C, 3, 3), generator=g) / (C * 9) ** 0.5
+    bias = torch.randn(O, generator=g)
+    add = torch.randn(B, O, H, W, generator=g)
+    noise = torch.randn(B, 1, H, W, generator=g)
+    nw = torch.tensor([0.3])
+    d = dev()
+    old = _C.conv_flags
+    _C.conv_flags = _lib.CONV_FORCE_TC
+    try:
+        for kw in (dict(), dict(bias=bias, act=True, gain=1.4, noise=noise, noise_w=nw), dict(add=add, gain=0.7)):
+            want = backend_oracle.conv2d_forward(x, w, 1, 1, alpha=0.9, **kw)
+            dk = {a: (v.to(d) if isinstance(v, torch.Tensor) else v) for a, v in kw.items()}
+            got = _C.conv2d_forward(x.to(d), w.to(d), 1, 1, alpha=0.9, **dk)
+            assert rel_err(got, want) < 1e-2, (list(kw), rel_err(got, want))
+        # dgrad: the same filter rows traversed right to left
+        dy = torch.randn(B, O, H, W, generator=g)
+        got = _C.conv2d_dgrad(dy.to(d), w.to(d), (H, W), 1, 1)
+        want = ops.conv2d_dgrad(dy, w, (H, W), 1, 1)
+        assert rel_err(got, want) < 1e-2, rel_err(got, want)
+        if not per and C % 32 == 0:
+            # two-source K loop (decoder concatenation) through the same kernel
+            x2 = torch.randn(B, 32, H, W, generator=g)
+            w2 = torch.randn(O, C + 32, 3, 3, generator=g) / ((C + 32) * 9) ** 0.5
+            got = _C.conv2d_forward(x.to(d), w2.to(d), 1, 1, x2=x2.to(d))
+            want = ops.conv2d(torch.cat([x, x2], 1), w2, 1, 1)
+            assert rel_err(got, want) < 1e-2, rel_err(got, want)
+    finally:
+        _C.conv_flags = old

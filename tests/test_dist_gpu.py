@@ -40,8 +40,9 @@ def _train(rank, dev, process_group=None):
     noise, steps = _inputs(rank)
     opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"])
     opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"])
-    mw = ModelWrapper(FixedNoiseGenerator(G, [n.to(dev) for n in noise], 3), D, opt_g, opt_d, hyperparameters=hp,
-                      generator_ema=__import__("copy").deepcopy(G), device=dev, process_group=process_group)
+    wrapped = FixedNoiseGenerator(G, [n.to(dev) for n in noise], 3)
+    mw = ModelWrapper(wrapped, D, opt_g, opt_d, hyperparameters=hp, generator_ema=__import__("copy").deepcopy(wrapped),
+                      device=dev, process_group=process_group)
     losses = []
     for s in steps:
         out = mw.train_step(s["real"].to(dev), z_d=[z.to(dev) for z in s["z_d"]], z_g=[z.to(dev) for z in s["z_g"]],
@@ -104,8 +105,15 @@ def test_two_ranks_over_nccl_equal_one_gpu_with_per_group_statistics(built_libra
         except BaseException as exc:            # a dead participant must not leave the other one in the barrier
             errors.append(exc)
             ls.barrier.abort()
+    class _Pending:
+        def __init__(self, tensors):
+            self.tensors = tensors
+
+        def wait(self):
+            return ls.all_reduce_tensors(self.tensors)
     with um.patch.object(mdist, "world_size", lambda group=None: WORLD), \
-            um.patch.object(mdist, "all_reduce_tensors", ls.all_reduce_tensors):
+            um.patch.object(mdist, "all_reduce_tensors", ls.all_reduce_tensors), \
+            um.patch.object(mdist, "all_reduce_tensors_begin", lambda tensors, group=None: _Pending(tensors) if tensors else None):
         threads = [threading.Thread(target=run, args=(r,)) for r in range(WORLD)]
         for t in threads:
             t.start()

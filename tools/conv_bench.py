@@ -56,10 +56,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default=None, help="substring filter on the conv case names")
+    ap.add_argument("--no-bw", action="store_true", help="skip the bandwidth-bound kernels")
     args = ap.parse_args()
     rows = []
     # (name, B, C, O, R, k, per_sample, stride, pad)
     cases = [
+        ("G conv 3x3 512->512 @256 shared W", 8, 512, 512, 256, 3, False, 1, None),
+        ("G conv 3x3 512->512 @128 shared W", 8, 512, 512, 128, 3, False, 1, None),
+        ("D conv 3x3 128->128 @256 B=16", 16, 128, 128, 256, 3, False, 1, None),
         ("G modconv 3x3 512->512 @256", 8, 512, 512, 256, 3, True, 1, None),
         ("G modconv 3x3 512->512 @128", 8, 512, 512, 128, 3, True, 1, None),
         ("G modconv 3x3 512->512 @64", 8, 512, 512, 64, 3, True, 1, None),
@@ -71,7 +76,9 @@ def main():
         ("D conv 3x3 s2 128->128 @256", 8, 128, 128, 256, 3, False, 2, 0),
     ]
     if args.quick:
-        cases = cases[:1] + cases[3:4]
+        cases = [c for c in cases if c[0].startswith("D conv 3x3") and c[7] == 1] + cases[:1]
+    if args.only:
+        cases = [c for c in cases if args.only in c[0]]
     print("%-32s %9s %9s %9s   TFLOP/s fwd / dgrad / wgrad" % ("conv (tcgen05, TF32)", "fwd ms", "dgrad ms", "wgrad ms"))
     for name, B, C, O, R, k, per, s, p in cases:
         flops, t = conv_case(B, C, O, R, k, per, s, p)
@@ -84,7 +91,7 @@ def main():
     print("\n%-44s %9s %9s" % ("bandwidth-bound kernel (channels-last fp32)", "ms", "GB/s"))
     k4 = torch.tensor([1., 3., 3., 1.], device=DEV)
     k2d = (k4[None] * k4[:, None]) / 64
-    for R in ([128] if args.quick else [64, 128, 256]):
+    for R in ([] if args.no_bw else [128] if args.quick else [64, 128, 256]):
         n_pool = 3
         xs = [cl(torch.randn(8, 512, R, R, device=DEV)) for _ in range(n_pool)]
         x4 = [x.permute(0, 2, 3, 1) for x in xs]
