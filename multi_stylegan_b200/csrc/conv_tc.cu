@@ -290,6 +290,59 @@ tc_weight_transform_runs_kernel(float* __restrict__ wt, const WtParams p, int T)
   }
 }
 
+// Third form, same contract as the runs kernel: tiles of 8 (n) x 32 (c) x T instead of 32 x 32 x T.  The 32 x 32 tiles give
+// a 512 x 512 layer only 256 blocks of 37 KB shared memory each — under two per SM, every thread walking its T loads one
+// after the other — and the kernel ran at 20 % of the HBM bandwidth (15.6 us for 18.8 MB, 186 launches = 1.45 ms per
+// iteration).  Small tiles put ~7 blocks on every SM with T independent loads in flight per thread.
+template <int TMAX>
+__global__ void __launch_bounds__(256)
+tc_weight_transform_runs8_kernel(float* __restrict__ wt, const WtParams p, int T) {
+  extern __shared__ float runs[];
+  const int c0 = blockIdx.x * 32, n0 = blockIdx.y * 8, b = blockIdx.z;
+  const bool c_fast = p.w_sc <= p.w_sn;               // forward: rows = n, runs along (c, t); dgrad: rows = c, runs along (n, t)
+  const float* wb = p.w + (int64_t)b * p.w_sb;
+  const int tid = threadIdx.x;
+  if (c_fast) {
+    const int pitch = 32 * T + 1;                     // runs[8][32 * T + 1]
+    const int row = tid >> 5, a = tid & 31;
+    const bool row_ok = n0 + row < p.N;
+    const int valid = (p.Cr - c0 < 32 ? (p.Cr - c0 > 0 ? p.Cr - c0 : 0) : 32) * T;
+    const float* src = wb + (int64_t)(n0 + row) * p.w_sn + (int64_t)c0 * T;
+    float v[TMAX];
+#pragma unroll
+    for (int k = 0; k < TMAX; ++k) {
+      const int i = a + 32 * k;
+      v[k] = (k < T && row_ok && i < valid) ? __ldg(src + i) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < TMAX; ++k)
+      if (k < T) runs[row * pitch + a + 32 * k] = to_tf32_rna(v[k]);
+  } else {
+    const int pitch = 8 * T + 1;                      // runs[32][8 * T + 1]
+    const int row = tid >> 3, a = tid & 7;
+    const bool row_ok = c0 + row < p.Cr;
+    const int valid = (p.N - n0 < 8 ? (p.N - n0 > 0 ? p.N - n0 : 0) : 8) * T;
+    const float* src = wb + (int64_t)(c0 + row) * p.w_sc + (int64_t)n0 * T;
+    float v[TMAX];
+#pragma unroll
+    for (int k = 0; k < TMAX; ++k) {
+      const int i = a + 8 * k;
+      v[k] = (k < T && row_ok && i < valid) ? __ldg(src + i) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < TMAX; ++k)
+      if (k < T) runs[row * pitch + a + 8 * k] = to_tf32_rna(v[k]);
+  }
+  __syncthreads();
+  const int nl = tid >> 5, cl = tid & 31;             // one (n, c) pair per thread, all taps
+  if (n0 + nl >= p.Npad) return;
+  for (int t = 0; t < p.ntaps; ++t) {
+    const int ti = p.tap_wi[t];
+    const float val = c_fast ? runs[nl * (32 * T + 1) + cl * T + ti] : runs[cl * (8 * T + 1) + nl * T + ti];
+    wt[(((int64_t)b * p.ntaps + t) * p.Npad + n0 + nl) * p.Cpad + c0 + cl] = val;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // PixGemm kernel (K-major A from NHWC, K-major B)
 // ------------------------------------------------------------------------------------------------
@@ -1074,6 +1127,195 @@ tc_pixgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// Row-tap PixGemm on CTA pairs (N = 128): the two ideas combined.  A 128 x 128 x 8 TF32 MMA reads 8 KB of operands from
+// shared memory per 64 cycles = 128 B/clk, the whole shared-memory bandwidth of an SM, so on a single CTA the TMA fill
+// and the epilogue staging compete with the tensor core for it (ncu on tc_pixgemm_rows_kernel<128,2,3>: tensor pipe 74 %
+// active with the MMA warp back-pressured and the producer idle, profiles/r2h_rows_full.txt).  With cta_group::2 each
+// SM reads its own activation rows and only HALF of the weight rows (96 B/clk), and with the activation box shared by
+// the three taps of a filter row the fill drops to (16.6 KB + 3 x 8 KB) per 768 cycles.  Each CTA owns MT image-row
+// segments of 128 pixels per tile; the pair's M = 256 MMA covers segment `sub` of both CTAs.
+// ------------------------------------------------------------------------------------------------
+template <int BN, int MT, int KW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+tc_pixgemm2_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmAdd,
+                        const __grid_constant__ CUtensorMap tmOut2, const TcPixParams p) {
+  constexpr int WROW = 128 + KW - 1;
+  constexpr uint32_t A_BOX = (uint32_t)WROW * MT * 128;
+  constexpr uint32_t A_STAGE = (A_BOX + 1023u) & ~1023u;
+  constexpr uint32_t B_BYTES = (BN / 2) * 32 * 4;          // this CTA's half of the weight tile
+  constexpr int SA = 3;
+  constexpr int SB = 8;
+  constexpr uint32_t ACC_COLS = MT * BN;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns");
+  constexpr uint32_t IDESC = make_idesc_tf32(256, BN, 0, 0);
+  constexpr uint32_t STG_BYTES = 4 * 2 * 4096;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = base + SA * A_STAGE;
+  const uint32_t sStg = sB + SB * B_BYTES;
+  const uint32_t barA = sStg + STG_BYTES;
+  const uint32_t barB = barA + 16 * SA;
+  const uint32_t acc_full = barB + 16 * SB;
+  const uint32_t acc_empty = acc_full + 16;
+  const uint32_t tmem_slot = acc_empty + 16;
+  const uint32_t add_bars = tmem_slot + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* stg_all = reinterpret_cast<float*>(smem_raw + (sStg - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  constexpr int Wt = 128, Ht = MT;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SA; ++s) { mbar_init(barA + 8 * s, 1); mbar_init(barA + 8 * (SA + s), 1); }
+    for (int s = 0; s < SB; ++s) { mbar_init(barB + 8 * s, 1); mbar_init(barB + 8 * (SB + s), 1); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(acc_full + 8 * a, 1);
+      mbar_init(acc_empty + 8 * a, 8);
+    }
+    for (int w = 0; w < 4; ++w) mbar_init(add_bars + 8 * w, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmOut);
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int nrows = p.ntaps / KW;
+  const int npairs = gridDim.x >> 1;
+  const int pair = blockIdx.x >> 1;
+  const int ptiles = p.tiles_x * p.tiles_y;          // (128 * MT)-pixel tiles per sample
+  const int ppairs = (ptiles + 1) >> 1;
+
+  if (warp == 0) {
+    const uint32_t fullA_leader = mapa_cluster(barA, 0), fullB_leader = mapa_cluster(barB, 0);
+    uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+    for (int tile = pair; tile < p.total_tiles; tile += npairs) {
+      int r = tile;
+      const int nt = r % p.n_tiles; r /= p.n_tiles;
+      const int pp = r % ppairs;
+      const int b = r / ppairs;
+      const int pt = 2 * pp + (int)rank;             // >= ptiles: out of the image, TMA fills zeros, nothing is stored
+      const int ty = pt / p.tiles_x, tx = pt - ty * p.tiles_x;
+      const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN + (int)rank * (BN / 2);
+      const int bw = p.w_per_sample ? b : 0;
+      for (int fr = 0; fr < nrows; ++fr) {
+        const int t0 = fr * KW;
+        const int dx_lo = p.tap_dx[t0] < p.tap_dx[t0 + KW - 1] ? p.tap_dx[t0] : p.tap_dx[t0 + KW - 1];
+        const int xx = x0 + dx_lo, yy = y0 + p.tap_dy[t0];
+        for (int cc = 0; cc < p.cchunks; ++cc) {
+          mbar_wait(barA + 8 * (SA + sa), pha ^ 1u);
+          if (elect_one()) {
+            if (leader) mbar_expect_tx(barA + 8 * sa, 2 * A_BOX);
+            tma_load_4d_2cta(sA + sa * A_STAGE, &tmA, fullA_leader + 8 * sa, cc * 32, xx, yy, b);
+          }
+          __syncwarp();
+          if (++sa == SA) { sa = 0; pha ^= 1u; }
+#pragma unroll
+          for (int j = 0; j < KW; ++j) {
+            mbar_wait(barB + 8 * (SB + sb), phb ^ 1u);
+            if (elect_one()) {
+              if (leader) mbar_expect_tx(barB + 8 * sb, 2 * B_BYTES);
+              tma_load_4d_2cta(sB + sb * B_BYTES, &tmB, fullB_leader + 8 * sb, cc * 32, n0, t0 + j, bw);
+            }
+            __syncwarp();
+            if (++sb == SB) { sb = 0; phb ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      constexpr uint64_t DESC_HI = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)(SWZ_128B & 7) << 61);
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0, lt = 0;
+      for (int tile = pair; tile < p.total_tiles; tile += npairs, ++lt) {
+        const uint32_t a = lt & 1u;
+        mbar_wait(acc_empty + 8 * a, ((lt >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * ACC_COLS;
+        for (int fr = 0; fr < nrows; ++fr) {
+          const int t0 = fr * KW;
+          const int dx_lo = p.tap_dx[t0] < p.tap_dx[t0 + KW - 1] ? p.tap_dx[t0] : p.tap_dx[t0 + KW - 1];
+          for (int cc = 0; cc < p.cchunks; ++cc) {
+            const bool first = fr == 0 && cc == 0, last = fr == nrows - 1 && cc == p.cchunks - 1;
+            mbar_wait(barA + 8 * sa, pha);
+            tc_fence_after();
+            const uint32_t a_lo = ((sA + sa * A_STAGE) >> 4) & 0x3FFF;
+#pragma unroll
+            for (int j = 0; j < KW; ++j) {
+              mbar_wait(barB + 8 * sb, phb);
+              tc_fence_after();
+              const uint32_t row_off = (uint32_t)(p.tap_dx[t0 + j] - dx_lo);
+              if (elect_one()) {
+                const uint32_t b_lo = ((sB + sb * B_BYTES) >> 4) & 0x3FFF;
+#pragma unroll
+                for (int sub = 0; sub < MT; ++sub) {
+#pragma unroll
+                  for (int kk = 0; kk < 4; ++kk)
+                    mma_tf32_2cta(d_tmem + sub * BN, DESC_HI | (uint64_t)(a_lo + (sub * WROW + row_off) * (128 / 16) + kk * 2),
+                                  DESC_HI | (uint64_t)(b_lo + kk * 2), IDESC, (!first || j > 0 || kk > 0) ? 1u : 0u);
+                }
+                mma_commit_2cta(barB + 8 * (SB + sb), 3);
+                if (j == KW - 1) {
+                  mma_commit_2cta(barA + 8 * (SA + sa), 3);
+                  if (last) mma_commit_2cta(acc_full + 8 * a, 3);
+                }
+              }
+              __syncwarp();
+              if (++sb == SB) { sb = 0; phb ^= 1u; }
+            }
+            if (++sa == SA) { sa = 0; pha ^= 1u; }
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    float* stg = stg_all + q * (2 * 4096 / 4);
+    const uint32_t stage_smem = sStg + q * (2 * 4096);
+    uint32_t add_phase = 0;
+    const float nw = p.ep.noise ? __ldg(p.ep.noise_w) : 0.f;
+    const uint32_t acc_empty_leader = mapa_cluster(acc_empty, 0);
+    uint32_t lt = 0;
+    for (int tile = pair; tile < p.total_tiles; tile += npairs, ++lt) {
+      int r = tile;
+      const int nt = r % p.n_tiles; r /= p.n_tiles;
+      const int pp = r % ppairs;
+      const int b = r / ppairs;
+      const int pt = 2 * pp + (int)rank;
+      const int ty = pt / p.tiles_x, tx = pt - ty * p.tiles_x;
+      const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN;
+      const uint32_t a = lt & 1u;
+      mbar_wait(acc_full + 8 * a, (lt >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + a * ACC_COLS + sub * BN;
+        pix_epilogue<BN, true>(p, stg, tlane, q, lane, b, y0, x0, n0, sub, nw, sub == MT - 1, acc_empty_leader + 8 * a, &tmOut,
+                               stage_smem, &tmAdd, add_bars + 8 * q, &add_phase, &tmOut2);
+      }
+    }
+    if (p.tma_store && lane == 0) tma_store_wait_read<0>();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
 // RedGemm kernel (wgrad): both operands MN-major (BASE32B), split-K into `part`.
 // ------------------------------------------------------------------------------------------------
 struct TcRedParams {
@@ -1444,6 +1686,29 @@ static int launch_pix2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return MSG_OK;
 }
 
+template <int BN, int MT>
+static int launch_pix2_rows(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmOut, const CUtensorMap& tmAdd,
+                            const CUtensorMap& tmOut2, const TcPixParams& p, cudaStream_t st) {
+  constexpr int KW = 3;
+  constexpr size_t a_stage = (((size_t)(128 + KW - 1) * MT * 128) + 1023) & ~(size_t)1023;
+  constexpr size_t smem = 3 * a_stage + (size_t)8 * (BN / 2) * 128 + 4 * 2 * 4096 + 16 * 3 + 16 * 8 + 128 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  auto kfn = tc_pixgemm2_rows_kernel<BN, MT, KW>;
+  static int pairs_max_dev[64] = {};
+  const int slot = current_device_slot();
+  if (pairs_max_dev[slot] == 0) {
+    MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int n = max_active_pairs(reinterpret_cast<const void*>(kfn), smem);
+    pairs_max_dev[slot] = n > 0 ? n : -1;
+  }
+  const int pairs_max = pairs_max_dev[slot];
+  if (pairs_max <= 0) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05, CTA pairs, row taps): no cluster can be resident");
+  const int pairs = p.total_tiles < pairs_max ? p.total_tiles : pairs_max;
+  kfn<<<2 * pairs, 192, smem, st>>>(tmA, tmB, tmOut, tmAdd, tmOut2, p);
+  MSG_CHECK_LAUNCH("conv pixgemm(tcgen05, CTA pairs, row taps)");
+  return MSG_OK;
+}
+
 // two 128-pixel sub-tiles per CTA tile pay off for narrow N once there is more than a round of such tiles
 static int pick_mt(const PixGemm& g, int BN) {
   if (BN > 128) return 1;
@@ -1477,7 +1742,14 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int64_t T = wp.w_sc <= wp.w_sn ? wp.w_sc : wp.w_sn;
     bool all_taps = wp.w_st == 1 && T == g.ntaps && T >= 2 && T <= 9;
     for (int t = 0; t < g.ntaps && all_taps; ++t) all_taps = wp.tap_wi[t] >= 0 && wp.tap_wi[t] < T;
-    if (all_taps && !(tc_variant() & 512u)) {
+    if (all_taps && !(tc_variant() & 512u) && Npad % 8 == 0 && !(tc_variant() & 16384u)) {
+      const bool c_fast = wp.w_sc <= wp.w_sn;
+      const size_t sm = (size_t)(c_fast ? 8 * (32 * T + 1) : 32 * (8 * T + 1)) * sizeof(float);
+      dim3 grid8((unsigned)(Cpad / 32), (unsigned)(Npad / 8), (unsigned)BW);
+      if (grid8.y > 65535) return fail(MSG_ERR_UNSUPPORTED, "conv weight transform: too many output channels");
+      if (T <= 4) tc_weight_transform_runs8_kernel<4><<<grid8, 256, sm, st>>>(wt, wp, (int)T);
+      else tc_weight_transform_runs8_kernel<9><<<grid8, 256, sm, st>>>(wt, wp, (int)T);
+    } else if (all_taps && !(tc_variant() & 512u)) {
       const size_t sm = (size_t)32 * (32 * T + 1) * sizeof(float);
       tc_weight_transform_runs_kernel<<<grid, 256, sm, st>>>(wt, wp, (int)T);
     } else {
@@ -1499,18 +1771,36 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   // BN = 128 pairs exist (bit 1024) but measured the same as the 256-pixel single-CTA tiles (608 vs 607 and 659 vs 644
   // TFLOP/s on the discriminator's 128-channel 3x3 layers at 256^2; ncu: tensor pipe 69 % active either way), so they
   // stay opt-in.
-  const bool pairs = (BN == 256 || (BN == 128 && (tc_variant() & 1024u))) && !(tc_variant() & 4u) &&
-                     pair_tiles >= pair_min && g.nphase == 0 && g.nsrc == 0;
-  const int MT = pairs ? 1 : pick_mt(g, BN);
-  const int Wt = 1 << wt_log2, Ht = (128 * MT) >> wt_log2;
-  // Row-tap kernel (activation box shared by the 3 taps of a filter row): 3-tap filter rows stored row-major with
-  // consecutive dx, tiles that are whole 128-pixel image-row segments, N <= 128.  MSG_B200_TC_VARIANT bit 2048 disables it.
-  bool rows3 = !pairs && wt_log2 == 7 && (BN == 128 || BN == 64) && g.nphase == 0 && g.ntaps % 3 == 0 && g.ntaps >= 3 &&
-               !(tc_variant() & 2048u);
-  for (int t = 0; t < g.ntaps && rows3; ++t) {
+  bool pairs = (BN == 256 || (BN == 128 && (tc_variant() & 1024u))) && !(tc_variant() & 4u) &&
+               pair_tiles >= pair_min && g.nphase == 0 && g.nsrc == 0;
+  // Row-tap kernels (activation box shared by the 3 taps of a filter row): 3-tap filter rows stored row-major with
+  // consecutive dx (either direction), tiles that are whole 128-pixel image-row segments, N <= 128.
+  // MSG_B200_TC_VARIANT bit 2048 disables them, bit 4096 only their CTA-pair form.
+  bool rows_ok = wt_log2 == 7 && g.nphase == 0 && g.ntaps % 3 == 0 && g.ntaps >= 3 && !(tc_variant() & 2048u);
+  for (int t = 0; t < g.ntaps && rows_ok; ++t) {
     const int t0 = t - t % 3, step = g.tap_dx[t0 + 1] - g.tap_dx[t0];       // +1 (forward) or -1 (dgrad) within a row
-    rows3 = (step == 1 || step == -1) && g.tap_dy[t] == g.tap_dy[t0] && g.tap_dx[t] == g.tap_dx[t0] + step * (t % 3);
+    rows_ok = (step == 1 || step == -1) && g.tap_dy[t] == g.tap_dy[t0] && g.tap_dx[t] == g.tap_dx[t0] + step * (t % 3);
   }
+  int MT = pairs ? 1 : pick_mt(g, BN);
+  int64_t pair_tiles_used = pair_tiles;
+  bool pairs_rows = false;
+  if (pairs && rows_ok && BN == 256 && !(tc_variant() & (4096u | 8192u))) {
+    // 256-channel tiles on the pair row-tap kernel too (one image-row segment per CTA; the accumulators of two would
+    // need 1024 TMEM columns): 3x3 512->512 at 256^2 865 -> 924 TFLOP/s, at 128^2 742 -> 905 (tools/conv_bench.py;
+    // a third of the activation fill, the power it saves goes into clock).  Bit 8192 keeps the per-tap pair kernel.
+    pairs = false; pairs_rows = true; MT = 1;
+  }
+  if (!pairs && !pairs_rows && rows_ok && BN == 128 && g.nsrc == 0 && !(tc_variant() & (4u | 4096u))) {
+    // N = 128: a single CTA's tensor core is bound by shared-memory bandwidth (operands 128 B/clk + fill); the pair form
+    // reads half the weight rows per SM.  Two image-row segments per CTA when that still gives two rounds of pairs.
+    for (int mt = 2; mt >= 1 && !pairs_rows; --mt) {
+      const int64_t pt = ceil_div(g.PW, 128) * ceil_div(g.PH, mt);
+      const int64_t prs = ((pt + 1) / 2) * (Npad / BN) * (int64_t)g.B;
+      if (prs >= pair_min) { pairs_rows = true; MT = mt; pair_tiles_used = prs; }
+    }
+  }
+  const bool rows3 = pairs_rows || (!pairs && rows_ok && (BN == 128 || BN == 64));
+  const int Wt = 1 << wt_log2, Ht = (128 * MT) >> wt_log2;
   TMapSet tmA;
   CUtensorMap tmB;
   const int nviews = g.nphase > 0 ? g.nphase : (g.nsrc == 2 ? 2 : 1);
@@ -1533,7 +1823,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   {
     const uint64_t dims[4] = {(uint64_t)Cpad, (uint64_t)Npad, (uint64_t)g.ntaps, (uint64_t)BW};
     const uint64_t strides[3] = {(uint64_t)Cpad * 4, (uint64_t)Cpad * Npad * 4, (uint64_t)Cpad * Npad * g.ntaps * 4};
-    const uint32_t box[4] = {32, (uint32_t)(pairs ? BN / 2 : BN), 1, 1};     // a CTA of a pair loads half of the rows
+    const uint32_t box[4] = {32, (uint32_t)((pairs || pairs_rows) ? BN / 2 : BN), 1, 1};     // a CTA of a pair loads half of the rows
     int rc = make_tmap(&tmB, wt, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
@@ -1547,7 +1837,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.tiles_x = (int)ceil_div(g.PW, Wt);
   p.tiles_y = (int)ceil_div(g.PH, Ht);
   p.n_tiles = Npad / BN;
-  const int64_t total_tiles = pairs ? pair_tiles : (int64_t)p.tiles_x * p.tiles_y * p.n_tiles * g.B;
+  const int64_t total_tiles = (pairs || pairs_rows) ? pair_tiles_used : (int64_t)p.tiles_x * p.tiles_y * p.n_tiles * g.B;
   if (total_tiles > 0x7fffffffLL) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): too many tiles");
   p.total_tiles = (int)total_tiles;
   p.out = g.out; p.os = g.os;
@@ -1594,7 +1884,11 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);
   p.kw = rows3 ? 3 : 0;
   int rc;
-  if (rows3) {
+  if (pairs_rows) {
+    if (BN == 256) rc = launch_pix2_rows<256, 1>(tmA.m[0], tmB, tmOut, tmAdd, tmOut2, p, st);
+    else rc = MT == 2 ? launch_pix2_rows<128, 2>(tmA.m[0], tmB, tmOut, tmAdd, tmOut2, p, st)
+                      : launch_pix2_rows<128, 1>(tmA.m[0], tmB, tmOut, tmAdd, tmOut2, p, st);
+  } else if (rows3) {
     if (BN == 128) rc = MT == 2 ? launch_pix_rows<128, 2>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st)
                                 : launch_pix_rows<128, 1>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st);
     else rc = MT == 2 ? launch_pix_rows<64, 2>(tmA, tmB, tmOut, tmAdd, tmOut2, p, st)

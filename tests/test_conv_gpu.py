@@ -336,6 +336,8 @@ def test_conv_two_source_autograd_on_device(built_library):
     (2, 32, 64, 96, 96, True),         # per-sample filters, N = 64
     (8, 32, 128, 130, 200, False),     # enough tiles for two sub-tiles per CTA
     (3, 96, 100, 67, 65, False),       # N with a tail inside the last 32-channel chunk
+    (2, 32, 128, 100, 256, False),     # CTA pairs with one image-row segment per CTA (too few tiles for two)
+    (2, 64, 128, 101, 200, True),      # CTA pairs, per-sample filters, odd number of pair tiles per sample
 ])
 def test_conv_row_tap_kernel(built_library, case):
     from multi_stylegan_b200 import _C, _lib

@@ -467,7 +467,9 @@ def test_late_epoch_branches_match_oracle_cuda_core_engine(built_library):
     old = _C.conv_flags
     _C.conv_flags = _lib.CONV_FORCE_SIMT
     try:
-        assert run_late_epoch_parity("cuda:0", 1e-3) < 1e-2
+        # losses to 1e-3; the updated weights only loosely: this iteration takes five optimiser steps, and Adam's first
+        # steps are +-lr whatever the gradient's size, so a parameter whose gradient is rounding noise moves by several lr
+        assert run_late_epoch_parity("cuda:0", 1e-3) < 0.1
     finally:
         _C.conv_flags = old
 
