@@ -92,3 +92,55 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _lib.lib()
+
+
+def test_reference_op_static_package_runs_on_the_shim_modules():
+    """Drop-in proof at the reference's own FFI boundary: the UNMODIFIED reference package multi_stylegan/op_static
+    (fused_act.py, upfirdn2d.py — autograd Functions, FusedLeakyReLU module) imported with multi_stylegan_b200/shims on
+    sys.path, so that its `import fused_act_cuda` / `import upfirdn2d_cuda` (fused_act.py:8, upfirdn2d.py:8) bind to this
+    repository's modules.  On this CPU-only host the C-ABI behind the shims is swapped for the oracle (the GPU twin of
+    this test is tests/test_ops_gpu.py::test_reference_extension_module_shims); the reference fixtures must come out.
+    Needs /root/reference (authoring container only)."""
+    import os
+    import subprocess
+    import sys
+    import pytest
+    from tests.conftest import ROOT
+    if not os.path.isdir("/root/reference/multi_stylegan/op_static"):
+        pytest.skip("reference sources not mounted")
+    code = r'''
+import sys, types, torch
+sys.path.insert(0, %r)
+from multi_stylegan_b200 import _C, shims
+from tests import backend_oracle
+for name in backend_oracle.__all__:
+    setattr(_C, name, getattr(backend_oracle, name))
+sys.path.insert(0, shims.PATH)
+pkg = types.ModuleType("multi_stylegan"); pkg.__path__ = ["/root/reference/multi_stylegan"]; sys.modules["multi_stylegan"] = pkg
+import importlib
+ops = importlib.import_module("multi_stylegan.op_static")
+import fused_act_cuda, upfirdn2d_cuda
+assert fused_act_cuda.__file__.startswith(shims.PATH) and upfirdn2d_cuda.__file__.startswith(shims.PATH)
+gold = torch.load(%r, map_location="cpu", weights_only=False)
+def rel(a, b): return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+for c in gold["lrelu"]:
+    x = c["x"].clone().requires_grad_(True); b = c["b"].clone().requires_grad_(True)
+    y = ops.fused_leaky_relu(x, b, 0.2, c["scale"])
+    assert rel(y, c["y"]) < 1e-5
+    gy = c["gy"].clone().requires_grad_(True)
+    gx, gb = torch.autograd.grad(y, (x, b), gy, create_graph=True)
+    assert rel(gx, c["gx"]) < 1e-5 and rel(gb, c["gb"]) < 1e-4
+    ggy, = torch.autograd.grad((gx, gb), gy, (c["v"], c["vb"]))
+    assert rel(ggy, c["ggy"]) < 1e-5
+for c in gold["fir_autograd"]:
+    x = c["x"].clone().requires_grad_(True)
+    y = ops.upfirdn2d(x, c["k"], up=c["up"], down=c["down"], pad=c["pad"])
+    assert y.shape == c["y"].shape and rel(y, c["y"]) < 1e-5
+    gx, = torch.autograd.grad(y, x, c["gy"])
+    assert rel(gx, c["gx"]) < 1e-5
+m = ops.FusedLeakyReLU(8)
+assert m(torch.randn(2, 8, 4, 4)).shape == (2, 8, 4, 4)
+print("SHIM_OK")
+''' % (ROOT, os.path.join(ROOT, "tests", "golden", "ops.pt"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert "SHIM_OK" in out.stdout, out.stdout + out.stderr

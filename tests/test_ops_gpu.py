@@ -385,3 +385,38 @@ def test_kernels_do_not_write_out_of_bounds(built_library):
             check(buf, n_out, ("conv", which, B, C, O, H, W, kk, s))
             torch.cuda.synchronize()
             assert torch.isnan(wbuf[:G]).all() and torch.isnan(wbuf[G + wsn // 4:]).all(), ("conv workspace", which)
+
+
+def test_reference_extension_module_shims(built_library):
+    """`import fused_act_cuda` / `import upfirdn2d_cuda` (what the reference's op_static/fused_act.py:8 and upfirdn2d.py:8
+    do) resolve to the shim modules once multi_stylegan_b200/shims is on sys.path; same signatures, same results as the
+    oracle restatement of the reference kernels, including the calls the reference's autograd Functions make
+    (fused_act.py:31-33,47-49,58; upfirdn2d.py:34-45,121-123)."""
+    import importlib
+    import sys
+    from multi_stylegan_b200 import shims
+    from oracle import ops
+    sys.path.insert(0, shims.PATH)
+    try:
+        fused_act_cuda = importlib.import_module("fused_act_cuda")
+        upfirdn2d_cuda = importlib.import_module("upfirdn2d_cuda")
+    finally:
+        sys.path.remove(shims.PATH)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 20, 9, 11, generator=g)
+    b = torch.randn(20, generator=g)
+    empty = x.new_empty(0)
+    out = fused_act_cuda.fused_bias_act(x.cuda(), b.cuda(), empty.cuda(), 3, 0, 0.2, 1.0)                 # forward (:58)
+    want = ops.fused_bias_act(x, b, empty, 3, 0, 0.2, 1.0)
+    assert rel_err(out, want) < 1e-6
+    gy = torch.randn(x.shape, generator=g)
+    gi = fused_act_cuda.fused_bias_act(gy.cuda(), empty.cuda(), out, 3, 1, 0.2, 1.0)                      # backward (:31-33)
+    assert rel_err(gi, ops.fused_bias_act(gy, empty, want, 3, 1, 0.2, 1.0)) < 1e-6
+    gg = fused_act_cuda.fused_bias_act(gy.cuda(), b.cuda(), out, 3, 1, 0.2, 1.0)                          # double backward (:47-49)
+    assert rel_err(gg, ops.fused_bias_act(gy, b, want, 3, 1, 0.2, 1.0)) < 1e-6
+    k = torch.tensor([1., 3., 3., 1.])
+    k = k[None] * k[:, None] / 64
+    inp = torch.randn(6, 12, 14, 1, generator=g)
+    for cfg in ((1, 1, 1, 1, 2, 1, 2, 1), (2, 2, 1, 1, 2, 1, 2, 1), (1, 1, 2, 2, 1, 1, 1, 1), (1, 1, 1, 1, 2, 2, 2, 2)):
+        got = upfirdn2d_cuda.upfirdn2d(inp.cuda(), k.cuda(), *cfg)
+        assert rel_err(got, ops.upfirdn2d(inp, k, *cfg)) < 1e-5, cfg
