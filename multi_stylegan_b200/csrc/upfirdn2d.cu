@@ -169,8 +169,11 @@ __device__ __forceinline__ void fma4(float4& a, const float4& v, float k) {
 // up == down == 1, taps <= 4x4.  A warp spans 32 channel quads (512 contiguous bytes) of one output column pair;
 // each thread slides down the rows of its tile keeping the four partially accumulated output rows in registers,
 // so every input row is loaded once per thread (COLS + 3 float4 loads per COLS outputs; neighbours hit in L1).
-template <int COLS>
-__global__ void __launch_bounds__(256, 4)
+// EP: 0 = plain FIR (the upfirdn2d op), 1 = fused noise / bias / leaky ReLU tail, 2 = the tail of the shared-weight
+// modulated up-convolution (per-sample channel scale before the tail, second output).  Separate instantiations: the
+// plain blur runs at 64 registers (4 CTAs per SM) only without the tail's operands live across the row loop.
+template <int COLS, int EP>
+__global__ void __launch_bounds__(256, EP == 0 ? 4 : 3)
 fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, const float* __restrict__ kernel,
                    const FirClParams p) {
   __shared__ float sk[4][4];
@@ -207,16 +210,25 @@ fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, cons
   for (int s = 0; s < 4; ++s)
 #pragma unroll
     for (int c = 0; c < COLS; ++c) acc[s][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const bool fused = p.ep_act || p.ep_bias || p.ep_noise || p.ep_cscale || p.ep_out2;
+  constexpr bool fused = EP > 0;
   float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.ep_bias) bz = __ldg(reinterpret_cast<const float4*>(p.ep_bias) + q);
   float4 cs = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (p.ep_cscale) cs = __ldg(reinterpret_cast<const float4*>(p.ep_cscale + b * p.ep_cscale_bs) + q);
   float4 s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (p.ep_out2) s2 = __ldg(reinterpret_cast<const float4*>(p.ep_out2_scale + b * p.ep_out2_scale_bs) + q);
-  float4* out2b = p.ep_out2 ? p.ep_out2 + (b * p.out_h * (int64_t)p.out_w) * p.C4 + q : nullptr;
-  const float nw = p.ep_noise ? __ldg(p.ep_noise_w) : 0.f;
-  const float* nzb = p.ep_noise ? p.ep_noise + b * p.ep_noise_bs : nullptr;
+  float4* out2b = nullptr;
+  float nw = 0.f;
+  const float* nzb = nullptr;
+  if (EP > 0) {
+    if (p.ep_bias) bz = __ldg(reinterpret_cast<const float4*>(p.ep_bias) + q);
+    nw = p.ep_noise ? __ldg(p.ep_noise_w) : 0.f;
+    nzb = p.ep_noise ? p.ep_noise + b * p.ep_noise_bs : nullptr;
+  }
+  if (EP > 1) {
+    if (p.ep_cscale) cs = __ldg(reinterpret_cast<const float4*>(p.ep_cscale + b * p.ep_cscale_bs) + q);
+    if (p.ep_out2) {
+      s2 = __ldg(reinterpret_cast<const float4*>(p.ep_out2_scale + b * p.ep_out2_scale_bs) + q);
+      out2b = p.ep_out2 + (b * p.out_h * (int64_t)p.out_w) * p.C4 + q;
+    }
+  }
 
   const int n_in = p.tile_rows + 3;               // input rows i = 0 .. tile_rows + 2  (iy = oy0 - pad_y0 + i)
   for (int i0 = 0; i0 < n_in; i0 += 4) {
@@ -254,8 +266,12 @@ fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, cons
               float4 v = acc[s][c];
               if (fused) {
                 const float add = nzb ? nw * __ldg(nzb + (int64_t)oy * p.out_w + ox0 + c) : 0.f;
-                v.x = fmaf(v.x, cs.x, add + bz.x); v.y = fmaf(v.y, cs.y, add + bz.y);
-                v.z = fmaf(v.z, cs.z, add + bz.z); v.w = fmaf(v.w, cs.w, add + bz.w);
+                if (EP > 1) {
+                  v.x = fmaf(v.x, cs.x, add + bz.x); v.y = fmaf(v.y, cs.y, add + bz.y);
+                  v.z = fmaf(v.z, cs.z, add + bz.z); v.w = fmaf(v.w, cs.w, add + bz.w);
+                } else {
+                  v.x += add + bz.x; v.y += add + bz.y; v.z += add + bz.z; v.w += add + bz.w;
+                }
                 if (p.ep_act) {
                   v.x = v.x > 0.f ? v.x : v.x * p.ep_slope; v.y = v.y > 0.f ? v.y : v.y * p.ep_slope;
                   v.z = v.z > 0.f ? v.z : v.z * p.ep_slope; v.w = v.w > 0.f ? v.w : v.w * p.ep_slope;
@@ -263,8 +279,10 @@ fir_cl_blur_kernel(float4* __restrict__ out, const float4* __restrict__ in, cons
                 v.x *= p.ep_gain; v.y *= p.ep_gain; v.z *= p.ep_gain; v.w *= p.ep_gain;
               }
               orow[(int64_t)(ox0 + c) * p.C4] = v;
-              if (out2b)
-                out2b[((int64_t)oy * p.out_w + ox0 + c) * p.C4] = make_float4(v.x * s2.x, v.y * s2.y, v.z * s2.z, v.w * s2.w);
+              if (EP > 1) {
+                if (out2b)
+                  out2b[((int64_t)oy * p.out_w + ox0 + c) * p.C4] = make_float4(v.x * s2.x, v.y * s2.y, v.z * s2.z, v.w * s2.w);
+              }
             }
         }
 #pragma unroll
@@ -627,7 +645,10 @@ static int upfirdn2d_impl(void* out, const void* in, const void* kernel, int64_t
       p.tiles_y = (int)ceil_div(out_h, p.tile_rows);
       const int64_t blocks = major * p.tiles_y * p.tiles_x * p.chunks;
       if (blocks > 0x7fffffffLL) return fail(MSG_ERR_UNSUPPORTED, "upfirdn2d: grid too large");
-      fir_cl_blur_kernel<COLS><<<(unsigned)blocks, 256, 0, st>>>((float4*)out, (const float4*)in, (const float*)kernel, p);
+      const bool tail = p.ep_act || p.ep_bias || p.ep_noise, mod = p.ep_cscale || p.ep_out2;
+      if (mod) fir_cl_blur_kernel<COLS, 2><<<(unsigned)blocks, 256, 0, st>>>((float4*)out, (const float4*)in, (const float*)kernel, p);
+      else if (tail || p.ep_gain != 1.f) fir_cl_blur_kernel<COLS, 1><<<(unsigned)blocks, 256, 0, st>>>((float4*)out, (const float4*)in, (const float*)kernel, p);
+      else fir_cl_blur_kernel<COLS, 0><<<(unsigned)blocks, 256, 0, st>>>((float4*)out, (const float4*)in, (const float*)kernel, p);
       MSG_CHECK_LAUNCH("upfirdn2d(channels-last blur)");
       return MSG_OK;
     }
