@@ -220,6 +220,16 @@ int msg_conv2d_dgrad(float* dx, const float* dy, const float* w, const msg_conv_
 int msg_conv2d_dgrad_acc(float* dx, const float* dy, const float* w, const msg_conv_desc* d,
                          float alpha, const float* add, void* workspace, size_t workspace_bytes, int flags,
                          msg_stream_t stream);
+/* The dgrad of a layer fused with the activation backward of the layer that produced its input
+ * (op_static/fused_act.py:31-40 behind u_net_2d_discriminator.py:174-186; `ref` = that layer's activation output, layout of dx):
+ *   dx = alpha * conv^T(dy, w) * (ref > 0 ? 1 : slope) * gain ;   dbias[c] = sum_{b,y,x} dx[b,c,y,x]   (dbias may be NULL)
+ * tcgen05 engine, NHWC, stride 1, C % 4 == 0 (at least 32 channels); msg_conv2d_dgrad_mask_supported()
+ * answers 1 when the shape qualifies (otherwise run msg_conv2d_dgrad + msg_fused_bias_act_bwd).  Deterministic.
+ * workspace: msg_conv2d_workspace(d, 1, flags). */
+int msg_conv2d_dgrad_mask_supported(const msg_conv_desc* d, int flags);
+int msg_conv2d_dgrad_mask(float* dx, float* dbias, const float* dy, const float* w, const msg_conv_desc* d,
+                          float alpha, const float* ref, float slope, float gain, void* workspace,
+                          size_t workspace_bytes, int flags, msg_stream_t stream);
 int msg_conv2d_wgrad(float* dw, const float* dy, const float* x, const msg_conv_desc* d,
                      float alpha, void* workspace, size_t workspace_bytes, int flags,
                      msg_stream_t stream);

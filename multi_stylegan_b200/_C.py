@@ -438,6 +438,46 @@ def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Sequence[int], stride
     return dx
 
 
+def conv2d_dgrad_act_bwd(dy: torch.Tensor, w: torch.Tensor, ref: torch.Tensor, padding=0, alpha: float = 1.0,
+                         slope: float = 0.2, gain: float = 1.0, want_dbias: bool = True):
+    """(g_pre, dbias) = activation backward of the layer that produced `ref`, applied to the stride-1 dgrad of the NEXT
+    layer inside that dgrad's epilogue:  g_pre = alpha * conv^T(dy, w) * (ref > 0 ? 1 : slope) * gain,  dbias = sum over
+    (b, y, x) of g_pre.  Returns None when the shape is not eligible (the caller then runs conv2d_dgrad +
+    noise_bias_act_cl_bwd): tcgen05 engine, channels-last, shared weights."""
+    if w.dim() != 4 or not conv_channels_last or not dy.is_cuda:
+        return None
+    _check_f32(dy, "dy")
+    _check_f32(w, "w")
+    _check_f32(ref, "ref")
+    dy, layout = _act(dy)
+    w = _aligned(w)
+    B, O, OH, OW = dy.shape
+    per_sample, Ow, C, kh, kw = _w_dims(w, B, False)
+    if Ow != O:
+        raise RuntimeError("conv2d_dgrad_act_bwd: weight has %d output channels, dy has %d" % (Ow, O))
+    H, W = int(ref.shape[2]), int(ref.shape[3])
+    if tuple(ref.shape) != (B, C, H, W):
+        raise RuntimeError("conv2d_dgrad_act_bwd: `ref` must have the shape of dx")
+    d = _conv_desc(B, C, H, W, O, kh, kw, 1, padding, per_sample, layout, False)
+    if (d.OH, d.OW) != (OH, OW):
+        raise RuntimeError("conv2d_dgrad_act_bwd: dy spatial size inconsistent with `ref`")
+    L = _lib.lib()
+    if layout != _lib.LAYOUT_NHWC or not L.msg_conv2d_dgrad_mask_supported(ctypes.byref(d), conv_flags):
+        return None
+    ref = ref.contiguous(memory_format=torch.channels_last)
+    if ref.data_ptr() % 16:
+        return None
+    dx = _empty_act((B, C, H, W), layout, dy.device)
+    dbias = torch.empty(C, device=dy.device, dtype=torch.float32) if want_dbias else None
+    with _on_device(dy.device):
+        nbytes = L.msg_conv2d_workspace(ctypes.byref(d), 1, conv_flags)
+        ws, wsp = _workspace(nbytes, dy.device)
+        rc = L.msg_conv2d_dgrad_mask(_ptr(dx), _ptr(dbias), _ptr(dy), _ptr(w), ctypes.byref(d), float(alpha), _ptr(ref),
+                                     float(slope), float(gain), wsp, nbytes, conv_flags, _stream(dy))
+    _lib.check(rc, "conv2d_dgrad_act_bwd")
+    return dx, dbias
+
+
 def conv2d_wgrad(dy: torch.Tensor, x: torch.Tensor, khw: Sequence[int], stride=1, padding=0,
                  per_sample: bool = False, alpha: float = 1.0, w_transposed: bool = False) -> torch.Tensor:
     _check_f32(dy, "dy")

@@ -115,6 +115,10 @@ _SIGNATURES = {
                                     _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
     "msg_conv2d_dgrad_acc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc), _c.c_float,
                                         _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
+    "msg_conv2d_dgrad_mask_supported": (_c.c_int, [_c.POINTER(ConvDesc), _c.c_int]),
+    "msg_conv2d_dgrad_mask": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc),
+                                         _c.c_float, _c.c_void_p, _c.c_float, _c.c_float, _c.c_void_p, _c.c_size_t,
+                                         _c.c_int, _c.c_void_p]),
     "msg_conv2d_wgrad": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(ConvDesc), _c.c_float,
                                     _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p]),
     "msg_conv2d_last_engine": (_c.c_int, []),

@@ -230,9 +230,14 @@ class ResBlockFused(Function):
         need_x, need_x2, need_w1, need_b1, need_w2, need_b2, need_wr = need[:7]
         hw = tuple(x.shape[2:])
         g2_pre, db2, _ = _C.noise_bias_act_cl_bwd(gout, h2, None, slope, g2, need_b2)
-        gh1 = _C.conv2d_dgrad(g2_pre, w2, hw, 1, 1, alpha=a2)
+        # first activation's backward inside the dgrad that produces its incoming gradient (one kernel, no pass over gh1)
+        fused = _C.conv2d_dgrad_act_bwd(g2_pre, w2, h1, 1, alpha=a2, slope=slope, gain=g1, want_dbias=need_b1)
+        if fused is not None:
+            g1_pre, db1 = fused
+        else:
+            gh1 = _C.conv2d_dgrad(g2_pre, w2, hw, 1, 1, alpha=a2)
+            g1_pre, db1, _ = _C.noise_bias_act_cl_bwd(gh1, h1, None, slope, g1, need_b1)
         dw2 = _C.conv2d_wgrad(g2_pre, h1, (3, 3), 1, 1, False, alpha=a2) if need_w2 else None
-        g1_pre, db1, _ = _C.noise_bias_act_cl_bwd(gh1, h1, None, slope, g1, need_b1)
         dx = dx2 = dw1 = dwr = None
         if x2 is None:
             if need_x:

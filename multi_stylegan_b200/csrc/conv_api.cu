@@ -278,11 +278,13 @@ struct DgradPlan {
   int nph;                       // s*s phase problems
   PixGemm g[4];
   bool use_tc[4];
-  size_t off_x, off_eng, eng_each, total;
+  size_t off_x, off_eng, eng_each, off_colsum, total;
 };
 
+struct DgradMask { const float* ref; float slope, gain; };
+
 static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float* w, float* dx, float alpha, int flags,
-                            const float* add = nullptr) {
+                            const float* add = nullptr, const DgradMask* mask = nullptr) {
   DgradPlan pl{};
   const int s = d->stride_h;
   pl.nph = s * s;
@@ -304,6 +306,7 @@ static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float
     g.ep = Epilogue{};
     g.ep.gain = 1.f;
     g.ep.add = add;             // dx = alpha * conv^T(dy, w) + add  (gradient accumulation in the epilogue)
+    if (mask) { g.ep.add = mask->ref; g.ep.add_is_mask = 1; g.ep.slope = mask->slope; g.ep.gain = mask->gain; }
     g.ntaps = 0;
     for (int ky = 0; ky < d->kh; ++ky) {
       if ((py + d->pad_h - ky) % s != 0) continue;
@@ -334,8 +337,19 @@ static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float
   pl.eng_each = r256(eng);
   // each phase keeps its own transformed weights alive until its kernel has run
   off += (size_t)pl.nph * pl.eng_each;
+  pl.off_colsum = off;         // mask mode: per-(CTA, epilogue warp) column sums, [2 * #SMs * 4][C]
+  off += r256((size_t)2 * num_sms() * 4 * d->C * sizeof(float));
   pl.total = off + 256;
   return pl;
+}
+
+__global__ void __launch_bounds__(256)
+colsum_reduce_kernel(float* __restrict__ out, const float* __restrict__ partial, int rows, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float acc = 0.f;
+  for (int r = 0; r < rows; ++r) acc += partial[(int64_t)r * N + n];     // fixed order: deterministic
+  out[n] = acc;
 }
 
 struct WgradPlan {
@@ -591,6 +605,58 @@ extern "C" int msg_conv2d_dgrad_acc(float* dx, const float* dy, const float* w, 
       rc = simt_pixgemm(g, st);   // also zero-fills phases that no filter tap reaches
     }
     if (rc) return rc;
+  }
+  return MSG_OK;
+}
+
+// dx = alpha * conv^T(dy, w) * (ref > 0 ? 1 : slope) * gain  and (optionally) dbias[c] = sum over pixels of dx: the dgrad of
+// a layer fused with the activation backward of the layer that PRODUCED its input (ref = that layer's output) — inside a
+// residual block g1_pre = fba_bwd(dgrad(g2_pre, w2), h1) is one kernel instead of a GEMM plus a pass over the activation
+// (op_static/fused_act.py:31-40 behind u_net_2d_discriminator.py:174-186).
+static bool dgrad_mask_plan_ok(const msg_conv_desc* d, const DgradPlan& pl) {
+  return d->stride_h == 1 && pl.nph == 1 && pl.tc && pl.use_tc[0] && !pl.pad_in && tc_pixgemm_mask_ok(pl.g[0]);
+}
+
+extern "C" int msg_conv2d_dgrad_mask_supported(const msg_conv_desc* d, int flags) {
+  if (check_desc(d, "conv2d_dgrad_mask")) return 0;
+  if (d->B == 0) return 0;
+  float* al = const_cast<float*>(kAligned);
+  DgradMask m{al, 0.2f, 1.f};
+  DgradPlan pl = plan_dgrad(d, al, al, al, 1.f, flags, nullptr, &m);
+  return dgrad_mask_plan_ok(d, pl) ? 1 : 0;
+}
+
+extern "C" int msg_conv2d_dgrad_mask(float* dx, float* dbias, const float* dy, const float* w, const msg_conv_desc* d,
+                                     float alpha, const float* ref, float slope, float gain, void* workspace,
+                                     size_t workspace_bytes, int flags, msg_stream_t stream) {
+  int rc = check_desc(d, "conv2d_dgrad_mask");
+  if (rc) return rc;
+  if (d->B == 0) return MSG_OK;
+  if (!dx || !dy || !w || !ref) return fail(MSG_ERR_BAD_ARG, "conv2d_dgrad_mask: null pointer");
+  if (ref == dx) return fail(MSG_ERR_BAD_ARG, "conv2d_dgrad_mask: `ref` must not alias dx");
+  cudaStream_t st = (cudaStream_t)stream;
+  DgradMask m{ref, slope, gain};
+  DgradPlan pl = plan_dgrad(d, dy, w, dx, alpha, flags, nullptr, &m);
+  if (!dgrad_mask_plan_ok(d, pl))
+    return fail(MSG_ERR_UNSUPPORTED, "conv2d_dgrad_mask: needs the tcgen05 engine, NHWC, stride 1, C % 4 == 0 "
+                                     "(query msg_conv2d_dgrad_mask_supported)");
+  if (!workspace || workspace_bytes < pl.total)
+    return fail(MSG_ERR_WORKSPACE, "conv2d_dgrad_mask: workspace %zu < %zu", workspace_bytes, pl.total);
+  uint8_t* ws = ws_base(workspace);
+  PixGemm& g = pl.g[0];
+  const int rows = 2 * num_sms() * 4;
+  float* partial = reinterpret_cast<float*>(ws + pl.off_colsum);
+  if (dbias) {
+    MSG_CHECK_CUDA(cudaMemsetAsync(partial, 0, (size_t)rows * d->C * sizeof(float), st));
+    g.ep.colsum = partial;
+  }
+  g.in = dy;
+  g_last_engine = 2;
+  rc = tc_pixgemm(g, ws + pl.off_eng, pl.eng_each, st);
+  if (rc) return rc;
+  if (dbias) {
+    colsum_reduce_kernel<<<(unsigned)((d->C + 255) / 256), 256, 0, st>>>(dbias, partial, rows, d->C);
+    MSG_CHECK_LAUNCH("conv2d_dgrad_mask(bias gradient)");
   }
   return MSG_OK;
 }

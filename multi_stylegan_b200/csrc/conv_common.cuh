@@ -45,6 +45,12 @@ struct Epilogue {
   float* out2;              // second output with the layout of `out`
   const float* out2_scale;  // [B or 1, N]
   int64_t out2_scale_sb;
+  // mask mode (the activation backward of the PRODUCING layer fused into this dgrad): `add` is that layer's activation
+  // output and multiplies instead of adds:  out = alpha * acc * (add > 0 ? 1 : slope) * gain;  with `colsum` the
+  // per-channel sums of `out` (the bias gradient) are accumulated per CTA and epilogue warp:
+  // colsum[(cta * 4 + warp) * N + n]  (tcgen05 engine, TMA-store epilogue, one channel tile only)
+  int add_is_mask;
+  float* colsum;
   __host__ __device__ bool any() const { return bias || noise || add || act || gain != 1.f || cscale || out2; }
 };
 
@@ -107,6 +113,7 @@ uint32_t* tc_debug_host(size_t* words);
 void tc_profile_enable(int on);
 int tc_profile_summary(msg_profile_entry* out, int max_entries);
 bool tc_pixgemm_supported(const PixGemm& g);
+bool tc_pixgemm_mask_ok(const PixGemm& g);
 size_t tc_pixgemm_workspace(const PixGemm& g);
 int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st);
 bool tc_redgemm_supported(const RedGemm& g);

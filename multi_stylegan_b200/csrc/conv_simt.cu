@@ -169,6 +169,7 @@ redgemm_simt_kernel(const RedGemm g) {
 
 int simt_pixgemm(const PixGemm& g, cudaStream_t st) {
   if (g.B <= 0 || g.N <= 0 || g.PH <= 0 || g.PW <= 0) return MSG_OK;
+  if (g.ep.add_is_mask || g.ep.colsum) return fail(MSG_ERR_UNSUPPORTED, "conv(simt): mask-mode epilogue is a tcgen05-engine feature");
   dim3 grid((unsigned)ceil_div((int64_t)g.PH * g.PW, SM_), (unsigned)ceil_div(g.N, SN_), (unsigned)g.B);
   if (grid.y > 65535 || grid.z > 65535) return fail(MSG_ERR_UNSUPPORTED, "conv(simt): grid too large");
   pixgemm_simt_kernel<<<grid, 256, 0, st>>>(g);

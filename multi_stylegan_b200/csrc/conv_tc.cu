@@ -370,7 +370,7 @@ struct TcPixParams {
 // One 32-channel chunk of the TMA-store epilogue: fused transform in registers, then the pixel's 128-byte row goes to
 // the swizzled staging box.  The epilogue warps are one warp per scheduler, so this loop is bound by its instruction
 // count: the three common transforms are compiled select-free (NB = noise/bias term, ACT = leaky ReLU, ADD = residual).
-template <bool NB, bool ACT, bool ADD, bool MOD = false>
+template <bool NB, bool ACT, bool ADD, bool MOD = false, bool MASK = false>
 __device__ __forceinline__ void epi_chunk_to_smem(const float (&rr)[32], const float4 (&av)[8], const float* bias_nb,
                                                   int nvalid4, float nz, float alpha, float slope, float gain,
                                                   uint32_t dst, int lane, const float* cs_nb = nullptr,
@@ -397,7 +397,11 @@ __device__ __forceinline__ void epi_chunk_to_smem(const float (&rr)[32], const f
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * slope;
     }
-    if (ADD) { v[0] += av[j].x; v[1] += av[j].y; v[2] += av[j].z; v[3] += av[j].w; }
+    if (ADD && !MASK) { v[0] += av[j].x; v[1] += av[j].y; v[2] += av[j].z; v[3] += av[j].w; }
+    if (ADD && MASK) {          // `av` = the producing layer's activation output: leaky-ReLU mask of its backward
+      v[0] *= av[j].x > 0.f ? 1.f : slope; v[1] *= av[j].y > 0.f ? 1.f : slope;
+      v[2] *= av[j].z > 0.f ? 1.f : slope; v[3] *= av[j].w > 0.f ? 1.f : slope;
+    }
     if (NB || ACT || ADD || MOD) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[e] *= gain;
@@ -491,7 +495,9 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
 #pragma unroll
               for (int j = 0; j < 8; ++j) av[j] = make_float4(0.f, 0.f, 0.f, 0.f);   // (dead in the ADD = false variants)
               if (lane == 0) {
-                if (has_out2) tma_store_wait_read<0>();     // both boxes of the previous chunk have left their buffers
+                // both boxes of the previous chunk have left their buffers / a single-chunk tile (BN = 32) starts every
+                // call on buffer 0, which the PREVIOUS call's store may still be reading
+                if (has_out2 || BN == 32) tma_store_wait_read<0>();
                 else tma_store_wait_read<1>();              // the box stored two chunks ago has left this buffer
               }
             }
@@ -507,6 +513,9 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
               epi_chunk_to_smem<false, false, false>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
             else if (has_nb && has_act && !with_add)
               epi_chunk_to_smem<true, true, false>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
+            else if (!has_nb && !has_act && with_add && p.ep.add_is_mask)
+              epi_chunk_to_smem<false, false, true, false, true>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope,
+                                                                 valid ? ep_gain : 0.f, dst, lane);   // zeros outside the image
             else if (!has_nb && !has_act && with_add)
               epi_chunk_to_smem<false, false, true>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
             else if (has_act)
@@ -515,6 +524,21 @@ __device__ __forceinline__ void pix_epilogue(const TcPixParams& p, float* stg, u
               epi_chunk_to_smem<true, false, true>(rr, av, bias_nb, nvalid4, nz, ep_alpha, ep_slope, ep_gain, dst, lane);
             if (!(p.debug & 2)) fence_proxy_async_smem();
             __syncwarp();
+            if (p.ep.colsum != nullptr) {
+              // bias gradient: lane c sums column c of the staged 32-pixel x 32-channel box (bank-conflict free: for a
+              // fixed row the swizzled 16-byte groups of the 32 lanes are a permutation; rows of pixels outside the image
+              // were staged as zeros) and adds it to the row of the partial-sum matrix that this (CTA, warp) alone owns:
+              // a fire-and-forget reduction in program order — deterministic, and nothing waits for it
+              const uint32_t col = stage_smem + buf * 4096 + ((uint32_t)(lane & 3) << 2);
+              float acc = 0.f;
+#pragma unroll
+              for (int r = 0; r < 32; ++r) {
+                float t;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(col + r * 128 + ((uint32_t)((lane >> 2) ^ (r & 7)) << 4)) : "memory");
+                acc += t;
+              }
+              if (nb + lane < p.N) atomicAdd(p.ep.colsum + ((int64_t)blockIdx.x * 4 + q) * p.N + nb + lane, acc);
+            }
             if (lane == 0 && !(p.debug & 1)) {
               tma_store_4d(tm_out, stage_smem + buf * 4096, nb, bx, by, b);
               if (has_out2) tma_store_4d(tm_out2, stage_smem + 4096, nb, bx, by, b);
@@ -1602,6 +1626,15 @@ bool tc_pixgemm_supported(const PixGemm& g) {
   return true;
 }
 
+// Mask-mode epilogue (activation backward of the producing layer + bias-gradient column sums, conv_common.cuh): lives in
+// the TMA-store path only.
+bool tc_pixgemm_mask_ok(const PixGemm& g) {
+  if (!tc_pixgemm_supported(g) || g.nphase != 0 || g.out_my != 1 || g.out_mx != 1) return false;
+  if (pick_bn_pix(g) < 32) return false;
+  return g.os.sc == 1 && (g.N % 4 == 0) && al16(g.out) && g.os.sx % 4 == 0 && g.os.sy % 4 == 0 && g.os.sb % 4 == 0 &&
+         al16(g.ep.add) && !(tc_variant() & 16u);
+}
+
 size_t tc_pixgemm_workspace(const PixGemm& g) {
   const int BN = pick_bn_pix(g);
   const int64_t Npad = round_up(g.N, BN), Cpad = round_up(g.Cr, 32);
@@ -1861,6 +1894,10 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   memset(&tmOut2, 0, sizeof(tmOut2));
   if ((p.ep.cscale || p.ep.out2) && p.ep.add)
     return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): channel scales / second output together with a residual operand");
+  if ((p.ep.add_is_mask || p.ep.colsum) && !tc_pixgemm_mask_ok(g))
+    return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): mask-mode epilogue needs the TMA-store path");
+  if (p.ep.add_is_mask && (p.ep.bias || p.ep.noise || p.ep.act))
+    return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): mask-mode epilogue cannot be combined with bias / noise / activation");
   if (p.ep.out2 && !p.ep.out2_scale) return fail(MSG_ERR_BAD_ARG, "conv pixgemm(tcgen05): out2 needs out2_scale");
   if (p.vec_store && BN >= 32 && !(tc_variant() & 16u)) {
     const int bw = Wt < 32 ? Wt : 32;
@@ -1879,6 +1916,8 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     p.tma_store = ok ? 1 : 0;
     p.debug = (int)((tc_variant() >> 5) & 3u);
   }
+  if ((p.ep.add_is_mask || p.ep.colsum) && !p.tma_store)
+    return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): mask-mode epilogue: output not expressible as a TMA store");
   cudaEvent_t pstop;
   const int pslot = prof_begin(0, g.ntaps, g.Cr, g.N, (int64_t)g.B * g.PH * g.PW,
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.Cr * g.ntaps, st, &pstop);

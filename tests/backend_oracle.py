@@ -6,7 +6,7 @@ from oracle import ops
 
 __all__ = ["fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_forward", "conv2d_dgrad", "conv2d_wgrad",
            "modulate_weights", "noise_bias_act", "affine_warp", "noise_bias_act_cl", "noise_bias_act_cl_bwd", "modulate_weights_bwd", "blur_noise_bias_act", "affine_warp_bwd",
-           "demod_factors", "styled_act_bwd", "blur_noise_bias_act_mod"]
+           "demod_factors", "styled_act_bwd", "blur_noise_bias_act_mod", "conv2d_dgrad_act_bwd"]
 
 
 def fused_bias_act(input, bias, refer, act, grad, alpha, scale):
@@ -55,6 +55,12 @@ def _tail(v, bias, noise, noise_w, add, act, slope, gain):
 def conv2d_dgrad(dy, w, in_hw, stride=1, padding=0, alpha=1.0, w_transposed=False, add=None):
     dx = ops.conv2d_dgrad(dy, _wt(w, w_transposed), in_hw, stride, padding) * alpha
     return dx if add is None else dx + add
+
+
+def conv2d_dgrad_act_bwd(dy, w, ref, padding=0, alpha=1.0, slope=0.2, gain=1.0, want_dbias=True):
+    dx = ops.conv2d_dgrad(dy, w, tuple(ref.shape[2:]), 1, padding) * alpha
+    dx = dx * torch.where(ref > 0, torch.ones_like(ref), torch.full_like(ref, slope)) * gain
+    return dx, (dx.sum((0, 2, 3)) if want_dbias else None)
 
 
 def conv2d_wgrad(dy, x, khw, stride=1, padding=0, per_sample=False, alpha=1.0, w_transposed=False):

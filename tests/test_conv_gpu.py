@@ -375,3 +375,50 @@ def test_conv_row_tap_kernel(built_library, case):
             assert rel_err(got, want) < 1e-2, rel_err(got, want)
     finally:
         _C.conv_flags = old
+
+
+@pytest.mark.parametrize("case", [
+    # (B, C [dx channels], O [dy channels], H, W, k)
+    (2, 64, 64, 127, 127, 3),          # the discriminator's odd feature maps: pixel tiles hang over both image edges
+    (2, 128, 128, 64, 200, 3),         # 256-pixel tiles + row-tap kernel
+    (1, 512, 512, 31, 31, 3),          # two channel tiles
+    (3, 96, 32, 17, 40, 3),            # channel tail inside a 32-channel chunk
+    (2, 256, 256, 130, 256, 3),        # CTA pairs
+    (2, 64, 128, 20, 20, 1),           # 1x1 filter
+])
+def test_dgrad_with_activation_backward_epilogue(built_library, case):
+    """msg_conv2d_dgrad_mask: g_pre = alpha * conv^T(dy, w) * mask(ref) * gain and its per-channel sums against the two-step
+    reference (dgrad, then op_static/fused_act.py:31-40's backward).  The mask is exact (it is read from `ref`), so the
+    tolerance is the convolution's; the bias gradient is compared relative to the sum of magnitudes."""
+    from multi_stylegan_b200 import _C, _lib
+    from tests import backend_oracle
+    if not _C.tensor_core_path_available():
+        pytest.skip("not an sm_100 device")
+    B, C, O, H, W, k = case
+    g = torch.Generator().manual_seed(sum(case))
+    dy = torch.randn(B, O, H + 2 * (k // 2) - k + 1, W + 2 * (k // 2) - k + 1, generator=g)
+    w = torch.randn(O, C, k, k, generator=g) / (O * k * k) ** 0.5
+    ref = torch.randn(B, C, H, W, generator=g)
+    d = dev()
+    want, want_db = backend_oracle.conv2d_dgrad_act_bwd(dy, w, ref, k // 2, alpha=0.8, slope=0.2, gain=1.3)
+    old = _C.conv_flags
+    _C.conv_flags = _lib.CONV_FORCE_TC
+    try:
+        r = _C.conv2d_dgrad_act_bwd(dy.to(d), w.to(d), ref.to(d), k // 2, alpha=0.8, slope=0.2, gain=1.3)
+        assert r is not None, "shape expected to be eligible"
+        got, got_db = r
+        assert rel_err(got, want) < 1e-2, rel_err(got, want)
+        scale = want.abs().sum((0, 2, 3)).max()
+        assert (got_db.cpu() - want_db).abs().max() / scale < 1e-3
+        # deterministic
+        got2, got_db2 = _C.conv2d_dgrad_act_bwd(dy.to(d), w.to(d), ref.to(d), k // 2, alpha=0.8, slope=0.2, gain=1.3)
+        assert torch.equal(got, got2) and torch.equal(got_db, got_db2)
+        r = _C.conv2d_dgrad_act_bwd(dy.to(d), w.to(d), ref.to(d), k // 2, alpha=0.8, want_dbias=False)
+        assert r[1] is None
+    finally:
+        _C.conv_flags = old
+    _C.conv_flags = _lib.CONV_FORCE_SIMT
+    try:
+        assert _C.conv2d_dgrad_act_bwd(dy.to(d), w.to(d), ref.to(d), k // 2) is None      # caller falls back to two steps
+    finally:
+        _C.conv_flags = old
