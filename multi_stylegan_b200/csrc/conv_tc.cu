@@ -1534,6 +1534,186 @@ tc_redgemm_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------
+// RedGemm on CTA pairs (wide layers: N >= 256 output channels, 256-channel C tiles): tcgen05.mma.cta_group::2 with
+// M = 256 = the 128 output channels of each CTA, N = 256 input channels of which each CTA loads HALF, and TWO such MMA
+// units per pair and K step (two accumulators = all 512 TMEM columns) that share one operand tile:
+//   tap groups (grid.y < full groups): the units are two filter taps — one dy tile, two shifted x tiles;
+//   the remainder tap of an odd filter (3x3: the ninth): the units are two output-channel blocks — two dy tiles, one x
+//   tile — so these pairs advance through K at the pace of all the others and every K split of the grid walks ONE front
+//   through dy and x (with fewer, longer splits for the odd tap its pairs streamed both tensors a second time from
+//   DRAM: 4.7 GB instead of 2.1 GB at 512->512, 256^2).
+// Operand fill per SM: 48 KB per 1024 MMA cycles = 47 B/clk against 96 B/clk of the single-CTA kernel, whose 4 x 48 KB
+// ring could not cover the L2 latency at that rate (ncu: tensor pipe 78 % active; this kernel: 99 %).  A pair left with a
+// single unit (odd number of 256-channel blocks) takes proportionally fewer K splits so that it carries the same number
+// of MMAs.  Barrier protocol as in tc_pixgemm2_kernel.
+// ------------------------------------------------------------------------------------------------
+template <int STAGES, int TG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+tc_redgemm2_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmI,
+                   const TcRedParams p) {
+  constexpr int BN = 256;
+  constexpr uint32_t ATOM_BYTES = 32 * 32 * 4;
+  constexpr uint32_t T_BYTES = 4 * ATOM_BYTES;        // one operand tile of a CTA: 128 channels x 32 pixels
+  constexpr int SLOTS = 1 + TG;                       // tiles per stage
+  constexpr uint32_t TMEM_COLS = TG * BN <= 256 ? 256 : 512;
+  static_assert(TG == 1 || TG == 2, "one or two MMA units per K step");
+  constexpr uint32_t IDESC = make_idesc_tf32(256, BN, 1, 1);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  const uint32_t sT = base;                           // [STAGES][SLOTS] tiles
+  const uint32_t bars = sT + STAGES * SLOTS * T_BYTES;
+  const uint32_t acc_full = bars + 16 * STAGES;
+  const uint32_t tmem_slot = acc_full + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cl = blockIdx.x >> 1;
+  const int npairs = p.Npad >> 8;
+  const int npair = cl / p.ctiles, ctile = cl - npair * p.ctiles;
+  const int c_out0 = ctile * BN;                         // the pair's input channels (accumulator columns)
+  const int c_ld0 = c_out0 + (int)rank * (BN / 2);       // the half of them this CTA loads
+  const int full_groups = p.ntaps / TG;                  // groups per sample: full_groups (+ 1 for the odd tap)
+  const int groups = (p.ntaps + TG - 1) / TG;
+  const int grp = blockIdx.y % groups;
+  const int bs = blockIdx.y / groups;
+  const int split = blockIdx.z;
+  const int Wk = 1 << p.wk_log2, Hk = 32 >> p.wk_log2;
+
+  // the (up to) two MMA units of this pair: unit u accumulates tap tap_u of output-channel block nblk_u
+  const bool share_b = TG == 2 && grp >= full_groups;    // the odd tap: two output-channel blocks against one x tile
+  int nunit = TG, tap0 = grp * TG, tap1 = grp * TG + 1, nblk0 = npair, nblk1 = npair;
+  bool active = true;
+  if (share_b) {
+    tap1 = tap0;
+    nblk0 = 2 * npair; nblk1 = 2 * npair + 1;
+    active = nblk0 < npairs;
+    if (nblk1 >= npairs) nunit = 1;
+  }
+  const int n0_0 = (nblk0 * 2 + (int)rank) * 128, n0_1 = (nblk1 * 2 + (int)rank) * 128;   // this CTA's A rows per unit
+
+  // K range: a pair with one unit instead of TG is cut into proportionally fewer splits (equal MMA counts per CTA)
+  int nsplit = p.splits;
+  if (nunit < TG) nsplit = (p.splits + TG - 1) / TG;
+  const int per = p.chunks_x * p.chunks_y;
+  const int64_t total = (int64_t)per * (p.per_sample ? 1 : p.B);
+  int k_begin = 0, kiters = 0;
+  if (active && split < nsplit) {
+    k_begin = (int)(total * split / nsplit);
+    kiters = (int)(total * (split + 1) / nsplit) - k_begin;
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bars + 8 * s, 1);             // full  (used in the leader: its producer's arrive + both CTAs' bytes)
+      mbar_init(bars + 8 * (STAGES + s), 1);  // empty (one multicast commit per phase, in each CTA)
+    }
+    mbar_init(acc_full, 1);                   // multicast commit, in each CTA
+    fence_barrier_init();
+    tma_prefetch_desc(&tmG);
+    tma_prefetch_desc(&tmI);
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // stage slots: 0 = dy tile of unit 0, 1 = x tile of unit 0, 2 = x tile of unit 1 (tap groups) / dy tile of unit 1
+    const uint32_t full_leader = mapa_cluster(bars, 0);
+    int bl = k_begin / per;
+    int yc = (k_begin - bl * per) / p.chunks_x, xc = (k_begin - bl * per) - yc * p.chunks_x;
+    uint32_t s = 0, ph = 0;
+    for (int it = 0; it < kiters; ++it) {
+      mbar_wait(bars + 8 * (STAGES + s), ph ^ 1u);
+      const int b = p.per_sample ? bs : bl;
+      if (elect_one()) {
+        const uint32_t st0 = sT + s * SLOTS * T_BYTES, fb = full_leader + 8 * s;
+        if (leader) mbar_expect_tx(bars + 8 * s, 2 * (1 + nunit) * T_BYTES);
+        tma_load_5d_2cta(st0, &tmG, fb, 0, xc * Wk, yc * Hk, b, n0_0 >> 5);
+        tma_load_5d_2cta(st0 + T_BYTES, &tmI, fb, 0, xc * Wk + p.tap_dx[tap0], yc * Hk + p.tap_dy[tap0], b, c_ld0 >> 5);
+        if (TG == 2 && nunit == 2) {
+          if (share_b) tma_load_5d_2cta(st0 + 2 * T_BYTES, &tmG, fb, 0, xc * Wk, yc * Hk, b, n0_1 >> 5);
+          else tma_load_5d_2cta(st0 + 2 * T_BYTES, &tmI, fb, 0, xc * Wk + p.tap_dx[tap1], yc * Hk + p.tap_dy[tap1], b, c_ld0 >> 5);
+        }
+      }
+      __syncwarp();
+      if (++s == STAGES) { s = 0; ph ^= 1u; }
+      if (++xc == p.chunks_x) { xc = 0; if (++yc == p.chunks_y) { yc = 0; ++bl; } }
+    }
+  } else if (warp == 1) {
+    if (leader && kiters > 0) {
+      // MN-major BASE32B operands as in tc_redgemm_kernel: 32-channel atoms ATOM_BYTES apart (LBO), K atoms of 4 pixel
+      // rows 512 bytes apart (SBO); the peer's operands sit at the same shared-memory offsets
+      const uint64_t desc_hi = ((uint64_t)((ATOM_BYTES >> 4) & 0x3FFF) << 16) | ((uint64_t)((512u >> 4) & 0x3FFF) << 32) |
+                               ((uint64_t)1 << 46) | ((uint64_t)(SWZ_128B_BASE32B & 7) << 61);
+      const uint32_t a1_slot = share_b ? 2u : 0u, b1_slot = share_b ? 1u : 2u;
+      uint32_t s = 0, ph = 0;
+      for (int it = 0; it < kiters; ++it) {
+        mbar_wait(bars + 8 * s, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t t_lo = ((sT + s * SLOTS * T_BYTES) >> 4) & 0x3FFF;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+            mma_tf32_2cta(tmem_base, desc_hi | (uint64_t)(t_lo + k * 64), desc_hi | (uint64_t)(t_lo + (T_BYTES >> 4) + k * 64),
+                          IDESC, acc);
+            if (TG == 2 && nunit == 2)
+              mma_tf32_2cta(tmem_base + BN, desc_hi | (uint64_t)(t_lo + a1_slot * (T_BYTES >> 4) + k * 64),
+                            desc_hi | (uint64_t)(t_lo + b1_slot * (T_BYTES >> 4) + k * 64), IDESC, acc);
+          }
+          mma_commit_2cta(bars + 8 * (STAGES + s), 3);
+          if (it == kiters - 1) mma_commit_2cta(acc_full, 3);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (active) {
+    const int q = warp & 3;
+    const int n = q * 32 + lane;
+    if (kiters > 0) {
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+    }
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int64_t slots_y = (int64_t)(gridDim.y / groups) * p.ntaps;
+#pragma unroll 1
+    for (int u = 0; u < nunit; ++u) {
+      const int64_t slot = (int64_t)bs * p.ntaps + (u == 0 ? tap0 : tap1);
+      const int nrow = (u == 0 ? n0_0 : n0_1) + n;
+      float* prow = p.part + ((((int64_t)split * slots_y + slot) * p.Npad) + nrow) * p.Cpad + c_out0;
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        float r[32];
+        if (kiters > 0) {
+          tmem_ld_32x32(tlane + u * BN + cc, r);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(prow + cc + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+}
+
 struct RedReduceParams {
   const float* part;
   float* dw;
@@ -1969,6 +2149,7 @@ bool tc_redgemm_supported(const RedGemm& g) {
 struct RedPlan {
   int BN, Npad, Cpad, BS, splits, wk_log2, chunks_x, chunks_y;
   int TG;                   // filter taps per CTA
+  bool pairs;               // tc_redgemm2_kernel (CTA pairs, M = 256)
   size_t part_bytes;
 };
 
@@ -1992,6 +2173,31 @@ static RedPlan red_plan(const RedGemm& g) {
     else if (pl.BN == 32) pl.TG = g.ntaps < 9 ? (g.ntaps >= 4 ? 4 : 1) : 9;
     if (pl.TG == 3 && g.ntaps < 3) pl.TG = 1;
     if (pl.TG == 4 && g.ntaps < 4) pl.TG = 1;
+  }
+  // CTA pairs for wide layers: 256 output channels x 256 input channels x 2 taps per pair (MSG_B200_TC_VARIANT bit 32768
+  // keeps the single-CTA kernel)
+  if (pl.BN == 256 && g.N >= 256 && g.N % 32 == 0 && g.C % 32 == 0 && !(tc_variant() & (2u | 32768u))) {
+    pl.pairs = true;
+    pl.Npad = round_up(g.N, 256);
+    pl.TG = g.ntaps >= 2 ? 2 : 1;
+    const int64_t full_groups = g.ntaps / pl.TG, rem = g.ntaps % pl.TG;
+    const int64_t npairs = pl.Npad / 256, ctiles = pl.Cpad / 256;
+    const int64_t max_by_k = kiters / 8 > 0 ? kiters / 8 : 1;
+    const int64_t slots = num_sms() / 2;              // clusters resident at once
+    int64_t best = 1;
+    double best_t = 1e300;
+    for (int64_t sp = 1; sp <= 2 * slots && sp <= max_by_k; ++sp) {
+      // tap groups: one pair per (output block, C tile, group, split); the odd tap: one pair per two output blocks
+      // (a leftover single block runs half the splits) — see tc_redgemm2_kernel
+      const int64_t clusters = pl.BS * ctiles * (npairs * full_groups * sp +
+                                                 (rem ? (npairs / 2) * sp + (npairs % 2) * ceil_div(sp, pl.TG) : 0));
+      const int64_t rounds = ceil_div(clusters, slots);
+      const double t = (double)rounds * ((double)kiters / (double)sp * pl.TG + 24.0) + 2.0 * (double)sp;
+      if (t < best_t * 0.98) { best_t = t; best = sp; }
+    }
+    pl.splits = (int)best;
+    pl.part_bytes = (size_t)pl.splits * pl.BS * g.ntaps * pl.Npad * pl.Cpad * sizeof(float);
+    return pl;
   }
   const int64_t tgroups = ceil_div(g.ntaps, pl.TG);
   const int64_t tiles = (int64_t)(pl.Npad / 128) * (pl.Cpad / pl.BN) * tgroups * pl.BS;
@@ -2033,6 +2239,24 @@ static int launch_red(const CUtensorMap& tmG, const CUtensorMap& tmI, const TcRe
   return MSG_OK;
 }
 
+template <int TG>
+static int launch_red2(const CUtensorMap& tmG, const CUtensorMap& tmI, const TcRedParams& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t per_stage = (size_t)(1 + TG) * 16384;
+  constexpr int STAGES = (per_stage * 6 + 4096 <= 227 * 1024) ? 6 : 4;
+  constexpr size_t smem = (size_t)STAGES * per_stage + 16 * STAGES + 64 + 1024;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  auto kfn = tc_redgemm2_kernel<STAGES, TG>;
+  static bool attr_done[64] = {};
+  const int slot = current_device_slot();
+  if (!attr_done[slot]) {
+    MSG_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[slot] = true;
+  }
+  kfn<<<grid, 192, smem, st>>>(tmG, tmI, p);
+  MSG_CHECK_LAUNCH("conv redgemm(tcgen05, CTA pairs)");
+  return MSG_OK;
+}
+
 int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!tc_redgemm_supported(g)) return fail(MSG_ERR_UNSUPPORTED, "conv wgrad(tcgen05): shape not supported");
   const RedPlan pl = red_plan(g);
@@ -2062,7 +2286,7 @@ int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (b5d) {
     const uint64_t dims[5] = {32, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.B, (uint64_t)(g.C / 32)};
     const uint64_t strides[4] = {(uint64_t)g.is.sx * 4, (uint64_t)g.is.sy * 4, (uint64_t)g.is.sb * 4, 128};
-    const uint32_t box[5] = {32, (uint32_t)Wk, (uint32_t)Hk, 1, (uint32_t)(pl.BN / 32)};
+    const uint32_t box[5] = {32, (uint32_t)Wk, (uint32_t)Hk, 1, (uint32_t)(pl.pairs ? 4 : pl.BN / 32)};   // pairs: half per CTA
     int rc = make_tmap5(&tmI, g.in, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     if (rc) return rc;
   } else {
@@ -2086,6 +2310,10 @@ int tc_redgemm(const RedGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   const int pslot = prof_begin(1, g.ntaps, g.C, g.N, (int64_t)g.B * g.PH * g.PW,
                                2.0 * g.B * g.PH * g.PW * (double)g.N * g.C * g.ntaps, st, &pstop);
   int rc;
+  if (pl.pairs) {
+    if (!a5d || !b5d) return fail(MSG_ERR_UNSUPPORTED, "conv wgrad(tcgen05, CTA pairs): needs whole 32-channel atoms");
+    rc = pl.TG == 2 ? launch_red2<2>(tmG, tmI, p, grid, st) : launch_red2<1>(tmG, tmI, p, grid, st);
+  } else
   switch (pl.BN * 16 + pl.TG) {
     case 256 * 16 + 1: rc = launch_red<256, 1>(tmG, tmI, p, grid, st); break;
     case 128 * 16 + 1: rc = launch_red<128, 1>(tmG, tmI, p, grid, st); break;

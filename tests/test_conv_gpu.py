@@ -422,3 +422,35 @@ def test_dgrad_with_activation_backward_epilogue(built_library, case):
         assert _C.conv2d_dgrad_act_bwd(dy.to(d), w.to(d), ref.to(d), k // 2) is None      # caller falls back to two steps
     finally:
         _C.conv_flags = old
+
+
+@pytest.mark.parametrize("case", [
+    # (B, C, O, H, W, k, pad, per_sample): >= 256 output channels and 256-wide input-channel tiles -> CTA-pair wgrad
+    (2, 256, 256, 40, 40, 3, 1, False),
+    (1, 384, 384, 33, 17, 3, 1, False),       # channel counts that leave the last pair / last half tile partly empty
+    (2, 512, 256, 20, 20, 1, 0, False),       # one tap (TG = 1)
+    (2, 256, 256, 24, 24, 3, 1, True),        # one filter bank per sample
+    (3, 256, 512, 9, 130, 2, 0, False),       # four taps: two full groups, no remainder
+    (8, 512, 512, 64, 64, 3, 1, False),       # enough K for several splits (remainder tap group runs fewer of them)
+])
+def test_wgrad_cta_pair_kernel(built_library, case):
+    from multi_stylegan_b200 import _C, _lib
+    if not _C.tensor_core_path_available():
+        pytest.skip("not an sm_100 device")
+    B, C, O, H, W, k, pad, per = case
+    g = torch.Generator().manual_seed(sum(case[:7]))
+    x = torch.randn(B, C, H, W, generator=g)
+    OH, OW = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    dy = torch.randn(B, O, OH, OW, generator=g)
+    want = ops.conv2d_wgrad(dy, x, (k, k), 1, pad, per)
+    d = dev()
+    old = _C.conv_flags
+    _C.conv_flags = _lib.CONV_FORCE_TC
+    try:
+        got = _C.conv2d_wgrad(dy.to(d), x.to(d), (k, k), 1, pad, per)
+        got2 = _C.conv2d_wgrad(dy.to(d), x.to(d), (k, k), 1, pad, per)
+    finally:
+        _C.conv_flags = old
+    assert got.shape == want.shape
+    assert rel_err(got, want) < 1e-2, rel_err(got, want)
+    assert torch.equal(got, got2)

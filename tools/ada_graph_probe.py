@@ -36,7 +36,7 @@ for graphed in (False, True):
     mw._d_params = lambda: list(D.parameters())
     random.seed(7), np.random.seed(7), torch.manual_seed(7)
     gen = torch.Generator().manual_seed(11)
-    for it in range(5):
+    for it in range(int(os.environ.get("ITERS", "8"))):
         if not graphed:
             mw._graphs.clear()
         log.clear()
