@@ -61,6 +61,44 @@ typedef struct {
 void msg_profile_enable(int on);
 int msg_profile_summary(msg_profile_entry* out, int max_entries);
 
+/* ---- small-M linears of the generator (csrc/linear_ops.cu) ------------------------------------------------------------
+ * StyleMapping (multi_stylegan_generator.py:208-235): pixel norm (equalized_layer.py:257-277), then `depth` x
+ * [EqualizedLinear(K, K, bias=False) (:210-254) -> FusedLeakyReLU (op_static/fused_act.py:76-85)] as ONE launch
+ * (a cluster of 8 CTAs per 16 rows, activations in distributed shared memory):
+ *   x0 = z * rsqrt(mean_k z^2 + eps);  x_{l+1} = lrelu(alpha * x_l W_l^T + bias_l) * gain
+ * acts [depth, M, K] receives every layer's output (acts[depth-1] is the result; the rest is what the backward needs),
+ * x0 [M, K] the normalised input.  `weights` / `biases`: HOST arrays of `depth` device pointers (biases or its entries
+ * may be NULL).  K: multiple of 4, <= 512.  Backward: dW [depth, K, K], db [depth, K] (NULL: skipped) from gy [M, K];
+ * the gradient w.r.t. z is not produced.  Deterministic. */
+int msg_style_mapping_supported(int depth, int K);
+int msg_style_mapping_forward(float* acts, float* x0, const float* z, const float* const* weights,
+                              const float* const* biases, int depth, int M, int K, float alpha, float slope, float gain,
+                              float eps, msg_stream_t stream);
+int msg_style_mapping_backward(float* dW, float* db, const float* gy, const float* acts, const float* x0,
+                               const float* const* weights, const float* const* biases, int depth, int M, int K,
+                               float alpha, float slope, float gain, msg_stream_t stream);
+
+/* A group of independent linears that read slices of ONE input [M, in_row] (the style linears `modulation_mapping` of all
+ * ModulatedConv2d layers, multi_stylegan_generator.py:355-361, reading the per-layer latents) in one launch:
+ *   out_i [M, N] = alpha * in[:, in_off : in_off + K] W^T + beta * bias
+ * Item i's output is the contiguous block [out_off * M, (out_off + N) * M) of the flat `out` (out_off = sum of the
+ * preceding items' N), the layout `gout` has as well.  Backward: dW (flat, item i at w_off), db (flat, b_off), din [M, in_row] (slots = the distinct input slices; input
+ * columns no slot covers are NOT written).  At most 48 items; K multiple of 4, <= 2048.  Tables are host arrays. */
+typedef struct msg_linear_item {
+  const float* W;      /* [N, K] */
+  const float* bias;   /* [N] or NULL */
+  int N, K;
+  int in_off, out_off;
+  int w_off, b_off;
+  float alpha, beta;
+} msg_linear_item;
+typedef struct msg_linear_slot { int in_off, K, first, count; } msg_linear_slot;   /* items [first, first+count) share the slice */
+int msg_linear_group_forward(float* out, const float* in, int64_t in_row, const msg_linear_item* items,
+                             int n_items, int M, int max_n, int max_k, msg_stream_t stream);
+int msg_linear_group_backward(float* dW, float* db, float* din, const float* gout, const float* in,
+                              int64_t in_row, const msg_linear_item* items, int n_items, const msg_linear_slot* slots,
+                              int n_slots, int M, int max_n, int max_k, msg_stream_t stream);
+
 /* Roofline probe (bench.py): one launch of `iters` x 4 back-to-back tcgen05.mma.kind::tf32 (128 x 256 x 8, operands in
  * shared memory, one CTA per SM); *flops receives the FLOPs of the launch.  sink: >= 32 * #SMs floats or NULL. */
 int msg_tf32_mma_rate_probe(int iters, float* sink, double* flops, msg_stream_t stream);

@@ -532,6 +532,126 @@ def profile_summary():
     return out
 
 
+# ---------------------------------------------------------------------------------------------------
+# small-M linears (csrc/linear_ops.cu)
+# ---------------------------------------------------------------------------------------------------
+def style_mapping_supported(depth: int, K: int) -> bool:
+    return bool(_lib.lib().msg_style_mapping_supported(int(depth), int(K)))
+
+
+def _ptr_array(tensors):
+    arr = (ctypes.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+def style_mapping_forward(z: torch.Tensor, weights, biases, alpha: float, slope: float, gain: float, eps: float):
+    """(acts [depth, M, K], x0 [M, K]): pixel norm + depth x [linear -> bias + leaky ReLU] in one launch; acts[-1] is
+    the mapped latent."""
+    _check_f32(z, "z")
+    z = z.contiguous()
+    M, K = z.shape
+    L = len(weights)
+    ws = [w.contiguous() for w in weights]
+    for w in ws:
+        _check_f32(w, "weight")
+        if tuple(w.shape) != (K, K):
+            raise RuntimeError("style_mapping_forward: weights must be [K, K]")
+    acts = torch.empty((L, M, K), device=z.device, dtype=torch.float32)
+    x0 = torch.empty((M, K), device=z.device, dtype=torch.float32)
+    with _on_device(z.device):
+        rc = _lib.lib().msg_style_mapping_forward(_ptr(acts), _ptr(x0), _ptr(z), _ptr_array(ws), _ptr_array(list(biases)),
+                                                  L, M, K, float(alpha), float(slope), float(gain), float(eps), _stream(z))
+    _lib.check(rc, "style_mapping_forward")
+    return acts, x0
+
+
+def style_mapping_backward(gy: torch.Tensor, acts: torch.Tensor, x0: torch.Tensor, weights, biases, alpha: float,
+                           slope: float, gain: float):
+    """(dW [depth, K, K], db [depth, K]) of style_mapping_forward."""
+    gy = gy.contiguous()
+    L, M, K = acts.shape
+    ws = [w.contiguous() for w in weights]
+    dW = torch.empty((L, K, K), device=gy.device, dtype=torch.float32)
+    db = torch.zeros((L, K), device=gy.device, dtype=torch.float32)
+    with _on_device(gy.device):
+        rc = _lib.lib().msg_style_mapping_backward(_ptr(dW), _ptr(db), _ptr(gy), _ptr(acts), _ptr(x0), _ptr_array(ws),
+                                                   _ptr_array(list(biases)), L, M, K, float(alpha), float(slope), float(gain),
+                                                   _stream(gy))
+    _lib.check(rc, "style_mapping_backward")
+    return dW, db
+
+
+class LinearGroup(object):
+    """Host-side description of a group of linears reading slices of one [M, R] input (msg_linear_item table)."""
+
+    def __init__(self, specs):
+        """specs: list of (W [N, K], bias [N] or None, in_off, alpha, beta)."""
+        n = len(specs)
+        self.items = (_lib.LinearItem * n)()
+        self.params = []
+        out_off = w_off = b_off = 0
+        self.out_slices, self.w_slices, self.b_slices = [], [], []
+        slots = {}
+        for i, (W, b, in_off, alpha, beta) in enumerate(specs):
+            N, K = W.shape
+            it = self.items[i]
+            it.W, it.bias = W.data_ptr(), (None if b is None else b.data_ptr())
+            it.N, it.K, it.in_off, it.out_off, it.w_off, it.b_off = N, K, int(in_off), out_off, w_off, b_off
+            it.alpha, it.beta = float(alpha), float(beta)
+            self.out_slices.append((out_off, N))
+            self.w_slices.append((w_off, N, K))
+            self.b_slices.append((b_off, N) if b is not None else None)
+            slots.setdefault((int(in_off), K), []).append(i)
+            out_off += N
+            w_off += N * K
+            b_off += N
+            self.params.append((W, b))
+        self.out_row, self.w_total, self.b_total = out_off, w_off, b_off
+        self.max_n = max(W.shape[0] for W, *_ in specs)
+        self.max_k = max(W.shape[1] for W, *_ in specs)
+        # items of one slot must be adjacent in the table: reorder is not needed when specs arrive slot by slot; in general
+        # the slot table lists runs of adjacent items (several runs per slice are summed by the caller — not used here)
+        runs = []
+        for (in_off, K), idx in slots.items():
+            start = idx[0]
+            for a, b2 in zip(idx, idx[1:]):
+                if b2 != a + 1:
+                    raise RuntimeError("LinearGroup: items reading the same input slice must be adjacent")
+            runs.append((in_off, K, start, len(idx)))
+        self.slots = (_lib.LinearSlot * len(runs))()
+        for j, (in_off, K, first, count) in enumerate(runs):
+            s = self.slots[j]
+            s.in_off, s.K, s.first, s.count = in_off, K, first, count
+        self.covered = sorted((in_off, K) for in_off, K, _, _ in runs)
+        self.key = tuple((W.data_ptr(), None if b is None else b.data_ptr()) for W, b in self.params)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        M, R = x.shape
+        out = torch.empty(M * self.out_row, device=x.device, dtype=torch.float32)      # item-major: [M, N_i] blocks
+        with _on_device(x.device):
+            rc = _lib.lib().msg_linear_group_forward(_ptr(out), _ptr(x), R, self.items, len(self.items), M,
+                                                     self.max_n, self.max_k, _stream(x))
+        _lib.check(rc, "linear_group_forward")
+        return out
+
+    def backward(self, gout: torch.Tensor, x: torch.Tensor, need_dx: bool):
+        M, R = x.shape
+        dW = torch.empty(self.w_total, device=x.device, dtype=torch.float32)
+        db = torch.zeros(max(self.b_total, 1), device=x.device, dtype=torch.float32)
+        dx = None
+        if need_dx:
+            full = sum(k for _, k in self.covered) == R and all(a[0] + a[1] == b[0] for a, b in zip(self.covered, self.covered[1:]))
+            dx = torch.empty((M, R), device=x.device, dtype=torch.float32) if full else torch.zeros((M, R), device=x.device, dtype=torch.float32)
+        with _on_device(x.device):
+            rc = _lib.lib().msg_linear_group_backward(_ptr(dW), _ptr(db), _ptr(dx), _ptr(gout), _ptr(x), R,
+                                                      self.items, len(self.items), self.slots, len(self.slots), M,
+                                                      self.max_n, self.max_k, _stream(x))
+        _lib.check(rc, "linear_group_backward")
+        return dW, db, dx
+
+
 def tf32_mma_rate_probe(iters: int, device) -> float:
     """Launch the tensor-core issue-rate probe (csrc/mma_rate.cu) on torch's current stream; returns its FLOPs."""
     flops = ctypes.c_double(0.0)

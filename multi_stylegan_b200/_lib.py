@@ -39,6 +39,18 @@ class ConvEpilogue(ctypes.Structure):
                 ("y2", ctypes.c_void_p), ("y2_scale", ctypes.c_void_p), ("y2_scale_batch_stride", ctypes.c_int64)]
 
 
+class LinearItem(ctypes.Structure):
+    """msg_linear_item (include/msg_b200.h)."""
+    _fields_ = [("W", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("N", ctypes.c_int), ("K", ctypes.c_int),
+                ("in_off", ctypes.c_int), ("out_off", ctypes.c_int), ("w_off", ctypes.c_int), ("b_off", ctypes.c_int),
+                ("alpha", ctypes.c_float), ("beta", ctypes.c_float)]
+
+
+class LinearSlot(ctypes.Structure):
+    """msg_linear_slot (include/msg_b200.h)."""
+    _fields_ = [("in_off", ctypes.c_int), ("K", ctypes.c_int), ("first", ctypes.c_int), ("count", ctypes.c_int)]
+
+
 class ProfileEntry(ctypes.Structure):
     """msg_profile_entry (include/msg_b200.h)."""
     _fields_ = [("kind", ctypes.c_int), ("taps", ctypes.c_int), ("k_channels", ctypes.c_int),
@@ -78,6 +90,18 @@ _SIGNATURES = {
     "msg_debug_buffer": (_c.POINTER(_c.c_uint32), [_c.POINTER(_c.c_size_t)]),
     "msg_profile_enable": (None, [_c.c_int]),
     "msg_profile_summary": (_c.c_int, [_c.POINTER(ProfileEntry), _c.c_int]),
+    "msg_style_mapping_supported": (_c.c_int, [_c.c_int, _c.c_int]),
+    "msg_style_mapping_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_void_p),
+                                             _c.POINTER(_c.c_void_p), _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_float,
+                                             _c.c_float, _c.c_float, _c.c_void_p]),
+    "msg_style_mapping_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                              _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _c.c_int, _c.c_int, _c.c_int,
+                                              _c.c_float, _c.c_float, _c.c_float, _c.c_void_p]),
+    "msg_linear_group_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.POINTER(LinearItem),
+                                            _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "msg_linear_group_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                             _c.c_int64, _c.POINTER(LinearItem), _c.c_int, _c.POINTER(LinearSlot), _c.c_int,
+                                             _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "msg_tf32_mma_rate_probe": (_c.c_int, [_c.c_int, _c.c_void_p, _c.POINTER(_c.c_double), _c.c_void_p]),
     "msg_fused_bias_act": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                       _c.c_double, _c.c_double, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int,

@@ -55,6 +55,13 @@ inline int num_sms() {
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// per-device "already configured" flags (function attributes belong to the device's context)
+inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  return dev;
+}
+
 // ---- device helpers -----------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {

@@ -343,13 +343,23 @@ static DgradPlan plan_dgrad(const msg_conv_desc* d, const float* dy, const float
   return pl;
 }
 
+// dbias[n] = sum over the rows of the per-(CTA, warp) partial sums; block = 32 channels x 8 row groups, fixed order
 __global__ void __launch_bounds__(256)
 colsum_reduce_kernel(float* __restrict__ out, const float* __restrict__ partial, int rows, int N) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+  __shared__ float sm[8][33];
+  const int c = threadIdx.x & 31, j = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + c;
   float acc = 0.f;
-  for (int r = 0; r < rows; ++r) acc += partial[(int64_t)r * N + n];     // fixed order: deterministic
-  out[n] = acc;
+  if (n < N)
+    for (int r = j; r < rows; r += 8) acc += partial[(int64_t)r * N + n];
+  sm[j][c] = acc;
+  __syncthreads();
+  if (j == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][c];
+    out[n] = t;
+  }
 }
 
 struct WgradPlan {
@@ -655,7 +665,7 @@ extern "C" int msg_conv2d_dgrad_mask(float* dx, float* dbias, const float* dy, c
   rc = tc_pixgemm(g, ws + pl.off_eng, pl.eng_each, st);
   if (rc) return rc;
   if (dbias) {
-    colsum_reduce_kernel<<<(unsigned)((d->C + 255) / 256), 256, 0, st>>>(dbias, partial, rows, d->C);
+    colsum_reduce_kernel<<<(unsigned)((d->C + 31) / 32), 256, 0, st>>>(dbias, partial, rows, d->C);
     MSG_CHECK_LAUNCH("conv2d_dgrad_mask(bias gradient)");
   }
   return MSG_OK;

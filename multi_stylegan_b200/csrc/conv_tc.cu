@@ -1750,12 +1750,6 @@ tc_red_reduce_kernel(const RedReduceParams p) {
 // Host side
 // ------------------------------------------------------------------------------------------------
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-// per-device "already configured" flags (function attributes belong to the device's context)
-static inline int current_device_slot() {
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
-  return dev;
-}
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 

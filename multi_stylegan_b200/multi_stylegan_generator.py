@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 from torch import autograd
 
-from . import conv, equalized_layer, styled
+from . import _C, conv, equalized_layer, linear, styled
 from .op_static import FusedLeakyReLU, upfirdn2d
 from .op_static.fused_act import noise_bias_leaky_relu
 from .op_static.upfirdn2d import blur_noise_bias_leaky_relu
@@ -79,7 +79,25 @@ class StyleMapping(nn.Module):
         self.layers = nn.Sequential(*layers)
 
     def forward(self, noise: torch.Tensor) -> torch.Tensor:
+        if self._fused_eligible(noise):
+            # the whole network (pixel norm + depth x [linear -> bias + leaky ReLU]) as one launch (csrc/linear_ops.cu)
+            mods = list(self.layers)
+            lin0, act0 = mods[1], mods[2]
+            layers = [(mods[i].weight, mods[i + 1].bias) for i in range(1, len(mods), 2)]
+            return linear.style_mapping(noise, layers, lin0.scale, act0.negative_slope, act0.scale, mods[0].alpha)
         return self.layers(noise)
+
+    def _fused_eligible(self, noise: torch.Tensor) -> bool:
+        if not (noise.is_cuda and noise.dim() == 2 and noise.dtype == torch.float32) or _mode.higher_order():
+            return False
+        if noise.requires_grad and torch.is_grad_enabled():
+            return False                       # the fused backward does not produce the gradient w.r.t. the noise
+        mods = list(self.layers)
+        depth = (len(mods) - 1) // 2
+        if depth < 1 or not _C.style_mapping_supported(depth, noise.shape[1]):
+            return False
+        acts = mods[2::2]
+        return all(a.negative_slope == acts[0].negative_slope and a.scale == acts[0].scale for a in acts)
 
 
 class ConstantInput(nn.Module):
@@ -168,9 +186,13 @@ class ModulatedConv2d(nn.Module):
         return "{}, {}, kernel_size={}, stride={}, padding={}, upsampling={}".format(
             self.in_channels, self.out_channels, self.kernel_size, self.stride, self.padding, self.upsampling)
 
-    def modulated_weight(self, style: torch.Tensor, batch_size: int):
-        """Per-sample filter banks [B, O, C, kh, kw] (reference :379-388) and the modulated style [B,1,C,1,1]."""
-        if self.modulation_mapping is not None:
+    def modulated_weight(self, style: torch.Tensor, batch_size: int, modulated_style: Optional[torch.Tensor] = None):
+        """Per-sample filter banks [B, O, C, kh, kw] (reference :379-388) and the modulated style [B,1,C,1,1].
+        `modulated_style` [B, C]: the output of this layer's style linear when the caller has already computed it
+        (all style linears of the network in one launch, linear.style_linears)."""
+        if modulated_style is not None:
+            modulated_style = modulated_style.reshape(batch_size, 1, self.in_channels, 1, 1)
+        elif self.modulation_mapping is not None:
             modulated_style = self.modulation_mapping(style).view(batch_size, 1, self.in_channels, 1, 1)
         else:
             modulated_style = style
@@ -178,11 +200,11 @@ class ModulatedConv2d(nn.Module):
                                         self.scale, self.demodulate)             # [B, O, C, kh, kw]
         return weight, modulated_style
 
-    def forward(self, input: torch.Tensor, style: torch.Tensor):
+    def forward(self, input: torch.Tensor, style: torch.Tensor, modulated_style: Optional[torch.Tensor] = None):
         batch_size, features, height, width = input.shape
         assert features == self.in_channels, \
             "Expect input feature shape of {} but get {}.".format(self.in_channels, features)
-        weight, modulated_style = self.modulated_weight(style, batch_size)
+        weight, modulated_style = self.modulated_weight(style, batch_size, modulated_style)
         if self.upsampling:
             output = conv.conv_transpose2d(input, weight, stride=self.stride, padding=self.padding,
                                            weight_is_conv_layout=True)
@@ -274,9 +296,10 @@ class OutputBlock(nn.Module):
                                                      modulation_mapping=modulation_mapping)
         self.bias = nn.Parameter(torch.zeros(1, 1, 1, 1, dtype=torch.float32))
 
-    def forward(self, input: torch.Tensor, style: torch.Tensor, skip: torch.Tensor = None):
+    def forward(self, input: torch.Tensor, style: torch.Tensor, skip: torch.Tensor = None,
+                modulated_style: Optional[torch.Tensor] = None):
         if self.modulation_mapping:
-            output, style = self.modulated_convolution(input, style)
+            output, style = self.modulated_convolution(input, style, modulated_style)
         else:
             output = self.modulated_convolution(input, style)
         output = output + self.bias
@@ -347,7 +370,10 @@ class Generator(nn.Module):
         n_latent = self.n_latent
         if not input_is_latent:
             if isinstance(input, list):
-                styles = [self.style_mapping(z) for z in input]
+                if len(input) > 1 and all(z.shape == input[0].shape and z.dim() == 2 for z in input):
+                    styles = list(self.style_mapping(torch.cat(input, dim=0)).split(input[0].shape[0], dim=0))   # row-wise network
+                else:
+                    styles = [self.style_mapping(z) for z in input]
                 if torch.is_tensor(inject_index):
                     # crossover index held on the device (CUDA-graph replay): the same [B, n_latent, L] tensor as below
                     first = torch.arange(n_latent, device=styles[0].device).view(1, n_latent, 1) < inject_index
@@ -366,12 +392,12 @@ class Generator(nn.Module):
 
     @staticmethod
     def _paired_output(block_1: "OutputBlock", block_2: "OutputBlock", features: torch.Tensor, w: torch.Tensor,
-                       skip_12: torch.Tensor):
+                       skip_12: torch.Tensor, modulated_style: Optional[torch.Tensor] = None):
         """output_blocks_1[i](x, w, skip_1) and output_blocks_2[i](x, style, skip_2) (reference :188-189, :509-526) as ONE
         1x1 modulated convolution with the two 3-channel filter banks stacked (both read the same 512-channel
         features) and ONE skip upsampling on the stacked [B, 6, H, W] image; returns the stacked result and the style."""
         batch = features.shape[0]
-        weight_1, style = block_1.modulated_convolution.modulated_weight(w, batch)
+        weight_1, style = block_1.modulated_convolution.modulated_weight(w, batch, modulated_style)
         weight_2, _ = block_2.modulated_convolution.modulated_weight(style, batch)
         mc = block_1.modulated_convolution
         output = conv.conv2d(features, torch.cat([weight_1, weight_2], dim=1), stride=mc.stride, padding=mc.padding)
@@ -417,8 +443,12 @@ class Generator(nn.Module):
         B = latent.shape[0]
         dev = latent.device
 
-        def style_of(block: "StyledConv2d", w: torch.Tensor) -> torch.Tensor:
-            return block.modulated_convolution.modulation_mapping(w)                       # [B, C_in]
+        styles = self._all_styles(latent)
+
+        def style_of(block, w: torch.Tensor) -> torch.Tensor:
+            mc = block.modulated_convolution
+            s = styles.get(id(mc))
+            return mc.modulation_mapping(w) if s is None else s                            # [B, C_in]
 
         def draw(noise_map, h, w):
             return torch.randn(B, 1, h, w, device=dev, dtype=torch.float32) if noise_map is None else noise_map
@@ -443,7 +473,8 @@ class Generator(nn.Module):
         sb = s0.view(B, -1, 1, 1)
         out_1, xs = run(self.starting_convolution_1, self.constant_input_1.input * sb, s0, noise_start, s_next)
         out_2, _ = run(self.starting_convolution_2, self.constant_input_2.input * sb, s0, noise_start, None)
-        skip_1, style = self.starting_output_block_1(out_1, latent[:, 1])
+        skip_1, style = self.starting_output_block_1(out_1, latent[:, 1],
+                                                     modulated_style=styles.get(id(self.starting_output_block_1.modulated_convolution)))
         skip_2 = self.starting_output_block_2(out_2, style)
         skip_12 = torch.cat([skip_1, skip_2], dim=1)
         for i in range(n_main // 2):
@@ -453,8 +484,29 @@ class Generator(nn.Module):
             s_next = style_of(mains[2 * i + 2], latent[:, 2 * i + 3]) if 2 * i + 2 < n_main else None
             out_1, xs = run(mains[2 * i + 1], xs, s_cv, noise[2 * i + 1], s_next)
             skip_12, _ = self._paired_output(self.output_blocks_1[i], self.output_blocks_2[i], out_1,
-                                             latent[:, 2 * i + 3], skip_12)
+                                             latent[:, 2 * i + 3], skip_12,
+                                             styles.get(id(self.output_blocks_1[i].modulated_convolution)))
         return skip_12.reshape(B, 2, self.out_channels, skip_12.shape[2], skip_12.shape[3])
+
+    def _all_styles(self, latent: torch.Tensor) -> Dict[int, torch.Tensor]:
+        """Every style linear of the live network (`modulation_mapping` of the first branch's convolutions and tRGB
+        blocks, reference :355-361) in ONE launch: they are independent linears on slices of the [B, n_latent * L]
+        latent (linear.style_linears).  Keys: id() of the ModulatedConv2d.  Empty when the fused form does not apply."""
+        mains = self.main_convolutions_1
+        if not latent.is_cuda or latent.dim() != 3 or latent.dtype != torch.float32 or latent.shape[2] % 4 != 0:
+            return {}
+        L = latent.shape[2]
+        users = [(self.starting_convolution_1.modulated_convolution, 0), (self.starting_output_block_1.modulated_convolution, 1)]
+        users += [(m.modulated_convolution, j + 1) for j, m in enumerate(mains)]
+        users += [(ob.modulated_convolution, 2 * i + 3) for i, ob in enumerate(self.output_blocks_1)]
+        users = [(mc, j) for mc, j in users if mc.modulation_mapping is not None and j < latent.shape[1]]
+        users.sort(key=lambda u: u[1])                                       # items reading the same latent are adjacent
+        if not users or len(users) > 48:
+            return {}
+        specs = [(mc.modulation_mapping.weight, mc.modulation_mapping.bias, j * L, mc.modulation_mapping.scale,
+                  mc.modulation_mapping.scale_bias) for mc, j in users]
+        outs = linear.style_linears(latent.reshape(latent.shape[0], -1), specs)
+        return {id(mc): o for (mc, _), o in zip(users, outs)}
 
     def _forward_tail(self, latent, noise_start, noise, dead, return_path_length_grads, path_length_noise,
                       return_main_style_vectors):
