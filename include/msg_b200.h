@@ -99,6 +99,24 @@ int msg_linear_group_backward(float* dW, float* db, float* din, const float* gou
                               int64_t in_row, const msg_linear_item* items, int n_items, const msg_linear_slot* slots,
                               int n_slots, int M, int max_n, int max_k, msg_stream_t stream);
 
+/* ---- non-local (self-attention) block of the discriminator, u_net_2d_discriminator.py:332-381 (csrc/attention_ops.cu) ----
+ * The block's three input 1x1 convolutions run as one GEMM with stacked filters and the two attention products as 1x1
+ * convolutions with one filter bank per sample (msg_conv2d_forward / _wgrad, w_batch_stride != 0); these are the
+ * memory-bound passes in between, channels-last fp32:
+ *   msg_nl_split_pool:   qkv [B,H,W,cq+cq+cv] -> theta [B,H,W,cq] (copy), phi_p [B,H/2,W/2,cq], g_p [B,H/2,W/2,cv]
+ *                        (F.max_pool2d(kernel 2, stride 2), :367-368) and idx [B,H/2,W/2,(cq+cv)/4] (four 8-bit argmax
+ *                        positions per 32-bit word; first maximum in scan order)
+ *   msg_nl_merge_unpool: the adjoint: dqkv from dtheta, dphi_p, dg_p, idx (every element of dqkv is written)
+ *   msg_softmax_rows:    in-place softmax of `rows` rows of n floats (F.softmax(.., dim=-1), :372); n % 4 == 0, n <= 4096
+ *   msg_softmax_rows_bwd: dp_inout <- p * (dp_inout - sum_j p_j dp_inout_j)
+ * cq, cv: multiples of 4; pointers 16-byte aligned. */
+int msg_nl_split_pool(float* theta, float* phi_p, float* g_p, uint32_t* idx, const float* qkv, int B, int H, int W, int cq,
+                      int cv, msg_stream_t stream);
+int msg_nl_merge_unpool(float* dqkv, const float* dtheta, const float* dphi_p, const float* dg_p, const uint32_t* idx,
+                        int B, int H, int W, int cq, int cv, msg_stream_t stream);
+int msg_softmax_rows(float* x, int64_t rows, int n, msg_stream_t stream);
+int msg_softmax_rows_bwd(float* dp_inout, const float* p, int64_t rows, int n, msg_stream_t stream);
+
 /* Roofline probe (bench.py): one launch of `iters` x 4 back-to-back tcgen05.mma.kind::tf32 (128 x 256 x 8, operands in
  * shared memory, one CTA per SM); *flops receives the FLOPs of the launch.  sink: >= 32 * #SMs floats or NULL. */
 int msg_tf32_mma_rate_probe(int iters, float* sink, double* flops, msg_stream_t stream);

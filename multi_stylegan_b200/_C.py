@@ -652,6 +652,59 @@ class LinearGroup(object):
         return dW, db, dx
 
 
+# ---------------------------------------------------------------------------------------------------
+# non-local block passes (csrc/attention_ops.cu); all tensors channels-last [B, C, H, W] views
+# ---------------------------------------------------------------------------------------------------
+def _cl_empty(B, C, H, W, device):
+    return torch.empty((B, H, W, C), device=device, dtype=torch.float32).permute(0, 3, 1, 2)
+
+
+def nl_split_pool(qkv: torch.Tensor, cq: int, cv: int):
+    """qkv [B, cq+cq+cv, H, W] channels-last -> (theta [B,cq,H,W], phi_p [B,cq,H/2,W/2], g_p [B,cv,H/2,W/2], idx)."""
+    _check_f32(qkv, "qkv")
+    qkv = qkv.contiguous(memory_format=torch.channels_last)
+    B, CT, H, W = qkv.shape
+    if CT != 2 * cq + cv:
+        raise RuntimeError("nl_split_pool: channel count")
+    dev = qkv.device
+    theta, phi, g = _cl_empty(B, cq, H, W, dev), _cl_empty(B, cq, H // 2, W // 2, dev), _cl_empty(B, cv, H // 2, W // 2, dev)
+    idx = torch.empty((B, H // 2, W // 2, (cq + cv) // 4), device=dev, dtype=torch.int32)
+    with _on_device(dev):
+        rc = _lib.lib().msg_nl_split_pool(_ptr(theta), _ptr(phi), _ptr(g), _ptr(idx), _ptr(qkv), B, H, W, cq, cv, _stream(qkv))
+    _lib.check(rc, "nl_split_pool")
+    return theta, phi, g, idx
+
+
+def nl_merge_unpool(dtheta: torch.Tensor, dphi: torch.Tensor, dg: torch.Tensor, idx: torch.Tensor):
+    cl = torch.channels_last
+    dtheta, dphi, dg = dtheta.contiguous(memory_format=cl), dphi.contiguous(memory_format=cl), dg.contiguous(memory_format=cl)
+    B, cq, H, W = dtheta.shape
+    cv = dg.shape[1]
+    dqkv = _cl_empty(B, 2 * cq + cv, H, W, dtheta.device)
+    with _on_device(dtheta.device):
+        rc = _lib.lib().msg_nl_merge_unpool(_ptr(dqkv), _ptr(dtheta), _ptr(dphi), _ptr(dg), _ptr(idx), B, H, W, cq, cv,
+                                            _stream(dtheta))
+    _lib.check(rc, "nl_merge_unpool")
+    return dqkv
+
+
+def softmax_rows_(x: torch.Tensor, n: int) -> torch.Tensor:
+    """In-place softmax over runs of n consecutive floats of the (dense) tensor x."""
+    rows = x.numel() // n
+    with _on_device(x.device):
+        rc = _lib.lib().msg_softmax_rows(_ptr(x), rows, int(n), _stream(x))
+    _lib.check(rc, "softmax_rows")
+    return x
+
+
+def softmax_rows_bwd_(dp: torch.Tensor, p: torch.Tensor, n: int) -> torch.Tensor:
+    rows = dp.numel() // n
+    with _on_device(dp.device):
+        rc = _lib.lib().msg_softmax_rows_bwd(_ptr(dp), _ptr(p), rows, int(n), _stream(dp))
+    _lib.check(rc, "softmax_rows_bwd")
+    return dp
+
+
 def tf32_mma_rate_probe(iters: int, device) -> float:
     """Launch the tensor-core issue-rate probe (csrc/mma_rate.cu) on torch's current stream; returns its FLOPs."""
     flops = ctypes.c_double(0.0)

@@ -102,6 +102,12 @@ _SIGNATURES = {
     "msg_linear_group_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                              _c.c_int64, _c.POINTER(LinearItem), _c.c_int, _c.POINTER(LinearSlot), _c.c_int,
                                              _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "msg_nl_split_pool": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
+                                     _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "msg_nl_merge_unpool": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
+                                       _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
+    "msg_softmax_rows": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p]),
+    "msg_softmax_rows_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p]),
     "msg_tf32_mma_rate_probe": (_c.c_int, [_c.c_int, _c.c_void_p, _c.POINTER(_c.c_double), _c.c_void_p]),
     "msg_fused_bias_act": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                       _c.c_double, _c.c_double, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int,

@@ -1,7 +1,8 @@
 """U-Net discriminator (encoder/decoder of residual + non-local blocks, scalar and per-pixel heads) with
 the reference's module tree and state_dict names (multi_stylegan/u_net_2d_discriminator.py:14-381).
-Convolutions, blurs, upsampling and activations run on this package's sm_100a kernels; the 4096x1024
-attention of the non-local block keeps torch.bmm / softmax / max_pool2d as in the reference (:370-380).
+Convolutions, blurs, upsampling and activations run on this package's sm_100a kernels, and so does the non-local
+block in its first-order form (attention.py); the composite torch.bmm / softmax / max_pool2d formulation of the
+reference (:370-380) remains for double backward (R1) and for the CPU.
 The FFT input option relied on torch.rfft, which no longer exists; `fft: True` raises."""
 import math
 from typing import Any, Dict, List, Tuple
@@ -10,7 +11,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _C, _mode, conv, equalized_layer
+from . import _C, _mode, attention, conv, equalized_layer
 from .multi_stylegan_generator import _fir_kernel
 from .op_static import FusedLeakyReLU, upfirdn2d
 
@@ -141,7 +142,19 @@ class NonLocalBlock(nn.Module):
         self.residual_mapping = c1(in_channels, out_channels) if in_channels != out_channels else nn.Identity()
         self.register_parameter(name="gamma", param=nn.Parameter(torch.tensor(0.)))
 
-    def forward(self, input: torch.Tensor) -> torch.Tensor:
+    def forward(self, input: torch.Tensor, input_2: torch.Tensor = None) -> torch.Tensor:
+        """`input_2` (U-Net decoder): the block is applied to the channel concatenation [input | input_2] (reference :137)."""
+        res = self.residual_mapping
+        cq, cv = self.theta.weight.shape[0], self.g.weight.shape[0]
+        if (not _mode.higher_order() and isinstance(res, equalized_layer.EqualizedConv2d) and res.bias is None
+                and attention.eligible(input, cq, cv)):
+            if input_2 is not None and not _C.cat2_supported(input, input_2, 1):
+                input, input_2 = torch.cat([input, input_2], dim=1), None
+            return attention.non_local_block(input, input_2, self.theta.weight, self.phi.weight, self.g.weight,
+                                             self.o.weight, res.weight, self.gamma, self.theta.scale, self.o.scale,
+                                             res.scale / math.sqrt(2))
+        if input_2 is not None:
+            input = torch.cat([input, input_2], dim=1)
         batch_size, _, height, width = input.shape
 
         def rows(t: torch.Tensor) -> torch.Tensor:
@@ -226,7 +239,7 @@ class Discriminator(nn.Module):
             # of the pixels, and the upsampling on the smaller channel count.
             upsample, conv1x1 = up[0], up[1]
             up_x = upsample(conv1x1(x))
-            x = block(up_x, skip) if isinstance(block, ResNetBlock) else block(torch.cat([up_x, skip], dim=1))
+            x = block(up_x, skip)                      # both block types read the concatenation [up_x | skip] in place
         return classification, self.final_mapping(x).unsqueeze(dim=2)
 
 
