@@ -68,15 +68,16 @@ int msg_profile_summary(msg_profile_entry* out, int max_entries);
  *   x0 = z * rsqrt(mean_k z^2 + eps);  x_{l+1} = lrelu(alpha * x_l W_l^T + bias_l) * gain
  * acts [depth, M, K] receives every layer's output (acts[depth-1] is the result; the rest is what the backward needs),
  * x0 [M, K] the normalised input.  `weights` / `biases`: HOST arrays of `depth` device pointers (biases or its entries
- * may be NULL).  K: multiple of 4, <= 512.  Backward: dW [depth, K, K], db [depth, K] (NULL: skipped) from gy [M, K];
- * the gradient w.r.t. z is not produced.  Deterministic. */
+ * may be NULL).  K: multiple of 4, <= 512.  Backward: dW [depth, K, K], db [depth, K] (NULL: skipped) from gy [M, K]
+ * in two launches (the sequential chain on one cluster, then all weight gradients on the whole chip); workspace:
+ * depth * M * K floats; the gradient w.r.t. z is not produced.  Deterministic. */
 int msg_style_mapping_supported(int depth, int K);
 int msg_style_mapping_forward(float* acts, float* x0, const float* z, const float* const* weights,
                               const float* const* biases, int depth, int M, int K, float alpha, float slope, float gain,
                               float eps, msg_stream_t stream);
 int msg_style_mapping_backward(float* dW, float* db, const float* gy, const float* acts, const float* x0,
                                const float* const* weights, const float* const* biases, int depth, int M, int K,
-                               float alpha, float slope, float gain, msg_stream_t stream);
+                               float alpha, float slope, float gain, float* workspace, msg_stream_t stream);
 
 /* A group of independent linears that read slices of ONE input [M, in_row] (the style linears `modulation_mapping` of all
  * ModulatedConv2d layers, multi_stylegan_generator.py:355-361, reading the per-layer latents) in one launch:

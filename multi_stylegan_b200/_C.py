@@ -575,10 +575,11 @@ def style_mapping_backward(gy: torch.Tensor, acts: torch.Tensor, x0: torch.Tenso
     ws = [w.contiguous() for w in weights]
     dW = torch.empty((L, K, K), device=gy.device, dtype=torch.float32)
     db = torch.zeros((L, K), device=gy.device, dtype=torch.float32)
+    work = torch.empty((L, M, K), device=gy.device, dtype=torch.float32)
     with _on_device(gy.device):
         rc = _lib.lib().msg_style_mapping_backward(_ptr(dW), _ptr(db), _ptr(gy), _ptr(acts), _ptr(x0), _ptr_array(ws),
                                                    _ptr_array(list(biases)), L, M, K, float(alpha), float(slope), float(gain),
-                                                   _stream(gy))
+                                                   _ptr(work), _stream(gy))
     _lib.check(rc, "style_mapping_backward")
     return dW, db
 

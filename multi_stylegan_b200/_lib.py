@@ -96,7 +96,7 @@ _SIGNATURES = {
                                              _c.c_float, _c.c_float, _c.c_void_p]),
     "msg_style_mapping_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                               _c.POINTER(_c.c_void_p), _c.POINTER(_c.c_void_p), _c.c_int, _c.c_int, _c.c_int,
-                                              _c.c_float, _c.c_float, _c.c_float, _c.c_void_p]),
+                                              _c.c_float, _c.c_float, _c.c_float, _c.c_void_p, _c.c_void_p]),
     "msg_linear_group_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.POINTER(LinearItem),
                                             _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "msg_linear_group_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
