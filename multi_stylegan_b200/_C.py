@@ -401,7 +401,8 @@ def cat2_supported(x: torch.Tensor, x2: torch.Tensor, stride=1) -> bool:
     engine, channels-last CUDA tensors, stride 1, both channel counts multiples of 32."""
     s = stride if isinstance(stride, int) else stride[0]
     return (conv_channels_last and conv_flags != _lib.CONV_FORCE_SIMT and x.is_cuda and x2.is_cuda and s == 1
-            and x.shape[1] % 32 == 0 and x2.shape[1] % 32 == 0 and x.dtype == torch.float32 and x2.dtype == torch.float32)
+            and x.shape[1] % 32 == 0 and x2.shape[1] % 32 == 0 and x.dtype == torch.float32 and x2.dtype == torch.float32
+            and tensor_core_path_available())
 
 
 def conv2d_dgrad(dy: torch.Tensor, w: torch.Tensor, in_hw: Sequence[int], stride=1, padding=0,
