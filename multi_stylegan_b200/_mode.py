@@ -9,23 +9,23 @@ discriminator's input gradient (loss.py:311-316), path length the generator's la
 (multi_stylegan_generator.py:193-200).  ModelWrapper and Generator.forward(return_path_length_grads=True) enter the
 context themselves."""
 
-_depth = 0
+import threading
+
+_tls = threading.local()        # the form is a property of the thread that records the forward pass
 
 
 class higher_order_gradients(object):
     def __enter__(self):
-        global _depth
-        _depth += 1
+        _tls.depth = getattr(_tls, "depth", 0) + 1
         return self
 
     def __exit__(self, *exc):
-        global _depth
-        _depth -= 1
+        _tls.depth -= 1
         return False
 
 
 def higher_order() -> bool:
-    return _depth > 0
+    return getattr(_tls, "depth", 0) > 0
 
 
 NO_DOUBLE_BACKWARD = ("multi_stylegan_b200: this fused Function is first-order only; record the forward inside "

@@ -33,10 +33,10 @@ def _inputs(rank):
     return noise, steps
 
 
-def _train(rank, dev, process_group=None):
+def _train(rank, dev, process_group=None, nets=None):
     from multi_stylegan_b200.model_wrapper import ModelWrapper
     hp = _hp()
-    G, D = build(dev, seed=0)
+    G, D = build(dev, seed=0) if nets is None else nets
     noise, steps = _inputs(rank)
     opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"])
     opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"])
@@ -97,11 +97,14 @@ def test_two_ranks_over_nccl_equal_one_gpu_with_per_group_statistics(built_libra
 
     ls = _Lockstep(WORLD)
     results, errors = [None] * WORLD, []
+    # the replicas are built one after the other in this thread: torch's global CPU generator (parameter init) is shared
+    # by all threads of a process
+    replicas = [build(torch.device("cuda", 0), seed=0) for _ in range(WORLD)]
 
     def run(rank):
         try:
             ls.local.rank = rank
-            results[rank] = _train(rank, torch.device("cuda", 0))
+            results[rank] = _train(rank, torch.device("cuda", 0), nets=replicas[rank])
         except BaseException as exc:            # a dead participant must not leave the other one in the barrier
             errors.append(exc)
             ls.barrier.abort()
