@@ -44,6 +44,15 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return (a - b).abs().max().item() / (denom if denom > 0 else 1.0)
 
 
+@pytest.fixture(autouse=True)
+def _restore_global_torch_flags():
+    """ModelWrapper switches torch.backends.cuda.matmul.allow_tf32 on for the process (the reference environment's
+    default); tests that compare library fp32 matmuls at 1e-5 must not inherit it from an earlier test."""
+    saved = torch.backends.cuda.matmul.allow_tf32
+    yield
+    torch.backends.cuda.matmul.allow_tf32 = saved
+
+
 @pytest.fixture()
 def oracle_backend(monkeypatch):
     """Swap the device ops for the CPU oracle so the *host logic* (autograd wiring, module tree,
