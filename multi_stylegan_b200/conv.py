@@ -264,6 +264,43 @@ class ResBlockFused(Function):
                 None, None, None, None, None, None)
 
 
+class DownscaleTapFused(Function):
+    """(conv(x) + bias, x): the strided convolution that leaves an encoder stage of the U-Net together with the skip
+    connection that taps the same tensor (u_net_2d_discriminator.py:76-83,100-104).  Forward: the bias lives in the conv
+    epilogue.  Backward (first order): the skip connection's gradient is the `add` operand of the convolution's dgrad, so
+    the sum of the two gradients of x never runs as a separate pass."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, padding, alpha, beta):
+        bs = None if b is None else b * beta
+        y = _C.conv2d_forward(x, w, stride, padding, alpha=alpha, bias=bs)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, padding, alpha, beta, b is not None)
+        ctx.set_materialize_grads(False)
+        return y, x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, gy, gskip):
+        from ._mode import NO_DOUBLE_BACKWARD
+        if torch.is_grad_enabled():
+            raise RuntimeError(NO_DOUBLE_BACKWARD)
+        x, w = ctx.saved_tensors
+        stride, padding, alpha, beta, has_b = ctx.cfg
+        need = ctx.needs_input_grad
+        if gy is None:
+            return gskip, None, None, None, None, None, None
+        if _C.conv_channels_last and gy.is_cuda:
+            gy = gy.contiguous(memory_format=torch.channels_last)
+        dx = _C.conv2d_dgrad(gy, w, tuple(x.shape[2:]), stride, padding, alpha=alpha, add=gskip) if need[0] else None
+        dw = _C.conv2d_wgrad(gy, x, tuple(w.shape[-2:]), stride, padding, False, alpha=alpha) if need[1] else None
+        db = gy.sum((0, 2, 3)) * beta if (has_b and need[2]) else None
+        return dx, dw, db, None, None, None, None
+
+
+def downscale_with_tap(x, w, b, stride, padding, alpha: float, beta: float):
+    return DownscaleTapFused.apply(x, w, b, _pair(stride), _pair(padding), float(alpha), float(beta))
+
+
 def res_block(x, x2, w1, b1, w2, b2, wr, a1: float, a2: float, ar: float, slope: float, g1: float, g2: float):
     return ResBlockFused.apply(x, x2, w1, b1, w2, b2, wr, float(a1), float(a2), float(ar), float(slope), float(g1), float(g2))
 

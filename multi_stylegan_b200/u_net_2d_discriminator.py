@@ -230,8 +230,17 @@ class Discriminator(nn.Module):
         for index, block in enumerate(self.encoder_blocks):
             x = block(x)
             if index != last:
-                features.append(x)
-                x = self.downscale_convolutions[index](x)
+                down, blur = self.downscale_convolutions[index][0], self.downscale_convolutions[index][1]
+                if not _mode.higher_order() and x.dtype == torch.float32:
+                    # strided conv + bias and the skip tap as one Function: bias in the conv epilogue, the skip gradient
+                    # summed in the conv's dgrad epilogue (conv.DownscaleTapFused)
+                    y, skip = conv.downscale_with_tap(x, down.weight, down.bias, down.stride, down.padding, down.scale,
+                                                      down.scale_bias)
+                    features.append(skip)
+                    x = blur(y)
+                else:
+                    features.append(x)
+                    x = blur(down(x))
         classification = self.classification_head(x)
         for block, up, skip in zip(self.decoder_blocks, self.transposed_convolutions, reversed(features)):
             # reference: conv1x1(Upsample(x)) (:87,:135-137).  A 1x1 convolution (per pixel, across channels) and the
