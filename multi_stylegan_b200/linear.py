@@ -79,7 +79,8 @@ def style_linears(x: torch.Tensor, specs: Sequence[Tuple[torch.Tensor, Optional[
                   ) -> List[torch.Tensor]:
     """x [M, R]; specs: (W [N, K], bias [N] or None, in_off, alpha, beta), items reading the same slice adjacent.
     Returns the outputs as contiguous views [M, N_i] of one flat buffer."""
-    key = tuple((W.data_ptr(), None if b is None else b.data_ptr(), int(o), float(a), float(be)) for W, b, o, a, be in specs)
+    key = tuple((W.data_ptr(), tuple(W.shape), None if b is None else b.data_ptr(), int(o), float(a), float(be))
+                for W, b, o, a, be in specs)
     group = _GROUPS.get(key)
     if group is None:
         if len(_GROUPS) > 64:
