@@ -118,6 +118,20 @@ int msg_nl_merge_unpool(float* dqkv, const float* dtheta, const float* dphi_p, c
 int msg_softmax_rows(float* x, int64_t rows, int n, msg_stream_t stream);
 int msg_softmax_rows_bwd(float* dp_inout, const float* p, int64_t rows, int n, msg_stream_t stream);
 
+/* Backward of msg_demod_factors (what autograd derives from multi_stylegan_generator.py:386-388): from gd = dL/dd [B,O]
+ *   ds [B,C] (NULL: skipped; needs wsq) and dW [O,C,taps] = W * 2 sum_b q[b,o] s[b,c]^2 (NULL: skipped; needs W),
+ *   q = gd * d^3 * (-scale^2 / 2).  B <= 64. */
+int msg_demod_factors_bwd(float* dW, float* ds, const float* gd, const float* d, const float* s, const float* wsq,
+                          const float* W, int B, int O, int C, int taps, float scale, msg_stream_t stream);
+
+/* Deterministic reductions over channels-last activations: out[c] = scale * sum_r x[r,c] for a dense [rows, C] matrix (the
+ * bias gradient of a convolution without activation, equalized_layer.py:70-73; C % 4 == 0), and out[0] = scale * <a, b>
+ * (n % 4 == 0; the gradient of the non-local block's gamma, u_net_2d_discriminator.py:381).  msg_dot workspace: 4096 floats. */
+size_t msg_colsum_workspace(int64_t rows, int C);
+int msg_colsum_nhwc(float* out, const float* x, int64_t rows, int C, float scale, void* workspace, size_t workspace_bytes,
+                    msg_stream_t stream);
+int msg_dot(float* out, const float* a, const float* b, int64_t n, float scale, float* workspace, msg_stream_t stream);
+
 /* Roofline probe (bench.py): one launch of `iters` x 4 back-to-back tcgen05.mma.kind::tf32 (128 x 256 x 8, operands in
  * shared memory, one CTA per SM); *flops receives the FLOPs of the launch.  sink: >= 32 * #SMs floats or NULL. */
 int msg_tf32_mma_rate_probe(int iters, float* sink, double* flops, msg_stream_t stream);

@@ -707,6 +707,49 @@ def softmax_rows_bwd_(dp: torch.Tensor, p: torch.Tensor, n: int) -> torch.Tensor
     return dp
 
 
+def demod_factors_bwd(gd: torch.Tensor, d: torch.Tensor, s: torch.Tensor, wsq: torch.Tensor, W: torch.Tensor, scale: float,
+                      need_w: bool = True, need_s: bool = True):
+    """(dW [O,C,kh,kw] or None, ds [B,C] or None) of demod_factors."""
+    gd, d, s = gd.contiguous(), d.contiguous(), s.contiguous()
+    W = W.contiguous()
+    O, C = wsq.shape
+    B = s.shape[0]
+    taps = W.numel() // (O * C)
+    dW = torch.empty_like(W) if need_w else None
+    ds = torch.empty_like(s) if need_s else None
+    with _on_device(W.device):
+        rc = _lib.lib().msg_demod_factors_bwd(_ptr(dW), _ptr(ds), _ptr(gd), _ptr(d), _ptr(s), _ptr(wsq), _ptr(W), B, O, C, taps,
+                                              float(scale), _stream(W))
+    _lib.check(rc, "demod_factors_bwd")
+    return dW, ds
+
+
+def colsum_cl(x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """sum over (batch, height, width) of a channels-last [B, C, H, W] activation, times scale -> [C]; deterministic."""
+    x = x.contiguous(memory_format=torch.channels_last)
+    B, C, H, W = x.shape
+    out = torch.empty(C, device=x.device, dtype=torch.float32)
+    L = _lib.lib()
+    with _on_device(x.device):
+        nbytes = L.msg_colsum_workspace(B * H * W, C)
+        ws, wsp = _workspace(nbytes, x.device)
+        rc = L.msg_colsum_nhwc(_ptr(out), _ptr(x), B * H * W, C, float(scale), wsp, nbytes, _stream(x))
+    _lib.check(rc, "colsum_nhwc")
+    return out
+
+
+def dot(a: torch.Tensor, b: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """scale * sum(a * b) for two dense tensors with the same memory layout -> [1]; deterministic."""
+    if a.shape != b.shape or a.stride() != b.stride():
+        raise RuntimeError("dot: operands must share shape and strides")
+    out = torch.empty(1, device=a.device, dtype=torch.float32)
+    work = torch.empty(4096, device=a.device, dtype=torch.float32)
+    with _on_device(a.device):
+        rc = _lib.lib().msg_dot(_ptr(out), _ptr(a), _ptr(b), a.numel(), float(scale), _ptr(work), _stream(a))
+    _lib.check(rc, "dot")
+    return out
+
+
 def tf32_mma_rate_probe(iters: int, device) -> float:
     """Launch the tensor-core issue-rate probe (csrc/mma_rate.cu) on torch's current stream; returns its FLOPs."""
     flops = ctypes.c_double(0.0)

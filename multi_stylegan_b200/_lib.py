@@ -108,6 +108,12 @@ _SIGNATURES = {
                                        _c.c_int, _c.c_int, _c.c_int, _c.c_void_p]),
     "msg_softmax_rows": (_c.c_int, [_c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p]),
     "msg_softmax_rows_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p]),
+    "msg_demod_factors_bwd": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                         _c.c_void_p, _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_float, _c.c_void_p]),
+    "msg_colsum_workspace": (_c.c_size_t, [_c.c_int64, _c.c_int]),
+    "msg_colsum_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float, _c.c_void_p, _c.c_size_t,
+                                   _c.c_void_p]),
+    "msg_dot": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_float, _c.c_void_p, _c.c_void_p]),
     "msg_tf32_mma_rate_probe": (_c.c_int, [_c.c_int, _c.c_void_p, _c.POINTER(_c.c_double), _c.c_void_p]),
     "msg_fused_bias_act": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                       _c.c_double, _c.c_double, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int,

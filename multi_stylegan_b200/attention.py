@@ -65,11 +65,11 @@ class NonLocalFused(Function):
         hw = tuple(x.shape[2:])
         B = x.shape[0]
         nk = phi.shape[2] * phi.shape[3]
-        d_gamma = ((gout * o).sum() * j).reshape(gamma.shape) if need[7] else None
-        go = gout * (gamma.detach() * j)
-        datt = _C.conv2d_dgrad(go, w_o, hw, 1, 0, alpha=a_o)
-        dw_o = _C.conv2d_wgrad(go, att, (1, 1), 1, 0, False, alpha=a_o) if need[5] else None
-        del go
+        d_gamma = _C.dot(gout, o, j).reshape(gamma.shape) if need[7] else None
+        # gamma / sqrt(2) is a device scalar: it multiplies the (half as wide) results instead of the incoming gradient
+        gj = gamma.detach() * j
+        datt = _C.conv2d_dgrad(gout, w_o, hw, 1, 0, alpha=a_o) * gj
+        dw_o = _C.conv2d_wgrad(gout, att, (1, 1), 1, 0, False, alpha=a_o) * gj if need[5] else None
         dP = _C.conv2d_forward(datt, _as_filters(g), 1, 0)                          # [B, nk, H, W]
         dg = _C.conv2d_wgrad(datt, P, (1, 1), 1, 0, True, w_transposed=True)        # [B, nk, cv, 1, 1]
         _C.softmax_rows_bwd_(dP, P, nk)                                             # dP <- dS

@@ -293,7 +293,7 @@ class DownscaleTapFused(Function):
             gy = gy.contiguous(memory_format=torch.channels_last)
         dx = _C.conv2d_dgrad(gy, w, tuple(x.shape[2:]), stride, padding, alpha=alpha, add=gskip) if need[0] else None
         dw = _C.conv2d_wgrad(gy, x, tuple(w.shape[-2:]), stride, padding, False, alpha=alpha) if need[1] else None
-        db = gy.sum((0, 2, 3)) * beta if (has_b and need[2]) else None
+        db = _C.colsum_cl(gy, beta) if (has_b and need[2]) else None
         return dx, dw, db, None, None, None, None
 
 

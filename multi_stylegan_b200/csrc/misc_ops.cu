@@ -320,3 +320,110 @@ extern "C" int msg_affine_warp_bwd(float* dx, const float* g, const float* theta
   MSG_CHECK_LAUNCH("affine_warp_bwd");
   return MSG_OK;
 }
+
+// ---- deterministic reductions over channels-last activations --------------------------------------------------------------
+namespace msg {
+
+// partial[blockIdx.y][c] = sum of x[r][c] over this block's rows; block = 32 float4 columns x 8 row lanes
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(float4* __restrict__ partial, const float4* __restrict__ x, int64_t rows, int C4, int64_t rows_per_block) {
+  __shared__ float4 sm[8][32];
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  int64_t r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C4)
+    for (int64_t r = r0 + rl; r < r1; r += 8) {
+      const float4 v = __ldg(x + r * C4 + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  sm[rl][cl] = acc;
+  __syncthreads();
+  if (rl == 0 && c < C4) {
+    float4 t = sm[0][cl];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { t.x += sm[j][cl].x; t.y += sm[j][cl].y; t.z += sm[j][cl].z; t.w += sm[j][cl].w; }
+    partial[(int64_t)blockIdx.y * C4 + c] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(float* __restrict__ out, const float* __restrict__ partial, int nblocks, int C, float scale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float t = 0.f;
+  for (int j = 0; j < nblocks; ++j) t += partial[(int64_t)j * C + c];
+  out[c] = t * scale;
+}
+
+__global__ void __launch_bounds__(256)
+dot_partial_kernel(float* __restrict__ partial, const float4* __restrict__ a, const float4* __restrict__ b, int64_t n4) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 u = __ldg(a + i), v = __ldg(b + i);
+    acc += (u.x * v.x + u.y * v.y) + (u.z * v.z + u.w * v.w);
+  }
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+dot_final_kernel(float* __restrict__ out, const float* __restrict__ partial, int n, float scale) {
+  __shared__ float sm[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) out[0] = acc * scale;
+}
+
+}  // namespace msg
+
+// out[c] = scale * sum_r x[r, c] for a dense [rows, C] matrix (a channels-last activation: rows = B*H*W): the bias gradient
+// of a convolution without activation (equalized_layer.py:70-73).  workspace: msg_colsum_workspace(rows, C) bytes.
+extern "C" size_t msg_colsum_workspace(int64_t rows, int C) {
+  (void)rows;
+  return (size_t)4 * msg::num_sms() * (size_t)((C + 3) / 4 * 4) * sizeof(float) + 256;
+}
+
+extern "C" int msg_colsum_nhwc(float* out, const float* x, int64_t rows, int C, float scale, void* workspace,
+                               size_t workspace_bytes, msg_stream_t stream) {
+  using namespace msg;
+  if (rows < 0 || C < 4 || C % 4) return fail(MSG_ERR_UNSUPPORTED, "colsum_nhwc: C must be a positive multiple of 4");
+  if (!out || (rows > 0 && !x) || (reinterpret_cast<uintptr_t>(x) & 15u)) return fail(MSG_ERR_BAD_ARG, "colsum_nhwc: null or unaligned pointer");
+  if (!workspace || workspace_bytes < msg_colsum_workspace(rows, C)) return fail(MSG_ERR_WORKSPACE, "colsum_nhwc: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  const int C4 = C / 4;
+  const int gx = (int)ceil_div(C4, 32);
+  int64_t nb = ceil_div((int64_t)4 * num_sms(), gx);
+  if (nb > ceil_div(rows, 8)) nb = ceil_div(rows, 8);
+  if (nb < 1) nb = 1;
+  const int64_t rpb = ceil_div(rows > 0 ? rows : 1, nb);
+  nb = ceil_div(rows > 0 ? rows : 1, rpb);
+  colsum_partial_kernel<<<dim3((unsigned)gx, (unsigned)nb), 256, 0, st>>>(reinterpret_cast<float4*>(partial),
+                                                                        reinterpret_cast<const float4*>(x), rows, C4, rpb);
+  MSG_CHECK_LAUNCH("colsum_nhwc(partial)");
+  colsum_final_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(out, partial, (int)nb, C, scale);
+  MSG_CHECK_LAUNCH("colsum_nhwc");
+  return MSG_OK;
+}
+
+// out[0] = scale * <a, b> over n floats (n % 4 == 0, 16-byte aligned); deterministic two-stage sum.  workspace: 4096 floats.
+extern "C" int msg_dot(float* out, const float* a, const float* b, int64_t n, float scale, float* workspace, msg_stream_t stream) {
+  using namespace msg;
+  if (n < 0 || n % 4) return fail(MSG_ERR_UNSUPPORTED, "dot: n must be a multiple of 4");
+  if (!out || !workspace || (n > 0 && (!a || !b)) || ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15u))
+    return fail(MSG_ERR_BAD_ARG, "dot: null or unaligned pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = ceil_div(n / 4 > 0 ? n / 4 : 1, 256 * 8);
+  if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+  if (blocks > 4096) blocks = 4096;
+  dot_partial_kernel<<<(unsigned)blocks, 256, 0, st>>>(workspace, reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(b), n / 4);
+  MSG_CHECK_LAUNCH("dot(partial)");
+  dot_final_kernel<<<1, 256, 0, st>>>(out, workspace, (int)blocks, scale);
+  MSG_CHECK_LAUNCH("dot");
+  return MSG_OK;
+}

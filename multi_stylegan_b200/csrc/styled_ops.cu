@@ -222,6 +222,95 @@ extern "C" int msg_styled_act_bwd(float* g_pre, float* sums, const float* g_out,
   return MSG_OK;
 }
 
+// Backward of the demodulation factor d[b,o] = rsqrt(scale^2 sum_c s[b,c]^2 wsq[o,c] + 1e-8) (multi_stylegan_generator.py:386-388):
+//   q[b,o]   = gd[b,o] * d[b,o]^3 * (-scale^2 / 2)
+//   ds[b,c]  = 2 s[b,c] * sum_o q[b,o] wsq[o,c]
+//   dW[o,c,t] = W[o,c,t] * 2 sum_b q[b,o] s[b,c]^2
+// Two launches instead of autograd's chain of small [B,C] / [O,C] ATen kernels.  B <= 64.
+constexpr int kDemodMaxB = 64;
+
+// block = (32 consecutive c) x 8 o-slices: ds[b, c] for all b
+__global__ void __launch_bounds__(256)
+demod_bwd_ds_kernel(float* __restrict__ ds, const float* __restrict__ gd, const float* __restrict__ d,
+                    const float* __restrict__ s, const float* __restrict__ wsq, int B, int O, int C, float k) {
+  extern __shared__ float sm[];                        // q [B][O], then the partial sums [8][B][32]
+  float* q = sm;
+  float* part = sm + (size_t)B * O;
+  for (int i = threadIdx.x; i < B * O; i += 256) { const float dv = __ldg(d + i); q[i] = __ldg(gd + i) * dv * dv * dv * k; }
+  __syncthreads();
+  const int cl = threadIdx.x & 31, os = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float acc[kDemodMaxB];
+#pragma unroll
+  for (int b = 0; b < kDemodMaxB; ++b) acc[b] = 0.f;
+  if (c < C) {
+    for (int o = os; o < O; o += 8) {
+      const float w = __ldg(wsq + (int64_t)o * C + c);
+#pragma unroll
+      for (int b = 0; b < kDemodMaxB; ++b)
+        if (b < B) acc[b] = fmaf(q[b * O + o], w, acc[b]);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < kDemodMaxB; ++b)
+    if (b < B) part[(os * B + b) * 32 + cl] = acc[b];
+  __syncthreads();
+  for (int i = threadIdx.x; i < B * 32; i += 256) {
+    const int b = i >> 5, cc = blockIdx.x * 32 + (i & 31);
+    if (cc < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += part[(j * B + b) * 32 + (i & 31)];
+      ds[(int64_t)b * C + cc] = 2.f * __ldg(s + (int64_t)b * C + cc) * t;
+    }
+  }
+}
+
+// thread = one (o, c): coef = 2 sum_b q[b,o] s[b,c]^2, dW[o,c,:] = W[o,c,:] * coef
+__global__ void __launch_bounds__(256)
+demod_bwd_dw_kernel(float* __restrict__ dW, const float* __restrict__ W, const float* __restrict__ gd,
+                    const float* __restrict__ d, const float* __restrict__ s, int B, int O, int C, int taps, float k) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)O * C) return;
+  const int o = (int)(i / C), c = (int)(i - (int64_t)o * C);
+  float coef = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float dv = __ldg(d + (int64_t)b * O + o), sv = __ldg(s + (int64_t)b * C + c);
+    coef = fmaf(__ldg(gd + (int64_t)b * O + o) * dv * dv * dv * k, sv * sv, coef);
+  }
+  coef *= 2.f;
+  const float* w = W + i * taps;
+  float* g = dW + i * taps;
+  for (int t = 0; t < taps; ++t) g[t] = __ldg(w + t) * coef;
+}
+
+extern "C" int msg_demod_factors_bwd(float* dW, float* ds, const float* gd, const float* d, const float* s, const float* wsq,
+                                     const float* W, int B, int O, int C, int taps, float scale, msg_stream_t stream) {
+  if (B < 1 || B > kDemodMaxB || O <= 0 || C <= 0 || taps <= 0) return fail(MSG_ERR_UNSUPPORTED, "demod_factors_bwd: sizes (B <= %d)", kDemodMaxB);
+  if (!gd || !d || !s) return fail(MSG_ERR_BAD_ARG, "demod_factors_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float k = -0.5f * scale * scale;
+  if (ds) {
+    if (!wsq) return fail(MSG_ERR_BAD_ARG, "demod_factors_bwd: ds needs wsq");
+    const size_t smem = ((size_t)B * O + (size_t)8 * B * 32) * sizeof(float);
+    if (smem > 200 * 1024) return fail(MSG_ERR_UNSUPPORTED, "demod_factors_bwd: B * O too large");
+    static bool attr_done[64] = {};
+    const int slot = current_device_slot();
+    if (!attr_done[slot]) {
+      MSG_CHECK_CUDA(cudaFuncSetAttribute(demod_bwd_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done[slot] = true;
+    }
+    demod_bwd_ds_kernel<<<(unsigned)ceil_div(C, 32), 256, smem, st>>>(ds, gd, d, s, wsq, B, O, C, k);
+    MSG_CHECK_LAUNCH("demod_factors_bwd(style)");
+  }
+  if (dW) {
+    if (!W) return fail(MSG_ERR_BAD_ARG, "demod_factors_bwd: dW needs W");
+    demod_bwd_dw_kernel<<<(unsigned)ceil_div((int64_t)O * C, 256), 256, 0, st>>>(dW, W, gd, d, s, B, O, C, taps, k);
+    MSG_CHECK_LAUNCH("demod_factors_bwd(weights)");
+  }
+  return MSG_OK;
+}
+
 extern "C" int msg_demod_factors(float* d, float* wsq, const float* W, const float* s, int B, int O, int C, int taps,
                                  float scale, msg_stream_t stream) {
   if (B < 0 || O <= 0 || C <= 0 || taps <= 0) return fail(MSG_ERR_BAD_ARG, "demod_factors: bad sizes");

@@ -43,12 +43,8 @@ class DemodFactors(Function):
     def backward(ctx, gd):
         _check_first_order()
         W, s, d, wsq = ctx.saved_tensors
-        q = gd * d * d * d * (-0.5 * ctx.scale * ctx.scale)            # dL/d(sum) * scale^2      [B, O]
-        dW = ds = None
-        if ctx.needs_input_grad[1]:
-            ds = 2.0 * s * torch.mm(q, wsq)
-        if ctx.needs_input_grad[0]:
-            dW = W * (2.0 * torch.mm(q.t(), s * s)).view(W.shape[0], W.shape[1], 1, 1)
+        # q = gd * d^3 * (-scale^2 / 2);  ds = 2 s (q wsq);  dW = W * 2 (q^T s^2)  — two launches (msg_demod_factors_bwd)
+        dW, ds = _C.demod_factors_bwd(gd, d, s, wsq, W, ctx.scale, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
         return dW, ds, None
 
 

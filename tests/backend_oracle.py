@@ -6,7 +6,8 @@ from oracle import ops
 
 __all__ = ["fused_bias_act", "fused_bias_act_bwd", "upfirdn2d", "conv2d_forward", "conv2d_dgrad", "conv2d_wgrad",
            "modulate_weights", "noise_bias_act", "affine_warp", "noise_bias_act_cl", "noise_bias_act_cl_bwd", "modulate_weights_bwd", "blur_noise_bias_act", "affine_warp_bwd",
-           "demod_factors", "styled_act_bwd", "blur_noise_bias_act_mod", "conv2d_dgrad_act_bwd"]
+           "demod_factors", "styled_act_bwd", "blur_noise_bias_act_mod", "conv2d_dgrad_act_bwd",
+           "demod_factors_bwd", "colsum_cl", "dot"]
 
 
 def fused_bias_act(input, bias, refer, act, grad, alpha, scale):
@@ -146,3 +147,18 @@ def blur_noise_bias_act_mod(x, kernel, pad, col_scale, noise, noise_w, bias, slo
         y = y * col_scale.reshape(-1, C, 1, 1)
     out = ops.noise_bias_act_masked(y, None, noise, noise_w, bias, slope, gain)
     return out, (None if out2_scale is None else out * out2_scale.reshape(-1, C, 1, 1))
+
+
+def demod_factors_bwd(gd, d, s, wsq, W, scale, need_w=True, need_s=True):
+    q = gd * d * d * d * (-0.5 * scale * scale)
+    ds = 2.0 * s * torch.mm(q, wsq) if need_s else None
+    dW = W * (2.0 * torch.mm(q.t(), s * s)).view(W.shape[0], W.shape[1], 1, 1) if need_w else None
+    return dW, ds
+
+
+def colsum_cl(x, scale=1.0):
+    return x.sum((0, 2, 3)) * scale
+
+
+def dot(a, b, scale=1.0):
+    return ((a * b).sum() * scale).reshape(1)

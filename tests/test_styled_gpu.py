@@ -235,3 +235,32 @@ def test_dgrad_accumulate_operand(built_library, shape, engine):
     finally:
         _C.conv_flags = old
     assert rel_err(got, want) < (1e-2 if engine == "tc" else 1e-4), rel_err(got, want)
+
+
+def test_demod_backward_colsum_and_dot_kernels(built_library):
+    """msg_demod_factors_bwd / msg_colsum_nhwc / msg_dot against the tensor-op formulas autograd used before them."""
+    from multi_stylegan_b200 import _C
+    from tests import backend_oracle
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(4)
+    for B, O, C, k in ((8, 512, 512, 3), (3, 12, 20, 1), (16, 64, 96, 2)):
+        W = torch.randn(O, C, k, k, generator=g)
+        s = torch.randn(B, C, generator=g)
+        gd = torch.randn(B, O, generator=g)
+        scale = 1.0 / (C * k * k) ** 0.5
+        d, wsq = backend_oracle.demod_factors(W, s, scale)
+        want_w, want_s = backend_oracle.demod_factors_bwd(gd, d, s, wsq, W, scale)
+        got_w, got_s = _C.demod_factors_bwd(gd.to(dev), d.to(dev), s.to(dev), wsq.to(dev), W.to(dev), scale)
+        assert rel_err(got_w, want_w) < 1e-5 and rel_err(got_s, want_s) < 1e-5
+        only_s = _C.demod_factors_bwd(gd.to(dev), d.to(dev), s.to(dev), wsq.to(dev), W.to(dev), scale, need_w=False)
+        assert only_s[0] is None and torch.equal(only_s[1], got_s)
+    for shape in ((16, 128, 127, 127), (2, 4, 3, 5), (1, 36, 1, 1)):
+        x = torch.randn(shape, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+        got = _C.colsum_cl(x, 0.5)
+        want = x.double().sum((0, 2, 3)) * 0.5
+        assert ((got.double() - want).abs().max() / want.abs().max().clamp_min(1e-6)) < 1e-5
+        assert torch.equal(got, _C.colsum_cl(x, 0.5))
+        y = torch.randn(shape, generator=g).to(dev).contiguous(memory_format=torch.channels_last)
+        got = _C.dot(x, y, 2.0)
+        want = (x.double() * y.double()).sum() * 2.0
+        assert abs(float(got) - float(want)) < 1e-4 * (x.double() * y.double()).abs().sum().item()
