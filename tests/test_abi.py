@@ -74,6 +74,38 @@ def test_argument_validation_without_device(built_library):
     assert rc == _lib.MSG_ERR_BAD_ARG
 
 
+def test_argument_validation_of_the_round_2_entries(built_library):
+    """Error paths that return before any CUDA call: sizes the kernels do not take, null pointers, empty inputs."""
+    from multi_stylegan_b200 import _lib
+    L = built_library
+    assert L.msg_softmax_rows(None, 4, 6, None) == _lib.MSG_ERR_UNSUPPORTED            # row length not a multiple of 4
+    assert L.msg_softmax_rows(None, 4, 8192, None) == _lib.MSG_ERR_UNSUPPORTED         # longer than a warp keeps in registers
+    assert L.msg_softmax_rows(None, 0, 1024, None) == _lib.MSG_OK                      # no rows
+    assert L.msg_softmax_rows(None, 4, 1024, None) == _lib.MSG_ERR_BAD_ARG             # null pointer
+    assert L.msg_softmax_rows_bwd(None, None, 4, 1024, None) == _lib.MSG_ERR_BAD_ARG
+    assert L.msg_nl_split_pool(None, None, None, None, None, 1, 8, 8, 6, 8, None) == _lib.MSG_ERR_BAD_ARG     # cq % 4 != 0
+    assert L.msg_nl_split_pool(None, None, None, None, None, 0, 8, 8, 8, 8, None) == _lib.MSG_OK              # empty batch
+    assert L.msg_nl_merge_unpool(None, None, None, None, None, 1, 8, 8, 8, 8, None) == _lib.MSG_ERR_BAD_ARG
+    assert L.msg_style_mapping_supported(8, 512) == 1 and L.msg_style_mapping_supported(8, 1024) == 0
+    assert L.msg_style_mapping_supported(0, 512) == 0 and L.msg_style_mapping_supported(8, 510) == 0
+    assert L.msg_style_mapping_forward(None, None, None, None, None, 8, 4, 1024, 1.0, 0.2, 1.0, 1e-8, None) == _lib.MSG_ERR_UNSUPPORTED
+    assert L.msg_style_mapping_forward(None, None, None, None, None, 8, 4, 512, 1.0, 0.2, 1.0, 1e-8, None) == _lib.MSG_ERR_BAD_ARG
+    assert L.msg_linear_group_forward(None, None, 512, None, 0, 8, 512, 512, None) == _lib.MSG_ERR_BAD_ARG
+    item = (_lib.LinearItem * 1)()
+    item[0].W, item[0].N, item[0].K = 16, 8, 6                                          # K not a multiple of 4
+    assert L.msg_linear_group_forward(None, None, 512, item, 1, 8, 8, 8, None) == _lib.MSG_ERR_BAD_ARG
+    assert L.msg_colsum_nhwc(None, None, 10, 6, 1.0, None, 0, None) == _lib.MSG_ERR_UNSUPPORTED
+    assert L.msg_dot(None, None, None, 6, 1.0, None, None) == _lib.MSG_ERR_UNSUPPORTED
+    assert L.msg_demod_factors_bwd(None, None, None, None, None, None, None, 100, 4, 4, 9, 1.0, None) == _lib.MSG_ERR_UNSUPPORTED
+    d = _lib.ConvDesc()
+    d.B, d.C, d.H, d.W, d.O, d.kh, d.kw = 1, 64, 8, 8, 64, 3, 3
+    d.stride_h = d.stride_w = 1
+    d.pad_h = d.pad_w = 1
+    d.OH = d.OW = 8
+    assert L.msg_conv2d_dgrad_mask(None, None, None, None, ctypes.byref(d), 1.0, None, 0.2, 1.0, None, 0, 0, None) == _lib.MSG_ERR_BAD_ARG
+    assert L.msg_conv2d_dgrad_mask_supported(ctypes.byref(d), 0) in (0, 1)             # (0 without a device)
+
+
 def test_product_refuses_cpu_tensors(built_library):
     """No CPU fallback anywhere on the product path."""
     from multi_stylegan_b200.op_static import fused_leaky_relu, upfirdn2d
