@@ -132,6 +132,16 @@ int msg_colsum_nhwc(float* out, const float* x, int64_t rows, int C, float scale
                     msg_stream_t stream);
 int msg_dot(float* out, const float* a, const float* b, int64_t n, float scale, float* workspace, msg_stream_t stream);
 
+/* MinibatchStdDev (u_net_2d_discriminator.py:189-217), channels-last: out [B, HW, C+1] = cat(x [B, HW, C], plane) with
+ * plane[b] = mean over (c, pos) of sqrt(max(var over b's sub-batch, alpha)); the batch is `groups` sub-batches of B / groups
+ * consecutive samples (groups = 1: the reference; 2: the real and fake halves of one batched discriminator pass).
+ * Backward: gx = gout[..., :C] + the plane's gradient through the standard deviation.  Deterministic. */
+size_t msg_mbstd_workspace(int groups);
+int msg_mbstd_forward(float* out, const float* x, int B, int C, int64_t HW, int groups, float alpha, void* workspace,
+                      size_t workspace_bytes, msg_stream_t stream);
+int msg_mbstd_backward(float* gx, const float* gout, const float* x, int B, int C, int64_t HW, int groups, float alpha,
+                       void* workspace, size_t workspace_bytes, msg_stream_t stream);
+
 /* Roofline probe (bench.py): one launch of `iters` x 4 back-to-back tcgen05.mma.kind::tf32 (128 x 256 x 8, operands in
  * shared memory, one CTA per SM); *flops receives the FLOPs of the launch.  sink: >= 32 * #SMs floats or NULL. */
 int msg_tf32_mma_rate_probe(int iters, float* sink, double* flops, msg_stream_t stream);

@@ -750,6 +750,35 @@ def dot(a: torch.Tensor, b: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
     return out
 
 
+def mbstd_forward(x: torch.Tensor, groups: int, alpha: float) -> torch.Tensor:
+    """cat(x, minibatch-stddev plane) for a channels-last [B, C, H, W] activation -> [B, C+1, H, W] channels-last."""
+    _check_f32(x, "x")
+    x = x.contiguous(memory_format=torch.channels_last)
+    B, C, H, W = x.shape
+    out = _cl_empty(B, C + 1, H, W, x.device)
+    L = _lib.lib()
+    with _on_device(x.device):
+        nbytes = L.msg_mbstd_workspace(int(groups))
+        ws, wsp = _workspace(nbytes, x.device)
+        rc = L.msg_mbstd_forward(_ptr(out), _ptr(x), B, C, H * W, int(groups), float(alpha), wsp, nbytes, _stream(x))
+    _lib.check(rc, "mbstd_forward")
+    return out
+
+
+def mbstd_backward(gout: torch.Tensor, x: torch.Tensor, groups: int, alpha: float) -> torch.Tensor:
+    gout = gout.contiguous(memory_format=torch.channels_last)
+    x = x.contiguous(memory_format=torch.channels_last)
+    B, C, H, W = x.shape
+    gx = _cl_empty(B, C, H, W, x.device)
+    L = _lib.lib()
+    with _on_device(x.device):
+        nbytes = L.msg_mbstd_workspace(int(groups))
+        ws, wsp = _workspace(nbytes, x.device)
+        rc = L.msg_mbstd_backward(_ptr(gx), _ptr(gout), _ptr(x), B, C, H * W, int(groups), float(alpha), wsp, nbytes, _stream(x))
+    _lib.check(rc, "mbstd_backward")
+    return gx
+
+
 def tf32_mma_rate_probe(iters: int, device) -> float:
     """Launch the tensor-core issue-rate probe (csrc/mma_rate.cu) on torch's current stream; returns its FLOPs."""
     flops = ctypes.c_double(0.0)

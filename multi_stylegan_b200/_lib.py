@@ -114,6 +114,11 @@ _SIGNATURES = {
     "msg_colsum_nhwc": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_float, _c.c_void_p, _c.c_size_t,
                                    _c.c_void_p]),
     "msg_dot": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int64, _c.c_float, _c.c_void_p, _c.c_void_p]),
+    "msg_mbstd_workspace": (_c.c_size_t, [_c.c_int]),
+    "msg_mbstd_forward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int, _c.c_float,
+                                     _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "msg_mbstd_backward": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int, _c.c_int64, _c.c_int,
+                                      _c.c_float, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "msg_tf32_mma_rate_probe": (_c.c_int, [_c.c_int, _c.c_void_p, _c.POINTER(_c.c_double), _c.c_void_p]),
     "msg_fused_bias_act": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int, _c.c_int,
                                       _c.c_double, _c.c_double, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int,

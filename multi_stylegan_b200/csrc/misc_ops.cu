@@ -427,3 +427,160 @@ extern "C" int msg_dot(float* out, const float* a, const float* b, int64_t n, fl
   MSG_CHECK_LAUNCH("dot");
   return MSG_OK;
 }
+
+// ---- MinibatchStdDev (u_net_2d_discriminator.py:189-217) ---------------------------------------------------------------
+// out = cat(x, plane): plane[b] = mean over (c,h,w) of sqrt(max(var over the sub-batch of b at that position, alpha)); the
+// batch is G independent sub-batches of B / G consecutive samples.  Channels-last: x [B][HW][C], out [B][HW][C + 1].
+namespace msg {
+
+struct MbStdParams {
+  const float* x;
+  float* out;            // forward: [B][HW][C+1]
+  const float* gout;     // backward: [B][HW][C+1]
+  float* gx;             // backward: [B][HW][C]
+  float* partial;        // [G][nblk]
+  float* stats;          // [G] plane values (forward) / sums of the plane's gradient (backward)
+  int B, C, G, nblk;
+  int64_t HW;
+  float alpha;
+};
+
+__global__ void __launch_bounds__(256)
+mbstd_partial_kernel(const MbStdParams p) {
+  __shared__ float sm[32];
+  const int g = blockIdx.y, Bg = p.B / p.G;
+  const int64_t n = p.HW * p.C;
+  const float* xg = p.x + (int64_t)g * Bg * n;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float mean = 0.f;
+    for (int m = 0; m < Bg; ++m) mean += __ldg(xg + (int64_t)m * n + i);
+    mean /= (float)Bg;
+    float var = 0.f;
+    for (int m = 0; m < Bg; ++m) { const float d = __ldg(xg + (int64_t)m * n + i) - mean; var = fmaf(d, d, var); }
+    acc += sqrtf(fmaxf(var / (float)Bg, p.alpha));
+  }
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) p.partial[g * p.nblk + blockIdx.x] = acc;
+}
+
+// stats[g] = scale * sum of the group's partials (fixed order)
+__global__ void mbstd_final_kernel(float* __restrict__ stats, const float* __restrict__ partial, int nblk, float scale) {
+  const int g = blockIdx.x;
+  __shared__ float sm[32];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < nblk; i += blockDim.x) acc += partial[g * nblk + i];
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) stats[g] = acc * scale;
+}
+
+__global__ void __launch_bounds__(256)
+mbstd_write_kernel(const MbStdParams p) {
+  const int C1 = p.C + 1, Bg = p.B / p.G;
+  const int64_t total = (int64_t)p.B * p.HW * C1;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C1);
+    const int64_t row = i / C1;                       // b * HW + pos
+    p.out[i] = c < p.C ? __ldg(p.x + row * p.C + c) : __ldg(p.stats + (int)(row / p.HW) / Bg);
+  }
+}
+
+// partial[g][blk] = sum over the group's (b, pos) of gout[b][pos][C]
+__global__ void __launch_bounds__(256)
+mbstd_gplane_partial_kernel(const MbStdParams p) {
+  __shared__ float sm[32];
+  const int g = blockIdx.y, Bg = p.B / p.G, C1 = p.C + 1;
+  const int64_t n = (int64_t)Bg * p.HW;
+  const float* gg = p.gout + (int64_t)g * n * C1 + p.C;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) acc += __ldg(gg + i * C1);
+  acc = block_sum(acc, sm);
+  if (threadIdx.x == 0) p.partial[g * p.nblk + blockIdx.x] = acc;
+}
+
+// gx[b][pos][c] = gout[b][pos][c] + stats[g] / (HW * C) * (x - mean) / (Bg * std_pos)   (0 where the variance was clamped)
+__global__ void __launch_bounds__(256)
+mbstd_backward_kernel(const MbStdParams p) {
+  const int g = blockIdx.y, Bg = p.B / p.G, C1 = p.C + 1;
+  const int64_t n = p.HW * p.C;
+  const float* xg = p.x + (int64_t)g * Bg * n;
+  const float gs = __ldg(p.stats + g) / ((float)n * (float)Bg);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float mean = 0.f;
+    for (int m = 0; m < Bg; ++m) mean += __ldg(xg + (int64_t)m * n + i);
+    mean /= (float)Bg;
+    float var = 0.f;
+    for (int m = 0; m < Bg; ++m) { const float d = __ldg(xg + (int64_t)m * n + i) - mean; var = fmaf(d, d, var); }
+    var /= (float)Bg;
+    const float coef = var > p.alpha ? gs * rsqrtf(var) : 0.f;
+    const int64_t pos = i / p.C;
+    const int c = (int)(i - pos * p.C);
+    for (int m = 0; m < Bg; ++m) {
+      const int64_t b = (int64_t)g * Bg + m;
+      p.gx[b * n + i] = __ldg(p.gout + (b * p.HW + pos) * C1 + c) + coef * (__ldg(xg + (int64_t)m * n + i) - mean);
+    }
+  }
+}
+
+static int mbstd_check(const char* what, int B, int C, int64_t HW, int G) {
+  if (B < 1 || C < 1 || HW < 1 || G < 1 || B % G != 0) return fail(MSG_ERR_BAD_ARG, "%s: batch %d must be a positive multiple of the group count %d", what, B, G);
+  if (G > 65535) return fail(MSG_ERR_UNSUPPORTED, "%s: too many groups", what);
+  return MSG_OK;
+}
+static int mbstd_blocks(int64_t n) {
+  int64_t b = ceil_div(n, 256 * 4);
+  const int64_t cap = 2 * num_sms();
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace msg
+
+// workspace (both directions): (groups * 2 * #SMs + groups) floats
+extern "C" size_t msg_mbstd_workspace(int groups) { return ((size_t)groups * 2 * msg::num_sms() + groups) * sizeof(float) + 256; }
+
+extern "C" int msg_mbstd_forward(float* out, const float* x, int B, int C, int64_t HW, int groups, float alpha, void* workspace,
+                                 size_t workspace_bytes, msg_stream_t stream) {
+  using namespace msg;
+  int rc = mbstd_check("mbstd_forward", B, C, HW, groups);
+  if (rc) return rc;
+  if (!out || !x) return fail(MSG_ERR_BAD_ARG, "mbstd_forward: null pointer");
+  if (!workspace || workspace_bytes < msg_mbstd_workspace(groups)) return fail(MSG_ERR_WORKSPACE, "mbstd_forward: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  MbStdParams p{};
+  p.x = x; p.out = out; p.B = B; p.C = C; p.G = groups; p.HW = HW; p.alpha = alpha;
+  p.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  p.nblk = mbstd_blocks(HW * C);
+  p.stats = p.partial + (size_t)groups * 2 * num_sms();
+  mbstd_partial_kernel<<<dim3((unsigned)p.nblk, (unsigned)groups), 256, 0, st>>>(p);
+  MSG_CHECK_LAUNCH("mbstd_forward(partial)");
+  mbstd_final_kernel<<<(unsigned)groups, 256, 0, st>>>(p.stats, p.partial, p.nblk, 1.f / ((float)HW * (float)C));
+  MSG_CHECK_LAUNCH("mbstd_forward(final)");
+  const int64_t total = (int64_t)B * HW * (C + 1);
+  const int64_t want = ceil_div(total, 256 * 4), cap = (int64_t)16 * num_sms();
+  mbstd_write_kernel<<<(unsigned)(want < cap ? (want > 0 ? want : 1) : cap), 256, 0, st>>>(p);
+  MSG_CHECK_LAUNCH("mbstd_forward(write)");
+  return MSG_OK;
+}
+
+extern "C" int msg_mbstd_backward(float* gx, const float* gout, const float* x, int B, int C, int64_t HW, int groups, float alpha,
+                                  void* workspace, size_t workspace_bytes, msg_stream_t stream) {
+  using namespace msg;
+  int rc = mbstd_check("mbstd_backward", B, C, HW, groups);
+  if (rc) return rc;
+  if (!gx || !gout || !x) return fail(MSG_ERR_BAD_ARG, "mbstd_backward: null pointer");
+  if (!workspace || workspace_bytes < msg_mbstd_workspace(groups)) return fail(MSG_ERR_WORKSPACE, "mbstd_backward: workspace");
+  cudaStream_t st = (cudaStream_t)stream;
+  MbStdParams p{};
+  p.x = x; p.gout = gout; p.gx = gx; p.B = B; p.C = C; p.G = groups; p.HW = HW; p.alpha = alpha;
+  p.partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  p.stats = p.partial + (size_t)groups * 2 * num_sms();
+  p.nblk = mbstd_blocks((int64_t)(B / groups) * HW);
+  mbstd_gplane_partial_kernel<<<dim3((unsigned)p.nblk, (unsigned)groups), 256, 0, st>>>(p);
+  MSG_CHECK_LAUNCH("mbstd_backward(plane gradient)");
+  mbstd_final_kernel<<<(unsigned)groups, 256, 0, st>>>(p.stats, p.partial, p.nblk, 1.f);
+  MSG_CHECK_LAUNCH("mbstd_backward(final)");
+  const int nb = mbstd_blocks(HW * C);
+  mbstd_backward_kernel<<<dim3((unsigned)nb, (unsigned)groups), 256, 0, st>>>(p);
+  MSG_CHECK_LAUNCH("mbstd_backward");
+  return MSG_OK;
+}

@@ -57,6 +57,23 @@ class Blur(nn.Module):
         return upfirdn2d(input, self.kernel, pad=self.padding)
 
 
+class _MbStdFused(torch.autograd.Function):
+    """MinibatchStdDev on the library's kernels (first-order; msg_mbstd_forward / _backward)."""
+
+    @staticmethod
+    def forward(ctx, x, groups, alpha):
+        ctx.save_for_backward(x)
+        ctx.cfg = (groups, alpha)
+        return _C.mbstd_forward(x, groups, alpha)
+
+    @staticmethod
+    def backward(ctx, gout):
+        if torch.is_grad_enabled():
+            raise RuntimeError(_mode.NO_DOUBLE_BACKWARD)
+        x, = ctx.saved_tensors
+        return _C.mbstd_backward(gout, x, *ctx.cfg), None, None
+
+
 class MinibatchStdDev(nn.Module):
     """One extra channel holding the mean over (c,h,w) of the per-position batch std — reference :189-217."""
 
@@ -66,6 +83,9 @@ class MinibatchStdDev(nn.Module):
         self.groups = 1      # > 1: the batch is `groups` independent sub-batches (Discriminator.forward_pair)
 
     def forward(self, input: torch.Tensor) -> torch.Tensor:
+        if (input.is_cuda and input.dtype == torch.float32 and input.dim() == 4 and not _mode.higher_order()
+                and input.shape[0] % self.groups == 0):
+            return _MbStdFused.apply(input, self.groups, self.alpha)       # three launches instead of ~10 ATen kernels
         if self.groups > 1:
             G, Bg = self.groups, input.shape[0] // self.groups
             x = input.reshape(G, Bg, *input.shape[1:])

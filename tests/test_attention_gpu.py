@@ -95,3 +95,29 @@ def test_non_local_block_matches_oracle(built_library):
     want = omodel.non_local_block(sd, "b", x)
     got = blk.to(dev())(cl(x.to(dev())))
     assert rel_err(got, want) < 1e-2, rel_err(got, want)
+
+
+@pytest.mark.parametrize("case", [(8, 12, 5, 7, 1), (16, 384, 32, 32, 2), (6, 20, 4, 4, 3), (4, 768, 16, 16, 1)],
+                         ids=lambda c: "B%d-C%d-%dx%d-groups%d" % c)
+def test_minibatch_stddev_kernels_match_tensor_op_formulation(built_library, case):
+    """msg_mbstd_forward / _backward vs the module's tensor-op formulation (u_net_2d_discriminator.py:189-217), which it still
+    runs under higher_order_gradients()."""
+    from multi_stylegan_b200 import _mode
+    import multi_stylegan_b200.u_net_2d_discriminator as D_mod
+    B, C, H, W, groups = case
+    torch.manual_seed(B + C)
+    m = D_mod.MinibatchStdDev()
+    m.groups = groups
+    x = cl(torch.randn(B, C, H, W, device=dev()) * 2).requires_grad_(True)
+    x.data[:, 0, 0, 0] = 1.25                      # one position with zero variance: the clamp branch
+    gout = cl(torch.randn(B, C + 1, H, W, device=dev()))
+    got = m(x)
+    got.backward(gout)
+    g1 = x.grad.clone()
+    x.grad = None
+    with _mode.higher_order_gradients():
+        want = m(x)
+    want.backward(gout)
+    assert got.shape == want.shape
+    assert rel_err(got, want) < 1e-6, rel_err(got, want)
+    assert rel_err(g1, x.grad) < 1e-5, rel_err(g1, x.grad)

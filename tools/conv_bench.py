@@ -74,6 +74,8 @@ def main():
         ("D conv 3x3 768->768 @32", 8, 768, 768, 32, 3, False, 1, None),
         ("D conv 1x1 256->128 @256", 8, 256, 128, 256, 1, False, 1, 0),
         ("D conv 3x3 s2 128->128 @256", 8, 128, 128, 256, 3, False, 2, 0),
+        ("D first conv 3x3 6->128 @256 B=16", 16, 6, 128, 256, 3, False, 1, None),
+        ("D first conv 1x1 6->128 @256 B=16", 16, 6, 128, 256, 1, False, 1, 0),
     ]
     if args.quick:
         cases = [c for c in cases if c[0].startswith("D conv 3x3") and c[7] == 1] + cases[:1]
