@@ -10,15 +10,15 @@ import torch.nn as nn
 @torch.no_grad()
 def exponential_moving_average(model_ema: nn.Module, model_train: nn.Module, decay: float = 0.999) -> None:
     """p_ema <- decay * p_ema + (1 - decay) * p over named parameters (buffers are not averaged),
-    as one fused multi-tensor update instead of the reference's per-tensor Python loop."""
+    as ONE multi-tensor pass (lerp) instead of the reference's per-tensor Python loop."""
     assert type(model_ema) is type(model_train), "EMA can only be performed on networks of the same type!"
     ema = dict(model_ema.named_parameters())
     train = dict(model_train.named_parameters())
     keys = list(ema.keys())
     dst = [ema[k].data for k in keys]
     src = [train[k].data for k in keys]
-    torch._foreach_mul_(dst, decay)
-    torch._foreach_add_(dst, src, alpha=1 - decay)
+    # one pass: p_ema + (1 - decay) * (p - p_ema)  ==  decay * p_ema + (1 - decay) * p
+    torch._foreach_lerp_(dst, src, 1 - decay)
 
 
 def random_permutation(n: int) -> torch.Tensor:
