@@ -47,8 +47,8 @@ struct Epilogue {
   int64_t out2_scale_sb;
   // mask mode (the activation backward of the PRODUCING layer fused into this dgrad): `add` is that layer's activation
   // output and multiplies instead of adds:  out = alpha * acc * (add > 0 ? 1 : slope) * gain;  with `colsum` the
-  // per-channel sums of `out` (the bias gradient) are accumulated per CTA and epilogue warp:
-  // colsum[(cta * 4 + warp) * N + n]  (tcgen05 engine, TMA-store epilogue, one channel tile only)
+  // per-channel sums of `out` (the bias gradient) are accumulated per CTA and epilogue warp into rows that this warp
+  // alone owns (pre-zeroed by the caller): colsum[(cta * 4 + warp) * N + n]  (tcgen05 engine, TMA-store epilogue)
   int add_is_mask;
   float* colsum;
   __host__ __device__ bool any() const { return bias || noise || add || act || gain != 1.f || cscale || out2; }
