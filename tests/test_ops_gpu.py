@@ -420,3 +420,124 @@ def test_reference_extension_module_shims(built_library):
     for cfg in ((1, 1, 1, 1, 2, 1, 2, 1), (2, 2, 1, 1, 2, 1, 2, 1), (1, 1, 2, 2, 1, 1, 1, 1), (1, 1, 1, 1, 2, 2, 2, 2)):
         got = upfirdn2d_cuda.upfirdn2d(inp.cuda(), k.cuda(), *cfg)
         assert rel_err(got, ops.upfirdn2d(inp, k, *cfg)) < 1e-5, cfg
+
+
+def test_round_2_kernels_do_not_write_out_of_bounds(built_library):
+    """The same guard-band check for the kernels added in round 2 (small-M linears, non-local passes, MinibatchStdDev,
+    demodulation backward, column sums), on ragged sizes, through the raw C-ABI."""
+    import ctypes
+    from multi_stylegan_b200 import _lib
+    L = _lib.lib()
+    d = dev()
+    G = 4096
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+    bufs = []
+
+    def guarded(n, dtype=torch.float32):
+        fill = float("nan") if dtype == torch.float32 else -7
+        buf = torch.full((n + 2 * G,), fill, device=d, dtype=dtype)
+        bufs.append((buf, n, dtype))
+        return buf[G:G + n]
+
+    def check(what):
+        torch.cuda.synchronize()
+        for buf, n, dtype in bufs:
+            if dtype == torch.float32:
+                assert torch.isnan(buf[:G]).all() and torch.isnan(buf[G + n:]).all(), what
+                assert not torch.isnan(buf[G:G + n]).any(), what
+            else:
+                assert (buf[:G] == -7).all() and (buf[G + n:] == -7).all(), what
+        bufs.clear()
+
+    # mapping network: K = 20 (column slices of 3, 3, ..., 2 / empty), M = 19 rows (three forward clusters, two backward chunks)
+    depth, M, K = 3, 19, 20
+    Ws = [torch.randn(K, K, device=d) for _ in range(depth)]
+    bs = [torch.randn(K, device=d) for _ in range(depth)]
+    warr = (ctypes.c_void_p * depth)(*[w.data_ptr() for w in Ws])
+    barr = (ctypes.c_void_p * depth)(*[b.data_ptr() for b in bs])
+    z = torch.randn(M, K, device=d)
+    acts, x0 = guarded(depth * M * K), guarded(M * K)
+    assert L.msg_style_mapping_forward(ptr(acts), ptr(x0), ptr(z), warr, barr, depth, M, K, 0.3, 0.2, 1.0, 1e-8, st) == 0
+    check("style_mapping_forward")
+    dW, db, work = guarded(depth * K * K), guarded(depth * K), guarded(depth * M * K)
+    gy = torch.randn(M, K, device=d)
+    assert L.msg_style_mapping_backward(ptr(dW), ptr(db), ptr(gy), ptr(acts), ptr(x0), warr, barr, depth, M, K, 0.3, 0.2, 1.0,
+                                        ptr(work), st) == 0
+    check("style_mapping_backward")
+
+    # grouped linears: N = 12 / 20 / 4, K = 8 / 12, M = 19
+    specs = [(12, 8, 0), (20, 8, 0), (4, 12, 8)]                 # (N, K, in_off); input row = 20 floats
+    items = (_lib.LinearItem * len(specs))()
+    keep, out_off, w_off, b_off = [], 0, 0, 0
+    for i, (N, Kk, off) in enumerate(specs):
+        W, b = torch.randn(N, Kk, device=d), torch.randn(N, device=d)
+        keep += [W, b]
+        it = items[i]
+        it.W, it.bias, it.N, it.K, it.in_off, it.out_off, it.w_off, it.b_off = W.data_ptr(), b.data_ptr(), N, Kk, off, out_off, w_off, b_off
+        it.alpha, it.beta = 0.5, 2.0
+        out_off, w_off, b_off = out_off + N, w_off + N * Kk, b_off + N
+    slots = (_lib.LinearSlot * 2)()
+    slots[0].in_off, slots[0].K, slots[0].first, slots[0].count = 0, 8, 0, 2
+    slots[1].in_off, slots[1].K, slots[1].first, slots[1].count = 8, 12, 2, 1
+    x = torch.randn(M, 20, device=d)
+    out = guarded(M * out_off)
+    assert L.msg_linear_group_forward(ptr(out), ptr(x), 20, items, 3, M, 20, 12, st) == 0
+    check("linear_group_forward")
+    gout = torch.randn(M * out_off, device=d)
+    dW, db, din = guarded(w_off), guarded(b_off), guarded(M * 20)
+    assert L.msg_linear_group_backward(ptr(dW), ptr(db), ptr(din), ptr(gout), ptr(x), 20, items, 3, slots, 2, M, 20, 12, st) == 0
+    check("linear_group_backward")
+
+    # non-local passes on an odd map
+    B, H, W, cq, cv = 2, 9, 7, 8, 12
+    qkv = torch.randn(B, H, W, 2 * cq + cv, device=d)
+    theta, phi, gp = guarded(B * H * W * cq), guarded(B * (H // 2) * (W // 2) * cq), guarded(B * (H // 2) * (W // 2) * cv)
+    idx = guarded(B * (H // 2) * (W // 2) * (cq + cv) // 4, torch.int32)
+    assert L.msg_nl_split_pool(ptr(theta), ptr(phi), ptr(gp), ptr(idx), ptr(qkv), B, H, W, cq, cv, st) == 0
+    check("nl_split_pool")
+    dq = guarded(B * H * W * (2 * cq + cv))
+    assert L.msg_nl_merge_unpool(ptr(dq), ptr(theta), ptr(phi), ptr(gp), ptr(idx), B, H, W, cq, cv, st) == 0
+    check("nl_merge_unpool")
+    for n in (12, 516, 1028, 2052):
+        rows = 13
+        s = guarded(rows * n)
+        s.copy_(torch.randn(rows * n, device=d))
+        assert L.msg_softmax_rows(ptr(s), rows, n, st) == 0
+        dp = guarded(rows * n)
+        dp.copy_(torch.randn(rows * n, device=d))
+        assert L.msg_softmax_rows_bwd(ptr(dp), ptr(s), rows, n, st) == 0
+        check(("softmax_rows", n))
+
+    # MinibatchStdDev, groups = 3 of 2 samples, C = 5 (odd), HW = 35
+    B, C, HW, groups = 6, 5, 35, 3
+    x = torch.randn(B * HW * C, device=d)
+    nws = L.msg_mbstd_workspace(groups)
+    out, ws = guarded(B * HW * (C + 1)), guarded(nws // 4 + 64)
+    assert L.msg_mbstd_forward(ptr(out), ptr(x), B, C, HW, groups, 1e-8, ptr(ws), nws, st) == 0
+    ws.fill_(0)
+    check("mbstd_forward")
+    gx, ws = guarded(B * HW * C), guarded(nws // 4 + 64)
+    go = torch.randn(B * HW * (C + 1), device=d)
+    assert L.msg_mbstd_backward(ptr(gx), ptr(go), ptr(x), B, C, HW, groups, 1e-8, ptr(ws), nws, st) == 0
+    ws.fill_(0)
+    check("mbstd_backward")
+
+    # demodulation backward and the deterministic reductions
+    B, O, C, taps = 5, 12, 20, 9
+    Wt, s_, gd, dd, wsq = (torch.randn(O * C * taps, device=d), torch.randn(B * C, device=d), torch.randn(B * O, device=d),
+                           torch.rand(B * O, device=d), torch.rand(O * C, device=d))
+    dW, ds = guarded(O * C * taps), guarded(B * C)
+    assert L.msg_demod_factors_bwd(ptr(dW), ptr(ds), ptr(gd), ptr(dd), ptr(s_), ptr(wsq), ptr(Wt), B, O, C, taps, 0.1, st) == 0
+    check("demod_factors_bwd")
+    rows, C = 1000, 36
+    x = torch.randn(rows * C, device=d)
+    nws = L.msg_colsum_workspace(rows, C)
+    out, ws = guarded(C), guarded(nws // 4 + 64)
+    assert L.msg_colsum_nhwc(ptr(out), ptr(x), rows, C, 1.0, ptr(ws), nws, st) == 0
+    ws.fill_(0)
+    check("colsum_nhwc")
+    out, ws = guarded(1), guarded(4096)
+    assert L.msg_dot(ptr(out), ptr(x), ptr(x), rows * C, 1.0, ptr(ws), st) == 0
+    ws.fill_(0)
+    check("dot")
