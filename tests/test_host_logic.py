@@ -21,24 +21,41 @@ class GradCheck:
     zero, which moves individual gradient entries by O(1) and bias-type sums by O(sqrt(flip rate)); stock
     PyTorch/cuDNN with TF32 shows the same on these fixtures (worst tensor 7.9 % in L2, measured on B200,
     tools/tf32_deviation.py).  So: every tensor within 25 % in relative L2 and all gradients together
-    within 10 % — a wrong tap, stride or layout gives >= 50 %."""
+    within 10 % — a wrong tap, stride or layout gives >= 50 %.  What these bounds sit on (B200, every compared tensor:
+    profiles/r2n_gradcheck_tf32.txt, written with MSG_GRADCHECK_LOG): worst single tensor 22.6 % (a one-element noise
+    weight), 18.8 % / 13.5 % (theta / phi of the non-local block), everything else below 10 %; all gradients of a check
+    together 0.05 % ... 4.1 %.  The same networks WITHOUT masks (leaky-ReLU slope 1 on both sides) are held to 1e-2 /
+    2e-2 per tensor in tests/test_maskfree_gradients_gpu.py, single kernels at the benchmark shapes to 1e-2 in
+    tests/test_baseline_shapes_gpu.py."""
 
     def __init__(self, tol: float, tf32: bool = False):
         self.tol, self.tf32 = tol, tf32
         self.num, self.den = 0.0, 0.0
+
+    @staticmethod
+    def _log(line: str) -> None:
+        import os
+        path = os.environ.get("MSG_GRADCHECK_LOG")          # measurement runs: every compared tensor with its error
+        if path:
+            with open(path, "a") as f:
+                f.write(line + "\n")
 
     def check(self, got, want, name=""):
         if self.tf32:
             g, w = got.detach().double().cpu(), want.detach().double().cpu()
             self.num += float((g - w).pow(2).sum())
             self.den += float(w.pow(2).sum())
-            assert l2_err(got, want) < 0.25, (name, l2_err(got, want))
+            e = l2_err(got, want)
+            self._log("tensor %-60s l2 %.4e" % (name, e))
+            assert e < 0.25, (name, e)
         else:
             assert rel_err(got, want) < self.tol, (name, rel_err(got, want))
 
     def finish(self):
         if self.tf32 and self.den > 0:
-            assert (self.num / self.den) ** 0.5 < 0.10, (self.num / self.den) ** 0.5
+            e = (self.num / self.den) ** 0.5
+            self._log("global %-60s l2 %.4e" % ("", e))
+            assert e < 0.10, e
 
 import multi_stylegan_b200.multi_stylegan_generator as G_mod
 import multi_stylegan_b200.u_net_2d_discriminator as D_mod
