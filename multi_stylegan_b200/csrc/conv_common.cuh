@@ -87,6 +87,7 @@ struct PixGemm {
   int out_my, out_mx, out_oy, out_ox;
   float alpha;
   Epilogue ep;            // zero-initialised = plain alpha * acc (gain must then be set to 1)
+  int ksplit;             // tcgen05 engine, internal: > 1 = this call is the tap-split pass of a small problem (conv_tc.cu)
 };
 
 struct RedGemm {

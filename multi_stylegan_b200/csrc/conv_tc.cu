@@ -364,6 +364,8 @@ struct TcPixParams {
   int tma_store;               // epilogue writes 32-pixel x 32-channel boxes with TMA
   int debug;                   // MSG_B200_TC_VARIANT bits 32/64 (timing experiments only): 1 = no stores, 2 = no proxy fence (wrong results)
   int kw;                      // row-tap kernel: taps per filter row (taps are stored row-major, dx consecutive)
+  int ksplit, tpg, bsz;        // tc_pixgemm_kernel: tap split (ksplit groups of tpg taps, partial sums of group g stored as
+                               // samples [g * bsz, (g + 1) * bsz) of the output view); ksplit = 1: none
   Epilogue ep;
 };
 
@@ -715,7 +717,6 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
-  const int kiters = p.ntaps * p.cchunks;
 
   if (warp == 0) {
     // producer: the whole warp runs the loop converged (tile / tap / chunk counters stay in uniform registers, no
@@ -723,13 +724,15 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
     uint32_t s = 0, ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int r = tile;
+      const int grp = r % p.ksplit; r /= p.ksplit;
       const int nt = r % p.n_tiles; r /= p.n_tiles;
       const int tx = r % p.tiles_x; r /= p.tiles_x;
       const int ty = r % p.tiles_y;
       const int b = r / p.tiles_y;
       const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN;
       const int bw = p.w_per_sample ? b : 0;
-      for (int t = 0; t < p.ntaps; ++t) {
+      const int t0 = grp * p.tpg, t1 = min(p.ntaps, t0 + p.tpg);
+      for (int t = t0; t < t1; ++t) {
         const int xx = x0 + p.tap_dx[t], yy = y0 + p.tap_dy[t];
         int view = 0, ca = 0;
         for (int cc = 0; cc < p.cchunks; ++cc) {
@@ -755,6 +758,7 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
       mbar_wait(acc_empty + 8 * a, ((lt >> 1) & 1u) ^ 1u);      // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + a * ACC_COLS;
+      const int kiters = min(p.ntaps - (tile % p.ksplit) * p.tpg, p.tpg) * p.cchunks;   // this tile's tap group
       for (int k = 0; k < kiters; ++k) {
         mbar_wait(bars + 8 * s, ph);
         tc_fence_after();
@@ -786,10 +790,11 @@ tc_pixgemm_kernel(const __grid_constant__ TMapSet tmAs, const __grid_constant__ 
     uint32_t lt = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
       int r = tile;
+      const int grp = r % p.ksplit; r /= p.ksplit;
       const int nt = r % p.n_tiles; r /= p.n_tiles;
       const int tx = r % p.tiles_x; r /= p.tiles_x;
       const int ty = r % p.tiles_y;
-      const int b = r / p.tiles_y;
+      const int b = r / p.tiles_y + grp * p.bsz;          // tap split: group g writes its partial sums as samples g * bsz + b
       const int y0 = ty * Ht, x0 = tx * Wt, n0 = nt * BN;
       const uint32_t a = lt & 1u;
       mbar_wait(acc_full + 8 * a, (lt >> 1) & 1u);
@@ -1809,11 +1814,71 @@ bool tc_pixgemm_mask_ok(const PixGemm& g) {
          al16(g.ep.add) && !(tc_variant() & 16u);
 }
 
+// Tap split for small problems.  A layer at 4x4 ... 16x16 pixels (or a 1024-channel block at 16x16) has 8 ... 40 output
+// tiles for 148 SMs, and every one of them walks the whole K loop (9 taps x C / 32 chunks = 144 stages at 512 channels):
+// 13-190 TFLOP/s.  Such a call is run as `ksplit` groups of taps that accumulate separate partial outputs (a tile index
+// carries its group; the persistent kernel is otherwise unchanged), followed by one pass that adds the groups in a fixed
+// order and applies the epilogue — deterministic, and the partial sums of a few-megabyte output cost next to nothing.
+// MSG_B200_TC_VARIANT bit 65536 disables it.  Returns the number of groups (1 = no split).
+static int pix_tap_split(const PixGemm& g) {
+  if (g.ksplit > 1) return g.ksplit;
+  if (tc_variant() & 65536u) return 1;
+  if (g.ntaps < 3 || g.nphase != 0 || g.nsrc != 0 || g.ep.add_is_mask || g.ep.colsum != nullptr) return 1;
+  const int BN = pick_bn(g.N, 16);
+  if (BN < 64) return 1;
+  int wt_log2 = ilog2_ceil(g.PW);
+  if (wt_log2 > 7) wt_log2 = 7;
+  const int64_t tiles = ceil_div(g.PW, 1 << wt_log2) * ceil_div(g.PH, 128 >> wt_log2) * (int64_t)g.B * ceil_div(g.N, BN);
+  if (tiles * 3 > num_sms()) return 1;                              // enough tiles, or too little to win
+  if ((int64_t)g.ntaps * ceil_div(g.Cr, 32) < 32) return 1;         // short K loop
+  int ks = (int)(num_sms() / tiles);
+  if (ks > g.ntaps) ks = g.ntaps;
+  const int tpg = (int)ceil_div(g.ntaps, ks);
+  return (int)ceil_div(g.ntaps, tpg);
+}
+
+struct TapReduceParams {
+  const float* part;        // [ksplit][B][PH][PW][N]
+  int ksplit, B, PH, PW, N;
+  float* out;
+  View4 os;
+  int out_my, out_mx, out_oy, out_ox;
+  float alpha;
+  Epilogue ep;
+};
+
+__global__ void __launch_bounds__(256)
+tap_split_reduce_kernel(const TapReduceParams p) {
+  const int64_t total = (int64_t)p.B * p.PH * p.PW * p.N;
+  const float nw = p.ep.noise ? __ldg(p.ep.noise_w) : 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i;
+    const int n = (int)(r % p.N); r /= p.N;
+    const int x = (int)(r % p.PW); r /= p.PW;
+    const int y = (int)(r % p.PH);
+    const int b = (int)(r / p.PH);
+    float acc = 0.f;
+    for (int g = 0; g < p.ksplit; ++g) acc += __ldg(p.part + (int64_t)g * total + i);
+    const int64_t off = (int64_t)b * p.os.sb + (int64_t)(y * p.out_my + p.out_oy) * p.os.sy +
+                        (int64_t)(x * p.out_mx + p.out_ox) * p.os.sx + (int64_t)n * p.os.sc;
+    const float bn = p.ep.bias ? __ldg(p.ep.bias + n) : 0.f;
+    const float nz = p.ep.noise ? nw * __ldg(p.ep.noise + (int64_t)b * p.ep.noise_sb + (int64_t)y * p.PW + x) : 0.f;
+    const float av = p.ep.add ? __ldg(p.ep.add + off) : 0.f;
+    const float cs = p.ep.cscale ? __ldg(p.ep.cscale + (int64_t)b * p.ep.cscale_sb + n) : 1.f;
+    const float o1 = apply_epilogue(p.ep, p.alpha * acc * cs, bn, nz, av);
+    p.out[off] = o1;
+    if (p.ep.out2) p.ep.out2[off] = o1 * __ldg(p.ep.out2_scale + (int64_t)b * p.ep.out2_scale_sb + n);
+  }
+}
+
 size_t tc_pixgemm_workspace(const PixGemm& g) {
-  const int BN = pick_bn_pix(g);
+  const int ks = pix_tap_split(g);
+  const int BN = ks > 1 ? pick_bn(g.N, 16) : pick_bn_pix(g);
   const int64_t Npad = round_up(g.N, BN), Cpad = round_up(g.Cr, 32);
   const int64_t BW = g.w_sb != 0 ? g.B : 1;
-  return (size_t)(BW * g.ntaps * Npad * Cpad) * sizeof(float) + 256;
+  size_t bytes = (size_t)(BW * g.ntaps * Npad * Cpad) * sizeof(float) + 256;
+  if (ks > 1 && g.ksplit <= 1) bytes += (size_t)ks * g.B * g.PH * g.PW * g.N * sizeof(float) + 256;   // partial outputs
+  return bytes;
 }
 
 template <int BN, int MT>
@@ -1930,8 +1995,37 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!tc_pixgemm_supported(g)) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): shape not supported");
   const size_t need = tc_pixgemm_workspace(g);
   if (!ws || ws_bytes < need) return fail(MSG_ERR_WORKSPACE, "conv pixgemm(tcgen05): workspace %zu < %zu", ws_bytes, need);
+  if (g.ksplit <= 1) {
+    const int ks = pix_tap_split(g);
+    if (ks > 1) {
+      // pass 1: the same kernel on `ks` tap groups, raw partial sums into the tail of the workspace
+      PixGemm gs = g;
+      gs.ksplit = ks;
+      gs.os = View4{(int64_t)g.PH * g.PW * g.N, 1, (int64_t)g.PW * g.N, (int64_t)g.N};
+      gs.out_my = gs.out_mx = 1; gs.out_oy = gs.out_ox = 0;
+      gs.alpha = 1.f;
+      gs.ep = Epilogue{};
+      gs.ep.gain = 1.f;
+      const size_t inner = tc_pixgemm_workspace(gs);            // transformed weights (same column tile as this call planned)
+      uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+      float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(wsb + inner) + 255) & ~(uintptr_t)255);
+      gs.out = part;
+      int rc = tc_pixgemm(gs, ws, inner, st);
+      if (rc) return rc;
+      // pass 2: sum of the groups (fixed order) + the call's epilogue
+      TapReduceParams rp{};
+      rp.part = part; rp.ksplit = ks; rp.B = g.B; rp.PH = g.PH; rp.PW = g.PW; rp.N = g.N;
+      rp.out = g.out; rp.os = g.os; rp.out_my = g.out_my; rp.out_mx = g.out_mx; rp.out_oy = g.out_oy; rp.out_ox = g.out_ox;
+      rp.alpha = g.alpha; rp.ep = g.ep;
+      const int64_t total = (int64_t)g.B * g.PH * g.PW * g.N;
+      const int64_t want = ceil_div(total, 256), cap = (int64_t)num_sms() * 8;
+      tap_split_reduce_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(rp);
+      MSG_CHECK_LAUNCH("conv pixgemm(tap-split reduce)");
+      return MSG_OK;
+    }
+  }
   float* wt = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  const int BN = pick_bn_pix(g);
+  const int BN = g.ksplit > 1 ? pick_bn(g.N, 16) : pick_bn_pix(g);
   const int Npad = round_up(g.N, BN), Cpad = round_up(g.Cr, 32);
   const int BW = g.w_sb != 0 ? g.B : 1;
 
@@ -1979,16 +2073,16 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   // TFLOP/s on the discriminator's 128-channel 3x3 layers at 256^2; ncu: tensor pipe 69 % active either way), so they
   // stay opt-in.
   bool pairs = (BN == 256 || (BN == 128 && (tc_variant() & 1024u))) && !(tc_variant() & 4u) &&
-               pair_tiles >= pair_min && g.nphase == 0 && g.nsrc == 0;
+               pair_tiles >= pair_min && g.nphase == 0 && g.nsrc == 0 && g.ksplit <= 1;
   // Row-tap kernels (activation box shared by the 3 taps of a filter row): 3-tap filter rows stored row-major with
   // consecutive dx (either direction), tiles that are whole 128-pixel image-row segments, N <= 128.
   // MSG_B200_TC_VARIANT bit 2048 disables them, bit 4096 only their CTA-pair form.
-  bool rows_ok = wt_log2 == 7 && g.nphase == 0 && g.ntaps % 3 == 0 && g.ntaps >= 3 && !(tc_variant() & 2048u);
+  bool rows_ok = wt_log2 == 7 && g.nphase == 0 && g.ntaps % 3 == 0 && g.ntaps >= 3 && !(tc_variant() & 2048u) && g.ksplit <= 1;
   for (int t = 0; t < g.ntaps && rows_ok; ++t) {
     const int t0 = t - t % 3, step = g.tap_dx[t0 + 1] - g.tap_dx[t0];       // +1 (forward) or -1 (dgrad) within a row
     rows_ok = (step == 1 || step == -1) && g.tap_dy[t] == g.tap_dy[t0] && g.tap_dx[t] == g.tap_dx[t0] + step * (t % 3);
   }
-  int MT = pairs ? 1 : pick_mt(g, BN);
+  int MT = (pairs || g.ksplit > 1) ? 1 : pick_mt(g, BN);
   int64_t pair_tiles_used = pair_tiles;
   bool pairs_rows = false;
   if (pairs && rows_ok && BN == 256 && !(tc_variant() & (4096u | 8192u))) {
@@ -2044,7 +2138,11 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   p.tiles_x = (int)ceil_div(g.PW, Wt);
   p.tiles_y = (int)ceil_div(g.PH, Ht);
   p.n_tiles = Npad / BN;
-  const int64_t total_tiles = (pairs || pairs_rows) ? pair_tiles_used : (int64_t)p.tiles_x * p.tiles_y * p.n_tiles * g.B;
+  p.ksplit = g.ksplit > 1 ? g.ksplit : 1;
+  p.tpg = (int)ceil_div(g.ntaps, p.ksplit);
+  p.bsz = g.B;
+  const int64_t total_tiles = (pairs || pairs_rows) ? pair_tiles_used
+                                                    : (int64_t)p.tiles_x * p.tiles_y * p.n_tiles * g.B * p.ksplit;
   if (total_tiles > 0x7fffffffLL) return fail(MSG_ERR_UNSUPPORTED, "conv pixgemm(tcgen05): too many tiles");
   p.total_tiles = (int)total_tiles;
   p.out = g.out; p.os = g.os;
@@ -2075,7 +2173,7 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (p.ep.out2 && !p.ep.out2_scale) return fail(MSG_ERR_BAD_ARG, "conv pixgemm(tcgen05): out2 needs out2_scale");
   if (p.vec_store && BN >= 32 && !(tc_variant() & 16u)) {
     const int bw = Wt < 32 ? Wt : 32;
-    const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B};
+    const uint64_t dims[4] = {(uint64_t)g.N, (uint64_t)g.PW, (uint64_t)g.PH, (uint64_t)g.B * (uint64_t)p.ksplit};
     const uint64_t strides[3] = {(uint64_t)g.os.sx * g.out_mx * 4, (uint64_t)g.os.sy * g.out_my * 4, (uint64_t)g.os.sb * 4};
     const uint32_t box[4] = {32, (uint32_t)bw, (uint32_t)(32 / bw), 1};
     const int64_t view_off = (int64_t)g.out_oy * g.os.sy + (int64_t)g.out_ox * g.os.sx;

@@ -454,3 +454,48 @@ def test_wgrad_cta_pair_kernel(built_library, case):
     assert got.shape == want.shape
     assert rel_err(got, want) < 1e-2, rel_err(got, want)
     assert torch.equal(got, got2)
+
+
+@pytest.mark.parametrize("case", [
+    # (B, C, O, H, W, k, per_sample): few output tiles, long K loop -> the tap-split pass + fixed-order reduce with the epilogue
+    (8, 512, 512, 4, 4, 3, False),
+    (2, 256, 256, 8, 8, 3, True),
+    (1, 96, 100, 16, 16, 3, False),         # channel tail in the last 32-channel chunk, N with a tail
+    (2, 128, 64, 9, 7, 2, False),           # four taps, odd map
+])
+def test_conv_tap_split_path(built_library, case):
+    from multi_stylegan_b200 import _C, _lib
+    from tests import backend_oracle
+    if not _C.tensor_core_path_available():
+        pytest.skip("not an sm_100 device")
+    B, C, O, H, W, k, per = case
+    pad = k // 2
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x = torch.randn(B, C, H, W, generator=g)
+    w = torch.randn((B, O, C, k, k) if per else (O, C, k, k), generator=g) / (C * k * k) ** 0.5
+    OH, OW = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+    bias, add = torch.randn(O, generator=g), torch.randn(B, O, OH, OW, generator=g)
+    noise, nw = torch.randn(B, 1, OH, OW, generator=g), torch.tensor([0.3])
+    cs, s2 = torch.rand(B, O, generator=g) + 0.5, torch.randn(B, O, generator=g)
+    d = dev()
+    old = _C.conv_flags
+    _C.conv_flags = _lib.CONV_FORCE_TC
+    try:
+        for kw in (dict(), dict(bias=bias, act=True, gain=1.4, noise=noise, noise_w=nw), dict(add=add, gain=0.7),
+                   dict(bias=bias, act=True, col_scale=cs, out2_scale=s2)):
+            want = backend_oracle.conv2d_forward(x, w, 1, pad, alpha=0.9, **kw)
+            dk = {a: (v.to(d) if isinstance(v, torch.Tensor) else v) for a, v in kw.items()}
+            got = _C.conv2d_forward(x.to(d), w.to(d), 1, pad, alpha=0.9, **dk)
+            if isinstance(want, tuple):
+                assert rel_err(got[0], want[0]) < 1e-2 and rel_err(got[1], want[1]) < 1e-2, list(kw)
+            else:
+                assert rel_err(got, want) < 1e-2, (list(kw), rel_err(got, want))
+            again = _C.conv2d_forward(x.to(d), w.to(d), 1, pad, alpha=0.9, **dk)
+            assert torch.equal(again[0] if isinstance(again, tuple) else again, got[0] if isinstance(got, tuple) else got)
+        dy = torch.randn(B, O, OH, OW, generator=g)
+        acc = torch.randn(B, C, H, W, generator=g)
+        got = _C.conv2d_dgrad(dy.to(d), w.to(d), (H, W), 1, pad, alpha=0.5, add=acc.to(d))
+        want = ops.conv2d_dgrad(dy, w, (H, W), 1, pad) * 0.5 + acc
+        assert rel_err(got, want) < 1e-2, rel_err(got, want)
+    finally:
+        _C.conv_flags = old
