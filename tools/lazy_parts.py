@@ -7,6 +7,7 @@ from multi_stylegan_b200 import config
 import multi_stylegan_b200.multi_stylegan_generator as G_mod
 import multi_stylegan_b200.u_net_2d_discriminator as D_mod
 from multi_stylegan_b200.model_wrapper import ModelWrapper
+from multi_stylegan_b200 import higher_order_gradients
 
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
@@ -39,7 +40,8 @@ def timed(name, fn, n=3):
 def r1_forward():
     mw._zero()
     x = real.detach().requires_grad_(True)
-    s, p = D(x, is_real=False, is_cut_mix=True)
+    with higher_order_gradients():          # what ModelWrapper does for the R1 step (_mode.py)
+        s, p = D(x, is_real=False, is_cut_mix=True)
     return x, s, p
 
 
