@@ -289,27 +289,33 @@ def run_ours(args):
                     "warm-up did not exercise the lazy regularisers"
 
     def warm_up_checked(w, plain):
-        ok = True
-        try:
-            warm_up(w, 4 if state["graphs"] else 1, plain)
-        except Exception as exc:                     # a capture that fails on this box must not cost the measurement
-            if not state["graphs"]:
-                raise
-            print("[bench rank %d] CUDA-graph capture failed (%s: %s)" % (rank, type(exc).__name__, str(exc)[:300]),
-                  file=sys.stderr, flush=True)
-            if VERBOSE:
-                import traceback
-                traceback.print_exc(file=sys.stderr)
-            ok = False
-        if state["graphs"] and not agree(ok):
-            # every rank leaves graph mode together and repeats the warm-up eagerly
+        """Graph mode degrades in steps that every rank takes together: NCCL all-reduces captured inside the iteration's
+        graph -> graph segments with eager collectives in between -> eager issue."""
+        while True:
+            ok = True
+            try:
+                warm_up(w, 4 if state["graphs"] else 1, plain)
+            except Exception as exc:                     # a capture that fails on this box must not cost the measurement
+                if not state["graphs"]:
+                    raise
+                print("[bench rank %d] CUDA-graph capture failed (%s: %s)" % (rank, type(exc).__name__, str(exc)[:300]),
+                      file=sys.stderr, flush=True)
+                if VERBOSE:
+                    import traceback
+                    traceback.print_exc(file=sys.stderr)
+                ok = False
+            if not state["graphs"] or agree(ok):
+                return
+            w._graphs.clear()
+            torch.cuda.synchronize()
+            if world > 1 and os.environ.get("MSG_B200_NCCL_IN_GRAPH", "0") == "1":
+                print("[bench rank %d] retrying with graph segments around eager collectives" % rank, file=sys.stderr, flush=True)
+                os.environ["MSG_B200_NCCL_IN_GRAPH"] = "0"
+                continue
             print("[bench rank %d] continuing with eager issue on all ranks" % rank, file=sys.stderr, flush=True)
             state["graphs"] = False
             args.no_graphs = True
             w.cuda_graphs = False
-            w._graphs.clear()
-            torch.cuda.synchronize()
-            warm_up(w, 1, plain)
     warm_up_checked(mw, max(args.warmup, 3))
     graphs = state["graphs"]
     barrier()
@@ -464,6 +470,9 @@ def run_ours(args):
     lazy_ms = [main["per_step"][i] for i in lazy_idx]
     cfg = workload_config(args, world)
     cfg["cuda_graphs"] = bool(graphs)
+    if world > 1:
+        cfg["gradient_all_reduce"] = ("NCCL, captured inside the iteration's CUDA graph" if graphs and mw._collectives_in_graph()
+                                      else "NCCL, issued eagerly between graph segments" if graphs else "NCCL, eager")
     cfg["lazy_r1_and_pl_steps_in_timed_region"] = len(lazy_idx)
     hbm, bf16_burst, bf16_sust, src = peaks()
     if mma_sust is not None:

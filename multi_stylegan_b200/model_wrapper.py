@@ -120,7 +120,8 @@ class ModelWrapper(object):
             return None
         tensors = [p.grad for p in params if p.grad is not None] + list(extra)
         prog = self._capture
-        if prog is None:
+        if prog is None or self._collectives_in_graph():
+            # (while capturing over NCCL: the flatten, the collective on NCCL's stream and the join are graph nodes)
             return ("eager", mdist.all_reduce_tensors_begin(tensors, self.process_group))
         box = {}
         self._segment_end(prog)
@@ -148,7 +149,7 @@ class ModelWrapper(object):
         (one graph break instead of two while capturing)."""
         if mdist.world_size(self.process_group) > 1 or self._always_break:
             prog = self._capture
-            if prog is None:
+            if prog is None or self._collectives_in_graph():
                 mdist.all_reduce_gradients(params, self.process_group)
                 mdist.all_reduce_tensors(list(extra), self.process_group)
             else:
@@ -158,6 +159,17 @@ class ModelWrapper(object):
                 self._segment_begin(prog)
         torch.nn.utils.clip_grad_norm_(params, max_norm=5.)
         optimizer.step()
+
+    def _collectives_in_graph(self) -> bool:
+        """Opt-in (MSG_B200_NCCL_IN_GRAPH=1): NCCL collectives are stream work like any kernel and can be captured
+        (NCCL >= 2.9); the iteration then stays ONE graph — the all-reduce runs on NCCL's stream between a captured fork and
+        join — instead of 2-4 segments with the collectives issued eagerly in between.  Parity of the two forms:
+        tests/test_dist_gpu.py (2 GPUs, small networks).  Not the default: at the benchmark's size (203 / 212 MB buffers)
+        a 2-GPU run of the one-graph form did not finish, so the segments stay the product path."""
+        if self._always_break or os.environ.get("MSG_B200_NCCL_IN_GRAPH", "0") != "1":
+            return False
+        return (mdist.world_size(self.process_group) > 1
+                and torch.distributed.get_backend(self.process_group) == "nccl")
 
     @staticmethod
     def _segment_begin(prog) -> None:

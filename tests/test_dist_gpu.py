@@ -144,3 +144,71 @@ def test_two_ranks_over_nccl_equal_one_gpu_with_per_group_statistics(built_libra
             for k in la:
                 assert rel_err(la[k], lb[k]) < 1e-3, (k, la[k], lb[k])
     assert "loss_path_length_regularization" in nccl[0]["losses"][-1]
+
+
+def _graph_worker(rank, world, port, tmp):
+    """Per rank: the same six iterations (plain + lazy variants) issued eagerly, replayed as ONE graph per variant with the
+    NCCL all-reduces captured inside it, and replayed as graph segments with the collectives issued eagerly in between."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import random
+    import numpy as np
+    import torch.distributed as dist
+    from multi_stylegan_b200.model_wrapper import ModelWrapper
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        hp = _hp()
+        hp["p_mixed_noise"] = 0.6
+        runs = {}
+        for mode in ("eager", "in_graph", "segments"):
+            os.environ["MSG_B200_NCCL_IN_GRAPH"] = "0" if mode == "segments" else "1"
+            G, D = build(dev, seed=0)
+            opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"], fused=True, capturable=True)
+            opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"], fused=True, capturable=True)
+            mw = ModelWrapper(G, D, opt_g, opt_d, hyperparameters=hp, device=dev, cuda_graphs=True)
+            random.seed(7), np.random.seed(7), torch.manual_seed(7)
+            gen = torch.Generator().manual_seed(11 + rank)          # every rank its own shard
+            hist = []
+            for it in range(6):
+                if mode == "eager":
+                    mw._graphs.clear()
+                real = torch.rand(4, 2, 3, 32, 32, generator=gen).to(dev)
+                hist.append({k: v.detach().cpu() for k, v in mw.train_step(real).items()})
+            torch.cuda.synchronize(dev)
+            n_graphs = {k[2:4]: sum(isinstance(i, torch.cuda.CUDAGraph) for i in st.program)
+                        for k, st in mw._graphs.items() if st is not None}
+            runs[mode] = dict(hist=hist, replays=mw.graph_replays, n_graphs=n_graphs,
+                              params=[p.detach().cpu() for p in list(G.parameters()) + list(D.parameters())],
+                              pl_mean=mw.path_length_regularization.mean_path_length.detach().cpu())
+        torch.save(runs, os.path.join(tmp, "graph%d.pt" % rank))
+    finally:
+        os.environ.pop("MSG_B200_NCCL_IN_GRAPH", None)
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(900)
+def test_nccl_all_reduce_inside_the_cuda_graph_matches_eager_and_segments(built_library, tmp_path):
+    """Multi-rank CUDA-graph replay, both forms: graph segments with the NCCL all-reduces issued eagerly in between (the
+    default) and the opt-in form with the all-reduces as nodes of the iteration's ONE graph
+    (ModelWrapper._collectives_in_graph); same losses / parameters as eager issue, replicas identical across ranks."""
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs %d GPUs" % WORLD)
+    port = 35500 + (os.getpid() % 2000)
+    mp.spawn(_graph_worker, args=(WORLD, port, str(tmp_path)), nprocs=WORLD, join=True)
+    res = [torch.load(os.path.join(str(tmp_path), "graph%d.pt" % r), weights_only=False) for r in range(WORLD)]
+    for r in range(WORLD):
+        assert res[r]["eager"]["replays"] == 0 and res[r]["in_graph"]["replays"] == 4 and res[r]["segments"]["replays"] == 4
+        assert res[r]["in_graph"]["n_graphs"] == {(False, False): 1, (True, True): 1}
+        assert res[r]["segments"]["n_graphs"] == {(False, False): 4, (True, True): 5}
+        for mode in ("in_graph", "segments"):
+            for a, b in zip(res[r]["eager"]["hist"], res[r][mode]["hist"]):
+                assert set(a) == set(b)
+                for k in a:
+                    assert torch.allclose(a[k], b[k], rtol=2e-3, atol=1e-5), (mode, k, a[k], b[k])
+            assert torch.allclose(res[r]["eager"]["pl_mean"], res[r][mode]["pl_mean"], rtol=2e-3)
+            for a, b in zip(res[r]["eager"]["params"], res[r][mode]["params"]):
+                assert rel_err(b, a) < 2e-3
+            for a, b in zip(res[r][mode]["params"], res[0][mode]["params"]):
+                assert torch.equal(a, b)

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--top", type=int, default=60)
     ap.add_argument("--aten-only", action="store_true")
+    ap.add_argument("--kernels", action="store_true", help="also print the device time per kernel name")
     ap.add_argument("--lazy", action="store_true", help="profile a lazy (R1 + path length) iteration instead")
     args = ap.parse_args()
     from multi_stylegan_b200 import _lib, config
@@ -67,6 +68,17 @@ def main():
         rows[key][0] += t
         rows[key][1] += ev.count
     print("device time in the profiled iteration: %.2f ms" % (total / 1e3))
+    if args.kernels:
+        from torch.autograd import DeviceType
+        kern = collections.defaultdict(lambda: [0.0, 0])
+        for ev in prof.events():
+            if ev.device_type == DeviceType.CUDA:
+                kern[ev.name[:110]][0] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+                kern[ev.name[:110]][1] += 1
+        ktotal = sum(v[0] for v in kern.values())
+        print("\n== device time per kernel (%.2f ms) ==" % (ktotal / 1e3))
+        for name, (t, n) in sorted(kern.items(), key=lambda kv: -kv[1][0])[:args.top]:
+            print("%8.3f ms %5.1f%% %5d  %s" % (t / 1e3, 100 * t / ktotal, n, name))
     by_site = collections.defaultdict(float)
     for (name, site), (t, n) in rows.items():
         if name.startswith("aten::"):
