@@ -456,6 +456,8 @@ class ModelWrapper(object):
                 tk.starting_iteration, tk.final_iteration = 0, 1
         history = []
         for self.epoch in range(epochs):
+            if hasattr(self.training_dataset, "set_epoch"):      # dataset.DeviceLoader: a new shared permutation per epoch
+                self.training_dataset.set_epoch(self.epoch)
             self.generator.train()
             self.discriminator.train()
             history.extend(self._gan_training(resume_training=resume_training, top_k=tk))

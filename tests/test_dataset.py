@@ -146,3 +146,51 @@ def test_device_loader_uploads_on_the_copy_stream(tree):
     assert len(got) == len(want) == 10
     for g, w in zip(got, want):
         assert float(g.cpu()) == float(w)
+
+
+class _Sequences(torch.utils.data.Dataset):
+    """In-memory stand-in with the tiny networks' sample shape."""
+
+    def __init__(self, n):
+        gen = torch.Generator().manual_seed(4)
+        self.data = torch.rand(n, 2, 3, 32, 32, generator=gen)
+        self.reads = []
+
+    def __len__(self):
+        return self.data.shape[0]
+
+    def __getitem__(self, i):
+        self.reads.append(i)
+        return self.data[i]
+
+
+def _train_over_loader(dev):
+    """ModelWrapper.train (model_wrapper.py:104-145, 245-257) fed by the device loader: every epoch walks a new
+    permutation, the last partial batch is dropped, one history entry per iteration."""
+    from multi_stylegan_b200.dataset import DeviceLoader
+    from multi_stylegan_b200.model_wrapper import ModelWrapper
+    from tests.test_train_step import _hp, build
+    G, D = build(dev)
+    hp = _hp()
+    opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"])
+    opt_d = torch.optim.Adam(D.parameters(), lr=6e-3, betas=hp["betas"])
+    ds = _Sequences(7)
+    loader = DeviceLoader(ds, batch_size=2, device=dev, workers=2, depth=2, seed=3)
+    before = [p.detach().clone() for p in G.parameters()]
+    mw = ModelWrapper(G, D, opt_g, opt_d, training_dataset=loader, hyperparameters=hp, device=dev)
+    history = mw.train(epochs=2)
+    assert len(history) == 2 * 3 and mw.iteration == 6
+    assert all(torch.isfinite(v).all() for h in history for v in h.values())
+    assert "loss_path_length_regularization" in history[1] and "loss_discriminator_regularization" in history[1]
+    first, second = ds.reads[:len(ds.reads) // 2], ds.reads[len(ds.reads) // 2:]
+    assert len(first) == len(second) == 6 and len(set(first)) == 6 and first != second
+    assert any(not torch.equal(a, b) for a, b in zip(before, G.parameters()))
+
+
+def test_training_loop_over_the_device_loader_host_logic(oracle_backend):
+    _train_over_loader("cpu")
+
+
+@pytest.mark.gpu
+def test_training_loop_over_the_device_loader(built_library):
+    _train_over_loader(torch.device("cuda:0"))
