@@ -165,7 +165,7 @@ class ModelWrapper(object):
         (NCCL >= 2.9); the iteration then stays ONE graph — the all-reduce runs on NCCL's stream between a captured fork and
         join — instead of 2-4 segments with the collectives issued eagerly in between.  Parity of the two forms:
         tests/test_dist_gpu.py (2 GPUs, small networks).  Not the default: at the benchmark's size (203 / 212 MB buffers)
-        a 2-GPU run of the one-graph form did not finish, so the segments stay the product path."""
+        2-GPU runs of the one-graph form did not finish, so the segments stay the product path."""
         if self._always_break or os.environ.get("MSG_B200_NCCL_IN_GRAPH", "0") != "1":
             return False
         return (mdist.world_size(self.process_group) > 1
