@@ -511,6 +511,25 @@ def run_ours(args):
                 if graphs else "the timed region",
                 "all_tcgen05_conv_kernels": {"ms": conv_ms, "share_of_step": conv_ms / ms_prof,
                                              "tflops": conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else None}}
+        # the same launches split by roofline regime: algorithmic bytes of a launch = its two activation-sized tensors at
+        # the GEMM's pixel count, 4 * pixels * (K + N) (filters are negligible, halo / tap re-reads come out of L2); a shape
+        # whose flops / byte is below the machine balance cannot reach the tensor peak whatever the kernel does
+        balance = tf32_peak * 1e12 / (hbm * 1e9)
+        regimes = {"tensor_bound": [0.0, 0.0, 0.0], "hbm_bound": [0.0, 0.0, 0.0]}
+        for e in prof:
+            nbytes = 4.0 * e["pixels"] * (e["k_channels"] + e["n_channels"])
+            r = regimes["tensor_bound" if e["flops_per_launch"] / nbytes >= balance else "hbm_bound"]
+            r[0] += e["ms_total"]
+            r[1] += e["flops_per_launch"] * e["launches"]
+            r[2] += nbytes * e["launches"]
+        roof["all_tcgen05_conv_kernels"]["by_regime"] = {
+            "machine_balance_flop_per_byte": balance,
+            "tensor_bound": {"ms": regimes["tensor_bound"][0], "share_of_step": regimes["tensor_bound"][0] / ms_prof,
+                             "tflops": regimes["tensor_bound"][1] / (regimes["tensor_bound"][0] * 1e-3) / 1e12
+                             if regimes["tensor_bound"][0] else None},
+            "hbm_bound": {"ms": regimes["hbm_bound"][0], "share_of_step": regimes["hbm_bound"][0] / ms_prof,
+                          "gbps": regimes["hbm_bound"][2] / (regimes["hbm_bound"][0] * 1e-3) / 1e9
+                          if regimes["hbm_bound"][0] else None, "hbm_peak_gbps": hbm}}
     # secondary roofline (north star: upfirdn2d against HBM): the generator's 256^2 blur, CUDA events, inputs rotate over
     # 3 x 1 GiB (> L2); algorithmic bytes = 4 * (N_in + N_out)
     roof_hbm = None
