@@ -2083,6 +2083,8 @@ int tc_pixgemm(const PixGemm& g, void* ws, size_t ws_bytes, cudaStream_t st) {
     rows_ok = (step == 1 || step == -1) && g.tap_dy[t] == g.tap_dy[t0] && g.tap_dx[t] == g.tap_dx[t0] + step * (t % 3);
   }
   int MT = (pairs || g.ksplit > 1) ? 1 : pick_mt(g, BN);
+  // experiment knob (MSG_B200_TC_VARIANT bit 16384): single-tap GEMMs (1x1 layers, up-convolution phases) on 128-pixel tiles
+  if ((tc_variant() & 16384u) && g.ntaps == 1) MT = 1;
   int64_t pair_tiles_used = pair_tiles;
   bool pairs_rows = false;
   if (pairs && rows_ok && BN == 256 && !(tc_variant() & (4096u | 8192u))) {

@@ -74,6 +74,11 @@ def main():
         ("D conv 3x3 768->768 @32", 8, 768, 768, 32, 3, False, 1, None),
         ("D conv 1x1 256->128 @256", 8, 256, 128, 256, 1, False, 1, 0),
         ("D conv 3x3 s2 128->128 @256", 8, 128, 128, 256, 3, False, 2, 0),
+        ("HBM-bound 1x1 256->128 @256 B=16", 16, 256, 128, 256, 1, False, 1, 0),
+        ("HBM-bound 1x1 128->128 @256 B=16", 16, 128, 128, 256, 1, False, 1, 0),
+        ("HBM-bound 1x1 128->256 @128 B=16", 16, 128, 256, 128, 1, False, 1, 0),
+        ("HBM-bound 1x1 512->512 @128", 8, 512, 512, 128, 1, False, 1, 0),
+        ("HBM-bound 1x1 384->256 @128 B=16", 16, 384, 256, 128, 1, False, 1, 0),
         ("D first conv 3x3 6->128 @256 B=16", 16, 6, 128, 256, 3, False, 1, None),
         ("D first conv 1x1 6->128 @256 B=16", 16, 6, 128, 256, 1, False, 1, 0),
     ]
@@ -86,6 +91,9 @@ def main():
         flops, t = conv_case(B, C, O, R, k, per, s, p)
         tf = {kk: flops / (v * 1e-3) / 1e12 for kk, v in t.items()}
         print("%-32s %9.3f %9.3f %9.3f   %6.0f / %6.0f / %6.0f" % (name, t["fwd"], t["dgrad"], t["wgrad"], tf["fwd"], tf["dgrad"], tf["wgrad"]))
+        if name.startswith("HBM-bound"):
+            nbytes = 4.0 * B * R * R * (C + O)          # algorithmic bytes: the two activation-sized tensors
+            print("%-32s %9s %9s %9s   %6.0f / %6.0f / %6.0f GB/s" % ("", "", "", "", *(nbytes / (t[kk] * 1e-3) / 1e9 for kk in ("fwd", "dgrad", "wgrad"))))
         rows.append(dict(kind="conv", name=name, flops=flops, ms=t, tflops=tf))
         torch.cuda.empty_cache()
 
