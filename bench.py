@@ -529,7 +529,9 @@ def run_ours(args):
                              if regimes["tensor_bound"][0] else None},
             "hbm_bound": {"ms": regimes["hbm_bound"][0], "share_of_step": regimes["hbm_bound"][0] / ms_prof,
                           "gbps": regimes["hbm_bound"][2] / (regimes["hbm_bound"][0] * 1e-3) / 1e9
-                          if regimes["hbm_bound"][0] else None, "hbm_peak_gbps": hbm}}
+                          if regimes["hbm_bound"][0] else None, "hbm_peak_gbps": hbm,
+                          "note": "bytes = the GEMM's two activation tensors only; residual operands and second outputs of "
+                                  "the epilogues are not counted, so this is a lower bound on the bandwidth these launches run at"}}
     # secondary roofline (north star: upfirdn2d against HBM): the generator's 256^2 blur, CUDA events, inputs rotate over
     # 3 x 1 GiB (> L2); algorithmic bytes = 4 * (N_in + N_out)
     roof_hbm = None
