@@ -2,8 +2,9 @@
 oracle/__init__.py): an element-wise restatement of what the reference's scripts compose from a generated sequence,
 written with explicit loops / indexing so that it shares no tensor-op sequence with the product.
 
-Parity pinned by construction only: the reference's scripts have no tests or golden outputs, and they need a trained
-checkpoint that is not in the repository; the restatement follows the cited lines."""
+PARITY UNPINNED: the reference's scripts have no tests or golden outputs, cannot be imported (argparse at module level,
+`.cuda()`, a trained checkpoint that is not in the repository); the restatement follows the cited lines.  The generator they
+call IS pinned (oracle/model.py against tests/golden/generator.pt)."""
 from typing import List, Tuple
 
 import torch
