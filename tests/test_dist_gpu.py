@@ -146,7 +146,7 @@ def test_two_ranks_over_nccl_equal_one_gpu_with_per_group_statistics(built_libra
     assert "loss_path_length_regularization" in nccl[0]["losses"][-1]
 
 
-def _graph_worker(rank, world, port, tmp):
+def _graph_worker(rank, world, port, tmp, modes):
     """Per rank: the same six iterations (plain + lazy variants) issued eagerly, replayed as ONE graph per variant with the
     NCCL all-reduces captured inside it, and replayed as graph segments with the collectives issued eagerly in between."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
@@ -162,7 +162,7 @@ def _graph_worker(rank, world, port, tmp):
         hp = _hp()
         hp["p_mixed_noise"] = 0.6
         runs = {}
-        for mode in ("eager", "in_graph", "segments"):
+        for mode in ("eager",) + tuple(modes):
             os.environ["MSG_B200_NCCL_IN_GRAPH"] = "0" if mode == "segments" else "1"
             G, D = build(dev, seed=0)
             opt_g = torch.optim.Adam(G.get_parameters(lr_main=2e-3, lr_style=2e-5), betas=hp["betas"], fused=True, capturable=True)
@@ -188,21 +188,15 @@ def _graph_worker(rank, world, port, tmp):
         dist.destroy_process_group()
 
 
-@pytest.mark.timeout(900)
-def test_nccl_all_reduce_inside_the_cuda_graph_matches_eager_and_segments(built_library, tmp_path):
-    """Multi-rank CUDA-graph replay, both forms: graph segments with the NCCL all-reduces issued eagerly in between (the
-    default) and the opt-in form with the all-reduces as nodes of the iteration's ONE graph
-    (ModelWrapper._collectives_in_graph); same losses / parameters as eager issue, replicas identical across ranks."""
-    if torch.cuda.device_count() < WORLD:
-        pytest.skip("needs %d GPUs" % WORLD)
+def _graph_forms(tmp_path, modes):
     port = 35500 + (os.getpid() % 2000)
-    mp.spawn(_graph_worker, args=(WORLD, port, str(tmp_path)), nprocs=WORLD, join=True)
+    mp.spawn(_graph_worker, args=(WORLD, port, str(tmp_path), tuple(modes)), nprocs=WORLD, join=True)
     res = [torch.load(os.path.join(str(tmp_path), "graph%d.pt" % r), weights_only=False) for r in range(WORLD)]
+    want_graphs = {"in_graph": {(False, False): 1, (True, True): 1}, "segments": {(False, False): 4, (True, True): 5}}
     for r in range(WORLD):
-        assert res[r]["eager"]["replays"] == 0 and res[r]["in_graph"]["replays"] == 4 and res[r]["segments"]["replays"] == 4
-        assert res[r]["in_graph"]["n_graphs"] == {(False, False): 1, (True, True): 1}
-        assert res[r]["segments"]["n_graphs"] == {(False, False): 4, (True, True): 5}
-        for mode in ("in_graph", "segments"):
+        assert res[r]["eager"]["replays"] == 0
+        for mode in modes:
+            assert res[r][mode]["replays"] == 4 and res[r][mode]["n_graphs"] == want_graphs[mode]
             for a, b in zip(res[r]["eager"]["hist"], res[r][mode]["hist"]):
                 assert set(a) == set(b)
                 for k in a:
@@ -212,3 +206,25 @@ def test_nccl_all_reduce_inside_the_cuda_graph_matches_eager_and_segments(built_
                 assert rel_err(b, a) < 2e-3
             for a, b in zip(res[r][mode]["params"], res[0][mode]["params"]):
                 assert torch.equal(a, b)
+
+
+@pytest.mark.timeout(600)
+def test_multi_rank_cuda_graph_segments_match_eager_over_nccl(built_library, tmp_path):
+    """Multi-rank CUDA-graph replay, the default form: graph segments with the NCCL all-reduces issued eagerly in between;
+    same losses / parameters as eager issue, replicas identical across ranks."""
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs %d GPUs" % WORLD)
+    _graph_forms(tmp_path, ("segments",))
+
+
+@pytest.mark.timeout(600)
+def test_nccl_all_reduce_inside_the_cuda_graph_matches_eager(built_library, tmp_path):
+    """The opt-in form (MSG_B200_NCCL_IN_GRAPH=1): the all-reduces as nodes of the iteration's ONE graph
+    (ModelWrapper._collectives_in_graph).  Runs only when MSG_B200_TEST_NCCL_IN_GRAPH=1: the form passed here on 2 GPUs
+    (profiles/r2q_dist_gpu_tests.txt) but did not finish at the benchmark's size, and a hung collective
+    must not be able to take a test run with it."""
+    if torch.cuda.device_count() < WORLD:
+        pytest.skip("needs %d GPUs" % WORLD)
+    if os.environ.get("MSG_B200_TEST_NCCL_IN_GRAPH") != "1":
+        pytest.skip("opt-in: MSG_B200_TEST_NCCL_IN_GRAPH=1")
+    _graph_forms(tmp_path, ("in_graph",))
